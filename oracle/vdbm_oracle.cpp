@@ -1,0 +1,1020 @@
+// vdbm_oracle.cpp — CPU ORACLE for the scan-integration hot path of vdb_mapping.
+//
+// *** TEST INFRASTRUCTURE ONLY. *** Nothing under vdb_mapping_b200/ (the product) may include,
+// link, import or execute this file. Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs use it, as the checker and as the timed CPU baseline.
+//
+// What it is: an OpenVDB-free restatement of the reference algorithm
+//   /root/reference/include/vdb_mapping/VDBMapping.hpp          (cited below as V:<line>)
+//   /root/reference/include/vdb_mapping/OccupancyVDBMapping.hpp  (cited below as O:<line>)
+// The arithmetic the reference delegates to OpenVDB (un-vendored dependency, unpinned,
+// README.md:10-13 says ">= 8.3, recommended v9.0.0") is restated from OpenVDB's published
+// algorithm: math/DDA.h (DDA<RayT,0>::init/step), math/Math.h (MinIndex), math/Ray.h,
+// math/Maps.h (ScaleMap::applyInverseMap), math/Coord.h (Coord::floor), math/Vec3.h
+// (length/unit), tree/LeafNode.h + LeafNodeBool.h (offset/mask layout), tree/InternalNode.h +
+// tree/RootNode.h (modifyValueAndActiveStateAndCache incl. the inverted-state tile probe),
+// tree/ValueAccessor.h (3-level node cache), tree/TreeIterator.h (value-on order).
+//
+// Parity pinning: PINNED on the five known-answer tests of /root/reference/tests/mapping.cpp
+// (tests/test_oracle_kat.py, tests/golden/mapping_kats.json). Everything those tests do not
+// cover (diagonal tie-breaking, multi-ray dedup, change grid, sections) is "PARITY UNPINNED at
+// the OpenVDB boundary": the reference itself cannot be compiled in this image (no OpenVDB /
+// PCL / Eigen headers, no network), so oracle/_ref cannot be built. See DESIGN.md section 3.
+//
+// Storage mirrors OpenVDB's cost model on purpose (so that it doubles as the timed CPU
+// baseline): map = Root(std::map) -> Internal<5> -> Internal<4> -> Leaf<3> (float),
+// update grid = Root -> Internal<1> -> Internal<4> -> Leaf<3> (bool), both accessed through a
+// ValueAccessor3-style cache of the last leaf / internal nodes.
+//
+// Build: see oracle/Makefile (-O3 -DNDEBUG -ffp-contract=off, no -march=native: the x86-64
+// baseline has no FMA, which is what a distro/ROS Release build of the reference executes).
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace vo {
+
+// --------------------------------------------------------------------------------------------
+// Coord (openvdb::math::Coord): 3 x int32, lexicographic x,y,z ordering (RootNode key order).
+// --------------------------------------------------------------------------------------------
+struct Coord
+{
+  int32_t v[3];
+  Coord() : v{0, 0, 0} {}
+  Coord(int32_t x, int32_t y, int32_t z) : v{x, y, z} {}
+  int32_t operator[](int i) const { return v[i]; }
+  int32_t& operator[](int i) { return v[i]; }
+  bool operator==(const Coord& o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2]; }
+  bool operator!=(const Coord& o) const { return !(*this == o); }
+  bool operator<(const Coord& o) const
+  {
+    if (v[0] != o.v[0]) return v[0] < o.v[0];
+    if (v[1] != o.v[1]) return v[1] < o.v[1];
+    return v[2] < o.v[2];
+  }
+  Coord masked(int32_t m) const { return Coord(v[0] & m, v[1] & m, v[2] & m); }
+};
+
+// --------------------------------------------------------------------------------------------
+// NodeMask<Log2Dim> (openvdb::util::NodeMask): SIZE bits in 64-bit words, word n>>6, bit n&63.
+// --------------------------------------------------------------------------------------------
+template <int LOG2DIM>
+struct NodeMask
+{
+  static constexpr uint32_t SIZE  = 1u << (3 * LOG2DIM);
+  static constexpr uint32_t WORDS = SIZE >= 64 ? SIZE / 64 : 1;
+  uint64_t w[WORDS];
+  NodeMask() { std::memset(w, 0, sizeof(w)); }
+  bool isOn(uint32_t n) const { return (w[n >> 6] >> (n & 63)) & 1u; }
+  void setOn(uint32_t n) { w[n >> 6] |= uint64_t(1) << (n & 63); }
+  void setOff(uint32_t n) { w[n >> 6] &= ~(uint64_t(1) << (n & 63)); }
+  void set(uint32_t n, bool on) { on ? setOn(n) : setOff(n); }
+  bool isOff() const
+  {
+    for (uint32_t i = 0; i < WORDS; ++i)
+      if (w[i]) return false;
+    return true;
+  }
+  // first set bit at position >= start, or SIZE
+  uint32_t findNextOn(uint32_t start) const
+  {
+    if (start >= SIZE) return SIZE;
+    uint32_t wi = start >> 6;
+    uint64_t b  = w[wi] & (~uint64_t(0) << (start & 63));
+    while (true)
+    {
+      if (b) return (wi << 6) + uint32_t(__builtin_ctzll(b));
+      if (++wi >= WORDS) return SIZE;
+      b = w[wi];
+    }
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+// Leaf nodes. Offset n = ((x&7)<<6)|((y&7)<<3)|(z&7)  (LeafNode::coordToOffset).
+// --------------------------------------------------------------------------------------------
+inline uint32_t leafOffset(const Coord& c)
+{
+  return (uint32_t(c[0] & 7) << 6) | (uint32_t(c[1] & 7) << 3) | uint32_t(c[2] & 7);
+}
+inline Coord leafOffsetToLocal(uint32_t n) { return Coord(int32_t(n >> 6), int32_t((n >> 3) & 7), int32_t(n & 7)); }
+
+struct FloatLeaf
+{
+  static constexpr int TOTAL = 3;
+  using ValueT               = float;
+  Coord origin;
+  NodeMask<3> vmask;
+  float buf[512];
+  FloatLeaf(const Coord& xyz, float bg, bool active) : origin(xyz.masked(~7))
+  {
+    for (int i = 0; i < 512; ++i) buf[i] = bg;
+    if (active)
+      for (auto& x : vmask.w) x = ~uint64_t(0);
+  }
+};
+
+struct BoolLeaf
+{
+  static constexpr int TOTAL = 3;
+  using ValueT               = bool;
+  Coord origin;
+  NodeMask<3> vmask; // active states
+  NodeMask<3> buf;   // bool values (LeafNode<bool,3> stores values as a second bit mask)
+  BoolLeaf(const Coord& xyz, bool bg, bool active) : origin(xyz.masked(~7))
+  {
+    if (bg)
+      for (auto& x : buf.w) x = ~uint64_t(0);
+    if (active)
+      for (auto& x : vmask.w) x = ~uint64_t(0);
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+// InternalNode<Child, Log2Dim> (openvdb::tree::InternalNode): child mask + value mask + a
+// union table of child pointers / tile values.
+// --------------------------------------------------------------------------------------------
+template <typename ChildT, int LOG2DIM>
+struct Internal
+{
+  using ValueT                    = typename ChildT::ValueT;
+  using Child                     = ChildT;
+  static constexpr int TOTAL      = LOG2DIM + ChildT::TOTAL;
+  static constexpr uint32_t NUM   = 1u << (3 * LOG2DIM);
+  static constexpr int32_t DIMM1  = (int32_t(1) << TOTAL) - 1;
+  union Slot
+  {
+    ChildT* child;
+    ValueT tile;
+  };
+  Coord origin;
+  NodeMask<LOG2DIM> childMask;
+  NodeMask<LOG2DIM> valueMask;
+  Slot nodes[NUM];
+
+  Internal(const Coord& xyz, ValueT bg, bool active) : origin(xyz.masked(~DIMM1))
+  {
+    for (uint32_t i = 0; i < NUM; ++i) nodes[i].tile = bg;
+    if (active)
+      for (auto& x : valueMask.w) x = ~uint64_t(0);
+  }
+  ~Internal()
+  {
+    for (uint32_t n = childMask.findNextOn(0); n < NUM; n = childMask.findNextOn(n + 1)) delete nodes[n].child;
+  }
+  Internal(const Internal&)            = delete;
+  Internal& operator=(const Internal&) = delete;
+
+  static uint32_t coordToOffset(const Coord& c)
+  {
+    return (uint32_t((c[0] & DIMM1) >> ChildT::TOTAL) << (2 * LOG2DIM)) |
+           (uint32_t((c[1] & DIMM1) >> ChildT::TOTAL) << LOG2DIM) | uint32_t((c[2] & DIMM1) >> ChildT::TOTAL);
+  }
+};
+
+using FloatI1 = Internal<FloatLeaf, 4>;  // 16^3 leaves  (128^3 voxels)
+using FloatI2 = Internal<FloatI1, 5>;    // 32^3 of those (4096^3 voxels)  -> Tree4<float,5,4,3>, V:88
+using BoolI1  = Internal<BoolLeaf, 4>;   // 16^3 leaves
+using BoolI2  = Internal<BoolI1, 1>;     // 2^3 of those (256^3 voxels)    -> Tree4<bool,1,4,3>, V:89
+
+// --------------------------------------------------------------------------------------------
+// Tree = RootNode(std::map keyed by child origin) + background.
+// --------------------------------------------------------------------------------------------
+template <typename I2T>
+struct Tree
+{
+  using I2    = I2T;
+  using I1    = typename I2T::Child;
+  using Leaf  = typename I1::Child;
+  using Value = typename Leaf::ValueT;
+  std::map<Coord, I2*> table; // RootNode::mTable: only children on this path (no root tiles)
+  Value background;
+  explicit Tree(Value bg) : background(bg) {}
+  ~Tree() { clear(); }
+  Tree(const Tree&)            = delete;
+  Tree& operator=(const Tree&) = delete;
+  void clear()
+  {
+    for (auto& kv : table) delete kv.second;
+    table.clear();
+  }
+  bool empty() const { return table.empty(); }
+  static Coord rootKey(const Coord& c) { return c.masked(~I2::DIMM1); }
+
+  template <typename F>
+  void forEachLeaf(F&& f) const // cbeginLeaf order: root key order, then offset order per level
+  {
+    for (auto& kv : table)
+    {
+      const I2* n2 = kv.second;
+      for (uint32_t a = n2->childMask.findNextOn(0); a < I2::NUM; a = n2->childMask.findNextOn(a + 1))
+      {
+        const I1* n1 = n2->nodes[a].child;
+        for (uint32_t b = n1->childMask.findNextOn(0); b < I1::NUM; b = n1->childMask.findNextOn(b + 1))
+          f(*n1->nodes[b].child);
+      }
+    }
+  }
+  size_t leafCount() const
+  {
+    size_t n = 0;
+    forEachLeaf([&](const Leaf&) { ++n; });
+    return n;
+  }
+};
+
+using FloatTree = Tree<FloatI2>;
+using BoolTree  = Tree<BoolI2>;
+
+// --------------------------------------------------------------------------------------------
+// ValueAccessor3-style accessor: caches the last leaf, I1 and I2 node (keys = node origins).
+// --------------------------------------------------------------------------------------------
+template <typename TreeT>
+struct Accessor
+{
+  using I2   = typename TreeT::I2;
+  using I1   = typename TreeT::I1;
+  using Leaf = typename TreeT::Leaf;
+  using V    = typename TreeT::Value;
+  TreeT* tree;
+  Coord k0, k1, k2;
+  Leaf* n0 = nullptr;
+  I1* n1   = nullptr;
+  I2* n2   = nullptr;
+  explicit Accessor(TreeT& t) : tree(&t) {}
+
+  bool hashed0(const Coord& c) const { return n0 && (c[0] & ~7) == k0[0] && (c[1] & ~7) == k0[1] && (c[2] & ~7) == k0[2]; }
+  bool hashed1(const Coord& c) const
+  {
+    return n1 && (c[0] & ~I1::DIMM1) == k1[0] && (c[1] & ~I1::DIMM1) == k1[1] && (c[2] & ~I1::DIMM1) == k1[2];
+  }
+  bool hashed2(const Coord& c) const
+  {
+    return n2 && (c[0] & ~I2::DIMM1) == k2[0] && (c[1] & ~I2::DIMM1) == k2[1] && (c[2] & ~I2::DIMM1) == k2[2];
+  }
+  void insert(const Coord& c, Leaf* l) { n0 = l; k0 = c.masked(~7); }
+  void insert(const Coord& c, I1* n) { n1 = n; k1 = c.masked(~I1::DIMM1); }
+  void insert(const Coord& c, I2* n) { n2 = n; k2 = c.masked(~I2::DIMM1); }
+
+  // ---- read path (probe without allocation) ----
+  const Leaf* probeLeaf(const Coord& c)
+  {
+    if (hashed0(c)) return n0;
+    I1* a = nullptr;
+    if (hashed1(c)) a = n1;
+    else
+    {
+      I2* b = nullptr;
+      if (hashed2(c)) b = n2;
+      else
+      {
+        auto it = tree->table.find(TreeT::rootKey(c));
+        if (it == tree->table.end()) return nullptr;
+        b = it->second;
+        insert(c, b);
+      }
+      uint32_t n = I2::coordToOffset(c);
+      if (!b->childMask.isOn(n)) return nullptr;
+      a = b->nodes[n].child;
+      insert(c, a);
+    }
+    uint32_t n = I1::coordToOffset(c);
+    if (!a->childMask.isOn(n)) return nullptr;
+    Leaf* l = a->nodes[n].child;
+    insert(c, l);
+    return l;
+  }
+
+  // ---- touch path used by setActiveState(true)/setValueOn on the bool tree: tiles are always
+  //      (background, inactive) here, and the requested state is "on", so a child is always
+  //      created (InternalNode::setActiveStateAndCache / setValueAndCache). ----
+  Leaf* touchLeaf(const Coord& c)
+  {
+    if (hashed0(c)) return n0;
+    I1* a = nullptr;
+    if (hashed1(c)) a = n1;
+    else
+    {
+      I2* b = nullptr;
+      if (hashed2(c)) b = n2;
+      else
+      {
+        Coord key = TreeT::rootKey(c);
+        auto it   = tree->table.find(key);
+        if (it == tree->table.end())
+        {
+          b = new I2(c, tree->background, false);
+          tree->table[key] = b;
+        }
+        else b = it->second;
+        insert(c, b);
+      }
+      uint32_t n = I2::coordToOffset(c);
+      if (!b->childMask.isOn(n))
+      {
+        V tile = b->nodes[n].tile;
+        bool on = b->valueMask.isOn(n);
+        b->nodes[n].child = new I1(c, tile, on);
+        b->childMask.setOn(n);
+        b->valueMask.setOff(n);
+      }
+      a = b->nodes[n].child;
+      insert(c, a);
+    }
+    uint32_t n = I1::coordToOffset(c);
+    if (!a->childMask.isOn(n))
+    {
+      V tile = a->nodes[n].tile;
+      bool on = a->valueMask.isOn(n);
+      a->nodes[n].child = new Leaf(c, tile, on);
+      a->childMask.setOn(n);
+      a->valueMask.setOff(n);
+    }
+    Leaf* l = a->nodes[n].child;
+    insert(c, l);
+    return l;
+  }
+};
+
+// bool-tree write ops used by the raycast (V:535, V:563)
+inline void setActiveStateOn(Accessor<BoolTree>& acc, const Coord& c) { acc.touchLeaf(c)->vmask.setOn(leafOffset(c)); }
+inline void setValueOnTrue(Accessor<BoolTree>& acc, const Coord& c)
+{
+  BoolLeaf* l = acc.touchLeaf(c);
+  uint32_t n  = leafOffset(c);
+  l->buf.setOn(n);
+  l->vmask.setOn(n);
+}
+
+// --------------------------------------------------------------------------------------------
+// modifyValueAndActiveState on the float tree, with OpenVDB's tile probe:
+//  InternalNode::modifyValueAndActiveStateAndCache: if the slot is a tile, the op is first run
+//  on copies (tileValue, !tileState); a child is created iff the result differs from the tile;
+//  then the op runs for real in the child. RootNode creates a missing child without a probe.
+// --------------------------------------------------------------------------------------------
+template <typename Op>
+inline void modifyInLeaf(FloatLeaf* l, const Coord& c, Op& op)
+{
+  uint32_t n = leafOffset(c);
+  bool state = l->vmask.isOn(n);
+  op(l->buf[n], state);
+  l->vmask.set(n, state);
+}
+
+template <typename Op>
+inline void modifyInI1(Accessor<FloatTree>& acc, FloatI1* a, const Coord& c, Op& op)
+{
+  uint32_t n    = FloatI1::coordToOffset(c);
+  bool hasChild = a->childMask.isOn(n);
+  if (!hasChild)
+  {
+    const bool tileState = a->valueMask.isOn(n);
+    const float tileVal  = a->nodes[n].tile;
+    bool modifiedState   = !tileState;
+    float modifiedVal    = tileVal;
+    op(modifiedVal, modifiedState);
+    if (modifiedState != tileState || !(modifiedVal == tileVal))
+    {
+      hasChild          = true;
+      a->nodes[n].child = new FloatLeaf(c, tileVal, tileState);
+      a->childMask.setOn(n);
+      a->valueMask.setOff(n);
+    }
+  }
+  if (hasChild)
+  {
+    FloatLeaf* l = a->nodes[n].child;
+    acc.insert(c, l);
+    modifyInLeaf(l, c, op);
+  }
+}
+
+template <typename Op>
+inline void modifyInI2(Accessor<FloatTree>& acc, FloatI2* b, const Coord& c, Op& op)
+{
+  uint32_t n    = FloatI2::coordToOffset(c);
+  bool hasChild = b->childMask.isOn(n);
+  if (!hasChild)
+  {
+    const bool tileState = b->valueMask.isOn(n);
+    const float tileVal  = b->nodes[n].tile;
+    bool modifiedState   = !tileState;
+    float modifiedVal    = tileVal;
+    op(modifiedVal, modifiedState);
+    if (modifiedState != tileState || !(modifiedVal == tileVal))
+    {
+      hasChild          = true;
+      b->nodes[n].child = new FloatI1(c, tileVal, tileState);
+      b->childMask.setOn(n);
+      b->valueMask.setOff(n);
+    }
+  }
+  if (hasChild)
+  {
+    FloatI1* a = b->nodes[n].child;
+    acc.insert(c, a);
+    modifyInI1(acc, a, c, op);
+  }
+}
+
+template <typename Op>
+inline void modifyValueAndActiveState(Accessor<FloatTree>& acc, const Coord& c, Op& op)
+{
+  if (acc.hashed0(c)) { modifyInLeaf(acc.n0, c, op); return; }
+  if (acc.hashed1(c)) { modifyInI1(acc, acc.n1, c, op); return; }
+  if (acc.hashed2(c)) { modifyInI2(acc, acc.n2, c, op); return; }
+  FloatTree* t = acc.tree;
+  Coord key    = FloatTree::rootKey(c);
+  auto it      = t->table.find(key);
+  FloatI2* b;
+  if (it == t->table.end())
+  {
+    b             = new FloatI2(c, t->background, false);
+    t->table[key] = b;
+  }
+  else b = it->second;
+  acc.insert(c, b);
+  modifyInI2(acc, b, c, op);
+}
+
+// --------------------------------------------------------------------------------------------
+// The mapping classes (restated reference logic).
+// --------------------------------------------------------------------------------------------
+struct Stats
+{
+  uint64_t rays        = 0; // points seen by raycastPointCloud (incl. NaN + clipped)
+  uint64_t nan_skipped = 0;
+  uint64_t clipped     = 0;
+  uint64_t visits      = 0; // setActiveState calls made by castRayIntoGrid
+  uint64_t voxel_updates = 0; // active update voxels consumed by updateMap
+  uint64_t state_changes = 0; // voxels written to the change grid
+};
+
+struct Source
+{
+  std::string id;
+  double max_range;
+  std::unique_ptr<BoolTree> update_grid;
+  std::unique_ptr<BoolTree> last_change; // what updateMap returned for this source last time
+};
+
+// VDBMapping<float,Config> + OccupancyVDBMapping node ops, polymorphic like the reference
+// (virtual updateFreeNode/updateOccupiedNode, V:1472-1473) so the per-voxel cost model matches.
+struct MappingBase
+{
+  double m_resolution;
+  double m_inv_resolution; // ScaleMap::mScaleValuesInverse = 1.0 / scale
+  double m_max_range = 0.0;
+  bool m_config_set  = false;
+  std::unique_ptr<FloatTree> m_vdb_grid;
+  std::map<std::string, std::unique_ptr<Source> > m_input_sources; // std::map order, V:1545
+  Stats stats;
+  bool replicate_probe_quirk = true; // SURVEY F9; false = report only real flag flips
+
+  explicit MappingBase(double resolution) : m_resolution(resolution), m_inv_resolution(1.0 / resolution)
+  {
+    m_vdb_grid.reset(new FloatTree(0.0f)); // createVDBMap V:163-169, background TData()
+  }
+  virtual ~MappingBase() {}
+  virtual bool updateFreeNode(float&, bool&) { return false; }
+  virtual bool updateOccupiedNode(float&, bool&) { return false; }
+
+  // V:174-186
+  void resetMap()
+  {
+    m_vdb_grid.reset(new FloatTree(0.0f));
+    for (auto& kv : m_input_sources) kv.second->update_grid.reset(new BoolTree(false));
+  }
+
+  // V:1352-1375 (threads not restated: the oracle is driven synchronously)
+  void addInputSource(const std::string& id, double max_range)
+  {
+    auto s       = std::make_unique<Source>();
+    s->id        = id;
+    s->max_range = (max_range == 0) ? m_max_range : max_range;
+    s->update_grid.reset(new BoolTree(false));
+    m_input_sources[id] = std::move(s);
+  }
+
+  // V:612-631; Transform::worldToIndex -> ScaleMap::applyInverseMap (multiply by 1/res);
+  // Coord::floor = Int32(std::floor(x)).
+  Coord worldToIndex(const double w[3]) const
+  {
+    Coord r;
+    for (int i = 0; i < 3; ++i)
+    {
+      double c = w[i];
+      if (std::fmod(c, m_resolution)) c = c + (m_resolution / 2.0);
+      r[i] = int32_t(std::floor(c * m_inv_resolution));
+    }
+    return r;
+  }
+
+  // V:550-566 + openvdb::math::Ray<double>(eye, dir, 0, 1) + DDA<RayT,0>(ray, 0)
+  void castRayIntoGrid(const Coord& o, const Coord& e, Accessor<BoolTree>& acc)
+  {
+    if (e == o) return; // V:559 (ray/dda construction has no side effect)
+    double dir[3], inv[3], pos[3], next[3], delta[3];
+    int32_t step[3];
+    Coord voxel;
+    for (int a = 0; a < 3; ++a)
+    {
+      dir[a] = double(e[a]) - double(o[a]);  // V:554 asVec3d() - Coord
+      pos[a] = double(o[a]) + 0.5;           // V:557 eye = origin + 0.5; ray(t0=0) = eye + dir*0
+      pos[a] = pos[a] + dir[a] * 0.0;
+      inv[a] = 1.0 / dir[a];                 // Ray::mInvDir = 1/mDir (true division; 1/0 = inf)
+      voxel[a] = int32_t(std::floor(pos[a])); // Coord::floor(pos) & ~(DIM-1), DIM = 1
+    }
+    for (int a = 0; a < 3; ++a)
+    {
+      if (dir[a] == 0.0) // math::isZero(dir[axis])
+      {
+        step[a]  = 0;
+        next[a]  = DBL_MAX;
+        delta[a] = DBL_MAX;
+      }
+      else if (inv[a] > 0)
+      {
+        step[a]  = 1;
+        next[a]  = 0.0 + (double(voxel[a] + 1) - pos[a]) * inv[a];
+        delta[a] = double(step[a]) * inv[a];
+      }
+      else
+      {
+        step[a]  = -1;
+        next[a]  = 0.0 + (double(voxel[a]) - pos[a]) * inv[a];
+        delta[a] = double(step[a]) * inv[a];
+      }
+    }
+    static const int kMinIndexTable[8] = {2, 1, 9, 1, 2, 9, 0, 0}; // math::MinIndex
+    bool more;
+    do
+    {
+      setActiveStateOn(acc, voxel); // V:563
+      ++stats.visits;
+      // DDA::step()
+      const int key  = (int(next[0] < next[1]) << 2) + (int(next[0] < next[2]) << 1) + int(next[1] < next[2]);
+      const int axis = kMinIndexTable[key];
+      const double t = next[axis];
+      next[axis] += delta[axis];
+      voxel[axis] += step[axis];
+      more = (t <= 1.0);
+    } while (more);
+  }
+
+  // V:466-539 (fast_mode is out of scope)
+  bool raycastPointCloud(const uint8_t* pts, size_t n, size_t stride, const double origin[3], double raycast_range,
+                         Accessor<BoolTree>& update_acc)
+  {
+    if (!m_config_set) return false; // V:478-482
+    const Coord ray_origin_index = worldToIndex(origin);
+    const bool origin_nan        = std::isnan(origin[0]) || std::isnan(origin[1]) || std::isnan(origin[2]);
+    for (size_t i = 0; i < n; ++i)
+    {
+      float p[3];
+      std::memcpy(p, pts + i * stride, sizeof(p));
+      double end[3]      = {double(p[0]), double(p[1]), double(p[2])}; // V:501
+      bool max_range_ray = false;
+      ++stats.rays;
+      if (std::isnan(end[0]) || std::isnan(end[1]) || std::isnan(end[2]) || origin_nan) // V:505-510
+      {
+        ++stats.nan_skipped;
+        continue;
+      }
+      if (raycast_range > 0.0)
+      {
+        // Vec3::length(): sqrt(x*x + y*y + z*z), left-associated
+        const double d[3] = {end[0] - origin[0], end[1] - origin[1], end[2] - origin[2]};
+        const double len  = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (len > raycast_range) // V:512
+        {
+          // origin + (d.unit() * range): unit() = d / len (true division), V:514-515
+          for (int a = 0; a < 3; ++a) end[a] = origin[a] + (d[a] / len) * raycast_range;
+          max_range_ray = true;
+          ++stats.clipped;
+        }
+      }
+      const Coord ray_end_index = worldToIndex(end); // V:519
+      castRayIntoGrid(ray_origin_index, ray_end_index, update_acc); // V:530
+      if (!max_range_ray) setValueOnTrue(update_acc, ray_end_index); // V:533-536
+    }
+    return true;
+  }
+
+  // V:316-346
+  int accumulateUpdate(const uint8_t* pts, size_t n, size_t stride, const double origin[3], const std::string& id)
+  {
+    auto it = m_input_sources.find(id);
+    if (it == m_input_sources.end()) return 1; // V:321-326: print + return
+    Source& s = *it->second;
+    Accessor<BoolTree> acc(*s.update_grid);
+    if (s.max_range > 0) // V:331
+    {
+      if (!raycastPointCloud(pts, n, stride, origin, s.max_range, acc)) return 2;
+    }
+    return 0;
+  }
+
+  // V:731-792 (artificial areas V:785-789: grid always empty here, out of scope)
+  std::unique_ptr<BoolTree> updateMap(const BoolTree& temp_grid)
+  {
+    auto change = std::make_unique<BoolTree>(false);
+    Accessor<BoolTree> change_acc(*change);
+    if (temp_grid.empty()) return change; // V:735-738
+
+    bool state_changed = false;
+    Accessor<FloatTree> acc(*m_vdb_grid);
+    const bool quirk = replicate_probe_quirk;
+    bool in_probe_guard = false; // used only when the quirk is switched off
+    (void)in_probe_guard;
+    auto miss = [&](float& voxel_value, bool& active) {
+      bool last_state = active;
+      updateFreeNode(voxel_value, active);
+      if (last_state != active) state_changed = true;
+    };
+    auto hit = [&](float& voxel_value, bool& active) {
+      bool last_state = active;
+      updateOccupiedNode(voxel_value, active);
+      if (last_state != active) state_changed = true;
+    };
+
+    // cbeginValueOn(): root key order, then child offset order per level, then leaf offset order
+    temp_grid.forEachLeaf([&](const BoolLeaf& ul) {
+      for (uint32_t n = ul.vmask.findNextOn(0); n < 512; n = ul.vmask.findNextOn(n + 1))
+      {
+        Coord l = leafOffsetToLocal(n);
+        Coord c(ul.origin[0] + l[0], ul.origin[1] + l[1], ul.origin[2] + l[2]);
+        ++stats.voxel_updates;
+        state_changed = false;
+        if (!quirk)
+        {
+          // "clean" semantics: report only a real flip of the stored voxel flag
+          const FloatLeaf* fl = acc.probeLeaf(c);
+          const bool before   = fl ? fl->vmask.isOn(n) : false;
+          if (ul.buf.isOn(n)) modifyValueAndActiveState(acc, c, hit);
+          else modifyValueAndActiveState(acc, c, miss);
+          const FloatLeaf* fl2 = acc.probeLeaf(c);
+          const bool after     = fl2 ? fl2->vmask.isOn(n) : false;
+          state_changed        = (before != after);
+        }
+        else
+        {
+          if (ul.buf.isOn(n)) modifyValueAndActiveState(acc, c, hit);
+          else modifyValueAndActiveState(acc, c, miss);
+        }
+        if (state_changed)
+        {
+          ++stats.state_changes;
+          if (ul.buf.isOn(n)) setValueOnTrue(change_acc, c);      // V:772
+          else setActiveStateOn(change_acc, c);                   // V:780
+        }
+      }
+    });
+    return change;
+  }
+
+  // V:375-387
+  void integrateUpdate()
+  {
+    for (auto& kv : m_input_sources)
+    {
+      Source& s     = *kv.second;
+      s.last_change = updateMap(*s.update_grid);
+      s.update_grid.reset(new BoolTree(false));
+    }
+  }
+};
+
+struct OccupancyMapping : MappingBase
+{
+  float m_logodds_hit = 0, m_logodds_miss = 0, m_logodds_thres_min = 0, m_logodds_thres_max = 0, m_max_logodds = 0,
+        m_min_logodds = 0;
+  explicit OccupancyMapping(double res) : MappingBase(res) {}
+
+  // base V:1456-1469 then O:59-89. Returns 0 ok, 1 base rejected, 2 derived rejected (the base
+  // has already flipped m_config_set by then, exactly like the reference).
+  int setConfig(double max_range, double prob_hit, double prob_miss, double prob_thres_min, double prob_thres_max)
+  {
+    if (max_range < 0.0) return 1;
+    m_max_range  = max_range;
+    m_config_set = true;
+    if (prob_miss > 0.5) return 2;
+    if (prob_hit < 0.5) return 2;
+    m_logodds_miss      = static_cast<float>(std::log(prob_miss) - std::log(1 - prob_miss));
+    m_logodds_hit       = static_cast<float>(std::log(prob_hit) - std::log(1 - prob_hit));
+    m_logodds_thres_min = static_cast<float>(std::log(prob_thres_min) - std::log(1 - prob_thres_min));
+    m_logodds_thres_max = static_cast<float>(std::log(prob_thres_max) - std::log(1 - prob_thres_max));
+    m_max_logodds       = static_cast<float>(std::log(0.99) - std::log(0.01));
+    m_min_logodds       = static_cast<float>(std::log(0.01) - std::log(0.99));
+    m_config_set        = true;
+    return 0;
+  }
+  // O:92-104
+  bool updateFreeNode(float& voxel_value, bool& active) override
+  {
+    voxel_value += m_logodds_miss;
+    if (voxel_value < m_logodds_thres_min)
+    {
+      active = false;
+      if (voxel_value < m_min_logodds) voxel_value = m_min_logodds;
+    }
+    return true;
+  }
+  // O:105-117
+  bool updateOccupiedNode(float& voxel_value, bool& active) override
+  {
+    voxel_value += m_logodds_hit;
+    if (voxel_value > m_logodds_thres_max)
+    {
+      active = true;
+      if (voxel_value > m_max_logodds) voxel_value = m_max_logodds;
+    }
+    return true;
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+// Canonical leaf-set export (leaves sorted by origin x,y,z == RootNode/offset order already,
+// because every level is visited in ascending x-major offset order... which is NOT globally
+// lexicographic across nodes, so sort explicitly).
+// --------------------------------------------------------------------------------------------
+struct LeafSet
+{
+  std::vector<int32_t> origins;  // 3 per leaf
+  std::vector<uint64_t> active;  // 8 per leaf
+  std::vector<uint64_t> valmask; // 8 per leaf (bool grids) or empty
+  std::vector<float> values;     // 512 per leaf (float grids) or empty
+  size_t size() const { return origins.size() / 3; }
+};
+
+template <typename T>
+static void permuteBlocks(std::vector<T>& v, const std::vector<size_t>& order, size_t block)
+{
+  if (v.empty()) return;
+  std::vector<T> out(v.size());
+  for (size_t i = 0; i < order.size(); ++i) std::memcpy(&out[i * block], &v[order[i] * block], block * sizeof(T));
+  v.swap(out);
+}
+
+static void sortLeafSet(LeafSet& s)
+{
+  size_t n = s.size();
+  std::vector<size_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+    return Coord(s.origins[3 * a], s.origins[3 * a + 1], s.origins[3 * a + 2]) <
+           Coord(s.origins[3 * b], s.origins[3 * b + 1], s.origins[3 * b + 2]);
+  });
+  permuteBlocks(s.origins, order, 3);
+  permuteBlocks(s.active, order, 8);
+  permuteBlocks(s.valmask, order, 8);
+  permuteBlocks(s.values, order, 512);
+}
+
+static LeafSet exportBool(const BoolTree& t)
+{
+  LeafSet s;
+  t.forEachLeaf([&](const BoolLeaf& l) {
+    for (int a = 0; a < 3; ++a) s.origins.push_back(l.origin[a]);
+    for (int w = 0; w < 8; ++w) s.active.push_back(l.vmask.w[w]);
+    for (int w = 0; w < 8; ++w) s.valmask.push_back(l.buf.w[w]);
+  });
+  sortLeafSet(s);
+  return s;
+}
+static LeafSet exportFloat(const FloatTree& t)
+{
+  LeafSet s;
+  t.forEachLeaf([&](const FloatLeaf& l) {
+    for (int a = 0; a < 3; ++a) s.origins.push_back(l.origin[a]);
+    for (int w = 0; w < 8; ++w) s.active.push_back(l.vmask.w[w]);
+    s.values.insert(s.values.end(), l.buf, l.buf + 512);
+  });
+  sortLeafSet(s);
+  return s;
+}
+
+// --------------------------------------------------------------------------------------------
+// getMapSection V:921-960 with extractSparseLeaf V:999-1011 / extractFullLeaf V:970-989 on an
+// inclusive index bounding box (createIndexBoundingBox V:857-871 stays with the caller: it is
+// host-side PCL/Eigen maths on 8 corners).
+//   result_float = false -> TResultGrid = UpdateGridT (bool, background false)
+//   result_float = true  -> TResultGrid = GridT       (float, background 0)
+// setValueOff(coord, v) on an (inactive, background) tile only creates nodes if v != background
+// (InternalNode::setValueOffAndCache), which is why "existence" is content-driven below.
+// --------------------------------------------------------------------------------------------
+static inline bool insideBox(const Coord& c, const Coord& mn, const Coord& mx)
+{
+  return c[0] >= mn[0] && c[0] <= mx[0] && c[1] >= mn[1] && c[1] <= mx[1] && c[2] >= mn[2] && c[2] <= mx[2];
+}
+
+static LeafSet mapSection(const FloatTree& map, const Coord& mn, const Coord& mx, bool full, bool result_float)
+{
+  LeafSet s;
+  map.forEachLeaf([&](const FloatLeaf& l) {
+    // leaf bbox = [origin, origin+7]; CoordBBox::hasOverlap
+    for (int a = 0; a < 3; ++a)
+      if (l.origin[a] + 7 < mn[a] || l.origin[a] > mx[a]) return;
+    uint64_t act[8] = {0}, vm[8] = {0};
+    float vals[512];
+    for (int i = 0; i < 512; ++i) vals[i] = 0.0f;
+    bool exists = false;
+    for (uint32_t n = 0; n < 512; ++n)
+    {
+      Coord loc = leafOffsetToLocal(n);
+      Coord c(l.origin[0] + loc[0], l.origin[1] + loc[1], l.origin[2] + loc[2]);
+      if (!insideBox(c, mn, mx)) continue;
+      const bool on = l.vmask.isOn(n);
+      if (!full)
+      {
+        if (!on) continue;
+        act[n >> 6] |= uint64_t(1) << (n & 63); // setValueOn(coord, true)
+        vm[n >> 6] |= uint64_t(1) << (n & 63);
+        vals[n] = 1.0f;
+        exists  = true;
+      }
+      else
+      {
+        const float v = l.buf[n];
+        if (on)
+        {
+          act[n >> 6] |= uint64_t(1) << (n & 63);
+          exists = true;
+        }
+        if (result_float)
+        {
+          vals[n] = v;
+          if (v != 0.0f) exists = true;
+        }
+        else if (v != 0.0f) // float -> bool
+        {
+          vm[n >> 6] |= uint64_t(1) << (n & 63);
+          exists = true;
+        }
+      }
+    }
+    if (!exists) return;
+    for (int a = 0; a < 3; ++a) s.origins.push_back(l.origin[a]);
+    for (int w = 0; w < 8; ++w) s.active.push_back(act[w]);
+    if (result_float) s.values.insert(s.values.end(), vals, vals + 512);
+    else
+      for (int w = 0; w < 8; ++w) s.valmask.push_back(vm[w]);
+  });
+  sortLeafSet(s);
+  return s;
+}
+
+struct Handle
+{
+  OccupancyMapping map;
+  LeafSet last_export;
+  explicit Handle(double res) : map(res) {}
+};
+
+} // namespace vo
+
+// ================================================================================================
+// C interface (ctypes / dlopen). All arrays are caller-allocated after a count query.
+// ================================================================================================
+extern "C" {
+
+void* vdbo_create(double resolution) { return new vo::Handle(resolution); }
+void vdbo_destroy(void* h) { delete static_cast<vo::Handle*>(h); }
+
+int vdbo_set_config(void* h, double max_range, double prob_hit, double prob_miss, double thres_min, double thres_max)
+{
+  return static_cast<vo::Handle*>(h)->map.setConfig(max_range, prob_hit, prob_miss, thres_min, thres_max);
+}
+void vdbo_set_probe_quirk(void* h, int on) { static_cast<vo::Handle*>(h)->map.replicate_probe_quirk = (on != 0); }
+
+// out[6] = hit, miss, thres_min, thres_max, max_logodds, min_logodds
+void vdbo_get_logodds(void* h, float* out)
+{
+  auto& m = static_cast<vo::Handle*>(h)->map;
+  out[0]  = m.m_logodds_hit;
+  out[1]  = m.m_logodds_miss;
+  out[2]  = m.m_logodds_thres_min;
+  out[3]  = m.m_logodds_thres_max;
+  out[4]  = m.m_max_logodds;
+  out[5]  = m.m_min_logodds;
+}
+
+void vdbo_add_source(void* h, const char* id, double max_range) { static_cast<vo::Handle*>(h)->map.addInputSource(id, max_range); }
+void vdbo_reset(void* h) { static_cast<vo::Handle*>(h)->map.resetMap(); }
+
+void vdbo_world_to_index(void* h, const double* w, int32_t* out)
+{
+  vo::Coord c = static_cast<vo::Handle*>(h)->map.worldToIndex(w);
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
+}
+
+// accumulateUpdate: 0 ok, 1 unknown source (no-op), 2 not configured (no-op)
+int vdbo_accumulate(void* h, const char* id, const void* pts, uint64_t n, uint64_t stride, const double* origin)
+{
+  return static_cast<vo::Handle*>(h)->map.accumulateUpdate(static_cast<const uint8_t*>(pts), n, stride, origin, id);
+}
+void vdbo_integrate(void* h) { static_cast<vo::Handle*>(h)->map.integrateUpdate(); }
+// insertPointCloud V:399-406
+int vdbo_insert(void* h, const char* id, const void* pts, uint64_t n, uint64_t stride, const double* origin)
+{
+  auto& m = static_cast<vo::Handle*>(h)->map;
+  int rc  = m.accumulateUpdate(static_cast<const uint8_t*>(pts), n, stride, origin, id);
+  m.integrateUpdate();
+  return rc;
+}
+
+// out[6] = rays, nan_skipped, clipped, visits, voxel_updates, state_changes (cumulative)
+void vdbo_stats(void* h, uint64_t* out)
+{
+  auto& s = static_cast<vo::Handle*>(h)->map.stats;
+  out[0] = s.rays; out[1] = s.nan_skipped; out[2] = s.clipped; out[3] = s.visits; out[4] = s.voxel_updates;
+  out[5] = s.state_changes;
+}
+
+// ---- exports: "prepare" snapshots a canonical (origin-sorted) leaf set and returns its size;
+//      "fetch" copies it out. kind: 0 = map (float), 1 = update grid of source, 2 = last change grid
+//      of source, 3 = section as UpdateGridT, 4 = section as GridT.
+int64_t vdbo_export_prepare(void* hh, int kind, const char* source, const int32_t* bbmin, const int32_t* bbmax, int full)
+{
+  auto* h = static_cast<vo::Handle*>(hh);
+  auto& m = h->map;
+  switch (kind)
+  {
+    case 0: h->last_export = vo::exportFloat(*m.m_vdb_grid); break;
+    case 1:
+    case 2: {
+      auto it = m.m_input_sources.find(source ? source : "");
+      if (it == m.m_input_sources.end()) return -1;
+      const vo::BoolTree* t = (kind == 1) ? it->second->update_grid.get() : it->second->last_change.get();
+      if (!t) { h->last_export = vo::LeafSet(); break; }
+      h->last_export = vo::exportBool(*t);
+      break;
+    }
+    case 3:
+    case 4:
+      h->last_export = vo::mapSection(*m.m_vdb_grid, vo::Coord(bbmin[0], bbmin[1], bbmin[2]),
+                                      vo::Coord(bbmax[0], bbmax[1], bbmax[2]), full != 0, kind == 4);
+      break;
+    default: return -2;
+  }
+  return int64_t(h->last_export.size());
+}
+
+// any pointer may be null. values: 512 f32 per leaf (kinds 0,4); valmask: 8 u64 per leaf (kinds 1,2,3)
+void vdbo_export_fetch(void* hh, int32_t* origins, uint64_t* active, uint64_t* valmask, float* values)
+{
+  auto& s = static_cast<vo::Handle*>(hh)->last_export;
+  if (origins && !s.origins.empty()) std::memcpy(origins, s.origins.data(), s.origins.size() * sizeof(int32_t));
+  if (active && !s.active.empty()) std::memcpy(active, s.active.data(), s.active.size() * sizeof(uint64_t));
+  if (valmask && !s.valmask.empty()) std::memcpy(valmask, s.valmask.data(), s.valmask.size() * sizeof(uint64_t));
+  if (values && !s.values.empty()) std::memcpy(values, s.values.data(), s.values.size() * sizeof(float));
+}
+
+// point query on the map (GridT::Accessor::getValue / isValueOn); returns active flag
+int vdbo_probe(void* hh, const int32_t* c, float* value)
+{
+  auto& m = static_cast<vo::Handle*>(hh)->map;
+  vo::Accessor<vo::FloatTree> acc(*m.m_vdb_grid);
+  vo::Coord cc(c[0], c[1], c[2]);
+  const vo::FloatLeaf* l = acc.probeLeaf(cc);
+  if (!l) { *value = 0.0f; return 0; }
+  uint32_t n = vo::leafOffset(cc);
+  *value     = l->buf[n];
+  return l->vmask.isOn(n) ? 1 : 0;
+}
+
+uint64_t vdbo_map_leaf_count(void* hh) { return static_cast<vo::Handle*>(hh)->map.m_vdb_grid->leafCount(); }
+
+// import an update grid (leaf records) into a source's update grid: used to model
+// updateMap(UpdateGridT::Ptr) with a caller-provided grid and the multi-GPU exchange tests.
+int vdbo_update_import(void* hh, const char* source, uint64_t n, const int32_t* origins, const uint64_t* active,
+                       const uint64_t* valmask)
+{
+  auto& m = static_cast<vo::Handle*>(hh)->map;
+  auto it = m.m_input_sources.find(source);
+  if (it == m.m_input_sources.end()) return 1;
+  vo::Accessor<vo::BoolTree> acc(*it->second->update_grid);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    bool any = false;
+    for (int w = 0; w < 8; ++w) any |= (active[8 * i + w] != 0);
+    if (!any) continue;
+    vo::BoolLeaf* l = acc.touchLeaf(vo::Coord(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]));
+    for (int w = 0; w < 8; ++w)
+    {
+      l->vmask.w[w] |= active[8 * i + w];
+      l->buf.w[w] |= valmask[8 * i + w];
+    }
+  }
+  return 0;
+}
+
+} // extern "C"

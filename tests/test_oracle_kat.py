@@ -1,0 +1,175 @@
+"""Pins the CPU oracle on the reference's own known-answer tests (/root/reference/tests/mapping.cpp),
+transcribed in tests/golden/mapping_kats.json, and cross-checks it against the independent
+pure-Python restatement in tests/pyref.py."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleOccupancyVDBMapping
+import pyref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KATS = json.load(open(os.path.join(HERE, "golden", "mapping_kats.json")))
+
+
+def _const(name, cfg):
+    if name == "log_hit":
+        return np.float32(math.log(cfg["prob_hit"]) - math.log(1 - cfg["prob_hit"]))
+    if name == "log_miss":
+        return np.float32(math.log(cfg["prob_miss"]) - math.log(1 - cfg["prob_miss"]))
+    return np.float32(name)
+
+
+def kat_points(case):
+    if "points" in case:
+        return np.array(case["points"], dtype=np.float32)
+    res = case["resolution"]
+    # the reference test computes k * resolution in double, PointXYZ narrows to float
+    return np.array([[np.float32(k * res) for k in p] for p in case["points_in_resolutions"]], dtype=np.float32)
+
+
+def run_kat(make_map, case, cfg):
+    """Drives any object with the OccupancyVDBMapping-like surface through one reference test case."""
+    m = make_map(case["resolution"])
+    pts = kat_points(case)
+    if "pre_config_insert" in case:  # tests/mapping.cpp:10-15: insert before setConfig/addInputSource is a no-op
+        pre = case["pre_config_insert"]
+        m.insertPointCloud(np.array(pre["points"], dtype=np.float32), pre["origin"], "test")
+        for c, v, _ in pre["expect"]:
+            assert m.probe(c)[0] == _const(v, cfg)
+    assert m.setConfig(case["max_range"], cfg["prob_hit"], cfg["prob_miss"], cfg["prob_thres_min"], cfg["prob_thres_max"]) == 0
+    m.addInputSource("test", case["max_range"], 0)
+    assert m.insertPointCloud(pts, case["origin"], "test") is True
+    for c, v, a in case["expect"]:
+        val, on = m.probe(c)
+        assert np.float32(val) == _const(v, cfg), (case["name"], c, val)
+        if a is not None:
+            assert on == a, (case["name"], c)
+    if "after_reset_expect" in case:
+        m.resetMap()
+        for c, v, _ in case["after_reset_expect"]:
+            assert m.probe(c)[0] == _const(v, cfg)
+    return m
+
+
+@pytest.mark.parametrize("case", KATS["cases"], ids=[c["name"] for c in KATS["cases"]])
+def test_oracle_reference_kats(case):
+    run_kat(OracleOccupancyVDBMapping, case, KATS["config"])
+
+
+def test_logodds_constants():
+    # constants of the gtest config and of the typical ROS config
+    m = OracleOccupancyVDBMapping(0.1)
+    assert m.setConfig(10, 0.9, 0.1, 0.49, 0.51) == 0
+    lo = m.logodds()
+    assert lo[0] == np.float32(float.fromhex("0x1.193ea8p+1"))
+    assert lo[1] == -lo[0]
+    assert lo[4] == np.float32(float.fromhex("0x1.261672p+2")) and lo[5] == -lo[4]
+    assert m.setConfig(10, 0.7, 0.4, 0.12, 0.97) == 0
+    lo = m.logodds()
+    assert lo[0] == np.float32(float.fromhex("0x1.b1d106p-1"))
+    assert lo[1] == np.float32(-float.fromhex("0x1.9f323ep-2"))
+
+
+def test_setconfig_validation():
+    m = OracleOccupancyVDBMapping(0.1)
+    assert m.setConfig(-1, 0.9, 0.1, 0.49, 0.51) == 1      # VDBMapping.hpp:1458-1463
+    assert m.setConfig(10, 0.9, 0.6, 0.49, 0.51) == 2      # OccupancyVDBMapping.hpp:65-70
+    assert m.setConfig(10, 0.4, 0.1, 0.49, 0.51) == 2      # OccupancyVDBMapping.hpp:71-76
+
+
+def test_world_to_index_half_voxel_rule():
+    # VDBMapping.hpp:612-631: +res/2 only when fmod(c,res) != 0
+    m = OracleOccupancyVDBMapping(0.1)
+    for w in [0.0, 0.5, -0.5, 0.05, 0.04, 0.06, -0.04, -0.06, 0.7, 1e-9, -1e-9, 12.34, -7.77, 0.1, 0.2, 0.30000000000000004]:
+        got = m.worldToIndex([w, w, w])
+        exp = pyref.world_to_index([w, w, w], 0.1)
+        assert tuple(int(x) for x in got) == exp, w
+
+
+def _rand_cloud(rng, n, scale):
+    p = rng.normal(size=(n, 3)) * scale
+    return p.astype(np.float32)
+
+
+@pytest.mark.parametrize("cfg", [(0.9, 0.1, 0.49, 0.51), (0.7, 0.4, 0.12, 0.97)])
+@pytest.mark.parametrize("quirk", [True, False])
+def test_oracle_vs_pyref_random(cfg, quirk):
+    """Multi-scan random clouds: update grid, change grid and map must be identical to pyref."""
+    rng = np.random.default_rng(7)
+    res, max_range = 0.1, 2.0
+    hit, miss, tmin, tmax = cfg
+    o = OracleOccupancyVDBMapping(res)
+    o.setProbeQuirk(quirk)
+    assert o.setConfig(max_range, hit, miss, tmin, tmax) == 0
+    o.addInputSource("s", max_range, 0)
+    p = pyref.PyMap(res, max_range, hit, miss, tmin, tmax, quirk=quirk)
+    for k in range(6):
+        pts = _rand_cloud(rng, 60, 1.2)
+        pts[::17] = np.nan
+        origin = [0.137 * k, 0.061 * k, 0.013 * k]
+        assert o.accumulateUpdate(pts, origin, "s") == 0
+        upd_o = pyref.leafset_to_voxels(o.exportUpdateGrid("s"))
+        upd_p, chg_p = p.insert(pts, origin)
+        assert {k_: v[1] for k_, v in upd_o.items()} == upd_p
+        assert all(v[0] for v in upd_o.values())
+        o.integrateUpdate()
+        chg_o = pyref.leafset_to_voxels(o.exportLastChange("s"))
+        assert {k_: v[1] for k_, v in chg_o.items()} == chg_p
+        map_o = pyref.leafset_to_voxels(o.exportMap())
+        map_p = {v: (a, val) for v, (val, a) in p.vox.items() if a or val != 0}
+        assert map_o == map_p
+        assert len(o.exportUpdateGrid("s")) == 0
+    assert o.mapLeafCount() == len(p.leaves)
+
+
+def test_dda_invariants():
+    """visits == 1 + |dx|+|dy|+|dz|, last voxel == end voxel, incl. exact-tie rays."""
+    rng = np.random.default_rng(11)
+    ends = [(5, 5, 5), (-5, -5, -5), (3, 9, 0), (1, 3, 9), (0, 0, 7), (-4, 4, 2), (100, 1, 0), (7, 7, 1)]
+    ends += [tuple(int(x) for x in rng.integers(-40, 40, 3)) for _ in range(300)]
+    for e in ends:
+        o = tuple(int(x) for x in rng.integers(-5, 5, 3))
+        ee = tuple(o[a] + e[a] for a in range(3))
+        vox = pyref.dda_voxels(o, ee)
+        if ee == o:
+            assert vox == []
+            continue
+        assert len(vox) == 1 + sum(abs(x) for x in e)
+        assert vox[0] == o and vox[-1] == ee
+        assert len(set(vox)) == len(vox)
+
+
+def test_sections_vs_bruteforce():
+    rng = np.random.default_rng(3)
+    o = OracleOccupancyVDBMapping(0.1)
+    o.setConfig(3.0, 0.9, 0.1, 0.49, 0.51)
+    o.addInputSource("s", 3.0, 0)
+    for k in range(3):
+        o.insertPointCloud(_rand_cloud(rng, 80, 1.5), [0.05 * k, 0, 0], "s")
+    full_map = pyref.leafset_to_voxels(o.exportMap())
+    mn, mx = (-9, -4, -3), (6, 11, 5)
+    inside = lambda v: all(mn[a] <= v[a] <= mx[a] for a in range(3))
+    sparse_u = pyref.leafset_to_voxels(o.getMapSectionUpdateGrid(mn, mx, False))
+    assert sparse_u == {v: (True, True) for v, (a, _) in full_map.items() if a and inside(v)}
+    sparse_f = pyref.leafset_to_voxels(o.getMapSectionGrid(mn, mx, False))
+    assert sparse_f == {v: (True, np.float32(1.0)) for v, (a, _) in full_map.items() if a and inside(v)}
+    full_f = pyref.leafset_to_voxels(o.getMapSectionGrid(mn, mx, True))
+    assert full_f == {v: av for v, av in full_map.items() if inside(v)}
+    full_u = pyref.leafset_to_voxels(o.getMapSectionUpdateGrid(mn, mx, True))
+    assert full_u == {v: (a, bool(val != 0)) for v, (a, val) in full_map.items() if inside(v)}
+
+
+def test_zero_and_negative_source_range_inserts_nothing():
+    # VDBMapping.hpp:331: max_range <= 0 on the source => nothing is raycast, not even endpoints
+    o = OracleOccupancyVDBMapping(0.1)
+    o.setConfig(0.0, 0.9, 0.1, 0.49, 0.51)
+    o.addInputSource("s", 0.0, 0)   # 0 -> falls back to m_max_range (0) -> nothing
+    o.insertPointCloud(np.array([[0, 0, 0.5]], np.float32), [0, 0, 0], "s")
+    assert o.mapLeafCount() == 0
+    o.addInputSource("n", -1.0, 0)
+    o.insertPointCloud(np.array([[0, 0, 0.5]], np.float32), [0, 0, 0], "n")
+    assert o.mapLeafCount() == 0
