@@ -1,0 +1,184 @@
+/* vdbm_b200.h — C ABI of libvdbm_b200.so: the B200-native (sm_100a) scan-integration hot path of
+ * vdb_mapping. Plain C types only (no torch / OpenVDB / PCL / Eigen in any signature).
+ *
+ * The reference (/root/reference) has no FFI: its boundary is the header-level C++ API of
+ *   include/vdb_mapping/VDBMapping.hpp           (cited below as V:<line>)
+ *   include/vdb_mapping/OccupancyVDBMapping.hpp   (cited below as O:<line>)
+ * Every entry point names the reference member whose device work it replaces. The C++ shim in
+ * include/vdb_mapping/ keeps the reference's class/member signatures and calls only this ABI;
+ * INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every call returns a vdbm_status (0 = ok); nothing throws across the ABI;
+ *    vdbm_last_error() gives a human-readable message for the last non-zero status on a handle.
+ *  - handles are opaque, created/destroyed by paired calls, thread-compatible (not internally
+ *    locked): the shim keeps the reference's std::shared_mutex discipline (V:327,378).
+ *  - leaf layout mirrors OpenVDB: leaf origin = coord & ~7; voxel offset n = (x&7)<<6 | (y&7)<<3 |
+ *    (z&7); bit masks are 8 x uint64, word n>>6 (= x&7), bit n&63. Leaf values are 512 x f32 in
+ *    offset order. Exported leaf sets are sorted by origin (x, then y, then z).
+ *  - there is NO CPU fallback: without a CUDA device vdbm_create fails with VDBM_ERR_CUDA.
+ */
+#ifndef VDBM_B200_H_INCLUDED
+#define VDBM_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
+#endif
+
+#define VDBM_ABI_VERSION 1
+
+typedef enum vdbm_status
+{
+  VDBM_OK                 = 0,
+  VDBM_ERR_INVALID_ARG    = 1,
+  VDBM_ERR_NOT_CONFIGURED = 2, /* V:478-482: raycast before setConfig -> reference prints + returns false */
+  VDBM_ERR_UNKNOWN_SOURCE = 3, /* V:320-326: reference prints "Source not available" and returns */
+  VDBM_ERR_BAD_CONFIG     = 4, /* V:1458-1463 / O:65-76: reference prints and keeps the old values */
+  VDBM_ERR_CUDA           = 5,
+  VDBM_ERR_OUT_OF_MEMORY  = 6,
+  VDBM_ERR_COORD_RANGE    = 7  /* a voxel coordinate left the +-2^23 range the 63-bit leaf key covers */
+} vdbm_status;
+
+typedef struct vdbm_map vdbm_map;         /* device-resident map + per-source update grids */
+typedef struct vdbm_leafset vdbm_leafset; /* host-side list of 8^3 leaves returned by exports */
+
+typedef struct vdbm_params
+{
+  double resolution;               /* V:115 ctor argument */
+  int32_t device;                  /* CUDA ordinal, -1 = current device */
+  int32_t replicate_probe_quirk;   /* 1 (default): change grid reproduces OpenVDB's tile-probe side effect
+                                      (SURVEY.md F9); 0: report only real active-flag flips */
+  uint64_t update_capacity_leaves; /* initial slots of each per-source update-leaf hash (0 = 1<<20) */
+  uint64_t map_capacity_leaves;    /* initial map leaf pool size (0 = 1<<19); both grow on demand */
+  void* stream;                    /* cudaStream_t to launch on; NULL = library-owned stream */
+} vdbm_params;
+
+typedef struct vdbm_stats_t
+{
+  /* cumulative since create/reset */
+  uint64_t rays;          /* points seen by the raycast (incl. NaN and clipped) */
+  uint64_t nan_skipped;   /* V:505-510 (the B200 build also drops +-inf, undefined in the reference) */
+  uint64_t clipped;       /* V:512-517 */
+  uint64_t visits;        /* DDA voxel visits = setActiveState calls of V:563 */
+  uint64_t voxel_updates; /* active update voxels applied by updateMap (V:764) */
+  uint64_t state_changes; /* voxels reported in change grids (V:770-781) */
+  uint64_t map_leaves;    /* 8^3 leaves currently in the map */
+  uint64_t new_leaves;    /* map leaves created, cumulative */
+  /* last call */
+  uint64_t last_touched_leaves; /* update-grid leaves of the source(s) consumed by the last integrate/update_map,
+                                   or currently accumulated after accumulate */
+  uint64_t last_voxel_updates;
+  uint64_t last_visits;
+  float last_accumulate_ms; /* device time of the last accumulate (CUDA events, kernels only) */
+  float last_integrate_ms;  /* device time of the last integrate / update_map */
+  uint32_t update_capacity; /* current per-source update hash slots (max over sources) */
+  uint32_t map_capacity;    /* current map leaf pool size */
+  uint32_t gpu_launches;    /* kernels launched by the library since create (cumulative) */
+  uint32_t reserved;
+} vdbm_stats_t;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+/* VDBMapping(double resolution) V:115-134 + createVDBMap V:163-169 (background 0.0f, inactive). */
+int vdbm_create(const vdbm_params* params, vdbm_map** out);
+void vdbm_destroy(vdbm_map* map);
+/* resetMap V:174-186: empty map and empty per-source update grids. */
+int vdbm_reset(vdbm_map* map);
+/* OccupancyVDBMapping::setConfig O:59-89 over VDBMapping::setConfig V:1456-1469. Log-odds constants are
+ * computed on the host in double exactly like O:79-87 and narrowed to float. Returns VDBM_ERR_BAD_CONFIG
+ * for max_range < 0 (nothing changes) and for prob_miss > 0.5 / prob_hit < 0.5 (max_range and the
+ * "configured" flag ARE already updated then, like the reference). */
+int vdbm_set_config(vdbm_map* map, double max_range, double prob_hit, double prob_miss, double prob_thres_min,
+                    double prob_thres_max);
+/* out[6] = logodds hit, miss, thres_min, thres_max, max, min (O:179-199) */
+int vdbm_get_logodds(vdbm_map* map, float* out6);
+/* addInputSource V:1352-1375 (device part: the per-source update grid; max_range == 0 -> config max_range).
+ * Worker threads and rate limiting stay in the host shim. */
+int vdbm_source_add(vdbm_map* map, const char* source_id, double max_range);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* accumulateUpdate V:316-346 -> raycastPointCloud V:466-539 (castRayIntoGrid V:550-566, worldToIndex
+ * V:612-631) into the source's device update grid. `points` is a HOST buffer of n records with the
+ * pcl::PointXYZ layout (3 x f32 at the start of each `stride_bytes` record, normally 16); pinned memory is
+ * copied asynchronously. No-op (VDBM_OK) when the source's max_range <= 0 (V:331). */
+int vdbm_accumulate(vdbm_map* map, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes,
+                    const double origin[3]);
+/* Same, `points` already resident in device memory (used for the kernel-only benchmark leg and for callers
+ * that produce clouds on the GPU). */
+int vdbm_accumulate_device(vdbm_map* map, const char* source_id, const void* d_points, uint64_t n,
+                           uint64_t stride_bytes, const double origin[3]);
+/* raycastPointCloud V:466-472 with an explicit raycast_range, into the named source's update grid
+ * (the reference passes an UpdateGridT::Accessor; here the grid is addressed by its source). */
+int vdbm_raycast(vdbm_map* map, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes,
+                 const double origin[3], double raycast_range);
+/* integrateUpdate V:375-387: updateMap V:731-792 for every source in std::map key order, then fresh update
+ * grids. The change grids are discarded like V:382 unless keep_change != 0 (then vdbm_change_export works). */
+int vdbm_integrate(vdbm_map* map, int keep_change);
+/* insertPointCloud V:399-406 = accumulate + integrate. */
+int vdbm_insert(vdbm_map* map, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes,
+                const double origin[3]);
+/* updateMap(UpdateGridT::Ptr) V:731-792 on ONE source's accumulated update grid; the grid is emptied.
+ * If change != NULL it receives the returned change grid (active = flag flipped, value = it was a hit). */
+int vdbm_update_map(vdbm_map* map, const char* source_id, vdbm_leafset** change);
+
+/* ---- grids in and out (remote mapping, host mirror) ---------------------------------------- */
+/* The source's raw update grid (InputSource::update_grid V:97): origin, active mask, value mask per leaf. */
+int vdbm_update_export(vdbm_map* map, const char* source_id, vdbm_leafset** out);
+/* OR a host update grid into the source's device update grid (for updateMap() called with a grid that was
+ * produced elsewhere, e.g. byteArrayToGrid V:1328-1338 on the receiving side). */
+int vdbm_update_import(vdbm_map* map, const char* source_id, uint64_t n_leaves, const int32_t* origins /*[n][3]*/,
+                       const uint64_t* active /*[n][8]*/, const uint64_t* value /*[n][8]*/);
+/* Change grid kept by the last vdbm_integrate(map, 1) for that source. */
+int vdbm_change_export(vdbm_map* map, const char* source_id, vdbm_leafset** out);
+/* getGrid V:799: map leaves (origin, 512 x f32, active mask). dirty_only != 0: only leaves modified since the
+ * previous vdbm_map_export call (what an eager/lazy host mirror needs); 0: all leaves. */
+int vdbm_map_export(vdbm_map* map, int dirty_only, vdbm_leafset** out);
+/* getMapSection<T> V:921-960 with extractSparseLeaf V:999-1011 / extractFullLeaf V:970-989 on an INCLUSIVE
+ * index bounding box (createIndexBoundingBox V:857-871 is host maths and stays in the shim).
+ * result_float = 0 -> UpdateGridT result (active + value masks), 1 -> GridT result (active + 512 f32). */
+int vdbm_section(vdbm_map* map, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float,
+                 vdbm_leafset** out);
+/* GridT::Accessor::getValue / isValueOn for one voxel (tests/mapping.cpp:27-29). */
+int vdbm_probe(vdbm_map* map, const int32_t xyz[3], float* value, int32_t* active);
+
+/* ---- leaf sets ------------------------------------------------------------------------------ */
+uint64_t vdbm_leafset_size(const vdbm_leafset* s);
+const int32_t* vdbm_leafset_origins(const vdbm_leafset* s); /* [n][3] */
+const uint64_t* vdbm_leafset_active(const vdbm_leafset* s); /* [n][8] */
+const uint64_t* vdbm_leafset_valmask(const vdbm_leafset* s); /* [n][8] or NULL (float results) */
+const float* vdbm_leafset_values(const vdbm_leafset* s);    /* [n][512] or NULL (bool results) */
+void vdbm_leafset_free(vdbm_leafset* s);
+
+/* ---- multi-GPU: map sharded by leaf key, rays split across ranks -------------------- */
+/* Owner rank of a leaf (origin must be a multiple of 8): mix64(morton-brick(leaf)) % n_ranks. Pure function. */
+int32_t vdbm_leaf_owner(const int32_t origin[3], int32_t n_ranks);
+/* Bin the source's accumulated update leaves by owner into a device buffer of 136-byte records
+ * {uint64 key, uint64 active[8], uint64 value[8]} grouped by rank; counts[n_ranks] (host) receives the group
+ * sizes; the update grid is emptied. *d_records stays valid until the next call on this handle. */
+int vdbm_update_partition(vdbm_map* map, const char* source_id, int32_t n_ranks, uint64_t* counts,
+                          const void** d_records);
+/* OR device-resident records (as produced by vdbm_update_partition on any rank) into the source's grid. */
+int vdbm_update_import_device(vdbm_map* map, const char* source_id, const void* d_records, uint64_t n_records);
+
+/* ---- diagnostics ---------------------------------------------------------------------------- */
+int vdbm_stats(vdbm_map* map, vdbm_stats_t* out);
+const char* vdbm_last_error(vdbm_map* map);
+int vdbm_abi_version(void);
+/* wait for all work queued on the handle's stream */
+int vdbm_synchronize(vdbm_map* map);
+/* pinned host memory helpers for callers that want truly asynchronous uploads */
+void* vdbm_host_alloc(size_t bytes);
+void vdbm_host_free(void* p);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDBM_B200_H_INCLUDED */

@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/vdbm_b200.h declares; no compute call is made (there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vdbm_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vdbm_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def so_path():
+    from vdb_mapping_b200 import build
+    return build.build_lib()
+
+
+def test_header_declares_the_hot_path():
+    names = declared_functions()
+    for must in ["vdbm_create", "vdbm_destroy", "vdbm_set_config", "vdbm_source_add", "vdbm_accumulate", "vdbm_integrate",
+                 "vdbm_insert", "vdbm_update_map", "vdbm_update_export", "vdbm_update_import", "vdbm_map_export",
+                 "vdbm_section", "vdbm_probe", "vdbm_reset", "vdbm_stats", "vdbm_last_error"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(so_path):
+    lib = ctypes.CDLL(so_path)
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.vdbm_abi_version() == 1
+
+
+def test_only_the_abi_is_exported(so_path):
+    out = subprocess.run(["nm", "-D", "--defined-only", so_path], capture_output=True, text=True, check=True).stdout
+    syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert syms and all(s.startswith("vdbm_") for s in syms), [s for s in syms if not s.startswith("vdbm_")]
+
+
+def test_sass_is_sm100a_with_blackwell_256bit_accesses(so_path):
+    out = subprocess.run(["cuobjdump", "-sass", so_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out or "SM100a" in out.replace("_", "").upper() or "arch = sm_100" in out
+    assert ".256" in out          # LDG/STG.E.ENL2.256 in the update / gather kernels
+    assert "RED" in out           # red.global.or.b64 in the DDA kernel
+    assert "DFMA" not in out.split("raycast_dda_kernel")[1].split("Function :")[0]  # -fmad=false: no fused fp64 in the DDA
+
+
+def test_create_fails_loudly_without_gpu(so_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping, VdbmError
+    with pytest.raises(VdbmError):
+        OccupancyVDBMapping(0.1)
+
+
+def test_leaf_owner_is_a_pure_host_function(so_path):
+    from vdb_mapping_b200.mapping import leaf_owner
+    owners = [leaf_owner([8 * x, 8 * y, 0], 8) for x in range(-8, 8) for y in range(-8, 8)]
+    assert set(owners) <= set(range(8)) and len(set(owners)) == 8
+    # 2x2x2 bricks of leaves share an owner
+    assert leaf_owner([0, 0, 0], 8) == leaf_owner([8, 8, 8], 8)
+    assert leaf_owner([16, 0, 0], 4) == leaf_owner([24, 8, 8], 4)
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product package must never import / link / execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "vdb_mapping_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.lower().replace("no cpu fallback", ""), os.path.join(dirpath, f)

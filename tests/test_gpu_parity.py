@@ -1,0 +1,263 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bar: bit-exact leaf sets — voxel coordinates, active masks, hit masks, change masks, f32 log-odds bit patterns."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import CFG_GTEST, CFG_ROS, assert_leafsets_equal, popcount64
+from test_oracle_kat import KATS, run_kat
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(kind, res, **kw):
+    if kind == "gpu":
+        from vdb_mapping_b200.mapping import OccupancyVDBMapping
+        return OccupancyVDBMapping(res, **kw)
+    from oracle.oracle import OracleOccupancyVDBMapping
+    m = OracleOccupancyVDBMapping(res)
+    if "replicate_probe_quirk" in kw:
+        m.setProbeQuirk(kw["replicate_probe_quirk"])
+    return m
+
+
+def _pair(res, max_range, cfg, sources=("s",), **kw):
+    g, o = _mk("gpu", res, **kw), _mk("cpu", res, **{k: v for k, v in kw.items() if k == "replicate_probe_quirk"})
+    for m in (g, o):
+        assert m.setConfig(max_range, *cfg[:2], cfg[2], cfg[3]) == 0
+        for s in sources:
+            m.addInputSource(s, max_range, 0)
+    return g, o
+
+
+@pytest.mark.parametrize("case", KATS["cases"], ids=[c["name"] for c in KATS["cases"]])
+def test_reference_kats_on_gpu(case):
+    """The reference's own gtest cases (tests/mapping.cpp) through the CUDA path."""
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    run_kat(OccupancyVDBMapping, case, KATS["config"])
+
+
+def test_logodds_constants_match():
+    g, o = _pair(0.1, 10.0, CFG_ROS)
+    assert np.array_equal(g.logodds().view(np.uint32), o.logodds().view(np.uint32))
+    assert g.setConfig(-1, 0.9, 0.1, 0.49, 0.51) == 1
+    assert g.setConfig(10, 0.9, 0.6, 0.49, 0.51) == 2
+    assert g.setConfig(10, 0.4, 0.1, 0.49, 0.51) == 2
+
+
+@pytest.mark.parametrize("cfg", [CFG_GTEST, CFG_ROS], ids=["gtest_cfg", "ros_cfg"])
+@pytest.mark.parametrize("quirk", [True, False], ids=["quirk", "noquirk"])
+def test_small_sequences_bit_exact(cfg, quirk):
+    """Random multi-scan sequences with ties, axis-aligned, clipped, zero-length, NaN rays and a moving origin:
+    update grid, change grid and map identical after every scan."""
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, cfg, replicate_probe_quirk=quirk)
+    for k in range(8):
+        pts, origin = scans.small_scan(100 + k, n=3000, scale=2.5)
+        origin = origin + np.array([0.137 * k, 0.061 * k, 0.013 * k])
+        assert g.accumulateUpdate(pts, origin, "s") == 0 and o.accumulateUpdate(pts, origin, "s") == 0
+        assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), f"update grid scan {k}")
+        g.integrateUpdate(keep_change=True)
+        o.integrateUpdate()
+        assert_leafsets_equal(g.exportLastChange("s"), o.exportLastChange("s"), f"change grid scan {k}")
+        assert_leafsets_equal(g.exportMap(), o.exportMap(), f"map scan {k}")
+        assert len(g.exportUpdateGrid("s")) == 0
+    sg, so = g.stats(), o.stats()
+    for key in ("rays", "clipped", "visits", "voxel_updates", "state_changes"):
+        assert sg[key] == so[key], key
+    assert sg["map_leaves"] == o.mapLeafCount()
+
+
+def test_accumulation_over_several_scans_and_sources():
+    """Several accumulateUpdate calls before one integrate (dedup across scans) and two sources applied in
+    std::map key order (VDBMapping.hpp:380)."""
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.05, 3.0, CFG_GTEST, sources=("b_src", "a_src"))
+    for rep in range(3):
+        for i, s in enumerate(("b_src", "a_src", "b_src")):
+            pts, origin = scans.small_scan(7 * rep + i, n=2000, scale=1.5)
+            g.accumulateUpdate(pts, origin, s)
+            o.accumulateUpdate(pts, origin, s)
+        for s in ("a_src", "b_src"):
+            assert_leafsets_equal(g.exportUpdateGrid(s), o.exportUpdateGrid(s), f"update {s}")
+        g.integrateUpdate(keep_change=True)
+        o.integrateUpdate()
+        for s in ("a_src", "b_src"):
+            assert_leafsets_equal(g.exportLastChange(s), o.exportLastChange(s), f"change {s}")
+        assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
+
+
+def test_clamping_and_state_flips_after_repeated_hits():
+    """Same scan 12 times: values run into +-clamp, flags flip once; bit-exact all the way."""
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 5.0, CFG_ROS)
+    pts, origin = scans.small_scan(5, n=1500, scale=2.0)
+    for k in range(12):
+        g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+        chg = g.updateMap("s")
+        o.integrateUpdate()
+        assert_leafsets_equal(chg, o.exportLastChange("s"), f"change {k}")
+    mg = g.exportMap()
+    assert_leafsets_equal(mg, o.exportMap(), "map")
+    lo = g.logodds()
+    assert mg.values.max() == lo[4] and mg.values.min() == lo[5]
+
+
+def test_degenerate_miss_noop_config():
+    """prob_miss = 0.5 (log-odds 0) with thres_min > 0.5: OpenVDB's tile probe does not create leaves for misses."""
+    from vdb_mapping_b200 import scans
+    cfg = (0.9, 0.5, 0.6, 0.7)
+    g, o = _pair(0.1, 3.0, cfg)
+    for k in range(3):
+        pts, origin = scans.small_scan(40 + k, n=800, scale=1.5)
+        g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+        chg = g.updateMap("s")
+        o.integrateUpdate()
+        assert_leafsets_equal(chg, o.exportLastChange("s"), f"change {k}")
+        assert_leafsets_equal(g.exportMap(), o.exportMap(), f"map {k}")
+
+
+def test_edge_inputs():
+    g, o = _pair(0.1, 2.0, CFG_GTEST)
+    empty = np.zeros((0, 4), np.float32)
+    allnan = np.full((64, 4), np.nan, np.float32)
+    same = np.zeros((5, 4), np.float32)                       # zero-length rays: endpoint only
+    inf = np.array([[np.inf, 0, 0, 1], [0, -np.inf, 0, 1]], np.float32)
+    one = np.array([[0.31, -0.2, 0.77, 1]], np.float32)
+    for pts in (empty, allnan, same, one):
+        assert g.accumulateUpdate(pts, [0, 0, 0], "s") == 0 and o.accumulateUpdate(pts, [0, 0, 0], "s") == 0
+        assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "update")
+    g.accumulateUpdate(inf, [0, 0, 0], "s")                   # dropped (undefined in the reference)
+    assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "update after inf")
+    # NaN origin: every point skipped (VDBMapping.hpp:505-510)
+    g.accumulateUpdate(one, [np.nan, 0, 0], "s"); o.accumulateUpdate(one, [np.nan, 0, 0], "s")
+    assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "nan origin")
+    g.integrateUpdate(); o.integrateUpdate()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
+    # unknown source: no-op with status 1, unconfigured map: status 2
+    assert g.accumulateUpdate(one, [0, 0, 0], "nope") == 1
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    fresh = OccupancyVDBMapping(0.1)
+    fresh.addInputSource("s", 1.0)
+    assert fresh.accumulateUpdate(one, [0, 0, 0], "s") == 2
+    assert fresh.insertPointCloud(one, [0, 0, 0], "s") is True and fresh.mapLeafCount() == 0
+    # source max_range <= 0: nothing inserted (VDBMapping.hpp:331)
+    g.addInputSource("neg", -1.0)
+    assert g.accumulateUpdate(one, [0, 0, 0], "neg") == 0 and len(g.exportUpdateGrid("neg")) == 0
+
+
+def test_hash_growth_paths():
+    """Tiny initial capacities force update-hash overflow + replay, and map pool / hash growth."""
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.05, 6.0, CFG_GTEST, update_capacity_leaves=64, map_capacity_leaves=32)
+    for k in range(3):
+        pts, origin = scans.small_scan(900 + k, n=6000, scale=3.0)
+        g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+        assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), f"update {k}")
+        g.integrateUpdate(); o.integrateUpdate()
+        assert_leafsets_equal(g.exportMap(), o.exportMap(), f"map {k}")
+    st = g.stats()
+    assert st["update_capacity"] > 64 and st["map_capacity"] > 32
+    assert st["visits"] == o.stats()["visits"]          # replay must not double count
+
+
+def test_sections_and_dirty_export():
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, CFG_GTEST)
+    for k in range(3):
+        pts, origin = scans.small_scan(300 + k, n=4000, scale=2.5)
+        g.insertPointCloud(pts, origin, "s"); o.insertPointCloud(pts, origin, "s")
+    for mn, mx in [((-9, -4, -3), (6, 11, 5)), ((-100, -100, -100), (100, 100, 100)), ((0, 0, 0), (0, 0, 0)),
+                   ((3, 3, 3), (2, 2, 2)), ((-17, 5, -8), (-9, 23, 7))]:
+        for full in (False, True):
+            assert_leafsets_equal(g.getMapSectionUpdateGrid(mn, mx, full), o.getMapSectionUpdateGrid(mn, mx, full), f"section U {mn} {full}")
+            assert_leafsets_equal(g.getMapSectionGrid(mn, mx, full), o.getMapSectionGrid(mn, mx, full), f"section F {mn} {full}")
+    # dirty export: after a full export, only leaves touched by the next scan come back, with current content
+    full = g.exportMap()
+    pts, origin = scans.small_scan(999, n=500, scale=1.0)
+    g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+    touched = o.exportUpdateGrid("s")
+    g.integrateUpdate(); o.integrateUpdate()
+    dirty = g.exportMap(dirty_only=True)
+    assert np.array_equal(dirty.origins, touched.origins)
+    now = o.exportMap()
+    idx = {tuple(x): i for i, x in enumerate(now.origins)}
+    sel = [idx[tuple(x)] for x in dirty.origins]
+    assert np.array_equal(dirty.values.view(np.uint32), now.values[sel].view(np.uint32))
+    assert np.array_equal(dirty.active, now.active[sel])
+    assert len(g.exportMap(dirty_only=True)) == 0
+
+
+def test_update_grid_import_roundtrip_and_reset():
+    """updateMap(grid produced elsewhere): export on one map, import on another, maps end identical."""
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, CFG_ROS)
+    g2, _ = _pair(0.1, 4.0, CFG_ROS)
+    pts, origin = scans.small_scan(77, n=3000, scale=2.0)
+    g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+    upd = g.exportUpdateGrid("s")
+    g2.importUpdate("s", upd.origins, upd.active, upd.valmask)
+    g2.importUpdate("s", upd.origins[::2], upd.active[::2], upd.valmask[::2])   # OR is idempotent
+    assert_leafsets_equal(g2.exportUpdateGrid("s"), upd, "imported update grid")
+    g.integrateUpdate(); g2.integrateUpdate(); o.integrateUpdate()
+    assert_leafsets_equal(g2.exportMap(), o.exportMap(), "map via import")
+    g.resetMap(); o.resetMap()
+    assert len(g.exportMap()) == 0 and g.probe((0, 0, 1)) == (0.0, False)
+    g.insertPointCloud(pts, origin, "s"); o.insertPointCloud(pts, origin, "s")
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map after reset")
+
+
+def test_raycast_with_explicit_range():
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 1.0, CFG_ROS)
+    pts, origin = scans.small_scan(12, n=2000, scale=2.0)
+    assert g.raycastPointCloud(pts, origin, 2.5, "s")
+    o2 = _mk("cpu", 0.1)
+    o2.setConfig(2.5, *CFG_ROS); o2.addInputSource("s", 2.5)
+    o2.accumulateUpdate(pts, origin, "s")
+    assert_leafsets_equal(g.exportUpdateGrid("s"), o2.exportUpdateGrid("s"), "explicit range")
+
+
+@pytest.mark.parametrize("cfg_id", [1, 3, 2])
+def test_baseline_configs_one_scan_bit_exact(cfg_id):
+    """BASELINE.json configs 1-3 at full size: one scan, update grid + map bit-exact vs the oracle, then a second
+    scan from a moved origin (RMW on existing leaves)."""
+    from vdb_mapping_b200 import scans
+    c = scans.CONFIGS[cfg_id]
+    g, o = _pair(c.resolution, c.max_range, (c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max))
+    for k in range(2):
+        pts, origin = scans.make_scan(cfg_id, k)
+        g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+        ug, uo = g.exportUpdateGrid("s"), o.exportUpdateGrid("s")
+        assert_leafsets_equal(ug, uo, f"cfg{cfg_id} update grid scan {k}")
+        g.integrateUpdate(); o.integrateUpdate()
+        assert g.stats()["last_voxel_updates"] == popcount64(uo.active)
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), f"cfg{cfg_id} map")
+    sg, so = g.stats(), o.stats()
+    for key in ("rays", "clipped", "visits", "voxel_updates"):
+        assert sg[key] == so[key], key
+
+
+def test_full_size_properties_cfg2_sequence():
+    """Size-independent properties at BASELINE size (no oracle): idempotence of the update grid under re-insertion
+    of the same scan, permutation invariance, visits == sum(1+|d|_1), hit voxels are active."""
+    from vdb_mapping_b200 import scans
+    c = scans.CONFIGS[2]
+    cfg = (c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    g = OccupancyVDBMapping(c.resolution); g.setConfig(c.max_range, *cfg); g.addInputSource("s", c.max_range)
+    pts, origin = scans.make_scan(2, 3)
+    g.accumulateUpdate(pts, origin, "s")
+    a = g.exportUpdateGrid("s")
+    g.accumulateUpdate(pts, origin, "s")                      # idempotent OR
+    b = g.exportUpdateGrid("s")
+    assert_leafsets_equal(a, b, "idempotence")
+    g.updateMap("s")
+    perm = np.random.default_rng(0).permutation(pts.shape[0])
+    g.accumulateUpdate(pts[perm], origin, "s")                # order independence
+    assert_leafsets_equal(a, g.exportUpdateGrid("s"), "permutation invariance")
+    assert np.all((a.valmask & ~a.active) == 0)               # every hit voxel is active
+    st = g.stats()
+    assert st["last_visits"] > 1.4e8 and st["last_touched_leaves"] == len(a)

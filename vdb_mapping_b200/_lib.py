@@ -1,0 +1,85 @@
+"""ctypes binding of libvdbm_b200.so (the C ABI in include/vdbm_b200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libvdbm_b200.so")
+
+VDBM_OK, VDBM_ERR_INVALID_ARG, VDBM_ERR_NOT_CONFIGURED, VDBM_ERR_UNKNOWN_SOURCE = 0, 1, 2, 3
+VDBM_ERR_BAD_CONFIG, VDBM_ERR_CUDA, VDBM_ERR_OUT_OF_MEMORY, VDBM_ERR_COORD_RANGE = 4, 5, 6, 7
+
+
+class VdbmParams(C.Structure):
+    _fields_ = [("resolution", C.c_double), ("device", C.c_int32), ("replicate_probe_quirk", C.c_int32),
+                ("update_capacity_leaves", C.c_uint64), ("map_capacity_leaves", C.c_uint64), ("stream", C.c_void_p)]
+
+
+class VdbmStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "nan_skipped", "clipped", "visits", "voxel_updates", "state_changes",
+                                          "map_leaves", "new_leaves", "last_touched_leaves", "last_voxel_updates",
+                                          "last_visits")] + \
+               [("last_accumulate_ms", C.c_float), ("last_integrate_ms", C.c_float), ("update_capacity", C.c_uint32),
+                ("map_capacity", C.c_uint32), ("gpu_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing: build it with `python -m vdb_mapping_b200.build` (nvcc, sm_100a). "
+            "vdb_mapping_b200 has no CPU fallback.")
+    L = C.CDLL(SO_PATH)
+    vp, cp, dbl, i32, u64 = C.c_void_p, C.c_char_p, C.c_double, C.c_int32, C.c_uint64
+    pvp = C.POINTER(C.c_void_p)
+    i32p, u64p, f32p, dblp = C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_double)
+
+    def sig(name, res, *args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    sig("vdbm_abi_version", C.c_int)
+    sig("vdbm_create", C.c_int, C.POINTER(VdbmParams), pvp)
+    sig("vdbm_destroy", None, vp)
+    sig("vdbm_reset", C.c_int, vp)
+    sig("vdbm_set_config", C.c_int, vp, dbl, dbl, dbl, dbl, dbl)
+    sig("vdbm_get_logodds", C.c_int, vp, f32p)
+    sig("vdbm_source_add", C.c_int, vp, cp, dbl)
+    sig("vdbm_accumulate", C.c_int, vp, cp, vp, u64, u64, dblp)
+    sig("vdbm_accumulate_device", C.c_int, vp, cp, vp, u64, u64, dblp)
+    sig("vdbm_raycast", C.c_int, vp, cp, vp, u64, u64, dblp, dbl)
+    sig("vdbm_integrate", C.c_int, vp, C.c_int)
+    sig("vdbm_insert", C.c_int, vp, cp, vp, u64, u64, dblp)
+    sig("vdbm_update_map", C.c_int, vp, cp, pvp)
+    sig("vdbm_update_export", C.c_int, vp, cp, pvp)
+    sig("vdbm_update_import", C.c_int, vp, cp, u64, i32p, u64p, u64p)
+    sig("vdbm_change_export", C.c_int, vp, cp, pvp)
+    sig("vdbm_map_export", C.c_int, vp, C.c_int, pvp)
+    sig("vdbm_section", C.c_int, vp, i32p, i32p, C.c_int, C.c_int, pvp)
+    sig("vdbm_probe", C.c_int, vp, i32p, f32p, i32p)
+    sig("vdbm_leafset_size", u64, vp)
+    sig("vdbm_leafset_origins", i32p, vp)
+    sig("vdbm_leafset_active", u64p, vp)
+    sig("vdbm_leafset_valmask", u64p, vp)
+    sig("vdbm_leafset_values", f32p, vp)
+    sig("vdbm_leafset_free", None, vp)
+    sig("vdbm_leaf_owner", i32, i32p, i32)
+    sig("vdbm_update_partition", C.c_int, vp, cp, i32, u64p, pvp)
+    sig("vdbm_update_import_device", C.c_int, vp, cp, vp, u64)
+    sig("vdbm_stats", C.c_int, vp, C.POINTER(VdbmStats))
+    sig("vdbm_last_error", cp, vp)
+    sig("vdbm_synchronize", C.c_int, vp)
+    sig("vdbm_host_alloc", vp, C.c_size_t)
+    sig("vdbm_host_free", None, vp)
+    _lib = L
+    return L

@@ -1,0 +1,995 @@
+// vdbm_abi.cu — host side of libvdbm_b200.so: the C ABI declared in include/vdbm_b200.h.
+// Owns device memory (update-leaf hashes, map hash + leaf pool), sequencing of the kernels in
+// vdbm_kernels.cu, growth, and the export staging. No CPU compute path exists here: every grid
+// operation is a kernel launch; without a CUDA device vdbm_create fails.
+#include "../../include/vdbm_b200.h"
+#include "vdbm_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace vdbm;
+
+struct vdbm_leafset
+{
+  uint64_t n        = 0;
+  int32_t* origins  = nullptr;
+  uint64_t* active  = nullptr;
+  uint64_t* valmask = nullptr;
+  float* values     = nullptr;
+  bool pinned       = false;
+};
+
+namespace {
+
+struct Source
+{
+  std::string id;
+  double max_range = 0.0;
+  UpdateTable t{};
+  uint32_t cap       = 0;
+  uint32_t n_touched = 0;         // host copy, valid after every synchronising call
+  LeafRecord* d_change = nullptr; // change records of the last update (device)
+  uint32_t change_cap  = 0;
+  uint32_t n_change    = 0;
+};
+
+} // namespace
+
+struct vdbm_map
+{
+  vdbm_params params{};
+  int device          = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream     = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string last_error;
+
+  // config (VDBMapping.hpp:1456-1469, OccupancyVDBMapping.hpp:59-89)
+  double max_range = 0.0;
+  bool config_set  = false;
+  LogOdds lo{};
+
+  // device state
+  Counters* d_ctr = nullptr;
+  Counters* h_ctr = nullptr; // pinned
+  MapTable mt{};
+  uint32_t hcap     = 0;
+  uint32_t n_leaves = 0; // host copy
+  uint32_t* d_map_counters = nullptr; // [0] n_leaves, [1] n_dirty
+  uint32_t* h_small        = nullptr; // pinned scratch (>= 64 words)
+  std::map<std::string, std::unique_ptr<Source> > sources; // std::map order == integrateUpdate order (V:380)
+
+  // staging
+  uint8_t* d_points = nullptr;
+  size_t points_cap = 0;
+  RayRec* d_rays    = nullptr;
+  size_t rays_cap   = 0;
+  LeafRecord* d_part = nullptr; // partition output
+  size_t part_cap    = 0;
+  int dda_grid       = 0;
+
+  vdbm_stats_t stats{};
+  Counters base{}; // counters at the last reset, to keep cumulative numbers across device counter resets
+};
+
+namespace {
+
+#define CU_TRY(m, expr)                                                                                         \
+  do                                                                                                            \
+  {                                                                                                             \
+    cudaError_t e__ = (expr);                                                                                   \
+    if (e__ != cudaSuccess)                                                                                     \
+    {                                                                                                           \
+      (m)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                                    \
+      return (e__ == cudaErrorMemoryAllocation) ? VDBM_ERR_OUT_OF_MEMORY : VDBM_ERR_CUDA;                       \
+    }                                                                                                           \
+  } while (0)
+
+int fail(vdbm_map* m, int code, const std::string& msg)
+{
+  m->last_error = msg;
+  return code;
+}
+
+uint32_t nextPow2(uint64_t v)
+{
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return uint32_t(std::min<uint64_t>(p, 1ull << 31));
+}
+
+// ---- update table ------------------------------------------------------------------------------------
+int allocUpdateTable(vdbm_map* m, UpdateTable& t, uint32_t cap)
+{
+  CU_TRY(m, cudaMalloc(&t.keys, size_t(cap) * 8));
+  CU_TRY(m, cudaMalloc(&t.active, size_t(cap) * 64));
+  CU_TRY(m, cudaMalloc(&t.value, size_t(cap) * 64));
+  CU_TRY(m, cudaMalloc(&t.touched, size_t(cap) * 4));
+  CU_TRY(m, cudaMalloc(&t.n_touched, 4));
+  t.cap_mask = cap - 1;
+  CU_TRY(m, cudaMemsetAsync(t.keys, 0xFF, size_t(cap) * 8, m->stream));
+  CU_TRY(m, cudaMemsetAsync(t.active, 0, size_t(cap) * 64, m->stream));
+  CU_TRY(m, cudaMemsetAsync(t.value, 0, size_t(cap) * 64, m->stream));
+  CU_TRY(m, cudaMemsetAsync(t.n_touched, 0, 4, m->stream));
+  return VDBM_OK;
+}
+void freeUpdateTable(UpdateTable& t)
+{
+  cudaFree(t.keys); cudaFree(t.active); cudaFree(t.value); cudaFree(t.touched); cudaFree(t.n_touched);
+  t = UpdateTable{};
+}
+
+int growUpdateTable(vdbm_map* m, Source& s, uint32_t new_cap)
+{
+  UpdateTable nt{};
+  int rc = allocUpdateTable(m, nt, new_cap);
+  if (rc) return rc;
+  launchRehashUpdate(s.t, s.n_touched, nt, m->d_ctr, m->stream);
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  freeUpdateTable(s.t);
+  s.t   = nt;
+  s.cap = new_cap;
+  return VDBM_OK;
+}
+
+// ---- map ---------------------------------------------------------------------------------------------
+int allocMapHash(vdbm_map* m, uint32_t hcap)
+{
+  CU_TRY(m, cudaMalloc(&m->mt.hkeys, size_t(hcap) * 8));
+  CU_TRY(m, cudaMalloc(&m->mt.hvals, size_t(hcap) * 4));
+  CU_TRY(m, cudaMemsetAsync(m->mt.hkeys, 0xFF, size_t(hcap) * 8, m->stream));
+  m->mt.hcap_mask = hcap - 1;
+  m->hcap         = hcap;
+  return VDBM_OK;
+}
+
+int allocMapPool(vdbm_map* m, MapTable& t, uint32_t cap)
+{
+  CU_TRY(m, cudaMalloc(&t.leaf_keys, size_t(cap) * 8));
+  CU_TRY(m, cudaMalloc(&t.leaf_mask, size_t(cap) * 64));
+  CU_TRY(m, cudaMalloc(&t.leaf_vals, size_t(cap) * 2048));
+  CU_TRY(m, cudaMalloc(&t.leaf_dirty, size_t(cap) * 4));
+  CU_TRY(m, cudaMalloc(&t.dirty_list, size_t(cap) * 4));
+  CU_TRY(m, cudaMemsetAsync(t.leaf_dirty, 0, size_t(cap) * 4, m->stream));
+  t.pool_cap = cap;
+  return VDBM_OK;
+}
+void freeMapPool(MapTable& t)
+{
+  cudaFree(t.leaf_keys); cudaFree(t.leaf_mask); cudaFree(t.leaf_vals); cudaFree(t.leaf_dirty); cudaFree(t.dirty_list);
+}
+
+// make room for `extra` more leaves (pool) and keep the hash load factor <= 0.5
+int ensureMapCapacity(vdbm_map* m, uint64_t extra)
+{
+  const uint64_t need = uint64_t(m->n_leaves) + extra;
+  if (need > m->mt.pool_cap)
+  {
+    uint32_t new_cap = nextPow2(std::max<uint64_t>(need, uint64_t(m->mt.pool_cap) * 2));
+    MapTable nt      = m->mt;
+    int rc           = allocMapPool(m, nt, new_cap);
+    if (rc) return rc;
+    const size_t n = m->n_leaves;
+    if (n)
+    {
+      CU_TRY(m, cudaMemcpyAsync(nt.leaf_keys, m->mt.leaf_keys, n * 8, cudaMemcpyDeviceToDevice, m->stream));
+      CU_TRY(m, cudaMemcpyAsync(nt.leaf_mask, m->mt.leaf_mask, n * 64, cudaMemcpyDeviceToDevice, m->stream));
+      CU_TRY(m, cudaMemcpyAsync(nt.leaf_vals, m->mt.leaf_vals, n * 2048, cudaMemcpyDeviceToDevice, m->stream));
+      CU_TRY(m, cudaMemcpyAsync(nt.leaf_dirty, m->mt.leaf_dirty, n * 4, cudaMemcpyDeviceToDevice, m->stream));
+      CU_TRY(m, cudaMemcpyAsync(nt.dirty_list, m->mt.dirty_list, n * 4, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    freeMapPool(m->mt);
+    m->mt = nt;
+  }
+  if (need * 2 > m->hcap)
+  {
+    uint32_t new_h = nextPow2(need * 4);
+    cudaFree(m->mt.hkeys);
+    cudaFree(m->mt.hvals);
+    int rc = allocMapHash(m, new_h);
+    if (rc) return rc;
+    launchRehashMap(m->mt, m->n_leaves, m->d_ctr, m->stream);
+  }
+  return VDBM_OK;
+}
+
+// D2H of the counter block + map counters, synchronising the stream
+int syncCounters(vdbm_map* m)
+{
+  CU_TRY(m, cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(m->h_small, m->d_map_counters, 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  m->n_leaves = m->h_small[0];
+  const Counters& c      = *m->h_ctr;
+  m->stats.nan_skipped   = m->base.nan_skipped + c.nan_skipped;
+  m->stats.clipped       = m->base.clipped + c.clipped;
+  m->stats.visits        = m->base.visits + c.visits;
+  m->stats.voxel_updates = m->base.voxel_updates + c.voxel_updates;
+  m->stats.state_changes = m->base.state_changes + c.state_changes;
+  m->stats.new_leaves    = m->base.new_leaves + c.new_leaves;
+  m->stats.map_leaves    = m->n_leaves;
+  m->stats.map_capacity  = m->mt.pool_cap;
+  m->stats.gpu_launches  = launchCount();
+  return VDBM_OK;
+}
+
+int readTouched(vdbm_map* m, Source& s)
+{
+  CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s.t.n_touched, 4, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  s.n_touched = m->h_small[8];
+  return VDBM_OK;
+}
+
+Source* findSource(vdbm_map* m, const char* id)
+{
+  if (!id) return nullptr;
+  auto it = m->sources.find(id);
+  return it == m->sources.end() ? nullptr : it->second.get();
+}
+
+// host worldToIndex for the sensor origin (VDBMapping.hpp:612-631), same expression order as the reference
+bool originIndex(double res, const double o[3], int32_t out[3])
+{
+  const double inv = 1.0 / res;
+  for (int k = 0; k < 3; ++k)
+  {
+    double c = o[k];
+    if (std::fmod(c, res)) c = c + (res / 2.0);
+    const double fl = std::floor(c * inv);
+    if (!(std::fabs(fl) < double(kVoxelLimit))) return false;
+    out[k] = int32_t(fl);
+  }
+  return true;
+}
+
+// ---- the raycast (K0 + K1) on device-resident points ---------------------------------------------------
+int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, uint64_t stride, const double origin[3], double range)
+{
+  m->stats.rays += n;
+  m->stats.last_visits = 0;
+  if (n == 0) return VDBM_OK;
+  if (n > 0xFFFFFFF0ull) return fail(m, VDBM_ERR_INVALID_ARG, "more than 2^32 points in one cloud");
+  // VDBMapping.hpp:505-510: a NaN origin skips every point
+  if (std::isnan(origin[0]) || std::isnan(origin[1]) || std::isnan(origin[2]) || std::isinf(origin[0]) || std::isinf(origin[1]) ||
+      std::isinf(origin[2]))
+  {
+    m->base.nan_skipped += n;
+    m->stats.nan_skipped += n;
+    return VDBM_OK;
+  }
+  RaycastArgs a{};
+  a.points = d_points;
+  a.n      = n;
+  a.stride = uint32_t(stride);
+  for (int k = 0; k < 3; ++k) a.origin[k] = origin[k];
+  if (!originIndex(m->params.resolution, origin, a.origin_idx)) return fail(m, VDBM_ERR_COORD_RANGE, "sensor origin outside the +-2^23 voxel range");
+  a.range      = range;
+  a.resolution = m->params.resolution;
+  a.half_res   = m->params.resolution / 2.0;
+  a.inv_res    = 1.0 / m->params.resolution;
+  if (m->rays_cap < n)
+  {
+    cudaFree(m->d_rays);
+    m->d_rays   = nullptr;
+    m->rays_cap = 0;
+    CU_TRY(m, cudaMalloc(&m->d_rays, n * sizeof(RayRec)));
+    m->rays_cap = n;
+  }
+  a.rays = m->d_rays;
+
+  // counters before this attempt (needed if the scan has to be replayed after a hash overflow). Every ABI
+  // call that changes device counters ends with syncCounters(), so the pinned host copy is current.
+  int rc = VDBM_OK;
+  const Counters before = *m->h_ctr;
+  for (int attempt = 0; attempt < 24; ++attempt)
+  {
+    CU_TRY(m, cudaMemsetAsync(&m->d_ctr->ray_cursor, 0, sizeof(unsigned), m->stream));
+    CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+    launchPrepRays(a, m->d_ctr, m->stream);
+    launchRaycastDDA(a, s.t, m->d_ctr, m->dda_grid, m->stream);
+    CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
+    CU_TRY(m, cudaGetLastError());
+    rc = syncCounters(m);
+    if (rc) return rc;
+    rc = readTouched(m, s);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, m->ev0, m->ev1);
+    m->stats.last_accumulate_ms = ms;
+    const uint32_t flags = m->h_ctr->flags;
+    if (flags & kFlagCoordRange)
+    {
+      CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+      m->last_error = "some ray end points were outside the +-2^23 voxel range and were dropped";
+      // not fatal for the rest of the cloud; report it
+      m->stats.last_visits = m->h_ctr->visits - before.visits;
+      m->stats.last_touched_leaves = s.n_touched;
+      return VDBM_ERR_COORD_RANGE;
+    }
+    const bool overflow = (flags & kFlagUpdateOverflow) != 0;
+    const bool crowded  = uint64_t(s.n_touched) * 10 > uint64_t(s.cap) * 7;
+    if (!overflow && !crowded) break;
+    if (s.cap >= (1u << 31)) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "update hash cannot grow further");
+    rc = growUpdateTable(m, s, s.cap * 2);
+    if (rc) return rc;
+    if (!overflow) break; // table was only crowded: content is complete, no replay needed
+    // overflow: some marks were dropped. Restore the counters and replay the scan (marking is an idempotent OR).
+    Counters restored   = before;
+    restored.flags      = 0;
+    restored.ray_cursor = 0;
+    CU_TRY(m, cudaMemcpyAsync(m->d_ctr, &restored, sizeof(Counters), cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+  }
+  m->stats.last_visits         = m->h_ctr->visits - before.visits;
+  m->stats.last_touched_leaves = s.n_touched;
+  m->stats.update_capacity     = std::max(m->stats.update_capacity, s.cap);
+  return VDBM_OK;
+}
+
+int stagePoints(vdbm_map* m, const void* points, uint64_t n, uint64_t stride)
+{
+  const size_t bytes = size_t(n) * stride;
+  if (bytes > m->points_cap)
+  {
+    cudaFree(m->d_points);
+    m->d_points   = nullptr;
+    m->points_cap = 0;
+    CU_TRY(m, cudaMalloc(&m->d_points, bytes));
+    m->points_cap = bytes;
+  }
+  if (bytes) CU_TRY(m, cudaMemcpyAsync(m->d_points, points, bytes, cudaMemcpyHostToDevice, m->stream));
+  return VDBM_OK;
+}
+
+// updateMap for one source (K2). want_change: keep change records on the device.
+int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
+{
+  s.n_change = 0;
+  const uint32_t n = s.n_touched;
+  m->stats.last_touched_leaves += n;
+  if (n == 0) return VDBM_OK; // VDBMapping.hpp:735-738
+  int rc = ensureMapCapacity(m, n);
+  if (rc) return rc;
+  if (want_change && s.change_cap < n)
+  {
+    cudaFree(s.d_change);
+    s.d_change   = nullptr;
+    s.change_cap = 0;
+    CU_TRY(m, cudaMalloc(&s.d_change, size_t(n) * sizeof(LeafRecord)));
+    s.change_cap = n;
+  }
+  CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_change, 0, sizeof(unsigned), m->stream));
+  launchApplyUpdate(s.t, m->mt, m->lo, want_change ? s.d_change : nullptr, want_change ? s.change_cap : 0, m->d_ctr, n, m->stream);
+  CU_TRY(m, cudaMemsetAsync(s.t.n_touched, 0, 4, m->stream));
+  CU_TRY(m, cudaGetLastError());
+  s.n_touched = 0;
+  return VDBM_OK;
+}
+
+// ---- leaf sets ---------------------------------------------------------------------------------------
+void* hostAlloc(size_t bytes, bool pinned)
+{
+  if (bytes == 0) bytes = 8;
+  void* p = nullptr;
+  if (pinned)
+  {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+  }
+  return std::malloc(bytes);
+}
+
+vdbm_leafset* newLeafset(uint64_t n, bool with_valmask, bool with_values)
+{
+  auto* ls   = new vdbm_leafset();
+  ls->n      = n;
+  ls->pinned = (n * (with_values ? 2048 : 128)) >= (1u << 20);
+  ls->origins = static_cast<int32_t*>(hostAlloc(n * 12, ls->pinned));
+  ls->active  = static_cast<uint64_t*>(hostAlloc(n * 64, ls->pinned));
+  if (with_valmask) ls->valmask = static_cast<uint64_t*>(hostAlloc(n * 64, ls->pinned));
+  if (with_values) ls->values = static_cast<float*>(hostAlloc(n * 2048, ls->pinned));
+  return ls;
+}
+
+struct TempBuf
+{
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit TempBuf(cudaStream_t st) : s(st) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 8, s); }
+  ~TempBuf() { if (p) cudaFreeAsync(p, s); }
+  template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+// sort (key, idx) pairs on the device; keys/idx are overwritten with the sorted result
+int sortByKey(vdbm_map* m, uint64_t*& keys, uint32_t*& idx, uint64_t* keys_alt, uint32_t* idx_alt, uint32_t n)
+{
+  if (n == 0) return VDBM_OK;
+  size_t bytes = sortPairs(nullptr, 0, keys, keys_alt, idx, idx_alt, n, m->stream);
+  TempBuf tmp(m->stream);
+  CU_TRY(m, tmp.alloc(bytes));
+  sortPairs(tmp.p, bytes, keys, keys_alt, idx, idx_alt, n, m->stream);
+  CU_TRY(m, cudaGetLastError());
+  std::swap(keys, keys_alt);
+  std::swap(idx, idx_alt);
+  return VDBM_OK;
+}
+
+// export n LeafRecords that live on the device (unsorted) as a sorted bool leaf set
+int recordsToLeafset(vdbm_map* m, const LeafRecord* d_recs, uint32_t n, vdbm_leafset** out)
+{
+  vdbm_leafset* ls = newLeafset(n, true, false);
+  *out             = ls;
+  if (n == 0) return VDBM_OK;
+  // D2H the records, sort on the host by key (records are 136 B; change grids / sections are small)
+  std::vector<LeafRecord> recs(n);
+  CU_TRY(m, cudaMemcpyAsync(recs.data(), d_recs, size_t(n) * sizeof(LeafRecord), cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return recs[a].key < recs[b].key; });
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    const LeafRecord& r = recs[order[i]];
+    unpackLeafOrigin(r.key, ls->origins[3 * i], ls->origins[3 * i + 1], ls->origins[3 * i + 2]);
+    std::memcpy(ls->active + size_t(i) * 8, r.active, 64);
+    std::memcpy(ls->valmask + size_t(i) * 8, r.value, 64);
+  }
+  return VDBM_OK;
+}
+
+} // namespace
+
+// ======================================================================================================
+extern "C" {
+
+int vdbm_abi_version(void) { return VDBM_ABI_VERSION; }
+
+int vdbm_create(const vdbm_params* params, vdbm_map** out)
+{
+  if (!params || !out || !(params->resolution > 0.0)) return VDBM_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+  {
+    std::fprintf(stderr, "vdbm_b200: no CUDA device available; this library has no CPU fallback\n");
+    return VDBM_ERR_CUDA;
+  }
+  auto m    = std::make_unique<vdbm_map>();
+  m->params = *params;
+  if (params->device >= 0)
+  {
+    if (cudaSetDevice(params->device) != cudaSuccess) return VDBM_ERR_CUDA;
+  }
+  cudaGetDevice(&m->device);
+  if (params->stream) m->stream = static_cast<cudaStream_t>(params->stream);
+  else
+  {
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) return VDBM_ERR_CUDA;
+    m->own_stream = true;
+  }
+  vdbm_map* mm = m.get();
+  CU_TRY(mm, cudaEventCreate(&m->ev0));
+  CU_TRY(mm, cudaEventCreate(&m->ev1));
+  CU_TRY(mm, cudaMalloc(&m->d_ctr, sizeof(Counters)));
+  CU_TRY(mm, cudaMemsetAsync(m->d_ctr, 0, sizeof(Counters), m->stream));
+  CU_TRY(mm, cudaHostAlloc(&m->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+  CU_TRY(mm, cudaHostAlloc(&m->h_small, 64 * sizeof(uint32_t), cudaHostAllocDefault));
+  CU_TRY(mm, cudaMalloc(&m->d_map_counters, 8));
+  CU_TRY(mm, cudaMemsetAsync(m->d_map_counters, 0, 8, m->stream));
+  m->mt.n_leaves = m->d_map_counters;
+  m->mt.n_dirty  = m->d_map_counters + 1;
+  const uint32_t pool = nextPow2(params->map_capacity_leaves ? params->map_capacity_leaves : (1u << 19));
+  int rc = allocMapPool(mm, m->mt, pool);
+  if (rc) return rc;
+  rc = allocMapHash(mm, nextPow2(uint64_t(pool) * 2));
+  if (rc) return rc;
+  m->lo.replicate_quirk = params->replicate_probe_quirk ? 1u : 0u;
+  m->dda_grid           = raycastDDAGrid(m->device);
+  CU_TRY(mm, cudaStreamSynchronize(m->stream));
+  *out = m.release();
+  return VDBM_OK;
+}
+
+void vdbm_destroy(vdbm_map* m)
+{
+  if (!m) return;
+  cudaStreamSynchronize(m->stream);
+  for (auto& kv : m->sources)
+  {
+    freeUpdateTable(kv.second->t);
+    cudaFree(kv.second->d_change);
+  }
+  freeMapPool(m->mt);
+  cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
+  cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
+  cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);
+  cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1);
+  if (m->own_stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int vdbm_reset(vdbm_map* m)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  // resetMap V:174-186: new empty map, new empty update grids
+  CU_TRY(m, cudaMemsetAsync(m->mt.hkeys, 0xFF, size_t(m->hcap) * 8, m->stream));
+  CU_TRY(m, cudaMemsetAsync(m->mt.leaf_dirty, 0, size_t(m->mt.pool_cap) * 4, m->stream));
+  CU_TRY(m, cudaMemsetAsync(m->d_map_counters, 0, 8, m->stream));
+  m->n_leaves = 0;
+  for (auto& kv : m->sources)
+  {
+    Source& s = *kv.second;
+    if (s.n_touched) launchClearUpdate(s.t, s.n_touched, m->stream);
+    CU_TRY(m, cudaMemsetAsync(s.t.n_touched, 0, 4, m->stream));
+    s.n_touched = 0;
+    s.n_change  = 0;
+  }
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  m->stats.map_leaves = 0;
+  return VDBM_OK;
+}
+
+int vdbm_set_config(vdbm_map* m, double max_range, double prob_hit, double prob_miss, double prob_thres_min, double prob_thres_max)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  if (max_range < 0.0) return fail(m, VDBM_ERR_BAD_CONFIG, "Max range invalid. Range cannot be negative."); // V:1458-1463
+  m->max_range  = max_range;
+  m->config_set = true; // V:1468 — before the derived checks, like the reference
+  if (prob_miss > 0.5) return fail(m, VDBM_ERR_BAD_CONFIG, "Probability for a miss should be below 0.5"); // O:65-70
+  if (prob_hit < 0.5) return fail(m, VDBM_ERR_BAD_CONFIG, "Probability for a hit should be above 0.5");   // O:71-76
+  // O:79-87, evaluated in double on the host exactly like the reference, then narrowed
+  m->lo.miss      = static_cast<float>(std::log(prob_miss) - std::log(1 - prob_miss));
+  m->lo.hit       = static_cast<float>(std::log(prob_hit) - std::log(1 - prob_hit));
+  m->lo.thres_min = static_cast<float>(std::log(prob_thres_min) - std::log(1 - prob_thres_min));
+  m->lo.thres_max = static_cast<float>(std::log(prob_thres_max) - std::log(1 - prob_thres_max));
+  m->lo.max_lo    = static_cast<float>(std::log(0.99) - std::log(0.01));
+  m->lo.min_lo    = static_cast<float>(std::log(0.01) - std::log(0.99));
+  // OpenVDB InternalNode tile probe of a miss on an (0.0f, inactive) background tile, run with state=true
+  {
+    volatile float pv = 0.0f + m->lo.miss;
+    bool pa           = true;
+    if (pv < m->lo.thres_min)
+    {
+      pa = false;
+      if (pv < m->lo.min_lo) pv = m->lo.min_lo;
+    }
+    m->lo.miss_probe_flips     = pa ? 0u : 1u;
+    m->lo.miss_probe_no_create = (!pa && pv == 0.0f) ? 1u : 0u;
+  }
+  return VDBM_OK;
+}
+
+int vdbm_get_logodds(vdbm_map* m, float* out6)
+{
+  if (!m || !out6) return VDBM_ERR_INVALID_ARG;
+  out6[0] = m->lo.hit; out6[1] = m->lo.miss; out6[2] = m->lo.thres_min; out6[3] = m->lo.thres_max;
+  out6[4] = m->lo.max_lo; out6[5] = m->lo.min_lo;
+  return VDBM_OK;
+}
+
+int vdbm_source_add(vdbm_map* m, const char* source_id, double max_range)
+{
+  if (!m || !source_id) return VDBM_ERR_INVALID_ARG;
+  auto it = m->sources.find(source_id);
+  if (it != m->sources.end())
+  {
+    // the reference overwrites the map entry with a fresh InputSource (V:1374)
+    Source& s = *it->second;
+    if (s.n_touched) launchClearUpdate(s.t, s.n_touched, m->stream);
+    CU_TRY(m, cudaMemsetAsync(s.t.n_touched, 0, 4, m->stream));
+    s.n_touched = 0;
+    s.max_range = (max_range == 0) ? m->max_range : max_range;
+    return VDBM_OK;
+  }
+  auto s       = std::make_unique<Source>();
+  s->id        = source_id;
+  s->max_range = (max_range == 0) ? m->max_range : max_range; // V:1356-1363
+  s->cap       = nextPow2(m->params.update_capacity_leaves ? m->params.update_capacity_leaves : (1u << 20));
+  int rc       = allocUpdateTable(m, s->t, s->cap);
+  if (rc) return rc;
+  m->stats.update_capacity = std::max(m->stats.update_capacity, s->cap);
+  m->sources[source_id]    = std::move(s);
+  return VDBM_OK;
+}
+
+int vdbm_raycast(vdbm_map* m, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3],
+                 double raycast_range)
+{
+  if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
+  int rc = stagePoints(m, points, n, stride_bytes);
+  if (rc) return rc;
+  return raycastDevice(m, *s, m->d_points, n, stride_bytes, origin, raycast_range);
+}
+
+int vdbm_accumulate(vdbm_map* m, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3])
+{
+  if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : "")); // V:320-326
+  if (!(s->max_range > 0)) return VDBM_OK;                                                                             // V:331
+  if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
+  int rc = stagePoints(m, points, n, stride_bytes);
+  if (rc) return rc;
+  return raycastDevice(m, *s, m->d_points, n, stride_bytes, origin, s->max_range);
+}
+
+int vdbm_accumulate_device(vdbm_map* m, const char* source_id, const void* d_points, uint64_t n, uint64_t stride_bytes,
+                           const double origin[3])
+{
+  if (!m || (!d_points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  if (!(s->max_range > 0)) return VDBM_OK;
+  if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
+  return raycastDevice(m, *s, static_cast<const uint8_t*>(d_points), n, stride_bytes, origin, s->max_range);
+}
+
+int vdbm_integrate(vdbm_map* m, int keep_change)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  m->stats.last_touched_leaves = 0;
+  const uint64_t upd_before    = m->stats.voxel_updates;
+  CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+  for (auto& kv : m->sources) // std::map key order, V:380
+  {
+    int rc = updateMapInternal(m, *kv.second, keep_change != 0);
+    if (rc) return rc;
+    if (m->sources.size() > 1 || keep_change)
+    {
+      // the next source's capacity check needs the new leaf count; change export needs n_change
+      rc = syncCounters(m);
+      if (rc) return rc;
+      kv.second->n_change = std::min(m->h_ctr->n_change, kv.second->change_cap);
+    }
+  }
+  CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, m->ev0, m->ev1);
+  m->stats.last_integrate_ms  = ms;
+  m->stats.last_voxel_updates = m->stats.voxel_updates - upd_before;
+  if (m->h_ctr->flags & kFlagMapOverflow) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "map hash / leaf pool overflow");
+  return VDBM_OK;
+}
+
+int vdbm_insert(vdbm_map* m, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3])
+{
+  // insertPointCloud V:399-406: accumulateUpdate (whatever it does) then integrateUpdate
+  int rc_acc = vdbm_accumulate(m, source_id, points, n, stride_bytes, origin);
+  if (rc_acc == VDBM_ERR_INVALID_ARG || rc_acc == VDBM_ERR_CUDA || rc_acc == VDBM_ERR_OUT_OF_MEMORY) return rc_acc;
+  int rc_int = vdbm_integrate(m, 0);
+  return rc_int ? rc_int : rc_acc;
+}
+
+int vdbm_update_map(vdbm_map* m, const char* source_id, vdbm_leafset** change)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  m->stats.last_touched_leaves = 0;
+  const uint64_t upd_before    = m->stats.voxel_updates;
+  CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+  int rc = updateMapInternal(m, *s, change != nullptr);
+  if (rc) return rc;
+  CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
+  rc = syncCounters(m);
+  if (rc) return rc;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, m->ev0, m->ev1);
+  m->stats.last_integrate_ms  = ms;
+  m->stats.last_voxel_updates = m->stats.voxel_updates - upd_before;
+  if (m->h_ctr->flags & kFlagMapOverflow) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "map hash / leaf pool overflow");
+  if (change)
+  {
+    s->n_change = std::min(m->h_ctr->n_change, s->change_cap);
+    return recordsToLeafset(m, s->d_change, s->n_change, change);
+  }
+  return VDBM_OK;
+}
+
+int vdbm_change_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
+{
+  if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  return recordsToLeafset(m, s->d_change, s->n_change, out);
+}
+
+int vdbm_update_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
+{
+  if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  const uint32_t n = s->n_touched;
+  vdbm_leafset* ls = newLeafset(n, true, false);
+  *out             = ls;
+  if (n == 0) return VDBM_OK;
+  TempBuf k0(m->stream), k1(m->stream), i0(m->stream), i1(m->stream), recs(m->stream), so(m->stream), sa(m->stream), sv(m->stream);
+  CU_TRY(m, k0.alloc(size_t(n) * 8)); CU_TRY(m, k1.alloc(size_t(n) * 8));
+  CU_TRY(m, i0.alloc(size_t(n) * 4)); CU_TRY(m, i1.alloc(size_t(n) * 4));
+  CU_TRY(m, recs.alloc(size_t(n) * sizeof(LeafRecord)));
+  CU_TRY(m, so.alloc(size_t(n) * 12)); CU_TRY(m, sa.alloc(size_t(n) * 64)); CU_TRY(m, sv.alloc(size_t(n) * 64));
+  uint64_t* keys = k0.as<uint64_t>();
+  uint32_t* idx  = i0.as<uint32_t>();
+  launchKeysFromSlots(s->t.keys, s->t.touched, n, keys, idx, m->stream);
+  int rc = sortByKey(m, keys, idx, k1.as<uint64_t>(), i1.as<uint32_t>(), n);
+  if (rc) return rc;
+  launchGatherUpdate(s->t, n, idx, recs.as<LeafRecord>(), m->stream);
+  launchSplitRecords(recs.as<LeafRecord>(), n, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<uint64_t>(), m->stream);
+  CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(ls->active, sa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(ls->valmask, sv.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  return VDBM_OK;
+}
+
+int vdbm_update_import(vdbm_map* m, const char* source_id, uint64_t n, const int32_t* origins, const uint64_t* active, const uint64_t* value)
+{
+  if (!m || (n && (!origins || !active || !value))) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  if (n == 0) return VDBM_OK;
+  std::vector<LeafRecord> recs(n);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    for (int k = 0; k < 3; ++k)
+      if (std::abs(int64_t(origins[3 * i + k])) >= kVoxelLimit) return fail(m, VDBM_ERR_COORD_RANGE, "leaf origin outside the +-2^23 voxel range");
+    recs[i].key = packLeafKey(origins[3 * i] >> 3, origins[3 * i + 1] >> 3, origins[3 * i + 2] >> 3);
+    std::memcpy(recs[i].active, active + 8 * i, 64);
+    std::memcpy(recs[i].value, value + 8 * i, 64);
+  }
+  TempBuf d(m->stream);
+  CU_TRY(m, d.alloc(n * sizeof(LeafRecord)));
+  CU_TRY(m, cudaMemcpyAsync(d.p, recs.data(), n * sizeof(LeafRecord), cudaMemcpyHostToDevice, m->stream));
+  int rc = vdbm_update_import_device(m, source_id, d.p, n);
+  return rc;
+}
+
+int vdbm_update_import_device(vdbm_map* m, const char* source_id, const void* d_records, uint64_t n)
+{
+  if (!m || (n && !d_records)) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  if (n == 0) return VDBM_OK;
+  // make sure the table can take n more leaves at load factor <= 0.7 (worst case: all new)
+  while ((uint64_t(s->n_touched) + n) * 10 > uint64_t(s->cap) * 7)
+  {
+    if (s->cap >= (1u << 31)) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "update hash cannot grow further");
+    int rc = growUpdateTable(m, *s, s->cap * 2);
+    if (rc) return rc;
+  }
+  launchImportUpdate(s->t, static_cast<const LeafRecord*>(d_records), n, m->d_ctr, m->stream);
+  CU_TRY(m, cudaGetLastError());
+  int rc = readTouched(m, *s);
+  if (rc) return rc;
+  m->stats.last_touched_leaves = s->n_touched;
+  m->stats.update_capacity     = std::max(m->stats.update_capacity, s->cap);
+  return VDBM_OK;
+}
+
+int vdbm_map_export(vdbm_map* m, int dirty_only, vdbm_leafset** out)
+{
+  if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  const uint32_t n_dirty = m->h_small[1];
+  const uint32_t n       = dirty_only ? n_dirty : m->n_leaves;
+  vdbm_leafset* ls       = newLeafset(n, false, true);
+  *out                   = ls;
+  if (n)
+  {
+    TempBuf k0(m->stream), k1(m->stream), i0(m->stream), i1(m->stream), so(m->stream), sa(m->stream), sv(m->stream);
+    CU_TRY(m, k0.alloc(size_t(n) * 8)); CU_TRY(m, k1.alloc(size_t(n) * 8));
+    CU_TRY(m, i0.alloc(size_t(n) * 4)); CU_TRY(m, i1.alloc(size_t(n) * 4));
+    CU_TRY(m, so.alloc(size_t(n) * 12)); CU_TRY(m, sa.alloc(size_t(n) * 64)); CU_TRY(m, sv.alloc(size_t(n) * 2048));
+    uint64_t* keys = k0.as<uint64_t>();
+    uint32_t* idx  = i0.as<uint32_t>();
+    launchKeysFromSlots(m->mt.leaf_keys, dirty_only ? m->mt.dirty_list : nullptr, n, keys, idx, m->stream);
+    rc = sortByKey(m, keys, idx, k1.as<uint64_t>(), i1.as<uint32_t>(), n);
+    if (rc) return rc;
+    launchGatherMap(m->mt, n, idx, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<float>(), 0, m->stream);
+    CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(ls->active, sa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(ls->values, sv.p, size_t(n) * 2048, cudaMemcpyDeviceToHost, m->stream));
+  }
+  // every export (full or dirty) leaves the dirty list empty: the host mirror is now up to date
+  if (n_dirty)
+  {
+    CU_TRY(m, cudaMemsetAsync(m->mt.leaf_dirty, 0, size_t(m->mt.pool_cap) * 4, m->stream));
+    CU_TRY(m, cudaMemsetAsync(m->mt.n_dirty, 0, 4, m->stream));
+  }
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  return VDBM_OK;
+}
+
+int vdbm_section(vdbm_map* m, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float, vdbm_leafset** out)
+{
+  if (!m || !out || !bbmin || !bbmax) return VDBM_ERR_INVALID_ARG;
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  // upper bound of result leaves: leaves overlapping the box (clamped to the map size)
+  uint64_t box_leaves = 1;
+  for (int k = 0; k < 3; ++k)
+  {
+    if (bbmax[k] < bbmin[k]) { box_leaves = 0; break; }
+    const uint64_t span = uint64_t((int64_t(bbmax[k]) >> 3) - (int64_t(bbmin[k]) >> 3) + 1);
+    box_leaves          = std::min<uint64_t>(box_leaves * span, m->n_leaves);
+  }
+  const uint32_t cap = uint32_t(std::min<uint64_t>(box_leaves, m->n_leaves));
+  if (cap == 0)
+  {
+    *out = newLeafset(0, !result_float, result_float != 0);
+    return VDBM_OK;
+  }
+  TempBuf dk(m->stream), da(m->stream), dv(m->stream), df(m->stream);
+  CU_TRY(m, dk.alloc(size_t(cap) * 8));
+  CU_TRY(m, da.alloc(size_t(cap) * 64));
+  if (result_float) CU_TRY(m, df.alloc(size_t(cap) * 2048));
+  else CU_TRY(m, dv.alloc(size_t(cap) * 64));
+  CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_out, 0, sizeof(unsigned), m->stream));
+  launchSection(m->mt, m->n_leaves, bbmin, bbmax, full, result_float, dk.as<uint64_t>(), da.as<uint64_t>(), dv.as<uint64_t>(),
+                df.as<float>(), cap, m->d_ctr, m->stream);
+  CU_TRY(m, cudaGetLastError());
+  rc = syncCounters(m);
+  if (rc) return rc;
+  const uint32_t n = std::min(m->h_ctr->n_out, cap);
+  vdbm_leafset* ls = newLeafset(n, !result_float, result_float != 0);
+  *out             = ls;
+  if (n == 0) return VDBM_OK;
+  // small result: sort on the host by key
+  std::vector<uint64_t> keys(n);
+  std::vector<uint64_t> act(size_t(n) * 8), vm;
+  std::vector<float> vals;
+  CU_TRY(m, cudaMemcpyAsync(keys.data(), dk.p, size_t(n) * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(act.data(), da.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+  if (result_float)
+  {
+    vals.resize(size_t(n) * 512);
+    CU_TRY(m, cudaMemcpyAsync(vals.data(), df.p, size_t(n) * 2048, cudaMemcpyDeviceToHost, m->stream));
+  }
+  else
+  {
+    vm.resize(size_t(n) * 8);
+    CU_TRY(m, cudaMemcpyAsync(vm.data(), dv.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+  }
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    const uint32_t j = order[i];
+    unpackLeafOrigin(keys[j], ls->origins[3 * i], ls->origins[3 * i + 1], ls->origins[3 * i + 2]);
+    std::memcpy(ls->active + size_t(i) * 8, act.data() + size_t(j) * 8, 64);
+    if (result_float) std::memcpy(ls->values + size_t(i) * 512, vals.data() + size_t(j) * 512, 2048);
+    else std::memcpy(ls->valmask + size_t(i) * 8, vm.data() + size_t(j) * 8, 64);
+  }
+  return VDBM_OK;
+}
+
+int vdbm_probe(vdbm_map* m, const int32_t xyz[3], float* value, int32_t* active)
+{
+  if (!m || !xyz || !value || !active) return VDBM_ERR_INVALID_ARG;
+  TempBuf d(m->stream);
+  CU_TRY(m, d.alloc(16));
+  launchProbe(m->mt, xyz[0], xyz[1], xyz[2], d.as<float>(), reinterpret_cast<int32_t*>(d.as<float>() + 1), m->stream);
+  CU_TRY(m, cudaMemcpyAsync(m->h_small + 16, d.p, 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  std::memcpy(value, m->h_small + 16, 4);
+  *active = int32_t(m->h_small[17]);
+  return VDBM_OK;
+}
+
+uint64_t vdbm_leafset_size(const vdbm_leafset* s) { return s ? s->n : 0; }
+const int32_t* vdbm_leafset_origins(const vdbm_leafset* s) { return s ? s->origins : nullptr; }
+const uint64_t* vdbm_leafset_active(const vdbm_leafset* s) { return s ? s->active : nullptr; }
+const uint64_t* vdbm_leafset_valmask(const vdbm_leafset* s) { return s ? s->valmask : nullptr; }
+const float* vdbm_leafset_values(const vdbm_leafset* s) { return s ? s->values : nullptr; }
+void vdbm_leafset_free(vdbm_leafset* s)
+{
+  if (!s) return;
+  auto rel = [&](void* p) {
+    if (!p) return;
+    if (s->pinned) cudaFreeHost(p);
+    else std::free(p);
+  };
+  rel(s->origins); rel(s->active); rel(s->valmask); rel(s->values);
+  delete s;
+}
+
+int32_t vdbm_leaf_owner(const int32_t origin[3], int32_t n_ranks)
+{
+  if (!origin || n_ranks <= 0) return -1;
+  return leafOwner(packLeafKey(origin[0] >> 3, origin[1] >> 3, origin[2] >> 3), n_ranks);
+}
+
+int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, uint64_t* counts, const void** d_records)
+{
+  if (!m || !counts || !d_records || n_ranks <= 0 || n_ranks > 32) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  const uint32_t n = s->n_touched;
+  for (int r = 0; r < n_ranks; ++r) counts[r] = 0;
+  *d_records = m->d_part;
+  if (n == 0) return VDBM_OK;
+  if (m->part_cap < n)
+  {
+    cudaFree(m->d_part);
+    m->d_part   = nullptr;
+    m->part_cap = 0;
+    CU_TRY(m, cudaMalloc(&m->d_part, size_t(n) * sizeof(LeafRecord)));
+    m->part_cap = n;
+  }
+  *d_records = m->d_part;
+  TempBuf d(m->stream);
+  CU_TRY(m, d.alloc(64 * 4));
+  uint32_t* d_counts = d.as<uint32_t>();
+  uint32_t* d_cursor = d_counts + 32;
+  CU_TRY(m, cudaMemsetAsync(d_counts, 0, 64 * 4, m->stream));
+  launchPartition(s->t, n, n_ranks, d_counts, d_cursor, m->d_part, 0, m->stream);
+  CU_TRY(m, cudaMemcpyAsync(m->h_small + 24, d_counts, 32 * 4, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  uint32_t off[32];
+  uint32_t acc = 0;
+  for (int r = 0; r < 32; ++r)
+  {
+    off[r] = acc;
+    if (r < n_ranks)
+    {
+      counts[r] = m->h_small[24 + r];
+      acc += m->h_small[24 + r];
+    }
+  }
+  CU_TRY(m, cudaMemcpyAsync(d_cursor, off, 32 * 4, cudaMemcpyHostToDevice, m->stream));
+  launchPartition(s->t, n, n_ranks, d_counts, d_cursor, m->d_part, 1, m->stream);
+  CU_TRY(m, cudaMemsetAsync(s->t.n_touched, 0, 4, m->stream));
+  CU_TRY(m, cudaGetLastError());
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  s->n_touched = 0;
+  return VDBM_OK;
+}
+
+int vdbm_stats(vdbm_map* m, vdbm_stats_t* out)
+{
+  if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  m->stats.gpu_launches = launchCount();
+  *out                  = m->stats;
+  return VDBM_OK;
+}
+
+const char* vdbm_last_error(vdbm_map* m) { return m ? m->last_error.c_str() : "null handle"; }
+
+int vdbm_synchronize(vdbm_map* m)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  return VDBM_OK;
+}
+
+void* vdbm_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void vdbm_host_free(void* p)
+{
+  if (p) cudaFreeHost(p);
+}
+
+} // extern "C"

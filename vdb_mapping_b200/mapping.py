@@ -1,0 +1,243 @@
+"""Host-side Python mirror of the reference's OccupancyVDBMapping interface for the scan-integration
+path, over the C ABI of libvdbm_b200.so (include/vdbm_b200.h).
+
+Method names, argument meaning and error behaviour follow
+/root/reference/include/vdb_mapping/VDBMapping.hpp (insertPointCloud :399, accumulateUpdate :316,
+integrateUpdate :375, updateMap :731, getGrid :799, getMapSection* :883-960, addInputSource :1352,
+resetMap :174) and OccupancyVDBMapping.hpp (setConfig :59). Grids come back as LeafSet records
+(leaf origin + OpenVDB-layout masks / values) instead of openvdb::Grid objects; the C++ shim in
+include/vdb_mapping/ turns the same records into real grids.
+
+There is no CPU path here: everything is executed by the CUDA kernels behind the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass
+class LeafSet:
+    """Leaves sorted by origin (x, y, z). Layout as in OpenVDB: offset n=(x&7)<<6|(y&7)<<3|(z&7)."""
+    origins: np.ndarray          # (n, 3) int32
+    active: np.ndarray           # (n, 8) uint64
+    valmask: np.ndarray | None   # (n, 8) uint64 (bool grids)
+    values: np.ndarray | None    # (n, 512) float32 (float grids)
+
+    def __len__(self):
+        return int(self.origins.shape[0])
+
+
+class VdbmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vdbm status {code}: {msg}")
+        self.code = code
+
+
+def _pts16(points) -> np.ndarray:
+    p = np.asarray(points, dtype=np.float32)
+    if p.ndim != 2 or p.shape[1] not in (3, 4):
+        raise ValueError("points must be (n,3) or (n,4) float32")
+    if p.shape[1] == 3:
+        q = np.ones((p.shape[0], 4), dtype=np.float32)
+        q[:, :3] = p
+        p = q
+    return np.ascontiguousarray(p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class OccupancyVDBMapping:
+    """vdb_mapping::OccupancyVDBMapping on one B200 (device-resident map, CUDA kernels)."""
+
+    def __init__(self, resolution: float, device: int = -1, replicate_probe_quirk: bool = True,
+                 update_capacity_leaves: int = 0, map_capacity_leaves: int = 0, stream: int | None = None):
+        self._L = L.lib()
+        self.resolution = float(resolution)
+        p = L.VdbmParams(float(resolution), int(device), int(replicate_probe_quirk), int(update_capacity_leaves),
+                         int(map_capacity_leaves), C.c_void_p(stream) if stream else None)
+        h = C.c_void_p()
+        rc = self._L.vdbm_create(C.byref(p), C.byref(h))
+        if rc != L.VDBM_OK:
+            raise VdbmError(rc, "vdbm_create failed (CUDA device required; there is no CPU fallback)")
+        self._h = h
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.vdbm_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def _err(self) -> str:
+        return (self._L.vdbm_last_error(self._h) or b"").decode()
+
+    def _check(self, rc, allow=()):
+        if rc != L.VDBM_OK and rc not in allow:
+            raise VdbmError(rc, self._err())
+        return rc
+
+    def _take(self, ls_ptr, is_float: bool) -> LeafSet:
+        n = int(self._L.vdbm_leafset_size(ls_ptr))
+        try:
+            origins = np.ctypeslib.as_array(self._L.vdbm_leafset_origins(ls_ptr), shape=(n, 3)).copy() if n else np.zeros((0, 3), np.int32)
+            active = np.ctypeslib.as_array(self._L.vdbm_leafset_active(ls_ptr), shape=(n, 8)).copy() if n else np.zeros((0, 8), np.uint64)
+            valmask = values = None
+            if is_float:
+                values = np.ctypeslib.as_array(self._L.vdbm_leafset_values(ls_ptr), shape=(n, 512)).copy() if n else np.zeros((0, 512), np.float32)
+            else:
+                valmask = np.ctypeslib.as_array(self._L.vdbm_leafset_valmask(ls_ptr), shape=(n, 8)).copy() if n else np.zeros((0, 8), np.uint64)
+        finally:
+            self._L.vdbm_leafset_free(ls_ptr)
+        return LeafSet(origins, active, valmask, values)
+
+    # ---- reference surface ---------------------------------------------------------------------------
+    def setConfig(self, max_range, prob_hit, prob_miss, prob_thres_min, prob_thres_max) -> int:
+        """0 ok; 1 rejected by the base class (max_range < 0); 2 rejected by the occupancy checks."""
+        rc = self._L.vdbm_set_config(self._h, max_range, prob_hit, prob_miss, prob_thres_min, prob_thres_max)
+        if rc == L.VDBM_ERR_BAD_CONFIG:
+            return 1 if max_range < 0 else 2
+        self._check(rc)
+        return 0
+
+    def logodds(self) -> np.ndarray:
+        out = np.zeros(6, dtype=np.float32)
+        self._check(self._L.vdbm_get_logodds(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def addInputSource(self, source_id: str, max_range: float, max_rate: float = 0.0):
+        self._check(self._L.vdbm_source_add(self._h, source_id.encode(), float(max_range)))
+
+    def resetMap(self):
+        self._check(self._L.vdbm_reset(self._h))
+
+    def accumulateUpdate(self, points, origin, source_id: str) -> int:
+        """Returns 0 ok, 1 unknown source (no-op, like the reference's print+return), 2 not configured."""
+        p = _pts16(points)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        rc = self._L.vdbm_accumulate(self._h, source_id.encode(), p.ctypes.data, p.shape[0], 16, _dp(o))
+        if rc == L.VDBM_ERR_UNKNOWN_SOURCE:
+            return 1
+        if rc == L.VDBM_ERR_NOT_CONFIGURED:
+            return 2
+        self._check(rc)
+        return 0
+
+    def accumulateRaw(self, ptr: int, n: int, origin, source_id: str, on_device: bool = False, stride: int = 16):
+        """accumulateUpdate on a raw pointer (pinned host or device memory); used by bench.py."""
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        f = self._L.vdbm_accumulate_device if on_device else self._L.vdbm_accumulate
+        self._check(f(self._h, source_id.encode(), C.c_void_p(ptr), n, stride, _dp(o)))
+
+    def raycastPointCloud(self, points, origin, raycast_range: float, source_id: str) -> bool:
+        p = _pts16(points)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        rc = self._L.vdbm_raycast(self._h, source_id.encode(), p.ctypes.data, p.shape[0], 16, _dp(o), float(raycast_range))
+        if rc == L.VDBM_ERR_NOT_CONFIGURED:
+            return False
+        self._check(rc)
+        return True
+
+    def integrateUpdate(self, keep_change: bool = True):
+        self._check(self._L.vdbm_integrate(self._h, int(keep_change)))
+
+    def insertPointCloud(self, points, origin, source_id: str) -> bool:
+        p = _pts16(points)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        rc = self._L.vdbm_insert(self._h, source_id.encode(), p.ctypes.data, p.shape[0], 16, _dp(o))
+        self._check(rc, allow=(L.VDBM_ERR_UNKNOWN_SOURCE, L.VDBM_ERR_NOT_CONFIGURED))
+        return True  # VDBMapping.hpp:405 always returns true
+
+    def insertRaw(self, ptr: int, n: int, origin, source_id: str, stride: int = 16):
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._check(self._L.vdbm_insert(self._h, source_id.encode(), C.c_void_p(ptr), n, stride, _dp(o)))
+
+    def updateMap(self, source_id: str) -> LeafSet:
+        """updateMap(source's accumulated update grid) -> change grid."""
+        out = C.c_void_p()
+        self._check(self._L.vdbm_update_map(self._h, source_id.encode(), C.byref(out)))
+        return self._take(out, False)
+
+    def exportUpdateGrid(self, source_id: str) -> LeafSet:
+        out = C.c_void_p()
+        self._check(self._L.vdbm_update_export(self._h, source_id.encode(), C.byref(out)))
+        return self._take(out, False)
+
+    def exportLastChange(self, source_id: str) -> LeafSet:
+        out = C.c_void_p()
+        self._check(self._L.vdbm_change_export(self._h, source_id.encode(), C.byref(out)))
+        return self._take(out, False)
+
+    def importUpdate(self, source_id: str, origins, active, valmask):
+        o = np.ascontiguousarray(origins, dtype=np.int32)
+        a = np.ascontiguousarray(active, dtype=np.uint64)
+        v = np.ascontiguousarray(valmask, dtype=np.uint64)
+        self._check(self._L.vdbm_update_import(self._h, source_id.encode(), o.shape[0],
+                                               o.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               a.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               v.ctypes.data_as(C.POINTER(C.c_uint64))))
+
+    def exportMap(self, dirty_only: bool = False) -> LeafSet:
+        """getGrid(): the map's leaves (values + active masks)."""
+        out = C.c_void_p()
+        self._check(self._L.vdbm_map_export(self._h, int(dirty_only), C.byref(out)))
+        return self._take(out, True)
+
+    def _section(self, bbmin, bbmax, full, result_float) -> LeafSet:
+        mn = np.ascontiguousarray(bbmin, dtype=np.int32)
+        mx = np.ascontiguousarray(bbmax, dtype=np.int32)
+        out = C.c_void_p()
+        i32p = C.POINTER(C.c_int32)
+        self._check(self._L.vdbm_section(self._h, mn.ctypes.data_as(i32p), mx.ctypes.data_as(i32p), int(full),
+                                         int(result_float), C.byref(out)))
+        return self._take(out, bool(result_float))
+
+    def getMapSectionUpdateGrid(self, bbmin, bbmax, full=False) -> LeafSet:
+        return self._section(bbmin, bbmax, full, 0)
+
+    def getMapSectionGrid(self, bbmin, bbmax, full=False) -> LeafSet:
+        return self._section(bbmin, bbmax, full, 1)
+
+    def probe(self, coord):
+        c = np.ascontiguousarray(coord, dtype=np.int32)
+        v, a = C.c_float(0), C.c_int32(0)
+        self._check(self._L.vdbm_probe(self._h, c.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(v), C.byref(a)))
+        return float(np.float32(v.value)), bool(a.value)
+
+    def stats(self) -> dict:
+        s = L.VdbmStats()
+        self._check(self._L.vdbm_stats(self._h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in L.VdbmStats._fields_ if n != "reserved"}
+
+    def mapLeafCount(self) -> int:
+        return int(self.stats()["map_leaves"])
+
+    def synchronize(self):
+        self._check(self._L.vdbm_synchronize(self._h))
+
+    # ---- multi-GPU plumbing (see dist.py) -------------------------------------------------------------
+    def partitionUpdate(self, source_id: str, n_ranks: int):
+        counts = np.zeros(n_ranks, dtype=np.uint64)
+        ptr = C.c_void_p()
+        self._check(self._L.vdbm_update_partition(self._h, source_id.encode(), n_ranks,
+                                                  counts.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(ptr)))
+        return counts, (ptr.value or 0)
+
+    def importUpdateDevice(self, source_id: str, ptr: int, n: int):
+        self._check(self._L.vdbm_update_import_device(self._h, source_id.encode(), C.c_void_p(ptr), int(n)))
+
+
+def leaf_owner(origin, n_ranks: int) -> int:
+    o = np.ascontiguousarray(origin, dtype=np.int32)
+    return int(L.lib().vdbm_leaf_owner(o.ctypes.data_as(C.POINTER(C.c_int32)), n_ranks))
