@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — scan-integration throughput of the B200-native vdb_mapping hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg4]
+
+A "step" is one insertPointCloud (raycast into the update grid + updateMap) of one synthetic scan of the
+BASELINE.json config (default configs[1]: Ouster OS1-128-style 262,144-point scan, 0.05 m voxels, 30 m range,
+moving-sensor sequence). With N > 1 every rank owns one LiDAR of a merged multi-LiDAR rig (N x 262,144 points per
+step, weak scaling), rays stay rank-local, the map is sharded by leaf key and update leaves are exchanged with an
+NCCL all-to-all. Rank 0 prints ONE JSON line.
+
+Legs of the default (--impl ours) arm:
+  value : scans already resident in HBM, vdbm_accumulate_device + vdbm_integrate per step
+  e2e   : the public call (vdbm_insert) on PINNED HOST buffers: H2D of the cloud and D2H of the per-step counters
+          inside the timed region
+  cpu_baseline : the CPU oracle (restated reference, OpenVDB-free, 1 thread like the reference's serial path) on the
+          first scans of the same sequence (rank 0, N == 1 only)
+--impl reference times that CPU path alone, each step on a bounded sample of the scan.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vdb_mapping_b200 import scans  # noqa: E402
+
+REF_SAMPLE_STRIDE = 8  # reference arm: one contiguous 1/8 azimuth sector of the scan per step
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_cfg(name: str) -> int:
+    return {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4}[name]
+
+
+def alg_bytes(n_pts: int, leaves: int, change: bool = False) -> int:
+    """SURVEY.md 8(d) / BASELINE.md 4: 16 B per point + per touched leaf: update masks written+read (256 B),
+    map leaf values+mask read and written (4224 B) [+128 B change masks]."""
+    return 16 * n_pts + (4608 if change else 4480) * leaves
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the reference's own algorithm (oracle port; the reference itself needs OpenVDB and cannot be built
+    here) on the host cores. The reference's scan-integration path is serial per input source (VDBMapping.hpp:499,
+    561,764 — no TBB call anywhere), so 'all the host threads it can use' is 1."""
+    if rank != 0:
+        return
+    from oracle.oracle import OracleOccupancyVDBMapping
+    cfg = workload_cfg(args.workload)
+    c = scans.CONFIGS[cfg]
+    m = OracleOccupancyVDBMapping(c.resolution)
+    m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+    m.addInputSource("s", c.max_range)
+    stride = REF_SAMPLE_STRIDE
+    clouds = []
+    for k in range(args.warmup + args.steps):
+        pts, origin = scans.make_scan(cfg, k)
+        # a CONTIGUOUS 1/stride sector of the scan (azimuth-major order), rotating with k: neighbouring rays stay
+        # neighbours, so the per-ray cost (voxel dedup ratio, cache behaviour) is that of the full scan
+        per = pts.shape[0] // stride
+        lo = (k % stride) * per
+        pts = np.ascontiguousarray(pts[lo:lo + per])
+        clouds.append((pts, origin))
+    for k in range(args.warmup):
+        m.insertPointCloud(*clouds[k], "s")
+    s0 = m.stats()
+    t0 = time.perf_counter()
+    rays = 0
+    for k in range(args.warmup, args.warmup + args.steps):
+        m.insertPointCloud(*clouds[k], "s")
+        rays += clouds[k][0].shape[0]
+    dt = time.perf_counter() - t0
+    s1 = m.stats()
+    value = rays / dt
+    sample = f"a contiguous 1/{stride} azimuth sector of each scan ({clouds[0][0].shape[0]} of {c.n_points} rays per step, sector rotates with the step), full pipeline"
+    line = {
+        "impl": "reference", "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 DDA + f32 log-odds", "data": "synthetic",
+        "config": {"workload": c.name, "description": c.description, "resolution_m": c.resolution, "max_range_m": c.max_range,
+                   "points_per_scan": c.n_points, "sample": sample},
+        "voxel_updates_per_sec": (s1["voxel_updates"] - s0["voxel_updates"]) / dt,
+        "visits_per_sec": (s1["visits"] - s0["visits"]) / dt,
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "restated reference (OpenVDB-free oracle, tree+accessor cost model); the reference path is "
+                                 "single-threaded per input source; host has %d logical cores" % (os.cpu_count() or 0)},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(cfg: int, n_scans: int):
+    from oracle.oracle import OracleOccupancyVDBMapping
+    c = scans.CONFIGS[cfg]
+    m = OracleOccupancyVDBMapping(c.resolution)
+    m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+    m.addInputSource("s", c.max_range)
+    clouds = [scans.make_scan(cfg, k) for k in range(n_scans)]
+    t0 = time.perf_counter()
+    for pts, origin in clouds:
+        m.insertPointCloud(pts, origin, "s")
+    dt = time.perf_counter() - t0
+    st = m.stats()
+    return {"value": n_scans * c.n_points / dt, "unit": "rays/s", "cores": 1, "kind": "port",
+            "sample": f"first {n_scans} full scans of the same sequence ({dt:.1f} s of CPU work)",
+            "ms_per_scan": 1e3 * dt / n_scans, "voxel_updates_per_sec": st["voxel_updates"] / dt,
+            "visits_per_sec": st["visits"] / dt, "host_logical_cores": os.cpu_count(),
+            "note": "restated reference (OpenVDB-free oracle); serial like the reference's per-source path"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from vdb_mapping_b200 import dist as vdist
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = workload_cfg(args.workload)
+    c = scans.CONFIGS[cfg]
+    n_steps = args.warmup + args.steps
+    strong = (args.scaling == "strong") and world > 1
+
+    # ---- synthetic input: scan k of the sequence; with N > 1 rank r owns LiDAR r of the merged rig ----
+    clouds = []
+    for k in range(n_steps):
+        if strong:
+            pts, origin = scans.make_scan(cfg, k)
+            lo, hi = vdist.split_points(pts.shape[0], rank, world)
+            pts = np.ascontiguousarray(pts[lo:hi])
+        else:
+            pts, origin = scans.make_scan(cfg, k, sensor=rank) if cfg == 2 else scans.make_scan(cfg, k + 1000 * rank)
+        clouds.append((pts, origin))
+    n_pts = clouds[0][0].shape[0]
+    pinned = [torch.from_numpy(p).pin_memory() for p, _ in clouds]
+    resident = [t.to(dev, non_blocking=True) for t in pinned]
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    sampler = ClockSampler(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_leg(e2e: bool):
+        """W warm-up + K timed steps on a fresh map. Returns dict with device time (CUDA events on the launching
+        stream), counters and per-kernel times."""
+        with torch.cuda.stream(stream):
+            m = OccupancyVDBMapping(c.resolution, device=local_rank, stream=stream.cuda_stream)
+            m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+            m.addInputSource("s", c.max_range)
+            eng = vdist.CudaEngine(m, "s")
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            acc_ms, prep_ms, int_ms, leaves = [], [], [], []
+            sent = recv = 0
+            st0 = None
+            for k in range(n_steps):
+                if k == args.warmup:
+                    barrier()
+                    st0 = m.stats()
+                    launches0 = st0["gpu_launches"]
+                    if not e2e:
+                        sampler.start()
+                    t_wall0 = time.perf_counter()
+                    ev0.record(stream)
+                origin = clouds[k][1]
+                if e2e:
+                    eng.accumulate_raw(pinned[k].data_ptr(), n_pts, origin, on_device=False)
+                else:
+                    eng.accumulate_raw(resident[k].data_ptr(), n_pts, origin, on_device=True)
+                if k >= args.warmup:
+                    s = m.stats()
+                    acc_ms.append(s["last_accumulate_ms"]); prep_ms.append(s["last_prep_ms"]); leaves.append(s["last_touched_leaves"])
+                a, b = vdist.exchange_and_integrate(eng, world, dist if world > 1 else None)
+                if k >= args.warmup:
+                    sent += a; recv += b
+                    int_ms.append(m.stats()["last_integrate_ms"])
+            ev1.record(stream)
+            barrier()
+            t_wall = time.perf_counter() - t_wall0
+            clocks = sampler.stop() if not e2e else None
+            st1 = m.stats()
+            ms = ev0.elapsed_time(ev1)
+            out = {"ms": ms, "wall_ms": 1e3 * t_wall, "clocks": clocks,
+                   "rays": st1["rays"] - st0["rays"], "voxel_updates": st1["voxel_updates"] - st0["voxel_updates"],
+                   "visits": st1["visits"] - st0["visits"], "launches": st1["gpu_launches"] - launches0,
+                   "acc_ms": acc_ms, "prep_ms": prep_ms, "int_ms": int_ms, "leaves": leaves, "map_leaves": st1["map_leaves"],
+                   "sent": sent, "recv": recv}
+            m.close()
+            return out
+
+    res_v = run_leg(e2e=False)
+    res_e = run_leg(e2e=True)
+
+    # ---- max over ranks of the device time; totals over ranks ----
+    def reduce(vals, op):
+        if world == 1:
+            return vals
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return t.tolist()
+
+    ms_v, ms_e = reduce([res_v["ms"], res_e["ms"]], dist.ReduceOp.MAX if world > 1 else None)
+    tot = reduce([res_v["rays"], res_v["voxel_updates"], res_v["visits"], res_e["rays"], res_v["launches"], res_v["sent"]],
+                 dist.ReduceOp.SUM if world > 1 else None)
+    if rank != 0:
+        return
+    rays_v, upd_v, vis_v, rays_e, launches, sent = tot
+    K = args.steps
+    value = rays_v / (ms_v * 1e-3)
+    e2e_value = rays_e / (ms_e * 1e-3)
+    peak, peak_src = measured_peaks()
+    mean = lambda x: float(sum(x) / max(1, len(x)))
+    L = mean(res_v["leaves"])
+    t_prep, t_acc, t_int = mean(res_v["prep_ms"]), mean(res_v["acc_ms"]), mean(res_v["int_ms"])
+    t_dda = t_acc - t_prep
+    b_alg = alg_bytes(n_pts, int(L))
+    t_kernels = t_acc + t_int
+    upd_bytes = 4352 * L  # K2 alone: update masks read (128 B) + map leaf values+mask read and written (4224 B)
+    roofline = {
+        "bound": "hbm", "kernel": "scan step = prep_rays + raycast_dda + apply_update (SURVEY 8d definition)",
+        "achieved": b_alg / (t_kernels * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+        "frac": b_alg / (t_kernels * 1e-3) / 1e9 / peak, "traffic": None,
+        "algorithmic_bytes_per_step": b_alg, "touched_leaves_per_step": L, "kernel_ms_per_step": t_kernels,
+        "by_kernel": {
+            "prep_rays_kernel": {"ms": t_prep, "alg_bytes": 64 * n_pts, "achieved_gbs": 64 * n_pts / (t_prep * 1e-3) / 1e9 if t_prep else None},
+            "raycast_dda_kernel": {"ms": t_dda, "alg_bytes": 48 * n_pts + 128 * L,
+                                   "achieved_gbs": (48 * n_pts + 128 * L) / (t_dda * 1e-3) / 1e9 if t_dda else None,
+                                   "visits_per_sec": (res_v["visits"] / K) / (t_dda * 1e-3) if t_dda else None,
+                                   "note": "not HBM-bound: bounded by L2 atomic (RED) throughput and instruction issue"},
+            "apply_update_kernel": {"ms": t_int, "alg_bytes": upd_bytes, "achieved_gbs": upd_bytes / (t_int * 1e-3) / 1e9 if t_int else None,
+                                    "frac": upd_bytes / (t_int * 1e-3) / 1e9 / peak if t_int else None},
+        },
+    }
+    line = {
+        "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": ms_v / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f64 DDA + f32 log-odds", "data": "synthetic",
+        "config": {"workload": c.name, "description": c.description, "resolution_m": c.resolution, "max_range_m": c.max_range,
+                   "points_per_scan_per_gpu": n_pts, "points_per_step_total": int(rays_v / K),
+                   "sequence": "moving sensor, scan k of the sequence per step, fresh map at step 0",
+                   "parallelism": ("1 GPU" if world == 1 else (f"{world} GPUs: " + ("one scan split across ranks" if strong else "one LiDAR per GPU of a merged rig") +
+                                                               ", map sharded by leaf key, NCCL all-to-all of update leaves")),
+                   "l2": "no explicit flush: per-step working set (map leaves %.2f GB + update grid) exceeds the 126 MB L2 and every step has new input" % (res_v["map_leaves"] * 2112 / 1e9)},
+        "voxel_updates_per_sec": upd_v / (ms_v * 1e-3), "visits_per_sec": vis_v / (ms_v * 1e-3),
+        "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e / K, "h2d_bytes_per_step": 16 * n_pts,
+                "d2h_bytes_per_step": 164, "api": "vdbm_accumulate(host pinned cloud) + vdbm_integrate == insertPointCloud"},
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": res_v["clocks"],
+        "wall_ms_per_step": res_v["wall_ms"] / K,
+    }
+    if world > 1:
+        line["exchange"] = {"records_sent_per_step": sent / K, "bytes_sent_per_step": 136 * sent / K}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(cfg, args.cpu_scans)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-scans", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -75,12 +75,12 @@ typedef struct vdbm_stats_t
                                    or currently accumulated after accumulate */
   uint64_t last_voxel_updates;
   uint64_t last_visits;
-  float last_accumulate_ms; /* device time of the last accumulate (CUDA events, kernels only) */
-  float last_integrate_ms;  /* device time of the last integrate / update_map */
+  float last_accumulate_ms; /* device time of the last accumulate: prep_rays + raycast_dda kernels (CUDA events) */
+  float last_integrate_ms;  /* device time of the last integrate / update_map: apply_update kernel(s) */
+  float last_prep_ms;       /* prep_rays kernel share of last_accumulate_ms */
   uint32_t update_capacity; /* current per-source update hash slots (max over sources) */
   uint32_t map_capacity;    /* current map leaf pool size */
   uint32_t gpu_launches;    /* kernels launched by the library since create (cumulative) */
-  uint32_t reserved;
 } vdbm_stats_t;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */

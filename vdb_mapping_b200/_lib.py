@@ -23,8 +23,8 @@ class VdbmStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "nan_skipped", "clipped", "visits", "voxel_updates", "state_changes",
                                           "map_leaves", "new_leaves", "last_touched_leaves", "last_voxel_updates",
                                           "last_visits")] + \
-               [("last_accumulate_ms", C.c_float), ("last_integrate_ms", C.c_float), ("update_capacity", C.c_uint32),
-                ("map_capacity", C.c_uint32), ("gpu_launches", C.c_uint32), ("reserved", C.c_uint32)]
+               [("last_accumulate_ms", C.c_float), ("last_integrate_ms", C.c_float), ("last_prep_ms", C.c_float),
+                ("update_capacity", C.c_uint32), ("map_capacity", C.c_uint32), ("gpu_launches", C.c_uint32)]
 
 
 _lib = None

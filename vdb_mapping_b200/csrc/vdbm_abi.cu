@@ -49,7 +49,7 @@ struct vdbm_map
   int device          = 0;
   cudaStream_t stream = nullptr;
   bool own_stream     = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   std::string last_error;
 
   // config (VDBMapping.hpp:1456-1469, OccupancyVDBMapping.hpp:59-89)
@@ -296,6 +296,7 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     CU_TRY(m, cudaMemsetAsync(&m->d_ctr->ray_cursor, 0, sizeof(unsigned), m->stream));
     CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
     launchPrepRays(a, m->d_ctr, m->stream);
+    CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
     launchRaycastDDA(a, s.t, m->d_ctr, m->dda_grid, m->stream);
     CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
     CU_TRY(m, cudaGetLastError());
@@ -306,6 +307,8 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     float ms = 0.f;
     cudaEventElapsedTime(&ms, m->ev0, m->ev1);
     m->stats.last_accumulate_ms = ms;
+    cudaEventElapsedTime(&ms, m->ev0, m->ev2);
+    m->stats.last_prep_ms = ms;
     const uint32_t flags = m->h_ctr->flags;
     if (flags & kFlagCoordRange)
     {
@@ -481,6 +484,7 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
   vdbm_map* mm = m.get();
   CU_TRY(mm, cudaEventCreate(&m->ev0));
   CU_TRY(mm, cudaEventCreate(&m->ev1));
+  CU_TRY(mm, cudaEventCreate(&m->ev2));
   CU_TRY(mm, cudaMalloc(&m->d_ctr, sizeof(Counters)));
   CU_TRY(mm, cudaMemsetAsync(m->d_ctr, 0, sizeof(Counters), m->stream));
   CU_TRY(mm, cudaHostAlloc(&m->h_ctr, sizeof(Counters), cudaHostAllocDefault));
@@ -514,7 +518,7 @@ void vdbm_destroy(vdbm_map* m)
   cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
   cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);
-  cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1);
+  cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1); cudaEventDestroy(m->ev2);
   if (m->own_stream) cudaStreamDestroy(m->stream);
   delete m;
 }

@@ -1,0 +1,130 @@
+"""Multi-GPU scan integration: one process per GPU (torch.distributed), rays split across ranks, map sharded by
+leaf key.
+
+Per integrate, on every rank:
+  1. raycast the rank's share of the cloud into its local device update grid          (K0 + K1)
+  2. bin the touched update leaves by owner rank (vdbm_update_partition)               (136-byte leaf records)
+  3. all-to-all the per-peer record counts, then the records themselves                (NCCL over NVLink / NVSwitch)
+  4. OR the received records into the (now empty) local update grid (import)           -> only owned leaves remain
+  5. updateMap on the owned shard                                                      (K2)
+
+The exchange is the one real data-path collective of this path; everything else is rank-local. The host logic
+(split sizes, exchange, import order) is backend-agnostic so that it can be exercised on CPU with gloo in tests
+(tests/test_dist_gloo.py supplies a test double for the engine; the product engine is the CUDA library).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+RECORD_BYTES = 136  # uint64 key + 8 x uint64 active + 8 x uint64 value
+RECORD_WORDS = 17
+
+_MASK21 = (1 << 21) - 1
+_BIAS = 1 << 20
+
+
+def pack_leaf_key(origin) -> int:
+    """Same 63-bit key as packLeafKey() in csrc/vdbm_device.cuh (leaf coords = origin >> 3, 21 bits per axis)."""
+    x, y, z = (int(v) >> 3 for v in origin)
+    return (((x + _BIAS) & _MASK21) << 42) | (((y + _BIAS) & _MASK21) << 21) | ((z + _BIAS) & _MASK21)
+
+
+def _mix64(x: int) -> int:
+    m = (1 << 64) - 1
+    x ^= x >> 33
+    x = (x * 0xff51afd7ed558ccd) & m
+    x ^= x >> 33
+    x = (x * 0xc4ceb9fe1a85ec53) & m
+    x ^= x >> 33
+    return x
+
+
+def leaf_owner_py(origin, n_ranks: int) -> int:
+    """Pure-Python twin of vdbm_leaf_owner (2x2x2 leaf bricks share an owner)."""
+    key = pack_leaf_key(origin)
+    brick = key & ~((1 << 42) | (1 << 21) | 1)
+    return _mix64(brick ^ 0x9E3779B97F4A7C15) % n_ranks
+
+
+def split_points(n: int, rank: int, world: int):
+    """Contiguous 1/world slice of a cloud (strong-scaling mode: one scan split across ranks)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+class CudaEngine:
+    """The product engine: an OccupancyVDBMapping handle on this rank's GPU + torch tensors for the exchange."""
+
+    def __init__(self, mapping, source_id: str):
+        import torch
+        self.torch = torch
+        self.m = mapping
+        self.src = source_id
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def accumulate(self, points, origin):
+        return self.m.accumulateUpdate(points, origin, self.src)
+
+    def accumulate_raw(self, ptr, n, origin, on_device):
+        self.m.accumulateRaw(ptr, n, origin, self.src, on_device=on_device)
+
+    def partition(self, world: int):
+        """-> (counts int64[world] (host), send tensor int64 [(sum counts) * 17] on the device)"""
+        torch = self.torch
+        counts, ptr = self.m.partitionUpdate(self.src, world)
+        total = int(counts.sum())
+        if total == 0:
+            return counts.astype(np.int64), torch.empty(0, dtype=torch.int64, device=self.device)
+
+        class _Wrap:  # zero-copy view of the library-owned partition buffer
+            __cuda_array_interface__ = {"shape": (total * RECORD_WORDS,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+        return counts.astype(np.int64), torch.as_tensor(_Wrap(), device=self.device)
+
+    def new_recv(self, n_records: int):
+        return self.torch.empty(n_records * RECORD_WORDS, dtype=self.torch.int64, device=self.device)
+
+    def import_records(self, buf, n_records: int):
+        if n_records:
+            self.m.importUpdateDevice(self.src, buf.data_ptr(), n_records)
+
+    def integrate(self):
+        self.m.integrateUpdate(keep_change=False)
+
+    def counts_tensor(self, counts):
+        return self.torch.as_tensor(np.asarray(counts, dtype=np.int64), device=self.device)
+
+
+def exchange_and_integrate(engine, world: int, dist=None):
+    """Steps 2-5 above. `engine` implements partition/new_recv/import_records/integrate/counts_tensor;
+    `dist` is torch.distributed (or None / world == 1 for the single-rank short-cut).
+    Returns (records sent to other ranks, records received from other ranks)."""
+    if world == 1 or dist is None:
+        engine.integrate()
+        return 0, 0
+    rank = dist.get_rank()
+    counts, send = engine.partition(world)
+    send_counts = engine.counts_tensor(counts)
+    recv_counts = send_counts.new_empty(world)
+    dist.all_to_all_single(recv_counts, send_counts)
+    recv_host = [int(v) for v in recv_counts.cpu().tolist()]
+    n_recv = sum(recv_host)
+    recv = engine.new_recv(n_recv)
+    dist.all_to_all_single(recv, send,
+                           output_split_sizes=[c * RECORD_WORDS for c in recv_host],
+                           input_split_sizes=[int(c) * RECORD_WORDS for c in counts])
+    engine.import_records(recv, n_recv)
+    engine.integrate()
+    return int(counts.sum() - counts[rank]), n_recv - recv_host[rank]
+
+
+def sharded_insert(engine, points, origin, world: int, dist=None, mode: str = "own_cloud"):
+    """insertPointCloud across `world` ranks.
+    mode "own_cloud": `points` is this rank's own cloud (one sensor per GPU, weak scaling);
+    mode "split":     `points` is the same full cloud on every rank, each rank raycasts its 1/world slice."""
+    if mode == "split" and world > 1:
+        lo, hi = split_points(points.shape[0], dist.get_rank(), world)
+        points = points[lo:hi]
+    engine.accumulate(points, origin)
+    return exchange_and_integrate(engine, world, dist)

@@ -84,10 +84,12 @@ def _lidar_dirs(n_beams: int, n_az: int, elev_lo_deg: float, elev_hi_deg: float,
     return d
 
 
-def lidar_scan(cfg: int, k: int = 0, nan_frac: float = 0.01):
-    """cfg 1 / 2 / 4 scan number k. Returns (points (n,4) f32, origin (3,) f64)."""
+def lidar_scan(cfg: int, k: int = 0, nan_frac: float = 0.01, sensor: int = 0):
+    """cfg 1 / 2 / 4 scan number k. Returns (points (n,4) f32, origin (3,) f64).
+    sensor > 0 (cfg 2 only): another OS1-128 of a merged multi-LiDAR rig sharing the same origin, yawed by a
+    fraction of the azimuth step and pitched by 2.5 deg per sensor (used for the multi-GPU runs: one LiDAR per GPU)."""
     c = CONFIGS[cfg]
-    rng = np.random.default_rng(np.random.PCG64(1234 + cfg + 1000 * k))
+    rng = np.random.default_rng(np.random.PCG64(1234 + cfg + 1000 * k + 7919 * sensor))
     R = c.max_range
     if cfg == 1:
         origin = np.array([0.0, 0.0, 0.0])
@@ -95,7 +97,7 @@ def lidar_scan(cfg: int, k: int = 0, nan_frac: float = 0.01):
         r = _box_scene_range(origin, d, 0.8 * R, 0.8 * R, -1.8, None, 2.0 * R)
     elif cfg == 2:
         origin = np.array([0.137 * k, 0.061 * k, 0.013 * k])
-        d = _lidar_dirs(128, 2048, -22.5, 22.5, 0.5 * k)
+        d = _lidar_dirs(128, 2048, -22.5, 22.5, 0.5 * k + (360.0 / 2048.0) * (sensor / 8.0), pitch_deg=2.5 * sensor)
         r = _box_scene_range(origin, d, 0.8 * R, 0.8 * R, -1.8, None, 2.0 * R)
     elif cfg == 4:
         origin = np.array([0.211 * k, 0.093 * k, 0.0])
@@ -131,8 +133,8 @@ def rgbd_scan(k: int = 0, nan_frac: float = 0.01):
     return _finish(pts, rng, nan_frac), origin
 
 
-def make_scan(cfg: int, k: int = 0, nan_frac: float = 0.01):
-    return rgbd_scan(k, nan_frac) if cfg == 3 else lidar_scan(cfg, k, nan_frac)
+def make_scan(cfg: int, k: int = 0, nan_frac: float = 0.01, sensor: int = 0):
+    return rgbd_scan(k, nan_frac) if cfg == 3 else lidar_scan(cfg, k, nan_frac, sensor)
 
 
 def small_scan(seed: int, n: int = 4096, scale: float = 3.0, nan_frac: float = 0.02):
