@@ -33,9 +33,10 @@ struct Source
 {
   std::string id;
   double max_range = 0.0;
-  UpdateTable t{};
-  uint32_t cap       = 0;
-  uint32_t n_touched = 0;         // host copy, valid after every synchronising call
+  UpdateGrid g{};
+  uint32_t cap       = 0;         // brick slots
+  uint32_t n_bricks  = 0;         // host copies, valid after every synchronising call
+  uint32_t n_entries = 0;         // touched leaves (compact list is always rebuilt after a grid write)
   LeafRecord* d_change = nullptr; // change records of the last update (device)
   uint32_t change_cap  = 0;
   uint32_t n_change    = 0;
@@ -63,7 +64,7 @@ struct vdbm_map
   MapTable mt{};
   uint32_t hcap     = 0;
   uint32_t n_leaves = 0; // host copy
-  uint32_t* d_map_counters = nullptr; // [0] n_leaves, [1] n_dirty
+  uint32_t* d_map_counters = nullptr; // [0] n_leaves
   uint32_t* h_small        = nullptr; // pinned scratch (>= 64 words)
   std::map<std::string, std::unique_ptr<Source> > sources; // std::map order == integrateUpdate order (V:380)
 
@@ -71,6 +72,9 @@ struct vdbm_map
   uint8_t* d_points = nullptr;
   size_t points_cap = 0;
   RayRec* d_rays    = nullptr;
+  uint32_t* d_sort  = nullptr; // 4 x rays_cap u32: keys in/out, idx in/out
+  void* d_sort_tmp  = nullptr;
+  size_t sort_tmp_bytes = 0;
   size_t rays_cap   = 0;
   LeafRecord* d_part = nullptr; // partition output
   size_t part_cap    = 0;
@@ -106,37 +110,64 @@ uint32_t nextPow2(uint64_t v)
   return uint32_t(std::min<uint64_t>(p, 1ull << 31));
 }
 
-// ---- update table ------------------------------------------------------------------------------------
-int allocUpdateTable(vdbm_map* m, UpdateTable& t, uint32_t cap)
+// ---- update grid (brick hash) ------------------------------------------------------------------------
+int allocUpdateGrid(vdbm_map* m, UpdateGrid& g, uint32_t cap)
 {
-  CU_TRY(m, cudaMalloc(&t.keys, size_t(cap) * 8));
-  CU_TRY(m, cudaMalloc(&t.active, size_t(cap) * 64));
-  CU_TRY(m, cudaMalloc(&t.value, size_t(cap) * 64));
-  CU_TRY(m, cudaMalloc(&t.touched, size_t(cap) * 4));
-  CU_TRY(m, cudaMalloc(&t.n_touched, 4));
-  t.cap_mask = cap - 1;
-  CU_TRY(m, cudaMemsetAsync(t.keys, 0xFF, size_t(cap) * 8, m->stream));
-  CU_TRY(m, cudaMemsetAsync(t.active, 0, size_t(cap) * 64, m->stream));
-  CU_TRY(m, cudaMemsetAsync(t.value, 0, size_t(cap) * 64, m->stream));
-  CU_TRY(m, cudaMemsetAsync(t.n_touched, 0, 4, m->stream));
+  const size_t brick_bytes = size_t(kBrickLeaves) * 64;
+  CU_TRY(m, cudaMalloc(&g.bkeys, size_t(cap) * 8));
+  CU_TRY(m, cudaMalloc(&g.act, size_t(cap) * brick_bytes));
+  CU_TRY(m, cudaMalloc(&g.val, size_t(cap) * brick_bytes));
+  CU_TRY(m, cudaMalloc(&g.btouched, size_t(cap) * 4));
+  CU_TRY(m, cudaMalloc(&g.entries, size_t(cap) * kBrickLeaves * 4));
+  CU_TRY(m, cudaMalloc(&g.counters, 8));
+  g.cap_mask = cap - 1;
+  CU_TRY(m, cudaMemsetAsync(g.bkeys, 0xFF, size_t(cap) * 8, m->stream));
+  CU_TRY(m, cudaMemsetAsync(g.act, 0, size_t(cap) * brick_bytes, m->stream));
+  CU_TRY(m, cudaMemsetAsync(g.val, 0, size_t(cap) * brick_bytes, m->stream));
+  CU_TRY(m, cudaMemsetAsync(g.counters, 0, 8, m->stream));
   return VDBM_OK;
 }
-void freeUpdateTable(UpdateTable& t)
+void freeUpdateGrid(UpdateGrid& g)
 {
-  cudaFree(t.keys); cudaFree(t.active); cudaFree(t.value); cudaFree(t.touched); cudaFree(t.n_touched);
-  t = UpdateTable{};
+  cudaFree(g.bkeys); cudaFree(g.act); cudaFree(g.val); cudaFree(g.btouched); cudaFree(g.entries); cudaFree(g.counters);
+  g = UpdateGrid{};
 }
 
-int growUpdateTable(vdbm_map* m, Source& s, uint32_t new_cap)
+// read the grid counters (bricks, entries) to the host; synchronises
+int readGridCounters(vdbm_map* m, Source& s)
 {
-  UpdateTable nt{};
-  int rc = allocUpdateTable(m, nt, new_cap);
-  if (rc) return rc;
-  launchRehashUpdate(s.t, s.n_touched, nt, m->d_ctr, m->stream);
+  CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s.g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
-  freeUpdateTable(s.t);
-  s.t   = nt;
+  s.n_bricks  = m->h_small[8];
+  s.n_entries = m->h_small[9];
+  return VDBM_OK;
+}
+
+// double the brick table, move the occupied bricks, rebuild the leaf list
+int growUpdateGrid(vdbm_map* m, Source& s)
+{
+  if (s.cap >= (1u << 22)) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "update brick hash cannot grow further");
+  const uint32_t new_cap = s.cap * 2;
+  UpdateGrid ng{};
+  int rc = allocUpdateGrid(m, ng, new_cap);
+  if (rc) return rc;
+  launchRehashUpdate(s.g, std::min(s.n_bricks, s.cap), ng, m->d_ctr, m->stream);
+  launchCompactLeaves(ng, m->stream);
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  freeUpdateGrid(s.g);
+  s.g   = ng;
   s.cap = new_cap;
+  m->stats.update_capacity = std::max(m->stats.update_capacity, s.cap * uint32_t(kBrickLeaves));
+  return readGridCounters(m, s);
+}
+
+// drop everything accumulated in the grid (masks zeroed through the leaf list, bricks forgotten)
+int clearUpdateGrid(vdbm_map* m, Source& s)
+{
+  launchClearEntries(s.g, s.n_entries, m->stream);
+  launchResetBricks(s.g, s.n_bricks, m->stream);
+  CU_TRY(m, cudaGetLastError());
+  s.n_bricks = s.n_entries = 0;
   return VDBM_OK;
 }
 
@@ -157,14 +188,13 @@ int allocMapPool(vdbm_map* m, MapTable& t, uint32_t cap)
   CU_TRY(m, cudaMalloc(&t.leaf_mask, size_t(cap) * 64));
   CU_TRY(m, cudaMalloc(&t.leaf_vals, size_t(cap) * 2048));
   CU_TRY(m, cudaMalloc(&t.leaf_dirty, size_t(cap) * 4));
-  CU_TRY(m, cudaMalloc(&t.dirty_list, size_t(cap) * 4));
   CU_TRY(m, cudaMemsetAsync(t.leaf_dirty, 0, size_t(cap) * 4, m->stream));
   t.pool_cap = cap;
   return VDBM_OK;
 }
 void freeMapPool(MapTable& t)
 {
-  cudaFree(t.leaf_keys); cudaFree(t.leaf_mask); cudaFree(t.leaf_vals); cudaFree(t.leaf_dirty); cudaFree(t.dirty_list);
+  cudaFree(t.leaf_keys); cudaFree(t.leaf_mask); cudaFree(t.leaf_vals); cudaFree(t.leaf_dirty);
 }
 
 // make room for `extra` more leaves (pool) and keep the hash load factor <= 0.5
@@ -184,7 +214,6 @@ int ensureMapCapacity(vdbm_map* m, uint64_t extra)
       CU_TRY(m, cudaMemcpyAsync(nt.leaf_mask, m->mt.leaf_mask, n * 64, cudaMemcpyDeviceToDevice, m->stream));
       CU_TRY(m, cudaMemcpyAsync(nt.leaf_vals, m->mt.leaf_vals, n * 2048, cudaMemcpyDeviceToDevice, m->stream));
       CU_TRY(m, cudaMemcpyAsync(nt.leaf_dirty, m->mt.leaf_dirty, n * 4, cudaMemcpyDeviceToDevice, m->stream));
-      CU_TRY(m, cudaMemcpyAsync(nt.dirty_list, m->mt.dirty_list, n * 4, cudaMemcpyDeviceToDevice, m->stream));
     }
     CU_TRY(m, cudaStreamSynchronize(m->stream));
     freeMapPool(m->mt);
@@ -206,7 +235,7 @@ int ensureMapCapacity(vdbm_map* m, uint64_t extra)
 int syncCounters(vdbm_map* m)
 {
   CU_TRY(m, cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
-  CU_TRY(m, cudaMemcpyAsync(m->h_small, m->d_map_counters, 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(m->h_small, m->d_map_counters, 4, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   m->n_leaves = m->h_small[0];
   const Counters& c      = *m->h_ctr;
@@ -219,14 +248,6 @@ int syncCounters(vdbm_map* m)
   m->stats.map_leaves    = m->n_leaves;
   m->stats.map_capacity  = m->mt.pool_cap;
   m->stats.gpu_launches  = launchCount();
-  return VDBM_OK;
-}
-
-int readTouched(vdbm_map* m, Source& s)
-{
-  CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s.t.n_touched, 4, cudaMemcpyDeviceToHost, m->stream));
-  CU_TRY(m, cudaStreamSynchronize(m->stream));
-  s.n_touched = m->h_small[8];
   return VDBM_OK;
 }
 
@@ -279,13 +300,20 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   a.inv_res    = 1.0 / m->params.resolution;
   if (m->rays_cap < n)
   {
-    cudaFree(m->d_rays);
-    m->d_rays   = nullptr;
+    cudaFree(m->d_rays); cudaFree(m->d_sort); cudaFree(m->d_sort_tmp);
+    m->d_rays = nullptr; m->d_sort = nullptr; m->d_sort_tmp = nullptr;
     m->rays_cap = 0;
     CU_TRY(m, cudaMalloc(&m->d_rays, n * sizeof(RayRec)));
+    CU_TRY(m, cudaMalloc(&m->d_sort, n * 4 * sizeof(uint32_t)));
+    m->sort_tmp_bytes = sortRaysByLength(nullptr, 0, m->d_sort, m->d_sort + n, m->d_sort + 2 * n, m->d_sort + 3 * n, uint32_t(n), m->stream);
+    CU_TRY(m, cudaMalloc(&m->d_sort_tmp, m->sort_tmp_bytes ? m->sort_tmp_bytes : 8));
     m->rays_cap = n;
   }
   a.rays = m->d_rays;
+  // layout inside d_sort (stride = rays_cap): [keys_in | keys_out | idx_in | idx_out]
+  a.sort_keys = m->d_sort;
+  a.sort_idx  = m->d_sort + 2 * m->rays_cap;
+  a.order     = m->d_sort + 3 * m->rays_cap;
 
   // counters before this attempt (needed if the scan has to be replayed after a hash overflow). Every ABI
   // call that changes device counters ends with syncCounters(), so the pinned host copy is current.
@@ -296,14 +324,18 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     CU_TRY(m, cudaMemsetAsync(&m->d_ctr->ray_cursor, 0, sizeof(unsigned), m->stream));
     CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
     launchPrepRays(a, m->d_ctr, m->stream);
+    sortRaysByLength(m->d_sort_tmp, m->sort_tmp_bytes, a.sort_keys, m->d_sort + m->rays_cap, a.sort_idx, m->d_sort + 3 * m->rays_cap,
+                     uint32_t(n), m->stream);
     CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
-    launchRaycastDDA(a, s.t, m->d_ctr, m->dda_grid, m->stream);
+    launchRaycastDDA(a, s.g, m->d_ctr, m->dda_grid, m->stream);
+    launchCompactLeaves(s.g, m->stream);
     CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
     CU_TRY(m, cudaGetLastError());
-    rc = syncCounters(m);
+    CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s.g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
+    rc = syncCounters(m); // one synchronisation per accumulate: counters, flags, brick and leaf counts
     if (rc) return rc;
-    rc = readTouched(m, s);
-    if (rc) return rc;
+    s.n_bricks  = m->h_small[8];
+    s.n_entries = m->h_small[9];
     float ms = 0.f;
     cudaEventElapsedTime(&ms, m->ev0, m->ev1);
     m->stats.last_accumulate_ms = ms;
@@ -314,16 +346,14 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     {
       CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
       m->last_error = "some ray end points were outside the +-2^23 voxel range and were dropped";
-      // not fatal for the rest of the cloud; report it
-      m->stats.last_visits = m->h_ctr->visits - before.visits;
-      m->stats.last_touched_leaves = s.n_touched;
+      m->stats.last_visits         = m->h_ctr->visits - before.visits;
+      m->stats.last_touched_leaves = s.n_entries;
       return VDBM_ERR_COORD_RANGE;
     }
     const bool overflow = (flags & kFlagUpdateOverflow) != 0;
-    const bool crowded  = uint64_t(s.n_touched) * 10 > uint64_t(s.cap) * 7;
+    const bool crowded  = uint64_t(s.n_bricks) * 10 > uint64_t(s.cap) * 7;
     if (!overflow && !crowded) break;
-    if (s.cap >= (1u << 31)) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "update hash cannot grow further");
-    rc = growUpdateTable(m, s, s.cap * 2);
+    rc = growUpdateGrid(m, s);
     if (rc) return rc;
     if (!overflow) break; // table was only crowded: content is complete, no replay needed
     // overflow: some marks were dropped. Restore the counters and replay the scan (marking is an idempotent OR).
@@ -334,8 +364,8 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     CU_TRY(m, cudaStreamSynchronize(m->stream));
   }
   m->stats.last_visits         = m->h_ctr->visits - before.visits;
-  m->stats.last_touched_leaves = s.n_touched;
-  m->stats.update_capacity     = std::max(m->stats.update_capacity, s.cap);
+  m->stats.last_touched_leaves = s.n_entries;
+  m->stats.update_capacity     = std::max(m->stats.update_capacity, s.cap * uint32_t(kBrickLeaves));
   return VDBM_OK;
 }
 
@@ -358,9 +388,14 @@ int stagePoints(vdbm_map* m, const void* points, uint64_t n, uint64_t stride)
 int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
 {
   s.n_change = 0;
-  const uint32_t n = s.n_touched;
+  const uint32_t n = s.n_entries;
   m->stats.last_touched_leaves += n;
-  if (n == 0) return VDBM_OK; // VDBMapping.hpp:735-738
+  if (n == 0) // VDBMapping.hpp:735-738 (a grid with bricks but no touched leaf is empty too)
+  {
+    if (s.n_bricks) launchResetBricks(s.g, s.n_bricks, m->stream);
+    s.n_bricks = 0;
+    return VDBM_OK;
+  }
   int rc = ensureMapCapacity(m, n);
   if (rc) return rc;
   if (want_change && s.change_cap < n)
@@ -372,10 +407,10 @@ int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
     s.change_cap = n;
   }
   CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_change, 0, sizeof(unsigned), m->stream));
-  launchApplyUpdate(s.t, m->mt, m->lo, want_change ? s.d_change : nullptr, want_change ? s.change_cap : 0, m->d_ctr, n, m->stream);
-  CU_TRY(m, cudaMemsetAsync(s.t.n_touched, 0, 4, m->stream));
+  launchApplyUpdate(s.g, m->mt, m->lo, want_change ? s.d_change : nullptr, want_change ? s.change_cap : 0, m->d_ctr, n, m->stream);
+  launchResetBricks(s.g, s.n_bricks, m->stream); // fresh update grid (VDBMapping.hpp:384)
   CU_TRY(m, cudaGetLastError());
-  s.n_touched = 0;
+  s.n_bricks = s.n_entries = 0;
   return VDBM_OK;
 }
 
@@ -492,7 +527,6 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
   CU_TRY(mm, cudaMalloc(&m->d_map_counters, 8));
   CU_TRY(mm, cudaMemsetAsync(m->d_map_counters, 0, 8, m->stream));
   m->mt.n_leaves = m->d_map_counters;
-  m->mt.n_dirty  = m->d_map_counters + 1;
   const uint32_t pool = nextPow2(params->map_capacity_leaves ? params->map_capacity_leaves : (1u << 19));
   int rc = allocMapPool(mm, m->mt, pool);
   if (rc) return rc;
@@ -511,12 +545,13 @@ void vdbm_destroy(vdbm_map* m)
   cudaStreamSynchronize(m->stream);
   for (auto& kv : m->sources)
   {
-    freeUpdateTable(kv.second->t);
+    freeUpdateGrid(kv.second->g);
     cudaFree(kv.second->d_change);
   }
   freeMapPool(m->mt);
   cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
   cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
+  cudaFree(m->d_sort); cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);
   cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1); cudaEventDestroy(m->ev2);
   if (m->own_stream) cudaStreamDestroy(m->stream);
@@ -534,10 +569,9 @@ int vdbm_reset(vdbm_map* m)
   for (auto& kv : m->sources)
   {
     Source& s = *kv.second;
-    if (s.n_touched) launchClearUpdate(s.t, s.n_touched, m->stream);
-    CU_TRY(m, cudaMemsetAsync(s.t.n_touched, 0, 4, m->stream));
-    s.n_touched = 0;
-    s.n_change  = 0;
+    int rc    = clearUpdateGrid(m, s);
+    if (rc) return rc;
+    s.n_change = 0;
   }
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   m->stats.map_leaves = 0;
@@ -590,19 +624,19 @@ int vdbm_source_add(vdbm_map* m, const char* source_id, double max_range)
   {
     // the reference overwrites the map entry with a fresh InputSource (V:1374)
     Source& s = *it->second;
-    if (s.n_touched) launchClearUpdate(s.t, s.n_touched, m->stream);
-    CU_TRY(m, cudaMemsetAsync(s.t.n_touched, 0, 4, m->stream));
-    s.n_touched = 0;
+    int rc    = clearUpdateGrid(m, s);
+    if (rc) return rc;
     s.max_range = (max_range == 0) ? m->max_range : max_range;
     return VDBM_OK;
   }
   auto s       = std::make_unique<Source>();
   s->id        = source_id;
   s->max_range = (max_range == 0) ? m->max_range : max_range; // V:1356-1363
-  s->cap       = nextPow2(m->params.update_capacity_leaves ? m->params.update_capacity_leaves : (1u << 20));
-  int rc       = allocUpdateTable(m, s->t, s->cap);
+  // capacity hint is in leaves; the grid is a hash of 512-leaf bricks (64 KB each). Default: 4096 bricks = 256 MB.
+  s->cap = m->params.update_capacity_leaves ? nextPow2(std::max<uint64_t>(8, m->params.update_capacity_leaves / 64)) : 4096u;
+  int rc = allocUpdateGrid(m, s->g, s->cap);
   if (rc) return rc;
-  m->stats.update_capacity = std::max(m->stats.update_capacity, s->cap);
+  m->stats.update_capacity = std::max(m->stats.update_capacity, s->cap * uint32_t(kBrickLeaves));
   m->sources[source_id]    = std::move(s);
   return VDBM_OK;
 }
@@ -719,7 +753,7 @@ int vdbm_update_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
   if (!m || !out) return VDBM_ERR_INVALID_ARG;
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
-  const uint32_t n = s->n_touched;
+  const uint32_t n = s->n_entries;
   vdbm_leafset* ls = newLeafset(n, true, false);
   *out             = ls;
   if (n == 0) return VDBM_OK;
@@ -730,10 +764,10 @@ int vdbm_update_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
   CU_TRY(m, so.alloc(size_t(n) * 12)); CU_TRY(m, sa.alloc(size_t(n) * 64)); CU_TRY(m, sv.alloc(size_t(n) * 64));
   uint64_t* keys = k0.as<uint64_t>();
   uint32_t* idx  = i0.as<uint32_t>();
-  launchKeysFromSlots(s->t.keys, s->t.touched, n, keys, idx, m->stream);
+  launchEntryKeys(s->g, n, keys, idx, m->stream);
   int rc = sortByKey(m, keys, idx, k1.as<uint64_t>(), i1.as<uint32_t>(), n);
   if (rc) return rc;
-  launchGatherUpdate(s->t, n, idx, recs.as<LeafRecord>(), m->stream);
+  launchGatherUpdate(s->g, n, keys, idx, recs.as<LeafRecord>(), m->stream);
   launchSplitRecords(recs.as<LeafRecord>(), n, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<uint64_t>(), m->stream);
   CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaMemcpyAsync(ls->active, sa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
@@ -770,19 +804,27 @@ int vdbm_update_import_device(vdbm_map* m, const char* source_id, const void* d_
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   if (n == 0) return VDBM_OK;
-  // make sure the table can take n more leaves at load factor <= 0.7 (worst case: all new)
-  while ((uint64_t(s->n_touched) + n) * 10 > uint64_t(s->cap) * 7)
+  // optimistic: OR the records in; if the brick hash overflowed or got crowded, grow and replay (OR is idempotent)
+  for (int attempt = 0; attempt < 24; ++attempt)
   {
-    if (s->cap >= (1u << 31)) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "update hash cannot grow further");
-    int rc = growUpdateTable(m, *s, s->cap * 2);
+    launchImportUpdate(s->g, static_cast<const LeafRecord*>(d_records), n, m->d_ctr, m->stream);
+    launchCompactLeaves(s->g, m->stream);
+    CU_TRY(m, cudaGetLastError());
+    CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s->g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
+    int rc = syncCounters(m);
     if (rc) return rc;
+    s->n_bricks  = m->h_small[8];
+    s->n_entries = m->h_small[9];
+    const bool overflow = (m->h_ctr->flags & kFlagUpdateOverflow) != 0;
+    const bool crowded  = uint64_t(s->n_bricks) * 10 > uint64_t(s->cap) * 7;
+    if (!overflow && !crowded) break;
+    if (overflow) CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+    rc = growUpdateGrid(m, *s);
+    if (rc) return rc;
+    if (!overflow) break;
   }
-  launchImportUpdate(s->t, static_cast<const LeafRecord*>(d_records), n, m->d_ctr, m->stream);
-  CU_TRY(m, cudaGetLastError());
-  int rc = readTouched(m, *s);
-  if (rc) return rc;
-  m->stats.last_touched_leaves = s->n_touched;
-  m->stats.update_capacity     = std::max(m->stats.update_capacity, s->cap);
+  m->stats.last_touched_leaves = s->n_entries;
+  m->stats.update_capacity     = std::max(m->stats.update_capacity, s->cap * uint32_t(kBrickLeaves));
   return VDBM_OK;
 }
 
@@ -791,10 +833,24 @@ int vdbm_map_export(vdbm_map* m, int dirty_only, vdbm_leafset** out)
   if (!m || !out) return VDBM_ERR_INVALID_ARG;
   int rc = syncCounters(m);
   if (rc) return rc;
-  const uint32_t n_dirty = m->h_small[1];
-  const uint32_t n       = dirty_only ? n_dirty : m->n_leaves;
-  vdbm_leafset* ls       = newLeafset(n, false, true);
-  *out                   = ls;
+  const uint32_t n_all = m->n_leaves;
+  TempBuf dl(m->stream);
+  uint32_t n = n_all;
+  if (dirty_only)
+  {
+    // dirty leaves = flag set by apply_update since the previous export; collect (and clear) them on the device
+    CU_TRY(m, dl.alloc(size_t(std::max(1u, n_all)) * 4));
+    CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_out, 0, sizeof(unsigned), m->stream));
+    launchCollectDirty(m->mt, n_all, dl.as<uint32_t>(), m->d_ctr, m->stream);
+    CU_TRY(m, cudaGetLastError());
+    rc = syncCounters(m);
+    if (rc) return rc;
+    n = std::min(m->h_ctr->n_out, n_all);
+  }
+  else if (n_all)
+    CU_TRY(m, cudaMemsetAsync(m->mt.leaf_dirty, 0, size_t(n_all) * 4, m->stream)); // a full export also leaves nothing dirty
+  vdbm_leafset* ls = newLeafset(n, false, true);
+  *out             = ls;
   if (n)
   {
     TempBuf k0(m->stream), k1(m->stream), i0(m->stream), i1(m->stream), so(m->stream), sa(m->stream), sv(m->stream);
@@ -803,19 +859,13 @@ int vdbm_map_export(vdbm_map* m, int dirty_only, vdbm_leafset** out)
     CU_TRY(m, so.alloc(size_t(n) * 12)); CU_TRY(m, sa.alloc(size_t(n) * 64)); CU_TRY(m, sv.alloc(size_t(n) * 2048));
     uint64_t* keys = k0.as<uint64_t>();
     uint32_t* idx  = i0.as<uint32_t>();
-    launchKeysFromSlots(m->mt.leaf_keys, dirty_only ? m->mt.dirty_list : nullptr, n, keys, idx, m->stream);
+    launchKeysFromIdx(m->mt.leaf_keys, dirty_only ? dl.as<uint32_t>() : nullptr, n, keys, idx, m->stream);
     rc = sortByKey(m, keys, idx, k1.as<uint64_t>(), i1.as<uint32_t>(), n);
     if (rc) return rc;
-    launchGatherMap(m->mt, n, idx, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<float>(), 0, m->stream);
+    launchGatherMap(m->mt, n, idx, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<float>(), m->stream);
     CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(m, cudaMemcpyAsync(ls->active, sa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(m, cudaMemcpyAsync(ls->values, sv.p, size_t(n) * 2048, cudaMemcpyDeviceToHost, m->stream));
-  }
-  // every export (full or dirty) leaves the dirty list empty: the host mirror is now up to date
-  if (n_dirty)
-  {
-    CU_TRY(m, cudaMemsetAsync(m->mt.leaf_dirty, 0, size_t(m->mt.pool_cap) * 4, m->stream));
-    CU_TRY(m, cudaMemsetAsync(m->mt.n_dirty, 0, 4, m->stream));
   }
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   return VDBM_OK;
@@ -927,10 +977,15 @@ int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, u
   if (!m || !counts || !d_records || n_ranks <= 0 || n_ranks > 32) return VDBM_ERR_INVALID_ARG;
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
-  const uint32_t n = s->n_touched;
+  const uint32_t n = s->n_entries;
   for (int r = 0; r < n_ranks; ++r) counts[r] = 0;
   *d_records = m->d_part;
-  if (n == 0) return VDBM_OK;
+  if (n == 0)
+  {
+    if (s->n_bricks) launchResetBricks(s->g, s->n_bricks, m->stream);
+    s->n_bricks = 0;
+    return VDBM_OK;
+  }
   if (m->part_cap < n)
   {
     cudaFree(m->d_part);
@@ -945,7 +1000,7 @@ int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, u
   uint32_t* d_counts = d.as<uint32_t>();
   uint32_t* d_cursor = d_counts + 32;
   CU_TRY(m, cudaMemsetAsync(d_counts, 0, 64 * 4, m->stream));
-  launchPartition(s->t, n, n_ranks, d_counts, d_cursor, m->d_part, 0, m->stream);
+  launchPartition(s->g, n, n_ranks, d_counts, d_cursor, m->d_part, 0, m->stream);
   CU_TRY(m, cudaMemcpyAsync(m->h_small + 24, d_counts, 32 * 4, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   uint32_t off[32];
@@ -960,11 +1015,11 @@ int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, u
     }
   }
   CU_TRY(m, cudaMemcpyAsync(d_cursor, off, 32 * 4, cudaMemcpyHostToDevice, m->stream));
-  launchPartition(s->t, n, n_ranks, d_counts, d_cursor, m->d_part, 1, m->stream);
-  CU_TRY(m, cudaMemsetAsync(s->t.n_touched, 0, 4, m->stream));
+  launchPartition(s->g, n, n_ranks, d_counts, d_cursor, m->d_part, 1, m->stream);
+  launchResetBricks(s->g, s->n_bricks, m->stream);
   CU_TRY(m, cudaGetLastError());
   CU_TRY(m, cudaStreamSynchronize(m->stream));
-  s->n_touched = 0;
+  s->n_bricks = s->n_entries = 0;
   return VDBM_OK;
 }
 

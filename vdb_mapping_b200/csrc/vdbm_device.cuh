@@ -2,11 +2,12 @@
 //
 // Data layout in HBM:
 //   update grid (one per input source; replaces openvdb Tree4<bool,1,4,3>, VDBMapping.hpp:89,97)
-//     open-addressing hash, slot == storage:  keys[C] u64 | active[C][8] u64 | value[C][8] u64
-//     + touched[C] u32 : compact list of occupied slots in insertion order (drives the update kernel)
+//     open-addressing hash of 64^3-voxel BRICKS, slot == storage:
+//       bkeys[C] u64 | act[C][512 leaves][8] u64 | val[C][512][8] u64   (64 KB per brick slot)
+//     + btouched[C] (occupied slots) + entries[] (compact list of touched leaves, rebuilt after each raycast)
 //   map (replaces openvdb Tree4<float,5,4,3> = FloatTree, VDBMapping.hpp:88)
 //     open-addressing hash  hkeys[H] u64 -> hvals[H] u32 (leaf index)
-//     leaf pool (SoA):  leaf_keys[P] u64 | leaf_mask[P][8] u64 | leaf_vals[P][512] f32 | leaf_dirty[P] u32
+//     leaf pool (SoA):  leaf_keys[P] u64 | leaf_mask[P][8] u64 | leaf_vals[P][512] f32 | leaf_dirty[P] u32 (flag)
 //   in-leaf layout mirrors openvdb::tree::LeafNode<T,3>: offset n = (x&7)<<6 | (y&7)<<3 | (z&7),
 //   mask word n>>6, bit n&63.
 #pragma once
@@ -58,15 +59,40 @@ __host__ __device__ __forceinline__ int32_t leafOwner(uint64_t key, int32_t n_ra
 }
 
 // ------------------------------------------------------------------------------------------------
-struct UpdateTable
+// Update grid of one input source: an open-addressing hash of BRICKS (8^3 leaves = 64^3 voxels), slot ==
+// storage. Inside a brick every leaf mask word has a fixed address, so the DDA kernel needs a hash lookup only
+// when a ray enters a new brick (~every 50 visits) and addresses everything else arithmetically:
+//   word offset in brick = leaf_in_brick * 8 + (x & 7),  leaf_in_brick = ((x>>3)&7)<<6 | ((y>>3)&7)<<3 | ((z>>3)&7)
+// A "leaf entry" e = slot * 512 + leaf_in_brick indexes act/val (8 words each) directly.
+constexpr int kBrickLeaves = 512;
+struct UpdateGrid
 {
-  uint64_t* keys;    // [cap]
-  uint64_t* active;  // [cap][8]
-  uint64_t* value;   // [cap][8]
-  uint32_t* touched; // [cap]
-  uint32_t* n_touched; // device counter
-  uint32_t cap_mask; // cap - 1 (cap is a power of two)
+  uint64_t* bkeys;    // [cap]          brick key = packLeafKey(voxel >> 6 per axis)
+  uint64_t* act;      // [cap][512][8]  active masks of the brick's leaves (32 KB per brick)
+  uint64_t* val;      // [cap][512][8]  value (hit) masks
+  uint32_t* btouched; // [cap]          occupied brick slots in insertion order
+  uint32_t* entries;  // [cap*512]      compact list of touched leaf entries (built by compact_leaves_kernel)
+  uint32_t* counters; // [0] occupied bricks, [1] leaf entries
+  uint32_t cap_mask;  // cap - 1 (cap is a power of two)
 };
+
+// leaf key of entry e given its brick key
+__host__ __device__ __forceinline__ uint64_t leafKeyOfEntry(uint64_t bkey, uint32_t leaf_in_brick)
+{
+  const int32_t bx = int32_t(uint32_t(bkey >> 42) & 0x1FFFFFu) - kLeafBias;
+  const int32_t by = int32_t(uint32_t(bkey >> 21) & 0x1FFFFFu) - kLeafBias;
+  const int32_t bz = int32_t(uint32_t(bkey) & 0x1FFFFFu) - kLeafBias;
+  return packLeafKey(bx * 8 + int32_t(leaf_in_brick >> 6), by * 8 + int32_t((leaf_in_brick >> 3) & 7), bz * 8 + int32_t(leaf_in_brick & 7));
+}
+// brick key and leaf_in_brick of a LEAF key
+__host__ __device__ __forceinline__ uint64_t brickKeyOfLeaf(uint64_t lkey, uint32_t& leaf_in_brick)
+{
+  const int32_t lx = int32_t(uint32_t(lkey >> 42) & 0x1FFFFFu) - kLeafBias;
+  const int32_t ly = int32_t(uint32_t(lkey >> 21) & 0x1FFFFFu) - kLeafBias;
+  const int32_t lz = int32_t(uint32_t(lkey) & 0x1FFFFFu) - kLeafBias;
+  leaf_in_brick = (uint32_t(lx & 7) << 6) | (uint32_t(ly & 7) << 3) | uint32_t(lz & 7);
+  return packLeafKey(lx >> 3, ly >> 3, lz >> 3);
+}
 
 struct MapTable
 {
@@ -76,11 +102,9 @@ struct MapTable
   uint64_t* leaf_keys; // [pool_cap]
   uint64_t* leaf_mask; // [pool_cap][8]
   float* leaf_vals;    // [pool_cap][512]
-  uint32_t* leaf_dirty; // [pool_cap] 1 = in the dirty list
-  uint32_t* dirty_list; // [pool_cap]
+  uint32_t* leaf_dirty; // [pool_cap] 1 = modified since the last export
   uint32_t pool_cap;
   uint32_t* n_leaves; // device counter
-  uint32_t* n_dirty;  // device counter
 };
 
 struct LogOdds
@@ -132,33 +156,43 @@ struct RaycastArgs
   double half_res;   // resolution / 2.0
   double inv_res;    // 1.0 / resolution
   RayRec* rays;      // [n]
+  uint32_t* sort_keys; // [n] written by prep_rays: min(visits, 2^20-1); 0 for rays that need no DDA
+  uint32_t* sort_idx;  // [n] written by prep_rays: identity
+  const uint32_t* order; // [n] ray indices, longest first (LPT schedule for the DDA kernel)
 };
 
 // ---- launch wrappers (vdbm_kernels.cu) ----------------------------------------------------------------
 void launchPrepRays(const RaycastArgs& a, Counters* ctr, cudaStream_t s);
-void launchRaycastDDA(const RaycastArgs& a, UpdateTable ut, Counters* ctr, int grid, cudaStream_t s);
+void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, Counters* ctr, int grid, cudaStream_t s);
 int raycastDDAGrid(int device);
-void launchApplyUpdate(UpdateTable ut, MapTable mt, LogOdds lo, LeafRecord* change_out, uint32_t change_cap, Counters* ctr,
-                       uint32_t n_touched_hint, cudaStream_t s);
-void launchRehashUpdate(UpdateTable old_t, uint32_t old_n, UpdateTable new_t, Counters* ctr, cudaStream_t s);
+// rebuild ug.entries / counters[1] from the occupied bricks (brick count read on the device)
+void launchCompactLeaves(UpdateGrid ug, cudaStream_t s);
+void launchApplyUpdate(UpdateGrid ug, MapTable mt, LogOdds lo, LeafRecord* change_out, uint32_t change_cap, Counters* ctr,
+                       uint32_t n_entries, cudaStream_t s);
+// empty the grid after its entries were consumed (entry masks are zeroed by the consumer): reset brick keys + counters
+void launchResetBricks(UpdateGrid ug, uint32_t n_bricks, cudaStream_t s);
+// zero the masks of all listed entries (used by reset / source re-add; consumers zero masks themselves)
+void launchClearEntries(UpdateGrid ug, uint32_t n_entries, cudaStream_t s);
+void launchRehashUpdate(UpdateGrid old_g, uint32_t old_bricks, UpdateGrid new_g, Counters* ctr, cudaStream_t s);
 void launchRehashMap(MapTable mt, uint32_t n_leaves, Counters* ctr, cudaStream_t s);
-void launchGatherUpdate(UpdateTable ut, uint32_t n, const uint32_t* order, LeafRecord* out, cudaStream_t s);
-void launchImportUpdate(UpdateTable ut, const LeafRecord* recs, uint64_t n, Counters* ctr, cudaStream_t s);
-void launchClearUpdate(UpdateTable ut, uint32_t n, cudaStream_t s);
-void launchGatherMap(MapTable mt, uint32_t n, const uint32_t* leaf_idx, int32_t* origins, uint64_t* mask, float* vals,
-                     int clear_dirty, cudaStream_t s);
+void launchEntryKeys(UpdateGrid ug, uint32_t n_entries, uint64_t* out_keys, uint32_t* out_entries, cudaStream_t s);
+void launchGatherUpdate(UpdateGrid ug, uint32_t n, const uint64_t* keys, const uint32_t* entries, LeafRecord* out, cudaStream_t s);
+void launchImportUpdate(UpdateGrid ug, const LeafRecord* recs, uint64_t n, Counters* ctr, cudaStream_t s);
+void launchGatherMap(MapTable mt, uint32_t n, const uint32_t* leaf_idx, int32_t* origins, uint64_t* mask, float* vals, cudaStream_t s);
+void launchCollectDirty(MapTable mt, uint32_t n_leaves, uint32_t* out_idx, Counters* ctr, cudaStream_t s); // appends via ctr->n_out, clears flags
 void launchSection(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float,
                    uint64_t* out_keys, uint64_t* out_active, uint64_t* out_valmask, float* out_vals, uint32_t out_cap,
                    Counters* ctr, cudaStream_t s);
 void launchProbe(MapTable mt, int32_t x, int32_t y, int32_t z, float* out_val, int32_t* out_active, cudaStream_t s);
-void launchPartition(UpdateTable ut, uint32_t n, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_offsets,
+// pass 0: count entries per owner rank; pass 1: scatter records grouped by rank and zero the entry masks
+void launchPartition(UpdateGrid ug, uint32_t n_entries, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_cursor,
                      LeafRecord* out, int pass, cudaStream_t s);
-void launchKeysFromSlots(const uint64_t* keys, const uint32_t* slots, uint32_t n, uint64_t* out_keys, uint32_t* out_idx,
-                         cudaStream_t s);
-void launchIota(uint32_t* out, uint32_t n, cudaStream_t s);
-void launchUnpackOrigins(const uint64_t* keys, uint32_t n, int32_t* origins, cudaStream_t s);
+void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, uint64_t* out_keys, uint32_t* out_idx, cudaStream_t s);
 void launchSplitRecords(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s);
 uint32_t launchCount(); // kernels of this library launched by this process
+// CUB radix sort (descending) of (visit count, ray index) on key bits [4, 20); returns temp bytes when d_temp == nullptr
+size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,
+                        uint32_t* idx_out, uint32_t n, cudaStream_t s);
 // CUB radix sort of (key, idx) pairs; returns bytes of temp storage needed when d_temp == nullptr
 size_t sortPairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* idx_in,
                  uint32_t* idx_out, uint32_t n, cudaStream_t s);

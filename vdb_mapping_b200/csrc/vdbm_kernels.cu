@@ -11,8 +11,10 @@
 // can change the sequence of roundings the reference executes on an x86-64 (no-FMA) build.
 #include "vdbm_device.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cfloat>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace vdbm {
@@ -57,30 +59,36 @@ __device__ __forceinline__ void st256(float* p, const float (&v)[8])
                : "memory");
 }
 
-// ---- update-grid hash: find or insert a leaf slot (slot == storage; masks are zero for empty slots) ----
-__device__ __forceinline__ uint32_t updFindOrInsert(const UpdateTable& t, uint64_t key, Counters* ctr)
+// ---- update-grid brick hash: find or insert a brick slot (slot == storage; masks are zero for empty slots) ----
+__device__ __forceinline__ uint32_t brickFindOrInsert(const UpdateGrid& g, uint64_t bkey, Counters* ctr)
 {
-  uint32_t h = uint32_t(mix64(key)) & t.cap_mask;
-  const uint32_t max_probe = min(t.cap_mask, 4096u);
+  uint32_t h = uint32_t(mix64(bkey)) & g.cap_mask;
+  const uint32_t max_probe = min(g.cap_mask, 1024u);
   for (uint32_t probe = 0; probe <= max_probe; ++probe)
   {
-    uint64_t k = ldcg64(t.keys + h);
-    if (k == key) return h;
+    uint64_t k = ldcg64(g.bkeys + h);
+    if (k == bkey) return h;
     if (k == kEmptyKey)
     {
-      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(t.keys + h), kEmptyKey, key);
+      unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(g.bkeys + h), kEmptyKey, bkey);
       if (old == kEmptyKey)
       {
-        uint32_t idx   = atomicAdd(t.n_touched, 1u);
-        t.touched[idx] = h; // idx < cap always: at most cap successful claims
+        uint32_t idx    = atomicAdd(g.counters, 1u);
+        g.btouched[idx] = h; // idx < cap always: at most cap successful claims
         return h;
       }
-      if (old == key) return h;
+      if (old == bkey) return h;
     }
-    h = (h + 1) & t.cap_mask;
+    h = (h + 1) & g.cap_mask;
   }
   atomicOr(&ctr->flags, kFlagUpdateOverflow);
   return kInvalid;
+}
+
+// word offset (in uint64 units) of voxel (x,y,z)'s mask word inside its brick: leaf_in_brick * 8 + (x & 7)
+__device__ __forceinline__ uint32_t brickWordOffset(int x, int y, int z)
+{
+  return (uint32_t(x & 56) << 6) | (uint32_t(y & 56) << 3) | uint32_t(z & 56) | uint32_t(x & 7);
 }
 
 } // namespace
@@ -154,7 +162,9 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
         visits  = zero ? 0ull : (unsigned long long)(1 + l1); // castRayIntoGrid marks 1 + |dx|+|dy|+|dz| voxels
       }
     }
-    a.rays[i] = r;
+    a.rays[i]      = r;
+    a.sort_keys[i] = uint32_t(visits > 0xFFFFFull ? 0xFFFFFull : visits);
+    a.sort_idx[i]  = uint32_t(i);
   }
   // warp-aggregated statistics
   visits      = __reduce_add_sync(kFull, unsigned(visits)); // per-lane visits <= 1 + 3*2^24, 32 lanes fit in 32 bits
@@ -172,157 +182,304 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
 
 // ====================================================================================================
 // K1: 3D-DDA. Persistent warps; every lane owns one ray at a time and refills itself from a global cursor
-// the moment its ray ends, so ray-length variance (10..2000+ visits) costs no idle lanes.
+// when its ray ends, so ray-length variance (10..2000+ visits) costs no idle lanes.
 // Voxel stepping replays openvdb::math::DDA<Ray<double>,0> bit for bit:
 //   next[a] = 0.5*|1/dir[a]| (exact), then repeated  next[axis] += delta[axis]  in fp64,
 //   axis = MinIndex(next) with its tie table {2,1,9,1,2,9,0,0}, continue while t <= 1.0.
+// The step is branch-free (selects), so the 32 lanes stay converged whatever axis each one takes.
 // Marking: bits of consecutive visits that fall in the same (leaf, x-slice) 64-bit mask word are merged in a
-// register and flushed with ONE red.global.or.b64; x is monotonic along a ray, so every (leaf, word) pair is
-// flushed at most once per ray. Leaf slots come from the update hash on leaf change only.
+// register and flushed with ONE fire-and-forget red.global.or.b64; x is monotonic along a ray, so every mask
+// word is flushed at most once per ray. Mask words are addressed arithmetically inside a 64^3-voxel brick;
+// the brick hash is consulted only when a ray enters a new brick, and those lookups (like the ray refills) are
+// batched at warp-uniform points every kBatch iterations so that their L2 round trip is paid once per batch
+// and not once per lane event.
 // ====================================================================================================
-__global__ void __launch_bounds__(256) raycast_dda_kernel(RaycastArgs a, UpdateTable ut, Counters* ctr)
+constexpr int kBatch = 4;
+
+// MODE is a profiling hook (env VDBM_DDA_MODE, default 0): 0 = product path; 1 = no mask writes (pure traversal
+// cost); 2 = plain 64-bit stores instead of REDs (LSU path without the L2 atomic unit). Modes 1/2 give WRONG maps.
+template <int MODE>
+__device__ __forceinline__ void markWord(uint64_t* p, uint64_t v)
 {
+  if (MODE == 0) redOr64(p, v);
+  else if (MODE == 2) asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Near field: every ray starts at the sensor, so the mask words within a few leaves of it receive an update
+// from (almost) every ray: measured on B200 those same-address REDs serialise in a handful of L2 slices and cost
+// a third of the kernel. They are staged instead in a per-CTA shared-memory bitmap covering the leaf-aligned
+// 64^3-voxel cube [c0, c0+64) around the sensor (4096 mask words = 32 KB, same (leaf, x&7) word layout as the
+// global bricks) and flushed ONCE per CTA at the end.
+constexpr int kNearWords = 4096;
+
+__device__ __forceinline__ void nearOr(unsigned int* s_near, uint32_t word, uint64_t acc)
+{
+  const unsigned int lo = (unsigned int)acc, hi = (unsigned int)(acc >> 32);
+  if (lo) atomicOr(&s_near[2 * word], lo);
+  if (hi) atomicOr(&s_near[2 * word + 1], hi);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, Counters* ctr)
+{
+  __shared__ unsigned int s_near[2 * kNearWords]; // 64-bit mask words as 32-bit halves (native shared-memory atomicOr)
+  __shared__ uint32_t s_near_slot[8];
   const int lane = threadIdx.x & 31;
   const int ox = a.origin_idx[0], oy = a.origin_idx[1], oz = a.origin_idx[2];
+  // near cube origin: 4 leaves below the sensor's leaf on every axis (leaf aligned)
+  const int c0x = ((ox >> 3) - 4) << 3, c0y = ((oy >> 3) - 4) << 3, c0z = ((oz >> 3) - 4) << 3;
+  for (int i = threadIdx.x; i < 2 * kNearWords; i += blockDim.x) s_near[i] = 0u;
+  // the cube overlaps at most 2x2x2 bricks: resolve their slots once per CTA (needed for the final flush)
+  if (threadIdx.x < 8)
+  {
+    const int bx = (c0x >> 6) + (threadIdx.x >> 2), by = (c0y >> 6) + ((threadIdx.x >> 1) & 1), bz = (c0z >> 6) + (threadIdx.x & 1);
+    // only bricks the cube really reaches (the cube may sit inside a single brick along an axis)
+    const bool used = (bx <= ((c0x + 63) >> 6)) && (by <= ((c0y + 63) >> 6)) && (bz <= ((c0z + 63) >> 6));
+    s_near_slot[threadIdx.x] = used ? brickFindOrInsert(g, packLeafKey(bx, by, bz), ctr) : kInvalid;
+  }
+  __syncthreads();
+  // every ray starts in the sensor's brick
+  const uint32_t origin_slot =
+      s_near_slot[(((ox >> 6) - (c0x >> 6)) << 2) | (((oy >> 6) - (c0y >> 6)) << 1) | ((oz >> 6) - (c0z >> 6))];
 
-  bool busy = false, done = false;
+  bool busy = false, done = false, need = false;
   double n0 = 0, n1 = 0, n2 = 0, d0 = 0, d1 = 0, d2 = 0;
   int x = 0, y = 0, z = 0, sx = 0, sy = 0, sz = 0;
-  int ex = 0, ey = 0, ez = 0;
-  uint32_t rflags = 0;
-  int cur_x = INT_MIN, cur_ly = 0, cur_lz = 0;
-  uint32_t cur_slot = kInvalid;
+  uint32_t clipped = 0;
+  uint32_t slot    = kInvalid;
+  uint32_t cur_off  = kInvalid;
+  uint32_t cur_near = kInvalid; // word index in s_near when the current run lies in the near cube
   uint64_t acc      = 0;
 
-  for (;;)
+  for (uint32_t iter = 0;; ++iter)
   {
-    // ---- refill idle lanes ----
-    const unsigned need = __ballot_sync(kFull, !busy && !done);
-    if (need)
+    if ((iter & (kBatch - 1)) == 0)
     {
-      unsigned base = 0;
-      const int leader = __ffs(need) - 1;
-      if (lane == leader) base = atomicAdd(&ctr->ray_cursor, (unsigned)__popc(need));
-      base = __shfl_sync(kFull, base, leader);
-      if (!busy && !done)
+      // ---- refill idle lanes (warp-aggregated fetch from the global ray cursor) ----
+      const unsigned want = __ballot_sync(kFull, !busy && !done);
+      if (want)
       {
-        const uint64_t idx = uint64_t(base) + __popc(need & ((1u << lane) - 1u));
-        if (idx >= a.n) done = true;
-        else
+        unsigned base    = 0;
+        const int leader = __ffs(want) - 1;
+        if (lane == leader) base = atomicAdd(&ctr->ray_cursor, (unsigned)__popc(want));
+        base = __shfl_sync(kFull, base, leader);
+        if (!busy && !done)
         {
-          const RayRec r = a.rays[idx];
-          if (r.flags & kRayValid)
+          const uint64_t idx = uint64_t(base) + __popc(want & ((1u << lane) - 1u));
+          if (idx >= a.n) done = true;
+          else
           {
-            ex = r.end[0]; ey = r.end[1]; ez = r.end[2];
-            rflags = r.flags;
-            if (r.flags & kRayZeroLen)
+            const RayRec r = a.rays[a.order[idx]]; // longest rays first: the tail of the kernel is made of short rays
+            if (r.flags & kRayValid)
             {
-              // no DDA (VDBMapping.hpp:559); a non-clipped endpoint is still set on with value true (:533-536)
-              if (!(r.flags & kRayClipped))
+              if (r.flags & kRayZeroLen)
               {
-                const uint32_t slot = updFindOrInsert(ut, packLeafKey(ex >> 3, ey >> 3, ez >> 3), ctr);
-                if (slot != kInvalid)
+                // no DDA (VDBMapping.hpp:559); a non-clipped endpoint is still set on with value true (:533-536)
+                if (!(r.flags & kRayClipped) && origin_slot != kInvalid)
                 {
-                  const uint64_t bit = uint64_t(1) << (((ey & 7) << 3) | (ez & 7));
-                  redOr64(ut.active + size_t(slot) * 8 + (ex & 7), bit);
-                  redOr64(ut.value + size_t(slot) * 8 + (ex & 7), bit);
+                  const size_t w     = size_t(origin_slot) * (kBrickLeaves * 8) + brickWordOffset(ox, oy, oz);
+                  const uint64_t bit = uint64_t(1) << (((oy & 7) << 3) | (oz & 7));
+                  redOr64(g.act + w, bit);
+                  redOr64(g.val + w, bit);
                 }
               }
-            }
-            else
-            {
-              d0 = r.delta[0]; d1 = r.delta[1]; d2 = r.delta[2];
-              // DDA::init: next = t0 + (voxel + {1|0} - pos) * inv = 0.5 * |inv| exactly; DBL_MAX if dir == 0
-              n0 = (d0 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d0);
-              n1 = (d1 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d1);
-              n2 = (d2 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d2);
-              sx = (ex > ox) - (ex < ox); sy = (ey > oy) - (ey < oy); sz = (ez > oz) - (ez < oz);
-              x = ox; y = oy; z = oz;
-              cur_x = INT_MIN; cur_slot = kInvalid; acc = 0;
-              busy = true;
+              else
+              {
+                d0 = r.delta[0]; d1 = r.delta[1]; d2 = r.delta[2];
+                // DDA::init: next = t0 + (voxel + {1|0} - pos) * inv = 0.5 * |inv| exactly; DBL_MAX if dir == 0
+                n0 = (d0 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d0);
+                n1 = (d1 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d1);
+                n2 = (d2 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d2);
+                sx = (r.end[0] > ox) - (r.end[0] < ox);
+                sy = (r.end[1] > oy) - (r.end[1] < oy);
+                sz = (r.end[2] > oz) - (r.end[2] < oz);
+                x = ox; y = oy; z = oz;
+                clipped = r.flags & kRayClipped;
+                slot = origin_slot; cur_off = kInvalid; acc = 0;
+                need = false;
+                busy = true;
+              }
             }
           }
         }
       }
+      // ---- batched brick lookups for lanes that entered a new brick ----
+      if (__any_sync(kFull, busy && need))
+      {
+        if (busy && need)
+        {
+          slot = brickFindOrInsert(g, packLeafKey(x >> 6, y >> 6, z >> 6), ctr);
+          need = false;
+        }
+      }
+      if (__all_sync(kFull, done && !busy)) break;
     }
-    if (__all_sync(kFull, done && !busy)) break;
 
-    if (busy)
+    if (busy && !need)
     {
       // ---- mark current voxel (setActiveState(dda.voxel(), true), VDBMapping.hpp:563) ----
-      const int ly = y >> 3, lz = z >> 3;
-      if (x != cur_x || ly != cur_ly || lz != cur_lz)
+      const uint32_t off = brickWordOffset(x, y, z);
+      const uint64_t bit = uint64_t(1) << (((y & 7) << 3) | (z & 7));
+      uint64_t* const brick_act = g.act + size_t(slot) * (kBrickLeaves * 8);
+      if (off != cur_off)
       {
-        if (acc != 0 && cur_slot != kInvalid) redOr64(ut.active + size_t(cur_slot) * 8 + (cur_x & 7), acc);
-        const bool same_leaf = (cur_x != INT_MIN) && ((x >> 3) == (cur_x >> 3)) && ly == cur_ly && lz == cur_lz;
-        if (!same_leaf) cur_slot = updFindOrInsert(ut, packLeafKey(x >> 3, ly, lz), ctr);
-        cur_x = x; cur_ly = ly; cur_lz = lz;
-        acc = 0;
+        if (acc != 0 && slot != kInvalid)
+        {
+          if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
+          else markWord<MODE>(brick_act + cur_off, acc);
+        }
+        cur_off = off;
+        // is the new run inside the near cube? (runs never straddle it: the cube is leaf aligned)
+        {
+          const unsigned rx = unsigned(x - c0x), ry = unsigned(y - c0y), rz = unsigned(z - c0z);
+          cur_near = (rx < 64u && ry < 64u && rz < 64u) ? (((rx >> 3) << 9) | ((ry >> 3) << 6) | ((rz >> 3) << 3) | (rx & 7u)) : kInvalid;
+        }
+        acc     = 0;
       }
-      acc |= uint64_t(1) << (((y & 7) << 3) | (z & 7));
+      acc |= bit;
 
-      // ---- DDA::step(): MinIndex, t = next[axis], next[axis] += delta[axis], voxel[axis] += step[axis] ----
+      // ---- DDA::step(): axis = MinIndex(next); t = next[axis]; next[axis] += delta[axis]; voxel[axis] += step ----
       // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
-      //   (n0<n1 && n0<n2) -> 0 ; else (n1<n2) -> 1 ; else 2   (keys 2 and 5 are unreachable)
-      const bool c01 = n0 < n1, c02 = n0 < n2, c12 = n1 < n2;
-      double t;
-      if (c01 && c02) { t = n0; n0 = __dadd_rn(n0, d0); x += sx; }
-      else if (c12)   { t = n1; n1 = __dadd_rn(n1, d1); y += sy; }
-      else            { t = n2; n2 = __dadd_rn(n2, d2); z += sz; }
+      //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
+      const bool ax = (n0 < n1) && (n0 < n2);
+      const bool ay = !ax && (n1 < n2);
+      const bool az = !ax && !ay;
+      const double t  = ax ? n0 : (ay ? n1 : n2);
+      const double dl = ax ? d0 : (ay ? d1 : d2);
+      const double nn = __dadd_rn(t, dl);
+      n0 = ax ? nn : n0;
+      n1 = ay ? nn : n1;
+      n2 = az ? nn : n2;
+      x += ax ? sx : 0;
+      y += ay ? sy : 0;
+      z += az ? sz : 0;
       if (!(t <= 1.0))
       {
-        // ray finished: the voxel just stepped to is NOT marked. Flush, then the endpoint hit (:533-536).
-        if (cur_slot != kInvalid)
+        // ray finished: the voxel just stepped to is NOT marked. Flush; the last marked voxel is the end voxel,
+        // which also receives the hit unless the ray was clipped (VDBMapping.hpp:533-536).
+        if (slot != kInvalid)
         {
-          redOr64(ut.active + size_t(cur_slot) * 8 + (cur_x & 7), acc);
-          if (!(rflags & kRayClipped))
-            redOr64(ut.value + size_t(cur_slot) * 8 + (ex & 7), uint64_t(1) << (((ey & 7) << 3) | (ez & 7)));
+          if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
+          else markWord<MODE>(brick_act + cur_off, acc);
+          if (!clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
         }
         busy = false;
       }
+      else
+      {
+        // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
+        const int c  = ax ? x : (ay ? y : z);
+        const int st = ax ? sx : (ay ? sy : sz);
+        if (((c + (st < 0 ? 1 : 0)) & 63) == 0)
+        {
+          if (slot != kInvalid)
+          {
+            if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
+            else markWord<MODE>(brick_act + cur_off, acc);
+          }
+          acc     = 0;
+          cur_off = kInvalid;
+          need    = true;
+        }
+      }
+    }
+  }
+
+  // ---- flush the near-field bitmap: one RED per non-zero word and CTA ----
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNearWords; i += blockDim.x)
+  {
+    const unsigned long long v = (unsigned long long)s_near[2 * i] | ((unsigned long long)s_near[2 * i + 1] << 32);
+    if (v == 0ull) continue;
+    // word i = (leaf lx,ly,lz in the cube) * 8 + (x & 7)
+    const int lx = i >> 9, ly = (i >> 6) & 7, lz = (i >> 3) & 7, xw = i & 7;
+    const int vx = c0x + (lx << 3) + xw, vy = c0y + (ly << 3), vz = c0z + (lz << 3);
+    const uint32_t bs = s_near_slot[(((vx >> 6) - (c0x >> 6)) << 2) | (((vy >> 6) - (c0y >> 6)) << 1) | ((vz >> 6) - (c0z >> 6))];
+    if (bs != kInvalid) markWord<MODE>(g.act + size_t(bs) * (kBrickLeaves * 8) + brickWordOffset(vx, vy, vz), v);
+  }
+}
+
+// ====================================================================================================
+// K1b: rebuild the compact list of touched leaves from the occupied bricks. One block per brick, one thread per
+// leaf (512); a leaf is touched iff its 64-byte active mask is non-zero.
+// ====================================================================================================
+__global__ void __launch_bounds__(512) compact_leaves_kernel(UpdateGrid g)
+{
+  const int lane          = threadIdx.x & 31;
+  const uint32_t n_bricks = min(g.counters[0], g.cap_mask + 1u); // device-side count: no host round trip needed
+  for (uint32_t b = blockIdx.x; b < n_bricks; b += gridDim.x)
+  {
+    const uint32_t slot = g.btouched[b];
+    const uint32_t e    = slot * kBrickLeaves + threadIdx.x;
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(g.act + size_t(e) * 8);
+    const ulonglong2 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
+    const bool nz       = (q0.x | q0.y | q1.x | q1.y | q2.x | q2.y | q3.x | q3.y) != 0;
+    const unsigned m    = __ballot_sync(kFull, nz);
+    if (m)
+    {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(g.counters + 1, (uint32_t)__popc(m));
+      base = __shfl_sync(kFull, base, 0);
+      if (nz) g.entries[base + __popc(m & ((1u << lane) - 1u))] = e;
     }
   }
 }
 
 // ====================================================================================================
-// K2: updateMap. One warp per touched update leaf; lane L owns the 16 consecutive voxels [16L, 16L+16)
-// (= 64 contiguous bytes of leaf values, moved with two 256-bit loads/stores). Streaming RMW over the map leaf.
+// K2: updateMap. Warps take batches of 32 touched leaves.
+//  phase 1 (lane-parallel): every lane resolves ONE leaf: entry -> leaf key -> map hash probe / insert; new
+//          leaves are allocated with one warp-aggregated atomicAdd. 32 independent dependent-load chains are in
+//          flight per warp instead of one.
+//  phase 2 (warp-cooperative): for each of the 32 leaves, lane L owns the 16 consecutive voxels [16L, 16L+16)
+//          (= 64 contiguous bytes of leaf values, moved with two 256-bit loads/stores): streaming RMW of the map
+//          leaf with the update masks of the NEXT leaf prefetched while the current one is processed.
+// The update masks are zeroed as they are consumed (the grid is empty again afterwards, VDBMapping.hpp:384).
 // ====================================================================================================
-__global__ void __launch_bounds__(256) apply_update_kernel(UpdateTable ut, MapTable mt, LogOdds lo, LeafRecord* change_out,
-                                                          uint32_t change_cap, Counters* ctr)
+struct UpdMasks
+{
+  uint64_t A, V, M; // update active word, update value word, old map active word (held by lanes 0..7)
+};
+
+__device__ __forceinline__ UpdMasks loadMasks(const UpdateGrid& g, const MapTable& mt, uint32_t e, uint32_t leaf, int is_new, int lane)
+{
+  UpdMasks m{0, 0, 0};
+  if (lane < 8)
+  {
+    m.A = g.act[size_t(e) * 8 + lane];
+    m.V = g.val[size_t(e) * 8 + lane];
+    if (leaf != kInvalid && !is_new) m.M = mt.leaf_mask[size_t(leaf) * 8 + lane];
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(256, 4) apply_update_kernel(UpdateGrid g, MapTable mt, LogOdds lo, LeafRecord* change_out,
+                                                             uint32_t change_cap, Counters* ctr, uint32_t n)
 {
   const int lane         = threadIdx.x & 31;
   const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t n       = *ut.n_touched;
-  unsigned long long upd_total = 0, chg_total = 0, new_total = 0;
+  unsigned upd_total = 0, chg_total = 0, new_total = 0;
 
-  for (uint32_t i = warp; i < n; i += n_warps)
+  for (uint32_t base = warp * 32; base < n; base += n_warps * 32)
   {
-    const uint32_t slot = ut.touched[i];
-    const uint64_t key  = ut.keys[slot];
-    uint64_t A = 0, V = 0;
-    if (lane < 8)
+    // ---------------- phase 1: one leaf per lane ----------------
+    const uint32_t i = base + lane;
+    uint32_t e = 0, leaf = kInvalid, hslot = 0;
+    int is_new   = 0;
+    uint64_t key = 0;
+    if (i < n)
     {
-      A = ut.active[size_t(slot) * 8 + lane];
-      V = ut.value[size_t(slot) * 8 + lane];
-      // consume: leave the slot clean for the next accumulation period (VDBMapping.hpp:384)
-      ut.active[size_t(slot) * 8 + lane] = 0;
-      ut.value[size_t(slot) * 8 + lane]  = 0;
-    }
-    if (lane == 0) ut.keys[slot] = kEmptyKey;
-
-    const unsigned nz_words = __ballot_sync(kFull, A != 0) & 0xFFu;
-    if (nz_words == 0) continue; // nothing active (can only happen for imported empty records)
-    const unsigned hit_words = __ballot_sync(kFull, V != 0) & 0xFFu;
-
-    // ---- find or create the map leaf (lane 0 probes; keys are unique per launch, so no same-key races) ----
-    // OpenVDB tile probe: on a missing leaf a miss whose probe result is (0.0f, inactive) does not create it.
-    const bool create_ok = !lo.miss_probe_no_create || hit_words != 0;
-    uint32_t leaf = kInvalid;
-    int is_new    = 0;
-    if (lane == 0)
-    {
+      e   = g.entries[i];
+      key = leafKeyOfEntry(g.bkeys[e >> 9], e & 511u);
+      // OpenVDB tile probe: on a missing leaf a miss whose probe result is (0.0f, inactive) does not create it
+      bool create_ok = true;
+      if (lo.miss_probe_no_create)
+      {
+        uint64_t any_hit = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) any_hit |= g.val[size_t(e) * 8 + w];
+        create_ok = any_hit != 0;
+      }
       uint32_t h = uint32_t(mix64(key)) & mt.hcap_mask;
       for (uint32_t probe = 0; probe <= mt.hcap_mask; ++probe)
       {
@@ -331,159 +488,216 @@ __global__ void __launch_bounds__(256) apply_update_kernel(UpdateTable ut, MapTa
         if (k == kEmptyKey)
         {
           if (!create_ok) break;
+          // keys are unique within a launch, so nobody else inserts THIS key; another key may win this slot
           unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(mt.hkeys + h), kEmptyKey, key);
-          if (old == kEmptyKey)
-          {
-            const uint32_t li = atomicAdd(mt.n_leaves, 1u);
-            if (li >= mt.pool_cap) { atomicOr(&ctr->flags, kFlagMapOverflow); break; }
-            mt.hvals[h]      = li;
-            mt.leaf_keys[li] = key;
-            leaf             = li;
-            is_new           = 1;
-            break;
-          }
+          if (old == kEmptyKey) { is_new = 1; hslot = h; break; }
         }
         h = (h + 1) & mt.hcap_mask;
       }
-      if (leaf != kInvalid && atomicExch(mt.leaf_dirty + leaf, 1u) == 0u) mt.dirty_list[atomicAdd(mt.n_dirty, 1u)] = leaf;
     }
-    leaf   = __shfl_sync(kFull, leaf, 0);
-    is_new = __shfl_sync(kFull, is_new, 0);
-
-    const int w  = lane >> 2;        // mask word of this lane's 16 voxels
-    const int sh = (lane & 3) << 4;  // bit offset inside the word
-    const uint32_t ua = uint32_t(shfl64(A, w) >> sh) & 0xFFFFu; // active update bits
-    const uint32_t uv = uint32_t(shfl64(V, w) >> sh) & 0xFFFFu; // hit bits
-
-    // lowest-offset active update voxel of the leaf (first one the reference visits): offset n_first
-    const int w_first      = __ffs(nz_words) - 1;
-    const uint64_t a_first = shfl64(A, w_first), v_first = shfl64(V, w_first);
-    const int b_first      = __ffsll((long long)a_first) - 1;
-    const int n_first      = (w_first << 6) | b_first;
-    const bool first_is_hit = (v_first >> b_first) & 1;
-
-    uint32_t ca = 0, cv = 0; // change-grid bits of this lane's 16 voxels
-    if (leaf == kInvalid)
+    const unsigned new_mask = __ballot_sync(kFull, is_new);
+    if (new_mask)
     {
-      // no leaf and none may be created: every (miss) voxel only runs the tile probe. With the quirk each of
-      // them is reported when the probe flipped the inverted state (VDBMapping.hpp:743-750 via the lambda).
-      if (lo.replicate_quirk && lo.miss_probe_flips) ca = ua & ~uv;
-    }
-    else
-    {
-      uint64_t M = 0;
-      if (lane < 8 && !is_new) M = mt.leaf_mask[size_t(leaf) * 8 + lane];
-      const uint32_t oa = uint32_t(shfl64(M, w) >> sh) & 0xFFFFu;
-      float* vp = mt.leaf_vals + size_t(leaf) * 512 + lane * 16;
-      float v0[8], v1[8];
-      const bool touch = (ua != 0);
-      if (!is_new && touch) { ld256(vp, v0); ld256(vp + 8, v1); }
-      else
+      uint32_t first = 0;
+      if (lane == 0) first = atomicAdd(mt.n_leaves, (uint32_t)__popc(new_mask));
+      first = __shfl_sync(kFull, first, 0);
+      if (is_new)
       {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { v0[j] = 0.0f; v1[j] = 0.0f; }
-      }
-      uint32_t na = oa;
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-      {
-        const bool a_ = (ua >> j) & 1, h_ = (uv >> j) & 1, o_ = (oa >> j) & 1;
-        float& ref = (j < 8) ? v0[j & 7] : v1[j & 7];
-        // OccupancyVDBMapping.hpp:92-117 (clamping only inside the threshold branch)
-        float nv  = __fadd_rn(ref, h_ ? lo.hit : lo.miss);
-        bool act  = o_;
-        if (h_) { if (nv > lo.thres_max) { act = true;  if (nv > lo.max_lo) nv = lo.max_lo; } }
-        else    { if (nv < lo.thres_min) { act = false; if (nv < lo.min_lo) nv = lo.min_lo; } }
-        if (a_)
+        const uint32_t li = first + __popc(new_mask & ((1u << lane) - 1u));
+        if (li < mt.pool_cap)
         {
-          ref = nv;
-          na  = (na & ~(1u << j)) | (uint32_t(act) << j);
-          const bool changed = (act != o_);
-          ca |= uint32_t(changed) << j;
-          cv |= uint32_t(changed && h_) << j;
-        }
-      }
-      if (is_new || touch) { st256(vp, v0); st256(vp + 8, v1); }
-      // assemble the new 64-bit active word from the 4 lanes that share it
-      uint64_t piece = uint64_t(na) << sh;
-      piece |= shflXor64(piece, 1);
-      piece |= shflXor64(piece, 2);
-      if ((lane & 3) == 0) mt.leaf_mask[size_t(leaf) * 8 + w] = piece;
-
-      // tile-probe quirk: first visited voxel of a leaf that did not exist, if it is a miss whose
-      // probe flips the inverted tile state, is reported as changed although its flag did not change.
-      if (is_new && lo.replicate_quirk && lo.miss_probe_flips)
-      {
-        if (!lo.miss_probe_no_create)
-        {
-          if (!first_is_hit && (n_first >> 4) == lane) ca |= 1u << (n_first & 15);
+          mt.hvals[hslot]  = li;
+          mt.leaf_keys[li] = key;
+          leaf             = li;
         }
         else
         {
-          // degenerate config: misses do not create the leaf, so every miss BEFORE the first hit was probed
-          const int wh       = __ffs(hit_words) - 1;
-          const uint64_t vh  = shfl64(V, wh);
-          const int n_hit    = (wh << 6) | (__ffsll((long long)vh) - 1);
-          const int lo_n     = lane << 4;
-          uint32_t before    = 0;
-          if (n_hit >= lo_n + 16) before = 0xFFFFu;
-          else if (n_hit > lo_n) before = (1u << (n_hit - lo_n)) - 1u;
-          ca |= ua & ~uv & before;
+          atomicOr(&ctr->flags, kFlagMapOverflow); // host sizes the pool before the launch; cannot happen
+          is_new = 0;
         }
       }
+      new_total += __popc(new_mask);
     }
+    if (leaf != kInvalid) mt.leaf_dirty[leaf] = 1u;
 
-    upd_total += __popc(ua);
-    chg_total += __popc(ca);
-    new_total += (lane == 0 && is_new) ? 1 : 0;
-
-    if (change_out != nullptr)
+    // ---------------- phase 2: warp-cooperative RMW, one leaf at a time ----------------
+    const int cnt = int(min(32u, n - base));
+    const int w   = lane >> 2;       // mask word of this lane's 16 voxels
+    const int sh  = (lane & 3) << 4; // bit offset inside the word
+    UpdMasks nxt  = loadMasks(g, mt, __shfl_sync(kFull, e, 0), __shfl_sync(kFull, leaf, 0), __shfl_sync(kFull, is_new, 0), lane);
+    for (int j = 0; j < cnt; ++j)
     {
-      uint64_t pa = uint64_t(ca) << sh, pv = uint64_t(cv) << sh;
-      pa |= shflXor64(pa, 1); pa |= shflXor64(pa, 2);
-      pv |= shflXor64(pv, 1); pv |= shflXor64(pv, 2);
-      const unsigned any = __ballot_sync(kFull, ca != 0);
-      if (any)
+      const uint32_t e_j    = __shfl_sync(kFull, e, j);
+      const uint32_t leaf_j = __shfl_sync(kFull, leaf, j);
+      const int new_j       = __shfl_sync(kFull, is_new, j);
+      const UpdMasks cur    = nxt;
+      if (j + 1 < cnt) // prefetch the next leaf's masks while this one is processed
+        nxt = loadMasks(g, mt, __shfl_sync(kFull, e, j + 1), __shfl_sync(kFull, leaf, j + 1), __shfl_sync(kFull, is_new, j + 1), lane);
+      // consume: leave the update masks clean for the next accumulation period
+      if (lane < 8)
       {
-        uint32_t ci = 0;
-        if (lane == 0) ci = atomicAdd(&ctr->n_change, 1u);
-        ci = __shfl_sync(kFull, ci, 0);
-        if (ci < change_cap)
+        g.act[size_t(e_j) * 8 + lane] = 0;
+        g.val[size_t(e_j) * 8 + lane] = 0;
+      }
+      const uint32_t ua = uint32_t(shfl64(cur.A, w) >> sh) & 0xFFFFu; // active update bits of my 16 voxels
+      const uint32_t uv = uint32_t(shfl64(cur.V, w) >> sh) & 0xFFFFu; // hit bits
+      const unsigned nz_words  = __ballot_sync(kFull, cur.A != 0) & 0xFFu;
+      const unsigned hit_words = __ballot_sync(kFull, cur.V != 0) & 0xFFu;
+
+      uint32_t ca = 0, cv = 0; // change-grid bits of this lane's 16 voxels
+      if (leaf_j == kInvalid)
+      {
+        // no leaf and none may be created: every (miss) voxel only runs the tile probe. With the quirk each of
+        // them is reported when the probe flipped the inverted state (VDBMapping.hpp:743-750 via the lambda).
+        if (lo.replicate_quirk && lo.miss_probe_flips) ca = ua & ~uv;
+      }
+      else
+      {
+        const uint32_t oa = uint32_t(shfl64(cur.M, w) >> sh) & 0xFFFFu;
+        float* vp = mt.leaf_vals + size_t(leaf_j) * 512 + lane * 16;
+        float v0[8], v1[8];
+        const bool touch = (ua != 0);
+        if (!new_j && touch) { ld256(vp, v0); ld256(vp + 8, v1); }
+        else
         {
-          LeafRecord* r = change_out + ci;
-          if (lane == 0) r->key = key;
-          if ((lane & 3) == 0) { r->active[w] = pa; r->value[w] = pv; }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { v0[q] = 0.0f; v1[q] = 0.0f; }
+        }
+        // OccupancyVDBMapping.hpp:92-117, branch-free (all 32 lanes stay converged whatever mix of hits/misses):
+        //   nv = v + (hit ? logodds_hit : logodds_miss)
+        //   P  = hit ? (nv > thres_max) : (nv < thres_min)              threshold crossed
+        //   nv = P ? (hit ? min(nv, max_logodds) : max(nv, min_logodds)) : nv   (clamp only inside the threshold branch)
+        //   active = P ? hit : old_active
+        uint32_t pm = 0; // P bits of my 16 voxels
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+        {
+          const bool a_ = (ua >> q) & 1, h_ = (uv >> q) & 1;
+          float& ref    = (q < 8) ? v0[q & 7] : v1[q & 7];
+          const float nv  = __fadd_rn(ref, h_ ? lo.hit : lo.miss);
+          const bool P    = h_ ? (nv > lo.thres_max) : (nv < lo.thres_min);
+          const float cl  = h_ ? fminf(nv, lo.max_lo) : fmaxf(nv, lo.min_lo);
+          const float nv2 = P ? cl : nv;
+          ref = a_ ? nv2 : ref;
+          pm |= uint32_t(P) << q;
+        }
+        // bit-parallel mask algebra on the 16 voxels
+        const uint32_t act = (pm & uv) | (~pm & oa); // P ? hit : old
+        const uint32_t na  = (ua & act) | (~ua & oa);
+        const uint32_t chg = ua & (act ^ oa);        // VDBMapping.hpp:746-749: flag flipped
+        ca |= chg;
+        cv |= chg & uv;                              // :772 setValueOn(true) for hits, :780 setActiveState for misses
+        if (new_j || touch) { st256(vp, v0); st256(vp + 8, v1); }
+        // assemble the new 64-bit active word from the 4 lanes that share it
+        uint64_t piece = uint64_t(na) << sh;
+        piece |= shflXor64(piece, 1);
+        piece |= shflXor64(piece, 2);
+        if ((lane & 3) == 0) mt.leaf_mask[size_t(leaf_j) * 8 + w] = piece;
+
+        // tile-probe quirk: the first visited voxel (lowest offset) of a leaf that did not exist, if it
+        // is a miss whose probe flips the inverted tile state, is reported as changed although its flag did not.
+        if (new_j && lo.replicate_quirk && lo.miss_probe_flips)
+        {
+          if (!lo.miss_probe_no_create)
+          {
+            const int w_first       = __ffs(nz_words) - 1;
+            const uint64_t a_first  = shfl64(cur.A, w_first), v_first = shfl64(cur.V, w_first);
+            const int b_first       = __ffsll((long long)a_first) - 1;
+            const int n_first       = (w_first << 6) | b_first;
+            const bool first_is_hit = (v_first >> b_first) & 1;
+            if (!first_is_hit && (n_first >> 4) == lane) ca |= 1u << (n_first & 15);
+          }
+          else
+          {
+            // degenerate config: misses do not create the leaf, so every miss BEFORE the first hit was probed
+            const int wh      = __ffs(hit_words) - 1;
+            const uint64_t vh = shfl64(cur.V, wh);
+            const int n_hit   = (wh << 6) | (__ffsll((long long)vh) - 1);
+            const int lo_n    = lane << 4;
+            uint32_t before   = 0;
+            if (n_hit >= lo_n + 16) before = 0xFFFFu;
+            else if (n_hit > lo_n) before = (1u << (n_hit - lo_n)) - 1u;
+            ca |= ua & ~uv & before;
+          }
+        }
+      }
+      upd_total += __popc(ua);
+      chg_total += __popc(ca);
+
+      if (change_out != nullptr)
+      {
+        const unsigned any = __ballot_sync(kFull, ca != 0);
+        if (any)
+        {
+          uint64_t pa = uint64_t(ca) << sh, pv = uint64_t(cv) << sh;
+          pa |= shflXor64(pa, 1); pa |= shflXor64(pa, 2);
+          pv |= shflXor64(pv, 1); pv |= shflXor64(pv, 2);
+          const uint64_t key_j = shfl64(key, j);
+          uint32_t ci = 0;
+          if (lane == 0) ci = atomicAdd(&ctr->n_change, 1u);
+          ci = __shfl_sync(kFull, ci, 0);
+          if (ci < change_cap)
+          {
+            LeafRecord* r = change_out + ci;
+            if (lane == 0) r->key = key_j;
+            if ((lane & 3) == 0) { r->active[w] = pa; r->value[w] = pv; }
+          }
         }
       }
     }
   }
   // per-warp totals -> global counters
-  upd_total = __reduce_add_sync(kFull, unsigned(upd_total));
-  chg_total = __reduce_add_sync(kFull, unsigned(chg_total));
-  new_total = __reduce_add_sync(kFull, unsigned(new_total));
+  upd_total = __reduce_add_sync(kFull, upd_total);
+  chg_total = __reduce_add_sync(kFull, chg_total);
   if (lane == 0)
   {
-    if (upd_total) atomicAdd(&ctr->voxel_updates, upd_total);
-    if (chg_total) atomicAdd(&ctr->state_changes, chg_total);
-    if (new_total) atomicAdd(&ctr->new_leaves, new_total);
+    if (upd_total) atomicAdd(&ctr->voxel_updates, (unsigned long long)upd_total);
+    if (chg_total) atomicAdd(&ctr->state_changes, (unsigned long long)chg_total);
+    if (new_total) atomicAdd(&ctr->new_leaves, (unsigned long long)new_total);
   }
 }
 
 // ====================================================================================================
 // growth / import / export helpers
 // ====================================================================================================
-__global__ void rehash_update_kernel(UpdateTable old_t, uint32_t old_n, UpdateTable new_t, Counters* ctr)
+// after the entries were consumed (their masks are zero again): forget the bricks
+__global__ void reset_bricks_kernel(UpdateGrid g, uint32_t n_bricks)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= old_n) return;
-  const uint32_t s  = old_t.touched[i];
-  const uint32_t ns = updFindOrInsert(new_t, old_t.keys[s], ctr);
-  if (ns == kInvalid) return;
-#pragma unroll
-  for (int w = 0; w < 8; ++w)
+  if (i < n_bricks) g.bkeys[g.btouched[i]] = kEmptyKey;
+  if (i == 0) { g.counters[0] = 0; g.counters[1] = 0; }
+}
+
+__global__ void clear_entries_kernel(UpdateGrid g, uint32_t n_entries)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = t >> 4;
+  const int j      = t & 15;
+  if (i >= n_entries) return;
+  const uint32_t e = g.entries[i];
+  if (j < 8) g.act[size_t(e) * 8 + j] = 0;
+  else g.val[size_t(e) * 8 + (j - 8)] = 0;
+}
+
+// copy every occupied brick of the old grid into the (bigger) new grid; one block per brick
+__global__ void __launch_bounds__(256) rehash_update_kernel(UpdateGrid old_g, uint32_t old_bricks, UpdateGrid new_g, Counters* ctr)
+{
+  __shared__ uint32_t s_slot;
+  for (uint32_t b = blockIdx.x; b < old_bricks; b += gridDim.x)
   {
-    new_t.active[size_t(ns) * 8 + w] = old_t.active[size_t(s) * 8 + w];
-    new_t.value[size_t(ns) * 8 + w]  = old_t.value[size_t(s) * 8 + w];
+    const uint32_t os = old_g.btouched[b];
+    if (threadIdx.x == 0) s_slot = brickFindOrInsert(new_g, old_g.bkeys[os], ctr);
+    __syncthreads();
+    const uint32_t ns = s_slot;
+    if (ns != kInvalid)
+    {
+      const ulonglong2* sa = reinterpret_cast<const ulonglong2*>(old_g.act + size_t(os) * (kBrickLeaves * 8));
+      const ulonglong2* sv = reinterpret_cast<const ulonglong2*>(old_g.val + size_t(os) * (kBrickLeaves * 8));
+      ulonglong2* da       = reinterpret_cast<ulonglong2*>(new_g.act + size_t(ns) * (kBrickLeaves * 8));
+      ulonglong2* dv       = reinterpret_cast<ulonglong2*>(new_g.val + size_t(ns) * (kBrickLeaves * 8));
+      for (int k = threadIdx.x; k < kBrickLeaves * 4; k += blockDim.x) { da[k] = sa[k]; dv[k] = sv[k]; }
+    }
+    __syncthreads();
   }
 }
 
@@ -502,7 +716,7 @@ __global__ void rehash_map_kernel(MapTable mt, uint32_t n_leaves, Counters* ctr)
   atomicOr(&ctr->flags, kFlagMapOverflow);
 }
 
-__global__ void import_update_kernel(UpdateTable ut, const LeafRecord* recs, uint64_t n, Counters* ctr)
+__global__ void import_update_kernel(UpdateGrid g, const LeafRecord* recs, uint64_t n, Counters* ctr)
 {
   // 16 lanes per record: lane j<8 ORs active[j], lane 8..15 ORs value[j-8]
   const uint64_t t   = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -516,65 +730,52 @@ __global__ void import_update_kernel(UpdateTable ut, const LeafRecord* recs, uin
     word = (j < 8) ? recs[rec].active[j] : recs[rec].value[j - 8];
   }
   // the 16 lanes of a record agree on whether it has any active bit
-  const unsigned grp   = 0xFFFFu << (threadIdx.x & 16);
-  const unsigned nz    = __ballot_sync(kFull, valid && j < 8 && word != 0) & grp;
-  uint32_t slot        = kInvalid;
-  if (valid && nz && j == 0) slot = updFindOrInsert(ut, key, ctr);
+  const unsigned grp = 0xFFFFu << (threadIdx.x & 16);
+  const unsigned nz  = __ballot_sync(kFull, valid && j < 8 && word != 0) & grp;
+  uint32_t slot = kInvalid, lib = 0;
+  if (valid && nz && j == 0)
+  {
+    const uint64_t bkey = brickKeyOfLeaf(key, lib);
+    slot                = brickFindOrInsert(g, bkey, ctr);
+  }
   slot = __shfl_sync(kFull, slot, (threadIdx.x & 16));
+  lib  = __shfl_sync(kFull, lib, (threadIdx.x & 16));
   if (slot == kInvalid || word == 0) return;
-  uint64_t* dst = (j < 8) ? ut.active + size_t(slot) * 8 + j : ut.value + size_t(slot) * 8 + (j - 8);
+  const size_t e = size_t(slot) * kBrickLeaves + lib;
+  uint64_t* dst  = (j < 8) ? g.act + e * 8 + j : g.val + e * 8 + (j - 8);
   redOr64(dst, word);
 }
 
-__global__ void clear_update_kernel(UpdateTable ut, uint32_t n)
-{
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t i = t >> 4;
-  const int j      = t & 15;
-  if (i >= n) return;
-  const uint32_t s = ut.touched[i];
-  if (j < 8) ut.active[size_t(s) * 8 + j] = 0;
-  else ut.value[size_t(s) * 8 + (j - 8)] = 0;
-  if (j == 0) ut.keys[s] = kEmptyKey;
-}
-
-__global__ void keys_from_slots_kernel(const uint64_t* keys, const uint32_t* slots, uint32_t n, uint64_t* out_keys, uint32_t* out_idx)
+// leaf keys of the listed entries (+ the entry ids, for sorting)
+__global__ void entry_keys_kernel(UpdateGrid g, uint32_t n, uint64_t* out_keys, uint32_t* out_entries)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t s = slots ? slots[i] : i;
+  const uint32_t e = g.entries[i];
+  out_keys[i]      = leafKeyOfEntry(g.bkeys[e >> 9], e & 511u);
+  out_entries[i]   = e;
+}
+
+__global__ void keys_from_idx_kernel(const uint64_t* keys, const uint32_t* idx, uint32_t n, uint64_t* out_keys, uint32_t* out_idx)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = idx ? idx[i] : i;
   out_keys[i]      = keys[s];
   out_idx[i]       = s;
 }
 
-__global__ void iota_kernel(uint32_t* out, uint32_t n)
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = i;
-}
-
-__global__ void unpack_origins_kernel(const uint64_t* keys, uint32_t n, int32_t* origins)
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int32_t x, y, z;
-  unpackLeafOrigin(keys[i], x, y, z);
-  origins[3 * size_t(i) + 0] = x;
-  origins[3 * size_t(i) + 1] = y;
-  origins[3 * size_t(i) + 2] = z;
-}
-
-// update-grid leaves in `order` (slot indices) -> records
-__global__ void gather_update_kernel(UpdateTable ut, uint32_t n, const uint32_t* order, LeafRecord* out)
+// update-grid leaves (sorted keys + their entries) -> records
+__global__ void gather_update_kernel(UpdateGrid g, uint32_t n, const uint64_t* keys, const uint32_t* entries, LeafRecord* out)
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = t >> 4;
   const int j      = t & 15;
   if (i >= n) return;
-  const uint32_t s = order[i];
-  if (j < 8) out[i].active[j] = ut.active[size_t(s) * 8 + j];
-  else out[i].value[j - 8] = ut.value[size_t(s) * 8 + (j - 8)];
-  if (j == 0) out[i].key = ut.keys[s];
+  const uint32_t e = entries[i];
+  if (j < 8) out[i].active[j] = g.act[size_t(e) * 8 + j];
+  else out[i].value[j - 8] = g.val[size_t(e) * 8 + (j - 8)];
+  if (j == 0) out[i].key = keys[i];
 }
 
 __global__ void split_records_kernel(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value)
@@ -593,9 +794,9 @@ __global__ void split_records_kernel(const LeafRecord* recs, uint32_t n, int32_t
   }
 }
 
-// map leaves listed in leaf_idx -> SoA staging (one warp per leaf, 2 KB values with 256-bit accesses)
+// K4: map leaves listed in leaf_idx -> SoA staging (one warp per leaf, 2 KB values with 256-bit accesses)
 __global__ void __launch_bounds__(256) gather_map_kernel(MapTable mt, uint32_t n, const uint32_t* leaf_idx, int32_t* origins,
-                                                        uint64_t* mask, float* vals, int clear_dirty)
+                                                        uint64_t* mask, float* vals)
 {
   const int lane         = threadIdx.x & 31;
   const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -614,9 +815,27 @@ __global__ void __launch_bounds__(256) gather_map_kernel(MapTable mt, uint32_t n
       int32_t x, y, z;
       unpackLeafOrigin(mt.leaf_keys[l], x, y, z);
       origins[3 * size_t(i)] = x; origins[3 * size_t(i) + 1] = y; origins[3 * size_t(i) + 2] = z;
-      if (clear_dirty) mt.leaf_dirty[l] = 0;
     }
   }
+}
+
+// dirty leaves -> index list (warp-aggregated append through ctr->n_out); flags are cleared
+__global__ void collect_dirty_kernel(MapTable mt, uint32_t n_leaves, uint32_t* out_idx, Counters* ctr)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane   = threadIdx.x & 31;
+  bool d = false;
+  if (i < n_leaves)
+  {
+    d = mt.leaf_dirty[i] != 0;
+    if (d) mt.leaf_dirty[i] = 0;
+  }
+  const unsigned m = __ballot_sync(kFull, d);
+  if (!m) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&ctr->n_out, (uint32_t)__popc(m));
+  base = __shfl_sync(kFull, base, 0);
+  if (d) out_idx[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 // K3: getMapSection. One warp per map leaf; overlapping leaves with content inside the box are appended
@@ -724,14 +943,14 @@ __global__ void probe_kernel(MapTable mt, int32_t x, int32_t y, int32_t z, float
   }
 }
 
-// multi-GPU: bin touched update leaves by owner rank. pass 0 counts, pass 1 scatters (and clears the slots).
-__global__ void partition_kernel(UpdateTable ut, uint32_t n, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_cursor,
+// multi-GPU: bin touched update leaves by owner rank. pass 0 counts, pass 1 scatters (and zeroes the entry masks).
+__global__ void partition_kernel(UpdateGrid g, uint32_t n, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_cursor,
                                  LeafRecord* out, int pass)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t s   = ut.touched[i];
-  const uint64_t key = ut.keys[s];
+  const uint32_t e   = g.entries[i];
+  const uint64_t key = leafKeyOfEntry(g.bkeys[e >> 9], e & 511u);
   const int32_t r    = leafOwner(key, n_ranks);
   if (pass == 0) { atomicAdd(rank_counts + r, 1u); return; }
   const uint32_t dst = atomicAdd(rank_cursor + r, 1u);
@@ -739,12 +958,11 @@ __global__ void partition_kernel(UpdateTable ut, uint32_t n, int32_t n_ranks, ui
 #pragma unroll
   for (int w = 0; w < 8; ++w)
   {
-    out[dst].active[w] = ut.active[size_t(s) * 8 + w];
-    out[dst].value[w]  = ut.value[size_t(s) * 8 + w];
-    ut.active[size_t(s) * 8 + w] = 0;
-    ut.value[size_t(s) * 8 + w]  = 0;
+    out[dst].active[w] = g.act[size_t(e) * 8 + w];
+    out[dst].value[w]  = g.val[size_t(e) * 8 + w];
+    g.act[size_t(e) * 8 + w] = 0;
+    g.val[size_t(e) * 8 + w] = 0;
   }
-  ut.keys[s] = kEmptyKey;
 }
 
 // ====================================================================================================
@@ -754,112 +972,147 @@ static inline unsigned blocksFor(uint64_t n, unsigned per_block) { return unsign
 
 static std::atomic<uint32_t> g_launches{0};
 uint32_t launchCount() { return g_launches.load(); }
-#define VDBM_COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+#define VDBM_LAUNCH(kernel, grid, block, stream, ...)                 \
+  do                                                                  \
+  {                                                                   \
+    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);            \
+    g_launches.fetch_add(1, std::memory_order_relaxed);               \
+  } while (0)
+
+static int smCount()
+{
+  static int sms = 0;
+  if (!sms)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
 
 void launchPrepRays(const RaycastArgs& a, Counters* ctr, cudaStream_t s)
 {
   if (a.n == 0) return;
-  { prep_rays_kernel<<<blocksFor(a.n, 256), 256, 0, s>>>(a, ctr); VDBM_COUNT_LAUNCH(); }
+  VDBM_LAUNCH(prep_rays_kernel, blocksFor(a.n, 256), 256, s, a, ctr);
 }
 
 int raycastDDAGrid(int device)
 {
   int sms = 148, per_sm = 4;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_dda_kernel, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_dda_kernel<0>, 256, 0);
   if (per_sm < 1) per_sm = 1;
-  return sms * per_sm; // persistent: one wave exactly
+  return sms * per_sm; // persistent: exactly one resident wave
 }
 
-void launchRaycastDDA(const RaycastArgs& a, UpdateTable ut, Counters* ctr, int grid, cudaStream_t s)
+void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, Counters* ctr, int grid, cudaStream_t s)
 {
   if (a.n == 0) return;
-  const uint64_t warps_needed = (a.n + 31) / 32;
-  const uint64_t blocks       = (warps_needed + 7) / 8;
+  const uint64_t blocks = (((a.n + 31) / 32) + 7) / 8;
   if (uint64_t(grid) > blocks) grid = int(blocks);
-  { raycast_dda_kernel<<<grid, 256, 0, s>>>(a, ut, ctr); VDBM_COUNT_LAUNCH(); }
+  static const int mode = [] { const char* e = getenv("VDBM_DDA_MODE"); return e ? atoi(e) : 0; }();
+  if (mode == 1) VDBM_LAUNCH(raycast_dda_kernel<1>, grid, 256, s, a, g, ctr);
+  else if (mode == 2) VDBM_LAUNCH(raycast_dda_kernel<2>, grid, 256, s, a, g, ctr);
+  else VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, ctr);
 }
 
-void launchApplyUpdate(UpdateTable ut, MapTable mt, LogOdds lo, LeafRecord* change_out, uint32_t change_cap, Counters* ctr,
-                       uint32_t n_touched_hint, cudaStream_t s)
+void launchCompactLeaves(UpdateGrid g, cudaStream_t s)
 {
-  if (n_touched_hint == 0) return;
-  static int grid_cap = 0;
-  if (grid_cap == 0)
+  cudaMemsetAsync(g.counters + 1, 0, 4, s);
+  const unsigned grid = std::min<unsigned>(g.cap_mask + 1u, unsigned(smCount()) * 4u);
+  VDBM_LAUNCH(compact_leaves_kernel, grid, 512, s, g);
+}
+
+void launchApplyUpdate(UpdateGrid g, MapTable mt, LogOdds lo, LeafRecord* change_out, uint32_t change_cap, Counters* ctr,
+                       uint32_t n_entries, cudaStream_t s)
+{
+  if (n_entries == 0) return;
+  static int per_sm = 0;
+  if (per_sm == 0)
   {
-    int dev = 0, sms = 148, per_sm = 4;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apply_update_kernel, 256, 0);
-    grid_cap = sms * (per_sm < 1 ? 1 : per_sm);
+    if (per_sm < 1) per_sm = 1;
   }
-  unsigned grid = blocksFor(uint64_t(n_touched_hint) * 32, 256);
-  if (grid > unsigned(grid_cap)) grid = unsigned(grid_cap);
-  { apply_update_kernel<<<grid, 256, 0, s>>>(ut, mt, lo, change_out, change_cap, ctr); VDBM_COUNT_LAUNCH(); }
+  // one warp per batch of 32 leaves; at most one resident wave, at least enough warps to cover the list
+  unsigned grid = blocksFor(blocksFor(n_entries, 32), 8);
+  grid          = std::min<unsigned>(grid, unsigned(smCount() * per_sm));
+  VDBM_LAUNCH(apply_update_kernel, grid, 256, s, g, mt, lo, change_out, change_cap, ctr, n_entries);
 }
 
-void launchRehashUpdate(UpdateTable old_t, uint32_t old_n, UpdateTable new_t, Counters* ctr, cudaStream_t s)
+void launchResetBricks(UpdateGrid g, uint32_t n_bricks, cudaStream_t s)
 {
-  if (old_n) { rehash_update_kernel<<<blocksFor(old_n, 256), 256, 0, s>>>(old_t, old_n, new_t, ctr); VDBM_COUNT_LAUNCH(); }
+  VDBM_LAUNCH(reset_bricks_kernel, std::max(1u, blocksFor(n_bricks, 256)), 256, s, g, n_bricks);
+}
+void launchClearEntries(UpdateGrid g, uint32_t n_entries, cudaStream_t s)
+{
+  if (n_entries) VDBM_LAUNCH(clear_entries_kernel, blocksFor(uint64_t(n_entries) * 16, 256), 256, s, g, n_entries);
+}
+void launchRehashUpdate(UpdateGrid old_g, uint32_t old_bricks, UpdateGrid new_g, Counters* ctr, cudaStream_t s)
+{
+  if (old_bricks) VDBM_LAUNCH(rehash_update_kernel, std::min<unsigned>(old_bricks, unsigned(smCount()) * 8u), 256, s, old_g, old_bricks, new_g, ctr);
 }
 void launchRehashMap(MapTable mt, uint32_t n_leaves, Counters* ctr, cudaStream_t s)
 {
-  if (n_leaves) { rehash_map_kernel<<<blocksFor(n_leaves, 256), 256, 0, s>>>(mt, n_leaves, ctr); VDBM_COUNT_LAUNCH(); }
+  if (n_leaves) VDBM_LAUNCH(rehash_map_kernel, blocksFor(n_leaves, 256), 256, s, mt, n_leaves, ctr);
 }
-void launchGatherUpdate(UpdateTable ut, uint32_t n, const uint32_t* order, LeafRecord* out, cudaStream_t s)
+void launchEntryKeys(UpdateGrid g, uint32_t n_entries, uint64_t* out_keys, uint32_t* out_entries, cudaStream_t s)
 {
-  if (n) { gather_update_kernel<<<blocksFor(uint64_t(n) * 16, 256), 256, 0, s>>>(ut, n, order, out); VDBM_COUNT_LAUNCH(); }
+  if (n_entries) VDBM_LAUNCH(entry_keys_kernel, blocksFor(n_entries, 256), 256, s, g, n_entries, out_keys, out_entries);
 }
-void launchImportUpdate(UpdateTable ut, const LeafRecord* recs, uint64_t n, Counters* ctr, cudaStream_t s)
+void launchGatherUpdate(UpdateGrid g, uint32_t n, const uint64_t* keys, const uint32_t* entries, LeafRecord* out, cudaStream_t s)
 {
-  if (n) { import_update_kernel<<<blocksFor(n * 16, 256), 256, 0, s>>>(ut, recs, n, ctr); VDBM_COUNT_LAUNCH(); }
+  if (n) VDBM_LAUNCH(gather_update_kernel, blocksFor(uint64_t(n) * 16, 256), 256, s, g, n, keys, entries, out);
 }
-void launchClearUpdate(UpdateTable ut, uint32_t n, cudaStream_t s)
+void launchImportUpdate(UpdateGrid g, const LeafRecord* recs, uint64_t n, Counters* ctr, cudaStream_t s)
 {
-  if (n) { clear_update_kernel<<<blocksFor(uint64_t(n) * 16, 256), 256, 0, s>>>(ut, n); VDBM_COUNT_LAUNCH(); }
+  if (n) VDBM_LAUNCH(import_update_kernel, blocksFor(n * 16, 256), 256, s, g, recs, n, ctr);
 }
-void launchGatherMap(MapTable mt, uint32_t n, const uint32_t* leaf_idx, int32_t* origins, uint64_t* mask, float* vals,
-                     int clear_dirty, cudaStream_t s)
+void launchGatherMap(MapTable mt, uint32_t n, const uint32_t* leaf_idx, int32_t* origins, uint64_t* mask, float* vals, cudaStream_t s)
 {
   if (!n) return;
-  unsigned grid = blocksFor(uint64_t(n) * 32, 256);
-  if (grid > 148u * 8u) grid = 148u * 8u;
-  { gather_map_kernel<<<grid, 256, 0, s>>>(mt, n, leaf_idx, origins, mask, vals, clear_dirty); VDBM_COUNT_LAUNCH(); }
+  const unsigned grid = std::min<unsigned>(blocksFor(uint64_t(n) * 32, 256), unsigned(smCount()) * 8u);
+  VDBM_LAUNCH(gather_map_kernel, grid, 256, s, mt, n, leaf_idx, origins, mask, vals);
+}
+void launchCollectDirty(MapTable mt, uint32_t n_leaves, uint32_t* out_idx, Counters* ctr, cudaStream_t s)
+{
+  if (n_leaves) VDBM_LAUNCH(collect_dirty_kernel, blocksFor(n_leaves, 256), 256, s, mt, n_leaves, out_idx, ctr);
 }
 void launchSection(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float,
                    uint64_t* out_keys, uint64_t* out_active, uint64_t* out_valmask, float* out_vals, uint32_t out_cap,
                    Counters* ctr, cudaStream_t s)
 {
   if (!n_leaves) return;
-  unsigned grid = blocksFor(uint64_t(n_leaves) * 32, 256);
-  if (grid > 148u * 8u) grid = 148u * 8u;
-  section_kernel<<<grid, 256, 0, s>>>(mt, n_leaves, bbmin[0], bbmin[1], bbmin[2], bbmax[0], bbmax[1], bbmax[2], full, result_float,
-                                      out_keys, out_active, out_valmask, out_vals, out_cap, ctr);
+  const unsigned grid = std::min<unsigned>(blocksFor(uint64_t(n_leaves) * 32, 256), unsigned(smCount()) * 8u);
+  VDBM_LAUNCH(section_kernel, grid, 256, s, mt, n_leaves, bbmin[0], bbmin[1], bbmin[2], bbmax[0], bbmax[1], bbmax[2], full, result_float,
+              out_keys, out_active, out_valmask, out_vals, out_cap, ctr);
 }
 void launchProbe(MapTable mt, int32_t x, int32_t y, int32_t z, float* out_val, int32_t* out_active, cudaStream_t s)
 {
-  { probe_kernel<<<1, 1, 0, s>>>(mt, x, y, z, out_val, out_active); VDBM_COUNT_LAUNCH(); }
+  VDBM_LAUNCH(probe_kernel, 1, 1, s, mt, x, y, z, out_val, out_active);
 }
-void launchPartition(UpdateTable ut, uint32_t n, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_offsets, LeafRecord* out,
-                     int pass, cudaStream_t s)
+void launchPartition(UpdateGrid g, uint32_t n, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_cursor, LeafRecord* out, int pass,
+                     cudaStream_t s)
 {
-  if (n) { partition_kernel<<<blocksFor(n, 256), 256, 0, s>>>(ut, n, n_ranks, rank_counts, rank_offsets, out, pass); VDBM_COUNT_LAUNCH(); }
+  if (n) VDBM_LAUNCH(partition_kernel, blocksFor(n, 256), 256, s, g, n, n_ranks, rank_counts, rank_cursor, out, pass);
 }
-void launchKeysFromSlots(const uint64_t* keys, const uint32_t* slots, uint32_t n, uint64_t* out_keys, uint32_t* out_idx, cudaStream_t s)
+void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, uint64_t* out_keys, uint32_t* out_idx, cudaStream_t s)
 {
-  if (n) { keys_from_slots_kernel<<<blocksFor(n, 256), 256, 0, s>>>(keys, slots, n, out_keys, out_idx); VDBM_COUNT_LAUNCH(); }
-}
-void launchIota(uint32_t* out, uint32_t n, cudaStream_t s)
-{
-  if (n) { iota_kernel<<<blocksFor(n, 256), 256, 0, s>>>(out, n); VDBM_COUNT_LAUNCH(); }
-}
-void launchUnpackOrigins(const uint64_t* keys, uint32_t n, int32_t* origins, cudaStream_t s)
-{
-  if (n) { unpack_origins_kernel<<<blocksFor(n, 256), 256, 0, s>>>(keys, n, origins); VDBM_COUNT_LAUNCH(); }
+  if (n) VDBM_LAUNCH(keys_from_idx_kernel, blocksFor(n, 256), 256, s, keys, idx, n, out_keys, out_idx);
 }
 void launchSplitRecords(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s)
 {
-  if (n) { split_records_kernel<<<blocksFor(uint64_t(n) * 16, 256), 256, 0, s>>>(recs, n, origins, active, value); VDBM_COUNT_LAUNCH(); }
+  if (n) VDBM_LAUNCH(split_records_kernel, blocksFor(uint64_t(n) * 16, 256), 256, s, recs, n, origins, active, value);
+}
+
+size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,
+                        uint32_t* idx_out, uint32_t n, cudaStream_t s)
+{
+  size_t bytes = temp_bytes;
+  if (d_temp == nullptr) bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(d_temp, bytes, keys_in, keys_out, idx_in, idx_out, int(n), 4, 20, s);
+  return bytes;
 }
 
 size_t sortPairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* idx_in,
