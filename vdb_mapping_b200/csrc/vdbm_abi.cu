@@ -76,6 +76,8 @@ struct vdbm_map
   void* d_sort_tmp  = nullptr;
   size_t sort_tmp_bytes = 0;
   size_t rays_cap   = 0;
+  uint32_t* d_resolved = nullptr; // K2a output: map leaf index per touched update leaf
+  size_t resolved_cap  = 0;
   LeafRecord* d_part = nullptr; // partition output
   size_t part_cap    = 0;
   int dda_grid       = 0;
@@ -406,8 +408,18 @@ int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
     CU_TRY(m, cudaMalloc(&s.d_change, size_t(n) * sizeof(LeafRecord)));
     s.change_cap = n;
   }
+  if (m->resolved_cap < n)
+  {
+    cudaFree(m->d_resolved);
+    m->d_resolved   = nullptr;
+    m->resolved_cap = 0;
+    const size_t cap = size_t(n) + n / 4 + 1024;
+    CU_TRY(m, cudaMalloc(&m->d_resolved, cap * 4));
+    m->resolved_cap = cap;
+  }
   CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_change, 0, sizeof(unsigned), m->stream));
-  launchApplyUpdate(s.g, m->mt, m->lo, want_change ? s.d_change : nullptr, want_change ? s.change_cap : 0, m->d_ctr, n, m->stream);
+  launchApplyUpdate(s.g, m->mt, m->lo, m->d_resolved, want_change ? s.d_change : nullptr, want_change ? s.change_cap : 0, m->d_ctr, n,
+                    m->stream);
   launchResetBricks(s.g, s.n_bricks, m->stream); // fresh update grid (VDBMapping.hpp:384)
   CU_TRY(m, cudaGetLastError());
   s.n_bricks = s.n_entries = 0;
@@ -551,7 +563,7 @@ void vdbm_destroy(vdbm_map* m)
   freeMapPool(m->mt);
   cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
   cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
-  cudaFree(m->d_sort); cudaFree(m->d_sort_tmp);
+  cudaFree(m->d_sort); cudaFree(m->d_sort_tmp); cudaFree(m->d_resolved);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);
   cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1); cudaEventDestroy(m->ev2);
   if (m->own_stream) cudaStreamDestroy(m->stream);

@@ -167,8 +167,9 @@ void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, Counters* ctr, int gr
 int raycastDDAGrid(int device);
 // rebuild ug.entries / counters[1] from the occupied bricks (brick count read on the device)
 void launchCompactLeaves(UpdateGrid ug, cudaStream_t s);
-void launchApplyUpdate(UpdateGrid ug, MapTable mt, LogOdds lo, LeafRecord* change_out, uint32_t change_cap, Counters* ctr,
-                       uint32_t n_entries, cudaStream_t s);
+// resolve (K2a) + apply (K2b); `resolved` is a device scratch array of >= n_entries u32
+void launchApplyUpdate(UpdateGrid ug, MapTable mt, LogOdds lo, uint32_t* resolved, LeafRecord* change_out, uint32_t change_cap,
+                       Counters* ctr, uint32_t n_entries, cudaStream_t s);
 // empty the grid after its entries were consumed (entry masks are zeroed by the consumer): reset brick keys + counters
 void launchResetBricks(UpdateGrid ug, uint32_t n_bricks, cudaStream_t s);
 // zero the masks of all listed entries (used by reset / source re-add; consumers zero masks themselves)

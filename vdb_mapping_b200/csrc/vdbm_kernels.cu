@@ -45,6 +45,7 @@ __device__ __forceinline__ uint64_t shflXor64(uint64_t v, int m)
   uint32_t hi = __shfl_xor_sync(kFull, uint32_t(v >> 32), m);
   return (uint64_t(hi) << 32) | lo;
 }
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 256-bit global load/store (Blackwell sm_100+: LDG.E.ENL2.256 / STG.E.ENL2.256), one 32-byte sector per lane
 __device__ __forceinline__ void ld256(const float* p, float (&v)[8])
 {
@@ -426,222 +427,230 @@ __global__ void __launch_bounds__(512) compact_leaves_kernel(UpdateGrid g)
 }
 
 // ====================================================================================================
-// K2: updateMap. Warps take batches of 32 touched leaves.
-//  phase 1 (lane-parallel): every lane resolves ONE leaf: entry -> leaf key -> map hash probe / insert; new
-//          leaves are allocated with one warp-aggregated atomicAdd. 32 independent dependent-load chains are in
-//          flight per warp instead of one.
-//  phase 2 (warp-cooperative): for each of the 32 leaves, lane L owns the 16 consecutive voxels [16L, 16L+16)
-//          (= 64 contiguous bytes of leaf values, moved with two 256-bit loads/stores): streaming RMW of the map
-//          leaf with the update masks of the NEXT leaf prefetched while the current one is processed.
+// K2: updateMap, in two kernels.
+//  K2a resolve_leaves_kernel (one THREAD per touched leaf): entry -> leaf key -> map hash probe / insert. New leaves
+//      are allocated with one warp-aggregated atomicAdd. Output: resolved[i] = map leaf index | kNewLeafBit, or
+//      kInvalid when no leaf exists and none may be created. Hundreds of thousands of independent dependent-load
+//      chains are in flight, so the probe latency is hidden by parallelism, not paid per warp.
+//  K2b apply_update_kernel (one WARP per touched leaf): lane L owns the 16 consecutive voxels [16L, 16L+16) (= 64
+//      contiguous bytes of leaf values, moved with two 256-bit loads/stores): a pure streaming read-modify-write of
+//      the 2 KB map leaf; entry/resolved/mask words of the NEXT leaf are prefetched while the current one is processed.
 // The update masks are zeroed as they are consumed (the grid is empty again afterwards, VDBMapping.hpp:384).
 // ====================================================================================================
-struct UpdMasks
+constexpr uint32_t kNewLeafBit = 0x80000000u;
+
+__global__ void __launch_bounds__(256) resolve_leaves_kernel(UpdateGrid g, MapTable mt, LogOdds lo, uint32_t* resolved, Counters* ctr,
+                                                            uint32_t n)
 {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane   = threadIdx.x & 31;
+  uint32_t leaf = kInvalid, hslot = 0;
+  int is_new    = 0;
+  uint64_t key  = 0;
+  if (i < n)
+  {
+    const uint32_t e = g.entries[i];
+    key              = leafKeyOfEntry(g.bkeys[e >> 9], e & 511u);
+    // OpenVDB tile probe: on a missing leaf a miss whose probe result is (0.0f, inactive) does not create it
+    bool create_ok = true;
+    if (lo.miss_probe_no_create)
+    {
+      uint64_t any_hit = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) any_hit |= g.val[size_t(e) * 8 + w];
+      create_ok = any_hit != 0;
+    }
+    uint32_t h = uint32_t(mix64(key)) & mt.hcap_mask;
+    for (uint32_t probe = 0; probe <= mt.hcap_mask; ++probe)
+    {
+      const uint64_t k = ldcg64(mt.hkeys + h);
+      if (k == key) { leaf = mt.hvals[h]; break; }
+      if (k == kEmptyKey)
+      {
+        if (!create_ok) break;
+        // keys are unique within a launch, so nobody else inserts THIS key; another key may win this slot
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(mt.hkeys + h), kEmptyKey, key);
+        if (old == kEmptyKey) { is_new = 1; hslot = h; break; }
+      }
+      h = (h + 1) & mt.hcap_mask;
+    }
+  }
+  const unsigned new_mask = __ballot_sync(kFull, is_new);
+  if (new_mask)
+  {
+    uint32_t first = 0;
+    if (lane == 0) first = atomicAdd(mt.n_leaves, (uint32_t)__popc(new_mask));
+    first = __shfl_sync(kFull, first, 0);
+    if (is_new)
+    {
+      const uint32_t li = first + __popc(new_mask & ((1u << lane) - 1u));
+      if (li < mt.pool_cap)
+      {
+        mt.hvals[hslot]  = li;
+        mt.leaf_keys[li] = key;
+        leaf             = li;
+      }
+      else
+      {
+        atomicOr(&ctr->flags, kFlagMapOverflow); // host sizes the pool before the launch; cannot happen
+        is_new = 0;
+      }
+    }
+    if (lane == 0) atomicAdd(&ctr->new_leaves, (unsigned long long)__popc(new_mask));
+  }
+  if (i < n)
+  {
+    if (leaf != kInvalid) mt.leaf_dirty[leaf] = 1u;
+    resolved[i] = (leaf == kInvalid) ? kInvalid : (leaf | (is_new ? kNewLeafBit : 0u));
+  }
+}
+
+struct LeafWork
+{
+  uint32_t e, r;    // entry, resolved leaf (uniform across the warp)
   uint64_t A, V, M; // update active word, update value word, old map active word (held by lanes 0..7)
 };
 
-__device__ __forceinline__ UpdMasks loadMasks(const UpdateGrid& g, const MapTable& mt, uint32_t e, uint32_t leaf, int is_new, int lane)
+__device__ __forceinline__ LeafWork loadLeafWork(const UpdateGrid& g, const MapTable& mt, const uint32_t* resolved, uint32_t i, int lane)
 {
-  UpdMasks m{0, 0, 0};
+  LeafWork w;
+  w.e = g.entries[i];
+  w.r = resolved[i];
+  w.A = w.V = w.M = 0;
   if (lane < 8)
   {
-    m.A = g.act[size_t(e) * 8 + lane];
-    m.V = g.val[size_t(e) * 8 + lane];
-    if (leaf != kInvalid && !is_new) m.M = mt.leaf_mask[size_t(leaf) * 8 + lane];
+    w.A = g.act[size_t(w.e) * 8 + lane];
+    w.V = g.val[size_t(w.e) * 8 + lane];
+    if (w.r != kInvalid && !(w.r & kNewLeafBit)) w.M = mt.leaf_mask[size_t(w.r) * 8 + lane];
   }
-  return m;
+  return w;
 }
 
-__global__ void __launch_bounds__(256, 4) apply_update_kernel(UpdateGrid g, MapTable mt, LogOdds lo, LeafRecord* change_out,
-                                                             uint32_t change_cap, Counters* ctr, uint32_t n)
+__global__ void __launch_bounds__(256, 4) apply_update_kernel(UpdateGrid g, MapTable mt, LogOdds lo, const uint32_t* resolved,
+                                                             LeafRecord* change_out, uint32_t change_cap, Counters* ctr, uint32_t n)
 {
   const int lane         = threadIdx.x & 31;
   const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  unsigned upd_total = 0, chg_total = 0, new_total = 0;
+  const int w  = lane >> 2;       // mask word of this lane's 16 voxels
+  const int sh = (lane & 3) << 4; // bit offset inside the word
+  unsigned upd_total = 0, chg_total = 0;
 
-  for (uint32_t base = warp * 32; base < n; base += n_warps * 32)
+  LeafWork nxt{};
+  if (warp < n) nxt = loadLeafWork(g, mt, resolved, warp, lane);
+  for (uint32_t i = warp; i < n; i += n_warps)
   {
-    // ---------------- phase 1: one leaf per lane ----------------
-    const uint32_t i = base + lane;
-    uint32_t e = 0, leaf = kInvalid, hslot = 0;
-    int is_new   = 0;
-    uint64_t key = 0;
-    if (i < n)
+    const LeafWork cur = nxt;
+    const uint32_t leaf = (cur.r == kInvalid) ? kInvalid : (cur.r & ~kNewLeafBit);
+    const bool is_new   = (cur.r != kInvalid) && (cur.r & kNewLeafBit);
+    float* vp = mt.leaf_vals + size_t(leaf == kInvalid ? 0 : leaf) * 512 + lane * 16;
+    float v0[8], v1[8];
+    // issue the 2 KB leaf read first (independent of the mask words), then prefetch the next leaf's small words
+    if (leaf != kInvalid && !is_new) { ld256(vp, v0); ld256(vp + 8, v1); }
+    else
     {
-      e   = g.entries[i];
-      key = leafKeyOfEntry(g.bkeys[e >> 9], e & 511u);
-      // OpenVDB tile probe: on a missing leaf a miss whose probe result is (0.0f, inactive) does not create it
-      bool create_ok = true;
-      if (lo.miss_probe_no_create)
-      {
-        uint64_t any_hit = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) any_hit |= g.val[size_t(e) * 8 + w];
-        create_ok = any_hit != 0;
-      }
-      uint32_t h = uint32_t(mix64(key)) & mt.hcap_mask;
-      for (uint32_t probe = 0; probe <= mt.hcap_mask; ++probe)
-      {
-        const uint64_t k = ldcg64(mt.hkeys + h);
-        if (k == key) { leaf = mt.hvals[h]; break; }
-        if (k == kEmptyKey)
-        {
-          if (!create_ok) break;
-          // keys are unique within a launch, so nobody else inserts THIS key; another key may win this slot
-          unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(mt.hkeys + h), kEmptyKey, key);
-          if (old == kEmptyKey) { is_new = 1; hslot = h; break; }
-        }
-        h = (h + 1) & mt.hcap_mask;
-      }
+      for (int q = 0; q < 8; ++q) { v0[q] = 0.0f; v1[q] = 0.0f; }
     }
-    const unsigned new_mask = __ballot_sync(kFull, is_new);
-    if (new_mask)
+    if (i + n_warps < n) nxt = loadLeafWork(g, mt, resolved, i + n_warps, lane);
+    // consume: leave the update masks clean for the next accumulation period
+    if (lane < 8)
     {
-      uint32_t first = 0;
-      if (lane == 0) first = atomicAdd(mt.n_leaves, (uint32_t)__popc(new_mask));
-      first = __shfl_sync(kFull, first, 0);
-      if (is_new)
+      g.act[size_t(cur.e) * 8 + lane] = 0;
+      g.val[size_t(cur.e) * 8 + lane] = 0;
+    }
+    const uint32_t ua = uint32_t(shfl64(cur.A, w) >> sh) & 0xFFFFu; // active update bits of my 16 voxels
+    const uint32_t uv = uint32_t(shfl64(cur.V, w) >> sh) & 0xFFFFu; // hit bits
+    const unsigned nz_words  = __ballot_sync(kFull, cur.A != 0) & 0xFFu;
+    const unsigned hit_words = __ballot_sync(kFull, cur.V != 0) & 0xFFu;
+
+    uint32_t ca = 0, cv = 0; // change-grid bits of this lane's 16 voxels
+    if (leaf == kInvalid)
+    {
+      // no leaf and none may be created: every (miss) voxel only runs the tile probe. With the quirk each of
+      // them is reported when the probe flipped the inverted state (VDBMapping.hpp:743-750 via the lambda).
+      if (lo.replicate_quirk && lo.miss_probe_flips) ca = ua & ~uv;
+    }
+    else
+    {
+      const uint32_t oa = uint32_t(shfl64(cur.M, w) >> sh) & 0xFFFFu;
+      // OccupancyVDBMapping.hpp:92-117, branch-free (all 32 lanes stay converged whatever mix of hits/misses):
+      //   nv = v + (hit ? logodds_hit : logodds_miss)
+      //   P  = hit ? (nv > thres_max) : (nv < thres_min)              threshold crossed
+      //   nv = P ? (hit ? min(nv, max_logodds) : max(nv, min_logodds)) : nv   (clamp only inside the threshold branch)
+      //   active = P ? hit : old_active
+      uint32_t pm = 0; // P bits of my 16 voxels
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
       {
-        const uint32_t li = first + __popc(new_mask & ((1u << lane) - 1u));
-        if (li < mt.pool_cap)
+        const bool a_ = (ua >> q) & 1, h_ = (uv >> q) & 1;
+        float& ref    = (q < 8) ? v0[q & 7] : v1[q & 7];
+        const float nv  = __fadd_rn(ref, h_ ? lo.hit : lo.miss);
+        const bool P    = h_ ? (nv > lo.thres_max) : (nv < lo.thres_min);
+        const float cl  = h_ ? fminf(nv, lo.max_lo) : fmaxf(nv, lo.min_lo);
+        const float nv2 = P ? cl : nv;
+        ref = a_ ? nv2 : ref;
+        pm |= uint32_t(P) << q;
+      }
+      // bit-parallel mask algebra on the 16 voxels
+      const uint32_t act = (pm & uv) | (~pm & oa); // P ? hit : old
+      const uint32_t na  = (ua & act) | (~ua & oa);
+      const uint32_t chg = ua & (act ^ oa);        // VDBMapping.hpp:746-749: flag flipped
+      ca |= chg;
+      cv |= chg & uv;                              // :772 setValueOn(true) for hits, :780 setActiveState for misses
+      if (is_new || ua != 0) { st256(vp, v0); st256(vp + 8, v1); } // untouched 64-byte pieces are not rewritten
+      // assemble the new 64-bit active word from the 4 lanes that share it
+      uint64_t piece = uint64_t(na) << sh;
+      piece |= shflXor64(piece, 1);
+      piece |= shflXor64(piece, 2);
+      if ((lane & 3) == 0) mt.leaf_mask[size_t(leaf) * 8 + w] = piece;
+
+      // tile-probe quirk: the first visited voxel (lowest offset) of a leaf that did not exist, if it
+      // is a miss whose probe flips the inverted tile state, is reported as changed although its flag did not.
+      if (is_new && lo.replicate_quirk && lo.miss_probe_flips)
+      {
+        if (!lo.miss_probe_no_create)
         {
-          mt.hvals[hslot]  = li;
-          mt.leaf_keys[li] = key;
-          leaf             = li;
+          const int w_first       = __ffs(nz_words) - 1;
+          const uint64_t a_first  = shfl64(cur.A, w_first), v_first = shfl64(cur.V, w_first);
+          const int b_first       = __ffsll((long long)a_first) - 1;
+          const int n_first       = (w_first << 6) | b_first;
+          const bool first_is_hit = (v_first >> b_first) & 1;
+          if (!first_is_hit && (n_first >> 4) == lane) ca |= 1u << (n_first & 15);
         }
         else
         {
-          atomicOr(&ctr->flags, kFlagMapOverflow); // host sizes the pool before the launch; cannot happen
-          is_new = 0;
+          // degenerate config: misses do not create the leaf, so every miss BEFORE the first hit was probed
+          const int wh      = __ffs(hit_words) - 1;
+          const uint64_t vh = shfl64(cur.V, wh);
+          const int n_hit   = (wh << 6) | (__ffsll((long long)vh) - 1);
+          const int lo_n    = lane << 4;
+          uint32_t before   = 0;
+          if (n_hit >= lo_n + 16) before = 0xFFFFu;
+          else if (n_hit > lo_n) before = (1u << (n_hit - lo_n)) - 1u;
+          ca |= ua & ~uv & before;
         }
       }
-      new_total += __popc(new_mask);
     }
-    if (leaf != kInvalid) mt.leaf_dirty[leaf] = 1u;
+    upd_total += __popc(ua);
+    chg_total += __popc(ca);
 
-    // ---------------- phase 2: warp-cooperative RMW, one leaf at a time ----------------
-    const int cnt = int(min(32u, n - base));
-    const int w   = lane >> 2;       // mask word of this lane's 16 voxels
-    const int sh  = (lane & 3) << 4; // bit offset inside the word
-    UpdMasks nxt  = loadMasks(g, mt, __shfl_sync(kFull, e, 0), __shfl_sync(kFull, leaf, 0), __shfl_sync(kFull, is_new, 0), lane);
-    for (int j = 0; j < cnt; ++j)
+    if (change_out != nullptr)
     {
-      const uint32_t e_j    = __shfl_sync(kFull, e, j);
-      const uint32_t leaf_j = __shfl_sync(kFull, leaf, j);
-      const int new_j       = __shfl_sync(kFull, is_new, j);
-      const UpdMasks cur    = nxt;
-      if (j + 1 < cnt) // prefetch the next leaf's masks while this one is processed
-        nxt = loadMasks(g, mt, __shfl_sync(kFull, e, j + 1), __shfl_sync(kFull, leaf, j + 1), __shfl_sync(kFull, is_new, j + 1), lane);
-      // consume: leave the update masks clean for the next accumulation period
-      if (lane < 8)
+      const unsigned any = __ballot_sync(kFull, ca != 0);
+      if (any)
       {
-        g.act[size_t(e_j) * 8 + lane] = 0;
-        g.val[size_t(e_j) * 8 + lane] = 0;
-      }
-      const uint32_t ua = uint32_t(shfl64(cur.A, w) >> sh) & 0xFFFFu; // active update bits of my 16 voxels
-      const uint32_t uv = uint32_t(shfl64(cur.V, w) >> sh) & 0xFFFFu; // hit bits
-      const unsigned nz_words  = __ballot_sync(kFull, cur.A != 0) & 0xFFu;
-      const unsigned hit_words = __ballot_sync(kFull, cur.V != 0) & 0xFFu;
-
-      uint32_t ca = 0, cv = 0; // change-grid bits of this lane's 16 voxels
-      if (leaf_j == kInvalid)
-      {
-        // no leaf and none may be created: every (miss) voxel only runs the tile probe. With the quirk each of
-        // them is reported when the probe flipped the inverted state (VDBMapping.hpp:743-750 via the lambda).
-        if (lo.replicate_quirk && lo.miss_probe_flips) ca = ua & ~uv;
-      }
-      else
-      {
-        const uint32_t oa = uint32_t(shfl64(cur.M, w) >> sh) & 0xFFFFu;
-        float* vp = mt.leaf_vals + size_t(leaf_j) * 512 + lane * 16;
-        float v0[8], v1[8];
-        const bool touch = (ua != 0);
-        if (!new_j && touch) { ld256(vp, v0); ld256(vp + 8, v1); }
-        else
+        uint64_t pa = uint64_t(ca) << sh, pv = uint64_t(cv) << sh;
+        pa |= shflXor64(pa, 1); pa |= shflXor64(pa, 2);
+        pv |= shflXor64(pv, 1); pv |= shflXor64(pv, 2);
+        uint32_t ci = 0;
+        if (lane == 0) ci = atomicAdd(&ctr->n_change, 1u);
+        ci = __shfl_sync(kFull, ci, 0);
+        if (ci < change_cap)
         {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { v0[q] = 0.0f; v1[q] = 0.0f; }
-        }
-        // OccupancyVDBMapping.hpp:92-117, branch-free (all 32 lanes stay converged whatever mix of hits/misses):
-        //   nv = v + (hit ? logodds_hit : logodds_miss)
-        //   P  = hit ? (nv > thres_max) : (nv < thres_min)              threshold crossed
-        //   nv = P ? (hit ? min(nv, max_logodds) : max(nv, min_logodds)) : nv   (clamp only inside the threshold branch)
-        //   active = P ? hit : old_active
-        uint32_t pm = 0; // P bits of my 16 voxels
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-        {
-          const bool a_ = (ua >> q) & 1, h_ = (uv >> q) & 1;
-          float& ref    = (q < 8) ? v0[q & 7] : v1[q & 7];
-          const float nv  = __fadd_rn(ref, h_ ? lo.hit : lo.miss);
-          const bool P    = h_ ? (nv > lo.thres_max) : (nv < lo.thres_min);
-          const float cl  = h_ ? fminf(nv, lo.max_lo) : fmaxf(nv, lo.min_lo);
-          const float nv2 = P ? cl : nv;
-          ref = a_ ? nv2 : ref;
-          pm |= uint32_t(P) << q;
-        }
-        // bit-parallel mask algebra on the 16 voxels
-        const uint32_t act = (pm & uv) | (~pm & oa); // P ? hit : old
-        const uint32_t na  = (ua & act) | (~ua & oa);
-        const uint32_t chg = ua & (act ^ oa);        // VDBMapping.hpp:746-749: flag flipped
-        ca |= chg;
-        cv |= chg & uv;                              // :772 setValueOn(true) for hits, :780 setActiveState for misses
-        if (new_j || touch) { st256(vp, v0); st256(vp + 8, v1); }
-        // assemble the new 64-bit active word from the 4 lanes that share it
-        uint64_t piece = uint64_t(na) << sh;
-        piece |= shflXor64(piece, 1);
-        piece |= shflXor64(piece, 2);
-        if ((lane & 3) == 0) mt.leaf_mask[size_t(leaf_j) * 8 + w] = piece;
-
-        // tile-probe quirk: the first visited voxel (lowest offset) of a leaf that did not exist, if it
-        // is a miss whose probe flips the inverted tile state, is reported as changed although its flag did not.
-        if (new_j && lo.replicate_quirk && lo.miss_probe_flips)
-        {
-          if (!lo.miss_probe_no_create)
-          {
-            const int w_first       = __ffs(nz_words) - 1;
-            const uint64_t a_first  = shfl64(cur.A, w_first), v_first = shfl64(cur.V, w_first);
-            const int b_first       = __ffsll((long long)a_first) - 1;
-            const int n_first       = (w_first << 6) | b_first;
-            const bool first_is_hit = (v_first >> b_first) & 1;
-            if (!first_is_hit && (n_first >> 4) == lane) ca |= 1u << (n_first & 15);
-          }
-          else
-          {
-            // degenerate config: misses do not create the leaf, so every miss BEFORE the first hit was probed
-            const int wh      = __ffs(hit_words) - 1;
-            const uint64_t vh = shfl64(cur.V, wh);
-            const int n_hit   = (wh << 6) | (__ffsll((long long)vh) - 1);
-            const int lo_n    = lane << 4;
-            uint32_t before   = 0;
-            if (n_hit >= lo_n + 16) before = 0xFFFFu;
-            else if (n_hit > lo_n) before = (1u << (n_hit - lo_n)) - 1u;
-            ca |= ua & ~uv & before;
-          }
-        }
-      }
-      upd_total += __popc(ua);
-      chg_total += __popc(ca);
-
-      if (change_out != nullptr)
-      {
-        const unsigned any = __ballot_sync(kFull, ca != 0);
-        if (any)
-        {
-          uint64_t pa = uint64_t(ca) << sh, pv = uint64_t(cv) << sh;
-          pa |= shflXor64(pa, 1); pa |= shflXor64(pa, 2);
-          pv |= shflXor64(pv, 1); pv |= shflXor64(pv, 2);
-          const uint64_t key_j = shfl64(key, j);
-          uint32_t ci = 0;
-          if (lane == 0) ci = atomicAdd(&ctr->n_change, 1u);
-          ci = __shfl_sync(kFull, ci, 0);
-          if (ci < change_cap)
-          {
-            LeafRecord* r = change_out + ci;
-            if (lane == 0) r->key = key_j;
-            if ((lane & 3) == 0) { r->active[w] = pa; r->value[w] = pv; }
-          }
+          LeafRecord* rec = change_out + ci;
+          if (lane == 0) rec->key = leafKeyOfEntry(g.bkeys[cur.e >> 9], cur.e & 511u);
+          if ((lane & 3) == 0) { rec->active[w] = pa; rec->value[w] = pv; }
         }
       }
     }
@@ -653,7 +662,6 @@ __global__ void __launch_bounds__(256, 4) apply_update_kernel(UpdateGrid g, MapT
   {
     if (upd_total) atomicAdd(&ctr->voxel_updates, (unsigned long long)upd_total);
     if (chg_total) atomicAdd(&ctr->state_changes, (unsigned long long)chg_total);
-    if (new_total) atomicAdd(&ctr->new_leaves, (unsigned long long)new_total);
   }
 }
 
@@ -1025,8 +1033,8 @@ void launchCompactLeaves(UpdateGrid g, cudaStream_t s)
   VDBM_LAUNCH(compact_leaves_kernel, grid, 512, s, g);
 }
 
-void launchApplyUpdate(UpdateGrid g, MapTable mt, LogOdds lo, LeafRecord* change_out, uint32_t change_cap, Counters* ctr,
-                       uint32_t n_entries, cudaStream_t s)
+void launchApplyUpdate(UpdateGrid g, MapTable mt, LogOdds lo, uint32_t* resolved, LeafRecord* change_out, uint32_t change_cap,
+                       Counters* ctr, uint32_t n_entries, cudaStream_t s)
 {
   if (n_entries == 0) return;
   static int per_sm = 0;
@@ -1035,10 +1043,10 @@ void launchApplyUpdate(UpdateGrid g, MapTable mt, LogOdds lo, LeafRecord* change
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apply_update_kernel, 256, 0);
     if (per_sm < 1) per_sm = 1;
   }
-  // one warp per batch of 32 leaves; at most one resident wave, at least enough warps to cover the list
-  unsigned grid = blocksFor(blocksFor(n_entries, 32), 8);
-  grid          = std::min<unsigned>(grid, unsigned(smCount() * per_sm));
-  VDBM_LAUNCH(apply_update_kernel, grid, 256, s, g, mt, lo, change_out, change_cap, ctr, n_entries);
+  VDBM_LAUNCH(resolve_leaves_kernel, blocksFor(n_entries, 256), 256, s, g, mt, lo, resolved, ctr, n_entries);
+  // one warp per leaf, grid-stride; exactly one resident wave (multiple of the SM count)
+  unsigned grid = std::min<unsigned>(blocksFor(n_entries, 8), unsigned(smCount() * per_sm));
+  VDBM_LAUNCH(apply_update_kernel, grid, 256, s, g, mt, lo, resolved, change_out, change_cap, ctr, n_entries);
 }
 
 void launchResetBricks(UpdateGrid g, uint32_t n_bricks, cudaStream_t s)
