@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
         L.vdbo_map_leaf_count.argtypes = [vp]
         L.vdbo_update_import.restype = C.c_int
         L.vdbo_update_import.argtypes = [vp, C.c_char_p, C.c_uint64, i32p, u64p, u64p]
+        L.vdbo_update_clear.restype = C.c_int
+        L.vdbo_update_clear.argtypes = [vp, C.c_char_p]
         _lib = L
     return _lib
 
@@ -192,6 +194,9 @@ class OracleOccupancyVDBMapping:
 
     def mapLeafCount(self) -> int:
         return int(self._L.vdbo_map_leaf_count(self._h))
+
+    def clearUpdateGrid(self, source_id: str) -> int:
+        return self._L.vdbo_update_clear(self._h, source_id.encode())
 
     def importUpdate(self, source_id: str, origins, active, valmask) -> int:
         o = np.ascontiguousarray(origins, dtype=np.int32)

@@ -1017,4 +1017,14 @@ int vdbo_update_import(void* hh, const char* source, uint64_t n, const int32_t* 
   return 0;
 }
 
+// empty one source's update grid without applying it (models vdbm_update_partition, which hands the leaves over)
+int vdbo_update_clear(void* hh, const char* source)
+{
+  auto& m = static_cast<vo::Handle*>(hh)->map;
+  auto it = m.m_input_sources.find(source);
+  if (it == m.m_input_sources.end()) return 1;
+  it->second->update_grid.reset(new vo::BoolTree(false));
+  return 0;
+}
+
 } // extern "C"

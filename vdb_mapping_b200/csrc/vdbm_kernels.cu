@@ -45,7 +45,6 @@ __device__ __forceinline__ uint64_t shflXor64(uint64_t v, int m)
   uint32_t hi = __shfl_xor_sync(kFull, uint32_t(v >> 32), m);
   return (uint64_t(hi) << 32) | lo;
 }
-__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 256-bit global load/store (Blackwell sm_100+: LDG.E.ENL2.256 / STG.E.ENL2.256), one 32-byte sector per lane
 __device__ __forceinline__ void ld256(const float* p, float (&v)[8])
 {
@@ -221,7 +220,7 @@ __device__ __forceinline__ void nearOr(unsigned int* s_near, uint32_t word, uint
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, Counters* ctr)
+__global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, Counters* ctr)
 {
   __shared__ unsigned int s_near[2 * kNearWords]; // 64-bit mask words as 32-bit halves (native shared-memory atomicOr)
   __shared__ uint32_t s_near_slot[8];
@@ -250,6 +249,7 @@ __global__ void __launch_bounds__(256) raycast_dda_kernel(RaycastArgs a, UpdateG
   uint32_t slot    = kInvalid;
   uint32_t cur_off  = kInvalid;
   uint32_t cur_near = kInvalid; // word index in s_near when the current run lies in the near cube
+  bool in_near      = false;    // the ray has not left the near cube yet
   uint64_t acc      = 0;
 
   for (uint32_t iter = 0;; ++iter)
@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(256) raycast_dda_kernel(RaycastArgs a, UpdateG
                 x = ox; y = oy; z = oz;
                 clipped = r.flags & kRayClipped;
                 slot = origin_slot; cur_off = kInvalid; acc = 0;
+                in_near = true;
                 need = false;
                 busy = true;
               }
@@ -329,11 +330,15 @@ __global__ void __launch_bounds__(256) raycast_dda_kernel(RaycastArgs a, UpdateG
           if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
           else markWord<MODE>(brick_act + cur_off, acc);
         }
-        cur_off = off;
-        // is the new run inside the near cube? (runs never straddle it: the cube is leaf aligned)
+        cur_off  = off;
+        cur_near = kInvalid;
+        // is the new run inside the near cube? (runs never straddle it: the cube is leaf aligned; a ray is monotonic
+        // on every axis, so once it has left the cube it never comes back and the test is skipped for good)
+        if (in_near)
         {
           const unsigned rx = unsigned(x - c0x), ry = unsigned(y - c0y), rz = unsigned(z - c0z);
-          cur_near = (rx < 64u && ry < 64u && rz < 64u) ? (((rx >> 3) << 9) | ((ry >> 3) << 6) | ((rz >> 3) << 3) | (rx & 7u)) : kInvalid;
+          in_near = (rx < 64u && ry < 64u && rz < 64u);
+          if (in_near) cur_near = ((rx >> 3) << 9) | ((ry >> 3) << 6) | ((rz >> 3) << 3) | (rx & 7u);
         }
         acc     = 0;
       }
