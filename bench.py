@@ -23,7 +23,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -50,49 +49,61 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons DURING the timed region, sampled in-process through NVML every 10 ms
+    (spawning `nvidia-smi -lms` from every rank measurably perturbs multi-GPU runs)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.rows, self.stop_flag, self.t, self.h = gpu_index, [], threading.Event(), None, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except Exception:
+                    idx = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((sm, rs, pw))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        if self.h is None:
+            return
+        self.rows, self.stop_flag = [], threading.Event()
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None or self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag.set()
+        self.t.join(timeout=1)
+        sm = [r[0] for r in self.rows]
+        reasons = set()
+        for _, rs, _ in self.rows:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max((r[2] for r in self.rows), default=None), "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def workload_cfg(name: str) -> int:
@@ -153,7 +164,7 @@ def run_reference(args, rank, world):
                                  "single-threaded per input source; host has %d logical cores" % (os.cpu_count() or 0)},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_leg(cfg: int, n_scans: int):
@@ -229,7 +240,7 @@ def run_ours(args, rank, world, local_rank):
                     barrier()
                     st0 = m.stats()
                     launches0 = st0["gpu_launches"]
-                    if not e2e:
+                    if not e2e and not os.environ.get("VDBM_BENCH_NO_SAMPLER"):
                         sampler.start()
                     t_wall0 = time.perf_counter()
                     ev0.record(stream)
@@ -259,8 +270,12 @@ def run_ours(args, rank, world, local_rank):
             m.close()
             return out
 
-    res_v = run_leg(e2e=False)
-    res_e = run_leg(e2e=True)
+    if os.environ.get("VDBM_BENCH_E2E_FIRST"):
+        res_e = run_leg(e2e=True)
+        res_v = run_leg(e2e=False)
+    else:
+        res_v = run_leg(e2e=False)
+        res_e = run_leg(e2e=True)
 
     # ---- max over ranks of the device time; totals over ranks ----
     def reduce(vals, op):
@@ -324,10 +339,32 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu_baseline_leg(cfg, args.cpu_scans)
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    if world > 1 and vdist.PROFILE:
+        log = np.array(vdist.PROFILE_LOG[-K:])
+        line["exchange"]["host_phase_ms_rank0"] = dict(zip(["partition", "counts_a2a", "records_a2a_launch", "import", "integrate"],
+                                                           [float(x) for x in log.mean(axis=0)]))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Print the JSON line on the process's ORIGINAL stdout (fd 1 is redirected to stderr while the bench runs, so
+    that library chatter such as 'NCCL version ...' cannot pollute the one-line contract)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)

@@ -1,0 +1,519 @@
+// VDBMapping.hpp — B200 drop-in for the scan-integration members of vdb_mapping::VDBMapping<TData, TConfig>.
+//
+// Same namespace, class template, aliases and member signatures as the reference header
+// (/root/reference/include/vdb_mapping/VDBMapping.hpp, cited below as R:<line>), so that code written against the
+// reference — its ROS/ROS2 wrappers, its tests/mapping.cpp — compiles unchanged. Nothing of the algorithm lives
+// here: every grid operation is a call into the C ABI of libvdbm_b200.so (include/vdbm_b200.h), which runs the
+// CUDA kernels. This header only
+//   * keeps the host-side plumbing of the reference: input sources, the accumulation / integration worker threads,
+//     the shared map mutex with writer priority (R:133,1343-1430,1534-1540);
+//   * mirrors the device-resident map into a host grid object (`getGrid()`, R:799). Mirror modes:
+//       Eager (default)  every integrate copies the leaves it modified back, so a `GridT::Accessor` obtained
+//                        BEFORE an insert sees the new values afterwards (what tests/mapping.cpp:13-29 relies on);
+//       Lazy             nothing is copied until getGrid() is called (throughput mode: the scan-integration
+//                        path then never leaves the GPU).
+//   * converts between host grids and the leaf records of the ABI where the reference passes grids around
+//     (raycastPointCloud's accessor, updateMap's argument and result, getMapSection*).
+//
+// Scope: insertPointCloud, accumulateUpdate, addDataToAccumulate, integrateUpdate,
+// raycastPointCloud, updateMap, getGrid, getMapSection*, createIndexBoundingBox, addInputSource, setConfig,
+// resetMap, getMapMutex, worldToIndex. Persistence, morphology, artificial areas, raytrace and fast_mode are out
+// of scope of this build and are not declared (a translation unit that needs them keeps using the reference).
+// The device arithmetic implements the OccupancyVDBMapping node operations (TData = float); the protected virtual
+// update*Node hooks of the reference cannot be honoured on the device and are therefore not part of this class.
+#ifndef VDB_MAPPING_VDB_MAPPING_H_INCLUDED
+#define VDB_MAPPING_VDB_MAPPING_H_INCLUDED
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <shared_mutex>
+#include <string>
+#include <thread>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "vdb_mapping/detail/backend.hpp"
+#include "vdbm_b200.h"
+
+namespace vdb_mapping {
+
+/*! Configuration parameters, field for field as R:64-71. */
+struct BaseConfig
+{
+  double max_range;
+  bool fast_mode;
+  double accumulation_period;
+  std::string map_directory_path;
+};
+
+/*! How the host grid returned by getGrid() follows the device-resident map. */
+enum class MirrorMode
+{
+  Eager,
+  Lazy
+};
+
+template <typename TData, typename TConfig = BaseConfig>
+class VDBMapping
+{
+  static_assert(std::is_same<TData, float>::value, "the B200 path implements the float (occupancy log-odds) map");
+  using BackendT = detail::Backend<TData>;
+
+public:
+  using PointT      = typename BackendT::PointT;
+  using PointCloudT = typename BackendT::PointCloudT;
+  using GridT       = typename BackendT::GridT;
+  using UpdateGridT = typename BackendT::UpdateGridT;
+
+  /*! Host-side record of one input source (R:91-103); its update grid lives on the device. */
+  struct InputSource
+  {
+    std::string source_id;
+    double max_range;
+    std::mutex update_grid_mutex;
+    std::mutex input_data_mutex;
+    std::optional<std::pair<typename PointCloudT::ConstPtr, Eigen::Matrix<double, 3, 1> > > input_data;
+    std::chrono::milliseconds max_input_period;
+    std::condition_variable data_available_cv;
+  };
+
+  VDBMapping()                  = delete;
+  VDBMapping(const VDBMapping&) = delete;
+  VDBMapping& operator=(const VDBMapping&) = delete;
+
+  /*! R:115-134. The device map is created here; the integration thread starts like in the reference. */
+  explicit VDBMapping(const double resolution)
+    : m_resolution(resolution)
+    , m_config_set(false)
+  {
+    m_map_mutex = std::make_shared<std::shared_mutex>();
+    vdbm_params p{};
+    p.resolution            = resolution;
+    p.device                = -1;
+    p.replicate_probe_quirk = 1;
+    const int rc            = vdbm_create(&p, &m_device_map);
+    if (rc != VDBM_OK)
+    {
+      // no CPU fallback exists: the reference semantics cannot be provided without the device
+      std::cerr << "vdb_mapping (B200): could not create the device map (status " << rc << "); a CUDA device is required."
+                << std::endl;
+      m_device_map = nullptr;
+    }
+    m_vdb_grid           = createVDBMap(m_resolution);
+    m_integration_thread = std::thread(&VDBMapping::integrationThread, this);
+  }
+
+  /*! R:139-154 */
+  virtual ~VDBMapping()
+  {
+    m_thread_stop_signal = true;
+    for (auto& [source_id, worker_thread] : m_worker_threads)
+    {
+      m_input_sources[source_id]->data_available_cv.notify_all();
+      if (worker_thread.joinable()) worker_thread.join();
+    }
+    if (m_integration_thread.joinable()) m_integration_thread.join();
+    if (m_device_map) vdbm_destroy(m_device_map);
+  }
+
+  /*! R:163-169 */
+  typename GridT::Ptr createVDBMap(double resolution) { return BackendT::createMapGrid(resolution); }
+
+  /*! R:174-186 */
+  void resetMap()
+  {
+    std::unique_lock map_lock(*m_map_mutex);
+    if (m_device_map)
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex);
+      vdbm_reset(m_device_map);
+    }
+    m_vdb_grid->clear();
+    m_vdb_grid = createVDBMap(m_resolution);
+    map_lock.unlock();
+  }
+
+  /*! Mirror policy of getGrid(); see the header comment. Not part of the reference API. */
+  void setMirrorMode(MirrorMode mode) { m_mirror_mode = mode; }
+
+  /*! R:316-346. Unknown source: message + return; source range <= 0: nothing is raycast. */
+  void accumulateUpdate(const typename PointCloudT::ConstPtr& cloud,
+                        const Eigen::Matrix<double, 3, 1>& origin,
+                        const std::string source_id)
+  {
+    auto source = m_input_sources.find(source_id);
+    if (source == m_input_sources.end())
+    {
+      std::cout << "Tried to accumulate update for " << source_id << ". Source not available" << std::endl;
+      return;
+    }
+    std::shared_lock map_lock(*m_map_mutex);
+    std::unique_lock update_grid_lock(source->second->update_grid_mutex);
+    if (!m_device_map || !cloud) return;
+    const double o[3] = {origin.x(), origin.y(), origin.z()};
+    // The C ABI handle is thread-compatible, not thread-safe: sources share its stream and staging buffers, so the
+    // accumulation threads of different sources take turns on the device (they still overlap their host work).
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    // the ABI wants the pcl::PointXYZ records as they lie in the cloud (16-byte stride)
+    const int rc = vdbm_accumulate(m_device_map, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o);
+    report(rc);
+  }
+
+  /*! R:355-370: latest-wins hand-off to the source's accumulation thread. */
+  void addDataToAccumulate(const typename PointCloudT::ConstPtr& cloud,
+                           const Eigen::Matrix<double, 3, 1>& origin,
+                           const std::string source_id)
+  {
+    auto source = m_input_sources.find(source_id);
+    if (source == m_input_sources.end())
+    {
+      std::cout << "Tried to add data for accumulation of " << source_id << ". Source not available" << std::endl;
+      return;
+    }
+    std::unique_lock lock(source->second->input_data_mutex);
+    source->second->input_data = std::make_pair(cloud, origin);
+    source->second->data_available_cv.notify_all();
+  }
+
+  /*! R:375-387: exclusive map lock (writer priority flag), updateMap for every source in key order. */
+  void integrateUpdate()
+  {
+    m_map_mutex_requested = true;
+    std::unique_lock map_lock(*m_map_mutex);
+    m_map_mutex_requested = false;
+    if (!m_device_map) return;
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_integrate(m_device_map, 0));
+    if (m_mirror_mode == MirrorMode::Eager) syncMirrorLocked();
+    else m_mirror_stale = true;
+  }
+
+  /*! R:399-406 */
+  bool insertPointCloud(const typename PointCloudT::ConstPtr& cloud,
+                        const Eigen::Matrix<double, 3, 1>& origin,
+                        const std::string source_id)
+  {
+    accumulateUpdate(cloud, origin, source_id);
+    integrateUpdate();
+    return true;
+  }
+
+  /*! R:466-539 (fast_mode / intersector argument not supported). The rays are cast on the device into a scratch
+   *  source; the resulting update leaves are then merged into the grid behind `update_grid_acc`. */
+  bool raycastPointCloud(const typename PointCloudT::ConstPtr& cloud,
+                         const Eigen::Matrix<double, 3, 1>& origin,
+                         const double raycast_range,
+                         typename UpdateGridT::Accessor& update_grid_acc)
+  {
+    if (!m_config_set)
+    {
+      std::cerr << "Map not properly configured. Did you call setConfig method?" << std::endl;
+      return false;
+    }
+    if (!m_device_map || !cloud) return false;
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    ensureScratchSource();
+    const double o[3] = {origin.x(), origin.y(), origin.z()};
+    if (report(vdbm_raycast(m_device_map, kScratchSource, cloud->points.data(), cloud->points.size(), sizeof(PointT), o, raycast_range)) != VDBM_OK)
+      return false;
+    vdbm_leafset* ls = nullptr;
+    if (report(vdbm_update_export(m_device_map, kScratchSource, &ls)) != VDBM_OK) return false;
+    mergeIntoAccessor(ls, update_grid_acc);
+    vdbm_leafset_free(ls);
+    // empty the scratch grid without touching the map: re-adding a source clears its update grid (vdbm_source_add)
+    vdbm_source_add(m_device_map, kScratchSource, 1.0);
+    return true;
+  }
+
+  /*! R:612-631 */
+  openvdb::Coord worldToIndex(const openvdb::Vec3d& world_coordinate) const
+  {
+    double c[3] = {world_coordinate.x(), world_coordinate.y(), world_coordinate.z()};
+    openvdb::Int32 idx[3];
+    const double inv = 1.0 / m_resolution;
+    for (int a = 0; a < 3; ++a)
+    {
+      if (std::fmod(c[a], m_resolution)) c[a] = c[a] + (m_resolution / 2.0);
+      idx[a] = openvdb::Int32(std::floor(c[a] * inv));
+    }
+    return openvdb::Coord(idx[0], idx[1], idx[2]);
+  }
+
+  /*! R:731-792: applies a caller-provided update grid and returns the change grid. */
+  typename UpdateGridT::Ptr updateMap(const typename UpdateGridT::Ptr& temp_grid)
+  {
+    typename UpdateGridT::Ptr change = BackendT::createUpdateGrid(m_resolution);
+    if (!m_device_map || !temp_grid || temp_grid->empty()) return change;
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    ensureScratchSource();
+    std::vector<std::int32_t> origins;
+    std::vector<std::uint64_t> active, value;
+    BackendT::forEachUpdateLeaf(*temp_grid, [&](const std::int32_t o[3], const std::uint64_t* a, const std::uint64_t* v) {
+      origins.insert(origins.end(), o, o + 3);
+      active.insert(active.end(), a, a + 8);
+      value.insert(value.end(), v, v + 8);
+    });
+    if (report(vdbm_update_import(m_device_map, kScratchSource, origins.size() / 3, origins.data(), active.data(), value.data())) != VDBM_OK)
+      return change;
+    vdbm_leafset* ls = nullptr;
+    if (report(vdbm_update_map(m_device_map, kScratchSource, &ls)) != VDBM_OK) return change;
+    const std::uint64_t n = vdbm_leafset_size(ls);
+    for (std::uint64_t i = 0; i < n; ++i)
+      BackendT::putUpdateLeaf(*change, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_active(ls) + 8 * i, vdbm_leafset_valmask(ls) + 8 * i);
+    vdbm_leafset_free(ls);
+    if (m_mirror_mode == MirrorMode::Eager) syncMirrorLocked();
+    else m_mirror_stale = true;
+    return change;
+  }
+
+  /*! R:799. The returned grid object is the live host mirror of the device map. */
+  typename GridT::Ptr getGrid() const
+  {
+    if (m_mirror_stale)
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex);
+      const_cast<VDBMapping*>(this)->syncMirrorLocked();
+    }
+    return m_vdb_grid;
+  }
+
+  /*! R:857-871 with R:810-847: index bounding box of a box given in a reference frame. The 8 corners are stored as
+   *  float (pcl::PointXYZ), transformed with the 4x4 double matrix, min/max taken, then worldToIndex + floor. */
+  openvdb::CoordBBox createIndexBoundingBox(const Eigen::Matrix<double, 3, 1>& min_boundary,
+                                            const Eigen::Matrix<double, 3, 1>& max_boundary,
+                                            const Eigen::Matrix<double, 4, 4>& map_to_reference_tf) const
+  {
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    bool first  = true;
+    for (int k = 0; k < 8; ++k)
+    {
+      const float p[3] = {static_cast<float>((k & 4) ? max_boundary.x() : min_boundary.x()),
+                          static_cast<float>((k & 2) ? max_boundary.y() : min_boundary.y()),
+                          static_cast<float>((k & 1) ? max_boundary.z() : min_boundary.z())};
+      // pcl::transformPointCloud with a double matrix: float(M(r,0)*x + M(r,1)*y + M(r,2)*z + M(r,3))
+      for (int r = 0; r < 3; ++r)
+      {
+        const float q = static_cast<float>(map_to_reference_tf(r, 0) * p[0] + map_to_reference_tf(r, 1) * p[1] +
+                                           map_to_reference_tf(r, 2) * p[2] + map_to_reference_tf(r, 3));
+        if (first || q < lo[r]) lo[r] = q;
+        if (first || q > hi[r]) hi[r] = q;
+      }
+      first = false;
+    }
+    const double inv = 1.0 / m_resolution;
+    openvdb::Vec3d mn(lo[0] * inv, lo[1] * inv, lo[2] * inv), mx(hi[0] * inv, hi[1] * inv, hi[2] * inv);
+    return openvdb::CoordBBox(openvdb::Coord::floor(mn), openvdb::Coord::floor(mx));
+  }
+
+  /*! R:883-891 */
+  typename UpdateGridT::Ptr getMapSectionUpdateGrid(const Eigen::Matrix<double, 3, 1>& min_boundary,
+                                                    const Eigen::Matrix<double, 3, 1>& max_boundary,
+                                                    const Eigen::Matrix<double, 4, 4>& map_to_reference_tf,
+                                                    const bool full_grid = false) const
+  {
+    typename UpdateGridT::Ptr out = BackendT::createUpdateGrid(m_resolution);
+    const openvdb::CoordBBox bb   = createIndexBoundingBox(min_boundary, max_boundary, map_to_reference_tf);
+    const std::int32_t mn[3] = {bb.min().x(), bb.min().y(), bb.min().z()}, mx[3] = {bb.max().x(), bb.max().y(), bb.max().z()};
+    std::shared_lock map_lock(*m_map_mutex);
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    vdbm_leafset* ls = nullptr;
+    if (m_device_map && vdbm_section(m_device_map, mn, mx, full_grid ? 1 : 0, 0, &ls) == VDBM_OK)
+    {
+      const std::uint64_t n = vdbm_leafset_size(ls);
+      for (std::uint64_t i = 0; i < n; ++i)
+        BackendT::putUpdateLeaf(*out, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_active(ls) + 8 * i, vdbm_leafset_valmask(ls) + 8 * i);
+      vdbm_leafset_free(ls);
+    }
+    BackendT::setSectionMeta(*out, mn, mx); // R:955-958
+    return out;
+  }
+
+  /*! R:902-909 */
+  typename GridT::Ptr getMapSectionGrid(const Eigen::Matrix<double, 3, 1>& min_boundary,
+                                        const Eigen::Matrix<double, 3, 1>& max_boundary,
+                                        const Eigen::Matrix<double, 4, 4>& map_to_reference_tf,
+                                        const bool full_grid = false) const
+  {
+    typename GridT::Ptr out     = BackendT::createMapGrid(m_resolution);
+    const openvdb::CoordBBox bb = createIndexBoundingBox(min_boundary, max_boundary, map_to_reference_tf);
+    const std::int32_t mn[3] = {bb.min().x(), bb.min().y(), bb.min().z()}, mx[3] = {bb.max().x(), bb.max().y(), bb.max().z()};
+    std::shared_lock map_lock(*m_map_mutex);
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    vdbm_leafset* ls = nullptr;
+    if (m_device_map && vdbm_section(m_device_map, mn, mx, full_grid ? 1 : 0, 1, &ls) == VDBM_OK)
+    {
+      const std::uint64_t n = vdbm_leafset_size(ls);
+      for (std::uint64_t i = 0; i < n; ++i)
+        BackendT::putMapLeaf(*out, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_values(ls) + 512 * i, vdbm_leafset_active(ls) + 8 * i);
+      vdbm_leafset_free(ls);
+    }
+    BackendT::setSectionMeta(*out, mn, mx);
+    return out;
+  }
+
+  /*! R:1343 */
+  std::shared_ptr<std::shared_mutex> getMapMutex() { return m_map_mutex; }
+
+  /*! R:1352-1375. The source is registered BEFORE its worker thread starts (the reference starts the thread first). */
+  void addInputSource(std::string source_id, double max_range, double max_rate)
+  {
+    auto s       = std::make_shared<InputSource>();
+    s->source_id = source_id;
+    s->max_range = (max_range == 0) ? m_max_range : max_range;
+    s->max_input_period = (max_rate <= 0) ? std::chrono::milliseconds(0) : std::chrono::milliseconds((int)(1000.0 / max_rate));
+    if (m_device_map)
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex);
+      report(vdbm_source_add(m_device_map, source_id.c_str(), max_range));
+    }
+    auto old = m_worker_threads.find(source_id);
+    m_input_sources[source_id] = s;
+    if (old == m_worker_threads.end()) m_worker_threads[source_id] = std::thread(&VDBMapping::accumulationThread, this, source_id);
+  }
+
+  /*! R:1456-1469 */
+  virtual void setConfig(const TConfig& config)
+  {
+    if (config.max_range < 0.0)
+    {
+      std::cerr << "Max range of " << config.max_range << " invalid. Range cannot be negative." << std::endl;
+      return;
+    }
+    m_max_range           = config.max_range;
+    m_map_directory_path  = config.map_directory_path;
+    m_fast_mode           = config.fast_mode;
+    m_accumulation_period = (int)(config.accumulation_period * 1000);
+    m_config_set          = true;
+  }
+
+  /*! Counters of the device path (rays, visits, voxel updates, kernel times); not part of the reference API. */
+  bool deviceStats(vdbm_stats_t& out) const { return m_device_map && vdbm_stats(m_device_map, &out) == VDBM_OK; }
+
+protected:
+  static constexpr const char* kScratchSource = "\x01vdbm_scratch";
+
+  int report(int rc) const
+  {
+    // the reference reports problems on std::cout / std::cerr and carries on; so does the shim
+    if (rc != VDBM_OK && rc != VDBM_ERR_UNKNOWN_SOURCE && m_device_map)
+      std::cerr << "vdb_mapping (B200): " << vdbm_last_error(m_device_map) << std::endl;
+    return rc;
+  }
+
+  void ensureScratchSource()
+  {
+    if (!m_scratch_ready && m_device_map)
+    {
+      vdbm_source_add(m_device_map, kScratchSource, 1.0);
+      m_scratch_ready = true;
+    }
+  }
+
+  void mergeIntoAccessor(vdbm_leafset* ls, typename UpdateGridT::Accessor& acc)
+  {
+    const std::uint64_t n = vdbm_leafset_size(ls);
+    for (std::uint64_t i = 0; i < n; ++i)
+    {
+      const std::int32_t* o  = vdbm_leafset_origins(ls) + 3 * i;
+      const std::uint64_t* a = vdbm_leafset_active(ls) + 8 * i;
+      const std::uint64_t* v = vdbm_leafset_valmask(ls) + 8 * i;
+      for (unsigned k = 0; k < 512; ++k)
+      {
+        if (!((a[k >> 6] >> (k & 63)) & 1u)) continue;
+        const openvdb::Coord c(o[0] + int(k >> 6), o[1] + int((k >> 3) & 7), o[2] + int(k & 7));
+        if ((v[k >> 6] >> (k & 63)) & 1u) acc.setValueOn(c, true); // R:535
+        else acc.setActiveState(c, true);                          // R:563
+      }
+    }
+  }
+
+  /*! copies the leaves modified since the last call from the device into the host grid (caller holds the map lock
+   *  or is the only user) */
+  void syncMirrorLocked()
+  {
+    m_mirror_stale = false;
+    if (!m_device_map) return;
+    vdbm_leafset* ls = nullptr;
+    if (report(vdbm_map_export(m_device_map, 1, &ls)) != VDBM_OK) return;
+    const std::uint64_t n = vdbm_leafset_size(ls);
+    for (std::uint64_t i = 0; i < n; ++i)
+      BackendT::putMapLeaf(*m_vdb_grid, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_values(ls) + 512 * i, vdbm_leafset_active(ls) + 8 * i);
+    vdbm_leafset_free(ls);
+  }
+
+  /*! R:1383-1411 */
+  void accumulationThread(std::string source_id)
+  {
+    while (!m_config_set && !m_thread_stop_signal) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    while (!m_thread_stop_signal)
+    {
+      std::shared_ptr<InputSource> src = m_input_sources[source_id];
+      auto wake_time = std::chrono::high_resolution_clock::now() + src->max_input_period;
+      std::unique_lock lock(src->input_data_mutex);
+      src->data_available_cv.wait(lock, [&] { return src->input_data || m_thread_stop_signal; });
+      if (m_thread_stop_signal) break;
+      if (!m_map_mutex_requested)
+      {
+        auto measurement = *src->input_data;
+        src->input_data.reset();
+        lock.unlock();
+        accumulateUpdate(measurement.first, measurement.second, source_id);
+        std::this_thread::sleep_until(wake_time);
+      }
+      else
+      {
+        lock.unlock();
+        std::this_thread::yield();
+      }
+    }
+  }
+
+  /*! R:1416-1430. An accumulation period of 0 (or an uninitialised one, as in the reference's tests) only lets the
+   *  explicit integrateUpdate()/insertPointCloud() calls integrate. */
+  void integrationThread()
+  {
+    while (!m_config_set && !m_thread_stop_signal) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    while (!m_thread_stop_signal)
+    {
+      if (m_accumulation_period <= 0 || m_accumulation_period > 3600000)
+      {
+        std::this_thread::sleep_for(std::chrono::milliseconds(20));
+        continue;
+      }
+      auto wake_time = std::chrono::high_resolution_clock::now() + std::chrono::milliseconds(m_accumulation_period);
+      integrateUpdate();
+      std::this_thread::sleep_until(wake_time);
+    }
+  }
+
+  vdbm_map* m_device_map = nullptr;
+  typename GridT::Ptr m_vdb_grid;
+  double m_max_range = 0.0;
+  double m_resolution;
+  bool m_fast_mode          = false;
+  int m_accumulation_period = 0;
+  std::string m_map_directory_path;
+  std::atomic<bool> m_config_set;
+  MirrorMode m_mirror_mode = MirrorMode::Eager;
+  mutable bool m_mirror_stale = false;
+  bool m_scratch_ready        = false;
+  mutable std::mutex m_device_mutex; // serialises calls into the (thread-compatible) C ABI handle
+  mutable std::shared_ptr<std::shared_mutex> m_map_mutex;
+  mutable std::atomic<bool> m_map_mutex_requested{false};
+  std::map<std::string, std::shared_ptr<InputSource> > m_input_sources;
+  std::atomic<bool> m_thread_stop_signal{false};
+  std::map<std::string, std::thread> m_worker_threads;
+  std::thread m_integration_thread;
+};
+
+} // namespace vdb_mapping
+
+#endif /* VDB_MAPPING_VDB_MAPPING_H_INCLUDED */

@@ -1,0 +1,148 @@
+// C++ drop-in check: the reference's known-answer scenarios (/root/reference/tests/mapping.cpp) driven through the
+// SHIM headers (include/vdb_mapping/*.hpp) -> C ABI -> CUDA kernels, written against the same public API the
+// reference's tests use (OccupancyVDBMapping, PointCloudT, Config, getGrid()->getAccessor(), openvdb::Coord).
+// Table-driven instead of one TEST per scenario; plus API cases the reference does not test (updateMap with a
+// caller grid, raycastPointCloud into an accessor, sections, lazy mirror).
+#include <cmath>
+#include <vdb_mapping/OccupancyVDBMapping.hpp>
+
+#include "mini_gtest.h"
+
+using vdb_mapping::Config;
+using vdb_mapping::OccupancyVDBMapping;
+
+static Config gtestConfig(double max_range)
+{
+  Config conf;
+  conf.max_range           = max_range;
+  conf.fast_mode           = false;
+  conf.accumulation_period = 0.0; // the reference leaves it uninitialised; 0 = only explicit integrates
+  conf.prob_hit            = 0.9;
+  conf.prob_miss           = 0.1;
+  conf.prob_thres_max      = 0.51;
+  conf.prob_thres_min      = 0.49;
+  return conf;
+}
+static float logOdds(double p) { return static_cast<float>(std::log(p) - std::log(1 - p)); }
+
+struct Expect { int z; int kind; bool check_flag; bool flag; }; // kind: 0 untouched, 1 miss, 2 hit
+
+static void runAxisCase(double resolution, double max_range, double z_in_resolutions, std::initializer_list<Expect> exp)
+{
+  OccupancyVDBMapping map(resolution);
+  const Config conf = gtestConfig(max_range);
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0, 0, z_in_resolutions * resolution);
+  Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  EXPECT_TRUE(map.insertPointCloud(cloud, origin, "test"));
+  OccupancyVDBMapping::GridT::Accessor acc = map.getGrid()->getAccessor();
+  for (const Expect& e : exp)
+  {
+    const openvdb::Coord c(0, 0, e.z);
+    const float want = e.kind == 0 ? 0.0f : (e.kind == 1 ? logOdds(conf.prob_miss) : logOdds(conf.prob_hit));
+    EXPECT_EQ(acc.getValue(c), want);
+    if (e.check_flag) EXPECT_EQ(acc.isValueOn(c), e.flag);
+  }
+}
+
+TEST(Shim, InsertBeforeConfigIsANoOpAndAccessorStaysLive)
+{
+  OccupancyVDBMapping map(1);
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0, 0, 1);
+  Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  map.insertPointCloud(cloud, origin, "test"); // no source, no config: nothing happens
+  OccupancyVDBMapping::GridT::Accessor acc = map.getGrid()->getAccessor();
+  EXPECT_EQ(acc.getValue(openvdb::Coord(0, 0, 1)), 0.0f);
+  const Config conf = gtestConfig(10);
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  map.insertPointCloud(cloud, origin, "test");
+  // read through the accessor obtained BEFORE the insert (eager mirror keeps the grid object alive and current)
+  EXPECT_EQ(acc.getValue(openvdb::Coord(0, 0, 0)), logOdds(0.1));
+  EXPECT_EQ(acc.getValue(openvdb::Coord(0, 0, 1)), logOdds(0.9));
+}
+
+TEST(Shim, PositiveAxisRay)
+{
+  runAxisCase(0.1, 10, 5, {{0, 1, true, false}, {1, 1, true, false}, {2, 1, true, false}, {3, 1, true, false}, {4, 1, true, false}, {5, 2, true, true}});
+}
+TEST(Shim, NegativeAxisRay)
+{
+  runAxisCase(0.1, 10, -5, {{-1, 1, true, false}, {-2, 1, true, false}, {-3, 1, true, false}, {-4, 1, true, false}, {-5, 2, true, true}});
+}
+TEST(Shim, MaxRangeRayFreesTheClippedVoxelOnly)
+{
+  runAxisCase(0.1, 0.5, 7, {{0, 1, true, false}, {1, 1, true, false}, {2, 1, true, false}, {3, 1, true, false}, {4, 1, true, false}, {5, 1, true, false}, {6, 0, true, false}});
+}
+
+TEST(Shim, ResetMapGivesAFreshGrid)
+{
+  OccupancyVDBMapping map(1);
+  const Config conf = gtestConfig(10);
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0, 0, 1);
+  Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  map.insertPointCloud(cloud, origin, "test");
+  OccupancyVDBMapping::GridT::Accessor acc = map.getGrid()->getAccessor();
+  EXPECT_EQ(acc.getValue(openvdb::Coord(0, 0, 1)), logOdds(0.9));
+  map.resetMap();
+  acc = map.getGrid()->getAccessor();
+  EXPECT_EQ(acc.getValue(openvdb::Coord(0, 0, 1)), 0.0f);
+}
+
+TEST(Shim, RaycastIntoAccessorThenUpdateMapReturnsChangeGrid)
+{
+  OccupancyVDBMapping map(0.1);
+  const Config conf = gtestConfig(10);
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0.35f, 0.0f, 0.0f);
+  cloud->points.emplace_back(0.0f, -0.25f, 0.0f);
+  Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  OccupancyVDBMapping::UpdateGridT::Ptr upd = OccupancyVDBMapping::UpdateGridT::create(false);
+  OccupancyVDBMapping::UpdateGridT::Accessor uacc = upd->getAccessor();
+  EXPECT_TRUE(map.raycastPointCloud(cloud, origin, 10.0, uacc));
+  EXPECT_TRUE(uacc.isValueOn(openvdb::Coord(0, 0, 0)));
+  EXPECT_FALSE(uacc.getValue(openvdb::Coord(0, 0, 0)));      // free-space voxel: active, value false
+  EXPECT_TRUE(uacc.getValue(openvdb::Coord(3, 0, 0)));       // endpoint of the first ray: hit
+  EXPECT_TRUE(uacc.getValue(openvdb::Coord(0, -2, 0)));      // endpoint of the second ray (worldToIndex half-voxel rule)
+  OccupancyVDBMapping::UpdateGridT::Ptr change = map.updateMap(upd);
+  OccupancyVDBMapping::UpdateGridT::Accessor cacc = change->getAccessor();
+  EXPECT_TRUE(cacc.isValueOn(openvdb::Coord(3, 0, 0)));      // hit flipped inactive -> active
+  EXPECT_TRUE(cacc.getValue(openvdb::Coord(3, 0, 0)));
+  OccupancyVDBMapping::GridT::Accessor acc = map.getGrid()->getAccessor();
+  EXPECT_EQ(acc.getValue(openvdb::Coord(3, 0, 0)), logOdds(0.9));
+  EXPECT_EQ(acc.getValue(openvdb::Coord(1, 0, 0)), logOdds(0.1));
+  // a section around the first endpoint contains exactly that active voxel
+  Eigen::Matrix<double, 3, 1> mn(0.25, -0.05, -0.05), mx(0.39, 0.05, 0.05);
+  auto section = map.getMapSectionUpdateGrid(mn, mx, Eigen::Matrix<double, 4, 4>::Identity(), false);
+  EXPECT_EQ(section->activeVoxelCount(), std::uint64_t(1));
+  EXPECT_TRUE(section->getAccessor().isValueOn(openvdb::Coord(3, 0, 0)));
+}
+
+TEST(Shim, LazyMirrorSyncsOnGetGrid)
+{
+  OccupancyVDBMapping map(0.1);
+  map.setMirrorMode(vdb_mapping::MirrorMode::Lazy);
+  const Config conf = gtestConfig(10);
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0, 0, 0.5f);
+  Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  map.insertPointCloud(cloud, origin, "test");
+  map.insertPointCloud(cloud, origin, "test");
+  OccupancyVDBMapping::GridT::Accessor acc = map.getGrid()->getAccessor();
+  EXPECT_EQ(acc.getValue(openvdb::Coord(0, 0, 5)), logOdds(0.9) + logOdds(0.9));
+  vdbm_stats_t st;
+  EXPECT_TRUE(map.deviceStats(st));
+  EXPECT_EQ(st.rays, std::uint64_t(2));
+}
+
+int main() { return RUN_ALL_TESTS(); }

@@ -73,7 +73,7 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--mode", default="own_cloud")
     ap.add_argument("--scans", type=int, default=3)
-    ap.add_argument("--n", type=int, default=3000)
+    ap.add_argument("--points", type=int, default=3000)
     args = ap.parse_args()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -99,7 +99,7 @@ def main():
             ref.addInputSource("s", rng)
         for k in range(args.scans):
             if args.mode == "own_cloud":
-                clouds = [scans.small_scan(500 + 10 * k + r, n=args.n, scale=2.5) for r in range(world)]
+                clouds = [scans.small_scan(500 + 10 * k + r, n=args.points, scale=2.5) for r in range(world)]
                 origin = clouds[0][1]
                 pts = clouds[rank][0]  # every sensor's cloud is already in map coordinates; all share clouds[0]'s origin
                 vdist.sharded_insert(eng, pts, origin, world, dist, mode="own_cloud")
@@ -108,7 +108,7 @@ def main():
                         ref.accumulateUpdate(clouds[r][0], origin, "s")
                     ref.integrateUpdate()
             else:
-                pts, origin = scans.small_scan(700 + k, n=args.n, scale=2.5)
+                pts, origin = scans.small_scan(700 + k, n=args.points, scale=2.5)
                 vdist.sharded_insert(eng, pts, origin, world, dist, mode="split")
                 if ref:
                     ref.insertPointCloud(pts, origin, "s")

@@ -61,4 +61,4 @@ def test_sharded_map_world2_nccl(mode, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    _run(2, "nccl", mode, tmp_path, extra=("--n", "20000"))
+    _run(2, "nccl", mode, tmp_path, extra=("--points", "20000"))

@@ -14,7 +14,13 @@ The exchange is the one real data-path collective of this path; everything else 
 """
 from __future__ import annotations
 
+import os
+import time
+
 import numpy as np
+
+PROFILE = bool(os.environ.get("VDBM_DIST_PROFILE"))  # host-side phase times (ms) of every exchange, for tuning
+PROFILE_LOG: list = []
 
 RECORD_BYTES = 136  # uint64 key + 8 x uint64 active + 8 x uint64 value
 RECORD_WORDS = 17
@@ -104,18 +110,26 @@ def exchange_and_integrate(engine, world: int, dist=None):
         engine.integrate()
         return 0, 0
     rank = dist.get_rank()
+    t = [time.perf_counter()] if PROFILE else None
     counts, send = engine.partition(world)
+    if PROFILE: t.append(time.perf_counter())
     send_counts = engine.counts_tensor(counts)
     recv_counts = send_counts.new_empty(world)
     dist.all_to_all_single(recv_counts, send_counts)
     recv_host = [int(v) for v in recv_counts.cpu().tolist()]
+    if PROFILE: t.append(time.perf_counter())
     n_recv = sum(recv_host)
     recv = engine.new_recv(n_recv)
     dist.all_to_all_single(recv, send,
                            output_split_sizes=[c * RECORD_WORDS for c in recv_host],
                            input_split_sizes=[int(c) * RECORD_WORDS for c in counts])
+    if PROFILE: t.append(time.perf_counter())
     engine.import_records(recv, n_recv)
+    if PROFILE: t.append(time.perf_counter())
     engine.integrate()
+    if PROFILE:
+        t.append(time.perf_counter())
+        PROFILE_LOG.append([round(1e3 * (b - a), 3) for a, b in zip(t, t[1:])])  # partition, counts, a2a launch, import, integrate
     return int(counts.sum() - counts[rank]), n_recv - recv_host[rank]
 
 
