@@ -231,6 +231,9 @@ def run_ours(args, rank, world, local_rank):
             m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
             m.addInputSource("s", c.max_range)
             eng = vdist.CudaEngine(m, "s")
+            p2p = world > 1 and args.exchange == "p2p"
+            if p2p:
+                vdist.connect_peers(m, dist, capacity_records_per_sender=1 << 19)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             acc_ms, prep_ms, int_ms, leaves = [], [], [], []
             sent = recv = 0
@@ -252,7 +255,11 @@ def run_ours(args, rank, world, local_rank):
                 if k >= args.warmup:
                     s = m.stats()
                     acc_ms.append(s["last_accumulate_ms"]); prep_ms.append(s["last_prep_ms"]); leaves.append(s["last_touched_leaves"])
-                a, b = vdist.exchange_and_integrate(eng, world, dist if world > 1 else None)
+                if p2p:
+                    vdist.push_pull_and_integrate(eng)
+                    a = b = 0
+                else:
+                    a, b = vdist.exchange_and_integrate(eng, world, dist if world > 1 else None)
                 if k >= args.warmup:
                     sent += a; recv += b
                     int_ms.append(m.stats()["last_integrate_ms"])
@@ -325,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
                    "points_per_scan_per_gpu": n_pts, "points_per_step_total": int(rays_v / K),
                    "sequence": "moving sensor, scan k of the sequence per step, fresh map at step 0",
                    "parallelism": ("1 GPU" if world == 1 else (f"{world} GPUs: " + ("one scan split across ranks" if strong else "one LiDAR per GPU of a merged rig") +
-                                                               ", map sharded by leaf key, NCCL all-to-all of update leaves")),
+                                                               ", map sharded by leaf key, " + ("peer-memory (NVLink) push" if args.exchange == "p2p" else "NCCL all-to-all") + " of update leaves")),
                    "l2": "no explicit flush: per-step working set (map leaves %.2f GB + update grid) exceeds the 126 MB L2 and every step has new input" % (res_v["map_leaves"] * 2112 / 1e9)},
         "voxel_updates_per_sec": upd_v / (ms_v * 1e-3), "visits_per_sec": vis_v / (ms_v * 1e-3),
         "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e / K, "h2d_bytes_per_step": 16 * n_pts,
@@ -334,7 +341,9 @@ def run_ours(args, rank, world, local_rank):
         "wall_ms_per_step": res_v["wall_ms"] / K,
     }
     if world > 1:
-        line["exchange"] = {"records_sent_per_step": sent / K, "bytes_sent_per_step": 136 * sent / K}
+        line["exchange"] = {"kind": args.exchange, "records_sent_per_step": (sent / K) if args.exchange == "nccl" else None,
+                            "bytes_sent_per_step": (136 * sent / K) if args.exchange == "nccl" else None,
+                            "note": "p2p = one kernel bins the update leaves by owner and stores the 136-byte records into the owners' inboxes over NVLink (CUDA IPC), device-side epoch wait; nccl = count + record all-to-all"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(cfg, args.cpu_scans)
     else:
@@ -372,6 +381,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU update-leaf exchange: fused peer-memory stores over NVLink (default) or NCCL all-to-all")
     ap.add_argument("--cpu-scans", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

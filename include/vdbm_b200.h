@@ -165,6 +165,22 @@ int vdbm_update_partition(vdbm_map* map, const char* source_id, int32_t n_ranks,
 /* OR device-resident records (as produced by vdbm_update_partition on any rank) into the source's grid. */
 int vdbm_update_import_device(vdbm_map* map, const char* source_id, const void* d_records, uint64_t n_records);
 
+/* ---- multi-GPU exchange over peer memory (one process per GPU on one NVLink/NVSwitch box) -------------------
+ * Fused bin-and-send: ONE kernel bins the source's accumulated update leaves by owner rank and stores each 136-byte
+ * record straight into the owner's inbox (peer memory mapped with CUDA IPC, stores travel over NVLink), then
+ * publishes (epoch, count) words to the peers. The receiving side waits on those words ON THE DEVICE, so no counts
+ * cross the host and no collective library call is on the data path.
+ *   vdbm_exchange_create : allocate this rank's inbox (2 parities x n_ranks sender regions x capacity records) and
+ *                          return its IPC handles (VDBM_IPC_HANDLE_BYTES bytes) for an all-gather by the caller
+ *   vdbm_exchange_connect: map every peer's inbox from the gathered handles (n_ranks x VDBM_IPC_HANDLE_BYTES)
+ *   vdbm_update_push     : bin + send the source's update leaves (its grid is emptied); asynchronous
+ *   vdbm_update_pull     : wait for all senders of this epoch, OR their records into the source's grid */
+#define VDBM_IPC_HANDLE_BYTES 128
+int vdbm_exchange_create(vdbm_map* map, int32_t rank, int32_t n_ranks, uint64_t capacity_records_per_sender, void* handles_out);
+int vdbm_exchange_connect(vdbm_map* map, const void* all_handles);
+int vdbm_update_push(vdbm_map* map, const char* source_id);
+int vdbm_update_pull(vdbm_map* map, const char* source_id);
+
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 int vdbm_stats(vdbm_map* map, vdbm_stats_t* out);
 const char* vdbm_last_error(vdbm_map* map);

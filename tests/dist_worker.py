@@ -74,6 +74,7 @@ def main():
     ap.add_argument("--mode", default="own_cloud")
     ap.add_argument("--scans", type=int, default=3)
     ap.add_argument("--points", type=int, default=3000)
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
     args = ap.parse_args()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -93,6 +94,18 @@ def main():
         m.setConfig(rng, *cfg)
         m.addInputSource("s", rng)
         eng = vdist.CudaEngine(m, "s") if args.backend == "nccl" else OracleEngine(m, "s")
+        p2p = args.backend == "nccl" and args.exchange == "p2p"
+        if p2p:
+            vdist.connect_peers(m, dist, capacity_records_per_sender=1 << 16)
+
+        def insert(points, origin, mode):
+            if not p2p:
+                return vdist.sharded_insert(eng, points, origin, world, dist, mode=mode)
+            if mode == "split":
+                lo, hi = vdist.split_points(points.shape[0], rank, world)
+                points = points[lo:hi]
+            eng.accumulate(points, origin)
+            vdist.push_pull_and_integrate(eng)
         ref = OracleOccupancyVDBMapping(res) if rank == 0 else None
         if ref:
             ref.setConfig(rng, *cfg)
@@ -102,14 +115,14 @@ def main():
                 clouds = [scans.small_scan(500 + 10 * k + r, n=args.points, scale=2.5) for r in range(world)]
                 origin = clouds[0][1]
                 pts = clouds[rank][0]  # every sensor's cloud is already in map coordinates; all share clouds[0]'s origin
-                vdist.sharded_insert(eng, pts, origin, world, dist, mode="own_cloud")
+                insert(pts, origin, "own_cloud")
                 if ref:
                     for r in range(world):
                         ref.accumulateUpdate(clouds[r][0], origin, "s")
                     ref.integrateUpdate()
             else:
                 pts, origin = scans.small_scan(700 + k, n=args.points, scale=2.5)
-                vdist.sharded_insert(eng, pts, origin, world, dist, mode="split")
+                insert(pts, origin, "split")
                 if ref:
                     ref.insertPointCloud(pts, origin, "s")
         # gather the shards on rank 0 and compare the union with the single-process oracle map

@@ -56,9 +56,12 @@ def test_exchange_logic_world2_gloo(mode, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
 @pytest.mark.parametrize("mode", ["own_cloud", "split"])
-def test_sharded_map_world2_nccl(mode, tmp_path):
+def test_sharded_map_world2_gpu(mode, exchange, tmp_path):
+    """Union of the per-rank map shards == oracle map, with the NCCL all-to-all exchange and with the fused
+    peer-memory (CUDA IPC / NVLink) exchange."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    _run(2, "nccl", mode, tmp_path, extra=("--points", "20000"))
+    _run(2, "nccl", mode, tmp_path, extra=("--points", "20000", "--exchange", exchange))

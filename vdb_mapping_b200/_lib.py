@@ -12,6 +12,7 @@ SO_PATH = os.path.join(HERE, "libvdbm_b200.so")
 
 VDBM_OK, VDBM_ERR_INVALID_ARG, VDBM_ERR_NOT_CONFIGURED, VDBM_ERR_UNKNOWN_SOURCE = 0, 1, 2, 3
 VDBM_ERR_BAD_CONFIG, VDBM_ERR_CUDA, VDBM_ERR_OUT_OF_MEMORY, VDBM_ERR_COORD_RANGE = 4, 5, 6, 7
+VDBM_IPC_HANDLE_BYTES = 128
 
 
 class VdbmParams(C.Structure):
@@ -76,6 +77,10 @@ def lib() -> C.CDLL:
     sig("vdbm_leaf_owner", i32, i32p, i32)
     sig("vdbm_update_partition", C.c_int, vp, cp, i32, u64p, pvp)
     sig("vdbm_update_import_device", C.c_int, vp, cp, vp, u64)
+    sig("vdbm_exchange_create", C.c_int, vp, i32, i32, u64, vp)
+    sig("vdbm_exchange_connect", C.c_int, vp, vp)
+    sig("vdbm_update_push", C.c_int, vp, cp)
+    sig("vdbm_update_pull", C.c_int, vp, cp)
     sig("vdbm_stats", C.c_int, vp, C.POINTER(VdbmStats))
     sig("vdbm_last_error", cp, vp)
     sig("vdbm_synchronize", C.c_int, vp)

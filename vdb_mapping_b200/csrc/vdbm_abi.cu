@@ -82,6 +82,19 @@ struct vdbm_map
   size_t part_cap    = 0;
   int dda_grid       = 0;
 
+  // peer-memory exchange (multi-GPU)
+  struct Exchange
+  {
+    ExchangePeers px{};
+    LeafRecord* inbox = nullptr;          // own inbox [2][n_ranks][cap]
+    unsigned long long* ctrl = nullptr;   // own ctrl  [2][n_ranks]
+    uint32_t* d_cursors = nullptr;        // [kMaxRanks] send cursors
+    uint32_t* d_counts  = nullptr;        // [kMaxRanks] received counts of the current epoch
+    std::vector<void*> opened;            // peer mappings to close
+    uint32_t epoch = 0;
+    bool created = false, connected = false;
+  } ex;
+
   vdbm_stats_t stats{};
   Counters base{}; // counters at the last reset, to keep cumulative numbers across device counter resets
 };
@@ -564,6 +577,8 @@ void vdbm_destroy(vdbm_map* m)
   cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
   cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
   cudaFree(m->d_sort); cudaFree(m->d_sort_tmp); cudaFree(m->d_resolved);
+  for (void* p : m->ex.opened) cudaIpcCloseMemHandle(p);
+  cudaFree(m->ex.inbox); cudaFree(m->ex.ctrl); cudaFree(m->ex.d_cursors); cudaFree(m->ex.d_counts);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);
   cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1); cudaEventDestroy(m->ev2);
   if (m->own_stream) cudaStreamDestroy(m->stream);
@@ -1032,6 +1047,108 @@ int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, u
   CU_TRY(m, cudaGetLastError());
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   s->n_bricks = s->n_entries = 0;
+  return VDBM_OK;
+}
+
+int vdbm_exchange_create(vdbm_map* m, int32_t rank, int32_t n_ranks, uint64_t cap, void* handles_out)
+{
+  if (!m || !handles_out || n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks || cap == 0 || cap > 0xFFFFFFu)
+    return VDBM_ERR_INVALID_ARG;
+  if (m->ex.created) return fail(m, VDBM_ERR_INVALID_ARG, "exchange already created on this handle");
+  auto& ex = m->ex;
+  const size_t inbox_bytes = size_t(2) * n_ranks * cap * sizeof(LeafRecord);
+  CU_TRY(m, cudaMalloc(&ex.inbox, inbox_bytes));
+  CU_TRY(m, cudaMalloc(&ex.ctrl, size_t(2) * kMaxRanks * sizeof(unsigned long long)));
+  CU_TRY(m, cudaMalloc(&ex.d_cursors, kMaxRanks * sizeof(uint32_t)));
+  CU_TRY(m, cudaMalloc(&ex.d_counts, kMaxRanks * sizeof(uint32_t)));
+  CU_TRY(m, cudaMemset(ex.ctrl, 0, size_t(2) * kMaxRanks * sizeof(unsigned long long)));
+  CU_TRY(m, cudaMemset(ex.d_counts, 0, kMaxRanks * sizeof(uint32_t)));
+  ex.px.cap = uint32_t(cap); ex.px.n_ranks = n_ranks; ex.px.rank = rank;
+  cudaIpcMemHandle_t h[2];
+  CU_TRY(m, cudaIpcGetMemHandle(&h[0], ex.inbox));
+  CU_TRY(m, cudaIpcGetMemHandle(&h[1], ex.ctrl));
+  static_assert(sizeof(h) == VDBM_IPC_HANDLE_BYTES, "two CUDA IPC handles");
+  std::memcpy(handles_out, h, sizeof(h));
+  ex.created = true;
+  return VDBM_OK;
+}
+
+int vdbm_exchange_connect(vdbm_map* m, const void* all_handles)
+{
+  if (!m || !all_handles) return VDBM_ERR_INVALID_ARG;
+  auto& ex = m->ex;
+  if (!ex.created) return fail(m, VDBM_ERR_INVALID_ARG, "vdbm_exchange_create first");
+  const auto* hs = static_cast<const unsigned char*>(all_handles);
+  for (int r = 0; r < ex.px.n_ranks; ++r)
+  {
+    if (r == ex.px.rank)
+    {
+      ex.px.inbox[r] = ex.inbox;
+      ex.px.ctrl[r]  = ex.ctrl;
+      continue;
+    }
+    cudaIpcMemHandle_t h[2];
+    std::memcpy(h, hs + size_t(r) * VDBM_IPC_HANDLE_BYTES, sizeof(h));
+    void *pi = nullptr, *pc = nullptr;
+    CU_TRY(m, cudaIpcOpenMemHandle(&pi, h[0], cudaIpcMemLazyEnablePeerAccess));
+    CU_TRY(m, cudaIpcOpenMemHandle(&pc, h[1], cudaIpcMemLazyEnablePeerAccess));
+    ex.opened.push_back(pi);
+    ex.opened.push_back(pc);
+    ex.px.inbox[r] = static_cast<LeafRecord*>(pi);
+    ex.px.ctrl[r]  = static_cast<unsigned long long*>(pc);
+  }
+  ex.connected = true;
+  return VDBM_OK;
+}
+
+int vdbm_update_push(vdbm_map* m, const char* source_id)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  auto& ex = m->ex;
+  if (!ex.connected) return fail(m, VDBM_ERR_INVALID_ARG, "exchange not connected");
+  ex.epoch += 1;
+  launchPushUpdate(s->g, s->n_entries, ex.px, ex.epoch & 1u, ex.epoch, ex.d_cursors, m->d_ctr, m->stream);
+  launchResetBricks(s->g, s->n_bricks, m->stream);
+  CU_TRY(m, cudaGetLastError());
+  s->n_bricks = s->n_entries = 0;
+  return VDBM_OK;
+}
+
+int vdbm_update_pull(vdbm_map* m, const char* source_id)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  auto& ex = m->ex;
+  if (!ex.connected || ex.epoch == 0) return fail(m, VDBM_ERR_INVALID_ARG, "vdbm_update_push first");
+  for (int attempt = 0; attempt < 24; ++attempt)
+  {
+    launchPullUpdate(s->g, ex.inbox, ex.ctrl, ex.px.cap, ex.px.n_ranks, ex.epoch & 1u, ex.epoch, ex.d_counts, m->d_ctr, m->stream);
+    launchCompactLeaves(s->g, m->stream);
+    CU_TRY(m, cudaGetLastError());
+    CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s->g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
+    int rc = syncCounters(m);
+    if (rc) return rc;
+    s->n_bricks  = m->h_small[8];
+    s->n_entries = m->h_small[9];
+    const uint32_t flags = m->h_ctr->flags;
+    if (flags & (kFlagExchangeOverflow | kFlagExchangeTimeout))
+    {
+      CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+      return fail(m, VDBM_ERR_OUT_OF_MEMORY, (flags & kFlagExchangeTimeout) ? "exchange: a peer did not publish its epoch in time"
+                                                                            : "exchange: inbox capacity_records_per_sender too small");
+    }
+    const bool overflow = (flags & kFlagUpdateOverflow) != 0;
+    const bool crowded  = uint64_t(s->n_bricks) * 10 > uint64_t(s->cap) * 7;
+    if (!overflow && !crowded) break;
+    if (overflow) CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+    rc = growUpdateGrid(m, *s);
+    if (rc) return rc;
+    if (!overflow) break; // the inbox still holds this epoch's records: a replay of the pull is idempotent
+  }
+  m->stats.last_touched_leaves = s->n_entries;
   return VDBM_OK;
 }
 

@@ -25,6 +25,8 @@ constexpr int32_t kVoxelLimit  = 1 << 23; // |voxel coordinate| must stay below 
 constexpr uint32_t kFlagUpdateOverflow = 1u; // update hash full / probe limit hit
 constexpr uint32_t kFlagMapOverflow    = 2u; // map hash or leaf pool full
 constexpr uint32_t kFlagCoordRange     = 4u; // voxel coordinate outside +-2^23
+constexpr uint32_t kFlagExchangeOverflow = 8u; // a sender region of a peer inbox was too small
+constexpr uint32_t kFlagExchangeTimeout  = 16u; // a peer did not publish its epoch in time
 
 // 63-bit leaf key from LEAF coordinates (voxel >> 3). Sorting keys ascending == sorting leaf origins
 // lexicographically by (x, y, z) (the canonical export order).
@@ -161,6 +163,17 @@ struct RaycastArgs
   const uint32_t* order; // [n] ray indices, longest first (LPT schedule for the DDA kernel)
 };
 
+// Peer-memory exchange state (device-visible part). inbox layout on every rank: [parity 2][sender n_ranks][cap] records;
+// ctrl layout: [parity 2][sender n_ranks] uint64 = (epoch << 32) | record count, written by the sender.
+constexpr int kMaxRanks = 16;
+struct ExchangePeers
+{
+  LeafRecord* inbox[kMaxRanks];        // peer r's inbox base (mapped into this process), [rank] = own
+  unsigned long long* ctrl[kMaxRanks]; // peer r's ctrl base
+  uint32_t cap;                        // records per sender region
+  int32_t n_ranks, rank;
+};
+
 // ---- launch wrappers (vdbm_kernels.cu) ----------------------------------------------------------------
 void launchPrepRays(const RaycastArgs& a, Counters* ctr, cudaStream_t s);
 void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, Counters* ctr, int grid, cudaStream_t s);
@@ -190,6 +203,12 @@ void launchPartition(UpdateGrid ug, uint32_t n_entries, int32_t n_ranks, uint32_
                      LeafRecord* out, int pass, cudaStream_t s);
 void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, uint64_t* out_keys, uint32_t* out_idx, cudaStream_t s);
 void launchSplitRecords(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s);
+// fused bin + send over peer memory; cursors = device scratch [kMaxRanks] (zeroed by the wrapper)
+void launchPushUpdate(UpdateGrid ug, uint32_t n_entries, ExchangePeers px, uint32_t parity, uint32_t epoch, uint32_t* cursors,
+                      Counters* ctr, cudaStream_t s);
+// wait for every sender's (epoch, count) word, then OR all inbox records of this parity into the grid
+void launchPullUpdate(UpdateGrid ug, const LeafRecord* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks,
+                      uint32_t parity, uint32_t epoch, uint32_t* counts_out, Counters* ctr, cudaStream_t s);
 uint32_t launchCount(); // kernels of this library launched by this process
 // CUB radix sort (descending) of (visit count, ray index) on key bits [4, 20); returns temp bytes when d_temp == nullptr
 size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,

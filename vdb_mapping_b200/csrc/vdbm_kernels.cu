@@ -979,6 +979,120 @@ __global__ void partition_kernel(UpdateGrid g, uint32_t n, int32_t n_ranks, uint
 }
 
 // ====================================================================================================
+// Multi-GPU: fused bin-and-send over peer memory (NVLink). A block takes 256 touched update leaves:
+//   A  every thread finds the owner rank of its leaf and reserves a slot in a per-block, per-owner histogram (smem)
+//   B  one global atomicAdd per (block, owner) reserves the block's range in that owner's sender region
+//   C  16 lanes per record gather the 17 words from the brick masks and store them into the OWNER'S inbox
+//      (a mapped peer pointer: the stores go over NVLink); the update masks are zeroed as they are read
+// publish_counts_kernel then releases (epoch << 32 | count) to every peer with system scope.
+// ====================================================================================================
+__global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t n, ExchangePeers px, uint32_t parity, uint32_t* cursors,
+                                                         Counters* ctr)
+{
+  __shared__ uint32_t s_count[kMaxRanks], s_base[kMaxRanks];
+  __shared__ uint32_t s_entry[256], s_dst[256]; // entry id, (owner << 24 | local slot)
+  __shared__ uint64_t s_key[256];
+  const uint32_t i0 = blockIdx.x * 256u;
+  if (threadIdx.x < kMaxRanks) s_count[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t i = i0 + threadIdx.x;
+  if (i < n)
+  {
+    const uint32_t e   = g.entries[i];
+    const uint64_t key = leafKeyOfEntry(g.bkeys[e >> 9], e & 511u);
+    const uint32_t r   = uint32_t(leafOwner(key, px.n_ranks));
+    s_entry[threadIdx.x] = e;
+    s_key[threadIdx.x]   = key;
+    s_dst[threadIdx.x]   = (r << 24) | atomicAdd(&s_count[r], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < px.n_ranks) s_base[threadIdx.x] = s_count[threadIdx.x] ? atomicAdd(cursors + threadIdx.x, s_count[threadIdx.x]) : 0u;
+  __syncthreads();
+  const uint32_t n_here = min(256u, n - i0);
+  for (uint32_t t = threadIdx.x; t < n_here * 16u; t += 256u)
+  {
+    const uint32_t k = t >> 4, j = t & 15u;
+    const uint32_t e = s_entry[k], r = s_dst[k] >> 24, pos = s_base[r] + (s_dst[k] & 0xFFFFFFu);
+    uint64_t word;
+    if (j < 8) { word = g.act[size_t(e) * 8 + j]; g.act[size_t(e) * 8 + j] = 0; }
+    else       { word = g.val[size_t(e) * 8 + (j - 8)]; g.val[size_t(e) * 8 + (j - 8)] = 0; }
+    if (pos >= px.cap) { if (j == 0) atomicOr(&ctr->flags, kFlagExchangeOverflow); continue; }
+    LeafRecord* dst = px.inbox[r] + (size_t(parity) * px.n_ranks + px.rank) * px.cap + pos;
+    if (j < 8) dst->active[j] = word;
+    else dst->value[j - 8] = word;
+    if (j == 0) dst->key = s_key[k];
+  }
+}
+
+__global__ void publish_counts_kernel(ExchangePeers px, uint32_t parity, uint32_t epoch, const uint32_t* cursors)
+{
+  const int r = threadIdx.x;
+  if (r >= px.n_ranks) return;
+  const unsigned long long word = ((unsigned long long)epoch << 32) | min(cursors[r], px.cap);
+  __threadfence_system(); // the records written by push_update_kernel (previous launch on this stream) come first
+  unsigned long long* p = px.ctrl[r] + size_t(parity) * px.n_ranks + px.rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(word) : "memory");
+}
+
+// single warp: wait (bounded) until every sender has published this epoch, then leave the counts in device memory
+__global__ void wait_peers_kernel(const unsigned long long* ctrl, int32_t n_ranks, uint32_t parity, uint32_t epoch, uint32_t* counts_out,
+                                  Counters* ctr)
+{
+  const int s = threadIdx.x;
+  if (s >= n_ranks) return;
+  const unsigned long long* p = ctrl + size_t(parity) * n_ranks + s;
+  const long long t0 = clock64();
+  unsigned long long w = 0;
+  for (;;)
+  {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    if (uint32_t(w >> 32) == epoch) break;
+    if (clock64() - t0 > 4000000000ll) { atomicOr(&ctr->flags, kFlagExchangeTimeout); w = 0; break; } // ~2 s
+    __nanosleep(200);
+  }
+  counts_out[s] = uint32_t(w);
+}
+
+__global__ void __launch_bounds__(256) pull_update_kernel(UpdateGrid g, const LeafRecord* inbox, uint32_t cap, int32_t n_ranks, uint32_t parity,
+                                                         const uint32_t* counts, Counters* ctr)
+{
+  // 16 lanes per record, grid-stride over all sender regions of this parity
+  const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, n_groups = (gridDim.x * blockDim.x) >> 4;
+  const int j = threadIdx.x & 15;
+  for (int s = 0; s < n_ranks; ++s)
+  {
+    const uint32_t cnt       = counts[s];
+    const LeafRecord* region = inbox + (size_t(parity) * n_ranks + s) * cap;
+    // all 32 lanes of a warp run the same number of iterations (ballot below needs the full warp)
+    const uint32_t iters = (cnt + n_groups - 1) / n_groups;
+    for (uint32_t it = 0; it < iters; ++it)
+    {
+      const uint32_t rec = it * n_groups + group;
+      const bool valid   = rec < cnt;
+      uint64_t word = 0, key = 0;
+      if (valid)
+      {
+        key  = region[rec].key;
+        word = (j < 8) ? region[rec].active[j] : region[rec].value[j - 8];
+      }
+      const unsigned grp = 0xFFFFu << (threadIdx.x & 16);
+      const unsigned nz  = __ballot_sync(kFull, valid && j < 8 && word != 0) & grp;
+      uint32_t slot = kInvalid, lib = 0;
+      if (valid && nz && j == 0)
+      {
+        const uint64_t bkey = brickKeyOfLeaf(key, lib);
+        slot                = brickFindOrInsert(g, bkey, ctr);
+      }
+      slot = __shfl_sync(kFull, slot, (threadIdx.x & 16));
+      lib  = __shfl_sync(kFull, lib, (threadIdx.x & 16));
+      if (slot == kInvalid || word == 0) continue;
+      const size_t e = size_t(slot) * kBrickLeaves + lib;
+      redOr64((j < 8) ? g.act + e * 8 + j : g.val + e * 8 + (j - 8), word);
+    }
+  }
+}
+
+// ====================================================================================================
 // launch wrappers
 // ====================================================================================================
 static inline unsigned blocksFor(uint64_t n, unsigned per_block) { return unsigned((n + per_block - 1) / per_block); }
@@ -1117,6 +1231,21 @@ void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, ui
 void launchSplitRecords(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s)
 {
   if (n) VDBM_LAUNCH(split_records_kernel, blocksFor(uint64_t(n) * 16, 256), 256, s, recs, n, origins, active, value);
+}
+
+void launchPushUpdate(UpdateGrid g, uint32_t n_entries, ExchangePeers px, uint32_t parity, uint32_t epoch, uint32_t* cursors, Counters* ctr,
+                      cudaStream_t s)
+{
+  cudaMemsetAsync(cursors, 0, kMaxRanks * sizeof(uint32_t), s);
+  if (n_entries) VDBM_LAUNCH(push_update_kernel, blocksFor(n_entries, 256), 256, s, g, n_entries, px, parity, cursors, ctr);
+  VDBM_LAUNCH(publish_counts_kernel, 1, 32, s, px, parity, epoch, cursors);
+}
+
+void launchPullUpdate(UpdateGrid g, const LeafRecord* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks, uint32_t parity,
+                      uint32_t epoch, uint32_t* counts_out, Counters* ctr, cudaStream_t s)
+{
+  VDBM_LAUNCH(wait_peers_kernel, 1, 32, s, ctrl, n_ranks, parity, epoch, counts_out, ctr);
+  VDBM_LAUNCH(pull_update_kernel, unsigned(smCount()) * 4u, 256, s, g, inbox, cap, n_ranks, parity, counts_out, ctr);
 }
 
 size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,

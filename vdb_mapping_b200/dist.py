@@ -102,6 +102,26 @@ class CudaEngine:
         return self.torch.as_tensor(np.asarray(counts, dtype=np.int64), device=self.device)
 
 
+def connect_peers(mapping, dist, capacity_records_per_sender: int = 1 << 19):
+    """One-time set-up of the peer-memory exchange: every rank allocates its inbox, the CUDA IPC handles are
+    all-gathered through torch.distributed and every peer inbox is mapped. Returns True when the fused path is usable."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = mapping.exchangeCreate(rank, world, capacity_records_per_sender)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    mapping.exchangeConnect(b"".join(gathered))
+    dist.barrier()
+    return True
+
+
+def push_pull_and_integrate(engine):
+    """Fused exchange: bin + NVLink stores into the owners' inboxes, device-side wait on the peers' epoch words, import,
+    updateMap. No counts cross the host, no collective call on the data path."""
+    engine.m.updatePush(engine.src)
+    engine.m.updatePull(engine.src)
+    engine.integrate()
+
+
 def exchange_and_integrate(engine, world: int, dist=None):
     """Steps 2-5 above. `engine` implements partition/new_recv/import_records/integrate/counts_tensor;
     `dist` is torch.distributed (or None / world == 1 for the single-rank short-cut).

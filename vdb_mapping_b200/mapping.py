@@ -238,6 +238,22 @@ class OccupancyVDBMapping:
         self._check(self._L.vdbm_update_import_device(self._h, source_id.encode(), C.c_void_p(ptr), int(n)))
 
 
+    # peer-memory exchange (CUDA IPC over NVLink), see dist.py
+    def exchangeCreate(self, rank: int, n_ranks: int, capacity_records_per_sender: int) -> bytes:
+        buf = C.create_string_buffer(L.VDBM_IPC_HANDLE_BYTES)
+        self._check(self._L.vdbm_exchange_create(self._h, rank, n_ranks, capacity_records_per_sender, buf))
+        return buf.raw
+
+    def exchangeConnect(self, all_handles: bytes):
+        self._check(self._L.vdbm_exchange_connect(self._h, C.c_char_p(all_handles)))
+
+    def updatePush(self, source_id: str):
+        self._check(self._L.vdbm_update_push(self._h, source_id.encode()))
+
+    def updatePull(self, source_id: str):
+        self._check(self._L.vdbm_update_pull(self._h, source_id.encode()))
+
+
 def leaf_owner(origin, n_ranks: int) -> int:
     o = np.ascontiguousarray(origin, dtype=np.int32)
     return int(L.lib().vdbm_leaf_owner(o.ctypes.data_as(C.POINTER(C.c_int32)), n_ranks))
