@@ -92,6 +92,12 @@ class CudaEngine:
         return self.torch.empty(n_records * RECORD_WORDS, dtype=self.torch.int64, device=self.device)
 
     def import_records(self, buf, n_records: int):
+        # torch orders its NCCL collectives after/before work on torch's CURRENT stream only. If the library launches on
+        # another stream (its own, or one that is not current), the received buffer must be complete before the import
+        # kernel may read it: wait for the collective on the host.
+        torch = self.torch
+        if self.m.stream_handle == 0 or self.m.stream_handle != torch.cuda.current_stream().cuda_stream:
+            torch.cuda.current_stream().synchronize()
         if n_records:
             self.m.importUpdateDevice(self.src, buf.data_ptr(), n_records)
 

@@ -60,6 +60,7 @@ class OccupancyVDBMapping:
                  update_capacity_leaves: int = 0, map_capacity_leaves: int = 0, stream: int | None = None):
         self._L = L.lib()
         self.resolution = float(resolution)
+        self.stream_handle = int(stream) if stream else 0  # 0 = library-owned stream
         p = L.VdbmParams(float(resolution), int(device), int(replicate_probe_quirk), int(update_capacity_leaves),
                          int(map_capacity_leaves), C.c_void_p(stream) if stream else None)
         h = C.c_void_p()
