@@ -129,14 +129,20 @@ struct Counters
   unsigned int n_out;                                             // generic output counter (sections, partition)
 };
 
-// One prepared ray (written by prep_rays_kernel, consumed by raycast_dda_kernel). 48 bytes.
+// One prepared ray (written by prep_rays_kernel, consumed by raycast_dda_kernel). 32 bytes.
 struct __align__(16) RayRec
 {
   double delta[3];  // |1/dir| per axis, DBL_MAX when dir == 0     (DDA::mDelta)
-  int32_t end[3];   // end voxel
-  uint32_t flags;   // bit0 valid, bit1 clipped (no hit at the end voxel), bit2 zero-length
+  uint32_t visits;  // voxels castRayIntoGrid marks: 1 + |dx| + |dy| + |dz| (0 for a zero-length ray)
+  uint32_t flags;   // bit0 valid, bit1 clipped (no hit at the end voxel), bit2 zero-length, bits 4..9 step signs
 };
 constexpr uint32_t kRayValid = 1u, kRayClipped = 2u, kRayZeroLen = 4u;
+// step sign of axis a in bits (4+2a, 5+2a): 0 = none, 1 = +1, 2 = -1
+__host__ __device__ __forceinline__ int rayStep(uint32_t flags, int axis)
+{
+  const uint32_t f = (flags >> (4 + 2 * axis)) & 3u;
+  return f == 1u ? 1 : (f == 2u ? -1 : 0);
+}
 
 // 136-byte exchange / export record of an update-grid leaf
 struct LeafRecord

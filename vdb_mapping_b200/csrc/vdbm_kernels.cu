@@ -114,9 +114,10 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
     const float* p = reinterpret_cast<const float*>(a.points + i * a.stride);
     double e[3]    = {double(p[0]), double(p[1]), double(p[2])}; // VDBMapping.hpp:501
     RayRec r;
-    r.flags = 0;
-    r.end[0] = r.end[1] = r.end[2] = 0;
+    r.flags  = 0;
+    r.visits = 0;
     r.delta[0] = r.delta[1] = r.delta[2] = DBL_MAX;
+    uint32_t sign_bits = 0;
     // VDBMapping.hpp:505-510 skips NaN; +-inf is undefined behaviour in the reference and is dropped here too
     const bool finite = isfinite(e[0]) && isfinite(e[1]) && isfinite(e[2]);
     if (!finite) nan_skipped = 1;
@@ -146,11 +147,11 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
         const double fl = floor(__dmul_rn((fmod(e[k], a.resolution) != 0.0) ? __dadd_rn(e[k], a.half_res) : e[k], a.inv_res));
         if (!(fabs(fl) < double(kVoxelLimit))) in_range = false;
         const int32_t ei = in_range ? int32_t(fl) : 0;
-        r.end[k]         = ei;
         const double dir = __dsub_rn(double(ei), double(a.origin_idx[k])); // exact
         if (dir != 0.0)
         {
           zero       = false;
+          sign_bits |= (dir > 0.0 ? 1u : 2u) << (4 + 2 * k);
           r.delta[k] = fabs(__ddiv_rn(1.0, dir)); // Ray::mInvDir = 1/dir; DDA::mDelta = step * inv = |inv|
           l1 += (long long)fabs(dir);
         }
@@ -158,8 +159,9 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
       if (!in_range) range_err = 1;
       else
       {
-        r.flags = kRayValid | (max_range_ray ? kRayClipped : 0u) | (zero ? kRayZeroLen : 0u);
-        visits  = zero ? 0ull : (unsigned long long)(1 + l1); // castRayIntoGrid marks 1 + |dx|+|dy|+|dz| voxels
+        r.flags  = kRayValid | (max_range_ray ? kRayClipped : 0u) | (zero ? kRayZeroLen : 0u) | sign_bits;
+        visits   = zero ? 0ull : (unsigned long long)(1 + l1); // castRayIntoGrid marks 1 + |dx|+|dy|+|dz| voxels
+        r.visits = uint32_t(visits);
       }
     }
     a.rays[i]      = r;
@@ -245,16 +247,17 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
   bool busy = false, done = false, need = false;
   double n0 = 0, n1 = 0, n2 = 0, d0 = 0, d1 = 0, d2 = 0;
   int x = 0, y = 0, z = 0, sx = 0, sy = 0, sz = 0;
-  uint32_t clipped = 0;
-  uint32_t slot    = kInvalid;
-  uint32_t cur_off  = kInvalid;
-  uint32_t cur_near = kInvalid; // word index in s_near when the current run lies in the near cube
-  bool in_near      = false;    // the ray has not left the near cube yet
-  uint64_t acc      = 0;
+  uint32_t remaining = 0; // voxels still to mark on the current ray (exact: 1 + |dx|+|dy|+|dz|, see prep_rays_kernel)
+  uint32_t clipped   = 0;
+  uint32_t slot      = kInvalid;
+  uint32_t cur_off   = kInvalid;
+  uint32_t cur_near  = kInvalid; // word index in s_near when the current run lies in the near cube
+  bool in_near       = false;    // the ray has not left the near cube yet
+  uint64_t acc       = 0;
 
-  for (uint32_t iter = 0;; ++iter)
+  for (;;)
   {
-    if ((iter & (kBatch - 1)) == 0)
+    // ================= batch point (warp-uniform): refills + brick lookups, every kBatch voxel steps =================
     {
       // ---- refill idle lanes (warp-aggregated fetch from the global ray cursor) ----
       const unsigned want = __ballot_sync(kFull, !busy && !done);
@@ -291,11 +294,10 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
                 n0 = (d0 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d0);
                 n1 = (d1 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d1);
                 n2 = (d2 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d2);
-                sx = (r.end[0] > ox) - (r.end[0] < ox);
-                sy = (r.end[1] > oy) - (r.end[1] < oy);
-                sz = (r.end[2] > oz) - (r.end[2] < oz);
+                sx = rayStep(r.flags, 0); sy = rayStep(r.flags, 1); sz = rayStep(r.flags, 2);
                 x = ox; y = oy; z = oz;
-                clipped = r.flags & kRayClipped;
+                remaining = r.visits;
+                clipped   = r.flags & kRayClipped;
                 slot = origin_slot; cur_off = kInvalid; acc = 0;
                 in_near = true;
                 need = false;
@@ -317,75 +319,81 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
       if (__all_sync(kFull, done && !busy)) break;
     }
 
-    if (busy && !need)
+    // ================= kBatch voxel steps =================
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
     {
-      // ---- mark current voxel (setActiveState(dda.voxel(), true), VDBMapping.hpp:563) ----
-      const uint32_t off = brickWordOffset(x, y, z);
-      const uint64_t bit = uint64_t(1) << (((y & 7) << 3) | (z & 7));
-      uint64_t* const brick_act = g.act + size_t(slot) * (kBrickLeaves * 8);
-      if (off != cur_off)
+      if (busy && !need)
       {
-        if (acc != 0 && slot != kInvalid)
+        // ---- mark current voxel (setActiveState(dda.voxel(), true), VDBMapping.hpp:563) ----
+        const uint32_t off = brickWordOffset(x, y, z);
+        const uint64_t bit = uint64_t(1) << (((y & 7) << 3) | (z & 7));
+        uint64_t* const brick_act = g.act + size_t(slot) * (kBrickLeaves * 8);
+        if (off != cur_off)
         {
-          if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
-          else markWord<MODE>(brick_act + cur_off, acc);
-        }
-        cur_off  = off;
-        cur_near = kInvalid;
-        // is the new run inside the near cube? (runs never straddle it: the cube is leaf aligned; a ray is monotonic
-        // on every axis, so once it has left the cube it never comes back and the test is skipped for good)
-        if (in_near)
-        {
-          const unsigned rx = unsigned(x - c0x), ry = unsigned(y - c0y), rz = unsigned(z - c0z);
-          in_near = (rx < 64u && ry < 64u && rz < 64u);
-          if (in_near) cur_near = ((rx >> 3) << 9) | ((ry >> 3) << 6) | ((rz >> 3) << 3) | (rx & 7u);
-        }
-        acc     = 0;
-      }
-      acc |= bit;
-
-      // ---- DDA::step(): axis = MinIndex(next); t = next[axis]; next[axis] += delta[axis]; voxel[axis] += step ----
-      // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
-      //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
-      const bool ax = (n0 < n1) && (n0 < n2);
-      const bool ay = !ax && (n1 < n2);
-      const bool az = !ax && !ay;
-      const double t  = ax ? n0 : (ay ? n1 : n2);
-      const double dl = ax ? d0 : (ay ? d1 : d2);
-      const double nn = __dadd_rn(t, dl);
-      n0 = ax ? nn : n0;
-      n1 = ay ? nn : n1;
-      n2 = az ? nn : n2;
-      x += ax ? sx : 0;
-      y += ay ? sy : 0;
-      z += az ? sz : 0;
-      if (!(t <= 1.0))
-      {
-        // ray finished: the voxel just stepped to is NOT marked. Flush; the last marked voxel is the end voxel,
-        // which also receives the hit unless the ray was clipped (VDBMapping.hpp:533-536).
-        if (slot != kInvalid)
-        {
-          if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
-          else markWord<MODE>(brick_act + cur_off, acc);
-          if (!clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
-        }
-        busy = false;
-      }
-      else
-      {
-        // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
-        const int c  = ax ? x : (ay ? y : z);
-        const int st = ax ? sx : (ay ? sy : sz);
-        if (((c + (st < 0 ? 1 : 0)) & 63) == 0)
-        {
-          if (slot != kInvalid)
+          if (acc != 0 && slot != kInvalid)
           {
             if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
             else markWord<MODE>(brick_act + cur_off, acc);
           }
-          acc     = 0;
-          cur_off = kInvalid;
-          need    = true;
+          cur_off  = off;
+          cur_near = kInvalid;
+          acc      = 0;
+          // is the new run inside the near cube? (runs never straddle it: the cube is leaf aligned; a ray is monotonic
+          // on every axis, so once it has left the cube it never comes back and the test is skipped for good)
+          if (in_near)
+          {
+            const unsigned rx = unsigned(x - c0x), ry = unsigned(y - c0y), rz = unsigned(z - c0z);
+            in_near = (rx < 64u && ry < 64u && rz < 64u);
+            if (in_near) cur_near = ((rx >> 3) << 9) | ((ry >> 3) << 6) | ((rz >> 3) << 3) | (rx & 7u);
+          }
+        }
+        acc |= bit;
+
+        if (--remaining == 0)
+        {
+          // Last voxel of the ray (= the end voxel). OpenVDB's loop ends when the NEXT crossing time exceeds t1 = 1;
+          // that happens exactly after 1 + |dx|+|dy|+|dz| marks (the crossing times of axis a are (m + 0.5)/|d_a| up to
+          // fp64 rounding, m < |d_a| <=> t < 1 with a margin of 0.5/|d_a| >> accumulated rounding for |d_a| < 2^24).
+          // Flush; the end voxel also receives the hit unless the ray was clipped (VDBMapping.hpp:533-536).
+          if (slot != kInvalid)
+          {
+            if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
+            else markWord<MODE>(brick_act + cur_off, acc);
+            if (!clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
+          }
+          busy = false;
+        }
+        else
+        {
+          // ---- DDA::step(): axis = MinIndex(next); next[axis] += delta[axis]; voxel[axis] += step[axis] ----
+          // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
+          //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
+          // Branch-free: every lane executes the three predicated adds whatever axis it takes.
+          const bool ax = (n0 < n1) && (n0 < n2);
+          const bool ay = !ax && (n1 < n2);
+          const bool az = !ax && !ay;
+          const double a0 = __dadd_rn(n0, d0), a1 = __dadd_rn(n1, d1), a2 = __dadd_rn(n2, d2);
+          n0 = ax ? a0 : n0;
+          n1 = ay ? a1 : n1;
+          n2 = az ? a2 : n2;
+          x += ax ? sx : 0;
+          y += ay ? sy : 0;
+          z += az ? sz : 0;
+          // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
+          const int c  = ax ? x : (ay ? y : z);
+          const int st = ax ? sx : (ay ? sy : sz);
+          if (((c + (st < 0 ? 1 : 0)) & 63) == 0)
+          {
+            if (slot != kInvalid)
+            {
+              if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
+              else markWord<MODE>(brick_act + cur_off, acc);
+            }
+            acc     = 0;
+            cur_off = kInvalid;
+            need    = true;
+          }
         }
       }
     }
