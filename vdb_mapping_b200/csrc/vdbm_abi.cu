@@ -76,6 +76,7 @@ struct vdbm_map
   void* d_sort_tmp  = nullptr;
   size_t sort_tmp_bytes = 0;
   size_t rays_cap   = 0;
+  uint64_t* d_near     = nullptr; // privatised near-field brick copies (always left zeroed)
   uint32_t* d_resolved = nullptr; // K2a output: map leaf index per touched update leaf
   size_t resolved_cap  = 0;
   LeafRecord* d_part = nullptr; // partition output
@@ -342,7 +343,7 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     sortRaysByLength(m->d_sort_tmp, m->sort_tmp_bytes, a.sort_keys, m->d_sort + m->rays_cap, a.sort_idx, m->d_sort + 3 * m->rays_cap,
                      uint32_t(n), m->stream);
     CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
-    launchRaycastDDA(a, s.g, m->d_ctr, m->dda_grid, m->stream);
+    launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream);
     launchCompactLeaves(s.g, m->stream);
     CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
     CU_TRY(m, cudaGetLastError());
@@ -557,6 +558,8 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
   if (rc) return rc;
   rc = allocMapHash(mm, nextPow2(uint64_t(pool) * 2));
   if (rc) return rc;
+  CU_TRY(mm, cudaMalloc(&m->d_near, nearCopiesBytes()));
+  CU_TRY(mm, cudaMemsetAsync(m->d_near, 0, nearCopiesBytes(), m->stream));
   m->lo.replicate_quirk = params->replicate_probe_quirk ? 1u : 0u;
   m->dda_grid           = raycastDDAGrid(m->device);
   CU_TRY(mm, cudaStreamSynchronize(m->stream));
@@ -576,7 +579,7 @@ void vdbm_destroy(vdbm_map* m)
   freeMapPool(m->mt);
   cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
   cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
-  cudaFree(m->d_sort); cudaFree(m->d_sort_tmp); cudaFree(m->d_resolved);
+  cudaFree(m->d_sort); cudaFree(m->d_sort_tmp); cudaFree(m->d_resolved); cudaFree(m->d_near);
   for (void* p : m->ex.opened) cudaIpcCloseMemHandle(p);
   cudaFree(m->ex.inbox); cudaFree(m->ex.ctrl); cudaFree(m->ex.d_cursors); cudaFree(m->ex.d_counts);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);

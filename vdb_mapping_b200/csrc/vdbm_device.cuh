@@ -182,7 +182,9 @@ struct ExchangePeers
 
 // ---- launch wrappers (vdbm_kernels.cu) ----------------------------------------------------------------
 void launchPrepRays(const RaycastArgs& a, Counters* ctr, cudaStream_t s);
-void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, Counters* ctr, int grid, cudaStream_t s);
+// near_act: zero-initialised scratch of nearCopiesBytes() bytes (privatised near-field bricks), left zeroed again
+void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s);
+size_t nearCopiesBytes();
 int raycastDDAGrid(int device);
 // rebuild ug.entries / counters[1] from the occupied bricks (brick count read on the device)
 void launchCompactLeaves(UpdateGrid ug, cudaStream_t s);

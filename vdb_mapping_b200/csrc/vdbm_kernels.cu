@@ -209,50 +209,50 @@ __device__ __forceinline__ void markWord(uint64_t* p, uint64_t v)
 
 // Near field: every ray starts at the sensor, so the mask words within a few leaves of it receive an update
 // from (almost) every ray: measured on B200 those same-address REDs serialise in a handful of L2 slices and cost
-// a third of the kernel. They are staged instead in a per-CTA shared-memory bitmap covering the leaf-aligned
-// 64^3-voxel cube [c0, c0+64) around the sensor (4096 mask words = 32 KB, same (leaf, x&7) word layout as the
-// global bricks) and flushed ONCE per CTA at the end.
-constexpr int kNearWords = 4096;
+// a third of the kernel. The 2x2x2 bricks around the sensor (a 128^3-voxel region with the sensor at least 32
+// voxels inside) are therefore PRIVATISED: kNearCopies zero-initialised copies of their active masks live in
+// global memory, a CTA marks copy (blockIdx % kNearCopies), and merge_near_kernel ORs the copies into the real
+// bricks afterwards. The hot addresses are spread kNearCopies-fold and the inner loop keeps ONE uniform mark path
+// (a brick is just a base pointer).
+constexpr int kNearCopies = 32;
+constexpr int kNearBricks = 8;
 
-__device__ __forceinline__ void nearOr(unsigned int* s_near, uint32_t word, uint64_t acc)
+// first brick (per axis) of the 2x2x2 near region: the brick below the sensor's if the sensor sits in the lower half
+__host__ __device__ __forceinline__ int nearBrick0(int o) { return (o >> 6) - (((o & 63) < 32) ? 1 : 0); }
+
+// in-place predicated adds (one instruction each; keeps the three DDA axes branch-free without select chains)
+__device__ __forceinline__ void addIf(double& n, double d, bool p)
 {
-  const unsigned int lo = (unsigned int)acc, hi = (unsigned int)(acc >> 32);
-  if (lo) atomicOr(&s_near[2 * word], lo);
-  if (hi) atomicOr(&s_near[2 * word + 1], hi);
+  asm("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q add.rn.f64 %0, %0, %1; }" : "+d"(n) : "d"(d), "r"((unsigned)p));
+}
+__device__ __forceinline__ void addIf(int& n, int d, bool p)
+{
+  asm("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q add.s32 %0, %0, %1; }" : "+r"(n) : "r"(d), "r"((unsigned)p));
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, Counters* ctr)
+__global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, uint64_t* near_act, Counters* ctr)
 {
-  __shared__ unsigned int s_near[2 * kNearWords]; // 64-bit mask words as 32-bit halves (native shared-memory atomicOr)
-  __shared__ uint32_t s_near_slot[8];
+  __shared__ uint32_t s_near_slot[kNearBricks];
   const int lane = threadIdx.x & 31;
   const int ox = a.origin_idx[0], oy = a.origin_idx[1], oz = a.origin_idx[2];
-  // near cube origin: 4 leaves below the sensor's leaf on every axis (leaf aligned)
-  const int c0x = ((ox >> 3) - 4) << 3, c0y = ((oy >> 3) - 4) << 3, c0z = ((oz >> 3) - 4) << 3;
-  for (int i = threadIdx.x; i < 2 * kNearWords; i += blockDim.x) s_near[i] = 0u;
-  // the cube overlaps at most 2x2x2 bricks: resolve their slots once per CTA (needed for the final flush)
-  if (threadIdx.x < 8)
-  {
-    const int bx = (c0x >> 6) + (threadIdx.x >> 2), by = (c0y >> 6) + ((threadIdx.x >> 1) & 1), bz = (c0z >> 6) + (threadIdx.x & 1);
-    // only bricks the cube really reaches (the cube may sit inside a single brick along an axis)
-    const bool used = (bx <= ((c0x + 63) >> 6)) && (by <= ((c0y + 63) >> 6)) && (bz <= ((c0z + 63) >> 6));
-    s_near_slot[threadIdx.x] = used ? brickFindOrInsert(g, packLeafKey(bx, by, bz), ctr) : kInvalid;
-  }
+  const int nbx = nearBrick0(ox), nby = nearBrick0(oy), nbz = nearBrick0(oz);
+  // resolve the real slots of the 8 near bricks once per CTA (endpoint hits and the merge kernel use them)
+  if (threadIdx.x < kNearBricks)
+    s_near_slot[threadIdx.x] = brickFindOrInsert(g, packLeafKey(nbx + (threadIdx.x >> 2), nby + ((threadIdx.x >> 1) & 1), nbz + (threadIdx.x & 1)), ctr);
   __syncthreads();
-  // every ray starts in the sensor's brick
-  const uint32_t origin_slot =
-      s_near_slot[(((ox >> 6) - (c0x >> 6)) << 2) | (((oy >> 6) - (c0y >> 6)) << 1) | ((oz >> 6) - (c0z >> 6))];
+  uint64_t* const my_near = near_act + size_t(blockIdx.x % kNearCopies) * (kNearBricks * kBrickLeaves * 8);
+  const int origin_ni     = (((ox >> 6) - nbx) << 2) | (((oy >> 6) - nby) << 1) | ((oz >> 6) - nbz);
+  const uint32_t origin_slot = s_near_slot[origin_ni];
 
   bool busy = false, done = false, need = false;
   double n0 = 0, n1 = 0, n2 = 0, d0 = 0, d1 = 0, d2 = 0;
   int x = 0, y = 0, z = 0, sx = 0, sy = 0, sz = 0;
   uint32_t remaining = 0; // voxels still to mark on the current ray (exact: 1 + |dx|+|dy|+|dz|, see prep_rays_kernel)
   uint32_t clipped   = 0;
-  uint32_t slot      = kInvalid;
+  uint32_t slot      = kInvalid;  // real brick slot (value masks, validity)
+  uint64_t* act_base = my_near;   // where this brick's active mask words go: a private near copy or the real brick
   uint32_t cur_off   = kInvalid;
-  uint32_t cur_near  = kInvalid; // word index in s_near when the current run lies in the near cube
-  bool in_near       = false;    // the ray has not left the near cube yet
   uint64_t acc       = 0;
 
   for (;;)
@@ -298,8 +298,9 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
                 x = ox; y = oy; z = oz;
                 remaining = r.visits;
                 clipped   = r.flags & kRayClipped;
-                slot = origin_slot; cur_off = kInvalid; acc = 0;
-                in_near = true;
+                slot      = origin_slot;
+                act_base  = my_near + size_t(origin_ni) * (kBrickLeaves * 8);
+                cur_off = kInvalid; acc = 0;
                 need = false;
                 busy = true;
               }
@@ -312,7 +313,19 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
       {
         if (busy && need)
         {
-          slot = brickFindOrInsert(g, packLeafKey(x >> 6, y >> 6, z >> 6), ctr);
+          const int bx = x >> 6, by = y >> 6, bz = z >> 6;
+          const unsigned rx = unsigned(bx - nbx), ry = unsigned(by - nby), rz = unsigned(bz - nbz);
+          if (rx < 2u && ry < 2u && rz < 2u)
+          {
+            const int ni = int((rx << 2) | (ry << 1) | rz);
+            slot         = s_near_slot[ni];
+            act_base     = my_near + size_t(ni) * (kBrickLeaves * 8);
+          }
+          else
+          {
+            slot     = brickFindOrInsert(g, packLeafKey(bx, by, bz), ctr);
+            act_base = g.act + size_t(slot) * (kBrickLeaves * 8);
+          }
           need = false;
         }
       }
@@ -328,25 +341,11 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
         // ---- mark current voxel (setActiveState(dda.voxel(), true), VDBMapping.hpp:563) ----
         const uint32_t off = brickWordOffset(x, y, z);
         const uint64_t bit = uint64_t(1) << (((y & 7) << 3) | (z & 7));
-        uint64_t* const brick_act = g.act + size_t(slot) * (kBrickLeaves * 8);
         if (off != cur_off)
         {
-          if (acc != 0 && slot != kInvalid)
-          {
-            if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
-            else markWord<MODE>(brick_act + cur_off, acc);
-          }
-          cur_off  = off;
-          cur_near = kInvalid;
-          acc      = 0;
-          // is the new run inside the near cube? (runs never straddle it: the cube is leaf aligned; a ray is monotonic
-          // on every axis, so once it has left the cube it never comes back and the test is skipped for good)
-          if (in_near)
-          {
-            const unsigned rx = unsigned(x - c0x), ry = unsigned(y - c0y), rz = unsigned(z - c0z);
-            in_near = (rx < 64u && ry < 64u && rz < 64u);
-            if (in_near) cur_near = ((rx >> 3) << 9) | ((ry >> 3) << 6) | ((rz >> 3) << 3) | (rx & 7u);
-          }
+          if (acc != 0 && slot != kInvalid) markWord<MODE>(act_base + cur_off, acc);
+          cur_off = off;
+          acc     = 0;
         }
         acc |= bit;
 
@@ -358,8 +357,7 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
           // Flush; the end voxel also receives the hit unless the ray was clipped (VDBMapping.hpp:533-536).
           if (slot != kInvalid)
           {
-            if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
-            else markWord<MODE>(brick_act + cur_off, acc);
+            markWord<MODE>(act_base + cur_off, acc);
             if (!clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
           }
           busy = false;
@@ -369,27 +367,18 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
           // ---- DDA::step(): axis = MinIndex(next); next[axis] += delta[axis]; voxel[axis] += step[axis] ----
           // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
           //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
-          // Branch-free: every lane executes the three predicated adds whatever axis it takes.
+          // Branch-free: three predicated in-place adds per lane, whatever axis it takes.
           const bool ax = (n0 < n1) && (n0 < n2);
           const bool ay = !ax && (n1 < n2);
           const bool az = !ax && !ay;
-          const double a0 = __dadd_rn(n0, d0), a1 = __dadd_rn(n1, d1), a2 = __dadd_rn(n2, d2);
-          n0 = ax ? a0 : n0;
-          n1 = ay ? a1 : n1;
-          n2 = az ? a2 : n2;
-          x += ax ? sx : 0;
-          y += ay ? sy : 0;
-          z += az ? sz : 0;
+          addIf(n0, d0, ax); addIf(n1, d1, ay); addIf(n2, d2, az);
+          addIf(x, sx, ax);  addIf(y, sy, ay);  addIf(z, sz, az);
           // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
           const int c  = ax ? x : (ay ? y : z);
           const int st = ax ? sx : (ay ? sy : sz);
           if (((c + (st < 0 ? 1 : 0)) & 63) == 0)
           {
-            if (slot != kInvalid)
-            {
-              if (cur_near != kInvalid) nearOr(s_near, cur_near, acc);
-              else markWord<MODE>(brick_act + cur_off, acc);
-            }
+            if (slot != kInvalid) markWord<MODE>(act_base + cur_off, acc);
             acc     = 0;
             cur_off = kInvalid;
             need    = true;
@@ -398,19 +387,27 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
       }
     }
   }
+}
 
-  // ---- flush the near-field bitmap: one RED per non-zero word and CTA ----
+// OR the privatised near-brick copies into the real bricks and leave the copies zeroed for the next scan
+__global__ void __launch_bounds__(256) merge_near_kernel(UpdateGrid g, uint64_t* near_act, int nbx, int nby, int nbz, Counters* ctr)
+{
+  __shared__ uint32_t s_slot[kNearBricks];
+  if (threadIdx.x < kNearBricks)
+    s_slot[threadIdx.x] = brickFindOrInsert(g, packLeafKey(nbx + (threadIdx.x >> 2), nby + ((threadIdx.x >> 1) & 1), nbz + (threadIdx.x & 1)), ctr);
   __syncthreads();
-  for (int i = threadIdx.x; i < kNearWords; i += blockDim.x)
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // word index in [0, 8 * 4096)
+  if (i >= kNearBricks * kBrickLeaves * 8) return;
+  uint64_t v = 0;
+#pragma unroll 8
+  for (int c = 0; c < kNearCopies; ++c)
   {
-    const unsigned long long v = (unsigned long long)s_near[2 * i] | ((unsigned long long)s_near[2 * i + 1] << 32);
-    if (v == 0ull) continue;
-    // word i = (leaf lx,ly,lz in the cube) * 8 + (x & 7)
-    const int lx = i >> 9, ly = (i >> 6) & 7, lz = (i >> 3) & 7, xw = i & 7;
-    const int vx = c0x + (lx << 3) + xw, vy = c0y + (ly << 3), vz = c0z + (lz << 3);
-    const uint32_t bs = s_near_slot[(((vx >> 6) - (c0x >> 6)) << 2) | (((vy >> 6) - (c0y >> 6)) << 1) | ((vz >> 6) - (c0z >> 6))];
-    if (bs != kInvalid) markWord<MODE>(g.act + size_t(bs) * (kBrickLeaves * 8) + brickWordOffset(vx, vy, vz), v);
+    uint64_t* p = near_act + size_t(c) * (kNearBricks * kBrickLeaves * 8) + i;
+    const uint64_t w = *p;
+    if (w) { v |= w; *p = 0; }
   }
+  const uint32_t slot = s_slot[i / (kBrickLeaves * 8)];
+  if (v && slot != kInvalid) g.act[size_t(slot) * (kBrickLeaves * 8) + (i % (kBrickLeaves * 8))] |= v;
 }
 
 // ====================================================================================================
@@ -1142,15 +1139,19 @@ int raycastDDAGrid(int device)
   return sms * per_sm; // persistent: exactly one resident wave
 }
 
-void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, Counters* ctr, int grid, cudaStream_t s)
+size_t nearCopiesBytes() { return size_t(kNearCopies) * kNearBricks * kBrickLeaves * 8 * sizeof(uint64_t); }
+
+void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s)
 {
   if (a.n == 0) return;
   const uint64_t blocks = (((a.n + 31) / 32) + 7) / 8;
   if (uint64_t(grid) > blocks) grid = int(blocks);
   static const int mode = [] { const char* e = getenv("VDBM_DDA_MODE"); return e ? atoi(e) : 0; }();
-  if (mode == 1) VDBM_LAUNCH(raycast_dda_kernel<1>, grid, 256, s, a, g, ctr);
-  else if (mode == 2) VDBM_LAUNCH(raycast_dda_kernel<2>, grid, 256, s, a, g, ctr);
-  else VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, ctr);
+  if (mode == 1) VDBM_LAUNCH(raycast_dda_kernel<1>, grid, 256, s, a, g, near_act, ctr);
+  else if (mode == 2) VDBM_LAUNCH(raycast_dda_kernel<2>, grid, 256, s, a, g, near_act, ctr);
+  else VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, near_act, ctr);
+  VDBM_LAUNCH(merge_near_kernel, (kNearBricks * kBrickLeaves * 8) / 256, 256, s, g, near_act, nearBrick0(a.origin_idx[0]),
+              nearBrick0(a.origin_idx[1]), nearBrick0(a.origin_idx[2]), ctr);
 }
 
 void launchCompactLeaves(UpdateGrid g, cudaStream_t s)
