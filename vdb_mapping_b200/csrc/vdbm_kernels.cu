@@ -555,8 +555,11 @@ __global__ void __launch_bounds__(256, 4) apply_update_kernel(UpdateGrid g, MapT
     const bool is_new   = (cur.r != kInvalid) && (cur.r & kNewLeafBit);
     float* vp = mt.leaf_vals + size_t(leaf == kInvalid ? 0 : leaf) * 512 + lane * 16;
     float v0[8], v1[8];
-    // issue the 2 KB leaf read first (independent of the mask words), then prefetch the next leaf's small words
-    if (leaf != kInvalid && !is_new) { ld256(vp, v0); ld256(vp + 8, v1); }
+    // The mask words of this leaf were prefetched one iteration ago, so the update bits of my 16 voxels are known
+    // without waiting: issue the leaf read first, and only for the 64-byte pieces that actually get an update
+    // (a piece without update bits is neither read nor written), then prefetch the next leaf's small words.
+    const uint32_t ua = uint32_t(shfl64(cur.A, w) >> sh) & 0xFFFFu; // active update bits of my 16 voxels
+    if (leaf != kInvalid && !is_new && ua != 0) { ld256(vp, v0); ld256(vp + 8, v1); }
     else
     {
 #pragma unroll
@@ -569,7 +572,6 @@ __global__ void __launch_bounds__(256, 4) apply_update_kernel(UpdateGrid g, MapT
       g.act[size_t(cur.e) * 8 + lane] = 0;
       g.val[size_t(cur.e) * 8 + lane] = 0;
     }
-    const uint32_t ua = uint32_t(shfl64(cur.A, w) >> sh) & 0xFFFFu; // active update bits of my 16 voxels
     const uint32_t uv = uint32_t(shfl64(cur.V, w) >> sh) & 0xFFFFu; // hit bits
     const unsigned nz_words  = __ballot_sync(kFull, cur.A != 0) & 0xFFu;
     const unsigned hit_words = __ballot_sync(kFull, cur.V != 0) & 0xFFu;
