@@ -25,6 +25,7 @@ struct vdbm_leafset
   uint64_t* valmask = nullptr;
   float* values     = nullptr;
   bool pinned       = false;
+  vdbm_map* lender  = nullptr; // non-null: the arrays live in the handle's persistent pinned staging buffer
 };
 
 namespace {
@@ -95,6 +96,11 @@ struct vdbm_map
     uint32_t epoch = 0;
     bool created = false, connected = false;
   } ex;
+
+  // persistent pinned staging for large exports (page-locking hundreds of MB per call costs more than the copy)
+  void* h_stage      = nullptr;
+  size_t h_stage_cap = 0;
+  bool h_stage_lent  = false;
 
   vdbm_stats_t stats{};
   Counters base{}; // counters at the last reset, to keep cumulative numbers across device counter resets
@@ -453,10 +459,36 @@ void* hostAlloc(size_t bytes, bool pinned)
   return std::malloc(bytes);
 }
 
-vdbm_leafset* newLeafset(uint64_t n, bool with_valmask, bool with_values)
+vdbm_leafset* newLeafset(vdbm_map* m, uint64_t n, bool with_valmask, bool with_values)
 {
-  auto* ls   = new vdbm_leafset();
-  ls->n      = n;
+  auto* ls = new vdbm_leafset();
+  ls->n    = n;
+  auto up  = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t b_or = up(n * 12), b_ac = up(n * 64), b_vm = with_valmask ? up(n * 64) : 0, b_va = with_values ? up(n * 2048) : 0;
+  const size_t total = b_or + b_ac + b_vm + b_va;
+  if (m && total >= (size_t(8) << 20) && !m->h_stage_lent)
+  {
+    if (m->h_stage_cap < total)
+    {
+      if (m->h_stage) cudaFreeHost(m->h_stage);
+      m->h_stage     = nullptr;
+      m->h_stage_cap = 0;
+      const size_t want = total + total / 2;
+      if (cudaHostAlloc(&m->h_stage, want, cudaHostAllocDefault) == cudaSuccess) m->h_stage_cap = want;
+    }
+    if (m->h_stage_cap >= total)
+    {
+      char* p     = static_cast<char*>(m->h_stage);
+      ls->origins = reinterpret_cast<int32_t*>(p); p += b_or;
+      ls->active  = reinterpret_cast<uint64_t*>(p); p += b_ac;
+      if (with_valmask) { ls->valmask = reinterpret_cast<uint64_t*>(p); p += b_vm; }
+      if (with_values) ls->values = reinterpret_cast<float*>(p);
+      ls->pinned      = true;
+      ls->lender      = m;
+      m->h_stage_lent = true;
+      return ls;
+    }
+  }
   ls->pinned = (n * (with_values ? 2048 : 128)) >= (1u << 20);
   ls->origins = static_cast<int32_t*>(hostAlloc(n * 12, ls->pinned));
   ls->active  = static_cast<uint64_t*>(hostAlloc(n * 64, ls->pinned));
@@ -492,7 +524,7 @@ int sortByKey(vdbm_map* m, uint64_t*& keys, uint32_t*& idx, uint64_t* keys_alt, 
 // export n LeafRecords that live on the device (unsorted) as a sorted bool leaf set
 int recordsToLeafset(vdbm_map* m, const LeafRecord* d_recs, uint32_t n, vdbm_leafset** out)
 {
-  vdbm_leafset* ls = newLeafset(n, true, false);
+  vdbm_leafset* ls = newLeafset(m, n, true, false);
   *out             = ls;
   if (n == 0) return VDBM_OK;
   // D2H the records, sort on the host by key (records are 136 B; change grids / sections are small)
@@ -583,6 +615,7 @@ void vdbm_destroy(vdbm_map* m)
   for (void* p : m->ex.opened) cudaIpcCloseMemHandle(p);
   cudaFree(m->ex.inbox); cudaFree(m->ex.ctrl); cudaFree(m->ex.d_cursors); cudaFree(m->ex.d_counts);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);
+  if (m->h_stage) cudaFreeHost(m->h_stage);
   cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1); cudaEventDestroy(m->ev2);
   if (m->own_stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -784,7 +817,7 @@ int vdbm_update_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   const uint32_t n = s->n_entries;
-  vdbm_leafset* ls = newLeafset(n, true, false);
+  vdbm_leafset* ls = newLeafset(m, n, true, false);
   *out             = ls;
   if (n == 0) return VDBM_OK;
   TempBuf k0(m->stream), k1(m->stream), i0(m->stream), i1(m->stream), recs(m->stream), so(m->stream), sa(m->stream), sv(m->stream);
@@ -879,7 +912,7 @@ int vdbm_map_export(vdbm_map* m, int dirty_only, vdbm_leafset** out)
   }
   else if (n_all)
     CU_TRY(m, cudaMemsetAsync(m->mt.leaf_dirty, 0, size_t(n_all) * 4, m->stream)); // a full export also leaves nothing dirty
-  vdbm_leafset* ls = newLeafset(n, false, true);
+  vdbm_leafset* ls = newLeafset(m, n, false, true);
   *out             = ls;
   if (n)
   {
@@ -917,7 +950,7 @@ int vdbm_section(vdbm_map* m, const int32_t bbmin[3], const int32_t bbmax[3], in
   const uint32_t cap = uint32_t(std::min<uint64_t>(box_leaves, m->n_leaves));
   if (cap == 0)
   {
-    *out = newLeafset(0, !result_float, result_float != 0);
+    *out = newLeafset(m, 0, !result_float, result_float != 0);
     return VDBM_OK;
   }
   TempBuf dk(m->stream), da(m->stream), dv(m->stream), df(m->stream);
@@ -932,7 +965,7 @@ int vdbm_section(vdbm_map* m, const int32_t bbmin[3], const int32_t bbmax[3], in
   rc = syncCounters(m);
   if (rc) return rc;
   const uint32_t n = std::min(m->h_ctr->n_out, cap);
-  vdbm_leafset* ls = newLeafset(n, !result_float, result_float != 0);
+  vdbm_leafset* ls = newLeafset(m, n, !result_float, result_float != 0);
   *out             = ls;
   if (n == 0) return VDBM_OK;
   // small result: sort on the host by key
@@ -987,6 +1020,12 @@ const float* vdbm_leafset_values(const vdbm_leafset* s) { return s ? s->values :
 void vdbm_leafset_free(vdbm_leafset* s)
 {
   if (!s) return;
+  if (s->lender)
+  {
+    s->lender->h_stage_lent = false; // arrays belong to the handle's staging buffer
+    delete s;
+    return;
+  }
   auto rel = [&](void* p) {
     if (!p) return;
     if (s->pinned) cudaFreeHost(p);
