@@ -106,6 +106,23 @@ class ClockSampler:
                 "power_w_max": max((r[2] for r in self.rows), default=None), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu capture (profiles/traffic_*.json), or None.
+    bench.py never runs under the profiler; the capture is taken separately with tools/profile_gpu.sh."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        files = sorted(f for f in os.listdir(pdir) if f.startswith("traffic_") and f.endswith(".json"))
+        if not files:
+            return None, None
+        d = json.load(open(os.path.join(pdir, files[-1])))
+        for k, v in d.items():
+            if k.startswith(kernel):
+                return float(v["dram_bytes_per_launch"]), files[-1]
+    except Exception:
+        pass
+    return None, None
+
+
 def workload_cfg(name: str) -> int:
     return {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4}[name]
 
@@ -309,10 +326,14 @@ def run_ours(args, rank, world, local_rank):
     b_alg = alg_bytes(n_pts, int(L))
     t_kernels = t_acc + t_int
     upd_bytes = 4352 * L  # K2 alone: update masks read (128 B) + map leaf values+mask read and written (4224 B)
+    tr_dda, tr_src = measured_traffic("raycast_dda_kernel")
+    tr_upd, _ = measured_traffic("apply_update_kernel")
+    traffic = (tr_dda + tr_upd) if (tr_dda is not None and tr_upd is not None and cfg == 2) else None
     roofline = {
         "bound": "hbm", "kernel": "scan step = prep_rays + raycast_dda + apply_update (SURVEY 8d definition)",
         "achieved": b_alg / (t_kernels * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-        "frac": b_alg / (t_kernels * 1e-3) / 1e9 / peak, "traffic": None,
+        "frac": b_alg / (t_kernels * 1e-3) / 1e9 / peak, "traffic": traffic,
+        "traffic_source": (f"profiles/{tr_src}: dram bytes of raycast_dda_kernel + apply_update_kernel per scan (ncu --set full, cfg2)" if traffic else None),
         "algorithmic_bytes_per_step": b_alg, "touched_leaves_per_step": L, "kernel_ms_per_step": t_kernels,
         "by_kernel": {
             "prep_rays_kernel": {"ms": t_prep, "alg_bytes": 64 * n_pts, "achieved_gbs": 64 * n_pts / (t_prep * 1e-3) / 1e9 if t_prep else None},

@@ -143,6 +143,18 @@ int vdbm_map_export(vdbm_map* map, int dirty_only, vdbm_leafset** out);
  * result_float = 0 -> UpdateGridT result (active + value masks), 1 -> GridT result (active + 512 f32). */
 int vdbm_section(vdbm_map* map, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float,
                  vdbm_leafset** out);
+/* ---- receiver side of remote mapping ---------------------------------------------- */
+/* applyMapSectionUpdateGrid V:1058-1085 (without the optional OpenVDB morphology smoothing): deactivate every active
+ * map voxel inside the inclusive index box [bbmin, bbmax] (the section's bb_min / bb_max metadata, floored), then
+ * activate every active voxel of the section (missing leaves are created with background values). */
+int vdbm_section_apply_update(vdbm_map* map, const int32_t bbmin[3], const int32_t bbmax[3], uint64_t n_leaves,
+                              const int32_t* origins /*[n][3]*/, const uint64_t* active /*[n][8]*/);
+/* applyMapSectionGrid V:1022-1047: every section leaf replaces the map leaf voxel for voxel (value + state).
+ * replicate_tile_quirk != 0 also reproduces the reference's visits of the section tree's inactive background tiles
+ * (cbeginValueAll): map.setValueOff(tile origin, 0) clears one voxel per missing leaf slot / 128^3 slot wherever the
+ * map has a leaf. */
+int vdbm_section_apply_grid(vdbm_map* map, uint64_t n_leaves, const int32_t* origins /*[n][3]*/, const uint64_t* active /*[n][8]*/,
+                            const float* values /*[n][512]*/, int replicate_tile_quirk);
 /* GridT::Accessor::getValue / isValueOn for one voxel (tests/mapping.cpp:27-29). */
 int vdbm_probe(vdbm_map* map, const int32_t xyz[3], float* value, int32_t* active);
 

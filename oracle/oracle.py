@@ -62,6 +62,10 @@ def lib() -> C.CDLL:
         L.vdbo_map_leaf_count.argtypes = [vp]
         L.vdbo_update_import.restype = C.c_int
         L.vdbo_update_import.argtypes = [vp, C.c_char_p, C.c_uint64, i32p, u64p, u64p]
+        L.vdbo_apply_section_update.restype = C.c_int
+        L.vdbo_apply_section_update.argtypes = [vp, i32p, i32p, C.c_uint64, i32p, u64p]
+        L.vdbo_apply_section_grid.restype = C.c_int
+        L.vdbo_apply_section_grid.argtypes = [vp, C.c_uint64, i32p, u64p, f32p, C.c_int]
         L.vdbo_update_clear.restype = C.c_int
         L.vdbo_update_clear.argtypes = [vp, C.c_char_p]
         _lib = L
@@ -194,6 +198,21 @@ class OracleOccupancyVDBMapping:
 
     def mapLeafCount(self) -> int:
         return int(self._L.vdbo_map_leaf_count(self._h))
+
+    def applyMapSectionUpdateGrid(self, bbmin, bbmax, section: "LeafSet"):
+        """VDBMapping.hpp:1058-1085 with the section's bb_min / bb_max metadata passed explicitly."""
+        i32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+        mn = np.ascontiguousarray(bbmin, dtype=np.int32); mx = np.ascontiguousarray(bbmax, dtype=np.int32)
+        o = np.ascontiguousarray(section.origins, dtype=np.int32); a = np.ascontiguousarray(section.active, dtype=np.uint64)
+        self._L.vdbo_apply_section_update(self._h, mn.ctypes.data_as(i32p), mx.ctypes.data_as(i32p), o.shape[0],
+                                          o.ctypes.data_as(i32p), a.ctypes.data_as(u64p))
+
+    def applyMapSectionGrid(self, section: "LeafSet", tile_quirk: bool = True):
+        """VDBMapping.hpp:1022-1047."""
+        i32p, u64p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_float)
+        o = np.ascontiguousarray(section.origins, dtype=np.int32); a = np.ascontiguousarray(section.active, dtype=np.uint64)
+        v = np.ascontiguousarray(section.values, dtype=np.float32)
+        self._L.vdbo_apply_section_grid(self._h, o.shape[0], o.ctypes.data_as(i32p), a.ctypes.data_as(u64p), v.ctypes.data_as(f32p), int(tile_quirk))
 
     def clearUpdateGrid(self, source_id: str) -> int:
         return self._L.vdbo_update_clear(self._h, source_id.encode())

@@ -872,6 +872,148 @@ static LeafSet mapSection(const FloatTree& map, const Coord& mn, const Coord& mx
   return s;
 }
 
+// --------------------------------------------------------------------------------------------
+// Receiver side of remote mapping.
+// applyMapSectionUpdateGrid V:1058-1085 (smoothing = OpenVDB morphology, out of scope): every ACTIVE map voxel inside
+// the inclusive index box [floor(bb_min), floor(bb_max)] is deactivated (value kept), then every active voxel of the
+// section is activated in the map (accessor setActiveState(true): a missing leaf is created with background values).
+// --------------------------------------------------------------------------------------------
+static void applySectionUpdate(FloatTree& map, const Coord& mn, const Coord& mx, size_t n, const int32_t* origins, const uint64_t* active)
+{
+  // step 1: V:1073-1079
+  std::vector<FloatLeaf*> leaves;
+  map.forEachLeaf([&](const FloatLeaf& l) { leaves.push_back(const_cast<FloatLeaf*>(&l)); });
+  for (FloatLeaf* l : leaves)
+  {
+    bool overlap = true;
+    for (int a = 0; a < 3; ++a)
+      if (l->origin[a] + 7 < mn[a] || l->origin[a] > mx[a]) overlap = false;
+    if (!overlap) continue;
+    for (uint32_t k = l->vmask.findNextOn(0); k < 512; k = l->vmask.findNextOn(k + 1))
+    {
+      Coord loc = leafOffsetToLocal(k);
+      if (insideBox(Coord(l->origin[0] + loc[0], l->origin[1] + loc[1], l->origin[2] + loc[2]), mn, mx)) l->vmask.setOff(k);
+    }
+  }
+  // step 2: V:1080-1083
+  Accessor<FloatTree> acc(map);
+  struct TouchOp { void operator()(float&, bool& a) const { a = true; } };
+  for (size_t i = 0; i < n; ++i)
+    for (uint32_t k = 0; k < 512; ++k)
+    {
+      if (!((active[8 * i + (k >> 6)] >> (k & 63)) & 1u)) continue;
+      Coord loc = leafOffsetToLocal(k);
+      Coord c(origins[3 * i] + loc[0], origins[3 * i + 1] + loc[1], origins[3 * i + 2] + loc[2]);
+      // setActiveState(xyz, true) == InternalNode::setActiveStateAndCache: a child is created when the tile state differs
+      // (inactive background tile, on = true), then the leaf bit is set; the value is left alone.
+      FloatLeaf* l = const_cast<FloatLeaf*>(acc.probeLeaf(c));
+      if (!l)
+      {
+        // create the path down to the leaf with background tiles (same node construction as touchLeaf on the bool tree)
+        Coord key = FloatTree::rootKey(c);
+        auto it   = map.table.find(key);
+        FloatI2* b;
+        if (it == map.table.end()) { b = new FloatI2(c, map.background, false); map.table[key] = b; }
+        else b = it->second;
+        uint32_t nb = FloatI2::coordToOffset(c);
+        if (!b->childMask.isOn(nb)) { b->nodes[nb].child = new FloatI1(c, b->nodes[nb].tile, false); b->childMask.setOn(nb); }
+        FloatI1* a1 = b->nodes[nb].child;
+        uint32_t na = FloatI1::coordToOffset(c);
+        if (!a1->childMask.isOn(na)) { a1->nodes[na].child = new FloatLeaf(c, a1->nodes[na].tile, false); a1->childMask.setOn(na); }
+        l = a1->nodes[na].child;
+        acc.insert(c, l);
+      }
+      l->vmask.setOn(leafOffset(c));
+    }
+}
+
+// applyMapSectionGrid V:1022-1047: for (iter = section->cbeginValueAll()): on -> map.setValueOn(coord, v), off ->
+// map.setValueOff(coord, v). cbeginValueAll visits EVERY voxel of every section leaf (so a section leaf overwrites the
+// map leaf completely, also outside the box it was cut from) AND every tile of the section tree's internal nodes: an
+// inactive background tile yields map.setValueOff(tile origin, background), which zeroes + deactivates that one voxel
+// wherever the map already has a leaf (setValueOffAndCache only descends into existing children for a background
+// value). `tile_quirk` = false skips those tile visits.
+static void applySectionGrid(FloatTree& map, size_t n, const int32_t* origins, const uint64_t* active, const float* values, bool tile_quirk)
+{
+  Accessor<FloatTree> acc(map);
+  auto setOffExisting = [&](const Coord& c) {
+    FloatLeaf* l = const_cast<FloatLeaf*>(acc.probeLeaf(c));
+    if (!l) return;
+    const uint32_t k = leafOffset(c);
+    l->buf[k] = 0.0f;
+    l->vmask.setOff(k);
+  };
+  if (tile_quirk && n)
+  {
+    // the section tree as the receiver sees it: exactly the exported leaves
+    FloatTree sec(0.0f);
+    Accessor<FloatTree> sacc(sec);
+    struct Nop { void operator()(float&, bool&) const {} };
+    for (size_t i = 0; i < n; ++i)
+    {
+      Coord c(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+      Coord key = FloatTree::rootKey(c);
+      auto it   = sec.table.find(key);
+      FloatI2* b;
+      if (it == sec.table.end()) { b = new FloatI2(c, 0.0f, false); sec.table[key] = b; }
+      else b = it->second;
+      uint32_t nb = FloatI2::coordToOffset(c);
+      if (!b->childMask.isOn(nb)) { b->nodes[nb].child = new FloatI1(c, 0.0f, false); b->childMask.setOn(nb); }
+      FloatI1* a1 = b->nodes[nb].child;
+      uint32_t na = FloatI1::coordToOffset(c);
+      if (!a1->childMask.isOn(na)) { a1->nodes[na].child = new FloatLeaf(c, 0.0f, false); a1->childMask.setOn(na); }
+    }
+    for (auto& kv : sec.table)
+    {
+      const FloatI2* b = kv.second;
+      for (uint32_t nb = 0; nb < FloatI2::NUM; ++nb)
+      {
+        // offset -> coordinate of the slot's origin (InternalNode::offsetToGlobalCoord)
+        const Coord o2(b->origin[0] + int32_t((nb >> 10) << 7), b->origin[1] + int32_t(((nb >> 5) & 31) << 7), b->origin[2] + int32_t((nb & 31) << 7));
+        if (!b->childMask.isOn(nb)) { setOffExisting(o2); continue; }
+        const FloatI1* a1 = b->nodes[nb].child;
+        for (uint32_t na = 0; na < FloatI1::NUM; ++na)
+        {
+          if (a1->childMask.isOn(na)) continue;
+          setOffExisting(Coord(a1->origin[0] + int32_t((na >> 8) << 3), a1->origin[1] + int32_t(((na >> 4) & 15) << 3), a1->origin[2] + int32_t((na & 15) << 3)));
+        }
+      }
+    }
+  }
+  for (size_t i = 0; i < n; ++i)
+  {
+    const Coord o(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+    FloatLeaf* l = const_cast<FloatLeaf*>(acc.probeLeaf(o));
+    if (!l)
+    {
+      // a leaf is created by the first voxel that is active or differs from the background
+      bool content = false;
+      for (int w = 0; w < 8 && !content; ++w) content = active[8 * i + w] != 0;
+      for (int k = 0; k < 512 && !content; ++k) content = values[512 * i + k] != 0.0f;
+      if (!content) continue;
+      struct Nop { void operator()(float&, bool&) const {} };
+      // create the path (values background, inactive); the loop below then writes every voxel
+      Coord key = FloatTree::rootKey(o);
+      auto it   = map.table.find(key);
+      FloatI2* b;
+      if (it == map.table.end()) { b = new FloatI2(o, map.background, false); map.table[key] = b; }
+      else b = it->second;
+      uint32_t nb = FloatI2::coordToOffset(o);
+      if (!b->childMask.isOn(nb)) { b->nodes[nb].child = new FloatI1(o, b->nodes[nb].tile, false); b->childMask.setOn(nb); }
+      FloatI1* a1 = b->nodes[nb].child;
+      uint32_t na = FloatI1::coordToOffset(o);
+      if (!a1->childMask.isOn(na)) { a1->nodes[na].child = new FloatLeaf(o, a1->nodes[na].tile, false); a1->childMask.setOn(na); }
+      l = a1->nodes[na].child;
+      acc.insert(o, l);
+    }
+    for (uint32_t k = 0; k < 512; ++k)
+    {
+      l->buf[k] = values[512 * i + k];
+      l->vmask.set(k, (active[8 * i + (k >> 6)] >> (k & 63)) & 1u);
+    }
+  }
+}
+
 struct Handle
 {
   OccupancyMapping map;
@@ -1014,6 +1156,19 @@ int vdbo_update_import(void* hh, const char* source, uint64_t n, const int32_t* 
       l->buf.w[w] |= valmask[8 * i + w];
     }
   }
+  return 0;
+}
+
+int vdbo_apply_section_update(void* hh, const int32_t* bbmin, const int32_t* bbmax, uint64_t n, const int32_t* origins, const uint64_t* active)
+{
+  auto& m = static_cast<vo::Handle*>(hh)->map;
+  vo::applySectionUpdate(*m.m_vdb_grid, vo::Coord(bbmin[0], bbmin[1], bbmin[2]), vo::Coord(bbmax[0], bbmax[1], bbmax[2]), n, origins, active);
+  return 0;
+}
+int vdbo_apply_section_grid(void* hh, uint64_t n, const int32_t* origins, const uint64_t* active, const float* values, int tile_quirk)
+{
+  auto& m = static_cast<vo::Handle*>(hh)->map;
+  vo::applySectionGrid(*m.m_vdb_grid, n, origins, active, values, tile_quirk != 0);
   return 0;
 }
 

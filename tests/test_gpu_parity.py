@@ -261,3 +261,44 @@ def test_full_size_properties_cfg2_sequence():
     assert np.all((a.valmask & ~a.active) == 0)               # every hit voxel is active
     st = g.stats()
     assert st["last_visits"] > 1.4e8 and st["last_touched_leaves"] == len(a)
+
+
+def _sender_receiver(seed_a, seed_b):
+    from vdb_mapping_b200 import scans
+    pairs = []
+    for seed in (seed_a, seed_b):
+        g, o = _pair(0.1, 4.0, CFG_GTEST)
+        for k in range(3):
+            pts, origin = scans.small_scan(seed * 10 + k, n=3000, scale=2.5)
+            g.insertPointCloud(pts, origin, "s"); o.insertPointCloud(pts, origin, "s")
+        pairs.append((g, o))
+    return pairs
+
+
+@pytest.mark.parametrize("box", [((-9, -4, -3), (6, 11, 5)), ((-40, -40, -40), (40, 40, 40)), ((2, 2, 2), (2, 2, 2))])
+def test_apply_map_section_update_grid(box):
+    """Receiver side: applyMapSectionUpdateGrid, VDBMapping.hpp:1058-1085."""
+    (ga, oa), (gb, ob) = _sender_receiver(61, 62)
+    mn, mx = box
+    section = ga.getMapSectionUpdateGrid(mn, mx, False)
+    assert_leafsets_equal(section, oa.getMapSectionUpdateGrid(mn, mx, False), "section")
+    gb.applyMapSectionUpdateGrid(mn, mx, section)
+    ob.applyMapSectionUpdateGrid(mn, mx, section)
+    assert_leafsets_equal(gb.exportMap(), ob.exportMap(), "map after applyMapSectionUpdateGrid")
+    # the touched leaves are reported dirty (host mirror); a later scan still integrates bit-exactly
+    from vdb_mapping_b200 import scans
+    pts, origin = scans.small_scan(999, n=2000, scale=2.0)
+    gb.insertPointCloud(pts, origin, "s"); ob.insertPointCloud(pts, origin, "s")
+    assert_leafsets_equal(gb.exportMap(), ob.exportMap(), "map after a following scan")
+
+
+@pytest.mark.parametrize("quirk", [True, False], ids=["tilequirk", "noquirk"])
+@pytest.mark.parametrize("full", [True, False], ids=["full", "sparse"])
+def test_apply_map_section_grid(full, quirk):
+    """Receiver side: applyMapSectionGrid, VDBMapping.hpp:1022-1047, incl. the value-all tile visits."""
+    (ga, oa), (gb, ob) = _sender_receiver(71, 72)
+    mn, mx = (-12, -7, -6), (9, 14, 8)
+    section = ga.getMapSectionGrid(mn, mx, full)
+    gb.applyMapSectionGrid(section, tile_quirk=quirk)
+    ob.applyMapSectionGrid(section, tile_quirk=quirk)
+    assert_leafsets_equal(gb.exportMap(), ob.exportMap(), "map after applyMapSectionGrid")

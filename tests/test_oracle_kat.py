@@ -173,3 +173,75 @@ def test_zero_and_negative_source_range_inserts_nothing():
     o.addInputSource("n", -1.0, 0)
     o.insertPointCloud(np.array([[0, 0, 0.5]], np.float32), [0, 0, 0], "n")
     assert o.mapLeafCount() == 0
+
+
+def _map_dict(m):
+    return pyref.leafset_to_voxels(m.exportMap())
+
+
+def _two_maps(seed_a, seed_b):
+    """sender map A and receiver map B with different content"""
+    rng = np.random.default_rng(seed_a)
+    maps = []
+    for seed in (seed_a, seed_b):
+        m = OracleOccupancyVDBMapping(0.1)
+        m.setConfig(3.0, 0.9, 0.1, 0.49, 0.51)
+        m.addInputSource("s", 3.0, 0)
+        r = np.random.default_rng(seed)
+        for k in range(3):
+            m.insertPointCloud(_rand_cloud(r, 80, 1.5), [0.05 * k, 0.02 * seed, 0], "s")
+        maps.append(m)
+    return maps
+
+
+def test_apply_section_update_grid_vs_bruteforce():
+    """applyMapSectionUpdateGrid (VDBMapping.hpp:1058-1085): deactivate active voxels in the box, activate the section's."""
+    a, b = _two_maps(1, 2)
+    mn, mx = (-9, -4, -3), (6, 11, 5)
+    inside = lambda v: all(mn[i] <= v[i] <= mx[i] for i in range(3))
+    section = a.getMapSectionUpdateGrid(mn, mx, False)
+    before = _map_dict(b)
+    b.applyMapSectionUpdateGrid(mn, mx, section)
+    want = {}
+    for v, (act, val) in before.items():
+        want[v] = (act and not inside(v), val)
+    for v in pyref.leafset_to_voxels(section):
+        want[v] = (True, want.get(v, (False, np.float32(0)))[1])
+    want = {v: av for v, av in want.items() if av[0] or av[1] != 0}
+    assert _map_dict(b) == want
+
+
+@pytest.mark.parametrize("quirk", [False, True])
+def test_apply_section_grid_vs_bruteforce(quirk):
+    """applyMapSectionGrid (VDBMapping.hpp:1022-1047): section leaves overwrite map leaves completely; with the
+    value-all tile visits every missing leaf slot of the section's internal nodes clears its origin voxel in the map."""
+    a, b = _two_maps(3, 4)
+    mn, mx = (-9, -4, -3), (6, 11, 5)
+    section = a.getMapSectionGrid(mn, mx, True)
+    before = _map_dict(b)
+    leaves_before = {tuple(o) for o in b.exportMap().origins}
+    b.applyMapSectionGrid(section, tile_quirk=quirk)
+    want = dict(before)
+    sec_leaves = {tuple(int(x) for x in o) for o in section.origins}
+    if quirk:
+        i1 = {tuple((c >> 7) << 7 for c in o) for o in sec_leaves}
+        i2 = {tuple((c >> 12) << 12 for c in o) for o in sec_leaves}
+        for blk in i1:  # every leaf slot of an I1 node of the section without a section leaf: its origin voxel
+            for i in range(16):
+                for j in range(16):
+                    for k in range(16):
+                        o = (blk[0] + 8 * i, blk[1] + 8 * j, blk[2] + 8 * k)
+                        if o not in sec_leaves and o in leaves_before:
+                            want.pop(o, None)
+        for blk in i2:  # every I1 slot of an I2 node without child: origin voxel of that 128^3 block
+            for i in range(32):
+                for j in range(32):
+                    for k in range(32):
+                        o = (blk[0] + 128 * i, blk[1] + 128 * j, blk[2] + 128 * k)
+                        if tuple((c >> 7) << 7 for c in o) not in i1 and o in leaves_before:
+                            want.pop(o, None)
+    for o in sec_leaves:  # section leaves replace map leaves voxel for voxel
+        for v in [v for v in want if tuple((c >> 3) << 3 for c in v) == o]:
+            del want[v]
+    want.update(pyref.leafset_to_voxels(section))
+    assert _map_dict(b) == want

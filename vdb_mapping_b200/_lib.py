@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
     sig("vdbm_change_export", C.c_int, vp, cp, pvp)
     sig("vdbm_map_export", C.c_int, vp, C.c_int, pvp)
     sig("vdbm_section", C.c_int, vp, i32p, i32p, C.c_int, C.c_int, pvp)
+    sig("vdbm_section_apply_update", C.c_int, vp, i32p, i32p, u64, i32p, u64p)
+    sig("vdbm_section_apply_grid", C.c_int, vp, u64, i32p, u64p, f32p, C.c_int)
     sig("vdbm_probe", C.c_int, vp, i32p, f32p, i32p)
     sig("vdbm_leafset_size", u64, vp)
     sig("vdbm_leafset_origins", i32p, vp)

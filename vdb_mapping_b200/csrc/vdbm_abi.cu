@@ -137,15 +137,16 @@ int allocUpdateGrid(vdbm_map* m, UpdateGrid& g, uint32_t cap)
 {
   const size_t brick_bytes = size_t(kBrickLeaves) * 64;
   CU_TRY(m, cudaMalloc(&g.bkeys, size_t(cap) * 8));
-  CU_TRY(m, cudaMalloc(&g.act, size_t(cap) * brick_bytes));
-  CU_TRY(m, cudaMalloc(&g.val, size_t(cap) * brick_bytes));
+  // one extra "trash" brick at index cap: where marks go when the hash is full (scan is replayed after growing)
+  CU_TRY(m, cudaMalloc(&g.act, (size_t(cap) + 1) * brick_bytes));
+  CU_TRY(m, cudaMalloc(&g.val, (size_t(cap) + 1) * brick_bytes));
   CU_TRY(m, cudaMalloc(&g.btouched, size_t(cap) * 4));
   CU_TRY(m, cudaMalloc(&g.entries, size_t(cap) * kBrickLeaves * 4));
   CU_TRY(m, cudaMalloc(&g.counters, 8));
   g.cap_mask = cap - 1;
   CU_TRY(m, cudaMemsetAsync(g.bkeys, 0xFF, size_t(cap) * 8, m->stream));
-  CU_TRY(m, cudaMemsetAsync(g.act, 0, size_t(cap) * brick_bytes, m->stream));
-  CU_TRY(m, cudaMemsetAsync(g.val, 0, size_t(cap) * brick_bytes, m->stream));
+  CU_TRY(m, cudaMemsetAsync(g.act, 0, (size_t(cap) + 1) * brick_bytes, m->stream));
+  CU_TRY(m, cudaMemsetAsync(g.val, 0, (size_t(cap) + 1) * brick_bytes, m->stream));
   CU_TRY(m, cudaMemsetAsync(g.counters, 0, 8, m->stream));
   return VDBM_OK;
 }
@@ -997,6 +998,98 @@ int vdbm_section(vdbm_map* m, const int32_t bbmin[3], const int32_t bbmax[3], in
     else std::memcpy(ls->valmask + size_t(i) * 8, vm.data() + size_t(j) * 8, 64);
   }
   return VDBM_OK;
+}
+
+namespace {
+// leaf keys of host leaf origins (validated); sorted-unique parent block keys at a coarser alignment
+int originsToKeys(vdbm_map* m, uint64_t n, const int32_t* origins, std::vector<uint64_t>& keys)
+{
+  keys.resize(n);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    for (int k = 0; k < 3; ++k)
+      if (std::abs(int64_t(origins[3 * i + k])) >= kVoxelLimit) return fail(m, VDBM_ERR_COORD_RANGE, "leaf origin outside the +-2^23 voxel range");
+    keys[i] = packLeafKey(origins[3 * i] >> 3, origins[3 * i + 1] >> 3, origins[3 * i + 2] >> 3);
+  }
+  return VDBM_OK;
+}
+std::vector<uint64_t> parentBlocks(uint64_t n, const int32_t* origins, int log2dim)
+{
+  std::vector<uint64_t> b(n);
+  for (uint64_t i = 0; i < n; ++i)
+    b[i] = packLeafKey(((origins[3 * i] >> log2dim) << log2dim) >> 3, ((origins[3 * i + 1] >> log2dim) << log2dim) >> 3,
+                       ((origins[3 * i + 2] >> log2dim) << log2dim) >> 3);
+  std::sort(b.begin(), b.end());
+  b.erase(std::unique(b.begin(), b.end()), b.end());
+  return b;
+}
+} // namespace
+
+int vdbm_section_apply_update(vdbm_map* m, const int32_t bbmin[3], const int32_t bbmax[3], uint64_t n, const int32_t* origins,
+                              const uint64_t* active)
+{
+  if (!m || !bbmin || !bbmax || (n && (!origins || !active))) return VDBM_ERR_INVALID_ARG;
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  launchSectionDeactivate(m->mt, m->n_leaves, bbmin, bbmax, m->stream);
+  if (n)
+  {
+    std::vector<uint64_t> keys;
+    rc = originsToKeys(m, n, origins, keys);
+    if (rc) return rc;
+    rc = ensureMapCapacity(m, n);
+    if (rc) return rc;
+    TempBuf dk(m->stream), da(m->stream);
+    CU_TRY(m, dk.alloc(n * 8));
+    CU_TRY(m, da.alloc(n * 64));
+    CU_TRY(m, cudaMemcpyAsync(dk.p, keys.data(), n * 8, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(da.p, active, n * 64, cudaMemcpyHostToDevice, m->stream));
+    launchSectionActivate(m->mt, dk.as<uint64_t>(), da.as<uint64_t>(), uint32_t(n), m->d_ctr, m->stream);
+    CU_TRY(m, cudaGetLastError());
+    rc = syncCounters(m); // the staged host vectors must outlive the copies
+    if (rc) return rc;
+  }
+  return syncCounters(m);
+}
+
+int vdbm_section_apply_grid(vdbm_map* m, uint64_t n, const int32_t* origins, const uint64_t* active, const float* values, int tile_quirk)
+{
+  if (!m || (n && (!origins || !active || !values))) return VDBM_ERR_INVALID_ARG;
+  if (n == 0) return VDBM_OK;
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  std::vector<uint64_t> keys;
+  rc = originsToKeys(m, n, origins, keys);
+  if (rc) return rc;
+  rc = ensureMapCapacity(m, n);
+  if (rc) return rc;
+  TempBuf dk(m->stream), da(m->stream), dv(m->stream), db0(m->stream), db1(m->stream), ds(m->stream);
+  CU_TRY(m, dk.alloc(n * 8));
+  CU_TRY(m, da.alloc(n * 64));
+  CU_TRY(m, dv.alloc(n * 2048));
+  CU_TRY(m, cudaMemcpyAsync(dk.p, keys.data(), n * 8, cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(da.p, active, n * 64, cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(dv.p, values, n * 2048, cudaMemcpyHostToDevice, m->stream));
+  std::vector<uint64_t> sorted_keys, i1, i2;
+  if (tile_quirk)
+  {
+    // tiles first (they only touch voxels outside the section leaves, so the order does not matter)
+    sorted_keys = keys;
+    std::sort(sorted_keys.begin(), sorted_keys.end());
+    i1 = parentBlocks(n, origins, 7);   // 128^3 blocks = Internal<4> nodes of the section tree
+    i2 = parentBlocks(n, origins, 12);  // 4096^3 blocks = Internal<5> nodes
+    CU_TRY(m, ds.alloc(sorted_keys.size() * 8));
+    CU_TRY(m, db0.alloc(i1.size() * 8));
+    CU_TRY(m, db1.alloc(i2.size() * 8));
+    CU_TRY(m, cudaMemcpyAsync(ds.p, sorted_keys.data(), sorted_keys.size() * 8, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(db0.p, i1.data(), i1.size() * 8, cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaMemcpyAsync(db1.p, i2.data(), i2.size() * 8, cudaMemcpyHostToDevice, m->stream));
+    launchSectionTileQuirk(m->mt, db0.as<uint64_t>(), uint32_t(i1.size()), 0, ds.as<uint64_t>(), uint32_t(sorted_keys.size()), m->stream);
+    launchSectionTileQuirk(m->mt, db1.as<uint64_t>(), uint32_t(i2.size()), 1, db0.as<uint64_t>(), uint32_t(i1.size()), m->stream);
+  }
+  launchSectionApplyGrid(m->mt, dk.as<uint64_t>(), da.as<uint64_t>(), dv.as<float>(), uint32_t(n), m->d_ctr, m->stream);
+  CU_TRY(m, cudaGetLastError());
+  return syncCounters(m);
 }
 
 int vdbm_probe(vdbm_map* m, const int32_t xyz[3], float* value, int32_t* active)

@@ -211,6 +211,11 @@ void launchPartition(UpdateGrid ug, uint32_t n_entries, int32_t n_ranks, uint32_
                      LeafRecord* out, int pass, cudaStream_t s);
 void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, uint64_t* out_keys, uint32_t* out_idx, cudaStream_t s);
 void launchSplitRecords(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s);
+// receiver side of remote mapping (applyMapSection*)
+void launchSectionDeactivate(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], cudaStream_t s);
+void launchSectionActivate(MapTable mt, const uint64_t* keys, const uint64_t* active, uint32_t n, Counters* ctr, cudaStream_t s);
+void launchSectionApplyGrid(MapTable mt, const uint64_t* keys, const uint64_t* active, const float* values, uint32_t n, Counters* ctr, cudaStream_t s);
+void launchSectionTileQuirk(MapTable mt, const uint64_t* blocks, uint32_t n_blocks, int level, const uint64_t* present, uint32_t n_present, cudaStream_t s);
 // fused bin + send over peer memory; cursors = device scratch [kMaxRanks] (zeroed by the wrapper)
 void launchPushUpdate(UpdateGrid ug, uint32_t n_entries, ExchangePeers px, uint32_t parity, uint32_t epoch, uint32_t* cursors,
                       Counters* ctr, cudaStream_t s);

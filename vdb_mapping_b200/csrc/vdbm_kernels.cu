@@ -85,6 +85,15 @@ __device__ __forceinline__ uint32_t brickFindOrInsert(const UpdateGrid& g, uint6
   return kInvalid;
 }
 
+// Same, but a full table yields the TRASH brick (slot == capacity; the mask arrays hold capacity + 1 bricks): marks
+// go somewhere harmless, the overflow flag makes the host grow the table and replay the scan. Lets the DDA kernel
+// mark without validity checks.
+__device__ __forceinline__ uint32_t brickFindOrInsertOrTrash(const UpdateGrid& g, uint64_t bkey, Counters* ctr)
+{
+  const uint32_t s = brickFindOrInsert(g, bkey, ctr);
+  return s == kInvalid ? g.cap_mask + 1u : s;
+}
+
 // word offset (in uint64 units) of voxel (x,y,z)'s mask word inside its brick: leaf_in_brick * 8 + (x & 7)
 __device__ __forceinline__ uint32_t brickWordOffset(int x, int y, int z)
 {
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
   const int nbx = nearBrick0(ox), nby = nearBrick0(oy), nbz = nearBrick0(oz);
   // resolve the real slots of the 8 near bricks once per CTA (endpoint hits and the merge kernel use them)
   if (threadIdx.x < kNearBricks)
-    s_near_slot[threadIdx.x] = brickFindOrInsert(g, packLeafKey(nbx + (threadIdx.x >> 2), nby + ((threadIdx.x >> 1) & 1), nbz + (threadIdx.x & 1)), ctr);
+    s_near_slot[threadIdx.x] = brickFindOrInsertOrTrash(g, packLeafKey(nbx + (threadIdx.x >> 2), nby + ((threadIdx.x >> 1) & 1), nbz + (threadIdx.x & 1)), ctr);
   __syncthreads();
   uint64_t* const my_near = near_act + size_t(blockIdx.x % kNearCopies) * (kNearBricks * kBrickLeaves * 8);
   const int origin_ni     = (((ox >> 6) - nbx) << 2) | (((oy >> 6) - nby) << 1) | ((oz >> 6) - nbz);
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
               if (r.flags & kRayZeroLen)
               {
                 // no DDA (VDBMapping.hpp:559); a non-clipped endpoint is still set on with value true (:533-536)
-                if (!(r.flags & kRayClipped) && origin_slot != kInvalid)
+                if (!(r.flags & kRayClipped))
                 {
                   const size_t w     = size_t(origin_slot) * (kBrickLeaves * 8) + brickWordOffset(ox, oy, oz);
                   const uint64_t bit = uint64_t(1) << (((oy & 7) << 3) | (oz & 7));
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
           }
           else
           {
-            slot     = brickFindOrInsert(g, packLeafKey(bx, by, bz), ctr);
+            slot     = brickFindOrInsertOrTrash(g, packLeafKey(bx, by, bz), ctr);
             act_base = g.act + size_t(slot) * (kBrickLeaves * 8);
           }
           need = false;
@@ -333,6 +342,8 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
     }
 
     // ================= kBatch voxel steps =================
+    // The body is written with predicates instead of nested branches: every lane executes the same instruction
+    // stream, the three possible mask writes are single predicated REDs.
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
     {
@@ -341,49 +352,39 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
         // ---- mark current voxel (setActiveState(dda.voxel(), true), VDBMapping.hpp:563) ----
         const uint32_t off = brickWordOffset(x, y, z);
         const uint64_t bit = uint64_t(1) << (((y & 7) << 3) | (z & 7));
-        if (off != cur_off)
-        {
-          if (acc != 0 && slot != kInvalid) markWord<MODE>(act_base + cur_off, acc);
-          cur_off = off;
-          acc     = 0;
-        }
-        acc |= bit;
+        const bool new_run = off != cur_off;
+        if (new_run && acc != 0) markWord<MODE>(act_base + cur_off, acc); // flush the finished run
+        acc     = new_run ? bit : (acc | bit);
+        cur_off = off;
 
-        if (--remaining == 0)
-        {
-          // Last voxel of the ray (= the end voxel). OpenVDB's loop ends when the NEXT crossing time exceeds t1 = 1;
-          // that happens exactly after 1 + |dx|+|dy|+|dz| marks (the crossing times of axis a are (m + 0.5)/|d_a| up to
-          // fp64 rounding, m < |d_a| <=> t < 1 with a margin of 0.5/|d_a| >> accumulated rounding for |d_a| < 2^24).
-          // Flush; the end voxel also receives the hit unless the ray was clipped (VDBMapping.hpp:533-536).
-          if (slot != kInvalid)
-          {
-            markWord<MODE>(act_base + cur_off, acc);
-            if (!clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
-          }
-          busy = false;
-        }
-        else
-        {
-          // ---- DDA::step(): axis = MinIndex(next); next[axis] += delta[axis]; voxel[axis] += step[axis] ----
-          // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
-          //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
-          // Branch-free: three predicated in-place adds per lane, whatever axis it takes.
-          const bool ax = (n0 < n1) && (n0 < n2);
-          const bool ay = !ax && (n1 < n2);
-          const bool az = !ax && !ay;
-          addIf(n0, d0, ax); addIf(n1, d1, ay); addIf(n2, d2, az);
-          addIf(x, sx, ax);  addIf(y, sy, ay);  addIf(z, sz, az);
-          // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
-          const int c  = ax ? x : (ay ? y : z);
-          const int st = ax ? sx : (ay ? sy : sz);
-          if (((c + (st < 0 ? 1 : 0)) & 63) == 0)
-          {
-            if (slot != kInvalid) markWord<MODE>(act_base + cur_off, acc);
-            acc     = 0;
-            cur_off = kInvalid;
-            need    = true;
-          }
-        }
+        // Last voxel of the ray (= the end voxel)? OpenVDB's loop ends when the NEXT crossing time exceeds t1 = 1; that
+        // happens exactly after 1 + |dx|+|dy|+|dz| marks (the crossing times of axis a are (m + 0.5)/|d_a| up to fp64
+        // rounding, m < |d_a| <=> t < 1 with a margin of 0.5/|d_a| >> accumulated rounding for |d_a| < 2^24).
+        const bool last = (--remaining == 0);
+
+        // ---- DDA::step(): axis = MinIndex(next); next[axis] += delta[axis]; voxel[axis] += step[axis] ----
+        // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
+        //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
+        // (executed for the last voxel too; its result is simply never used)
+        const bool ax = (n0 < n1) && (n0 < n2);
+        const bool ay = !ax && (n1 < n2);
+        const bool az = !ax && !ay;
+        addIf(n0, d0, ax); addIf(n1, d1, ay); addIf(n2, d2, az);
+        addIf(x, sx, ax);  addIf(y, sy, ay);  addIf(z, sz, az);
+        // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
+        const int c        = ax ? x : (ay ? y : z);
+        const int st       = ax ? sx : (ay ? sy : sz);
+        const bool crossed = ((c + (st < 0 ? 1 : 0)) & 63) == 0;
+
+        // ray end or brick exit: flush the open run; the end voxel also receives the hit unless the ray was clipped
+        // (VDBMapping.hpp:533-536)
+        const bool close = last || crossed;
+        if (close) markWord<MODE>(act_base + cur_off, acc);
+        if (last && !clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
+        acc     = close ? 0 : acc;
+        cur_off = close ? kInvalid : cur_off;
+        need    = crossed && !last;
+        busy    = !last;
       }
     }
   }
@@ -986,6 +987,186 @@ __global__ void partition_kernel(UpdateGrid g, uint32_t n, int32_t n_ranks, uint
 }
 
 // ====================================================================================================
+// Receiver side of remote mapping: applyMapSectionUpdateGrid / applyMapSectionGrid
+// ====================================================================================================
+// 64-bit in-box mask of mask word w (x = ox + w) of the leaf at (ox, oy, oz) for the inclusive box
+__device__ __forceinline__ uint64_t inBoxWord(int xx, int oy, int oz, int bx0, int by0, int bz0, int bx1, int by1, int bz1)
+{
+  if (xx < bx0 || xx > bx1) return 0;
+  uint64_t zb = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) zb |= uint64_t(oz + k >= bz0 && oz + k <= bz1) << k;
+  uint64_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (oy + j >= by0 && oy + j <= by1) m |= zb << (8 * j);
+  return m;
+}
+
+// VDBMapping.hpp:1073-1079: every active map voxel inside the box is deactivated (values stay). Thread per (leaf, word).
+__global__ void section_deactivate_kernel(MapTable mt, uint32_t n_leaves, int bx0, int by0, int bz0, int bx1, int by1, int bz1)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t l = t >> 3;
+  const int w      = t & 7;
+  if (l >= n_leaves) return;
+  int32_t ox, oy, oz;
+  unpackLeafOrigin(mt.leaf_keys[l], ox, oy, oz);
+  if (ox + 7 < bx0 || ox > bx1 || oy + 7 < by0 || oy > by1 || oz + 7 < bz0 || oz > bz1) return;
+  const uint64_t in  = inBoxWord(ox + w, oy, oz, bx0, by0, bz0, bx1, by1, bz1);
+  const uint64_t old = mt.leaf_mask[size_t(l) * 8 + w];
+  if (old & in)
+  {
+    mt.leaf_mask[size_t(l) * 8 + w] = old & ~in;
+    mt.leaf_dirty[l]                = 1u;
+  }
+}
+
+// find (or create, if `create`) the map leaf of `key`; lane 0 of the warp does the probe. Returns leaf index / kInvalid.
+__device__ __forceinline__ uint32_t warpFindOrCreateLeaf(MapTable& mt, uint64_t key, bool create, int lane, int& is_new, Counters* ctr)
+{
+  uint32_t leaf = kInvalid;
+  is_new        = 0;
+  if (lane == 0)
+  {
+    uint32_t h = uint32_t(mix64(key)) & mt.hcap_mask;
+    for (uint32_t probe = 0; probe <= mt.hcap_mask; ++probe)
+    {
+      const uint64_t k = ldcg64(mt.hkeys + h);
+      if (k == key) { leaf = mt.hvals[h]; break; }
+      if (k == kEmptyKey)
+      {
+        if (!create) break;
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(mt.hkeys + h), kEmptyKey, key);
+        if (old == kEmptyKey)
+        {
+          const uint32_t li = atomicAdd(mt.n_leaves, 1u);
+          if (li >= mt.pool_cap) { atomicOr(&ctr->flags, kFlagMapOverflow); break; }
+          mt.hvals[h]      = li;
+          mt.leaf_keys[li] = key;
+          leaf             = li;
+          is_new           = 1;
+          atomicAdd(&ctr->new_leaves, 1ull);
+          break;
+        }
+      }
+      h = (h + 1) & mt.hcap_mask;
+    }
+  }
+  leaf   = __shfl_sync(kFull, leaf, 0);
+  is_new = __shfl_sync(kFull, is_new, 0);
+  return leaf;
+}
+
+// VDBMapping.hpp:1080-1083: setActiveState(coord, true) for every active section voxel (a missing leaf is created with
+// background values). Warp per section leaf (keys are unique).
+__global__ void __launch_bounds__(256) section_activate_kernel(MapTable mt, const uint64_t* keys, const uint64_t* active, uint32_t n, Counters* ctr)
+{
+  const int lane         = threadIdx.x & 31;
+  const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < n; i += n_warps)
+  {
+    uint64_t a = (lane < 8) ? active[size_t(i) * 8 + lane] : 0;
+    if (!(__ballot_sync(kFull, a != 0) & 0xFFu)) continue;
+    int is_new;
+    const uint32_t leaf = warpFindOrCreateLeaf(mt, keys[i], true, lane, is_new, ctr);
+    if (leaf == kInvalid) continue;
+    if (is_new)
+    {
+      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      st256(mt.leaf_vals + size_t(leaf) * 512 + lane * 16, z);
+      st256(mt.leaf_vals + size_t(leaf) * 512 + lane * 16 + 8, z);
+    }
+    if (lane < 8) mt.leaf_mask[size_t(leaf) * 8 + lane] = (is_new ? 0ull : mt.leaf_mask[size_t(leaf) * 8 + lane]) | a;
+    if (lane == 0) mt.leaf_dirty[leaf] = 1u;
+  }
+}
+
+// VDBMapping.hpp:1034-1045 for the voxels of the section LEAVES: the section leaf replaces the map leaf voxel for voxel
+// (value and state). A missing map leaf is only created when the section leaf holds an active voxel or a non-background value.
+__global__ void __launch_bounds__(256) section_apply_grid_kernel(MapTable mt, const uint64_t* keys, const uint64_t* active, const float* values,
+                                                                uint32_t n, Counters* ctr)
+{
+  const int lane         = threadIdx.x & 31;
+  const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < n; i += n_warps)
+  {
+    float a[8], b[8];
+    ld256(values + size_t(i) * 512 + lane * 16, a);
+    ld256(values + size_t(i) * 512 + lane * 16 + 8, b);
+    const uint64_t m = (lane < 8) ? active[size_t(i) * 8 + lane] : 0;
+    bool content = (m != 0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) content = content || a[q] != 0.0f || b[q] != 0.0f;
+    const bool any_content = __any_sync(kFull, content);
+    int is_new;
+    const uint32_t leaf = warpFindOrCreateLeaf(mt, keys[i], any_content, lane, is_new, ctr);
+    if (leaf == kInvalid) continue;
+    st256(mt.leaf_vals + size_t(leaf) * 512 + lane * 16, a);
+    st256(mt.leaf_vals + size_t(leaf) * 512 + lane * 16 + 8, b);
+    if (lane < 8) mt.leaf_mask[size_t(leaf) * 8 + lane] = m;
+    if (lane == 0) mt.leaf_dirty[leaf] = 1u;
+  }
+}
+
+__device__ __forceinline__ bool sortedContains(const uint64_t* a, uint32_t n, uint64_t key)
+{
+  uint32_t lo = 0, hi = n;
+  while (lo < hi)
+  {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint64_t v   = a[mid];
+    if (v == key) return true;
+    if (v < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void clearVoxel0IfLeafExists(MapTable& mt, uint64_t key)
+{
+  uint32_t h = uint32_t(mix64(key)) & mt.hcap_mask;
+  for (uint32_t probe = 0; probe <= mt.hcap_mask; ++probe)
+  {
+    const uint64_t k = mt.hkeys[h];
+    if (k == kEmptyKey) return;
+    if (k == key)
+    {
+      const uint32_t l = mt.hvals[h];
+      mt.leaf_vals[size_t(l) * 512] = 0.0f;                // setValueOff(tile origin, background): value 0 ...
+      atomicAnd(reinterpret_cast<unsigned long long*>(mt.leaf_mask + size_t(l) * 8), ~1ull); // ... and inactive
+      mt.leaf_dirty[l] = 1u;
+      return;
+    }
+    h = (h + 1) & mt.hcap_mask;
+  }
+}
+
+// The value-all iteration of the reference also visits the inactive background TILES of the section tree's internal
+// nodes (VDBMapping.hpp:1034 cbeginValueAll): map.setValueOff(tile origin, 0) clears that one voxel wherever the map
+// has a leaf. level 0: the 16^3 leaf slots of every 128^3 block (I1 node) that holds a section leaf;
+// level 1: the 32^3 I1 slots of every 4096^3 block (I2 node). `blocks` = sorted unique block keys (leaf-key format).
+__global__ void section_tile_quirk_kernel(MapTable mt, const uint64_t* blocks, uint32_t n_blocks, int level, const uint64_t* present,
+                                          uint32_t n_present)
+{
+  const uint32_t per   = level == 0 ? 4096u : 32768u;
+  const uint64_t t     = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= uint64_t(n_blocks) * per) return;
+  const uint32_t bi = uint32_t(t / per), slot = uint32_t(t % per);
+  int32_t ox, oy, oz;
+  unpackLeafOrigin(blocks[bi], ox, oy, oz);
+  int32_t x, y, z;
+  if (level == 0) { x = ox + int32_t(slot >> 8) * 8; y = oy + int32_t((slot >> 4) & 15) * 8; z = oz + int32_t(slot & 15) * 8; }
+  else            { x = ox + int32_t(slot >> 10) * 128; y = oy + int32_t((slot >> 5) & 31) * 128; z = oz + int32_t(slot & 31) * 128; }
+  const uint64_t key = packLeafKey(x >> 3, y >> 3, z >> 3);
+  // level 0: slots holding a section leaf are not tiles; level 1: slots holding an I1 node are not tiles
+  if (sortedContains(present, n_present, key)) return;
+  clearVoxel0IfLeafExists(mt, key);
+}
+
+// ====================================================================================================
 // Multi-GPU: fused bin-and-send over peer memory (NVLink). A block takes 256 touched update leaves:
 //   A  every thread finds the owner rank of its leaf and reserves a slot in a per-block, per-owner histogram (smem)
 //   B  one global atomicAdd per (block, owner) reserves the block's range in that owner's sender region
@@ -1242,6 +1423,25 @@ void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, ui
 void launchSplitRecords(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s)
 {
   if (n) VDBM_LAUNCH(split_records_kernel, blocksFor(uint64_t(n) * 16, 256), 256, s, recs, n, origins, active, value);
+}
+
+void launchSectionDeactivate(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], cudaStream_t s)
+{
+  if (n_leaves) VDBM_LAUNCH(section_deactivate_kernel, blocksFor(uint64_t(n_leaves) * 8, 256), 256, s, mt, n_leaves, bbmin[0], bbmin[1], bbmin[2], bbmax[0], bbmax[1], bbmax[2]);
+}
+void launchSectionActivate(MapTable mt, const uint64_t* keys, const uint64_t* active, uint32_t n, Counters* ctr, cudaStream_t s)
+{
+  if (n) VDBM_LAUNCH(section_activate_kernel, std::min<unsigned>(blocksFor(uint64_t(n) * 32, 256), unsigned(smCount()) * 8u), 256, s, mt, keys, active, n, ctr);
+}
+void launchSectionApplyGrid(MapTable mt, const uint64_t* keys, const uint64_t* active, const float* values, uint32_t n, Counters* ctr, cudaStream_t s)
+{
+  if (n) VDBM_LAUNCH(section_apply_grid_kernel, std::min<unsigned>(blocksFor(uint64_t(n) * 32, 256), unsigned(smCount()) * 8u), 256, s, mt, keys, active, values, n, ctr);
+}
+void launchSectionTileQuirk(MapTable mt, const uint64_t* blocks, uint32_t n_blocks, int level, const uint64_t* present, uint32_t n_present, cudaStream_t s)
+{
+  if (!n_blocks) return;
+  const uint64_t threads = uint64_t(n_blocks) * (level == 0 ? 4096u : 32768u);
+  VDBM_LAUNCH(section_tile_quirk_kernel, blocksFor(threads, 256), 256, s, mt, blocks, n_blocks, level, present, n_present);
 }
 
 void launchPushUpdate(UpdateGrid g, uint32_t n_entries, ExchangePeers px, uint32_t parity, uint32_t epoch, uint32_t* cursors, Counters* ctr,

@@ -210,6 +210,25 @@ class OccupancyVDBMapping:
     def getMapSectionGrid(self, bbmin, bbmax, full=False) -> LeafSet:
         return self._section(bbmin, bbmax, full, 1)
 
+    def applyMapSectionUpdateGrid(self, bbmin, bbmax, section: LeafSet):
+        """VDBMapping.hpp:1058-1085 (bb_min / bb_max = the section grid's metadata)."""
+        i32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+        mn = np.ascontiguousarray(bbmin, dtype=np.int32)
+        mx = np.ascontiguousarray(bbmax, dtype=np.int32)
+        o = np.ascontiguousarray(section.origins, dtype=np.int32)
+        a = np.ascontiguousarray(section.active, dtype=np.uint64)
+        self._check(self._L.vdbm_section_apply_update(self._h, mn.ctypes.data_as(i32p), mx.ctypes.data_as(i32p), o.shape[0],
+                                                      o.ctypes.data_as(i32p), a.ctypes.data_as(u64p)))
+
+    def applyMapSectionGrid(self, section: LeafSet, tile_quirk: bool = True):
+        """VDBMapping.hpp:1022-1047."""
+        i32p, u64p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_float)
+        o = np.ascontiguousarray(section.origins, dtype=np.int32)
+        a = np.ascontiguousarray(section.active, dtype=np.uint64)
+        v = np.ascontiguousarray(section.values, dtype=np.float32)
+        self._check(self._L.vdbm_section_apply_grid(self._h, o.shape[0], o.ctypes.data_as(i32p), a.ctypes.data_as(u64p),
+                                                    v.ctypes.data_as(f32p), int(tile_quirk)))
+
     def probe(self, coord):
         c = np.ascontiguousarray(coord, dtype=np.int32)
         v, a = C.c_float(0), C.c_int32(0)
