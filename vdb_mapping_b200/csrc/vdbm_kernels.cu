@@ -342,8 +342,6 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
     }
 
     // ================= kBatch voxel steps =================
-    // The body is written with predicates instead of nested branches: every lane executes the same instruction
-    // stream, the three possible mask writes are single predicated REDs.
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
     {
@@ -352,39 +350,46 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
         // ---- mark current voxel (setActiveState(dda.voxel(), true), VDBMapping.hpp:563) ----
         const uint32_t off = brickWordOffset(x, y, z);
         const uint64_t bit = uint64_t(1) << (((y & 7) << 3) | (z & 7));
-        const bool new_run = off != cur_off;
-        if (new_run && acc != 0) markWord<MODE>(act_base + cur_off, acc); // flush the finished run
-        acc     = new_run ? bit : (acc | bit);
-        cur_off = off;
+        if (off != cur_off)
+        {
+          if (acc != 0) markWord<MODE>(act_base + cur_off, acc);
+          cur_off = off;
+          acc     = 0;
+        }
+        acc |= bit;
 
-        // Last voxel of the ray (= the end voxel)? OpenVDB's loop ends when the NEXT crossing time exceeds t1 = 1; that
-        // happens exactly after 1 + |dx|+|dy|+|dz| marks (the crossing times of axis a are (m + 0.5)/|d_a| up to fp64
-        // rounding, m < |d_a| <=> t < 1 with a margin of 0.5/|d_a| >> accumulated rounding for |d_a| < 2^24).
-        const bool last = (--remaining == 0);
-
-        // ---- DDA::step(): axis = MinIndex(next); next[axis] += delta[axis]; voxel[axis] += step[axis] ----
-        // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
-        //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
-        // (executed for the last voxel too; its result is simply never used)
-        const bool ax = (n0 < n1) && (n0 < n2);
-        const bool ay = !ax && (n1 < n2);
-        const bool az = !ax && !ay;
-        addIf(n0, d0, ax); addIf(n1, d1, ay); addIf(n2, d2, az);
-        addIf(x, sx, ax);  addIf(y, sy, ay);  addIf(z, sz, az);
-        // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
-        const int c        = ax ? x : (ay ? y : z);
-        const int st       = ax ? sx : (ay ? sy : sz);
-        const bool crossed = ((c + (st < 0 ? 1 : 0)) & 63) == 0;
-
-        // ray end or brick exit: flush the open run; the end voxel also receives the hit unless the ray was clipped
-        // (VDBMapping.hpp:533-536)
-        const bool close = last || crossed;
-        if (close) markWord<MODE>(act_base + cur_off, acc);
-        if (last && !clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
-        acc     = close ? 0 : acc;
-        cur_off = close ? kInvalid : cur_off;
-        need    = crossed && !last;
-        busy    = !last;
+        if (--remaining == 0)
+        {
+          // Last voxel of the ray (= the end voxel). OpenVDB's loop ends when the NEXT crossing time exceeds t1 = 1;
+          // that happens exactly after 1 + |dx|+|dy|+|dz| marks (the crossing times of axis a are (m + 0.5)/|d_a| up to
+          // fp64 rounding, m < |d_a| <=> t < 1 with a margin of 0.5/|d_a| >> accumulated rounding for |d_a| < 2^24).
+          // Flush; the end voxel also receives the hit unless the ray was clipped (VDBMapping.hpp:533-536).
+          markWord<MODE>(act_base + cur_off, acc);
+          if (!clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
+          busy = false;
+        }
+        else
+        {
+          // ---- DDA::step(): axis = MinIndex(next); next[axis] += delta[axis]; voxel[axis] += step[axis] ----
+          // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
+          //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
+          // Branch-free: three predicated in-place adds per lane, whatever axis it takes.
+          const bool ax = (n0 < n1) && (n0 < n2);
+          const bool ay = !ax && (n1 < n2);
+          const bool az = !ax && !ay;
+          addIf(n0, d0, ax); addIf(n1, d1, ay); addIf(n2, d2, az);
+          addIf(x, sx, ax);  addIf(y, sy, ay);  addIf(z, sz, az);
+          // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
+          const int c  = ax ? x : (ay ? y : z);
+          const int st = ax ? sx : (ay ? sy : sz);
+          if (((c + (st < 0 ? 1 : 0)) & 63) == 0)
+          {
+            markWord<MODE>(act_base + cur_off, acc);
+            acc     = 0;
+            cur_off = kInvalid;
+            need    = true;
+          }
+        }
       }
     }
   }
