@@ -16,8 +16,8 @@
 //     (raycastPointCloud's accessor, updateMap's argument and result, getMapSection*).
 //
 // Scope: insertPointCloud, accumulateUpdate, addDataToAccumulate, integrateUpdate,
-// raycastPointCloud, updateMap, getGrid, getMapSection*, createIndexBoundingBox, addInputSource, setConfig,
-// resetMap, getMapMutex, worldToIndex. Persistence, morphology, artificial areas, raytrace and fast_mode are out
+// raycastPointCloud, updateMap, getGrid, getMapSection*, applyMapSection*, createIndexBoundingBox, addInputSource,
+// setConfig, resetMap, getMapMutex, worldToIndex. Persistence, morphology, artificial areas, raytrace and fast_mode are out
 // of scope of this build and are not declared (a translation unit that needs them keeps using the reference).
 // The device arithmetic implements the OccupancyVDBMapping node operations (TData = float); the protected virtual
 // update*Node hooks of the reference cannot be honoured on the device and are therefore not part of this class.
@@ -357,6 +357,49 @@ public:
     }
     BackendT::setSectionMeta(*out, mn, mx);
     return out;
+  }
+
+  /*! R:1022-1047. The optional morphological smoothing (OpenVDB tools::dilate/erodeActiveValues, R:1094-1147) is not
+   *  part of this build: smooth_map = true is reported and ignored. */
+  void applyMapSectionGrid(const typename GridT::Ptr section, bool smooth_map = false, int smoothing_iterations = 2)
+  {
+    (void)smoothing_iterations;
+    if (smooth_map) std::cerr << "vdb_mapping (B200): morphological smoothing is not supported; section applied unsmoothed" << std::endl;
+    if (!m_device_map || !section) return;
+    std::vector<std::int32_t> origins;
+    std::vector<std::uint64_t> active;
+    std::vector<float> values;
+    BackendT::forEachMapLeaf(*section, [&](const std::int32_t o[3], const float* v, const std::uint64_t* a) {
+      origins.insert(origins.end(), o, o + 3);
+      values.insert(values.end(), v, v + 512);
+      active.insert(active.end(), a, a + 8);
+    });
+    std::unique_lock map_lock(*m_map_mutex);
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_section_apply_grid(m_device_map, origins.size() / 3, origins.data(), active.data(), values.data(), 1));
+    if (m_mirror_mode == MirrorMode::Eager) syncMirrorLocked();
+    else m_mirror_stale = true;
+  }
+
+  /*! R:1058-1085 (same remark on smoothing). The box comes from the section's bb_min / bb_max metadata. */
+  void applyMapSectionUpdateGrid(const typename UpdateGridT::Ptr section, bool smooth_map = false, int smoothing_iterations = 2)
+  {
+    (void)smoothing_iterations;
+    if (smooth_map) std::cerr << "vdb_mapping (B200): morphological smoothing is not supported; section applied unsmoothed" << std::endl;
+    if (!m_device_map || !section) return;
+    std::int32_t mn[3], mx[3];
+    BackendT::getSectionMeta(*section, mn, mx);
+    std::vector<std::int32_t> origins;
+    std::vector<std::uint64_t> active;
+    BackendT::forEachUpdateLeaf(*section, [&](const std::int32_t o[3], const std::uint64_t* a, const std::uint64_t*) {
+      origins.insert(origins.end(), o, o + 3);
+      active.insert(active.end(), a, a + 8);
+    });
+    std::unique_lock map_lock(*m_map_mutex);
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_section_apply_update(m_device_map, mn, mx, origins.size() / 3, origins.data(), active.data()));
+    if (m_mirror_mode == MirrorMode::Eager) syncMirrorLocked();
+    else m_mirror_stale = true;
   }
 
   /*! R:1343 */

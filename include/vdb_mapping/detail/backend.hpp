@@ -87,6 +87,26 @@ struct Backend
       f(origin, active, value);
     }
   }
+  // enumerate the leaves of a float grid: f(origin[3], values[512], active[8])
+  template <typename F>
+  static void forEachMapLeaf(const GridT& grid, F&& f)
+  {
+    for (auto it = grid.tree().cbeginLeaf(); it; ++it)
+    {
+      const openvdb::Coord o = it->origin();
+      std::int32_t origin[3] = {o.x(), o.y(), o.z()};
+      std::uint64_t active[8];
+      for (int w = 0; w < 8; ++w) active[w] = it->getValueMask().template getWord<openvdb::Index64>(w);
+      f(origin, it->buffer().data(), active);
+    }
+  }
+  template <typename G>
+  static void getSectionMeta(const G& g, std::int32_t mn[3], std::int32_t mx[3])
+  {
+    const openvdb::Coord a = openvdb::Coord::floor(g.template metaValue<openvdb::Vec3d>("bb_min"));
+    const openvdb::Coord b = openvdb::Coord::floor(g.template metaValue<openvdb::Vec3d>("bb_max"));
+    for (int k = 0; k < 3; ++k) { mn[k] = a[k]; mx[k] = b[k]; }
+  }
   static void setSectionMeta(UpdateGridT& g, const std::int32_t mn[3], const std::int32_t mx[3])
   {
     g.insertMeta("bb_min", openvdb::Vec3DMetadata(openvdb::Vec3d(mn[0], mn[1], mn[2])));
@@ -158,6 +178,21 @@ struct Backend
       std::int32_t origin[3] = {kv.first[0], kv.first[1], kv.first[2]};
       f(origin, kv.second.active, kv.second.valmask);
     }
+  }
+  template <typename F>
+  static void forEachMapLeaf(const GridT& grid, F&& f)
+  {
+    for (auto& kv : grid.leaves())
+    {
+      std::int32_t origin[3] = {kv.first[0], kv.first[1], kv.first[2]};
+      f(origin, kv.second.values, kv.second.active);
+    }
+  }
+  template <typename G>
+  static void getSectionMeta(const G& g, std::int32_t mn[3], std::int32_t mx[3])
+  {
+    const openvdb::Coord a = openvdb::Coord::floor(g.metaValue("bb_min")), b = openvdb::Coord::floor(g.metaValue("bb_max"));
+    for (int k = 0; k < 3; ++k) { mn[k] = a[k]; mx[k] = b[k]; }
   }
   template <typename G>
   static void setSectionMeta(G& g, const std::int32_t mn[3], const std::int32_t mx[3])

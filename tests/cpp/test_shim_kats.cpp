@@ -126,6 +126,45 @@ TEST(Shim, RaycastIntoAccessorThenUpdateMapReturnsChangeGrid)
   EXPECT_TRUE(section->getAccessor().isValueOn(openvdb::Coord(3, 0, 0)));
 }
 
+TEST(Shim, SectionsTravelFromOneMapToAnother)
+{
+  // remote mapping round trip: sender map -> getMapSection*Grid -> receiver applyMapSection*Grid
+  const Config conf = gtestConfig(10);
+  OccupancyVDBMapping sender(0.1), receiver(0.1);
+  for (OccupancyVDBMapping* m : {&sender, &receiver})
+  {
+    m->setConfig(conf);
+    m->addInputSource("test", conf.max_range, 0);
+  }
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0.45f, 0.0f, 0.0f);
+  cloud->points.emplace_back(0.0f, 0.35f, 0.1f);
+  Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  sender.insertPointCloud(cloud, origin, "test");
+  Eigen::Matrix<double, 3, 1> mn(-1, -1, -1), mx(1, 1, 1);
+  const auto I4 = Eigen::Matrix<double, 4, 4>::Identity();
+  auto full     = sender.getMapSectionGrid(mn, mx, I4, true);
+  receiver.applyMapSectionGrid(full);
+  OccupancyVDBMapping::GridT::Accessor racc = receiver.getGrid()->getAccessor();
+  EXPECT_EQ(racc.getValue(openvdb::Coord(4, 0, 0)), logOdds(0.9));
+  EXPECT_TRUE(racc.isValueOn(openvdb::Coord(4, 0, 0)));
+  EXPECT_EQ(racc.getValue(openvdb::Coord(2, 0, 0)), logOdds(0.1));
+  // update-grid section: receiver gets exactly the sender's active voxels inside the box
+  OccupancyVDBMapping third(0.1);
+  third.setConfig(conf);
+  third.addInputSource("test", conf.max_range, 0);
+  OccupancyVDBMapping::PointCloudT::Ptr other(new OccupancyVDBMapping::PointCloudT);
+  other->points.emplace_back(-0.25f, 0.0f, 0.0f);
+  third.insertPointCloud(other, origin, "test");            // active voxel (-2,0,0) inside the box -> must be deactivated
+  auto sparse = sender.getMapSectionUpdateGrid(mn, mx, I4, false);
+  third.applyMapSectionUpdateGrid(sparse);
+  OccupancyVDBMapping::GridT::Accessor tacc = third.getGrid()->getAccessor();
+  EXPECT_FALSE(tacc.isValueOn(openvdb::Coord(-2, 0, 0)));
+  EXPECT_EQ(tacc.getValue(openvdb::Coord(-2, 0, 0)), logOdds(0.9)); // value kept, only the flag changes
+  EXPECT_TRUE(tacc.isValueOn(openvdb::Coord(4, 0, 0)));
+  EXPECT_EQ(tacc.getValue(openvdb::Coord(4, 0, 0)), 0.0f);          // activated with the background value
+}
+
 TEST(Shim, LazyMirrorSyncsOnGetGrid)
 {
   OccupancyVDBMapping map(0.1);
