@@ -222,12 +222,13 @@ def run_ours(args, rank, world, local_rank):
     for k in range(n_steps):
         if strong:
             pts, origin = scans.make_scan(cfg, k)
-            lo, hi = vdist.split_points(pts.shape[0], rank, world)
-            pts = np.ascontiguousarray(pts[lo:hi])
+            # azimuth sectors with equal voxel visits: a rank then touches ~1/N of the leaves, not all of them
+            pts = np.ascontiguousarray(pts[vdist.sector_split(pts, origin, c.resolution, c.max_range, rank, world)])
         else:
             pts, origin = scans.make_scan(cfg, k, sensor=rank) if cfg == 2 else scans.make_scan(cfg, k + 1000 * rank)
         clouds.append((pts, origin))
     n_pts = clouds[0][0].shape[0]
+    n_pts_k = [p.shape[0] for p, _ in clouds]
     pinned = [torch.from_numpy(p).pin_memory() for p, _ in clouds]
     resident = [t.to(dev, non_blocking=True) for t in pinned]
     torch.cuda.synchronize()
@@ -250,7 +251,7 @@ def run_ours(args, rank, world, local_rank):
             eng = vdist.CudaEngine(m, "s")
             p2p = world > 1 and args.exchange == "p2p"
             if p2p:
-                vdist.connect_peers(m, dist, capacity_records_per_sender=1 << 19)
+                vdist.connect_peers(m, dist, capacity_records_per_sender=(1 << 22) if cfg == 4 else (1 << 19))
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             acc_ms, prep_ms, int_ms, leaves = [], [], [], []
             sent = recv = 0
@@ -266,9 +267,9 @@ def run_ours(args, rank, world, local_rank):
                     ev0.record(stream)
                 origin = clouds[k][1]
                 if e2e:
-                    eng.accumulate_raw(pinned[k].data_ptr(), n_pts, origin, on_device=False)
+                    eng.accumulate_raw(pinned[k].data_ptr(), n_pts_k[k], origin, on_device=False)
                 else:
-                    eng.accumulate_raw(resident[k].data_ptr(), n_pts, origin, on_device=True)
+                    eng.accumulate_raw(resident[k].data_ptr(), n_pts_k[k], origin, on_device=True)
                 if k >= args.warmup:
                     s = m.stats()
                     acc_ms.append(s["last_accumulate_ms"]); prep_ms.append(s["last_prep_ms"]); leaves.append(s["last_touched_leaves"])
@@ -300,6 +301,12 @@ def run_ours(args, rank, world, local_rank):
     else:
         res_v = run_leg(e2e=False)
         res_e = run_leg(e2e=True)
+    if world > 1 and vdist.PROFILE:
+        mean_ = lambda x: float(sum(x) / max(1, len(x)))
+        log = np.array(vdist.PROFILE_LOG[-args.steps:]) if vdist.PROFILE_LOG else np.zeros((1, 3))
+        print(f"[rank {rank}] value leg: step {res_v['ms'] / args.steps:.3f} ms  acc {mean_(res_v['acc_ms']):.3f}  int {mean_(res_v['int_ms']):.3f} | "
+              f"e2e leg: step {res_e['ms'] / args.steps:.3f} ms acc {mean_(res_e['acc_ms']):.3f} int {mean_(res_e['int_ms']):.3f} phases {log.mean(axis=0).round(3).tolist()} "
+              f"leaves {mean_(res_v['leaves']):.0f} map_leaves {res_v['map_leaves']}", file=sys.stderr, flush=True)
 
     # ---- max over ranks of the device time; totals over ranks ----
     def reduce(vals, op):
@@ -371,8 +378,10 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = None
     if world > 1 and vdist.PROFILE:
         log = np.array(vdist.PROFILE_LOG[-K:])
-        line["exchange"]["host_phase_ms_rank0"] = dict(zip(["partition", "counts_a2a", "records_a2a_launch", "import", "integrate"],
-                                                           [float(x) for x in log.mean(axis=0)]))
+        names = ["push_launch", "pull_wait_import_sync", "integrate"] if args.exchange == "p2p" else \
+            ["partition", "counts_a2a", "records_a2a_launch", "import", "integrate"]
+        line["exchange"]["host_phase_ms_rank0"] = dict(zip(names, [float(x) for x in log.mean(axis=0)]))
+        line["exchange"]["accumulate_ms_rank0"] = mean(res_e["acc_ms"])
     emit(line)
 
 
