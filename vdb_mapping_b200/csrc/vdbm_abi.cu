@@ -88,7 +88,7 @@ struct vdbm_map
   struct Exchange
   {
     ExchangePeers px{};
-    LeafRecord* inbox = nullptr;          // own inbox [2][n_ranks][cap]
+    uint64_t* inbox = nullptr;            // own inbox: masks [2*n_ranks][cap][16] then keys [2*n_ranks][cap]
     unsigned long long* ctrl = nullptr;   // own ctrl  [2][n_ranks]
     uint32_t* d_cursors = nullptr;        // [kMaxRanks] send cursors
     uint32_t* d_counts  = nullptr;        // [kMaxRanks] received counts of the current epoch
@@ -1191,7 +1191,7 @@ int vdbm_exchange_create(vdbm_map* m, int32_t rank, int32_t n_ranks, uint64_t ca
     return VDBM_ERR_INVALID_ARG;
   if (m->ex.created) return fail(m, VDBM_ERR_INVALID_ARG, "exchange already created on this handle");
   auto& ex = m->ex;
-  const size_t inbox_bytes = size_t(2) * n_ranks * cap * sizeof(LeafRecord);
+  const size_t inbox_bytes = inboxBytes(2u * uint32_t(n_ranks), uint32_t(cap));
   CU_TRY(m, cudaMalloc(&ex.inbox, inbox_bytes));
   CU_TRY(m, cudaMalloc(&ex.ctrl, size_t(2) * kMaxRanks * sizeof(unsigned long long)));
   CU_TRY(m, cudaMalloc(&ex.d_cursors, kMaxRanks * sizeof(uint32_t)));
@@ -1229,7 +1229,7 @@ int vdbm_exchange_connect(vdbm_map* m, const void* all_handles)
     CU_TRY(m, cudaIpcOpenMemHandle(&pc, h[1], cudaIpcMemLazyEnablePeerAccess));
     ex.opened.push_back(pi);
     ex.opened.push_back(pc);
-    ex.px.inbox[r] = static_cast<LeafRecord*>(pi);
+    ex.px.inbox[r] = static_cast<uint64_t*>(pi);
     ex.px.ctrl[r]  = static_cast<unsigned long long*>(pc);
   }
   ex.connected = true;

@@ -169,16 +169,24 @@ struct RaycastArgs
   const uint32_t* order; // [n] ray indices, longest first (LPT schedule for the DDA kernel)
 };
 
-// Peer-memory exchange state (device-visible part). inbox layout on every rank: [parity 2][sender n_ranks][cap] records;
+// Peer-memory exchange state (device-visible part). inbox layout on every rank, SoA so that every record's 16 mask
+// words form ONE aligned 128-byte line (full-line NVLink stores): for region R = parity * n_ranks + sender:
+//   masks: uint64 [R][cap][16]  (active[8] | value[8])      keys: uint64 [2 * n_ranks * cap + R * cap + i] after the masks
 // ctrl layout: [parity 2][sender n_ranks] uint64 = (epoch << 32) | record count, written by the sender.
 constexpr int kMaxRanks = 16;
 struct ExchangePeers
 {
-  LeafRecord* inbox[kMaxRanks];        // peer r's inbox base (mapped into this process), [rank] = own
+  uint64_t* inbox[kMaxRanks];          // peer r's inbox base (mapped into this process), [rank] = own
   unsigned long long* ctrl[kMaxRanks]; // peer r's ctrl base
   uint32_t cap;                        // records per sender region
   int32_t n_ranks, rank;
 };
+__host__ __device__ __forceinline__ size_t inboxMaskWord(uint32_t region, uint32_t cap, uint32_t i) { return (size_t(region) * cap + i) * 16; }
+__host__ __device__ __forceinline__ size_t inboxKeyWord(uint32_t n_regions, uint32_t region, uint32_t cap, uint32_t i)
+{
+  return size_t(n_regions) * cap * 16 + size_t(region) * cap + i;
+}
+__host__ __device__ __forceinline__ size_t inboxBytes(uint32_t n_regions, uint32_t cap) { return size_t(n_regions) * cap * 17 * sizeof(uint64_t); }
 
 // ---- launch wrappers (vdbm_kernels.cu) ----------------------------------------------------------------
 void launchPrepRays(const RaycastArgs& a, Counters* ctr, cudaStream_t s);
@@ -220,7 +228,7 @@ void launchSectionTileQuirk(MapTable mt, const uint64_t* blocks, uint32_t n_bloc
 void launchPushUpdate(UpdateGrid ug, uint32_t n_entries, ExchangePeers px, uint32_t parity, uint32_t epoch, uint32_t* cursors,
                       Counters* ctr, cudaStream_t s);
 // wait for every sender's (epoch, count) word, then OR all inbox records of this parity into the grid
-void launchPullUpdate(UpdateGrid ug, const LeafRecord* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks,
+void launchPullUpdate(UpdateGrid ug, const uint64_t* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks,
                       uint32_t parity, uint32_t epoch, uint32_t* counts_out, Counters* ctr, cudaStream_t s);
 uint32_t launchCount(); // kernels of this library launched by this process
 // CUB radix sort (descending) of (visit count, ray index) on key bits [4, 20); returns temp bytes when d_temp == nullptr

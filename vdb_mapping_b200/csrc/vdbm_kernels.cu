@@ -1210,10 +1210,16 @@ __global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t
     if (j < 8) { word = g.act[size_t(e) * 8 + j]; g.act[size_t(e) * 8 + j] = 0; }
     else       { word = g.val[size_t(e) * 8 + (j - 8)]; g.val[size_t(e) * 8 + (j - 8)] = 0; }
     if (pos >= px.cap) { if (j == 0) atomicOr(&ctr->flags, kFlagExchangeOverflow); continue; }
-    LeafRecord* dst = px.inbox[r] + (size_t(parity) * px.n_ranks + px.rank) * px.cap + pos;
-    if (j < 8) dst->active[j] = word;
-    else dst->value[j - 8] = word;
-    if (j == 0) dst->key = s_key[k];
+    const uint32_t region = parity * uint32_t(px.n_ranks) + uint32_t(px.rank);
+    // 16 lanes x 8 bytes = one aligned 128-byte line in the owner's inbox
+    px.inbox[r][inboxMaskWord(region, px.cap, pos) + j] = word;
+  }
+  // keys: thread t writes the key of record t (records of one owner are contiguous per block -> coalesced runs)
+  if (threadIdx.x < n_here)
+  {
+    const uint32_t r = s_dst[threadIdx.x] >> 24, pos = s_base[r] + (s_dst[threadIdx.x] & 0xFFFFFFu);
+    if (pos < px.cap)
+      px.inbox[r][inboxKeyWord(2u * uint32_t(px.n_ranks), parity * uint32_t(px.n_ranks) + uint32_t(px.rank), px.cap, pos)] = s_key[threadIdx.x];
   }
 }
 
@@ -1246,7 +1252,7 @@ __global__ void wait_peers_kernel(const unsigned long long* ctrl, int32_t n_rank
   counts_out[s] = uint32_t(w);
 }
 
-__global__ void __launch_bounds__(256) pull_update_kernel(UpdateGrid g, const LeafRecord* inbox, uint32_t cap, int32_t n_ranks, uint32_t parity,
+__global__ void __launch_bounds__(256) pull_update_kernel(UpdateGrid g, const uint64_t* inbox, uint32_t cap, int32_t n_ranks, uint32_t parity,
                                                          const uint32_t* counts, Counters* ctr)
 {
   // 16 lanes per record, grid-stride over all sender regions of this parity
@@ -1254,8 +1260,8 @@ __global__ void __launch_bounds__(256) pull_update_kernel(UpdateGrid g, const Le
   const int j = threadIdx.x & 15;
   for (int s = 0; s < n_ranks; ++s)
   {
-    const uint32_t cnt       = counts[s];
-    const LeafRecord* region = inbox + (size_t(parity) * n_ranks + s) * cap;
+    const uint32_t cnt    = counts[s];
+    const uint32_t region = parity * uint32_t(n_ranks) + uint32_t(s);
     // all 32 lanes of a warp run the same number of iterations (ballot below needs the full warp)
     const uint32_t iters = (cnt + n_groups - 1) / n_groups;
     for (uint32_t it = 0; it < iters; ++it)
@@ -1265,8 +1271,8 @@ __global__ void __launch_bounds__(256) pull_update_kernel(UpdateGrid g, const Le
       uint64_t word = 0, key = 0;
       if (valid)
       {
-        key  = region[rec].key;
-        word = (j < 8) ? region[rec].active[j] : region[rec].value[j - 8];
+        word = inbox[inboxMaskWord(region, cap, rec) + j];
+        if (j == 0) key = inbox[inboxKeyWord(2u * uint32_t(n_ranks), region, cap, rec)];
       }
       const unsigned grp = 0xFFFFu << (threadIdx.x & 16);
       const unsigned nz  = __ballot_sync(kFull, valid && j < 8 && word != 0) & grp;
@@ -1457,7 +1463,7 @@ void launchPushUpdate(UpdateGrid g, uint32_t n_entries, ExchangePeers px, uint32
   VDBM_LAUNCH(publish_counts_kernel, 1, 32, s, px, parity, epoch, cursors);
 }
 
-void launchPullUpdate(UpdateGrid g, const LeafRecord* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks, uint32_t parity,
+void launchPullUpdate(UpdateGrid g, const uint64_t* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks, uint32_t parity,
                       uint32_t epoch, uint32_t* counts_out, Counters* ctr, cudaStream_t s)
 {
   VDBM_LAUNCH(wait_peers_kernel, 1, 32, s, ctrl, n_ranks, parity, epoch, counts_out, ctr);
