@@ -302,3 +302,32 @@ def test_apply_map_section_grid(full, quirk):
     gb.applyMapSectionGrid(section, tile_quirk=quirk)
     ob.applyMapSectionGrid(section, tile_quirk=quirk)
     assert_leafsets_equal(gb.exportMap(), ob.exportMap(), "map after applyMapSectionGrid")
+
+
+@pytest.mark.parametrize("seg_len", ["257", "1024", "auto"])
+def test_long_rays_are_split_into_segments_exactly(seg_len, monkeypatch):
+    """Rays longer than 1.5 x the segment length are traversed as independent segments whose start states come
+    from a per-axis pre-pass; the result must stay bit-identical to the sequential oracle (ties, negative directions,
+    axis-aligned and clipped long rays, zero components)."""
+    if seg_len != "auto":
+        monkeypatch.setenv("VDBM_SEG_LEN", seg_len)   # forced split; "auto" plans it from the previous scan
+    rng = np.random.default_rng(123)
+    res, max_range = 0.01, 60.0
+    g, o = _pair(res, max_range, CFG_GTEST)
+    for k in range(3):
+        n = 600
+        d = rng.normal(size=(n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        r = rng.uniform(5.0, 80.0, size=(n, 1))                 # 500 .. 8000 voxels, some clipped at 60 m
+        pts = d * r
+        pts[:20, 1:] = 0.0                                       # axis-aligned long rays (two disabled axes)
+        pts[20:40, 2] = 0.0                                      # planar rays
+        pts[40:60] = np.round(pts[40:60] * 8) / 8                # lattice end points: exact ties in the DDA
+        pts[60:70] = np.array([[40.0, 40.0, 40.0]]) * rng.choice([-1, 1], size=(10, 3))   # perfect diagonals
+        origin = np.array([0.0031 * k, -0.0042 * k, 0.0017 * k])
+        cloud = np.ones((n, 4), np.float32); cloud[:, :3] = (pts + origin).astype(np.float32)
+        g.accumulateUpdate(cloud, origin, "s"); o.accumulateUpdate(cloud, origin, "s")
+        assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), f"update grid scan {k}")
+        g.integrateUpdate(); o.integrateUpdate()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
+    assert g.stats()["visits"] == o.stats()["visits"]

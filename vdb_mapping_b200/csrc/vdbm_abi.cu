@@ -36,6 +36,8 @@ struct Source
   double max_range = 0.0;
   UpdateGrid g{};
   uint32_t cap       = 0;         // brick slots
+  uint64_t prev_visits     = 0;   // voxel marks and longest ray of this source's previous scan: the segment length of
+  uint32_t prev_max_visits = 0;   // the next scan is planned from them (consecutive scans of a sensor look alike)
   uint32_t n_bricks  = 0;         // host copies, valid after every synchronising call
   uint32_t n_entries = 0;         // touched leaves (compact list is always rebuilt after a grid write)
   LeafRecord* d_change = nullptr; // change records of the last update (device)
@@ -73,7 +75,10 @@ struct vdbm_map
   uint8_t* d_points = nullptr;
   size_t points_cap = 0;
   RayRec* d_rays    = nullptr;
-  uint32_t* d_sort  = nullptr; // 4 x rays_cap u32: keys in/out, idx in/out
+  SegRec* d_segs    = nullptr; // seg_cap segments (first rays_cap: one per ray)
+  uint32_t* d_long  = nullptr; // 2 x rays_cap u32: long-ray list, extra-segment base per ray
+  size_t seg_cap    = 0;
+  uint32_t* d_sort  = nullptr; // 4 x seg_cap u32: keys in/out, idx in/out
   void* d_sort_tmp  = nullptr;
   size_t sort_tmp_bytes = 0;
   size_t rays_cap   = 0;
@@ -323,20 +328,42 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   a.inv_res    = 1.0 / m->params.resolution;
   if (m->rays_cap < n)
   {
-    cudaFree(m->d_rays); cudaFree(m->d_sort); cudaFree(m->d_sort_tmp);
-    m->d_rays = nullptr; m->d_sort = nullptr; m->d_sort_tmp = nullptr;
+    cudaFree(m->d_rays); cudaFree(m->d_segs); cudaFree(m->d_long); cudaFree(m->d_sort); cudaFree(m->d_sort_tmp);
+    m->d_rays = nullptr; m->d_segs = nullptr; m->d_long = nullptr; m->d_sort = nullptr; m->d_sort_tmp = nullptr;
     m->rays_cap = 0;
+    // one segment per ray + a pool of extra segments for long rays (a ray that finds the pool empty stays whole)
+    const size_t seg_cap = n + 4 * n + 65536;
     CU_TRY(m, cudaMalloc(&m->d_rays, n * sizeof(RayRec)));
-    CU_TRY(m, cudaMalloc(&m->d_sort, n * 4 * sizeof(uint32_t)));
-    m->sort_tmp_bytes = sortRaysByLength(nullptr, 0, m->d_sort, m->d_sort + n, m->d_sort + 2 * n, m->d_sort + 3 * n, uint32_t(n), m->stream);
+    CU_TRY(m, cudaMalloc(&m->d_segs, seg_cap * sizeof(SegRec)));
+    CU_TRY(m, cudaMalloc(&m->d_long, n * 2 * sizeof(uint32_t)));
+    CU_TRY(m, cudaMalloc(&m->d_sort, seg_cap * 4 * sizeof(uint32_t)));
+    m->sort_tmp_bytes = sortRaysByLength(nullptr, 0, m->d_sort, m->d_sort + seg_cap, m->d_sort + 2 * seg_cap, m->d_sort + 3 * seg_cap,
+                                         uint32_t(seg_cap), m->stream);
     CU_TRY(m, cudaMalloc(&m->d_sort_tmp, m->sort_tmp_bytes ? m->sort_tmp_bytes : 8));
     m->rays_cap = n;
+    m->seg_cap  = seg_cap;
   }
-  a.rays = m->d_rays;
-  // layout inside d_sort (stride = rays_cap): [keys_in | keys_out | idx_in | idx_out]
+  a.rays      = m->d_rays;
+  a.segs      = m->d_segs;
+  a.seg_cap   = uint32_t(std::min<size_t>(m->seg_cap, 0xFFFFFFF0u));
+  a.long_rays = m->d_long;
+  a.seg_base  = m->d_long + m->rays_cap;
+  // layout inside d_sort (stride = seg_cap): [keys_in | keys_out | idx_in | idx_out]
   a.sort_keys = m->d_sort;
-  a.sort_idx  = m->d_sort + 2 * m->rays_cap;
-  a.order     = m->d_sort + 3 * m->rays_cap;
+  a.sort_idx  = m->d_sort + 2 * m->seg_cap;
+  a.order     = m->d_sort + 3 * m->seg_cap;
+  a.sorted_keys = m->d_sort + m->seg_cap;
+  // Segment plan. A ray is sequential, so the DDA kernel cannot finish before its longest work item; splitting costs a
+  // pre-pass and extra refills, so it is only done when the longest ray of the previous scan exceeded TWICE the average
+  // load of a resident lane (few rays per lane: multi-GPU shards, very long rays), with segments of half that load.
+  a.seg_len = 0;
+  if (const char* e = getenv("VDBM_SEG_LEN")) a.seg_len = uint32_t(atoi(e)); // experiment override
+  else if (s.prev_visits)
+  {
+    const uint64_t lanes    = uint64_t(m->dda_grid) * 256;
+    const uint64_t per_lane = std::max<uint64_t>(1, s.prev_visits / lanes);
+    if (uint64_t(s.prev_max_visits) > per_lane * 2) a.seg_len = uint32_t(std::min<uint64_t>(4096, std::max<uint64_t>(256, per_lane / 2)));
+  }
 
   // counters before this attempt (needed if the scan has to be replayed after a hash overflow). Every ABI
   // call that changes device counters ends with syncCounters(), so the pinned host copy is current.
@@ -346,9 +373,23 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   {
     CU_TRY(m, cudaMemsetAsync(&m->d_ctr->ray_cursor, 0, sizeof(unsigned), m->stream));
     CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+    CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_extra, 0, 3 * sizeof(unsigned), m->stream)); // n_extra, n_long, max_visits
+    // extra-segment slots that end up unused must carry a zero sort key (the DDA kernel stops at the first zero key)
+    CU_TRY(m, cudaMemsetAsync(m->d_sort + n, 0, (m->seg_cap - n) * sizeof(uint32_t), m->stream));
     launchPrepRays(a, m->d_ctr, m->stream);
-    sortRaysByLength(m->d_sort_tmp, m->sort_tmp_bytes, a.sort_keys, m->d_sort + m->rays_cap, a.sort_idx, m->d_sort + 3 * m->rays_cap,
-                     uint32_t(n), m->stream);
+    uint32_t n_long = 0, n_extra = 0;
+    if (a.seg_len)
+    {
+      // how many rays were split, how many extra segments exist (one small read-back; the sort needs the exact count)
+      CU_TRY(m, cudaMemcpyAsync(m->h_small + 12, &m->d_ctr->n_extra, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream));
+      CU_TRY(m, cudaStreamSynchronize(m->stream));
+      n_long  = m->h_small[13];
+      n_extra = uint32_t(std::min<uint64_t>(m->h_small[12], a.seg_cap - n));
+    }
+    a.n_segs = uint32_t(n) + n_extra;
+    launchLongRaySegments(a, n_long, m->stream);
+    sortRaysByLength(m->d_sort_tmp, m->sort_tmp_bytes, a.sort_keys, m->d_sort + m->seg_cap, a.sort_idx, m->d_sort + 3 * m->seg_cap,
+                     a.n_segs, m->stream);
     CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
     launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream);
     launchCompactLeaves(s.g, m->stream);
@@ -389,6 +430,8 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   m->stats.last_visits         = m->h_ctr->visits - before.visits;
   m->stats.last_touched_leaves = s.n_entries;
   m->stats.update_capacity     = std::max(m->stats.update_capacity, s.cap * uint32_t(kBrickLeaves));
+  s.prev_visits     = m->stats.last_visits;
+  s.prev_max_visits = m->h_ctr->max_visits;
   return VDBM_OK;
 }
 
@@ -612,7 +655,7 @@ void vdbm_destroy(vdbm_map* m)
   freeMapPool(m->mt);
   cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
   cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
-  cudaFree(m->d_sort); cudaFree(m->d_sort_tmp); cudaFree(m->d_resolved); cudaFree(m->d_near);
+  cudaFree(m->d_sort); cudaFree(m->d_sort_tmp); cudaFree(m->d_resolved); cudaFree(m->d_near); cudaFree(m->d_segs); cudaFree(m->d_long);
   for (void* p : m->ex.opened) cudaIpcCloseMemHandle(p);
   cudaFree(m->ex.inbox); cudaFree(m->ex.ctrl); cudaFree(m->ex.d_cursors); cudaFree(m->ex.d_counts);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);

@@ -127,6 +127,9 @@ struct Counters
   unsigned int ray_cursor;                                        // work-fetch cursor of the DDA kernel
   unsigned int n_change;                                          // change records appended
   unsigned int n_out;                                             // generic output counter (sections, partition)
+  unsigned int n_extra;                                           // extra segment slots handed out by prep_rays
+  unsigned int n_long;                                            // rays split into segments
+  unsigned int max_visits;                                        // longest ray of the last prep_rays launch
 };
 
 // One prepared ray (written by prep_rays_kernel, consumed by raycast_dda_kernel). 32 bytes.
@@ -143,6 +146,21 @@ __host__ __device__ __forceinline__ int rayStep(uint32_t flags, int axis)
   const uint32_t f = (flags >> (4 + 2 * axis)) & 3u;
   return f == 1u ? 1 : (f == 2u ? -1 : 0);
 }
+
+// One unit of DDA work: a whole ray, or one SEGMENT of a long ray. A segment starts from the exact DDA state
+// (next[3], steps taken per axis) that the sequential traversal passes through at a time threshold t = j/P: all
+// crossings with time < t happen before any crossing with time >= t whatever the tie rules, so that state is visited
+// by the reference's loop too, and the three axes' crossing-time sequences (v_0 = d/2, v_{k+1} = fl(v_k + d)) are
+// independent of each other -> long_ray_segments_kernel can compute them per axis without marking anything. 48 bytes.
+struct __align__(16) SegRec
+{
+  double next[3];   // DDA::mNext at the segment start
+  uint32_t m[3];    // steps already taken along each axis (start voxel = origin + step * m)
+  uint32_t count;   // voxels this segment marks (0 = nothing to do)
+  uint32_t ray;     // index into RaycastArgs::rays
+  uint32_t last;    // 1: this segment ends at the ray's end voxel (it alone delivers the hit)
+};
+// (segment length is a per-scan runtime choice, RaycastArgs::seg_len; 0 = do not split)
 
 // 136-byte exchange / export record of an update-grid leaf
 struct LeafRecord
@@ -164,9 +182,16 @@ struct RaycastArgs
   double half_res;   // resolution / 2.0
   double inv_res;    // 1.0 / resolution
   RayRec* rays;      // [n]
-  uint32_t* sort_keys; // [n] written by prep_rays: min(visits, 2^20-1); 0 for rays that need no DDA
-  uint32_t* sort_idx;  // [n] written by prep_rays: identity
-  const uint32_t* order; // [n] ray indices, longest first (LPT schedule for the DDA kernel)
+  SegRec* segs;      // [seg_cap]: segment i < n is ray i's first (or only) segment, the rest are extra segments of long rays
+  uint32_t seg_cap;
+  uint32_t seg_len;  // target voxel marks per segment; rays with more than 1.5 x seg_len marks are split. 0 = never split
+  uint32_t n_segs;   // segments to traverse (n + extra segments in use); set by the host before the DDA kernel
+  uint32_t* long_rays; // [n] indices of rays that were split (count in Counters::n_long)
+  uint32_t* seg_base;  // [n] first extra segment slot of a split ray
+  uint32_t* sort_keys; // [seg_cap] min(segment marks, 2^20-1); 0 = nothing to do
+  uint32_t* sort_idx;  // [seg_cap] identity
+  const uint32_t* order; // [n_segs] segment indices, longest first (LPT schedule for the DDA kernel)
+  const uint32_t* sorted_keys; // [n_segs] the keys in that order (descending)
 };
 
 // Peer-memory exchange state (device-visible part). inbox layout on every rank, SoA so that every record's 16 mask
@@ -190,6 +215,7 @@ __host__ __device__ __forceinline__ size_t inboxBytes(uint32_t n_regions, uint32
 
 // ---- launch wrappers (vdbm_kernels.cu) ----------------------------------------------------------------
 void launchPrepRays(const RaycastArgs& a, Counters* ctr, cudaStream_t s);
+void launchLongRaySegments(const RaycastArgs& a, uint32_t n_long, cudaStream_t s);
 // near_act: zero-initialised scratch of nearCopiesBytes() bytes (privatised near-field bricks), left zeroed again
 void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s);
 size_t nearCopiesBytes();

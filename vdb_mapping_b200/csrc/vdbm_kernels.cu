@@ -173,11 +173,38 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
         r.visits = uint32_t(visits);
       }
     }
-    a.rays[i]      = r;
-    a.sort_keys[i] = uint32_t(visits > 0xFFFFFull ? 0xFFFFFull : visits);
+    a.rays[i] = r;
+    // segment i = this ray's first (or only) segment, starting at the sensor voxel
+    SegRec sg;
+    sg.next[0] = (r.delta[0] == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, r.delta[0]); // DDA::init: 0.5 * |inv| exactly
+    sg.next[1] = (r.delta[1] == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, r.delta[1]);
+    sg.next[2] = (r.delta[2] == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, r.delta[2]);
+    sg.m[0] = sg.m[1] = sg.m[2] = 0;
+    sg.count = r.visits;
+    sg.ray   = uint32_t(i);
+    sg.last  = 1;
+    // zero-length rays with a hit still need one visit by the DDA kernel (count 0, flagged in the ray record)
+    uint32_t key = uint32_t(visits > 0xFFFFFull ? 0xFFFFFull : visits);
+    if ((r.flags & kRayValid) && (r.flags & kRayZeroLen) && !(r.flags & kRayClipped)) key = 1;
+    if (a.seg_len != 0 && r.visits > a.seg_len + a.seg_len / 2)
+    {
+      // long ray: reserve P - 1 extra segment slots; if the pool is exhausted the ray simply stays whole (the
+      // reservation is not given back: every later one fails too, and the unused slots keep a zero sort key)
+      const uint32_t P    = (r.visits + a.seg_len - 1) / a.seg_len;
+      const uint32_t base = atomicAdd(&ctr->n_extra, P - 1);
+      if (uint64_t(a.n) + base + (P - 1) <= a.seg_cap)
+      {
+        a.seg_base[i] = uint32_t(a.n) + base;
+        a.long_rays[atomicAdd(&ctr->n_long, 1u)] = uint32_t(i);
+        key = 0; // finalised (with the extra segments) by long_ray_segments_kernel
+      }
+    }
+    a.segs[i]      = sg;
+    a.sort_keys[i] = key;
     a.sort_idx[i]  = uint32_t(i);
   }
   // warp-aggregated statistics
+  const unsigned vmax = __reduce_max_sync(kFull, unsigned(visits));
   visits      = __reduce_add_sync(kFull, unsigned(visits)); // per-lane visits <= 1 + 3*2^24, 32 lanes fit in 32 bits
   nan_skipped = __reduce_add_sync(kFull, nan_skipped);
   clipped     = __reduce_add_sync(kFull, clipped);
@@ -185,9 +212,66 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
   if ((threadIdx.x & 31) == 0)
   {
     if (visits) atomicAdd(&ctr->visits, visits);
+    if (vmax) atomicMax(&ctr->max_visits, vmax);
     if (nan_skipped) atomicAdd(&ctr->nan_skipped, (unsigned long long)nan_skipped);
     if (clipped) atomicAdd(&ctr->clipped, (unsigned long long)clipped);
     if (range_err) atomicOr(&ctr->flags, kFlagCoordRange);
+  }
+}
+
+// ====================================================================================================
+// K0b: segment boundaries of long rays. Three adjacent lanes per ray, one per axis: each walks ITS axis' crossing-time
+// sequence v_0 = d/2, v_{k+1} = fl(v_k + d) (the same fp64 additions the DDA performs, in the same order) and records,
+// for every threshold t_j = j / P, how many steps precede it and the value of `next` there. No marking, no memory
+// traffic inside the loop: ~30x cheaper per step than the DDA itself, and it removes the serial floor of one ray.
+// ====================================================================================================
+__global__ void __launch_bounds__(128) long_ray_segments_kernel(RaycastArgs a, uint32_t n_long)
+{
+  // a warp takes 10 rays: lanes 0..29 = (ray, axis) pairs, lanes 30 and 31 idle, so a ray never straddles warps
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane      = threadIdx.x & 31;
+  const uint32_t li   = warp * 10u + uint32_t(lane / 3);
+  const int axis      = lane % 3;
+  if (lane >= 30 || li >= n_long) return;
+  const uint32_t ray = a.long_rays[li];
+  const RayRec r     = a.rays[ray];
+  const uint32_t P   = (r.visits + a.seg_len - 1) / a.seg_len;
+  const uint32_t xb  = a.seg_base[ray];           // extra segments j = 1..P-1 live at xb + j - 1
+  const double d     = r.delta[axis];
+  const double invP  = 1.0 / double(P);
+  double v   = (d == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d);
+  uint32_t m = 0;
+  for (uint32_t j = 1; j < P; ++j)
+  {
+    const double tj = double(j) * invP;           // any threshold works as long as the three axes use the same value
+    while (v < tj) { v = __dadd_rn(v, d); ++m; }
+    SegRec* sg    = a.segs + (xb + j - 1);
+    sg->next[axis] = v;
+    sg->m[axis]    = m;
+  }
+  // the three lanes of this ray are in the same warp: make their writes visible to the finalising lane
+  __syncwarp(__activemask());
+  if (axis != 0) return;
+  // finalise: marks per segment = steps between consecutive boundaries; the last one runs to the end voxel
+  uint32_t s_prev = 0; // steps before segment j
+  for (uint32_t j = 0; j < P; ++j)
+  {
+    SegRec* sg = (j == 0) ? a.segs + ray : a.segs + (xb + j - 1);
+    uint32_t s_next;
+    if (j + 1 < P)
+    {
+      const SegRec* nx = a.segs + (xb + j);
+      s_next           = nx->m[0] + nx->m[1] + nx->m[2];
+    }
+    else s_next = r.visits; // marks V_{s_prev} .. V_T, T = visits - 1
+    const uint32_t cnt = s_next - s_prev;
+    sg->count = cnt;
+    sg->ray   = ray;
+    sg->last  = (j + 1 == P) ? 1u : 0u;
+    const uint32_t slot = (j == 0) ? ray : (xb + j - 1);
+    a.sort_keys[slot]   = cnt > 0xFFFFFu ? 0xFFFFFu : cnt;
+    a.sort_idx[slot]    = slot;
+    s_prev              = s_next;
   }
 }
 
@@ -279,10 +363,13 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
         if (!busy && !done)
         {
           const uint64_t idx = uint64_t(base) + __popc(want & ((1u << lane) - 1u));
-          if (idx >= a.n) done = true;
+          // keys are sorted descending: the first zero key means only empty work items (NaN / zero-length rays without a
+          // hit, unused segment slots) follow
+          if (idx >= a.n_segs || a.sorted_keys[idx] == 0u) done = true;
           else
           {
-            const RayRec r = a.rays[a.order[idx]]; // longest rays first: the tail of the kernel is made of short rays
+            const SegRec sg = a.segs[a.order[idx]]; // longest segments first: the tail of the kernel is made of short ones
+            const RayRec r  = a.rays[sg.ray];
             if (r.flags & kRayValid)
             {
               if (r.flags & kRayZeroLen)
@@ -296,21 +383,26 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
                   redOr64(g.val + w, bit);
                 }
               }
-              else
+              else if (sg.count != 0)
               {
                 d0 = r.delta[0]; d1 = r.delta[1]; d2 = r.delta[2];
-                // DDA::init: next = t0 + (voxel + {1|0} - pos) * inv = 0.5 * |inv| exactly; DBL_MAX if dir == 0
-                n0 = (d0 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d0);
-                n1 = (d1 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d1);
-                n2 = (d2 == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, d2);
+                n0 = sg.next[0]; n1 = sg.next[1]; n2 = sg.next[2];
                 sx = rayStep(r.flags, 0); sy = rayStep(r.flags, 1); sz = rayStep(r.flags, 2);
-                x = ox; y = oy; z = oz;
-                remaining = r.visits;
-                clipped   = r.flags & kRayClipped;
-                slot      = origin_slot;
-                act_base  = my_near + size_t(origin_ni) * (kBrickLeaves * 8);
+                x = ox + sx * int(sg.m[0]); y = oy + sy * int(sg.m[1]); z = oz + sz * int(sg.m[2]);
+                remaining = sg.count;
+                // only the segment that reaches the end voxel delivers the hit; a clipped ray never does
+                clipped   = (r.flags & kRayClipped) | (sg.last ? 0u : 1u);
                 cur_off = kInvalid; acc = 0;
-                need = false;
+                if (sg.m[0] | sg.m[1] | sg.m[2])
+                {
+                  need = true; // a later segment starts somewhere along the ray: look its brick up below
+                }
+                else
+                {
+                  slot     = origin_slot;
+                  act_base = my_near + size_t(origin_ni) * (kBrickLeaves * 8);
+                  need     = false;
+                }
                 busy = true;
               }
             }
@@ -1324,6 +1416,11 @@ void launchPrepRays(const RaycastArgs& a, Counters* ctr, cudaStream_t s)
   VDBM_LAUNCH(prep_rays_kernel, blocksFor(a.n, 256), 256, s, a, ctr);
 }
 
+void launchLongRaySegments(const RaycastArgs& a, uint32_t n_long, cudaStream_t s)
+{
+  if (n_long) VDBM_LAUNCH(long_ray_segments_kernel, blocksFor(blocksFor(n_long, 10), 4), 128, s, a, n_long);
+}
+
 int raycastDDAGrid(int device)
 {
   int sms = 148, per_sm = 4;
@@ -1338,7 +1435,7 @@ size_t nearCopiesBytes() { return size_t(kNearCopies) * kNearBricks * kBrickLeav
 void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s)
 {
   if (a.n == 0) return;
-  const uint64_t blocks = (((a.n + 31) / 32) + 7) / 8;
+  const uint64_t blocks = (((uint64_t(a.n_segs) + 31) / 32) + 7) / 8;
   if (uint64_t(grid) > blocks) grid = int(blocks);
   static const int mode = [] { const char* e = getenv("VDBM_DDA_MODE"); return e ? atoi(e) : 0; }();
   if (mode == 1) VDBM_LAUNCH(raycast_dda_kernel<1>, grid, 256, s, a, g, near_act, ctr);
