@@ -303,7 +303,7 @@ def run_ours(args, rank, world, local_rank):
         res_e = run_leg(e2e=True)
     if world > 1 and vdist.PROFILE:
         mean_ = lambda x: float(sum(x) / max(1, len(x)))
-        log = np.array(vdist.PROFILE_LOG[-args.steps:]) if vdist.PROFILE_LOG else np.zeros((1, 3))
+        log = np.array(vdist.PROFILE_LOG[-args.steps:]) if vdist.PROFILE_LOG else np.zeros((1, 6))
         print(f"[rank {rank}] value leg: step {res_v['ms'] / args.steps:.3f} ms  acc {mean_(res_v['acc_ms']):.3f}  int {mean_(res_v['int_ms']):.3f} | "
               f"e2e leg: step {res_e['ms'] / args.steps:.3f} ms acc {mean_(res_e['acc_ms']):.3f} int {mean_(res_e['int_ms']):.3f} phases {log.mean(axis=0).round(3).tolist()} "
               f"leaves {mean_(res_v['leaves']):.0f} map_leaves {res_v['map_leaves']}", file=sys.stderr, flush=True)
@@ -378,7 +378,7 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = None
     if world > 1 and vdist.PROFILE:
         log = np.array(vdist.PROFILE_LOG[-K:])
-        names = ["push_launch", "pull_wait_import_sync", "integrate"] if args.exchange == "p2p" else \
+        names = ["push_launch", "pull_wait_import_sync", "integrate", "dev_push", "dev_wait", "dev_import"] if args.exchange == "p2p" else \
             ["partition", "counts_a2a", "records_a2a_launch", "import", "integrate"]
         line["exchange"]["host_phase_ms_rank0"] = dict(zip(names, [float(x) for x in log.mean(axis=0)]))
         line["exchange"]["accumulate_ms_rank0"] = mean(res_e["acc_ms"])

@@ -197,6 +197,9 @@ int vdbm_exchange_create(vdbm_map* map, int32_t rank, int32_t n_ranks, uint64_t 
 int vdbm_exchange_connect(vdbm_map* map, const void* all_handles);
 int vdbm_update_push(vdbm_map* map, const char* source_id);
 int vdbm_update_pull(vdbm_map* map, const char* source_id);
+/* device times (ms, CUDA events) of the last push / pull pair: out[0] bin+send kernels, out[1] wait for the peers'
+ * epoch words (includes their raycast skew), out[2] import + leaf compaction */
+int vdbm_exchange_timings(vdbm_map* map, float* out3);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 int vdbm_stats(vdbm_map* map, vdbm_stats_t* out);

@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     sig("vdbm_exchange_connect", C.c_int, vp, vp)
     sig("vdbm_update_push", C.c_int, vp, cp)
     sig("vdbm_update_pull", C.c_int, vp, cp)
+    sig("vdbm_exchange_timings", C.c_int, vp, f32p)
     sig("vdbm_stats", C.c_int, vp, C.POINTER(VdbmStats))
     sig("vdbm_last_error", cp, vp)
     sig("vdbm_synchronize", C.c_int, vp)

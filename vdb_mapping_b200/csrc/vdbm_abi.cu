@@ -100,6 +100,8 @@ struct vdbm_map
     std::vector<void*> opened;            // peer mappings to close
     uint32_t epoch = 0;
     bool created = false, connected = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // push begin/end, wait end, import end
+    float ms[3] = {0, 0, 0};
   } ex;
 
   // persistent pinned staging for large exports (page-locking hundreds of MB per call costs more than the copy)
@@ -658,6 +660,7 @@ void vdbm_destroy(vdbm_map* m)
   cudaFree(m->d_sort); cudaFree(m->d_sort_tmp); cudaFree(m->d_resolved); cudaFree(m->d_near); cudaFree(m->d_segs); cudaFree(m->d_long);
   for (void* p : m->ex.opened) cudaIpcCloseMemHandle(p);
   cudaFree(m->ex.inbox); cudaFree(m->ex.ctrl); cudaFree(m->ex.d_cursors); cudaFree(m->ex.d_counts);
+  for (auto& e : m->ex.ev) if (e) cudaEventDestroy(e);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1); cudaEventDestroy(m->ev2);
@@ -1247,7 +1250,15 @@ int vdbm_exchange_create(vdbm_map* m, int32_t rank, int32_t n_ranks, uint64_t ca
   CU_TRY(m, cudaIpcGetMemHandle(&h[1], ex.ctrl));
   static_assert(sizeof(h) == VDBM_IPC_HANDLE_BYTES, "two CUDA IPC handles");
   std::memcpy(handles_out, h, sizeof(h));
+  for (auto& e : ex.ev) CU_TRY(m, cudaEventCreate(&e));
   ex.created = true;
+  return VDBM_OK;
+}
+
+int vdbm_exchange_timings(vdbm_map* m, float* out3)
+{
+  if (!m || !out3) return VDBM_ERR_INVALID_ARG;
+  out3[0] = m->ex.ms[0]; out3[1] = m->ex.ms[1]; out3[2] = m->ex.ms[2];
   return VDBM_OK;
 }
 
@@ -1287,7 +1298,9 @@ int vdbm_update_push(vdbm_map* m, const char* source_id)
   auto& ex = m->ex;
   if (!ex.connected) return fail(m, VDBM_ERR_INVALID_ARG, "exchange not connected");
   ex.epoch += 1;
+  CU_TRY(m, cudaEventRecord(ex.ev[0], m->stream));
   launchPushUpdate(s->g, s->n_entries, ex.px, ex.epoch & 1u, ex.epoch, ex.d_cursors, m->d_ctr, m->stream);
+  CU_TRY(m, cudaEventRecord(ex.ev[1], m->stream));
   launchResetBricks(s->g, s->n_bricks, m->stream);
   CU_TRY(m, cudaGetLastError());
   s->n_bricks = s->n_entries = 0;
@@ -1301,10 +1314,13 @@ int vdbm_update_pull(vdbm_map* m, const char* source_id)
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   auto& ex = m->ex;
   if (!ex.connected || ex.epoch == 0) return fail(m, VDBM_ERR_INVALID_ARG, "vdbm_update_push first");
+  launchWaitPeers(ex.ctrl, ex.px.n_ranks, ex.epoch & 1u, ex.epoch, ex.d_counts, m->d_ctr, m->stream);
+  CU_TRY(m, cudaEventRecord(ex.ev[2], m->stream));
   for (int attempt = 0; attempt < 24; ++attempt)
   {
     launchPullUpdate(s->g, ex.inbox, ex.ctrl, ex.px.cap, ex.px.n_ranks, ex.epoch & 1u, ex.epoch, ex.d_counts, m->d_ctr, m->stream);
     launchCompactLeaves(s->g, m->stream);
+    CU_TRY(m, cudaEventRecord(ex.ev[3], m->stream));
     CU_TRY(m, cudaGetLastError());
     CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s->g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
     int rc = syncCounters(m);
@@ -1327,6 +1343,9 @@ int vdbm_update_pull(vdbm_map* m, const char* source_id)
     if (!overflow) break; // the inbox still holds this epoch's records: a replay of the pull is idempotent
   }
   m->stats.last_touched_leaves = s->n_entries;
+  cudaEventElapsedTime(&ex.ms[0], ex.ev[0], ex.ev[1]);
+  cudaEventElapsedTime(&ex.ms[1], ex.ev[1], ex.ev[2]);
+  cudaEventElapsedTime(&ex.ms[2], ex.ev[2], ex.ev[3]);
   return VDBM_OK;
 }
 

@@ -253,7 +253,9 @@ void launchSectionTileQuirk(MapTable mt, const uint64_t* blocks, uint32_t n_bloc
 // fused bin + send over peer memory; cursors = device scratch [kMaxRanks] (zeroed by the wrapper)
 void launchPushUpdate(UpdateGrid ug, uint32_t n_entries, ExchangePeers px, uint32_t parity, uint32_t epoch, uint32_t* cursors,
                       Counters* ctr, cudaStream_t s);
-// wait for every sender's (epoch, count) word, then OR all inbox records of this parity into the grid
+void launchWaitPeers(const unsigned long long* ctrl, int32_t n_ranks, uint32_t parity, uint32_t epoch, uint32_t* counts_out, Counters* ctr,
+                     cudaStream_t s);
+// after launchWaitPeers: OR all inbox records of this parity into the grid
 void launchPullUpdate(UpdateGrid ug, const uint64_t* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks,
                       uint32_t parity, uint32_t epoch, uint32_t* counts_out, Counters* ctr, cudaStream_t s);
 uint32_t launchCount(); // kernels of this library launched by this process

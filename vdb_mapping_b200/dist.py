@@ -161,7 +161,8 @@ def push_pull_and_integrate(engine):
     engine.integrate()
     if PROFILE:
         t.append(time.perf_counter())
-        PROFILE_LOG.append([round(1e3 * (b - a), 3) for a, b in zip(t, t[1:])])  # push (async), pull (wait + import + sync), integrate
+        # host: push (async launch), pull (wait + import + sync), integrate; device: push kernels, wait, import
+        PROFILE_LOG.append([round(1e3 * (b - a), 3) for a, b in zip(t, t[1:])] + [round(x, 3) for x in engine.m.exchangeTimings()])
 
 
 def exchange_and_integrate(engine, world: int, dist=None):

@@ -273,6 +273,11 @@ class OccupancyVDBMapping:
     def updatePull(self, source_id: str):
         self._check(self._L.vdbm_update_pull(self._h, source_id.encode()))
 
+    def exchangeTimings(self):
+        out = np.zeros(3, dtype=np.float32)
+        self._check(self._L.vdbm_exchange_timings(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return [float(x) for x in out]  # push kernels, wait for peers, import + compaction (ms)
+
 
 def leaf_owner(origin, n_ranks: int) -> int:
     o = np.ascontiguousarray(origin, dtype=np.int32)
