@@ -26,10 +26,19 @@ open(os.path.join(pr, f"launch_shares_{tag}.csv"), "w").write("\n".join(lines) +
 print("\n".join(lines))
 
 # ---- full captures
-rep = os.path.join(go, f"prof_{tag}.ncu-rep")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-hdr, units, data = rows[0], rows[1], rows[2:]
+import glob
+hdr, units, data = None, None, []
+for rep in sorted(glob.glob(os.path.join(go, f"prof_{tag}_*.ncu-rep"))):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        continue
+    if hdr is None:
+        hdr, units = rows[0], rows[1]
+    # different kernels expose the same metric set with --set full; align by name
+    idxmap = {h: i for i, h in enumerate(rows[0])}
+    for r in rows[2:]:
+        data.append([r[idxmap[h]] if h in idxmap else "" for h in hdr])
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
