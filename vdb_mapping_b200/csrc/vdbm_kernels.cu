@@ -1294,17 +1294,33 @@ __global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t
   if (threadIdx.x < px.n_ranks) s_base[threadIdx.x] = s_count[threadIdx.x] ? atomicAdd(cursors + threadIdx.x, s_count[threadIdx.x]) : 0u;
   __syncthreads();
   const uint32_t n_here = min(256u, n - i0);
-  for (uint32_t t = threadIdx.x; t < n_here * 16u; t += 256u)
+  // 16 lanes per record, 16 records per pass, 16 passes. All loads of a thread are issued before its first store
+  // (otherwise every pass exposes one full load latency: the stores may alias the next loads for the compiler).
+  const uint32_t j = threadIdx.x & 15u, k0 = threadIdx.x >> 4;
+  const uint32_t region = parity * uint32_t(px.n_ranks) + uint32_t(px.rank);
+  uint64_t w[16];
+#pragma unroll
+  for (int it = 0; it < 16; ++it)
   {
-    const uint32_t k = t >> 4, j = t & 15u;
+    const uint32_t k = k0 + 16u * it;
+    w[it] = 0;
+    if (k < n_here)
+    {
+      const uint32_t e = s_entry[k];
+      w[it] = (j < 8) ? g.act[size_t(e) * 8 + j] : g.val[size_t(e) * 8 + (j - 8)];
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 16; ++it)
+  {
+    const uint32_t k = k0 + 16u * it;
+    if (k >= n_here) continue;
     const uint32_t e = s_entry[k], r = s_dst[k] >> 24, pos = s_base[r] + (s_dst[k] & 0xFFFFFFu);
-    uint64_t word;
-    if (j < 8) { word = g.act[size_t(e) * 8 + j]; g.act[size_t(e) * 8 + j] = 0; }
-    else       { word = g.val[size_t(e) * 8 + (j - 8)]; g.val[size_t(e) * 8 + (j - 8)] = 0; }
+    if (j < 8) g.act[size_t(e) * 8 + j] = 0;
+    else g.val[size_t(e) * 8 + (j - 8)] = 0;
     if (pos >= px.cap) { if (j == 0) atomicOr(&ctr->flags, kFlagExchangeOverflow); continue; }
-    const uint32_t region = parity * uint32_t(px.n_ranks) + uint32_t(px.rank);
     // 16 lanes x 8 bytes = one aligned 128-byte line in the owner's inbox
-    px.inbox[r][inboxMaskWord(region, px.cap, pos) + j] = word;
+    px.inbox[r][inboxMaskWord(region, px.cap, pos) + j] = w[it];
   }
   // keys: thread t writes the key of record t (records of one owner are contiguous per block -> coalesced runs)
   if (threadIdx.x < n_here)
@@ -1347,38 +1363,50 @@ __global__ void wait_peers_kernel(const unsigned long long* ctrl, int32_t n_rank
 __global__ void __launch_bounds__(256) pull_update_kernel(UpdateGrid g, const uint64_t* inbox, uint32_t cap, int32_t n_ranks, uint32_t parity,
                                                          const uint32_t* counts, Counters* ctr)
 {
-  // 16 lanes per record, grid-stride over all sender regions of this parity
+  // 16 lanes per record, kU records per pass and group (all loads of a pass are issued before the first RED, so a pass
+  // exposes one load latency, not kU), grid-stride over all sender regions of this parity
+  constexpr int kU = 4;
   const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, n_groups = (gridDim.x * blockDim.x) >> 4;
   const int j = threadIdx.x & 15;
   for (int s = 0; s < n_ranks; ++s)
   {
     const uint32_t cnt    = counts[s];
     const uint32_t region = parity * uint32_t(n_ranks) + uint32_t(s);
-    // all 32 lanes of a warp run the same number of iterations (ballot below needs the full warp)
-    const uint32_t iters = (cnt + n_groups - 1) / n_groups;
-    for (uint32_t it = 0; it < iters; ++it)
+    // all 32 lanes of a warp run the same number of passes (the ballot below needs the full warp)
+    const uint32_t passes = (cnt + n_groups * kU - 1) / (n_groups * kU);
+    for (uint32_t it = 0; it < passes; ++it)
     {
-      const uint32_t rec = it * n_groups + group;
-      const bool valid   = rec < cnt;
-      uint64_t word = 0, key = 0;
-      if (valid)
+      uint64_t word[kU], key[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
       {
-        word = inbox[inboxMaskWord(region, cap, rec) + j];
-        if (j == 0) key = inbox[inboxKeyWord(2u * uint32_t(n_ranks), region, cap, rec)];
+        const uint32_t rec = (it * kU + u) * n_groups + group;
+        word[u] = 0; key[u] = 0;
+        if (rec < cnt)
+        {
+          word[u] = inbox[inboxMaskWord(region, cap, rec) + j];
+          if (j == 0) key[u] = inbox[inboxKeyWord(2u * uint32_t(n_ranks), region, cap, rec)];
+        }
       }
-      const unsigned grp = 0xFFFFu << (threadIdx.x & 16);
-      const unsigned nz  = __ballot_sync(kFull, valid && j < 8 && word != 0) & grp;
-      uint32_t slot = kInvalid, lib = 0;
-      if (valid && nz && j == 0)
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
       {
-        const uint64_t bkey = brickKeyOfLeaf(key, lib);
-        slot                = brickFindOrInsert(g, bkey, ctr);
+        const uint32_t rec = (it * kU + u) * n_groups + group;
+        const bool valid   = rec < cnt;
+        const unsigned grp = 0xFFFFu << (threadIdx.x & 16);
+        const unsigned nz  = __ballot_sync(kFull, valid && j < 8 && word[u] != 0) & grp;
+        uint32_t slot = kInvalid, lib = 0;
+        if (valid && nz && j == 0)
+        {
+          const uint64_t bkey = brickKeyOfLeaf(key[u], lib);
+          slot                = brickFindOrInsert(g, bkey, ctr);
+        }
+        slot = __shfl_sync(kFull, slot, (threadIdx.x & 16));
+        lib  = __shfl_sync(kFull, lib, (threadIdx.x & 16));
+        if (slot == kInvalid || word[u] == 0) continue;
+        const size_t e = size_t(slot) * kBrickLeaves + lib;
+        redOr64((j < 8) ? g.act + e * 8 + j : g.val + e * 8 + (j - 8), word[u]);
       }
-      slot = __shfl_sync(kFull, slot, (threadIdx.x & 16));
-      lib  = __shfl_sync(kFull, lib, (threadIdx.x & 16));
-      if (slot == kInvalid || word == 0) continue;
-      const size_t e = size_t(slot) * kBrickLeaves + lib;
-      redOr64((j < 8) ? g.act + e * 8 + j : g.val + e * 8 + (j - 8), word);
     }
   }
 }

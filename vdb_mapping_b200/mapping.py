@@ -264,8 +264,8 @@ class OccupancyVDBMapping:
         self._check(self._L.vdbm_exchange_create(self._h, rank, n_ranks, capacity_records_per_sender, buf))
         return buf.raw
 
-    def exchangeConnect(self, all_handles: bytes):
-        self._check(self._L.vdbm_exchange_connect(self._h, C.c_char_p(all_handles)))
+    def exchangeConnect(self, all_handles: bytes | None):
+        self._check(self._L.vdbm_exchange_connect(self._h, C.c_char_p(all_handles) if all_handles else None))
 
     def updatePush(self, source_id: str):
         self._check(self._L.vdbm_update_push(self._h, source_id.encode()))
