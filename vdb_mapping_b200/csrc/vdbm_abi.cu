@@ -333,16 +333,18 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     cudaFree(m->d_rays); cudaFree(m->d_segs); cudaFree(m->d_long); cudaFree(m->d_sort); cudaFree(m->d_sort_tmp);
     m->d_rays = nullptr; m->d_segs = nullptr; m->d_long = nullptr; m->d_sort = nullptr; m->d_sort_tmp = nullptr;
     m->rays_cap = 0;
+    // grow geometrically: cloud sizes fluctuate from scan to scan and every reallocation synchronises the device
+    const size_t rc = size_t(n) + n / 4 + 4096;
     // one segment per ray + a pool of extra segments for long rays (a ray that finds the pool empty stays whole)
-    const size_t seg_cap = n + 4 * n + 65536;
-    CU_TRY(m, cudaMalloc(&m->d_rays, n * sizeof(RayRec)));
+    const size_t seg_cap = rc + 4 * rc + 65536;
+    CU_TRY(m, cudaMalloc(&m->d_rays, rc * sizeof(RayRec)));
     CU_TRY(m, cudaMalloc(&m->d_segs, seg_cap * sizeof(SegRec)));
-    CU_TRY(m, cudaMalloc(&m->d_long, n * 2 * sizeof(uint32_t)));
+    CU_TRY(m, cudaMalloc(&m->d_long, rc * 2 * sizeof(uint32_t)));
     CU_TRY(m, cudaMalloc(&m->d_sort, seg_cap * 4 * sizeof(uint32_t)));
     m->sort_tmp_bytes = sortRaysByLength(nullptr, 0, m->d_sort, m->d_sort + seg_cap, m->d_sort + 2 * seg_cap, m->d_sort + 3 * seg_cap,
                                          uint32_t(seg_cap), m->stream);
     CU_TRY(m, cudaMalloc(&m->d_sort_tmp, m->sort_tmp_bytes ? m->sort_tmp_bytes : 8));
-    m->rays_cap = n;
+    m->rays_cap = rc;
     m->seg_cap  = seg_cap;
   }
   a.rays      = m->d_rays;
@@ -445,8 +447,9 @@ int stagePoints(vdbm_map* m, const void* points, uint64_t n, uint64_t stride)
     cudaFree(m->d_points);
     m->d_points   = nullptr;
     m->points_cap = 0;
-    CU_TRY(m, cudaMalloc(&m->d_points, bytes));
-    m->points_cap = bytes;
+    const size_t want = bytes + bytes / 4 + 65536; // geometric growth: no reallocation for slightly larger clouds
+    CU_TRY(m, cudaMalloc(&m->d_points, want));
+    m->points_cap = want;
   }
   if (bytes) CU_TRY(m, cudaMemcpyAsync(m->d_points, points, bytes, cudaMemcpyHostToDevice, m->stream));
   return VDBM_OK;
@@ -471,8 +474,9 @@ int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
     cudaFree(s.d_change);
     s.d_change   = nullptr;
     s.change_cap = 0;
-    CU_TRY(m, cudaMalloc(&s.d_change, size_t(n) * sizeof(LeafRecord)));
-    s.change_cap = n;
+    const uint32_t want = n + n / 4 + 1024;
+    CU_TRY(m, cudaMalloc(&s.d_change, size_t(want) * sizeof(LeafRecord)));
+    s.change_cap = want;
   }
   if (m->resolved_cap < n)
   {
@@ -1199,8 +1203,9 @@ int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, u
     cudaFree(m->d_part);
     m->d_part   = nullptr;
     m->part_cap = 0;
-    CU_TRY(m, cudaMalloc(&m->d_part, size_t(n) * sizeof(LeafRecord)));
-    m->part_cap = n;
+    const size_t want = size_t(n) + n / 4 + 1024;
+    CU_TRY(m, cudaMalloc(&m->d_part, want * sizeof(LeafRecord)));
+    m->part_cap = want;
   }
   *d_records = m->d_part;
   TempBuf d(m->stream);
