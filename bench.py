@@ -124,7 +124,21 @@ def measured_traffic(kernel: str):
 
 
 def workload_cfg(name: str) -> int:
-    return {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4}[name]
+    """cfg5 = cfg2's scan sequence driven through the whole wrapper-side pipeline: change grid of every
+    updateMap read back, every 10th scan a sparse and a full-leaf map section of a 20x20x6 m box around the sensor."""
+    return {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 2}[name]
+
+
+def section_box(origin, resolution: float):
+    """Index bounding box (inclusive) of the 20 x 20 x 6 m box centred on the sensor."""
+    half = np.array([10.0, 10.0, 3.0])
+    lo = np.floor((np.asarray(origin) - half) / resolution).astype(np.int32)
+    hi = np.floor((np.asarray(origin) + half) / resolution).astype(np.int32)
+    return lo, hi
+
+
+def workload_name(args, c) -> str:
+    return c.name if args.workload != "cfg5" else "cfg5_" + c.name.split("_", 1)[1] + "_change+sections"
 
 
 def alg_bytes(n_pts: int, leaves: int, change: bool = False) -> int:
@@ -156,13 +170,24 @@ def run_reference(args, rank, world):
         lo = (k % stride) * per
         pts = np.ascontiguousarray(pts[lo:lo + per])
         clouds.append((pts, origin))
-    for k in range(args.warmup):
+    mixed = args.workload == "cfg5"
+
+    def step(k):
         m.insertPointCloud(*clouds[k], "s")
+        if mixed:
+            m.exportLastChange("s")
+            if k % 10 == 9:
+                lo, hi = section_box(clouds[k][1], c.resolution)
+                m.getMapSectionUpdateGrid(lo, hi, full=False)
+                m.getMapSectionGrid(lo, hi, full=True)
+
+    for k in range(args.warmup):
+        step(k)
     s0 = m.stats()
     t0 = time.perf_counter()
     rays = 0
     for k in range(args.warmup, args.warmup + args.steps):
-        m.insertPointCloud(*clouds[k], "s")
+        step(k)
         rays += clouds[k][0].shape[0]
     dt = time.perf_counter() - t0
     s1 = m.stats()
@@ -172,7 +197,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 DDA + f32 log-odds", "data": "synthetic",
-        "config": {"workload": c.name, "description": c.description, "resolution_m": c.resolution, "max_range_m": c.max_range,
+        "config": {"workload": workload_name(args, c), "description": c.description, "resolution_m": c.resolution, "max_range_m": c.max_range,
                    "points_per_scan": c.n_points, "sample": sample},
         "voxel_updates_per_sec": (s1["voxel_updates"] - s0["voxel_updates"]) / dt,
         "visits_per_sec": (s1["visits"] - s0["visits"]) / dt,

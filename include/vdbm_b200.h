@@ -155,6 +155,40 @@ int vdbm_section_apply_update(vdbm_map* map, const int32_t bbmin[3], const int32
  * map has a leaf. */
 int vdbm_section_apply_grid(vdbm_map* map, uint64_t n_leaves, const int32_t* origins /*[n][3]*/, const uint64_t* active /*[n][8]*/,
                             const float* values /*[n][512]*/, int replicate_tile_quirk);
+/* ---- remote-mapping deltas: createUpdate / applyUpdate -------------------------------------
+ * BASELINE north_star names createUpdate/applyUpdate with a "reduction level"; the reference revision under
+ * /root/reference has no such members (its wrapper ships whole grids through gridToByteArray V:1310-1338), so the levels
+ * are defined here from the grids the reference DOES produce:
+ *   level 0  the source's raw update grid (InputSource::update_grid V:97)        -> apply = updateMap V:731-792
+ *   level 1  the change ("overwrite") grid updateMap returned V:733,772,780     -> apply = every active voxel forced
+ *            occupied (value bit) / free with setNodeToOccupied / setNodeToFree O:118-129
+ *   level 2  the REDUCED update: the end voxel of every ray of the source's last accumulate call (active; value = the
+ *            ray was not range-clipped, V:533-536) + that scan's origin. castRayIntoGrid V:550-566 depends only on the
+ *            two voxel indices, so the receiver re-raycasts the set from the origin and obtains the sender's update grid
+ *            bit for bit: ~one voxel per ray crosses the wire instead of hundreds.
+ * vdbm_update_create: level 0/2 must be called between accumulate and integrate, level 1 after vdbm_integrate(map, 1)
+ * or vdbm_update_map. origin_out (may be NULL) receives the origin of the source's last accumulate. */
+int vdbm_update_create(vdbm_map* map, const char* source_id, int level, vdbm_leafset** out, double origin_out[3]);
+/* Apply such a grid to THIS map (library-owned scratch grid; no input source involved). origin is required for level 2.
+ * If change != NULL it receives the change grid of the updateMap run (levels 0 and 2; empty for level 1). */
+int vdbm_update_apply(vdbm_map* map, int level, uint64_t n_leaves, const int32_t* origins /*[n][3]*/, const uint64_t* active /*[n][8]*/,
+                      const uint64_t* value /*[n][8]*/, const double origin[3], vdbm_leafset** change);
+
+/* ---- direct map edits and artificial areas ---------------------------------------------------- */
+/* addPointsToGrid V:431-447 (occupied != 0: value = max log-odds, active) / removePointsFromGrid V:413-429 (value = min
+ * log-odds, inactive) for the voxel Coord::floor(point / resolution) of every point (host buffer, pcl::PointXYZ layout). */
+int vdbm_points_set(vdbm_map* map, const void* points, uint64_t n, uint64_t stride_bytes, int occupied);
+/* addArtificialAreas V:1175-1236: restoreMapIntegrity, then one wall per polygon edge (closing edge included), each wall
+ * = castRayIntoGrid(start + (0,0,i), end + (0,0,i)) for i in [(int)(negative_height/res), (int)(positive_height/res)) into
+ * the artificial-area grid. xyz holds sum(counts) world points (x, y, z). From then on every updateMap ends by forcing
+ * those voxels active (V:785-789). */
+int vdbm_artificial_areas_add(vdbm_map* map, uint64_t n_polygons, const uint32_t* counts, const double* xyz, double negative_height,
+                              double positive_height);
+/* restoreMapIntegrity V:1152-1166: active = (value > thres_max) for every artificial-area voxel, then the grid is cleared. */
+int vdbm_map_integrity_restore(vdbm_map* map);
+/* the artificial-area grid (m_artificial_area_grid V:1493) as a bool leaf set */
+int vdbm_artificial_export(vdbm_map* map, vdbm_leafset** out);
+
 /* GridT::Accessor::getValue / isValueOn for one voxel (tests/mapping.cpp:27-29). */
 int vdbm_probe(vdbm_map* map, const int32_t xyz[3], float* value, int32_t* active);
 

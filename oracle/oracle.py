@@ -68,6 +68,12 @@ def lib() -> C.CDLL:
         L.vdbo_apply_section_grid.argtypes = [vp, C.c_uint64, i32p, u64p, f32p, C.c_int]
         L.vdbo_update_clear.restype = C.c_int
         L.vdbo_update_clear.argtypes = [vp, C.c_char_p]
+        L.vdbo_update_apply.restype = C.c_int
+        L.vdbo_update_apply.argtypes = [vp, C.c_char_p, C.c_int, C.c_uint64, i32p, u64p, u64p, C.POINTER(dbl)]
+        L.vdbo_last_origin.argtypes = [vp, C.c_char_p, C.POINTER(dbl)]
+        L.vdbo_points_set.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int]
+        L.vdbo_add_artificial_areas.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(dbl), dbl, dbl]
+        L.vdbo_restore_map_integrity.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -167,6 +173,7 @@ class OracleOccupancyVDBMapping:
         origins = np.zeros((n, 3), dtype=np.int32)
         active = np.zeros((n, 8), dtype=np.uint64)
         is_float = kind in (0, 4)
+
         valmask = None if is_float else np.zeros((n, 8), dtype=np.uint64)
         values = np.zeros((n, 512), dtype=np.float32) if is_float else None
         self._L.vdbo_export_fetch(
@@ -225,3 +232,48 @@ class OracleOccupancyVDBMapping:
                                           o.ctypes.data_as(C.POINTER(C.c_int32)),
                                           a.ctypes.data_as(C.POINTER(C.c_uint64)),
                                           v.ctypes.data_as(C.POINTER(C.c_uint64)))
+
+    # ---- remote-mapping deltas: createUpdate / applyUpdate ----
+    def createUpdate(self, source_id: str, level: int):
+        """level 0: the source's raw update grid; 1: the change ("overwrite") grid of the last integrate; 2: the reduced
+        update of the last accumulate (ray end voxels, value = hit). Returns (LeafSet, origin of that accumulate)."""
+        o = np.zeros(3, dtype=np.float64)
+        self._L.vdbo_last_origin(self._h, source_id.encode(), _dp(o))
+        if level == 0:
+            return self._export(1, source_id), o
+        if level == 1:
+            return self._export(2, source_id), o
+        if level == 2:
+            return self._export(1, source_id, full=2), o
+        raise ValueError(level)
+
+    def applyUpdate(self, source_id: str, level: int, update: "LeafSet", origin=None) -> int:
+        i32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+        o = np.ascontiguousarray(update.origins, dtype=np.int32)
+        a = np.ascontiguousarray(update.active, dtype=np.uint64)
+        v = np.ascontiguousarray(update.valmask, dtype=np.uint64)
+        og = np.ascontiguousarray(origin if origin is not None else [0, 0, 0], dtype=np.float64)
+        return self._L.vdbo_update_apply(self._h, source_id.encode(), level, o.shape[0], o.ctypes.data_as(i32p),
+                                         a.ctypes.data_as(u64p), v.ctypes.data_as(u64p), _dp(og))
+
+    # ---- direct map edits + artificial areas (SURVEY.md 8f N4) ----
+    def addPointsToGrid(self, points):
+        p = _pts16(points)
+        self._L.vdbo_points_set(self._h, p.ctypes.data, p.shape[0], 16, 1)
+
+    def removePointsFromGrid(self, points):
+        p = _pts16(points)
+        self._L.vdbo_points_set(self._h, p.ctypes.data, p.shape[0], 16, 0)
+
+    def addArtificialAreas(self, polygons, negative_height: float, positive_height: float):
+        """polygons: list of (k_i, 3) arrays of world points (VDBMapping.hpp:1175-1236)."""
+        counts = np.asarray([len(p) for p in polygons], dtype=np.uint32)
+        xyz = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64)[:, :3] for p in polygons]) if len(polygons) else np.zeros((0, 3)))
+        self._L.vdbo_add_artificial_areas(self._h, len(polygons), counts.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(xyz),
+                                          float(negative_height), float(positive_height))
+
+    def restoreMapIntegrity(self):
+        self._L.vdbo_restore_map_integrity(self._h)
+
+    def exportArtificialAreaGrid(self) -> LeafSet:
+        return self._export(5)

@@ -346,6 +346,9 @@ struct Accessor
 
 // bool-tree write ops used by the raycast (V:535, V:563)
 inline void setActiveStateOn(Accessor<BoolTree>& acc, const Coord& c) { acc.touchLeaf(c)->vmask.setOn(leafOffset(c)); }
+// GridT::Accessor::setActiveState(xyz, true) on the float map (V:788, V:1082): tiles are inactive background, so a
+// child is created down to the leaf, the value is left alone
+inline void setActiveStateOn(Accessor<FloatTree>& acc, const Coord& c) { acc.touchLeaf(c)->vmask.setOn(leafOffset(c)); }
 inline void setValueOnTrue(Accessor<BoolTree>& acc, const Coord& c)
 {
   BoolLeaf* l = acc.touchLeaf(c);
@@ -464,6 +467,11 @@ struct Source
   double max_range;
   std::unique_ptr<BoolTree> update_grid;
   std::unique_ptr<BoolTree> last_change; // what updateMap returned for this source last time
+  // "reduced" update of the last accumulateUpdate call (level 2): the end voxel of every ray, active,
+  // value = the ray delivered a hit (was not clipped), plus the scan origin. castRayIntoGrid depends only on the two
+  // voxel indices, so re-raycasting this set from the origin reproduces that call's update grid exactly.
+  std::unique_ptr<BoolTree> reduced;
+  double last_origin[3] = {0, 0, 0};
 };
 
 // VDBMapping<float,Config> + OccupancyVDBMapping node ops, polymorphic like the reference
@@ -486,6 +494,10 @@ struct MappingBase
   virtual ~MappingBase() {}
   virtual bool updateFreeNode(float&, bool&) { return false; }
   virtual bool updateOccupiedNode(float&, bool&) { return false; }
+  virtual bool setNodeToFree(float&, bool&) { return false; }     // V:1474
+  virtual bool setNodeToOccupied(float&, bool&) { return false; } // V:1475
+  virtual bool setNodeState(float&, bool&) { return false; }      // V:1476
+  std::unique_ptr<BoolTree> m_artificial_area_grid{new BoolTree(false)}; // V:132,1493
 
   // V:174-186
   void resetMap()
@@ -572,7 +584,7 @@ struct MappingBase
 
   // V:466-539 (fast_mode is out of scope)
   bool raycastPointCloud(const uint8_t* pts, size_t n, size_t stride, const double origin[3], double raycast_range,
-                         Accessor<BoolTree>& update_acc)
+                         Accessor<BoolTree>& update_acc, Accessor<BoolTree>* reduced_acc = nullptr)
   {
     if (!m_config_set) return false; // V:478-482
     const Coord ray_origin_index = worldToIndex(origin);
@@ -605,6 +617,11 @@ struct MappingBase
       const Coord ray_end_index = worldToIndex(end); // V:519
       castRayIntoGrid(ray_origin_index, ray_end_index, update_acc); // V:530
       if (!max_range_ray) setValueOnTrue(update_acc, ray_end_index); // V:533-536
+      if (reduced_acc)
+      {
+        if (max_range_ray) setActiveStateOn(*reduced_acc, ray_end_index);
+        else setValueOnTrue(*reduced_acc, ray_end_index);
+      }
     }
     return true;
   }
@@ -618,12 +635,110 @@ struct MappingBase
     Accessor<BoolTree> acc(*s.update_grid);
     if (s.max_range > 0) // V:331
     {
-      if (!raycastPointCloud(pts, n, stride, origin, s.max_range, acc)) return 2;
+      s.reduced.reset(new BoolTree(false));
+      for (int a = 0; a < 3; ++a) s.last_origin[a] = origin[a];
+      Accessor<BoolTree> racc(*s.reduced);
+      const uint64_t visits = stats.visits;
+      if (!raycastPointCloud(pts, n, stride, origin, s.max_range, acc, &racc)) return 2;
+      (void)visits;
     }
     return 0;
   }
 
-  // V:731-792 (artificial areas V:785-789: grid always empty here, out of scope)
+  // Receiver side of a level-2 (reduced) update: re-raycast every end voxel from the transmitted origin
+  // (castRayIntoGrid V:550-566 + the end-point rule V:533-536) into `acc`.
+  void raycastReducedGrid(const BoolTree& reduced, const double origin[3], Accessor<BoolTree>& acc)
+  {
+    const Coord o = worldToIndex(origin);
+    reduced.forEachLeaf([&](const BoolLeaf& rl) {
+      for (uint32_t n = rl.vmask.findNextOn(0); n < 512; n = rl.vmask.findNextOn(n + 1))
+      {
+        Coord l = leafOffsetToLocal(n);
+        Coord c(rl.origin[0] + l[0], rl.origin[1] + l[1], rl.origin[2] + l[2]);
+        ++stats.rays;
+        castRayIntoGrid(o, c, acc);
+        if (rl.buf.isOn(n)) setValueOnTrue(acc, c);
+      }
+    });
+  }
+
+  // Level-1 apply ("overwrite" grid = the change grid updateMap returned): every active voxel is forced to the
+  // occupied (value true) or free (value false) state with the reference's own node ops, V:1474-1475 / O:118-129.
+  void overwriteMap(const BoolTree& grid)
+  {
+    Accessor<FloatTree> acc(*m_vdb_grid);
+    auto occ = [&](float& v, bool& a) { setNodeToOccupied(v, a); };
+    auto fre = [&](float& v, bool& a) { setNodeToFree(v, a); };
+    grid.forEachLeaf([&](const BoolLeaf& gl) {
+      for (uint32_t n = gl.vmask.findNextOn(0); n < 512; n = gl.vmask.findNextOn(n + 1))
+      {
+        Coord l = leafOffsetToLocal(n);
+        Coord c(gl.origin[0] + l[0], gl.origin[1] + l[1], gl.origin[2] + l[2]);
+        if (gl.buf.isOn(n)) modifyValueAndActiveState(acc, c, occ);
+        else modifyValueAndActiveState(acc, c, fre);
+      }
+    });
+  }
+
+  // addPointsToGrid V:431-447 / removePointsFromGrid V:413-429: Coord::floor(grid->worldToIndex(pt)) (the plain
+  // transform, NOT the fmod variant of V:612-631), then setNodeToOccupied / setNodeToFree.
+  void setPoints(const uint8_t* pts, size_t n, size_t stride, bool occupied)
+  {
+    Accessor<FloatTree> acc(*m_vdb_grid);
+    auto occ = [&](float& v, bool& a) { setNodeToOccupied(v, a); };
+    auto fre = [&](float& v, bool& a) { setNodeToFree(v, a); };
+    for (size_t i = 0; i < n; ++i)
+    {
+      float p[3];
+      std::memcpy(p, pts + i * stride, sizeof(p));
+      if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue; // undefined in the reference
+      Coord c;
+      for (int a = 0; a < 3; ++a) c[a] = int32_t(std::floor(double(p[a]) * m_inv_resolution));
+      if (occupied) modifyValueAndActiveState(acc, c, occ);
+      else modifyValueAndActiveState(acc, c, fre);
+    }
+  }
+
+  // V:1152-1166
+  void restoreMapIntegrity()
+  {
+    Accessor<FloatTree> acc(*m_vdb_grid);
+    auto restore = [&](float& v, bool& a) { setNodeState(v, a); };
+    m_artificial_area_grid->forEachLeaf([&](const BoolLeaf& gl) {
+      for (uint32_t n = gl.vmask.findNextOn(0); n < 512; n = gl.vmask.findNextOn(n + 1))
+      {
+        Coord l = leafOffsetToLocal(n);
+        modifyValueAndActiveState(acc, Coord(gl.origin[0] + l[0], gl.origin[1] + l[1], gl.origin[2] + l[2]), restore);
+      }
+    });
+    m_artificial_area_grid.reset(new BoolTree(false));
+  }
+  // V:1219-1236; start/end are world points
+  void addArtificialWall(const double start[3], const double end[3], double negative_height, double positive_height)
+  {
+    Accessor<BoolTree> acc(*m_artificial_area_grid);
+    const Coord s = worldToIndex(start), e = worldToIndex(end);
+    const int negative_index = (int)(negative_height / m_resolution);
+    const int positive_index = (int)(positive_height / m_resolution);
+    const uint64_t visits = stats.visits;
+    for (int i = negative_index; i < positive_index; ++i)
+      castRayIntoGrid(Coord(s[0], s[1], s[2] + i), Coord(e[0], e[1], e[2] + i), acc);
+    stats.visits = visits; // walls are not scan rays
+  }
+  // V:1175-1206; polygons: n_poly polygons, counts[p] points each, xyz triples (the 4th homogeneous component is unused)
+  void addArtificialAreas(size_t n_poly, const uint32_t* counts, const double* xyz, double negative_height, double positive_height)
+  {
+    restoreMapIntegrity();
+    size_t base = 0;
+    for (size_t p = 0; p < n_poly; ++p)
+    {
+      for (uint32_t i = 0; i < counts[p]; ++i)
+        addArtificialWall(xyz + 3 * (base + i), xyz + 3 * (base + (i + 1) % counts[p]), negative_height, positive_height);
+      base += counts[p];
+    }
+  }
+
+  // V:731-792
   std::unique_ptr<BoolTree> updateMap(const BoolTree& temp_grid)
   {
     auto change = std::make_unique<BoolTree>(false);
@@ -676,6 +791,14 @@ struct MappingBase
           if (ul.buf.isOn(n)) setValueOnTrue(change_acc, c);      // V:772
           else setActiveStateOn(change_acc, c);                   // V:780
         }
+      }
+    });
+    // V:785-789: every artificial-area voxel is forced active (a missing leaf is created with background values)
+    m_artificial_area_grid->forEachLeaf([&](const BoolLeaf& gl) {
+      for (uint32_t n = gl.vmask.findNextOn(0); n < 512; n = gl.vmask.findNextOn(n + 1))
+      {
+        Coord l = leafOffsetToLocal(n);
+        setActiveStateOn(acc, Coord(gl.origin[0] + l[0], gl.origin[1] + l[1], gl.origin[2] + l[2]));
       }
     });
     return change;
@@ -737,6 +860,24 @@ struct OccupancyMapping : MappingBase
       active = true;
       if (voxel_value > m_max_logodds) voxel_value = m_max_logodds;
     }
+    return true;
+  }
+  // O:118-135
+  bool setNodeToFree(float& voxel_value, bool& active) override
+  {
+    voxel_value = m_min_logodds;
+    active      = false;
+    return true;
+  }
+  bool setNodeToOccupied(float& voxel_value, bool& active) override
+  {
+    voxel_value = m_max_logodds;
+    active      = true;
+    return true;
+  }
+  bool setNodeState(float& voxel_value, bool& active) override
+  {
+    active = voxel_value > m_logodds_thres_max;
     return true;
   }
 };
@@ -1096,10 +1237,12 @@ int64_t vdbo_export_prepare(void* hh, int kind, const char* source, const int32_
       auto it = m.m_input_sources.find(source ? source : "");
       if (it == m.m_input_sources.end()) return -1;
       const vo::BoolTree* t = (kind == 1) ? it->second->update_grid.get() : it->second->last_change.get();
+      if (kind == 1 && full == 2) t = it->second->reduced.get(); // level-2 reduced update of the last accumulate
       if (!t) { h->last_export = vo::LeafSet(); break; }
       h->last_export = vo::exportBool(*t);
       break;
     }
+    case 5: h->last_export = vo::exportBool(*m.m_artificial_area_grid); break;
     case 3:
     case 4:
       h->last_export = vo::mapSection(*m.m_vdb_grid, vo::Coord(bbmin[0], bbmin[1], bbmin[2]),
@@ -1171,6 +1314,64 @@ int vdbo_apply_section_grid(void* hh, uint64_t n, const int32_t* origins, const 
   vo::applySectionGrid(*m.m_vdb_grid, n, origins, active, values, tile_quirk != 0);
   return 0;
 }
+
+static void leafsetToTree(vo::BoolTree& t, uint64_t n, const int32_t* origins, const uint64_t* active, const uint64_t* valmask)
+{
+  vo::Accessor<vo::BoolTree> acc(t);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    bool any = false;
+    for (int w = 0; w < 8; ++w) any |= (active[8 * i + w] != 0);
+    if (!any) continue;
+    vo::BoolLeaf* l = acc.touchLeaf(vo::Coord(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]));
+    for (int w = 0; w < 8; ++w)
+    {
+      l->vmask.w[w] |= active[8 * i + w];
+      l->buf.w[w] |= valmask[8 * i + w];
+    }
+  }
+}
+
+// createUpdate's counterpart on the receiving map. level 0: the grid is a raw update grid -> updateMap;
+// level 1: it is an overwrite (change) grid -> overwriteMap; level 2: it is a reduced grid -> re-raycast from `origin`,
+// then updateMap. The change grid of levels 0/2 is kept as the named source's last change grid.
+int vdbo_update_apply(void* hh, const char* source, int level, uint64_t n, const int32_t* origins, const uint64_t* active,
+                      const uint64_t* valmask, const double* origin)
+{
+  auto& m = static_cast<vo::Handle*>(hh)->map;
+  auto it = m.m_input_sources.find(source ? source : "");
+  if (it == m.m_input_sources.end()) return 1;
+  vo::BoolTree in(false);
+  leafsetToTree(in, n, origins, active, valmask);
+  if (level == 0) it->second->last_change = m.updateMap(in);
+  else if (level == 1) m.overwriteMap(in);
+  else if (level == 2)
+  {
+    vo::BoolTree full(false);
+    vo::Accessor<vo::BoolTree> acc(full);
+    m.raycastReducedGrid(in, origin, acc);
+    it->second->last_change = m.updateMap(full);
+  }
+  else return 2;
+  return 0;
+}
+void vdbo_last_origin(void* hh, const char* source, double* out)
+{
+  auto& m = static_cast<vo::Handle*>(hh)->map;
+  auto it = m.m_input_sources.find(source ? source : "");
+  if (it == m.m_input_sources.end()) return;
+  for (int a = 0; a < 3; ++a) out[a] = it->second->last_origin[a];
+}
+// addPointsToGrid (occupied != 0) / removePointsFromGrid
+void vdbo_points_set(void* hh, const void* pts, uint64_t n, uint64_t stride, int occupied)
+{
+  static_cast<vo::Handle*>(hh)->map.setPoints(static_cast<const uint8_t*>(pts), n, stride, occupied != 0);
+}
+void vdbo_add_artificial_areas(void* hh, uint64_t n_poly, const uint32_t* counts, const double* xyz, double negative_height, double positive_height)
+{
+  static_cast<vo::Handle*>(hh)->map.addArtificialAreas(n_poly, counts, xyz, negative_height, positive_height);
+}
+void vdbo_restore_map_integrity(void* hh) { static_cast<vo::Handle*>(hh)->map.restoreMapIntegrity(); }
 
 // empty one source's update grid without applying it (models vdbm_update_partition, which hands the leaves over)
 int vdbo_update_clear(void* hh, const char* source)

@@ -331,3 +331,155 @@ def test_long_rays_are_split_into_segments_exactly(seg_len, monkeypatch):
         g.integrateUpdate(); o.integrateUpdate()
     assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
     assert g.stats()["visits"] == o.stats()["visits"]
+
+
+# ---- remote-mapping deltas: createUpdate / applyUpdate ---------------------------------------
+@pytest.mark.parametrize("cfg", [CFG_GTEST, CFG_ROS], ids=["gtest_cfg", "ros_cfg"])
+def test_create_and_apply_update_levels(cfg):
+    """Sender GPU vs sender oracle: the three update kinds are identical. Receiver GPUs fed with the GPU-made updates
+    vs receiver oracles fed with the oracle-made ones: maps and change grids identical; the level-2 (reduced) receiver
+    additionally equals the SENDER's map bit for bit."""
+    from vdb_mapping_b200 import scans
+    gs, os_ = _pair(0.1, 4.0, cfg)
+    g0, o0 = _pair(0.1, 4.0, cfg)
+    g1, o1 = _pair(0.1, 4.0, cfg)
+    g2, o2 = _pair(0.1, 4.0, cfg)
+    for k in range(6):
+        pts, origin = scans.small_scan(300 + k, n=3000, scale=2.5)
+        origin = origin + np.array([0.137 * k, 0.061 * k, 0.013 * k])
+        gs.accumulateUpdate(pts, origin, "s"); os_.accumulateUpdate(pts, origin, "s")
+        raw_g, og = gs.createUpdate("s", 0); raw_o, oo = os_.createUpdate("s", 0)
+        red_g, og2 = gs.createUpdate("s", 2); red_o, _ = os_.createUpdate("s", 2)
+        assert np.array_equal(og, origin) and np.array_equal(og2, origin) and np.array_equal(oo, origin)
+        assert_leafsets_equal(raw_g, raw_o, f"raw update {k}")
+        assert_leafsets_equal(red_g, red_o, f"reduced update {k}")
+        assert_leafsets_equal(gs.exportUpdateGrid("s"), raw_o, "createUpdate must not disturb the accumulated grid")
+        gs.integrateUpdate(keep_change=True); os_.integrateUpdate()
+        chg_g, _ = gs.createUpdate("s", 1); chg_o, _ = os_.createUpdate("s", 1)
+        assert_leafsets_equal(chg_g, chg_o, f"overwrite grid {k}")
+        c0 = g0.applyUpdate(0, raw_g, want_change=True); o0.applyUpdate("s", 0, raw_o)
+        assert_leafsets_equal(c0, o0.exportLastChange("s"), f"level-0 change {k}")
+        g1.applyUpdate(1, chg_g); o1.applyUpdate("s", 1, chg_o)
+        c2 = g2.applyUpdate(2, red_g, origin=og2, want_change=True); o2.applyUpdate("s", 2, red_o, origin)
+        assert_leafsets_equal(c2, o2.exportLastChange("s"), f"level-2 change {k}")
+        assert_leafsets_equal(c2, chg_g, f"level-2 receiver change == sender change {k}")
+        assert_leafsets_equal(g1.exportMap(), o1.exportMap(), f"level-1 receiver map {k}")
+    sender = gs.exportMap()
+    assert_leafsets_equal(sender, os_.exportMap(), "sender map")
+    assert_leafsets_equal(g0.exportMap(), sender, "level-0 receiver == sender")
+    assert_leafsets_equal(g2.exportMap(), sender, "level-2 receiver == sender")
+    assert_leafsets_equal(g2.exportMap(), o2.exportMap(), "level-2 receiver vs oracle")
+
+
+def test_reduced_update_full_size_roundtrip():
+    """cfg1 at full size: sender -> reduced update -> receiver, three scans. The receiver's map equals the sender's, and
+    the reduced update carries < 1/50 of the raw update's voxels."""
+    from vdb_mapping_b200 import scans
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    c = scans.CONFIGS[1]
+    maps = []
+    for _ in range(2):
+        m = OccupancyVDBMapping(c.resolution)
+        m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+        m.addInputSource("s", c.max_range)
+        maps.append(m)
+    snd, rcv = maps
+    for k in range(3):
+        pts, origin = scans.make_scan(1, k)
+        snd.accumulateUpdate(pts, origin, "s")
+        raw_voxels = snd.stats()["last_touched_leaves"]
+        red, o = snd.createUpdate("s", 2)
+        assert 0 < popcount64(red.active) <= pts.shape[0]
+        snd.integrateUpdate(keep_change=False)
+        rcv.applyUpdate(2, red, origin=o)
+        assert raw_voxels > 0
+        assert snd.stats()["last_voxel_updates"] == rcv.stats()["last_voxel_updates"]
+        assert popcount64(red.active) * 50 < snd.stats()["last_voxel_updates"]
+    assert_leafsets_equal(rcv.exportMap(), snd.exportMap(), "receiver map after 3 reduced updates")
+
+
+def test_reduced_update_requires_last_accumulate_and_handles_empty():
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping, VdbmError
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, CFG_ROS, sources=("a", "b"))
+    with pytest.raises(VdbmError):
+        g.createUpdate("a", 2)  # nothing accumulated yet
+    pts, origin = scans.small_scan(1, n=500, scale=2.0)
+    g.accumulateUpdate(pts, origin, "a")
+    with pytest.raises(VdbmError):
+        g.createUpdate("b", 2)  # the reduced update belongs to source a's accumulate
+    red, og = g.createUpdate("a", 2)
+    assert len(red) > 0
+    # all-NaN cloud: empty reduced update, applying it is a no-op
+    nan = np.full((10, 3), np.nan, dtype=np.float32)
+    g.integrateUpdate()
+    g.accumulateUpdate(nan, origin, "a")
+    red2, _ = g.createUpdate("a", 2)
+    assert len(red2) == 0
+    r = OccupancyVDBMapping(0.1); r.setConfig(4.0, *CFG_ROS)
+    r.applyUpdate(2, red2, origin=origin)
+    assert r.mapLeafCount() == 0
+    r.applyUpdate(2, red, origin=og)
+    assert r.mapLeafCount() > 0
+
+
+# ---- direct edits + artificial areas (SURVEY.md 8f N4; the tail of updateMap V:785-789) ---------------------------
+def test_add_and_remove_points():
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, CFG_ROS)
+    rng = np.random.default_rng(11)
+    add = rng.uniform(-3, 3, size=(5000, 3)).astype(np.float32)
+    add[::25] = np.round(add[::25] * 10) / 10
+    add[7] = np.nan
+    for m in (g, o):
+        m.addPointsToGrid(add)
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "after addPointsToGrid")
+    pts, origin = scans.small_scan(5, n=2000, scale=2.5)
+    for m in (g, o):
+        m.insertPointCloud(pts, origin, "s")
+    rem = np.concatenate([add[:1500], rng.uniform(-3, 3, size=(1500, 3)).astype(np.float32)])
+    for m in (g, o):
+        m.removePointsFromGrid(rem)
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "after removePointsFromGrid")
+    for m in (g, o):
+        m.insertPointCloud(pts, origin + 0.05, "s")
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "scan after edits")
+
+
+@pytest.mark.parametrize("cfg", [CFG_GTEST, CFG_ROS, (0.7, 0.4, 0.12, 0.45)], ids=["gtest_cfg", "ros_cfg", "neg_thres_max"])
+def test_artificial_areas(cfg):
+    """addArtificialAreas -> artificial grid; every updateMap then re-activates the walls; restoreMapIntegrity. The third
+    config has thres_max < 0 (prob 0.45), where restoring a wall voxel in a missing leaf CREATES the leaf."""
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, cfg)
+    polys = [np.array([[0.52, 0.5, 0.0, 1], [2.31, 0.77, 0.0, 1], [1.9, 2.2, 0.0, 1], [0.4, 1.9, 0.1, 1]]),
+             np.array([[-1.0, -1.0, 0.2, 1], [-2.0, -1.5, 0.2, 1]]), np.array([[6.0, 6.0, 1.0, 1]])]
+    for m in (g, o):
+        m.addArtificialAreas(polys, -0.35, 0.55)
+    art = g.exportArtificialAreaGrid()
+    assert len(art) > 0
+    assert_leafsets_equal(art, o.exportArtificialAreaGrid(), "artificial grid")
+    assert g.mapLeafCount() == 0
+    for k in range(3):
+        pts, origin = scans.small_scan(20 + k, n=2500, scale=2.5)
+        g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+        g.integrateUpdate(keep_change=True); o.integrateUpdate()
+        assert_leafsets_equal(g.exportLastChange("s"), o.exportLastChange("s"), f"change {k}")
+        assert_leafsets_equal(g.exportMap(), o.exportMap(), f"map with walls {k}")
+    # replacing the areas restores the old walls first
+    for m in (g, o):
+        m.addArtificialAreas(polys[1:], -0.2, 0.3)
+    assert_leafsets_equal(g.exportArtificialAreaGrid(), o.exportArtificialAreaGrid(), "second artificial grid")
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map after replacing areas")
+    pts, origin = scans.small_scan(30, n=2500, scale=2.5)
+    for m in (g, o):
+        m.insertPointCloud(pts, origin, "s")
+        m.restoreMapIntegrity()
+    assert len(g.exportArtificialAreaGrid()) == 0
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map after restoreMapIntegrity")
+    # resetMap keeps the artificial grid (V:174-186 does not touch it)
+    for m in (g, o):
+        m.addArtificialAreas(polys[:1], -0.2, 0.3)
+        m.resetMap()
+        m.insertPointCloud(pts, origin, "s")
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "walls survive resetMap")

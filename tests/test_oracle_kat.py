@@ -10,6 +10,7 @@ import pytest
 
 from oracle.oracle import OracleOccupancyVDBMapping
 import pyref
+from helpers import CFG_GTEST, CFG_ROS, assert_leafsets_equal, popcount64
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 KATS = json.load(open(os.path.join(HERE, "golden", "mapping_kats.json")))
@@ -245,3 +246,130 @@ def test_apply_section_grid_vs_bruteforce(quirk):
             del want[v]
     want.update(pyref.leafset_to_voxels(section))
     assert _map_dict(b) == want
+
+
+# ---- remote-mapping deltas and direct edits -------------------------------------------
+def _voxel_dict(ls):
+    """{(x, y, z): (value, active)} of a float leaf set / {(x,y,z): hit} of a bool one (active voxels only for bool)."""
+    out = {}
+    for i in range(len(ls)):
+        ox, oy, oz = (int(v) for v in ls.origins[i])
+        for w in range(8):
+            word = int(ls.active[i, w])
+            vw = int(ls.valmask[i, w]) if ls.valmask is not None else 0
+            for b in range(64):
+                on = (word >> b) & 1
+                c = (ox + w, oy + (b >> 3), oz + (b & 7))
+                if ls.values is not None:
+                    out[c] = (np.float32(ls.values[i, w * 64 + b]), bool(on))
+                elif on:
+                    out[c] = bool((vw >> b) & 1)
+    return out
+
+
+def _mk_oracle(res=0.1, rng=4.0, cfg=CFG_ROS):
+    m = OracleOccupancyVDBMapping(res)
+    assert m.setConfig(rng, *cfg) == 0
+    m.addInputSource("s", rng)
+    return m
+
+
+def test_reduced_update_is_lossless_and_matches_ray_ends():
+    """Level 2: the reduced grid holds exactly the rays' end voxels (value = not clipped), and re-raycasting it on a
+    receiver reproduces the sender's update grid, change grid and map bit for bit."""
+    from vdb_mapping_b200 import scans
+    snd, rcv = _mk_oracle(), _mk_oracle()
+    for k in range(4):
+        pts, origin = scans.small_scan(40 + k, n=1500, scale=3.0)
+        origin = origin + np.array([0.137 * k, 0.061 * k, 0.013 * k])
+        snd.accumulateUpdate(pts, origin, "s")
+        full = snd.exportUpdateGrid("s")
+        red, o = snd.createUpdate("s", 2)
+        assert np.array_equal(o, origin)
+        # brute force: end voxel of every finite ray
+        expect = {}
+        oi = snd.worldToIndex(origin)
+        for p in pts[:, :3].astype(np.float64):
+            if not np.all(np.isfinite(p)):
+                continue
+            d = p - origin
+            ln = np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+            clipped = ln > 4.0
+            e = origin + (d / ln) * 4.0 if clipped else p
+            c = tuple(int(v) for v in snd.worldToIndex(e))
+            expect[c] = expect.get(c, False) or (not clipped)
+        assert _voxel_dict(red) == expect
+        snd.integrateUpdate()
+        rcv.applyUpdate("s", 2, red, o)
+        assert_leafsets_equal(rcv.exportLastChange("s"), snd.exportLastChange("s"), f"change scan {k}")
+        assert popcount64(red.active) < popcount64(full.active) // 20
+    assert_leafsets_equal(rcv.exportMap(), snd.exportMap(), "receiver map")
+
+
+def test_raw_and_overwrite_updates():
+    """Level 0 (raw update grid -> updateMap) reproduces the sender's map; level 1 (change grid -> overwrite) reproduces
+    its ACTIVE SET with values pinned to the clamping bounds (setNodeToOccupied / setNodeToFree)."""
+    from vdb_mapping_b200 import scans
+    snd, r0, r1 = _mk_oracle(cfg=CFG_GTEST), _mk_oracle(cfg=CFG_GTEST), _mk_oracle(cfg=CFG_GTEST)
+    lo = snd.logodds()
+    for k in range(5):
+        pts, origin = scans.small_scan(60 + k, n=1200, scale=2.5)
+        snd.accumulateUpdate(pts, origin, "s")
+        raw, _ = snd.createUpdate("s", 0)
+        snd.integrateUpdate()
+        chg, _ = snd.createUpdate("s", 1)
+        r0.applyUpdate("s", 0, raw)
+        r1.applyUpdate("s", 1, chg)
+    assert_leafsets_equal(r0.exportMap(), snd.exportMap(), "level-0 receiver")
+    a, b = _voxel_dict(snd.exportMap()), _voxel_dict(r1.exportMap())
+    assert {c for c, (v, on) in a.items() if on} == {c for c, (v, on) in b.items() if on}
+    for c, (v, on) in b.items():
+        assert (v == lo[4] and on) or (v == lo[5] and not on) or (v == 0 and not on)
+
+
+def test_points_set_brute_force():
+    m = _mk_oracle(res=0.1)
+    lo = m.logodds()
+    rng = np.random.default_rng(5)
+    add = (rng.uniform(-3, 3, size=(500, 3))).astype(np.float32)
+    add[::50] = np.round(add[::50] * 10) / 10  # points on voxel boundaries: plain floor(p / res), no half-voxel shift
+    m.addPointsToGrid(add)
+    rem = np.concatenate([add[:100], rng.uniform(-3, 3, size=(100, 3)).astype(np.float32)])
+    m.removePointsFromGrid(rem)
+    expect = {}
+    inv = 1.0 / 0.1
+    for p in add.astype(np.float64):
+        expect[tuple(int(np.floor(x * inv)) for x in p)] = (lo[4], True)
+    for p in rem.astype(np.float64):
+        expect[tuple(int(np.floor(x * inv)) for x in p)] = (lo[5], False)
+    got = {c: v for c, v in _voxel_dict(m.exportMap()).items() if v != (np.float32(0), False)}
+    assert got == expect
+
+
+def test_artificial_areas():
+    """Walls = castRayIntoGrid per height level into the artificial grid; every updateMap then forces them active;
+    restoreMapIntegrity re-derives the flags from the values."""
+    res = 0.1
+    m = _mk_oracle(res=res, cfg=CFG_GTEST)
+    poly = [np.array([[0.52, 0.5, 0.0], [2.31, 0.77, 0.0], [1.9, 2.2, 0.0]]), np.array([[-1.0, -1.0, 0.2], [-2.0, -1.5, 0.2]])]
+    m.addArtificialAreas(poly, -0.35, 0.55)
+    art = _voxel_dict(m.exportArtificialAreaGrid())
+    expect = set()
+    for pg in poly:
+        for i in range(len(pg)):
+            s, e = pyref.world_to_index(pg[i], res), pyref.world_to_index(pg[(i + 1) % len(pg)], res)
+            for lv in range(int(-0.35 / res), int(0.55 / res)):
+                expect |= set(pyref.dda_voxels((s[0], s[1], s[2] + lv), (e[0], e[1], e[2] + lv)))
+    assert set(art) == expect and len(expect) > 100
+    assert m.mapLeafCount() == 0  # nothing happens to the map until the next updateMap
+    from vdb_mapping_b200 import scans
+    pts, origin = scans.small_scan(3, n=800, scale=2.5)
+    m.insertPointCloud(pts, origin, "s")
+    mp = _voxel_dict(m.exportMap())
+    assert all(mp[c][1] for c in expect)
+    m.restoreMapIntegrity()
+    assert len(m.exportArtificialAreaGrid()) == 0
+    lo = m.logodds()
+    mp2 = _voxel_dict(m.exportMap())
+    for c in expect:
+        assert mp2[c][1] == bool(mp2[c][0] > lo[3])

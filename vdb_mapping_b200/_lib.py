@@ -70,6 +70,12 @@ def lib() -> C.CDLL:
     sig("vdbm_section_apply_update", C.c_int, vp, i32p, i32p, u64, i32p, u64p)
     sig("vdbm_section_apply_grid", C.c_int, vp, u64, i32p, u64p, f32p, C.c_int)
     sig("vdbm_probe", C.c_int, vp, i32p, f32p, i32p)
+    sig("vdbm_update_create", C.c_int, vp, cp, C.c_int, pvp, dblp)
+    sig("vdbm_update_apply", C.c_int, vp, C.c_int, u64, i32p, u64p, u64p, dblp, pvp)
+    sig("vdbm_points_set", C.c_int, vp, vp, u64, u64, C.c_int)
+    sig("vdbm_artificial_areas_add", C.c_int, vp, u64, C.POINTER(C.c_uint32), dblp, dbl, dbl)
+    sig("vdbm_map_integrity_restore", C.c_int, vp)
+    sig("vdbm_artificial_export", C.c_int, vp, pvp)
     sig("vdbm_leafset_size", u64, vp)
     sig("vdbm_leafset_origins", i32p, vp)
     sig("vdbm_leafset_active", u64p, vp)

@@ -70,6 +70,13 @@ struct vdbm_map
   uint32_t* d_map_counters = nullptr; // [0] n_leaves
   uint32_t* h_small        = nullptr; // pinned scratch (>= 64 words)
   std::map<std::string, std::unique_ptr<Source> > sources; // std::map order == integrateUpdate order (V:380)
+  std::unique_ptr<Source> scratch;    // library-owned bool grid for applyUpdate / reduced updates / point edits (lazy)
+  std::unique_ptr<Source> artificial; // m_artificial_area_grid V:132,1493 (lazy; survives resetMap like the reference's)
+  // end-voxel records of the last accumulate (the "reduced", level-2 update of that scan)
+  int4* d_ends       = nullptr; // [rays_cap]
+  Source* ends_src   = nullptr;
+  uint64_t ends_n    = 0;
+  double ends_origin[3] = {0, 0, 0};
 
   // staging
   uint8_t* d_points = nullptr;
@@ -304,9 +311,11 @@ bool originIndex(double res, const double o[3], int32_t out[3])
 }
 
 // ---- the raycast (K0 + K1) on device-resident points ---------------------------------------------------
-int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, uint64_t stride, const double origin[3], double range)
+int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, uint64_t stride, const double origin[3], double range,
+                  bool index_mode = false)
 {
   m->stats.rays += n;
+  if (!index_mode && m->ends_src == &s) m->ends_src = nullptr; // the previous scan's reduced update is gone
   m->stats.last_visits = 0;
   if (n == 0) return VDBM_OK;
   if (n > 0xFFFFFFF0ull) return fail(m, VDBM_ERR_INVALID_ARG, "more than 2^32 points in one cloud");
@@ -330,14 +339,16 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   a.inv_res    = 1.0 / m->params.resolution;
   if (m->rays_cap < n)
   {
-    cudaFree(m->d_rays); cudaFree(m->d_segs); cudaFree(m->d_long); cudaFree(m->d_sort); cudaFree(m->d_sort_tmp);
-    m->d_rays = nullptr; m->d_segs = nullptr; m->d_long = nullptr; m->d_sort = nullptr; m->d_sort_tmp = nullptr;
+    cudaFree(m->d_rays); cudaFree(m->d_segs); cudaFree(m->d_long); cudaFree(m->d_sort); cudaFree(m->d_sort_tmp); cudaFree(m->d_ends);
+    m->d_rays = nullptr; m->d_segs = nullptr; m->d_long = nullptr; m->d_sort = nullptr; m->d_sort_tmp = nullptr; m->d_ends = nullptr;
     m->rays_cap = 0;
+    m->ends_src = nullptr;
     // grow geometrically: cloud sizes fluctuate from scan to scan and every reallocation synchronises the device
     const size_t rc = size_t(n) + n / 4 + 4096;
     // one segment per ray + a pool of extra segments for long rays (a ray that finds the pool empty stays whole)
     const size_t seg_cap = rc + 4 * rc + 65536;
     CU_TRY(m, cudaMalloc(&m->d_rays, rc * sizeof(RayRec)));
+    CU_TRY(m, cudaMalloc(&m->d_ends, rc * sizeof(int4)));
     CU_TRY(m, cudaMalloc(&m->d_segs, seg_cap * sizeof(SegRec)));
     CU_TRY(m, cudaMalloc(&m->d_long, rc * 2 * sizeof(uint32_t)));
     CU_TRY(m, cudaMalloc(&m->d_sort, seg_cap * 4 * sizeof(uint32_t)));
@@ -348,6 +359,8 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     m->seg_cap  = seg_cap;
   }
   a.rays      = m->d_rays;
+  a.ends       = index_mode ? nullptr : m->d_ends;
+  a.index_mode = index_mode ? 1u : 0u;
   a.segs      = m->d_segs;
   a.seg_cap   = uint32_t(std::min<size_t>(m->seg_cap, 0xFFFFFFF0u));
   a.long_rays = m->d_long;
@@ -436,6 +449,12 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   m->stats.update_capacity     = std::max(m->stats.update_capacity, s.cap * uint32_t(kBrickLeaves));
   s.prev_visits     = m->stats.last_visits;
   s.prev_max_visits = m->h_ctr->max_visits;
+  if (!index_mode)
+  {
+    m->ends_src = &s;
+    m->ends_n   = n;
+    for (int k = 0; k < 3; ++k) m->ends_origin[k] = origin[k];
+  }
   return VDBM_OK;
 }
 
@@ -467,7 +486,8 @@ int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
     s.n_bricks = 0;
     return VDBM_OK;
   }
-  int rc = ensureMapCapacity(m, n);
+  const uint32_t n_art = m->artificial ? m->artificial->n_entries : 0;
+  int rc = ensureMapCapacity(m, uint64_t(n) + n_art);
   if (rc) return rc;
   if (want_change && s.change_cap < n)
   {
@@ -491,6 +511,7 @@ int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
   launchApplyUpdate(s.g, m->mt, m->lo, m->d_resolved, want_change ? s.d_change : nullptr, want_change ? s.change_cap : 0, m->d_ctr, n,
                     m->stream);
   launchResetBricks(s.g, s.n_bricks, m->stream); // fresh update grid (VDBMapping.hpp:384)
+  if (n_art) launchGridActivate(m->artificial->g, n_art, m->mt, m->d_ctr, m->stream); // V:785-789
   CU_TRY(m, cudaGetLastError());
   s.n_bricks = s.n_entries = 0;
   return VDBM_OK;
@@ -594,6 +615,128 @@ int recordsToLeafset(vdbm_map* m, const LeafRecord* d_recs, uint32_t n, vdbm_lea
   return VDBM_OK;
 }
 
+
+// a bool grid's touched leaves as a sorted leaf set (origin, active mask, value mask)
+int exportGrid(vdbm_map* m, Source& src, vdbm_leafset** out)
+{
+  Source* s        = &src;
+  const uint32_t n = s->n_entries;
+  vdbm_leafset* ls = newLeafset(m, n, true, false);
+  *out             = ls;
+  if (n == 0) return VDBM_OK;
+  TempBuf k0(m->stream), k1(m->stream), i0(m->stream), i1(m->stream), recs(m->stream), so(m->stream), sa(m->stream), sv(m->stream);
+  CU_TRY(m, k0.alloc(size_t(n) * 8)); CU_TRY(m, k1.alloc(size_t(n) * 8));
+  CU_TRY(m, i0.alloc(size_t(n) * 4)); CU_TRY(m, i1.alloc(size_t(n) * 4));
+  CU_TRY(m, recs.alloc(size_t(n) * sizeof(LeafRecord)));
+  CU_TRY(m, so.alloc(size_t(n) * 12)); CU_TRY(m, sa.alloc(size_t(n) * 64)); CU_TRY(m, sv.alloc(size_t(n) * 64));
+  uint64_t* keys = k0.as<uint64_t>();
+  uint32_t* idx  = i0.as<uint32_t>();
+  launchEntryKeys(s->g, n, keys, idx, m->stream);
+  int rc = sortByKey(m, keys, idx, k1.as<uint64_t>(), i1.as<uint32_t>(), n);
+  if (rc) return rc;
+  launchGatherUpdate(s->g, n, keys, idx, recs.as<LeafRecord>(), m->stream);
+  launchSplitRecords(recs.as<LeafRecord>(), n, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<uint64_t>(), m->stream);
+  CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(ls->active, sa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(ls->valmask, sv.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  return VDBM_OK;
+}
+
+// Run `mark` (kernels that OR bits into s.g; idempotent) until the brick hash neither overflowed nor is crowded;
+// rebuilds the leaf list and the host counts. One synchronisation per attempt.
+template <typename MarkFn>
+int markIntoGrid(vdbm_map* m, Source& s, MarkFn mark)
+{
+  for (int attempt = 0; attempt < 24; ++attempt)
+  {
+    mark();
+    launchCompactLeaves(s.g, m->stream);
+    CU_TRY(m, cudaGetLastError());
+    CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s.g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
+    int rc = syncCounters(m);
+    if (rc) return rc;
+    s.n_bricks  = m->h_small[8];
+    s.n_entries = m->h_small[9];
+    const bool overflow = (m->h_ctr->flags & kFlagUpdateOverflow) != 0;
+    const bool crowded  = uint64_t(s.n_bricks) * 10 > uint64_t(s.cap) * 7;
+    if (!overflow && !crowded) break;
+    if (overflow) CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+    rc = growUpdateGrid(m, s);
+    if (rc) return rc;
+    if (!overflow) break;
+  }
+  m->stats.update_capacity = std::max(m->stats.update_capacity, s.cap * uint32_t(kBrickLeaves));
+  return VDBM_OK;
+}
+
+int importRecords(vdbm_map* m, Source& s, const LeafRecord* d_records, uint64_t n)
+{
+  if (n == 0) return VDBM_OK;
+  // optimistic: OR the records in; if the brick hash overflowed or got crowded, grow and replay (OR is idempotent)
+  int rc = markIntoGrid(m, s, [&] { launchImportUpdate(s.g, d_records, n, m->d_ctr, m->stream); });
+  m->stats.last_touched_leaves = s.n_entries;
+  return rc;
+}
+
+// host leaf arrays -> device LeafRecords (stream-ordered temporary)
+int uploadRecords(vdbm_map* m, TempBuf& d, uint64_t n, const int32_t* origins, const uint64_t* active, const uint64_t* value)
+{
+  std::vector<LeafRecord> recs(n);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    for (int k = 0; k < 3; ++k)
+      if (std::abs(int64_t(origins[3 * i + k])) >= kVoxelLimit) return fail(m, VDBM_ERR_COORD_RANGE, "leaf origin outside the +-2^23 voxel range");
+    recs[i].key = packLeafKey(origins[3 * i] >> 3, origins[3 * i + 1] >> 3, origins[3 * i + 2] >> 3);
+    std::memcpy(recs[i].active, active + 8 * i, 64);
+    if (value) std::memcpy(recs[i].value, value + 8 * i, 64);
+    else std::memset(recs[i].value, 0, 64);
+  }
+  CU_TRY(m, d.alloc(n * sizeof(LeafRecord)));
+  CU_TRY(m, cudaMemcpyAsync(d.p, recs.data(), n * sizeof(LeafRecord), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream)); // `recs` is pageable and dies with this frame
+  return VDBM_OK;
+}
+
+// lazily created library-owned bool grids
+int auxGrid(vdbm_map* m, std::unique_ptr<Source>& p, const char* name, uint32_t cap)
+{
+  if (p) return VDBM_OK;
+  auto s = std::make_unique<Source>();
+  s->id  = name;
+  s->cap = cap;
+  int rc = allocUpdateGrid(m, s->g, s->cap);
+  if (rc) return rc;
+  p = std::move(s);
+  return VDBM_OK;
+}
+int scratchGrid(vdbm_map* m)
+{
+  int rc = auxGrid(m, m->scratch, "<scratch>", 256);
+  if (rc) return rc;
+  if (m->scratch->n_entries || m->scratch->n_bricks) return clearUpdateGrid(m, *m->scratch);
+  return VDBM_OK;
+}
+
+// finish a call that ran updateMapInternal on `s`: timings, counters, optional change grid
+int finishUpdate(vdbm_map* m, Source& s, uint64_t upd_before, vdbm_leafset** change)
+{
+  CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, m->ev0, m->ev1);
+  m->stats.last_integrate_ms  = ms;
+  m->stats.last_voxel_updates = m->stats.voxel_updates - upd_before;
+  if (m->h_ctr->flags & kFlagMapOverflow) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "map hash / leaf pool overflow");
+  if (change)
+  {
+    s.n_change = std::min(m->h_ctr->n_change, s.change_cap);
+    return recordsToLeafset(m, s.d_change, s.n_change, change);
+  }
+  return VDBM_OK;
+}
+
 } // namespace
 
 // ======================================================================================================
@@ -658,6 +801,9 @@ void vdbm_destroy(vdbm_map* m)
     freeUpdateGrid(kv.second->g);
     cudaFree(kv.second->d_change);
   }
+  for (Source* aux : {m->scratch.get(), m->artificial.get()})
+    if (aux) { freeUpdateGrid(aux->g); cudaFree(aux->d_change); }
+  cudaFree(m->d_ends);
   freeMapPool(m->mt);
   cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
   cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
@@ -687,6 +833,7 @@ int vdbm_reset(vdbm_map* m)
     if (rc) return rc;
     s.n_change = 0;
   }
+  m->ends_src = nullptr;
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   m->stats.map_leaves = 0;
   return VDBM_OK;
@@ -867,27 +1014,7 @@ int vdbm_update_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
   if (!m || !out) return VDBM_ERR_INVALID_ARG;
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
-  const uint32_t n = s->n_entries;
-  vdbm_leafset* ls = newLeafset(m, n, true, false);
-  *out             = ls;
-  if (n == 0) return VDBM_OK;
-  TempBuf k0(m->stream), k1(m->stream), i0(m->stream), i1(m->stream), recs(m->stream), so(m->stream), sa(m->stream), sv(m->stream);
-  CU_TRY(m, k0.alloc(size_t(n) * 8)); CU_TRY(m, k1.alloc(size_t(n) * 8));
-  CU_TRY(m, i0.alloc(size_t(n) * 4)); CU_TRY(m, i1.alloc(size_t(n) * 4));
-  CU_TRY(m, recs.alloc(size_t(n) * sizeof(LeafRecord)));
-  CU_TRY(m, so.alloc(size_t(n) * 12)); CU_TRY(m, sa.alloc(size_t(n) * 64)); CU_TRY(m, sv.alloc(size_t(n) * 64));
-  uint64_t* keys = k0.as<uint64_t>();
-  uint32_t* idx  = i0.as<uint32_t>();
-  launchEntryKeys(s->g, n, keys, idx, m->stream);
-  int rc = sortByKey(m, keys, idx, k1.as<uint64_t>(), i1.as<uint32_t>(), n);
-  if (rc) return rc;
-  launchGatherUpdate(s->g, n, keys, idx, recs.as<LeafRecord>(), m->stream);
-  launchSplitRecords(recs.as<LeafRecord>(), n, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<uint64_t>(), m->stream);
-  CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
-  CU_TRY(m, cudaMemcpyAsync(ls->active, sa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
-  CU_TRY(m, cudaMemcpyAsync(ls->valmask, sv.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
-  CU_TRY(m, cudaStreamSynchronize(m->stream));
-  return VDBM_OK;
+  return exportGrid(m, *s, out);
 }
 
 int vdbm_update_import(vdbm_map* m, const char* source_id, uint64_t n, const int32_t* origins, const uint64_t* active, const uint64_t* value)
@@ -896,20 +1023,10 @@ int vdbm_update_import(vdbm_map* m, const char* source_id, uint64_t n, const int
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   if (n == 0) return VDBM_OK;
-  std::vector<LeafRecord> recs(n);
-  for (uint64_t i = 0; i < n; ++i)
-  {
-    for (int k = 0; k < 3; ++k)
-      if (std::abs(int64_t(origins[3 * i + k])) >= kVoxelLimit) return fail(m, VDBM_ERR_COORD_RANGE, "leaf origin outside the +-2^23 voxel range");
-    recs[i].key = packLeafKey(origins[3 * i] >> 3, origins[3 * i + 1] >> 3, origins[3 * i + 2] >> 3);
-    std::memcpy(recs[i].active, active + 8 * i, 64);
-    std::memcpy(recs[i].value, value + 8 * i, 64);
-  }
   TempBuf d(m->stream);
-  CU_TRY(m, d.alloc(n * sizeof(LeafRecord)));
-  CU_TRY(m, cudaMemcpyAsync(d.p, recs.data(), n * sizeof(LeafRecord), cudaMemcpyHostToDevice, m->stream));
-  int rc = vdbm_update_import_device(m, source_id, d.p, n);
-  return rc;
+  int rc = uploadRecords(m, d, n, origins, active, value);
+  if (rc) return rc;
+  return importRecords(m, *s, d.as<LeafRecord>(), n);
 }
 
 int vdbm_update_import_device(vdbm_map* m, const char* source_id, const void* d_records, uint64_t n)
@@ -917,29 +1034,190 @@ int vdbm_update_import_device(vdbm_map* m, const char* source_id, const void* d_
   if (!m || (n && !d_records)) return VDBM_ERR_INVALID_ARG;
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
-  if (n == 0) return VDBM_OK;
-  // optimistic: OR the records in; if the brick hash overflowed or got crowded, grow and replay (OR is idempotent)
-  for (int attempt = 0; attempt < 24; ++attempt)
+  return importRecords(m, *s, static_cast<const LeafRecord*>(d_records), n);
+}
+
+// ---- remote-mapping deltas: createUpdate / applyUpdate --------------------------------------
+int vdbm_update_create(vdbm_map* m, const char* source_id, int level, vdbm_leafset** out, double origin_out[3])
+{
+  if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  if (origin_out)
+    for (int k = 0; k < 3; ++k) origin_out[k] = (m->ends_src == s) ? m->ends_origin[k] : 0.0;
+  if (level == 0) return exportGrid(m, *s, out);
+  if (level == 1) return recordsToLeafset(m, s->d_change, s->n_change, out);
+  if (level != 2) return fail(m, VDBM_ERR_INVALID_ARG, "update level must be 0, 1 or 2");
+  if (m->ends_src != s)
+    return fail(m, VDBM_ERR_INVALID_ARG, "no reduced update available: level 2 describes the source's LAST accumulate call on this handle");
+  int rc = scratchGrid(m);
+  if (rc) return rc;
+  Source& sc = *m->scratch;
+  rc = markIntoGrid(m, sc, [&] { launchMarkEnds(m->d_ends, m->ends_n, sc.g, m->d_ctr, m->stream); });
+  if (rc) return rc;
+  rc = exportGrid(m, sc, out);
+  if (rc) return rc;
+  return clearUpdateGrid(m, sc);
+}
+
+int vdbm_update_apply(vdbm_map* m, int level, uint64_t n, const int32_t* origins, const uint64_t* active, const uint64_t* value,
+                      const double origin[3], vdbm_leafset** change)
+{
+  if (!m || (n && (!origins || !active || !value)) || level < 0 || level > 2 || (level == 2 && !origin)) return VDBM_ERR_INVALID_ARG;
+  if (change) *change = nullptr;
+  if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
+  int rc = scratchGrid(m);
+  if (rc) return rc;
+  Source& sc = *m->scratch;
+  if (n)
   {
-    launchImportUpdate(s->g, static_cast<const LeafRecord*>(d_records), n, m->d_ctr, m->stream);
-    launchCompactLeaves(s->g, m->stream);
-    CU_TRY(m, cudaGetLastError());
-    CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s->g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
-    int rc = syncCounters(m);
+    TempBuf d(m->stream);
+    rc = uploadRecords(m, d, n, origins, active, value);
     if (rc) return rc;
-    s->n_bricks  = m->h_small[8];
-    s->n_entries = m->h_small[9];
-    const bool overflow = (m->h_ctr->flags & kFlagUpdateOverflow) != 0;
-    const bool crowded  = uint64_t(s->n_bricks) * 10 > uint64_t(s->cap) * 7;
-    if (!overflow && !crowded) break;
-    if (overflow) CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
-    rc = growUpdateGrid(m, *s);
+    rc = importRecords(m, sc, d.as<LeafRecord>(), n);
     if (rc) return rc;
-    if (!overflow) break;
   }
-  m->stats.last_touched_leaves = s->n_entries;
-  m->stats.update_capacity     = std::max(m->stats.update_capacity, s->cap * uint32_t(kBrickLeaves));
+  m->stats.last_touched_leaves = 0;
+  const uint64_t upd_before    = m->stats.voxel_updates;
+  if (level == 1)
+  {
+    // overwrite grid: every active voxel is forced occupied (value bit) or free, O:118-129
+    rc = ensureMapCapacity(m, sc.n_entries);
+    if (rc) return rc;
+    launchOverwrite(sc.g, sc.n_entries, m->mt, m->lo, m->d_ctr, m->stream);
+    rc = clearUpdateGrid(m, sc);
+    if (rc) return rc;
+    rc = syncCounters(m);
+    if (rc) return rc;
+    if (m->h_ctr->flags & kFlagMapOverflow) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "map hash / leaf pool overflow");
+    if (change) *change = newLeafset(m, 0, true, false);
+    return VDBM_OK;
+  }
+  if (level == 2 && sc.n_entries)
+  {
+    // reduced grid -> end-voxel records -> the sender's update grid again (castRayIntoGrid depends on voxel indices only)
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n * 8; ++i) total += uint64_t(__builtin_popcountll(active[i]));
+    if (total > 0xFFFFFFF0ull) return fail(m, VDBM_ERR_INVALID_ARG, "more than 2^32 rays in one reduced update");
+    if (total * 16 > m->points_cap)
+    {
+      cudaFree(m->d_points);
+      m->d_points   = nullptr;
+      m->points_cap = 0;
+      const size_t want = total * 16 + total * 4 + 65536;
+      CU_TRY(m, cudaMalloc(&m->d_points, want));
+      m->points_cap = want;
+    }
+    CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_out, 0, sizeof(unsigned), m->stream));
+    launchExpandEnds(sc.g, sc.n_entries, reinterpret_cast<int4*>(m->d_points), uint32_t(total), m->d_ctr, m->stream);
+    rc = clearUpdateGrid(m, sc);
+    if (rc) return rc;
+    rc = syncCounters(m);
+    if (rc) return rc;
+    const uint64_t n_rays = std::min<uint64_t>(m->h_ctr->n_out, total);
+    rc = raycastDevice(m, sc, m->d_points, n_rays, 16, origin, 0.0, /*index_mode=*/true);
+    if (rc) return rc;
+  }
+  CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+  rc = updateMapInternal(m, sc, change != nullptr);
+  if (rc) return rc;
+  return finishUpdate(m, sc, upd_before, change);
+}
+
+// ---- direct map edits -------------------------------------------------------------------------
+int vdbm_points_set(vdbm_map* m, const void* points, uint64_t n, uint64_t stride_bytes, int occupied)
+{
+  if (!m || (!points && n) || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  if (n == 0) return VDBM_OK;
+  if (n > 0xFFFFFFF0ull) return fail(m, VDBM_ERR_INVALID_ARG, "more than 2^32 points in one cloud");
+  if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
+  int rc = stagePoints(m, points, n, stride_bytes);
+  if (rc) return rc;
+  rc = scratchGrid(m);
+  if (rc) return rc;
+  Source& sc = *m->scratch;
+  TempBuf ends(m->stream);
+  CU_TRY(m, ends.alloc(size_t(n) * sizeof(int4)));
+  launchPointsToEnds(m->d_points, n, uint32_t(stride_bytes), 1.0 / m->params.resolution, occupied, ends.as<int4>(), m->d_ctr, m->stream);
+  rc = markIntoGrid(m, sc, [&] { launchMarkEnds(ends.as<int4>(), n, sc.g, m->d_ctr, m->stream); });
+  if (rc) return rc;
+  const bool range_err = (m->h_ctr->flags & kFlagCoordRange) != 0;
+  if (range_err) CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+  rc = ensureMapCapacity(m, sc.n_entries);
+  if (rc) return rc;
+  launchOverwrite(sc.g, sc.n_entries, m->mt, m->lo, m->d_ctr, m->stream);
+  rc = clearUpdateGrid(m, sc);
+  if (rc) return rc;
+  rc = syncCounters(m);
+  if (rc) return rc;
+  if (m->h_ctr->flags & kFlagMapOverflow) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "map hash / leaf pool overflow");
+  if (range_err) return fail(m, VDBM_ERR_COORD_RANGE, "some points were outside the +-2^23 voxel range and were dropped");
   return VDBM_OK;
+}
+
+int vdbm_map_integrity_restore(vdbm_map* m)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  if (!m->artificial || m->artificial->n_entries == 0) return VDBM_OK;
+  Source& ar = *m->artificial;
+  int rc     = ensureMapCapacity(m, (0.0f > m->lo.thres_max) ? ar.n_entries : 0);
+  if (rc) return rc;
+  launchRestoreState(ar.g, ar.n_entries, m->mt, m->lo, m->d_ctr, m->stream);
+  rc = clearUpdateGrid(m, ar); // V:1164
+  if (rc) return rc;
+  return syncCounters(m);
+}
+
+int vdbm_artificial_areas_add(vdbm_map* m, uint64_t n_polygons, const uint32_t* counts, const double* xyz, double negative_height,
+                              double positive_height)
+{
+  if (!m || (n_polygons && (!counts || !xyz))) return VDBM_ERR_INVALID_ARG;
+  int rc = vdbm_map_integrity_restore(m); // V:1181
+  if (rc) return rc;
+  rc = auxGrid(m, m->artificial, "<artificial>", 64);
+  if (rc) return rc;
+  Source& ar = *m->artificial;
+  // addArtificialPolygon V:1200-1207: one wall per polygon edge (closing edge included), end points through worldToIndex V:1224-1226
+  std::vector<int32_t> walls;
+  size_t base = 0;
+  for (uint64_t p = 0; p < n_polygons; ++p)
+  {
+    for (uint32_t i = 0; i < counts[p]; ++i)
+    {
+      int32_t a[3], b[3];
+      if (!originIndex(m->params.resolution, xyz + 3 * (base + i), a) || !originIndex(m->params.resolution, xyz + 3 * (base + (i + 1) % counts[p]), b))
+        return fail(m, VDBM_ERR_COORD_RANGE, "artificial area corner outside the +-2^23 voxel range");
+      walls.insert(walls.end(), {a[0], a[1], a[2], b[0], b[1], b[2]});
+    }
+    base += counts[p];
+  }
+  const uint32_t n_walls = uint32_t(walls.size() / 6);
+  if (n_walls == 0) return VDBM_OK;
+  const int32_t neg_index = int32_t(negative_height / m->params.resolution); // V:1228-1229: C cast, truncation
+  const int32_t pos_index = int32_t(positive_height / m->params.resolution);
+  TempBuf d(m->stream);
+  CU_TRY(m, d.alloc(walls.size() * 4));
+  CU_TRY(m, cudaMemcpyAsync(d.p, walls.data(), walls.size() * 4, cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  rc = markIntoGrid(m, ar, [&] { launchWallDDA(d.as<int32_t>(), n_walls, neg_index, pos_index, ar.g, m->d_ctr, m->stream); });
+  if (rc) return rc;
+  if (m->h_ctr->flags & kFlagCoordRange)
+  {
+    CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+    return fail(m, VDBM_ERR_COORD_RANGE, "an artificial wall left the +-2^23 voxel range");
+  }
+  return VDBM_OK;
+}
+
+int vdbm_artificial_export(vdbm_map* m, vdbm_leafset** out)
+{
+  if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  if (!m->artificial)
+  {
+    *out = newLeafset(m, 0, true, false);
+    return VDBM_OK;
+  }
+  return exportGrid(m, *m->artificial, out);
 }
 
 int vdbm_map_export(vdbm_map* m, int dirty_only, vdbm_leafset** out)

@@ -192,6 +192,8 @@ struct RaycastArgs
   uint32_t* sort_idx;  // [seg_cap] identity
   const uint32_t* order; // [n_segs] segment indices, longest first (LPT schedule for the DDA kernel)
   const uint32_t* sorted_keys; // [n_segs] the keys in that order (descending)
+  int4* ends;          // [n] or nullptr: end voxel of every ray + (bit0 valid | bit1 hit), the scan's "reduced" update
+  uint32_t index_mode; // 1: `points` holds such int4 end-voxel records (16-byte stride) instead of world points
 };
 
 // Peer-memory exchange state (device-visible part). inbox layout on every rank, SoA so that every record's 16 mask
@@ -258,6 +260,14 @@ void launchWaitPeers(const unsigned long long* ctrl, int32_t n_ranks, uint32_t p
 // after launchWaitPeers: OR all inbox records of this parity into the grid
 void launchPullUpdate(UpdateGrid ug, const uint64_t* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks,
                       uint32_t parity, uint32_t epoch, uint32_t* counts_out, Counters* ctr, cudaStream_t s);
+// remote-mapping deltas, direct edits, artificial areas
+void launchMarkEnds(const int4* ends, uint64_t n, UpdateGrid g, Counters* ctr, cudaStream_t s);
+void launchExpandEnds(UpdateGrid g, uint32_t n_entries, int4* out, uint32_t out_cap, Counters* ctr, cudaStream_t s); // appends via ctr->n_out
+void launchPointsToEnds(const uint8_t* points, uint64_t n, uint32_t stride, double inv_res, int occupied, int4* out, Counters* ctr, cudaStream_t s);
+void launchOverwrite(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, Counters* ctr, cudaStream_t s);
+void launchWallDDA(const int32_t* d_walls, uint32_t n_walls, int32_t neg_index, int32_t pos_index, UpdateGrid g, Counters* ctr, cudaStream_t s);
+void launchGridActivate(UpdateGrid g, uint32_t n_entries, MapTable mt, Counters* ctr, cudaStream_t s);
+void launchRestoreState(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, Counters* ctr, cudaStream_t s);
 uint32_t launchCount(); // kernels of this library launched by this process
 // CUB radix sort (descending) of (visit count, ray index) on key bits [4, 20); returns temp bytes when d_temp == nullptr
 size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,

@@ -120,20 +120,35 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
   unsigned nan_skipped = 0, clipped = 0, range_err = 0;
   if (i < a.n)
   {
-    const float* p = reinterpret_cast<const float*>(a.points + i * a.stride);
-    double e[3]    = {double(p[0]), double(p[1]), double(p[2])}; // VDBMapping.hpp:501
     RayRec r;
     r.flags  = 0;
     r.visits = 0;
     r.delta[0] = r.delta[1] = r.delta[2] = DBL_MAX;
     uint32_t sign_bits = 0;
-    // VDBMapping.hpp:505-510 skips NaN; +-inf is undefined behaviour in the reference and is dropped here too
-    const bool finite = isfinite(e[0]) && isfinite(e[1]) && isfinite(e[2]);
-    if (!finite) nan_skipped = 1;
+    int4 end_rec = make_int4(0, 0, 0, 0); // end voxel + (bit0 valid, bit1 hit): the "reduced" update of this scan
+    double e[3] = {0.0, 0.0, 0.0};
+    bool finite, index_ray = false, max_range_ray = false;
+    int32_t ei_given[3] = {0, 0, 0};
+    if (a.index_mode)
+    {
+      // receiver side of a reduced update: the record IS the end voxel (x, y, z, flags), no world arithmetic
+      const int4 q = *reinterpret_cast<const int4*>(a.points + i * a.stride);
+      finite        = (q.w & 1) != 0;
+      index_ray     = true;
+      max_range_ray = (q.w & 2) == 0;
+      ei_given[0] = q.x; ei_given[1] = q.y; ei_given[2] = q.z;
+    }
     else
     {
-      bool max_range_ray = false;
-      if (a.range > 0.0)
+      const float* p = reinterpret_cast<const float*>(a.points + i * a.stride);
+      e[0] = double(p[0]); e[1] = double(p[1]); e[2] = double(p[2]); // VDBMapping.hpp:501
+      // VDBMapping.hpp:505-510 skips NaN; +-inf is undefined behaviour in the reference and is dropped here too
+      finite = isfinite(e[0]) && isfinite(e[1]) && isfinite(e[2]);
+    }
+    if (!finite) nan_skipped = index_ray ? 0 : 1;
+    else
+    {
+      if (!index_ray && a.range > 0.0)
       {
         const double dx = __dsub_rn(e[0], a.origin[0]), dy = __dsub_rn(e[1], a.origin[1]), dz = __dsub_rn(e[2], a.origin[2]);
         // openvdb Vec3::length(): sqrt(x*x + y*y + z*z), left-associated
@@ -153,9 +168,11 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
 #pragma unroll
       for (int k = 0; k < 3; ++k)
       {
-        const double fl = floor(__dmul_rn((fmod(e[k], a.resolution) != 0.0) ? __dadd_rn(e[k], a.half_res) : e[k], a.inv_res));
+        const double fl = index_ray ? double(ei_given[k])
+                                    : floor(__dmul_rn((fmod(e[k], a.resolution) != 0.0) ? __dadd_rn(e[k], a.half_res) : e[k], a.inv_res));
         if (!(fabs(fl) < double(kVoxelLimit))) in_range = false;
         const int32_t ei = in_range ? int32_t(fl) : 0;
+        (&end_rec.x)[k]  = ei;
         const double dir = __dsub_rn(double(ei), double(a.origin_idx[k])); // exact
         if (dir != 0.0)
         {
@@ -171,9 +188,11 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
         r.flags  = kRayValid | (max_range_ray ? kRayClipped : 0u) | (zero ? kRayZeroLen : 0u) | sign_bits;
         visits   = zero ? 0ull : (unsigned long long)(1 + l1); // castRayIntoGrid marks 1 + |dx|+|dy|+|dz| voxels
         r.visits = uint32_t(visits);
+        end_rec.w = 1 | (max_range_ray ? 0 : 2);
       }
     }
     a.rays[i] = r;
+    if (a.ends) a.ends[i] = end_rec;
     // segment i = this ray's first (or only) segment, starting at the sensor voxel
     SegRec sg;
     sg.next[0] = (r.delta[0] == DBL_MAX) ? DBL_MAX : __dmul_rn(0.5, r.delta[0]); // DDA::init: 0.5 * |inv| exactly
@@ -1412,6 +1431,239 @@ __global__ void __launch_bounds__(256) pull_update_kernel(UpdateGrid g, const ui
 }
 
 // ====================================================================================================
+// Remote-mapping deltas (createUpdate / applyUpdate) and direct map edits (8f N4)
+// ====================================================================================================
+// end-voxel records (x, y, z, bit0 valid | bit1 hit) -> bits of a bool grid: active, and value where hit
+__global__ void __launch_bounds__(256) mark_ends_kernel(const int4* ends, uint64_t n, UpdateGrid g, Counters* ctr)
+{
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 q = ends[i];
+  if (!(q.w & 1)) return;
+  const uint64_t bkey = packLeafKey(q.x >> 6, q.y >> 6, q.z >> 6);
+  const uint32_t slot = brickFindOrInsert(g, bkey, ctr);
+  if (slot == kInvalid) return;
+  const size_t w     = size_t(slot) * (kBrickLeaves * 8) + brickWordOffset(q.x, q.y, q.z);
+  const uint64_t bit = uint64_t(1) << (((q.y & 7) << 3) | (q.z & 7));
+  redOr64(g.act + w, bit);
+  if (q.w & 2) redOr64(g.val + w, bit);
+}
+
+// the active voxels of a bool grid -> end-voxel records (any order). Warp per touched leaf, lane w < 8 owns mask word w.
+__global__ void __launch_bounds__(256) expand_ends_kernel(UpdateGrid g, uint32_t n_entries, int4* out, uint32_t out_cap, Counters* ctr)
+{
+  const int lane         = threadIdx.x & 31;
+  const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < n_entries; i += n_warps)
+  {
+    const uint32_t e = g.entries[i];
+    uint64_t a = 0, v = 0;
+    if (lane < 8) { a = g.act[size_t(e) * 8 + lane]; v = g.val[size_t(e) * 8 + lane]; }
+    const uint32_t cnt = uint32_t(__popcll(a));
+    uint32_t incl = cnt; // inclusive prefix sum over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    uint32_t base = 0;
+    if (lane == 0 && total) base = atomicAdd(&ctr->n_out, total);
+    base = __shfl_sync(kFull, base, 0);
+    if (!cnt) continue;
+    int32_t ox, oy, oz;
+    unpackLeafOrigin(leafKeyOfEntry(g.bkeys[e >> 9], e & 511u), ox, oy, oz);
+    uint32_t o = base + incl - cnt;
+    while (a)
+    {
+      const int b = __ffsll((long long)a) - 1;
+      a &= a - 1;
+      if (o < out_cap) out[o] = make_int4(ox + lane, oy + (b >> 3), oz + (b & 7), 1 | (((v >> b) & 1ull) ? 2 : 0));
+      ++o;
+    }
+  }
+}
+
+// pcl points -> end-voxel records for addPointsToGrid / removePointsFromGrid (VDBMapping.hpp:413-447):
+// Coord::floor(grid->worldToIndex(pt)) = floor(pt * (1/res)) per component, NOT the fmod variant of V:612-631
+__global__ void __launch_bounds__(256) points_to_ends_kernel(const uint8_t* points, uint64_t n, uint32_t stride, double inv_res, int occupied,
+                                                            int4* out, Counters* ctr)
+{
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(points + i * stride);
+  int4 q         = make_int4(0, 0, 0, 0);
+  bool ok        = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]); // non-finite points are undefined in the reference
+  bool in_range  = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    const double fl = floor(__dmul_rn(double(p[k]), inv_res));
+    if (!(fabs(fl) < double(kVoxelLimit))) in_range = false;
+    (&q.x)[k] = in_range ? int32_t(fl) : 0;
+  }
+  if (ok && !in_range) atomicOr(&ctr->flags, kFlagCoordRange);
+  q.w    = (ok && in_range) ? (1 | (occupied ? 2 : 0)) : 0;
+  out[i] = q;
+}
+
+// overwriteMap / setNodeToOccupied / setNodeToFree (OccupancyVDBMapping.hpp:118-129) for every active voxel of a bool
+// grid: value bit -> (max_logodds, active), else (min_logodds, inactive). Both ops change the value of a background
+// tile, so OpenVDB's tile probe always creates the leaf. Warp per touched leaf, lane = 16 consecutive voxels.
+__global__ void __launch_bounds__(256) overwrite_kernel(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, Counters* ctr)
+{
+  const int lane         = threadIdx.x & 31;
+  const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < n_entries; i += n_warps)
+  {
+    const uint32_t e = g.entries[i];
+    uint64_t a = 0, v = 0;
+    if (lane < 8) { a = g.act[size_t(e) * 8 + lane]; v = g.val[size_t(e) * 8 + lane]; }
+    if (!(__ballot_sync(kFull, a != 0) & 0xFFu)) continue;
+    int is_new;
+    const uint32_t leaf = warpFindOrCreateLeaf(mt, leafKeyOfEntry(g.bkeys[e >> 9], e & 511u), true, lane, is_new, ctr);
+    if (leaf == kInvalid) continue;
+    float x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float* dst = mt.leaf_vals + size_t(leaf) * 512 + lane * 16;
+    if (!is_new) { ld256(dst, x); ld256(dst + 8, y); }
+    // voxels lane*16 .. lane*16+15 live in mask word lane>>2, bits (lane&3)*16 ..
+    const uint32_t a16 = uint32_t(shfl64(a, lane >> 2) >> ((lane & 3) * 16)) & 0xFFFFu;
+    const uint32_t v16 = uint32_t(shfl64(v, lane >> 2) >> ((lane & 3) * 16)) & 0xFFFFu;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+    {
+      if ((a16 >> q) & 1u) x[q] = ((v16 >> q) & 1u) ? lo.max_lo : lo.min_lo;
+      if ((a16 >> (q + 8)) & 1u) y[q] = ((v16 >> (q + 8)) & 1u) ? lo.max_lo : lo.min_lo;
+    }
+    st256(dst, x);
+    st256(dst + 8, y);
+    if (lane < 8)
+    {
+      const uint64_t old = is_new ? 0ull : mt.leaf_mask[size_t(leaf) * 8 + lane];
+      mt.leaf_mask[size_t(leaf) * 8 + lane] = (old & ~a) | (a & v);
+    }
+    if (lane == 0) mt.leaf_dirty[leaf] = 1u;
+  }
+}
+
+// ---- artificial areas (VDBMapping.hpp:1152-1236 and the tail of updateMap V:785-789) ----
+// addArtificialWall: thread (wall, level) runs castRayIntoGrid(start + (0,0,i), end + (0,0,i)) with the same fp64 sequence
+// as the scan DDA and marks straight into the artificial-area grid. Walls are short and rare: no tuning here.
+__global__ void __launch_bounds__(128) wall_dda_kernel(const int32_t* walls /*[n][6] start xyz, end xyz*/, uint32_t n_walls, int32_t neg_index,
+                                                      int32_t pos_index, UpdateGrid g, Counters* ctr)
+{
+  const int32_t levels = pos_index - neg_index;
+  const uint64_t t     = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (levels <= 0 || t >= uint64_t(n_walls) * uint64_t(levels)) return;
+  const uint32_t w = uint32_t(t / uint64_t(levels));
+  const int32_t lv = neg_index + int32_t(t % uint64_t(levels));
+  int32_t vox[3]   = {walls[6 * w], walls[6 * w + 1], walls[6 * w + 2] + lv};
+  const int32_t en[3] = {walls[6 * w + 3], walls[6 * w + 4], walls[6 * w + 5] + lv};
+  if (vox[0] == en[0] && vox[1] == en[1] && vox[2] == en[2]) return; // V:559
+  double next[3], delta[3];
+  int32_t step[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    const double dir = __dsub_rn(double(en[k]), double(vox[k]));
+    if (dir == 0.0) { step[k] = 0; next[k] = DBL_MAX; delta[k] = DBL_MAX; }
+    else
+    {
+      delta[k] = fabs(__ddiv_rn(1.0, dir));
+      next[k]  = __dmul_rn(0.5, delta[k]);
+      step[k]  = dir > 0.0 ? 1 : -1;
+    }
+  }
+  uint64_t cur_bkey = kEmptyKey;
+  uint32_t slot     = kInvalid;
+  bool more;
+  do
+  {
+    if (max(abs(vox[0]), max(abs(vox[1]), abs(vox[2]))) >= kVoxelLimit) { atomicOr(&ctr->flags, kFlagCoordRange); return; }
+    const uint64_t bkey = packLeafKey(vox[0] >> 6, vox[1] >> 6, vox[2] >> 6);
+    if (bkey != cur_bkey) { cur_bkey = bkey; slot = brickFindOrInsert(g, bkey, ctr); }
+    if (slot != kInvalid)
+      redOr64(g.act + size_t(slot) * (kBrickLeaves * 8) + brickWordOffset(vox[0], vox[1], vox[2]), uint64_t(1) << (((vox[1] & 7) << 3) | (vox[2] & 7)));
+    // DDA::step with math::MinIndex: x iff n0 < n1 && n0 < n2; else y iff n1 < n2; else z
+    const int axis = (next[0] < next[1] && next[0] < next[2]) ? 0 : ((next[1] < next[2]) ? 1 : 2);
+    const double tt = next[axis];
+    next[axis]      = __dadd_rn(next[axis], delta[axis]);
+    vox[axis] += step[axis];
+    more = (tt <= 1.0);
+  } while (more);
+}
+
+// V:785-789: acc.setActiveState(coord, true) for every voxel of the artificial-area grid (a missing leaf is created with
+// background values). Warp per artificial leaf.
+__global__ void __launch_bounds__(256) grid_activate_kernel(UpdateGrid g, uint32_t n_entries, MapTable mt, Counters* ctr)
+{
+  const int lane         = threadIdx.x & 31;
+  const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < n_entries; i += n_warps)
+  {
+    const uint32_t e = g.entries[i];
+    const uint64_t a = (lane < 8) ? g.act[size_t(e) * 8 + lane] : 0;
+    if (!(__ballot_sync(kFull, a != 0) & 0xFFu)) continue;
+    int is_new;
+    const uint32_t leaf = warpFindOrCreateLeaf(mt, leafKeyOfEntry(g.bkeys[e >> 9], e & 511u), true, lane, is_new, ctr);
+    if (leaf == kInvalid) continue;
+    if (is_new)
+    {
+      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      st256(mt.leaf_vals + size_t(leaf) * 512 + lane * 16, z);
+      st256(mt.leaf_vals + size_t(leaf) * 512 + lane * 16 + 8, z);
+    }
+    if (lane < 8) mt.leaf_mask[size_t(leaf) * 8 + lane] = (is_new ? 0ull : mt.leaf_mask[size_t(leaf) * 8 + lane]) | a;
+    if (lane == 0) mt.leaf_dirty[leaf] = 1u;
+  }
+}
+
+// restoreMapIntegrity V:1152-1166: setNodeState (active = value > thres_max, O:130-135) through
+// modifyValueAndActiveState for every artificial-area voxel. On a missing leaf OpenVDB probes the (0, inactive) tile:
+// the leaf is created only if 0 > thres_max (then the voxel becomes active with value 0).
+__global__ void __launch_bounds__(256) restore_state_kernel(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, Counters* ctr)
+{
+  const int lane         = threadIdx.x & 31;
+  const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const bool bg_active   = 0.0f > lo.thres_max;
+  for (uint32_t i = warp; i < n_entries; i += n_warps)
+  {
+    const uint32_t e = g.entries[i];
+    const uint64_t a = (lane < 8) ? g.act[size_t(e) * 8 + lane] : 0;
+    if (!(__ballot_sync(kFull, a != 0) & 0xFFu)) continue;
+    int is_new;
+    const uint32_t leaf = warpFindOrCreateLeaf(mt, leafKeyOfEntry(g.bkeys[e >> 9], e & 511u), bg_active, lane, is_new, ctr);
+    if (leaf == kInvalid) continue;
+    float x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float* src = mt.leaf_vals + size_t(leaf) * 512 + lane * 16;
+    if (is_new) { st256(src, x); st256(src + 8, y); }
+    else { ld256(src, x); ld256(src + 8, y); }
+    // "value > thres_max" bits of this lane's 16 voxels, gathered into the 8 mask words
+    uint32_t on16 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+    {
+      on16 |= (x[q] > lo.thres_max ? 1u : 0u) << q;
+      on16 |= (y[q] > lo.thres_max ? 1u : 0u) << (q + 8);
+    }
+    uint64_t on = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) on |= uint64_t(__shfl_sync(kFull, on16, (lane & 7) * 4 + k)) << (16 * k);
+    if (lane < 8)
+    {
+      const uint64_t old = is_new ? 0ull : mt.leaf_mask[size_t(leaf) * 8 + lane];
+      mt.leaf_mask[size_t(leaf) * 8 + lane] = (old & ~a) | (a & on);
+    }
+    if (lane == 0) mt.leaf_dirty[leaf] = 1u;
+  }
+}
+
+
+// ====================================================================================================
 // launch wrappers
 // ====================================================================================================
 static inline unsigned blocksFor(uint64_t n, unsigned per_block) { return unsigned((n + per_block - 1) / per_block); }
@@ -1616,6 +1868,48 @@ size_t sortPairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint6
   if (d_temp == nullptr) bytes = 0;
   cub::DeviceRadixSort::SortPairs(d_temp, bytes, keys_in, keys_out, idx_in, idx_out, int(n), 0, 63, s);
   return bytes;
+}
+
+void launchMarkEnds(const int4* ends, uint64_t n, UpdateGrid g, Counters* ctr, cudaStream_t s)
+{
+  if (n == 0) return;
+  VDBM_LAUNCH(mark_ends_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), s, ends, n, g, ctr);
+}
+void launchExpandEnds(UpdateGrid g, uint32_t n_entries, int4* out, uint32_t out_cap, Counters* ctr, cudaStream_t s)
+{
+  if (n_entries == 0) return;
+  const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(n_entries) * 32 + 255) / 256, 148ull * 16));
+  VDBM_LAUNCH(expand_ends_kernel, dim3(blocks), dim3(256), s, g, n_entries, out, out_cap, ctr);
+}
+void launchPointsToEnds(const uint8_t* points, uint64_t n, uint32_t stride, double inv_res, int occupied, int4* out, Counters* ctr, cudaStream_t s)
+{
+  if (n == 0) return;
+  VDBM_LAUNCH(points_to_ends_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), s, points, n, stride, inv_res, occupied, out, ctr);
+}
+void launchOverwrite(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, Counters* ctr, cudaStream_t s)
+{
+  if (n_entries == 0) return;
+  const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(n_entries) * 32 + 255) / 256, 148ull * 16));
+  VDBM_LAUNCH(overwrite_kernel, dim3(blocks), dim3(256), s, g, n_entries, mt, lo, ctr);
+}
+void launchWallDDA(const int32_t* d_walls, uint32_t n_walls, int32_t neg_index, int32_t pos_index, UpdateGrid g, Counters* ctr, cudaStream_t s)
+{
+  const int64_t levels = int64_t(pos_index) - int64_t(neg_index);
+  if (n_walls == 0 || levels <= 0) return;
+  const uint64_t threads = uint64_t(n_walls) * uint64_t(levels);
+  VDBM_LAUNCH(wall_dda_kernel, dim3(unsigned((threads + 127) / 128)), dim3(128), s, d_walls, n_walls, neg_index, pos_index, g, ctr);
+}
+void launchGridActivate(UpdateGrid g, uint32_t n_entries, MapTable mt, Counters* ctr, cudaStream_t s)
+{
+  if (n_entries == 0) return;
+  const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(n_entries) * 32 + 255) / 256, 148ull * 16));
+  VDBM_LAUNCH(grid_activate_kernel, dim3(blocks), dim3(256), s, g, n_entries, mt, ctr);
+}
+void launchRestoreState(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, Counters* ctr, cudaStream_t s)
+{
+  if (n_entries == 0) return;
+  const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(n_entries) * 32 + 255) / 256, 148ull * 16));
+  VDBM_LAUNCH(restore_state_kernel, dim3(blocks), dim3(256), s, g, n_entries, mt, lo, ctr);
 }
 
 } // namespace vdbm

@@ -229,6 +229,53 @@ class OccupancyVDBMapping:
         self._check(self._L.vdbm_section_apply_grid(self._h, o.shape[0], o.ctypes.data_as(i32p), a.ctypes.data_as(u64p),
                                                     v.ctypes.data_as(f32p), int(tile_quirk)))
 
+    # ---- remote-mapping deltas (level semantics in include/vdbm_b200.h) ----
+    def createUpdate(self, source_id: str, level: int):
+        """-> (LeafSet, origin of the source's last accumulate). level 0: raw update grid, 1: change/overwrite grid of the
+        last integrate, 2: reduced update (ray end voxels, value = hit)."""
+        out = C.c_void_p()
+        o = np.zeros(3, dtype=np.float64)
+        self._check(self._L.vdbm_update_create(self._h, source_id.encode(), int(level), C.byref(out), _dp(o)))
+        return self._take(out, False), o
+
+    def applyUpdate(self, level: int, update: LeafSet, origin=None, want_change: bool = False):
+        i32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+        o = np.ascontiguousarray(update.origins, dtype=np.int32)
+        a = np.ascontiguousarray(update.active, dtype=np.uint64)
+        v = np.ascontiguousarray(update.valmask, dtype=np.uint64)
+        og = np.ascontiguousarray(origin if origin is not None else [0, 0, 0], dtype=np.float64)
+        out = C.c_void_p()
+        self._check(self._L.vdbm_update_apply(self._h, int(level), o.shape[0], o.ctypes.data_as(i32p), a.ctypes.data_as(u64p),
+                                              v.ctypes.data_as(u64p), _dp(og), C.byref(out) if want_change else None))
+        return self._take(out, False) if want_change else None
+
+    # ---- direct map edits + artificial areas (SURVEY.md 8f N4) ----
+    def addPointsToGrid(self, points) -> bool:
+        p = _pts16(points)
+        self._check(self._L.vdbm_points_set(self._h, p.ctypes.data, p.shape[0], 16, 1))
+        return True  # VDBMapping.hpp:446
+
+    def removePointsFromGrid(self, points) -> bool:
+        p = _pts16(points)
+        self._check(self._L.vdbm_points_set(self._h, p.ctypes.data, p.shape[0], 16, 0))
+        return True  # VDBMapping.hpp:428
+
+    def addArtificialAreas(self, polygons, negative_height: float, positive_height: float):
+        """polygons: list of (k_i, >=3) arrays of world points (VDBMapping.hpp:1175-1236)."""
+        counts = np.asarray([len(p) for p in polygons], dtype=np.uint32)
+        xyz = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64)[:, :3] for p in polygons])
+                                   if len(polygons) else np.zeros((0, 3)))
+        self._check(self._L.vdbm_artificial_areas_add(self._h, len(polygons), counts.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(xyz),
+                                                      float(negative_height), float(positive_height)))
+
+    def restoreMapIntegrity(self):
+        self._check(self._L.vdbm_map_integrity_restore(self._h))
+
+    def exportArtificialAreaGrid(self) -> LeafSet:
+        out = C.c_void_p()
+        self._check(self._L.vdbm_artificial_export(self._h, C.byref(out)))
+        return self._take(out, False)
+
     def probe(self, coord):
         c = np.ascontiguousarray(coord, dtype=np.int32)
         v, a = C.c_float(0), C.c_int32(0)
