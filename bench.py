@@ -124,8 +124,9 @@ def measured_traffic(kernel: str):
 
 
 def workload_cfg(name: str) -> int:
-    """cfg5 = cfg2's scan sequence driven through the whole wrapper-side pipeline: change grid of every
-    updateMap read back, every 10th scan a sparse and a full-leaf map section of a 20x20x6 m box around the sensor."""
+    """cfg5 (BASELINE configs[4]) = cfg2's scan sequence as REMOTE MAPPING: the sender raycasts, creates the
+    level-2 (reduced) update, integrates; a second map applies that update (re-raycast + updateMap); every 10th scan a
+    sparse and a full-leaf map section of a 20x20x6 m box around the sensor is extracted to the host."""
     return {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 2}[name]
 
 
@@ -138,7 +139,7 @@ def section_box(origin, resolution: float):
 
 
 def workload_name(args, c) -> str:
-    return c.name if args.workload != "cfg5" else "cfg5_" + c.name.split("_", 1)[1] + "_change+sections"
+    return c.name if args.workload != "cfg5" else "cfg5_remote_" + c.name.split("_", 1)[1] + "_level2+sections"
 
 
 def alg_bytes(n_pts: int, leaves: int, change: bool = False) -> int:
@@ -171,15 +172,26 @@ def run_reference(args, rank, world):
         pts = np.ascontiguousarray(pts[lo:lo + per])
         clouds.append((pts, origin))
     mixed = args.workload == "cfg5"
+    remote = None
+    if mixed:
+        remote = OracleOccupancyVDBMapping(c.resolution)
+        remote.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+        remote.addInputSource("s", c.max_range)
 
     def step(k):
-        m.insertPointCloud(*clouds[k], "s")
-        if mixed:
-            m.exportLastChange("s")
-            if k % 10 == 9:
-                lo, hi = section_box(clouds[k][1], c.resolution)
-                m.getMapSectionUpdateGrid(lo, hi, full=False)
-                m.getMapSectionGrid(lo, hi, full=True)
+        if not mixed:
+            m.insertPointCloud(*clouds[k], "s")
+            return
+        # remote mapping (BASELINE configs[4]): sender raycast -> reduced update -> sender updateMap; the remote map
+        # re-raycasts the reduced update; every 10th scan a sparse and a full-leaf section around the sensor
+        m.accumulateUpdate(*clouds[k], "s")
+        red, o = m.createUpdate("s", 2)
+        m.integrateUpdate()
+        remote.applyUpdate("s", 2, red, o)
+        if k % 10 == 9:
+            lo, hi = section_box(clouds[k][1], c.resolution)
+            m.getMapSectionUpdateGrid(lo, hi, full=False)
+            m.getMapSectionGrid(lo, hi, full=True)
 
     for k in range(args.warmup):
         step(k)
@@ -241,6 +253,7 @@ def run_ours(args, rank, world, local_rank):
     c = scans.CONFIGS[cfg]
     n_steps = args.warmup + args.steps
     strong = (args.scaling == "strong") and world > 1
+    mixed = args.workload == "cfg5"
 
     # ---- synthetic input: scan k of the sequence; with N > 1 rank r owns LiDAR r of the merged rig ----
     clouds = []
@@ -274,11 +287,16 @@ def run_ours(args, rank, world, local_rank):
             m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
             m.addInputSource("s", c.max_range)
             eng = vdist.CudaEngine(m, "s")
-            p2p = world > 1 and args.exchange == "p2p"
+            remote = None
+            if mixed:
+                remote = OccupancyVDBMapping(c.resolution, device=local_rank, stream=stream.cuda_stream)
+                remote.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+            p2p = world > 1 and args.exchange == "p2p" and not mixed
             if p2p:
                 vdist.connect_peers(m, dist, capacity_records_per_sender=(1 << 22) if cfg == 4 else (1 << 19))
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             acc_ms, prep_ms, int_ms, leaves = [], [], [], []
+            d2h_extra = [0, 0]  # cfg5: bytes read back (reduced updates + sections), sections extracted
             sent = recv = 0
             st0 = None
             for k in range(n_steps):
@@ -298,6 +316,21 @@ def run_ours(args, rank, world, local_rank):
                 if k >= args.warmup:
                     s = m.stats()
                     acc_ms.append(s["last_accumulate_ms"]); prep_ms.append(s["last_prep_ms"]); leaves.append(s["last_touched_leaves"])
+                if mixed:
+                    red, o = m.createUpdate("s", 2)          # device: end voxels -> leaf set; D2H of the reduced grid
+                    m.integrateUpdate(keep_change=False)
+                    if k >= args.warmup:
+                        int_ms.append(m.stats()["last_integrate_ms"])
+                        d2h_extra[0] += red.origins.nbytes + red.active.nbytes + red.valmask.nbytes
+                    remote.applyUpdate(2, red, origin=o)     # H2D of the reduced grid, re-raycast, updateMap
+                    if k % 10 == 9:
+                        lo, hi = section_box(origin, c.resolution)
+                        sp = m.getMapSectionUpdateGrid(lo, hi, full=False)
+                        fu = m.getMapSectionGrid(lo, hi, full=True)
+                        if k >= args.warmup:
+                            d2h_extra[0] += sp.origins.nbytes + sp.active.nbytes + sp.valmask.nbytes + fu.origins.nbytes + fu.active.nbytes + fu.values.nbytes
+                            d2h_extra[1] += 1
+                    continue
                 if p2p:
                     vdist.push_pull_and_integrate(eng)
                     a = b = 0
@@ -316,7 +349,15 @@ def run_ours(args, rank, world, local_rank):
                    "rays": st1["rays"] - st0["rays"], "voxel_updates": st1["voxel_updates"] - st0["voxel_updates"],
                    "visits": st1["visits"] - st0["visits"], "launches": st1["gpu_launches"] - launches0,
                    "acc_ms": acc_ms, "prep_ms": prep_ms, "int_ms": int_ms, "leaves": leaves, "map_leaves": st1["map_leaves"],
-                   "sent": sent, "recv": recv}
+                   "sent": sent, "recv": recv, "d2h_extra": d2h_extra}
+            if mixed:
+                # outside the timed region: the remote map must equal the sender's (level-2 updates are lossless)
+                a, b = m.exportMap(), remote.exportMap()
+                out["remote_identical"] = bool(len(a) == len(b) and np.array_equal(a.origins, b.origins) and np.array_equal(a.active, b.active)
+                                               and np.array_equal(a.values.view(np.uint32), b.values.view(np.uint32)))
+                out["remote_launches"] = 0
+                del a, b
+                remote.close()
             m.close()
             return out
 
@@ -355,7 +396,7 @@ def run_ours(args, rank, world, local_rank):
     L = mean(res_v["leaves"])
     t_prep, t_acc, t_int = mean(res_v["prep_ms"]), mean(res_v["acc_ms"]), mean(res_v["int_ms"])
     t_dda = t_acc - t_prep
-    b_alg = alg_bytes(n_pts, int(L))
+    b_alg = alg_bytes(n_pts, int(L))  # cfg5: roofline figures describe the SENDER's scan-step kernels only
     t_kernels = t_acc + t_int
     upd_bytes = 4352 * L  # K2 alone: update masks read (128 B) + map leaf values+mask read and written (4224 B)
     tr_dda, tr_src = measured_traffic("raycast_dda_kernel")
@@ -381,7 +422,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_v / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64 DDA + f32 log-odds", "data": "synthetic",
-        "config": {"workload": c.name, "description": c.description, "resolution_m": c.resolution, "max_range_m": c.max_range,
+        "config": {"workload": workload_name(args, c), "description": c.description, "resolution_m": c.resolution, "max_range_m": c.max_range,
                    "points_per_scan_per_gpu": n_pts, "points_per_step_total": int(rays_v / K),
                    "sequence": "moving sensor, scan k of the sequence per step, fresh map at step 0",
                    "parallelism": ("1 GPU" if world == 1 else (f"{world} GPUs: " + ("one scan split across ranks" if strong else "one LiDAR per GPU of a merged rig") +
@@ -393,7 +434,19 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches), "roofline": roofline, "clocks": res_v["clocks"],
         "wall_ms_per_step": res_v["wall_ms"] / K,
     }
-    if world > 1:
+    if mixed:
+        line["remote_mapping"] = {
+            "pipeline": "sender accumulate -> createUpdate(level 2) -> integrate; remote applyUpdate(level 2) on a second map of the same GPU; "
+                        "every 10th scan getMapSectionUpdateGrid (sparse) + getMapSectionGrid (full) of a 20x20x6 m box, read back to the host",
+            "remote_map_identical_to_sender": bool(res_v["remote_identical"] and res_e["remote_identical"]),
+            "d2h_bytes_per_step_reduced_updates_and_sections": res_v["d2h_extra"][0] / K,
+            "sections_per_step": res_v["d2h_extra"][1] / K,
+            "note": "rays_per_sec counts the SENDER's rays; every ray is traversed twice (sender + remote); the roofline block describes the sender's scan-step kernels"}
+        line["e2e"]["d2h_bytes_per_step"] = 164 + int(res_e["d2h_extra"][0] / K)
+        line["e2e"]["api"] = "accumulate(host pinned cloud) + createUpdate(2) + integrate + remote applyUpdate(2) + periodic getMapSection*"
+        line["config"]["parallelism"] = "1 GPU (sender and remote map)" if world == 1 else f"{world} independent sender/remote pairs, one per GPU"
+        line["exchange"] = None
+    if world > 1 and not mixed:
         line["exchange"] = {"kind": args.exchange, "records_sent_per_step": (sent / K) if args.exchange == "nccl" else None,
                             "bytes_sent_per_step": (136 * sent / K) if args.exchange == "nccl" else None,
                             "note": "p2p = one kernel bins the update leaves by owner and stores the 136-byte records into the owners' inboxes over NVLink (CUDA IPC), device-side epoch wait; nccl = count + record all-to-all"}
@@ -401,7 +454,7 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu_baseline_leg(cfg, args.cpu_scans)
     else:
         line["cpu_baseline"] = None
-    if world > 1 and vdist.PROFILE:
+    if world > 1 and vdist.PROFILE and not mixed:
         log = np.array(vdist.PROFILE_LOG[-K:])
         names = ["push_launch", "pull_wait_import_sync", "integrate", "dev_push", "dev_wait", "dev_import"] if args.exchange == "p2p" else \
             ["partition", "counts_a2a", "records_a2a_launch", "import", "integrate"]
@@ -434,7 +487,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)  # configs[1] is a 100-scan sequence
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU update-leaf exchange: fused peer-memory stores over NVLink (default) or NCCL all-to-all")

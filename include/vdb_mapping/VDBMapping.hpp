@@ -17,8 +17,10 @@
 //
 // Scope: insertPointCloud, accumulateUpdate, addDataToAccumulate, integrateUpdate,
 // raycastPointCloud, updateMap, getGrid, getMapSection*, applyMapSection*, createIndexBoundingBox, addInputSource,
-// setConfig, resetMap, getMapMutex, worldToIndex. Persistence, morphology, artificial areas, raytrace and fast_mode are out
-// of scope of this build and are not declared (a translation unit that needs them keeps using the reference).
+// setConfig, resetMap, getMapMutex, worldToIndex, addPointsToGrid, removePointsFromGrid, addArtificialAreas,
+// restoreMapIntegrity, plus createUpdate / applyUpdate (remote-mapping deltas; see vdbm_b200.h for the level semantics).
+// Persistence, morphology, raytrace and fast_mode are out of scope of this build and are not declared (a translation
+// unit that needs them keeps using the reference).
 // The device arithmetic implements the OccupancyVDBMapping node operations (TData = float); the protected virtual
 // update*Node hooks of the reference cannot be honoured on the device and are therefore not part of this class.
 #ifndef VDB_MAPPING_VDB_MAPPING_H_INCLUDED
@@ -402,6 +404,86 @@ public:
     else m_mirror_stale = true;
   }
 
+  /*! R:413-429 */
+  bool removePointsFromGrid(const typename PointCloudT::ConstPtr& cloud) { return setPoints(cloud, 0); }
+  /*! R:431-447 */
+  bool addPointsToGrid(const typename PointCloudT::ConstPtr& cloud) { return setPoints(cloud, 1); }
+
+  /*! R:1152-1166 */
+  void restoreMapIntegrity()
+  {
+    if (!m_device_map) return;
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_map_integrity_restore(m_device_map));
+    m_artificial_areas_present = false;
+    afterMapWriteLocked();
+  }
+
+  /*! R:1175-1189 (the walls reach the map with the next updateMap, exactly like R:785-789) */
+  void addArtificialAreas(const std::vector<std::vector<Eigen::Matrix<double, 4, 1> > >& artificial_areas,
+                          const double negative_height,
+                          const double positive_height)
+  {
+    if (!m_device_map) return;
+    std::vector<std::uint32_t> counts;
+    std::vector<double> xyz;
+    for (const auto& area : artificial_areas)
+    {
+      counts.push_back(static_cast<std::uint32_t>(area.size()));
+      for (const auto& p : area) xyz.insert(xyz.end(), {p[0], p[1], p[2]});
+    }
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_artificial_areas_add(m_device_map, counts.size(), counts.data(), xyz.data(), negative_height, positive_height));
+    m_artificial_areas_present = true;
+    afterMapWriteLocked(); // the implied restoreMapIntegrity may have changed flags
+  }
+
+  /*! Remote-mapping delta of one source (north_star "createUpdate"; levels in vdbm_b200.h): 0 raw update grid, 1 change
+   *  grid of the last integrate, 2 reduced update (ray end voxels). `origin` receives the scan origin (needed by
+   *  applyUpdate for level 2). Call levels 0 / 2 between accumulateUpdate and integrateUpdate. */
+  typename UpdateGridT::Ptr createUpdate(const std::string& source_id, int level, Eigen::Matrix<double, 3, 1>* origin = nullptr)
+  {
+    typename UpdateGridT::Ptr out = BackendT::createUpdateGrid(m_resolution);
+    if (!m_device_map) return out;
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    vdbm_leafset* ls = nullptr;
+    double o[3]      = {0, 0, 0};
+    if (report(vdbm_update_create(m_device_map, source_id.c_str(), level, &ls, o)) != VDBM_OK) return out;
+    if (origin) *origin = Eigen::Matrix<double, 3, 1>(o[0], o[1], o[2]);
+    const std::uint64_t n = vdbm_leafset_size(ls);
+    for (std::uint64_t i = 0; i < n; ++i)
+      BackendT::putUpdateLeaf(*out, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_active(ls) + 8 * i, vdbm_leafset_valmask(ls) + 8 * i);
+    vdbm_leafset_free(ls);
+    return out;
+  }
+
+  /*! Applies a grid made by createUpdate(level) on another map; returns the change grid (empty for level 1). */
+  typename UpdateGridT::Ptr applyUpdate(const typename UpdateGridT::Ptr& update, int level,
+                                        const Eigen::Matrix<double, 3, 1>& origin = Eigen::Matrix<double, 3, 1>(0, 0, 0))
+  {
+    typename UpdateGridT::Ptr change = BackendT::createUpdateGrid(m_resolution);
+    if (!m_device_map || !update) return change;
+    std::vector<std::int32_t> origins;
+    std::vector<std::uint64_t> active, value;
+    BackendT::forEachUpdateLeaf(*update, [&](const std::int32_t o[3], const std::uint64_t* a, const std::uint64_t* v) {
+      origins.insert(origins.end(), o, o + 3);
+      active.insert(active.end(), a, a + 8);
+      value.insert(value.end(), v, v + 8);
+    });
+    const double o[3] = {origin.x(), origin.y(), origin.z()};
+    std::unique_lock map_lock(*m_map_mutex);
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    vdbm_leafset* ls = nullptr;
+    if (report(vdbm_update_apply(m_device_map, level, origins.size() / 3, origins.data(), active.data(), value.data(), o, &ls)) != VDBM_OK)
+      return change;
+    const std::uint64_t n = ls ? vdbm_leafset_size(ls) : 0;
+    for (std::uint64_t i = 0; i < n; ++i)
+      BackendT::putUpdateLeaf(*change, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_active(ls) + 8 * i, vdbm_leafset_valmask(ls) + 8 * i);
+    if (ls) vdbm_leafset_free(ls);
+    afterMapWriteLocked();
+    return change;
+  }
+
   /*! R:1343 */
   std::shared_ptr<std::shared_mutex> getMapMutex() { return m_map_mutex; }
 
@@ -449,6 +531,22 @@ protected:
     if (rc != VDBM_OK && rc != VDBM_ERR_UNKNOWN_SOURCE && m_device_map)
       std::cerr << "vdb_mapping (B200): " << vdbm_last_error(m_device_map) << std::endl;
     return rc;
+  }
+
+  /*! after a device-side map write (caller holds m_device_mutex) */
+  void afterMapWriteLocked()
+  {
+    if (m_mirror_mode == MirrorMode::Eager) syncMirrorLocked();
+    else m_mirror_stale = true;
+  }
+
+  bool setPoints(const typename PointCloudT::ConstPtr& cloud, int occupied)
+  {
+    if (!m_device_map || !cloud) return true; // the reference returns true unconditionally (R:428,446)
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_points_set(m_device_map, cloud->points.data(), cloud->points.size(), sizeof(PointT), occupied));
+    afterMapWriteLocked();
+    return true;
   }
 
   void ensureScratchSource()
@@ -548,6 +646,7 @@ protected:
   MirrorMode m_mirror_mode = MirrorMode::Eager;
   mutable bool m_mirror_stale = false;
   bool m_scratch_ready        = false;
+  bool m_artificial_areas_present = false; // R:1529
   mutable std::mutex m_device_mutex; // serialises calls into the (thread-compatible) C ABI handle
   mutable std::shared_ptr<std::shared_mutex> m_map_mutex;
   mutable std::atomic<bool> m_map_mutex_requested{false};

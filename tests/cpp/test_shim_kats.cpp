@@ -184,4 +184,85 @@ TEST(Shim, LazyMirrorSyncsOnGetGrid)
   EXPECT_EQ(st.rays, std::uint64_t(2));
 }
 
+TEST(Shim, ReducedUpdateReproducesTheSenderOnARemoteMap)
+{
+  // createUpdate(level 2) ships one voxel per ray + the origin; applyUpdate re-raycasts it: the remote map equals the
+  // sender's. Level 1 (the change grid) pins the flipped voxels to the clamping bounds.
+  const Config conf = gtestConfig(10);
+  OccupancyVDBMapping sender(0.1), remote(0.1), overwritten(0.1);
+  for (OccupancyVDBMapping* m : {&sender, &remote, &overwritten})
+  {
+    m->setConfig(conf);
+    m->addInputSource("test", conf.max_range, 0);
+  }
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0.45f, 0.13f, 0.0f);
+  cloud->points.emplace_back(-0.2f, 0.35f, 0.1f);
+  cloud->points.emplace_back(30.0f, 1.0f, 0.5f); // clipped at max range: carves free space, no hit
+  Eigen::Matrix<double, 3, 1> origin(0.013, 0.02, 0.0), got_origin(9, 9, 9);
+  sender.accumulateUpdate(cloud, origin, "test");
+  auto reduced = sender.createUpdate("test", 2, &got_origin);
+  auto raw     = sender.createUpdate("test", 0);
+  EXPECT_EQ(got_origin.x(), origin.x());
+  EXPECT_EQ(got_origin.z(), origin.z());
+  EXPECT_EQ(reduced->activeVoxelCount(), std::uint64_t(3));
+  EXPECT_TRUE(raw->activeVoxelCount() > 100);
+  sender.integrateUpdate();
+  auto change = remote.applyUpdate(reduced, 2, got_origin);
+  EXPECT_TRUE(change->getAccessor().getValue(openvdb::Coord(4, 1, 0))); // hit flipped to active
+  OccupancyVDBMapping::GridT::Accessor sacc = sender.getGrid()->getAccessor();
+  OccupancyVDBMapping::GridT::Accessor racc = remote.getGrid()->getAccessor();
+  EXPECT_EQ(sender.getGrid()->activeVoxelCount(), remote.getGrid()->activeVoxelCount());
+  for (int x = -3; x <= 100; ++x)
+    for (int y = -1; y <= 5; ++y)
+      for (int z = -1; z <= 2; ++z)
+      {
+        const openvdb::Coord c(x, y, z);
+        EXPECT_EQ(sacc.getValue(c), racc.getValue(c));
+        EXPECT_EQ(sacc.isValueOn(c), racc.isValueOn(c));
+      }
+  overwritten.applyUpdate(change, 1);
+  OccupancyVDBMapping::GridT::Accessor oacc = overwritten.getGrid()->getAccessor();
+  EXPECT_TRUE(oacc.isValueOn(openvdb::Coord(4, 1, 0)));
+  EXPECT_EQ(oacc.getValue(openvdb::Coord(4, 1, 0)), logOdds(0.99));
+}
+
+TEST(Shim, PointEditsAndArtificialAreas)
+{
+  OccupancyVDBMapping map(0.1);
+  const Config conf = gtestConfig(10);
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  OccupancyVDBMapping::PointCloudT::Ptr pts(new OccupancyVDBMapping::PointCloudT);
+  pts->points.emplace_back(0.55f, 0.0f, 0.0f);
+  pts->points.emplace_back(0.2f, 0.0f, 0.0f); // exactly on a voxel boundary: plain floor(p / res) -> voxel 2
+  EXPECT_TRUE(map.addPointsToGrid(pts));
+  OccupancyVDBMapping::GridT::Accessor acc = map.getGrid()->getAccessor();
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(5, 0, 0)));
+  EXPECT_EQ(acc.getValue(openvdb::Coord(5, 0, 0)), logOdds(0.99));
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(2, 0, 0)));
+  EXPECT_TRUE(map.removePointsFromGrid(pts));
+  EXPECT_FALSE(acc.isValueOn(openvdb::Coord(5, 0, 0)));
+  EXPECT_EQ(acc.getValue(openvdb::Coord(5, 0, 0)), logOdds(0.01));
+  // a wall from (1,1) to (1,2) m, heights [-0.1, 0.2): invisible until the next updateMap, then always active
+  std::vector<std::vector<Eigen::Matrix<double, 4, 1> > > areas(1);
+  Eigen::Matrix<double, 4, 1> a, b;
+  a[0] = 1.0; a[1] = 1.0; a[2] = 0.0; a[3] = 1.0;
+  b[0] = 1.0; b[1] = 2.0; b[2] = 0.0; b[3] = 1.0;
+  areas[0] = {a, b};
+  map.addArtificialAreas(areas, -0.1, 0.2);
+  EXPECT_FALSE(acc.isValueOn(openvdb::Coord(10, 15, 0)));
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0.0f, 0.0f, 0.5f);
+  Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  map.insertPointCloud(cloud, origin, "test");
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(10, 15, 0)));
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(10, 15, 1)));
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(10, 15, -1)));
+  EXPECT_FALSE(acc.isValueOn(openvdb::Coord(10, 15, 2)));
+  EXPECT_EQ(acc.getValue(openvdb::Coord(10, 15, 0)), 0.0f);
+  map.restoreMapIntegrity(); // value 0 is not above the occupancy threshold -> inactive again
+  EXPECT_FALSE(acc.isValueOn(openvdb::Coord(10, 15, 0)));
+}
+
 int main() { return RUN_ALL_TESTS(); }

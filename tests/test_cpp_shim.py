@@ -28,6 +28,8 @@ def test_shim_public_surface_matches_the_reference_names():
     for name in ["insertPointCloud", "accumulateUpdate", "addDataToAccumulate", "integrateUpdate", "raycastPointCloud", "worldToIndex",
                  "updateMap", "getGrid", "createIndexBoundingBox", "getMapSectionUpdateGrid", "getMapSectionGrid", "getMapMutex",
                  "addInputSource", "setConfig", "resetMap", "createVDBMap", "struct BaseConfig", "struct InputSource",
+                 "addPointsToGrid", "removePointsFromGrid", "addArtificialAreas", "restoreMapIntegrity", "applyMapSectionGrid",
+                 "applyMapSectionUpdateGrid", "createUpdate", "applyUpdate",
                  "using PointCloudT", "using GridT", "using UpdateGridT"]:
         assert name in hdr, name
     occ = open(os.path.join(ROOT, "include", "vdb_mapping", "OccupancyVDBMapping.hpp")).read()

@@ -537,7 +537,9 @@ vdbm_leafset* newLeafset(vdbm_map* m, uint64_t n, bool with_valmask, bool with_v
   auto up  = [](size_t b) { return (b + 255) & ~size_t(255); };
   const size_t b_or = up(n * 12), b_ac = up(n * 64), b_vm = with_valmask ? up(n * 64) : 0, b_va = with_values ? up(n * 2048) : 0;
   const size_t total = b_or + b_ac + b_vm + b_va;
-  if (m && total >= (size_t(8) << 20) && !m->h_stage_lent)
+  // sets of 1 MB and more borrow the handle's persistent pinned staging buffer; everything else (and a second large
+  // set while the buffer is lent) lives in plain pageable memory: page-locking per call costs more than it saves
+  if (m && total >= (size_t(1) << 20) && !m->h_stage_lent)
   {
     if (m->h_stage_cap < total)
     {
@@ -560,7 +562,7 @@ vdbm_leafset* newLeafset(vdbm_map* m, uint64_t n, bool with_valmask, bool with_v
       return ls;
     }
   }
-  ls->pinned = (n * (with_values ? 2048 : 128)) >= (1u << 20);
+  ls->pinned  = false;
   ls->origins = static_cast<int32_t*>(hostAlloc(n * 12, ls->pinned));
   ls->active  = static_cast<uint64_t*>(hostAlloc(n * 64, ls->pinned));
   if (with_valmask) ls->valmask = static_cast<uint64_t*>(hostAlloc(n * 64, ls->pinned));
@@ -592,29 +594,29 @@ int sortByKey(vdbm_map* m, uint64_t*& keys, uint32_t*& idx, uint64_t* keys_alt, 
   return VDBM_OK;
 }
 
-// export n LeafRecords that live on the device (unsorted) as a sorted bool leaf set
+// export n LeafRecords that live on the device (unsorted) as a sorted bool leaf set: sort (key, index) on the device,
+// split the records in that order, copy the three arrays straight into the leaf set
 int recordsToLeafset(vdbm_map* m, const LeafRecord* d_recs, uint32_t n, vdbm_leafset** out)
 {
   vdbm_leafset* ls = newLeafset(m, n, true, false);
   *out             = ls;
   if (n == 0) return VDBM_OK;
-  // D2H the records, sort on the host by key (records are 136 B; change grids / sections are small)
-  std::vector<LeafRecord> recs(n);
-  CU_TRY(m, cudaMemcpyAsync(recs.data(), d_recs, size_t(n) * sizeof(LeafRecord), cudaMemcpyDeviceToHost, m->stream));
+  TempBuf k0(m->stream), k1(m->stream), i0(m->stream), i1(m->stream), so(m->stream), sa(m->stream), sv(m->stream);
+  CU_TRY(m, k0.alloc(size_t(n) * 8)); CU_TRY(m, k1.alloc(size_t(n) * 8));
+  CU_TRY(m, i0.alloc(size_t(n) * 4)); CU_TRY(m, i1.alloc(size_t(n) * 4));
+  CU_TRY(m, so.alloc(size_t(n) * 12)); CU_TRY(m, sa.alloc(size_t(n) * 64)); CU_TRY(m, sv.alloc(size_t(n) * 64));
+  uint64_t* keys = k0.as<uint64_t>();
+  uint32_t* idx  = i0.as<uint32_t>();
+  launchRecordKeys(d_recs, n, keys, idx, m->stream);
+  int rc = sortByKey(m, keys, idx, k1.as<uint64_t>(), i1.as<uint32_t>(), n);
+  if (rc) return rc;
+  launchSplitRecords(d_recs, idx, n, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<uint64_t>(), m->stream);
+  CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(ls->active, sa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(ls->valmask, sv.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
-  std::vector<uint32_t> order(n);
-  for (uint32_t i = 0; i < n; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return recs[a].key < recs[b].key; });
-  for (uint32_t i = 0; i < n; ++i)
-  {
-    const LeafRecord& r = recs[order[i]];
-    unpackLeafOrigin(r.key, ls->origins[3 * i], ls->origins[3 * i + 1], ls->origins[3 * i + 2]);
-    std::memcpy(ls->active + size_t(i) * 8, r.active, 64);
-    std::memcpy(ls->valmask + size_t(i) * 8, r.value, 64);
-  }
   return VDBM_OK;
 }
-
 
 // a bool grid's touched leaves as a sorted leaf set (origin, active mask, value mask)
 int exportGrid(vdbm_map* m, Source& src, vdbm_leafset** out)
@@ -635,7 +637,7 @@ int exportGrid(vdbm_map* m, Source& src, vdbm_leafset** out)
   int rc = sortByKey(m, keys, idx, k1.as<uint64_t>(), i1.as<uint32_t>(), n);
   if (rc) return rc;
   launchGatherUpdate(s->g, n, keys, idx, recs.as<LeafRecord>(), m->stream);
-  launchSplitRecords(recs.as<LeafRecord>(), n, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<uint64_t>(), m->stream);
+  launchSplitRecords(recs.as<LeafRecord>(), nullptr, n, so.as<int32_t>(), sa.as<uint64_t>(), sv.as<uint64_t>(), m->stream);
   CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaMemcpyAsync(ls->active, sa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaMemcpyAsync(ls->valmask, sv.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
@@ -679,22 +681,28 @@ int importRecords(vdbm_map* m, Source& s, const LeafRecord* d_records, uint64_t 
   return rc;
 }
 
-// host leaf arrays -> device LeafRecords (stream-ordered temporary)
-int uploadRecords(vdbm_map* m, TempBuf& d, uint64_t n, const int32_t* origins, const uint64_t* active, const uint64_t* value)
+// host leaf arrays (ABI layout) -> OR-ed into the grid of `s`. The arrays are copied as they are (three H2D copies) and
+// unpacked by the import kernel; nothing is repacked on the host.
+int importLeafArrays(vdbm_map* m, Source& s, uint64_t n, const int32_t* origins, const uint64_t* active, const uint64_t* value)
 {
-  std::vector<LeafRecord> recs(n);
-  for (uint64_t i = 0; i < n; ++i)
+  if (n == 0) return VDBM_OK;
+  TempBuf d_o(m->stream), d_a(m->stream), d_v(m->stream);
+  CU_TRY(m, d_o.alloc(n * 12)); CU_TRY(m, d_a.alloc(n * 64));
+  CU_TRY(m, cudaMemcpyAsync(d_o.p, origins, n * 12, cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(d_a.p, active, n * 64, cudaMemcpyHostToDevice, m->stream));
+  if (value)
   {
-    for (int k = 0; k < 3; ++k)
-      if (std::abs(int64_t(origins[3 * i + k])) >= kVoxelLimit) return fail(m, VDBM_ERR_COORD_RANGE, "leaf origin outside the +-2^23 voxel range");
-    recs[i].key = packLeafKey(origins[3 * i] >> 3, origins[3 * i + 1] >> 3, origins[3 * i + 2] >> 3);
-    std::memcpy(recs[i].active, active + 8 * i, 64);
-    if (value) std::memcpy(recs[i].value, value + 8 * i, 64);
-    else std::memset(recs[i].value, 0, 64);
+    CU_TRY(m, d_v.alloc(n * 64));
+    CU_TRY(m, cudaMemcpyAsync(d_v.p, value, n * 64, cudaMemcpyHostToDevice, m->stream));
   }
-  CU_TRY(m, d.alloc(n * sizeof(LeafRecord)));
-  CU_TRY(m, cudaMemcpyAsync(d.p, recs.data(), n * sizeof(LeafRecord), cudaMemcpyHostToDevice, m->stream));
-  CU_TRY(m, cudaStreamSynchronize(m->stream)); // `recs` is pageable and dies with this frame
+  int rc = markIntoGrid(m, s, [&] { launchImportUpdateSoA(s.g, d_o.as<int32_t>(), d_a.as<uint64_t>(), value ? d_v.as<uint64_t>() : nullptr, n, m->d_ctr, m->stream); });
+  m->stats.last_touched_leaves = s.n_entries;
+  if (rc) return rc;
+  if (m->h_ctr->flags & kFlagCoordRange)
+  {
+    CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+    return fail(m, VDBM_ERR_COORD_RANGE, "leaf origin outside the +-2^23 voxel range");
+  }
   return VDBM_OK;
 }
 
@@ -761,6 +769,16 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
     if (cudaSetDevice(params->device) != cudaSuccess) return VDBM_ERR_CUDA;
   }
   cudaGetDevice(&m->device);
+  {
+    // stream-ordered temporaries (exports, sections, imports) come from the device's default memory pool: keep freed
+    // blocks cached instead of returning them to the driver at every synchronisation (the default threshold is 0)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, m->device) == cudaSuccess && pool)
+    {
+      uint64_t keep = ~uint64_t(0);
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (params->stream) m->stream = static_cast<cudaStream_t>(params->stream);
   else
   {
@@ -1023,10 +1041,7 @@ int vdbm_update_import(vdbm_map* m, const char* source_id, uint64_t n, const int
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   if (n == 0) return VDBM_OK;
-  TempBuf d(m->stream);
-  int rc = uploadRecords(m, d, n, origins, active, value);
-  if (rc) return rc;
-  return importRecords(m, *s, d.as<LeafRecord>(), n);
+  return importLeafArrays(m, *s, n, origins, active, value);
 }
 
 int vdbm_update_import_device(vdbm_map* m, const char* source_id, const void* d_records, uint64_t n)
@@ -1069,14 +1084,8 @@ int vdbm_update_apply(vdbm_map* m, int level, uint64_t n, const int32_t* origins
   int rc = scratchGrid(m);
   if (rc) return rc;
   Source& sc = *m->scratch;
-  if (n)
-  {
-    TempBuf d(m->stream);
-    rc = uploadRecords(m, d, n, origins, active, value);
-    if (rc) return rc;
-    rc = importRecords(m, sc, d.as<LeafRecord>(), n);
-    if (rc) return rc;
-  }
+  rc = importLeafArrays(m, sc, n, origins, active, value);
+  if (rc) return rc;
   m->stats.last_touched_leaves = 0;
   const uint64_t upd_before    = m->stats.voxel_updates;
   if (level == 1)
@@ -1297,34 +1306,27 @@ int vdbm_section(vdbm_map* m, const int32_t bbmin[3], const int32_t bbmax[3], in
   vdbm_leafset* ls = newLeafset(m, n, !result_float, result_float != 0);
   *out             = ls;
   if (n == 0) return VDBM_OK;
-  // small result: sort on the host by key
-  std::vector<uint64_t> keys(n);
-  std::vector<uint64_t> act(size_t(n) * 8), vm;
-  std::vector<float> vals;
-  CU_TRY(m, cudaMemcpyAsync(keys.data(), dk.p, size_t(n) * 8, cudaMemcpyDeviceToHost, m->stream));
-  CU_TRY(m, cudaMemcpyAsync(act.data(), da.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
-  if (result_float)
-  {
-    vals.resize(size_t(n) * 512);
-    CU_TRY(m, cudaMemcpyAsync(vals.data(), df.p, size_t(n) * 2048, cudaMemcpyDeviceToHost, m->stream));
-  }
-  else
-  {
-    vm.resize(size_t(n) * 8);
-    CU_TRY(m, cudaMemcpyAsync(vm.data(), dv.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
-  }
+  // sort (key, row) on the device, permute the rows into key order, copy straight into the leaf set
+  TempBuf k1(m->stream), i0(m->stream), i1(m->stream), so(m->stream), pa(m->stream), pv(m->stream), pf(m->stream);
+  CU_TRY(m, k1.alloc(size_t(n) * 8)); CU_TRY(m, i0.alloc(size_t(n) * 4)); CU_TRY(m, i1.alloc(size_t(n) * 4));
+  CU_TRY(m, so.alloc(size_t(n) * 12)); CU_TRY(m, pa.alloc(size_t(n) * 64));
+  if (result_float) CU_TRY(m, pf.alloc(size_t(n) * 2048));
+  else CU_TRY(m, pv.alloc(size_t(n) * 64));
+  uint64_t* keys = dk.as<uint64_t>();
+  uint32_t* idx  = i0.as<uint32_t>();
+  launchKeysFromIdx(dk.as<uint64_t>(), nullptr, n, k1.as<uint64_t>(), idx, m->stream); // identity permutation (+ key copy)
+  keys              = k1.as<uint64_t>();
+  uint64_t* keys_alt = dk.as<uint64_t>();
+  rc = sortByKey(m, keys, idx, keys_alt, i1.as<uint32_t>(), n);
+  if (rc) return rc;
+  launchPermuteSection(n, keys, idx, da.as<uint64_t>(), result_float ? nullptr : dv.as<uint64_t>(), result_float ? df.as<float>() : nullptr,
+                       so.as<int32_t>(), pa.as<uint64_t>(), pv.as<uint64_t>(), pf.as<float>(), m->stream);
+  CU_TRY(m, cudaGetLastError());
+  CU_TRY(m, cudaMemcpyAsync(ls->origins, so.p, size_t(n) * 12, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(ls->active, pa.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
+  if (result_float) CU_TRY(m, cudaMemcpyAsync(ls->values, pf.p, size_t(n) * 2048, cudaMemcpyDeviceToHost, m->stream));
+  else CU_TRY(m, cudaMemcpyAsync(ls->valmask, pv.p, size_t(n) * 64, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
-  std::vector<uint32_t> order(n);
-  for (uint32_t i = 0; i < n; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
-  for (uint32_t i = 0; i < n; ++i)
-  {
-    const uint32_t j = order[i];
-    unpackLeafOrigin(keys[j], ls->origins[3 * i], ls->origins[3 * i + 1], ls->origins[3 * i + 2]);
-    std::memcpy(ls->active + size_t(i) * 8, act.data() + size_t(j) * 8, 64);
-    if (result_float) std::memcpy(ls->values + size_t(i) * 512, vals.data() + size_t(j) * 512, 2048);
-    else std::memcpy(ls->valmask + size_t(i) * 8, vm.data() + size_t(j) * 8, 64);
-  }
   return VDBM_OK;
 }
 

@@ -236,6 +236,10 @@ void launchRehashMap(MapTable mt, uint32_t n_leaves, Counters* ctr, cudaStream_t
 void launchEntryKeys(UpdateGrid ug, uint32_t n_entries, uint64_t* out_keys, uint32_t* out_entries, cudaStream_t s);
 void launchGatherUpdate(UpdateGrid ug, uint32_t n, const uint64_t* keys, const uint32_t* entries, LeafRecord* out, cudaStream_t s);
 void launchImportUpdate(UpdateGrid ug, const LeafRecord* recs, uint64_t n, Counters* ctr, cudaStream_t s);
+// same from leaf arrays in the ABI's host layout (value may be nullptr = all false); leaf origins outside the voxel
+// range raise kFlagCoordRange and are skipped
+void launchImportUpdateSoA(UpdateGrid ug, const int32_t* origins, const uint64_t* active, const uint64_t* value, uint64_t n, Counters* ctr,
+                           cudaStream_t s);
 void launchGatherMap(MapTable mt, uint32_t n, const uint32_t* leaf_idx, int32_t* origins, uint64_t* mask, float* vals, cudaStream_t s);
 void launchCollectDirty(MapTable mt, uint32_t n_leaves, uint32_t* out_idx, Counters* ctr, cudaStream_t s); // appends via ctr->n_out, clears flags
 void launchSection(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float,
@@ -246,7 +250,11 @@ void launchProbe(MapTable mt, int32_t x, int32_t y, int32_t z, float* out_val, i
 void launchPartition(UpdateGrid ug, uint32_t n_entries, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_cursor,
                      LeafRecord* out, int pass, cudaStream_t s);
 void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, uint64_t* out_keys, uint32_t* out_idx, cudaStream_t s);
-void launchSplitRecords(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s);
+// perm: optional permutation (output row i = record perm[i])
+void launchSplitRecords(const LeafRecord* recs, const uint32_t* perm, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s);
+void launchRecordKeys(const LeafRecord* recs, uint32_t n, uint64_t* keys, uint32_t* idx, cudaStream_t s);
+void launchPermuteSection(uint32_t n, const uint64_t* sorted_keys, const uint32_t* perm, const uint64_t* in_active, const uint64_t* in_valmask,
+                          const float* in_vals, int32_t* origins, uint64_t* out_active, uint64_t* out_valmask, float* out_vals, cudaStream_t s);
 // receiver side of remote mapping (applyMapSection*)
 void launchSectionDeactivate(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], cudaStream_t s);
 void launchSectionActivate(MapTable mt, const uint64_t* keys, const uint64_t* active, uint32_t n, Counters* ctr, cudaStream_t s);

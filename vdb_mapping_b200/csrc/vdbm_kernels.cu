@@ -883,6 +883,37 @@ __global__ void import_update_kernel(UpdateGrid g, const LeafRecord* recs, uint6
   redOr64(dst, word);
 }
 
+// same, from host-layout leaf arrays (origins [n][3], active [n][8], value [n][8]) copied to the device as they are
+__global__ void import_update_soa_kernel(UpdateGrid g, const int32_t* origins, const uint64_t* active, const uint64_t* value, uint64_t n,
+                                         Counters* ctr)
+{
+  const uint64_t t   = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t rec = t >> 4;
+  const int j        = int(t & 15);
+  const bool valid   = rec < n;
+  uint64_t word = 0;
+  if (valid) word = (j < 8) ? active[rec * 8 + j] : (value ? value[rec * 8 + (j - 8)] : 0ull);
+  const unsigned grp = 0xFFFFu << (threadIdx.x & 16);
+  const unsigned nz  = __ballot_sync(kFull, valid && j < 8 && word != 0) & grp;
+  uint32_t slot = kInvalid, lib = 0;
+  if (valid && nz && j == 0)
+  {
+    const int32_t x = origins[rec * 3], y = origins[rec * 3 + 1], z = origins[rec * 3 + 2];
+    if (max(abs(x), max(abs(y), abs(z))) >= kVoxelLimit) atomicOr(&ctr->flags, kFlagCoordRange);
+    else
+    {
+      const uint64_t bkey = brickKeyOfLeaf(packLeafKey(x >> 3, y >> 3, z >> 3), lib);
+      slot                = brickFindOrInsert(g, bkey, ctr);
+    }
+  }
+  slot = __shfl_sync(kFull, slot, (threadIdx.x & 16));
+  lib  = __shfl_sync(kFull, lib, (threadIdx.x & 16));
+  if (slot == kInvalid || word == 0) return;
+  const size_t e = size_t(slot) * kBrickLeaves + lib;
+  uint64_t* dst  = (j < 8) ? g.act + e * 8 + j : g.val + e * 8 + (j - 8);
+  redOr64(dst, word);
+}
+
 // leaf keys of the listed entries (+ the entry ids, for sorting)
 __global__ void entry_keys_kernel(UpdateGrid g, uint32_t n, uint64_t* out_keys, uint32_t* out_entries)
 {
@@ -915,23 +946,65 @@ __global__ void gather_update_kernel(UpdateGrid g, uint32_t n, const uint64_t* k
   if (j == 0) out[i].key = keys[i];
 }
 
-__global__ void split_records_kernel(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value)
+__global__ void split_records_kernel(const LeafRecord* recs, const uint32_t* perm, uint32_t n, int32_t* origins, uint64_t* active,
+                                     uint64_t* value)
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = t >> 4;
   const int j      = t & 15;
   if (i >= n) return;
-  if (j < 8) active[size_t(i) * 8 + j] = recs[i].active[j];
-  else value[size_t(i) * 8 + (j - 8)] = recs[i].value[j - 8];
+  const LeafRecord& r = recs[perm ? perm[i] : i];
+  if (j < 8) active[size_t(i) * 8 + j] = r.active[j];
+  else value[size_t(i) * 8 + (j - 8)] = r.value[j - 8];
   if (j == 0)
   {
     int32_t x, y, z;
-    unpackLeafOrigin(recs[i].key, x, y, z);
+    unpackLeafOrigin(r.key, x, y, z);
     origins[3 * size_t(i)] = x; origins[3 * size_t(i) + 1] = y; origins[3 * size_t(i) + 2] = z;
   }
 }
 
-// K4: map leaves listed in leaf_idx -> SoA staging (one warp per leaf, 2 KB values with 256-bit accesses)
+__global__ void record_keys_kernel(const LeafRecord* recs, uint32_t n, uint64_t* keys, uint32_t* idx)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = recs[i].key;
+  idx[i]  = i;
+}
+
+// section rows (written in arrival order by section_kernel) -> rows in sorted-key order + leaf origins. Warp per leaf.
+__global__ void __launch_bounds__(256) permute_section_kernel(uint32_t n, const uint64_t* sorted_keys, const uint32_t* perm, const uint64_t* in_active,
+                                                             const uint64_t* in_valmask, const float* in_vals, int32_t* origins,
+                                                             uint64_t* out_active, uint64_t* out_valmask, float* out_vals)
+{
+  const int lane         = threadIdx.x & 31;
+  const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < n; i += n_warps)
+  {
+    const uint32_t j = perm[i];
+    if (lane < 8)
+    {
+      out_active[size_t(i) * 8 + lane] = in_active[size_t(j) * 8 + lane];
+      if (in_valmask) out_valmask[size_t(i) * 8 + lane] = in_valmask[size_t(j) * 8 + lane];
+    }
+    if (in_vals)
+    {
+      float a[8], b[8];
+      ld256(in_vals + size_t(j) * 512 + lane * 16, a);
+      ld256(in_vals + size_t(j) * 512 + lane * 16 + 8, b);
+      st256(out_vals + size_t(i) * 512 + lane * 16, a);
+      st256(out_vals + size_t(i) * 512 + lane * 16 + 8, b);
+    }
+    if (lane == 0)
+    {
+      int32_t x, y, z;
+      unpackLeafOrigin(sorted_keys[i], x, y, z);
+      origins[3 * size_t(i)] = x; origins[3 * size_t(i) + 1] = y; origins[3 * size_t(i) + 2] = z;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_map_kernel(MapTable mt, uint32_t n, const uint32_t* leaf_idx, int32_t* origins,
                                                         uint64_t* mask, float* vals)
 {
@@ -1772,6 +1845,11 @@ void launchGatherUpdate(UpdateGrid g, uint32_t n, const uint64_t* keys, const ui
 {
   if (n) VDBM_LAUNCH(gather_update_kernel, blocksFor(uint64_t(n) * 16, 256), 256, s, g, n, keys, entries, out);
 }
+void launchImportUpdateSoA(UpdateGrid g, const int32_t* origins, const uint64_t* active, const uint64_t* value, uint64_t n, Counters* ctr,
+                           cudaStream_t s)
+{
+  if (n) VDBM_LAUNCH(import_update_soa_kernel, blocksFor(n * 16, 256), 256, s, g, origins, active, value, n, ctr);
+}
 void launchImportUpdate(UpdateGrid g, const LeafRecord* recs, uint64_t n, Counters* ctr, cudaStream_t s)
 {
   if (n) VDBM_LAUNCH(import_update_kernel, blocksFor(n * 16, 256), 256, s, g, recs, n, ctr);
@@ -1808,9 +1886,23 @@ void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, ui
 {
   if (n) VDBM_LAUNCH(keys_from_idx_kernel, blocksFor(n, 256), 256, s, keys, idx, n, out_keys, out_idx);
 }
-void launchSplitRecords(const LeafRecord* recs, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s)
+void launchSplitRecords(const LeafRecord* recs, const uint32_t* perm, uint32_t n, int32_t* origins, uint64_t* active, uint64_t* value, cudaStream_t s)
 {
-  if (n) VDBM_LAUNCH(split_records_kernel, blocksFor(uint64_t(n) * 16, 256), 256, s, recs, n, origins, active, value);
+  if (n == 0) return;
+  VDBM_LAUNCH(split_records_kernel, blocksFor(uint64_t(n) * 16, 256), 256, s, recs, perm, n, origins, active, value);
+}
+void launchRecordKeys(const LeafRecord* recs, uint32_t n, uint64_t* keys, uint32_t* idx, cudaStream_t s)
+{
+  if (n == 0) return;
+  VDBM_LAUNCH(record_keys_kernel, blocksFor(n, 256), 256, s, recs, n, keys, idx);
+}
+void launchPermuteSection(uint32_t n, const uint64_t* sorted_keys, const uint32_t* perm, const uint64_t* in_active, const uint64_t* in_valmask,
+                          const float* in_vals, int32_t* origins, uint64_t* out_active, uint64_t* out_valmask, float* out_vals, cudaStream_t s)
+{
+  if (n == 0) return;
+  const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(n) * 32 + 255) / 256, 148ull * 16));
+  VDBM_LAUNCH(permute_section_kernel, dim3(blocks), dim3(256), s, n, sorted_keys, perm, in_active, in_valmask, in_vals, origins, out_active,
+              out_valmask, out_vals);
 }
 
 void launchSectionDeactivate(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], cudaStream_t s)
