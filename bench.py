@@ -215,10 +215,78 @@ def run_reference(args, rank, world):
         "visits_per_sec": (s1["visits"] - s0["visits"]) / dt,
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": 1, "kind": "port", "sample": sample,
                          "note": "restated reference (OpenVDB-free oracle, tree+accessor cost model); the reference path is "
-                                 "single-threaded per input source; host has %d logical cores" % (os.cpu_count() or 0)},
+                                 "single-threaded per input source; host has %d logical cores" % (os.cpu_count() or 0),
+                         "multi_source": (cpu_multi_source_leg(cfg, 4, stride) if not mixed else None),
+                         "optimistic_flat_hash": (cpu_flat_probe_leg(cfg, 4, stride) if not mixed else None)},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+def cpu_multi_source_leg(cfg: int, n_scans: int, stride: int = 1):
+    """SURVEY.md 8(d) 'S-source variant': the reference's only parallelism is one accumulation thread per input source plus
+    one integrator (VDBMapping.hpp:1373,1416). The scan is split into S azimuth sectors fed as S sources: S threads raycast
+    concurrently into their own update grids, then updateMap runs per source, serially, under the map lock."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import OracleOccupancyVDBMapping
+    c = scans.CONFIGS[cfg]
+    S = max(1, min(4, (os.cpu_count() or 2) - 1))
+    m = OracleOccupancyVDBMapping(c.resolution)
+    m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+    ids = [f"s{i}" for i in range(S)]
+    for i in ids:
+        m.addInputSource(i, c.max_range)
+    clouds = []
+    for k in range(n_scans):
+        pts, origin = scans.make_scan(cfg, k)
+        per = pts.shape[0] // stride
+        pts = pts[(k % stride) * per:(k % stride) * per + per]
+        parts = [np.ascontiguousarray(pts[i * len(pts) // S:(i + 1) * len(pts) // S]) for i in range(S)]
+        clouds.append((parts, origin))
+    rays = 0
+    with ThreadPoolExecutor(max_workers=S) as pool:
+        t0 = time.perf_counter()
+        for parts, origin in clouds:
+            list(pool.map(lambda a: m.accumulateUpdate(a[1], origin, a[0]), zip(ids, parts)))
+            m.integrateUpdate()
+            rays += sum(len(p) for p in parts)
+        dt = time.perf_counter() - t0
+    return {"value": rays / dt, "unit": "rays/s", "sources": S, "threads": S, "ms_per_scan": 1e3 * dt / n_scans,
+            "sample": f"{n_scans} scan(s)" + (f", a 1/{stride} azimuth sector each" if stride > 1 else "") + f", split into {S} sources",
+            "note": "S accumulation threads + serial updateMap per source; voxels seen by several sources are updated once per source"}
+
+
+def cpu_flat_probe_leg(cfg: int, n_scans: int, stride: int = 1):
+    """SURVEY.md 8(d) 'optimistic CPU': oracle/flat_probe.cpp — same arithmetic on a flat leaf hash (no OpenVDB-style tree,
+    no virtual calls), single-threaded and with all host threads. A yardstick, not the reference."""
+    from oracle.oracle import FlatProbe, OracleOccupancyVDBMapping
+    c = scans.CONFIGS[cfg]
+    o = OracleOccupancyVDBMapping(c.resolution)
+    o.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+    lo = o.logodds()
+    clouds = []
+    for k in range(n_scans):
+        pts, origin = scans.make_scan(cfg, k)
+        per = pts.shape[0] // stride
+        clouds.append((np.ascontiguousarray(pts[(k % stride) * per:(k % stride) * per + per]), origin))
+    out = {}
+    for name, threads in (("single_thread", 1), ("all_threads", max(1, os.cpu_count() or 1))):
+        f = FlatProbe(c.resolution, lo)
+        f.insert(clouds[0][0], clouds[0][1], c.max_range, threads=threads)  # untimed: sizes the hash tables
+        st0 = f.stats()
+        t0 = time.perf_counter()
+        rays = 0
+        for pts, origin in clouds:
+            f.insert(pts, origin, c.max_range, threads=threads)
+            rays += len(pts)
+        dt = time.perf_counter() - t0
+        st = f.stats()
+        out[name] = {"value": rays / dt, "unit": "rays/s", "threads": threads, "ms_per_scan": 1e3 * dt / n_scans,
+                     "visits_per_sec": (st["visits"] - st0["visits"]) / dt,
+                     "voxel_updates_per_sec": (st["voxel_updates"] - st0["voxel_updates"]) / dt}
+    out["sample"] = f"{n_scans} scan(s)" + (f", a 1/{stride} azimuth sector each" if stride > 1 else "")
+    out["note"] = "flat 8^3-leaf hash + last-leaf cache instead of the OpenVDB-style tree; threads = private update grids, OR-merge, leaf-parallel update"
+    return out
 
 
 def cpu_baseline_leg(cfg: int, n_scans: int):
@@ -233,11 +301,15 @@ def cpu_baseline_leg(cfg: int, n_scans: int):
         m.insertPointCloud(pts, origin, "s")
     dt = time.perf_counter() - t0
     st = m.stats()
-    return {"value": n_scans * c.n_points / dt, "unit": "rays/s", "cores": 1, "kind": "port",
-            "sample": f"first {n_scans} full scans of the same sequence ({dt:.1f} s of CPU work)",
-            "ms_per_scan": 1e3 * dt / n_scans, "voxel_updates_per_sec": st["voxel_updates"] / dt,
-            "visits_per_sec": st["visits"] / dt, "host_logical_cores": os.cpu_count(),
-            "note": "restated reference (OpenVDB-free oracle); serial like the reference's per-source path"}
+    out = {"value": n_scans * c.n_points / dt, "unit": "rays/s", "cores": 1, "kind": "port",
+           "sample": f"first {n_scans} full scans of the same sequence ({dt:.1f} s of CPU work)",
+           "ms_per_scan": 1e3 * dt / n_scans, "voxel_updates_per_sec": st["voxel_updates"] / dt,
+           "visits_per_sec": st["visits"] / dt, "host_logical_cores": os.cpu_count(),
+           "note": "restated reference (OpenVDB-free oracle); serial like the reference's per-source path"}
+    del m
+    out["multi_source"] = cpu_multi_source_leg(cfg, 2)
+    out["optimistic_flat_hash"] = cpu_flat_probe_leg(cfg, 2)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -20,12 +20,48 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libvdbm_oracle.so")
 
 
+_FLAT_SO = os.path.join(_HERE, "libvdbm_flat_probe.so")
+
+
 def build(force: bool = False) -> str:
-    """Compile the oracle with oracle/Makefile (g++). Returns the .so path."""
-    src = os.path.join(_HERE, "vdbm_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    """Compile the oracle (and the flat-hash probe) with oracle/Makefile (g++). Returns the oracle .so path."""
+    stale = False
+    for so, src in ((_SO, "vdbm_oracle.cpp"), (_FLAT_SO, "flat_probe.cpp")):
+        src = os.path.join(_HERE, src)
+        stale = stale or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src)
+    if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _SO
+
+
+class FlatProbe:
+    """The 'optimistic CPU' yardstick of oracle/flat_probe.cpp: same arithmetic on a flat leaf hash, optional threads."""
+
+    def __init__(self, resolution: float, logodds6):
+        build()
+        self._L = C.CDLL(_FLAT_SO)
+        self._L.flat_create.restype = C.c_void_p
+        self._L.flat_create.argtypes = [C.c_double, C.POINTER(C.c_float)]
+        self._L.flat_destroy.argtypes = [C.c_void_p]
+        self._L.flat_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.c_double, C.c_int]
+        self._L.flat_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        lo = np.ascontiguousarray(logodds6, dtype=np.float32)
+        self._h = self._L.flat_create(resolution, lo.ctypes.data_as(C.POINTER(C.c_float)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.flat_destroy(self._h)
+            self._h = None
+
+    def insert(self, points, origin, max_range: float, threads: int = 1):
+        p = _pts16(points)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._L.flat_insert(self._h, p.ctypes.data, p.shape[0], 16, _dp(o), float(max_range), int(threads))
+
+    def stats(self) -> dict:
+        out = np.zeros(4, dtype=np.uint64)
+        self._L.flat_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return dict(zip(["visits", "voxel_updates", "map_leaves", "active_voxels"], (int(x) for x in out)))
 
 
 _lib = None

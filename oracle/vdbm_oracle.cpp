@@ -472,6 +472,7 @@ struct Source
   // voxel indices, so re-raycasting this set from the origin reproduces that call's update grid exactly.
   std::unique_ptr<BoolTree> reduced;
   double last_origin[3] = {0, 0, 0};
+  Stats stats; // raycast counters of this source (own block: sources may accumulate concurrently, one thread each, V:1373)
 };
 
 // VDBMapping<float,Config> + OccupancyVDBMapping node ops, polymorphic like the reference
@@ -531,7 +532,7 @@ struct MappingBase
   }
 
   // V:550-566 + openvdb::math::Ray<double>(eye, dir, 0, 1) + DDA<RayT,0>(ray, 0)
-  void castRayIntoGrid(const Coord& o, const Coord& e, Accessor<BoolTree>& acc)
+  void castRayIntoGrid(const Coord& o, const Coord& e, Accessor<BoolTree>& acc, Stats& st)
   {
     if (e == o) return; // V:559 (ray/dda construction has no side effect)
     double dir[3], inv[3], pos[3], next[3], delta[3];
@@ -571,7 +572,7 @@ struct MappingBase
     do
     {
       setActiveStateOn(acc, voxel); // V:563
-      ++stats.visits;
+      ++st.visits;
       // DDA::step()
       const int key  = (int(next[0] < next[1]) << 2) + (int(next[0] < next[2]) << 1) + int(next[1] < next[2]);
       const int axis = kMinIndexTable[key];
@@ -584,7 +585,7 @@ struct MappingBase
 
   // V:466-539 (fast_mode is out of scope)
   bool raycastPointCloud(const uint8_t* pts, size_t n, size_t stride, const double origin[3], double raycast_range,
-                         Accessor<BoolTree>& update_acc, Accessor<BoolTree>* reduced_acc = nullptr)
+                         Accessor<BoolTree>& update_acc, Stats& st, Accessor<BoolTree>* reduced_acc = nullptr)
   {
     if (!m_config_set) return false; // V:478-482
     const Coord ray_origin_index = worldToIndex(origin);
@@ -595,10 +596,10 @@ struct MappingBase
       std::memcpy(p, pts + i * stride, sizeof(p));
       double end[3]      = {double(p[0]), double(p[1]), double(p[2])}; // V:501
       bool max_range_ray = false;
-      ++stats.rays;
+      ++st.rays;
       if (std::isnan(end[0]) || std::isnan(end[1]) || std::isnan(end[2]) || origin_nan) // V:505-510
       {
-        ++stats.nan_skipped;
+        ++st.nan_skipped;
         continue;
       }
       if (raycast_range > 0.0)
@@ -611,11 +612,11 @@ struct MappingBase
           // origin + (d.unit() * range): unit() = d / len (true division), V:514-515
           for (int a = 0; a < 3; ++a) end[a] = origin[a] + (d[a] / len) * raycast_range;
           max_range_ray = true;
-          ++stats.clipped;
+          ++st.clipped;
         }
       }
       const Coord ray_end_index = worldToIndex(end); // V:519
-      castRayIntoGrid(ray_origin_index, ray_end_index, update_acc); // V:530
+      castRayIntoGrid(ray_origin_index, ray_end_index, update_acc, st); // V:530
       if (!max_range_ray) setValueOnTrue(update_acc, ray_end_index); // V:533-536
       if (reduced_acc)
       {
@@ -638,9 +639,7 @@ struct MappingBase
       s.reduced.reset(new BoolTree(false));
       for (int a = 0; a < 3; ++a) s.last_origin[a] = origin[a];
       Accessor<BoolTree> racc(*s.reduced);
-      const uint64_t visits = stats.visits;
-      if (!raycastPointCloud(pts, n, stride, origin, s.max_range, acc, &racc)) return 2;
-      (void)visits;
+      if (!raycastPointCloud(pts, n, stride, origin, s.max_range, acc, s.stats, &racc)) return 2;
     }
     return 0;
   }
@@ -656,7 +655,7 @@ struct MappingBase
         Coord l = leafOffsetToLocal(n);
         Coord c(rl.origin[0] + l[0], rl.origin[1] + l[1], rl.origin[2] + l[2]);
         ++stats.rays;
-        castRayIntoGrid(o, c, acc);
+        castRayIntoGrid(o, c, acc, stats);
         if (rl.buf.isOn(n)) setValueOnTrue(acc, c);
       }
     });
@@ -720,10 +719,9 @@ struct MappingBase
     const Coord s = worldToIndex(start), e = worldToIndex(end);
     const int negative_index = (int)(negative_height / m_resolution);
     const int positive_index = (int)(positive_height / m_resolution);
-    const uint64_t visits = stats.visits;
+    Stats walls; // walls are not scan rays: keep them out of the counters
     for (int i = negative_index; i < positive_index; ++i)
-      castRayIntoGrid(Coord(s[0], s[1], s[2] + i), Coord(e[0], e[1], e[2] + i), acc);
-    stats.visits = visits; // walls are not scan rays
+      castRayIntoGrid(Coord(s[0], s[1], s[2] + i), Coord(e[0], e[1], e[2] + i), acc, walls);
   }
   // V:1175-1206; polygons: n_poly polygons, counts[p] points each, xyz triples (the 4th homogeneous component is unused)
   void addArtificialAreas(size_t n_poly, const uint32_t* counts, const double* xyz, double negative_height, double positive_height)
@@ -1217,7 +1215,13 @@ int vdbo_insert(void* h, const char* id, const void* pts, uint64_t n, uint64_t s
 // out[6] = rays, nan_skipped, clipped, visits, voxel_updates, state_changes (cumulative)
 void vdbo_stats(void* h, uint64_t* out)
 {
-  auto& s = static_cast<vo::Handle*>(h)->map.stats;
+  auto& m = static_cast<vo::Handle*>(h)->map;
+  vo::Stats s = m.stats;
+  for (auto& kv : m.m_input_sources)
+  {
+    s.rays += kv.second->stats.rays; s.nan_skipped += kv.second->stats.nan_skipped;
+    s.clipped += kv.second->stats.clipped; s.visits += kv.second->stats.visits;
+  }
   out[0] = s.rays; out[1] = s.nan_skipped; out[2] = s.clipped; out[3] = s.visits; out[4] = s.voxel_updates;
   out[5] = s.state_changes;
 }

@@ -373,3 +373,24 @@ def test_artificial_areas():
     mp2 = _voxel_dict(m.exportMap())
     for c in expect:
         assert mp2[c][1] == bool(mp2[c][0] > lo[3])
+
+
+def test_flat_probe_counts_match_the_oracle():
+    """The bench-only 'optimistic CPU' probe (oracle/flat_probe.cpp) walks the same voxels and ends with the same map
+    occupancy as the oracle, single- and multi-threaded."""
+    from oracle.oracle import FlatProbe
+    from vdb_mapping_b200 import scans
+    o = _mk_oracle(res=0.1, rng=4.0, cfg=CFG_ROS)
+    f1, f3 = FlatProbe(0.1, o.logodds()), FlatProbe(0.1, o.logodds())
+    for k in range(4):
+        pts, origin = scans.small_scan(80 + k, n=2500, scale=2.5)
+        origin = origin + 0.037 * k
+        o.insertPointCloud(pts, origin, "s")
+        f1.insert(pts, origin, 4.0, threads=1)
+        f3.insert(pts, origin, 4.0, threads=3)
+    so = o.stats()
+    active = popcount64(o.exportMap().active)
+    for f in (f1, f3):
+        sf = f.stats()
+        assert sf["visits"] == so["visits"] and sf["voxel_updates"] == so["voxel_updates"]
+        assert sf["map_leaves"] == o.mapLeafCount() and sf["active_voxels"] == active
