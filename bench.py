@@ -368,7 +368,7 @@ def run_ours(args, rank, world, local_rank):
                 vdist.connect_peers(m, dist, capacity_records_per_sender=(1 << 22) if cfg == 4 else (1 << 19))
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             acc_ms, prep_ms, int_ms, leaves = [], [], [], []
-            d2h_extra = [0, 0]  # cfg5: bytes read back (reduced updates + sections), sections extracted
+            d2h_extra = [0, 0, 0]  # cfg5: bytes read back (reduced updates + sections), sections extracted, reduced-update bytes
             sent = recv = 0
             st0 = None
             for k in range(n_steps):
@@ -394,6 +394,7 @@ def run_ours(args, rank, world, local_rank):
                     if k >= args.warmup:
                         int_ms.append(m.stats()["last_integrate_ms"])
                         d2h_extra[0] += red.origins.nbytes + red.active.nbytes + red.valmask.nbytes
+                        d2h_extra[2] += red.origins.nbytes + red.active.nbytes + red.valmask.nbytes
                     remote.applyUpdate(2, red, origin=o)     # H2D of the reduced grid, re-raycast, updateMap
                     if k % 10 == 9:
                         lo, hi = section_box(origin, c.resolution)
@@ -515,6 +516,7 @@ def run_ours(args, rank, world, local_rank):
             "sections_per_step": res_v["d2h_extra"][1] / K,
             "note": "rays_per_sec counts the SENDER's rays; every ray is traversed twice (sender + remote); the roofline block describes the sender's scan-step kernels"}
         line["e2e"]["d2h_bytes_per_step"] = 164 + int(res_e["d2h_extra"][0] / K)
+        line["e2e"]["h2d_bytes_per_step"] = 16 * n_pts + int(res_e["d2h_extra"][2] / K)  # cloud + the reduced update fed to the remote map
         line["e2e"]["api"] = "accumulate(host pinned cloud) + createUpdate(2) + integrate + remote applyUpdate(2) + periodic getMapSection*"
         line["config"]["parallelism"] = "1 GPU (sender and remote map)" if world == 1 else f"{world} independent sender/remote pairs, one per GPU"
         line["exchange"] = None
