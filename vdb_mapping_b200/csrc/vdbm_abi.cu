@@ -770,12 +770,13 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
   }
   cudaGetDevice(&m->device);
   {
-    // stream-ordered temporaries (exports, sections, imports) come from the device's default memory pool: keep freed
-    // blocks cached instead of returning them to the driver at every synchronisation (the default threshold is 0)
+    // stream-ordered temporaries (exports, sections, imports) come from the device's default memory pool: keep up to
+    // 2 GB of freed blocks cached instead of returning everything to the driver at every synchronisation (the default
+    // threshold is 0, which turns each export into a round of driver allocations)
     cudaMemPool_t pool = nullptr;
     if (cudaDeviceGetDefaultMemPool(&pool, m->device) == cudaSuccess && pool)
     {
-      uint64_t keep = ~uint64_t(0);
+      uint64_t keep = uint64_t(2) << 30;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
