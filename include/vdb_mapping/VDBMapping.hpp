@@ -203,6 +203,24 @@ public:
                         const Eigen::Matrix<double, 3, 1>& origin,
                         const std::string source_id)
   {
+    if (m_mirror_mode == MirrorMode::Lazy && m_device_map && cloud)
+    {
+      // throughput mode: the scan is queued as one pipeline stage (vdbm_insert_async: upload overlapped with the previous
+      // scan, no host round trip between raycast and updateMap); getGrid() / any other member finishes it
+      auto source = m_input_sources.find(source_id);
+      if (source != m_input_sources.end())
+      {
+        m_map_mutex_requested = true;
+        std::unique_lock map_lock(*m_map_mutex);
+        m_map_mutex_requested = false;
+        std::unique_lock update_grid_lock(source->second->update_grid_mutex);
+        std::lock_guard<std::mutex> device_lock(m_device_mutex);
+        const double o[3] = {origin.x(), origin.y(), origin.z()};
+        report(vdbm_insert_async(m_device_map, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o, 0));
+        m_mirror_stale = true;
+        return true;
+      }
+    }
     accumulateUpdate(cloud, origin, source_id);
     integrateUpdate();
     return true;

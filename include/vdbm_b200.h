@@ -122,6 +122,19 @@ int vdbm_integrate(vdbm_map* map, int keep_change);
 /* insertPointCloud V:399-406 = accumulate + integrate. */
 int vdbm_insert(vdbm_map* map, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes,
                 const double origin[3]);
+/* insertPointCloud V:399-406 as a PIPELINE stage: same result as vdbm_insert, but the call returns once the scan is
+ * queued. The cloud is uploaded on a copy stream while the previous scan still computes, the whole chain (prep, sort,
+ * DDA, compaction, updateMap) is queued without a host round trip in between (a one-thread guard kernel takes the
+ * capacity decisions on the device), and the single host synchronisation of a scan happens when the NEXT call on the
+ * handle - any entry point except vdbm_stats / vdbm_last_error - finishes it. Scans the queued path cannot take (tables
+ * that must grow, long rays that need segmentation, several sources holding data, artificial areas, the first scans of a
+ * map) run synchronously inside the call or are redone by the finishing call; results are identical either way. A status
+ * belonging to a queued scan (e.g. VDBM_ERR_COORD_RANGE) is returned by the call that finishes it. points_on_device != 0:
+ * `points` is device memory and must stay valid until the scan is finished; a host buffer is free when the call returns. */
+int vdbm_insert_async(vdbm_map* map, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes,
+                      const double origin[3], int points_on_device);
+/* finish the queued scan, if any (every other entry point does this implicitly) */
+int vdbm_flush(vdbm_map* map);
 /* updateMap(UpdateGridT::Ptr) V:731-792 on ONE source's accumulated update grid; the grid is emptied.
  * If change != NULL it receives the returned change grid (active = flag flipped, value = it was a hit). */
 int vdbm_update_map(vdbm_map* map, const char* source_id, vdbm_leafset** change);

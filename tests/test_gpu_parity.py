@@ -483,3 +483,56 @@ def test_artificial_areas(cfg):
         m.resetMap()
         m.insertPointCloud(pts, origin, "s")
     assert_leafsets_equal(g.exportMap(), o.exportMap(), "walls survive resetMap")
+
+
+# ---- asynchronous scan pipeline (vdbm_insert_async) ------------------------------------------------------------------
+@pytest.mark.parametrize("small_tables", [False, True], ids=["default_capacity", "tiny_capacity"])
+def test_async_pipeline_matches_the_oracle(small_tables):
+    """insertPointCloudAsync queues whole scans (upload on a copy stream, device-side capacity guard, one host sync per
+    scan, taken by the NEXT call). Whatever mix of queued / redone / synchronous scans results - tiny tables force
+    redos - the map must equal the oracle's after every flush, and the counters must agree."""
+    from vdb_mapping_b200 import scans
+    kw = dict(update_capacity_leaves=1024, map_capacity_leaves=256) if small_tables else {}
+    g, o = _pair(0.1, 4.0, CFG_ROS, **kw)
+    for k in range(12):
+        pts, origin = scans.small_scan(500 + k, n=3000 + 200 * (k % 3), scale=2.5 + 0.3 * (k % 4))
+        origin = origin + np.array([0.137 * k, 0.061 * k, 0.013 * k])
+        g.insertPointCloudAsync(pts, origin, "s")
+        pts[:] = np.nan  # the host buffer is free again as soon as the call returns
+        pts2, _ = scans.small_scan(500 + k, n=3000 + 200 * (k % 3), scale=2.5 + 0.3 * (k % 4))
+        o.insertPointCloud(pts2, origin, "s")
+        if k % 4 == 3:
+            assert_leafsets_equal(g.exportMap(), o.exportMap(), f"map after scan {k}")  # exportMap finishes the queued scan
+    g.flush()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "final map")
+    sg, so = g.stats(), o.stats()
+    for key in ("rays", "clipped", "visits", "voxel_updates"):
+        assert sg[key] == so[key], key
+    assert sg["map_leaves"] == o.mapLeafCount()
+
+
+def test_async_pipeline_full_size_and_interleaved_calls():
+    """cfg1 at full size: async inserts interleaved with sections, a reduced update and a synchronous insert of a second
+    source equal the all-synchronous run."""
+    from vdb_mapping_b200 import scans
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    c = scans.CONFIGS[1]
+    maps = []
+    for _ in range(2):
+        m = OccupancyVDBMapping(c.resolution)
+        m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+        m.addInputSource("s", c.max_range); m.addInputSource("t", c.max_range)
+        maps.append(m)
+    a, b = maps
+    for k in range(8):
+        pts, origin = scans.make_scan(1, k)
+        a.insertPointCloudAsync(pts, origin, "s")
+        b.insertPointCloud(pts, origin, "s")
+        if k == 3:
+            lo, hi = np.array([-40, -40, -10], np.int32), np.array([40, 40, 10], np.int32)
+            assert_leafsets_equal(a.getMapSectionUpdateGrid(lo, hi), b.getMapSectionUpdateGrid(lo, hi), "section mid-pipeline")
+        if k == 5:
+            p2, o2 = scans.make_scan(1, 100)
+            a.insertPointCloud(p2[:5000], o2, "t"); b.insertPointCloud(p2[:5000], o2, "t")
+    assert_leafsets_equal(a.exportMap(), b.exportMap(), "async vs sync map")
+    assert a.stats()["visits"] == b.stats()["visits"] and a.stats()["voxel_updates"] == b.stats()["voxel_updates"]

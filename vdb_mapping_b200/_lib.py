@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
     sig("vdbm_raycast", C.c_int, vp, cp, vp, u64, u64, dblp, dbl)
     sig("vdbm_integrate", C.c_int, vp, C.c_int)
     sig("vdbm_insert", C.c_int, vp, cp, vp, u64, u64, dblp)
+    sig("vdbm_insert_async", C.c_int, vp, cp, vp, u64, u64, dblp, C.c_int)
+    sig("vdbm_flush", C.c_int, vp)
     sig("vdbm_update_map", C.c_int, vp, cp, pvp)
     sig("vdbm_update_export", C.c_int, vp, cp, pvp)
     sig("vdbm_update_import", C.c_int, vp, cp, u64, i32p, u64p, u64p)

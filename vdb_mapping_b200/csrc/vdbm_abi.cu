@@ -111,6 +111,25 @@ struct vdbm_map
     float ms[3] = {0, 0, 0};
   } ex;
 
+  // asynchronous scan pipeline (vdbm_insert_async): at most one scan in flight
+  struct Pending
+  {
+    bool active = false;
+    Source* src = nullptr;
+    uint64_t n = 0, stride = 0;
+    const uint8_t* d_pts = nullptr; // the device-resident cloud of the scan (own staging buffer or the caller's)
+    double origin[3] = {0, 0, 0};
+    Counters before{};
+    uint64_t rays_before = 0;
+  } pending;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_done = nullptr, ev3 = nullptr;
+  uint8_t* d_points_async[2] = {nullptr, nullptr};
+  size_t points_async_cap[2] = {0, 0};
+  int async_buf              = 0;
+  uint32_t async_expect      = 0; // touched leaves of the last finished scan: sizes the next deferred update
+  uint64_t async_fast = 0, async_redone = 0, async_sync = 0; // scans that took the queued path / were redone / went synchronous
+
   // persistent pinned staging for large exports (page-locking hundreds of MB per call costs more than the copy)
   void* h_stage      = nullptr;
   size_t h_stage_cap = 0;
@@ -745,6 +764,104 @@ int finishUpdate(vdbm_map* m, Source& s, uint64_t upd_before, vdbm_leafset** cha
   return VDBM_OK;
 }
 
+
+// ---- asynchronous scan pipeline ---------------------------------------------------------------------------------
+// vdbm_insert_async queues  H2D (copy stream) -> prep -> sort -> DDA -> compaction -> guard -> resolve -> apply -> reset
+// and returns. The only host synchronisation of a scan happens when the NEXT call (or any other entry point) finishes
+// it: the cloud of scan k+1 crosses PCIe while scan k computes, and the accumulate -> integrate round trip through the
+// host disappears. Capacity decisions the host would have taken in between are taken by update_guard_kernel; when it
+// refuses (growth needed, overflow, out-of-range points) the update kernels are no-ops and finishPending() simply redoes
+// the scan on the synchronous path from the cloud that is still resident (marking is an idempotent OR).
+int finishPending(vdbm_map* m)
+{
+  if (!m->pending.active) return VDBM_OK;
+  vdbm_map::Pending pd = m->pending;
+  m->pending.active    = false;
+  CU_TRY(m, cudaEventSynchronize(m->ev_done));
+  Source& s            = *pd.src;
+  const Counters& c    = *m->h_ctr; // snapshot copied at the end of the queued chain
+  m->n_leaves          = m->h_small[0];
+  if (c.deferred_skip)
+  {
+    // redo synchronously: restore the counters of before the scan, then the ordinary accumulate + integrate
+    ++m->async_redone;
+    Counters restored   = pd.before;
+    restored.flags      = 0;
+    restored.ray_cursor = 0;
+    CU_TRY(m, cudaMemcpyAsync(m->d_ctr, &restored, sizeof(Counters), cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    *m->h_ctr     = restored;
+    m->stats.rays = pd.rays_before;
+    CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s.g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    s.n_bricks  = m->h_small[8];
+    s.n_entries = m->h_small[9];
+    int rc = raycastDevice(m, s, pd.d_pts, pd.n, pd.stride, pd.origin, s.max_range);
+    if (rc != VDBM_OK && rc != VDBM_ERR_COORD_RANGE) return rc;
+    int rc2 = vdbm_integrate(m, 0);
+    m->async_expect = uint32_t(m->stats.last_touched_leaves);
+    return rc2 ? rc2 : rc;
+  }
+  ++m->async_fast;
+  // the queued path ran to completion: publish what accumulate + integrate would have published
+  const uint64_t upd_before = m->stats.voxel_updates;
+  m->stats.nan_skipped   = m->base.nan_skipped + c.nan_skipped;
+  m->stats.clipped       = m->base.clipped + c.clipped;
+  m->stats.visits        = m->base.visits + c.visits;
+  m->stats.voxel_updates = m->base.voxel_updates + c.voxel_updates;
+  m->stats.state_changes = m->base.state_changes + c.state_changes;
+  m->stats.new_leaves    = m->base.new_leaves + c.new_leaves;
+  m->stats.map_leaves    = m->n_leaves;
+  m->stats.map_capacity  = m->mt.pool_cap;
+  m->stats.gpu_launches  = launchCount();
+  m->stats.last_visits         = c.visits - pd.before.visits;
+  m->stats.last_touched_leaves = c.deferred_entries;
+  m->stats.last_voxel_updates  = m->stats.voxel_updates - upd_before;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, m->ev0, m->ev1); m->stats.last_accumulate_ms = ms;
+  cudaEventElapsedTime(&ms, m->ev0, m->ev2); m->stats.last_prep_ms = ms;
+  cudaEventElapsedTime(&ms, m->ev1, m->ev3); m->stats.last_integrate_ms = ms;
+  s.prev_visits     = m->stats.last_visits;
+  s.prev_max_visits = c.max_visits;
+  s.n_bricks = s.n_entries = 0;
+  s.n_change        = 0;
+  m->async_expect   = c.deferred_entries;
+  m->ends_src = &s; m->ends_n = pd.n;
+  for (int k = 0; k < 3; ++k) m->ends_origin[k] = pd.origin[k];
+  return VDBM_OK;
+}
+
+#define VDBM_ENTER(m)                          \
+  do                                           \
+  {                                            \
+    if ((m)->pending.active)                   \
+    {                                          \
+      int rc_enter__ = finishPending(m);       \
+      if (rc_enter__) return rc_enter__;       \
+    }                                          \
+  } while (0)
+
+// May this scan take the queued path? Everything the synchronous path decides on the host between kernels must be
+// unnecessary: one source holding data, no segmentation planned, no artificial areas, staging already large enough.
+bool asyncEligible(vdbm_map* m, Source& s, uint64_t n, const double origin[3])
+{
+  if (n == 0 || n > 0xFFFFFFF0ull || !(s.max_range > 0) || !m->config_set) return false;
+  for (int k = 0; k < 3; ++k)
+    if (!std::isfinite(origin[k])) return false;
+  for (auto& kv : m->sources)
+    if (kv.second->n_entries || kv.second->n_bricks) return false;
+  if (m->artificial && m->artificial->n_entries) return false;
+  if (m->rays_cap < n || m->async_expect == 0) return false; // first scans: let the synchronous path size everything
+  if (getenv("VDBM_SEG_LEN")) return false;
+  if (s.prev_visits)
+  {
+    const uint64_t lanes    = uint64_t(m->dda_grid) * 256;
+    const uint64_t per_lane = std::max<uint64_t>(1, s.prev_visits / lanes);
+    if (uint64_t(s.prev_max_visits) > per_lane * 2) return false; // long rays: the segment planner needs a read-back
+  }
+  return true;
+}
+
 } // namespace
 
 // ======================================================================================================
@@ -790,6 +907,10 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
   CU_TRY(mm, cudaEventCreate(&m->ev0));
   CU_TRY(mm, cudaEventCreate(&m->ev1));
   CU_TRY(mm, cudaEventCreate(&m->ev2));
+  CU_TRY(mm, cudaEventCreate(&m->ev3));
+  CU_TRY(mm, cudaEventCreateWithFlags(&m->ev_copy, cudaEventDisableTiming));
+  CU_TRY(mm, cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+  CU_TRY(mm, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   CU_TRY(mm, cudaMalloc(&m->d_ctr, sizeof(Counters)));
   CU_TRY(mm, cudaMemsetAsync(m->d_ctr, 0, sizeof(Counters), m->stream));
   CU_TRY(mm, cudaHostAlloc(&m->h_ctr, sizeof(Counters), cudaHostAllocDefault));
@@ -814,7 +935,12 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
 void vdbm_destroy(vdbm_map* m)
 {
   if (!m) return;
+  if (m->pending.active) finishPending(m);
   cudaStreamSynchronize(m->stream);
+  cudaStreamSynchronize(m->copy_stream);
+  cudaFree(m->d_points_async[0]); cudaFree(m->d_points_async[1]);
+  cudaEventDestroy(m->ev3); cudaEventDestroy(m->ev_copy); cudaEventDestroy(m->ev_done);
+  cudaStreamDestroy(m->copy_stream);
   for (auto& kv : m->sources)
   {
     freeUpdateGrid(kv.second->g);
@@ -840,6 +966,7 @@ void vdbm_destroy(vdbm_map* m)
 int vdbm_reset(vdbm_map* m)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   // resetMap V:174-186: new empty map, new empty update grids
   CU_TRY(m, cudaMemsetAsync(m->mt.hkeys, 0xFF, size_t(m->hcap) * 8, m->stream));
   CU_TRY(m, cudaMemsetAsync(m->mt.leaf_dirty, 0, size_t(m->mt.pool_cap) * 4, m->stream));
@@ -861,6 +988,7 @@ int vdbm_reset(vdbm_map* m)
 int vdbm_set_config(vdbm_map* m, double max_range, double prob_hit, double prob_miss, double prob_thres_min, double prob_thres_max)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   if (max_range < 0.0) return fail(m, VDBM_ERR_BAD_CONFIG, "Max range invalid. Range cannot be negative."); // V:1458-1463
   m->max_range  = max_range;
   m->config_set = true; // V:1468 — before the derived checks, like the reference
@@ -899,6 +1027,7 @@ int vdbm_get_logodds(vdbm_map* m, float* out6)
 int vdbm_source_add(vdbm_map* m, const char* source_id, double max_range)
 {
   if (!m || !source_id) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   auto it = m->sources.find(source_id);
   if (it != m->sources.end())
   {
@@ -925,6 +1054,7 @@ int vdbm_raycast(vdbm_map* m, const char* source_id, const void* points, uint64_
                  double raycast_range)
 {
   if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
@@ -936,6 +1066,7 @@ int vdbm_raycast(vdbm_map* m, const char* source_id, const void* points, uint64_
 int vdbm_accumulate(vdbm_map* m, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3])
 {
   if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : "")); // V:320-326
   if (!(s->max_range > 0)) return VDBM_OK;                                                                             // V:331
@@ -949,6 +1080,7 @@ int vdbm_accumulate_device(vdbm_map* m, const char* source_id, const void* d_poi
                            const double origin[3])
 {
   if (!m || (!d_points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   if (!(s->max_range > 0)) return VDBM_OK;
@@ -959,6 +1091,7 @@ int vdbm_accumulate_device(vdbm_map* m, const char* source_id, const void* d_poi
 int vdbm_integrate(vdbm_map* m, int keep_change)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   m->stats.last_touched_leaves = 0;
   const uint64_t upd_before    = m->stats.voxel_updates;
   CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
@@ -994,9 +1127,141 @@ int vdbm_insert(vdbm_map* m, const char* source_id, const void* points, uint64_t
   return rc_int ? rc_int : rc_acc;
 }
 
+int vdbm_flush(vdbm_map* m)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  return finishPending(m);
+}
+
+int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3],
+                      int points_on_device)
+{
+  if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  Source* sp = findSource(m, source_id);
+  // 1. start the upload of THIS cloud while the previous scan may still be computing (its buffer is the other one)
+  const int buf      = m->async_buf ^ 1;
+  const size_t bytes = size_t(n) * stride_bytes;
+  const uint8_t* d_pts = static_cast<const uint8_t*>(points);
+  bool uploaded = false;
+  if (sp && !points_on_device && bytes && bytes <= m->points_async_cap[buf])
+  {
+    CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+    CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
+    uploaded = true;
+  }
+  // 2. finish the previous scan (the one synchronisation per scan)
+  int rc = finishPending(m);
+  if (rc) return rc;
+  if (!sp) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  Source& s = *sp;
+  if (!points_on_device)
+  {
+    if (!uploaded && bytes)
+    {
+      if (bytes > m->points_async_cap[buf])
+      {
+        cudaFree(m->d_points_async[buf]);
+        m->d_points_async[buf]   = nullptr;
+        m->points_async_cap[buf] = 0;
+        const size_t want = bytes + bytes / 4 + 65536;
+        CU_TRY(m, cudaMalloc(&m->d_points_async[buf], want));
+        m->points_async_cap[buf] = want;
+      }
+      CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+      CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
+    }
+    d_pts = m->d_points_async[buf];
+    // the caller's buffer is free again when this call returns; by now the copy has normally long finished (it ran
+    // while finishPending waited for the previous scan)
+    if (bytes) CU_TRY(m, cudaEventSynchronize(m->ev_copy));
+    m->async_buf = buf;
+  }
+  // 3. not eligible for the queued path: the ordinary synchronous insert on the uploaded cloud
+  if (!asyncEligible(m, s, n, origin))
+  {
+    ++m->async_sync;
+    if (!(s.max_range > 0)) return vdbm_integrate(m, 0); // V:331 then integrateUpdate
+    if (!m->config_set)
+    {
+      vdbm_integrate(m, 0);
+      return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
+    }
+    int rc_acc = raycastDevice(m, s, d_pts, n, stride_bytes, origin, s.max_range);
+    if (rc_acc != VDBM_OK && rc_acc != VDBM_ERR_COORD_RANGE) return rc_acc;
+    int rc_int = vdbm_integrate(m, 0);
+    m->async_expect = uint32_t(std::max<uint64_t>(1, m->stats.last_touched_leaves));
+    return rc_int ? rc_int : rc_acc;
+  }
+  // 4. queue the whole scan
+  const uint32_t expect = m->async_expect + m->async_expect / 2 + 65536; // leaves the update is sized for (guard checks the truth)
+  rc = ensureMapCapacity(m, expect);
+  if (rc) return rc;
+  if (m->resolved_cap < expect)
+  {
+    cudaFree(m->d_resolved);
+    m->d_resolved   = nullptr;
+    m->resolved_cap = 0;
+    const size_t cap = size_t(expect) + expect / 4 + 1024;
+    CU_TRY(m, cudaMalloc(&m->d_resolved, cap * 4));
+    m->resolved_cap = cap;
+  }
+  RaycastArgs a{};
+  a.points = d_pts;
+  a.n      = n;
+  a.stride = uint32_t(stride_bytes);
+  for (int k = 0; k < 3; ++k) a.origin[k] = origin[k];
+  if (!originIndex(m->params.resolution, origin, a.origin_idx)) return fail(m, VDBM_ERR_COORD_RANGE, "sensor origin outside the +-2^23 voxel range");
+  a.range      = s.max_range;
+  a.resolution = m->params.resolution;
+  a.half_res   = m->params.resolution / 2.0;
+  a.inv_res    = 1.0 / m->params.resolution;
+  a.rays       = m->d_rays;
+  a.ends       = m->d_ends;
+  a.index_mode = 0;
+  a.segs       = m->d_segs;
+  a.seg_cap    = uint32_t(std::min<size_t>(m->seg_cap, 0xFFFFFFF0u));
+  a.long_rays  = m->d_long;
+  a.seg_base   = m->d_long + m->rays_cap;
+  a.sort_keys  = m->d_sort;
+  a.sort_idx   = m->d_sort + 2 * m->seg_cap;
+  a.order      = m->d_sort + 3 * m->seg_cap;
+  a.sorted_keys = m->d_sort + m->seg_cap;
+  a.seg_len    = 0;
+  a.n_segs     = uint32_t(n);
+  m->pending.before      = *m->h_ctr;
+  m->pending.rays_before = m->stats.rays;
+  m->stats.rays += n;
+  m->ends_src = nullptr;
+  CU_TRY(m, cudaMemsetAsync(&m->d_ctr->ray_cursor, 0, sizeof(unsigned), m->stream));
+  CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+  CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_extra, 0, 3 * sizeof(unsigned), m->stream));
+  CU_TRY(m, cudaMemsetAsync(m->d_sort + n, 0, (m->seg_cap - n) * sizeof(uint32_t), m->stream));
+  launchPrepRays(a, m->d_ctr, m->stream);
+  sortRaysByLength(m->d_sort_tmp, m->sort_tmp_bytes, a.sort_keys, m->d_sort + m->seg_cap, a.sort_idx, m->d_sort + 3 * m->seg_cap, a.n_segs,
+                   m->stream);
+  CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
+  launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream);
+  launchCompactLeaves(s.g, m->stream);
+  CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
+  launchApplyUpdateDeferred(s.g, m->mt, m->lo, m->d_resolved, uint32_t(std::min<size_t>(m->resolved_cap, 0xFFFFFFFFu)), m->d_ctr, expect, m->stream);
+  CU_TRY(m, cudaEventRecord(m->ev3, m->stream));
+  CU_TRY(m, cudaGetLastError());
+  CU_TRY(m, cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(m->h_small, m->d_map_counters, 4, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaEventRecord(m->ev_done, m->stream));
+  m->pending.active = true;
+  m->pending.src    = &s;
+  m->pending.n      = n;
+  m->pending.stride = stride_bytes;
+  m->pending.d_pts  = d_pts;
+  for (int k = 0; k < 3; ++k) m->pending.origin[k] = origin[k];
+  return VDBM_OK;
+}
+
 int vdbm_update_map(vdbm_map* m, const char* source_id, vdbm_leafset** change)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   m->stats.last_touched_leaves = 0;
@@ -1023,6 +1288,7 @@ int vdbm_update_map(vdbm_map* m, const char* source_id, vdbm_leafset** change)
 int vdbm_change_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
 {
   if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   return recordsToLeafset(m, s->d_change, s->n_change, out);
@@ -1031,6 +1297,7 @@ int vdbm_change_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
 int vdbm_update_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
 {
   if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   return exportGrid(m, *s, out);
@@ -1039,6 +1306,7 @@ int vdbm_update_export(vdbm_map* m, const char* source_id, vdbm_leafset** out)
 int vdbm_update_import(vdbm_map* m, const char* source_id, uint64_t n, const int32_t* origins, const uint64_t* active, const uint64_t* value)
 {
   if (!m || (n && (!origins || !active || !value))) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   if (n == 0) return VDBM_OK;
@@ -1048,6 +1316,7 @@ int vdbm_update_import(vdbm_map* m, const char* source_id, uint64_t n, const int
 int vdbm_update_import_device(vdbm_map* m, const char* source_id, const void* d_records, uint64_t n)
 {
   if (!m || (n && !d_records)) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   return importRecords(m, *s, static_cast<const LeafRecord*>(d_records), n);
@@ -1057,6 +1326,7 @@ int vdbm_update_import_device(vdbm_map* m, const char* source_id, const void* d_
 int vdbm_update_create(vdbm_map* m, const char* source_id, int level, vdbm_leafset** out, double origin_out[3])
 {
   if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   if (origin_out)
@@ -1080,6 +1350,7 @@ int vdbm_update_apply(vdbm_map* m, int level, uint64_t n, const int32_t* origins
                       const double origin[3], vdbm_leafset** change)
 {
   if (!m || (n && (!origins || !active || !value)) || level < 0 || level > 2 || (level == 2 && !origin)) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   if (change) *change = nullptr;
   if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
   int rc = scratchGrid(m);
@@ -1138,6 +1409,7 @@ int vdbm_update_apply(vdbm_map* m, int level, uint64_t n, const int32_t* origins
 int vdbm_points_set(vdbm_map* m, const void* points, uint64_t n, uint64_t stride_bytes, int occupied)
 {
   if (!m || (!points && n) || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   if (n == 0) return VDBM_OK;
   if (n > 0xFFFFFFF0ull) return fail(m, VDBM_ERR_INVALID_ARG, "more than 2^32 points in one cloud");
   if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
@@ -1168,6 +1440,7 @@ int vdbm_points_set(vdbm_map* m, const void* points, uint64_t n, uint64_t stride
 int vdbm_map_integrity_restore(vdbm_map* m)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   if (!m->artificial || m->artificial->n_entries == 0) return VDBM_OK;
   Source& ar = *m->artificial;
   int rc     = ensureMapCapacity(m, (0.0f > m->lo.thres_max) ? ar.n_entries : 0);
@@ -1182,6 +1455,7 @@ int vdbm_artificial_areas_add(vdbm_map* m, uint64_t n_polygons, const uint32_t* 
                               double positive_height)
 {
   if (!m || (n_polygons && (!counts || !xyz))) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   int rc = vdbm_map_integrity_restore(m); // V:1181
   if (rc) return rc;
   rc = auxGrid(m, m->artificial, "<artificial>", 64);
@@ -1222,6 +1496,7 @@ int vdbm_artificial_areas_add(vdbm_map* m, uint64_t n_polygons, const uint32_t* 
 int vdbm_artificial_export(vdbm_map* m, vdbm_leafset** out)
 {
   if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   if (!m->artificial)
   {
     *out = newLeafset(m, 0, true, false);
@@ -1233,6 +1508,7 @@ int vdbm_artificial_export(vdbm_map* m, vdbm_leafset** out)
 int vdbm_map_export(vdbm_map* m, int dirty_only, vdbm_leafset** out)
 {
   if (!m || !out) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   int rc = syncCounters(m);
   if (rc) return rc;
   const uint32_t n_all = m->n_leaves;
@@ -1276,6 +1552,7 @@ int vdbm_map_export(vdbm_map* m, int dirty_only, vdbm_leafset** out)
 int vdbm_section(vdbm_map* m, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float, vdbm_leafset** out)
 {
   if (!m || !out || !bbmin || !bbmax) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   int rc = syncCounters(m);
   if (rc) return rc;
   // upper bound of result leaves: leaves overlapping the box (clamped to the map size)
@@ -1360,6 +1637,7 @@ int vdbm_section_apply_update(vdbm_map* m, const int32_t bbmin[3], const int32_t
                               const uint64_t* active)
 {
   if (!m || !bbmin || !bbmax || (n && (!origins || !active))) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   int rc = syncCounters(m);
   if (rc) return rc;
   launchSectionDeactivate(m->mt, m->n_leaves, bbmin, bbmax, m->stream);
@@ -1386,6 +1664,7 @@ int vdbm_section_apply_update(vdbm_map* m, const int32_t bbmin[3], const int32_t
 int vdbm_section_apply_grid(vdbm_map* m, uint64_t n, const int32_t* origins, const uint64_t* active, const float* values, int tile_quirk)
 {
   if (!m || (n && (!origins || !active || !values))) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   if (n == 0) return VDBM_OK;
   int rc = syncCounters(m);
   if (rc) return rc;
@@ -1426,6 +1705,7 @@ int vdbm_section_apply_grid(vdbm_map* m, uint64_t n, const int32_t* origins, con
 int vdbm_probe(vdbm_map* m, const int32_t xyz[3], float* value, int32_t* active)
 {
   if (!m || !xyz || !value || !active) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   TempBuf d(m->stream);
   CU_TRY(m, d.alloc(16));
   launchProbe(m->mt, xyz[0], xyz[1], xyz[2], d.as<float>(), reinterpret_cast<int32_t*>(d.as<float>() + 1), m->stream);
@@ -1468,6 +1748,7 @@ int32_t vdbm_leaf_owner(const int32_t origin[3], int32_t n_ranks)
 int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, uint64_t* counts, const void** d_records)
 {
   if (!m || !counts || !d_records || n_ranks <= 0 || n_ranks > 32) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   const uint32_t n = s->n_entries;
@@ -1521,6 +1802,7 @@ int vdbm_exchange_create(vdbm_map* m, int32_t rank, int32_t n_ranks, uint64_t ca
 {
   if (!m || !handles_out || n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks || cap == 0 || cap > 0xFFFFFFu)
     return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   if (m->ex.created) return fail(m, VDBM_ERR_INVALID_ARG, "exchange already created on this handle");
   auto& ex = m->ex;
   const size_t inbox_bytes = inboxBytes(2u * uint32_t(n_ranks), uint32_t(cap));
@@ -1553,6 +1835,7 @@ int vdbm_exchange_timings(vdbm_map* m, float* out3)
 int vdbm_exchange_connect(vdbm_map* m, const void* all_handles)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   auto& ex = m->ex;
   if (!ex.created) return fail(m, VDBM_ERR_INVALID_ARG, "vdbm_exchange_create first");
   if (!all_handles)
@@ -1590,6 +1873,7 @@ int vdbm_exchange_connect(vdbm_map* m, const void* all_handles)
 int vdbm_update_push(vdbm_map* m, const char* source_id)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   auto& ex = m->ex;
@@ -1607,6 +1891,7 @@ int vdbm_update_push(vdbm_map* m, const char* source_id)
 int vdbm_update_pull(vdbm_map* m, const char* source_id)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   auto& ex = m->ex;
@@ -1659,6 +1944,7 @@ const char* vdbm_last_error(vdbm_map* m) { return m ? m->last_error.c_str() : "n
 int vdbm_synchronize(vdbm_map* m)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   return VDBM_OK;
 }

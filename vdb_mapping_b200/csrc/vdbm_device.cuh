@@ -130,6 +130,11 @@ struct Counters
   unsigned int n_extra;                                           // extra segment slots handed out by prep_rays
   unsigned int n_long;                                            // rays split into segments
   unsigned int max_visits;                                        // longest ray of the last prep_rays launch
+  // deferred updateMap (vdbm_insert_async): written by update_guard_kernel, read by the update kernels and the host
+  unsigned int deferred_entries;      // touched leaves the queued update kernels process (0 = skipped)
+  unsigned int deferred_bricks;       // occupied bricks the queued reset kernel forgets (0 = skipped)
+  unsigned int deferred_skip;         // 1: the guard refused (overflow / capacity): the host redoes the scan synchronously
+  unsigned int deferred_seen_entries; // touched leaves the guard saw, whatever it decided
 };
 
 // One prepared ray (written by prep_rays_kernel, consumed by raycast_dda_kernel). 32 bytes.
@@ -227,6 +232,11 @@ void launchCompactLeaves(UpdateGrid ug, cudaStream_t s);
 // resolve (K2a) + apply (K2b); `resolved` is a device scratch array of >= n_entries u32
 void launchApplyUpdate(UpdateGrid ug, MapTable mt, LogOdds lo, uint32_t* resolved, LeafRecord* change_out, uint32_t change_cap,
                        Counters* ctr, uint32_t n_entries, cudaStream_t s);
+// updateMap queued WITHOUT the host knowing the number of touched leaves: a one-thread guard kernel checks capacities and
+// flags on the device and publishes the counts; resolve / apply / reset then run (or turn into no-ops). expected_entries
+// only sizes the resolve grid (it is grid-stride).
+void launchApplyUpdateDeferred(UpdateGrid ug, MapTable mt, LogOdds lo, uint32_t* resolved, uint32_t resolved_cap, Counters* ctr,
+                               uint32_t expected_entries, cudaStream_t s);
 // empty the grid after its entries were consumed (entry masks are zeroed by the consumer): reset brick keys + counters
 void launchResetBricks(UpdateGrid ug, uint32_t n_bricks, cudaStream_t s);
 // zero the masks of all listed entries (used by reset / source re-add; consumers zero masks themselves)

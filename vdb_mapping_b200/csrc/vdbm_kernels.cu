@@ -566,11 +566,16 @@ __global__ void __launch_bounds__(512) compact_leaves_kernel(UpdateGrid g)
 // ====================================================================================================
 constexpr uint32_t kNewLeafBit = 0x80000000u;
 
+// n_dev != nullptr: the number of entries is read on the device (deferred launch: the host never saw it), n is then
+// only the bound the grid was sized for. All threads of a block run the same number of iterations (warp ballots inside).
 __global__ void __launch_bounds__(256) resolve_leaves_kernel(UpdateGrid g, MapTable mt, LogOdds lo, uint32_t* resolved, Counters* ctr,
-                                                            uint32_t n)
+                                                            uint32_t n, const uint32_t* n_dev)
 {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane   = threadIdx.x & 31;
+  if (n_dev) n = *n_dev;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+  {
+  const uint32_t i = base + threadIdx.x;
   uint32_t leaf = kInvalid, hslot = 0;
   int is_new    = 0;
   uint64_t key  = 0;
@@ -630,6 +635,7 @@ __global__ void __launch_bounds__(256) resolve_leaves_kernel(UpdateGrid g, MapTa
     if (leaf != kInvalid) mt.leaf_dirty[leaf] = 1u;
     resolved[i] = (leaf == kInvalid) ? kInvalid : (leaf | (is_new ? kNewLeafBit : 0u));
   }
+  }
 }
 
 struct LeafWork
@@ -654,8 +660,10 @@ __device__ __forceinline__ LeafWork loadLeafWork(const UpdateGrid& g, const MapT
 }
 
 __global__ void __launch_bounds__(256, 4) apply_update_kernel(UpdateGrid g, MapTable mt, LogOdds lo, const uint32_t* resolved,
-                                                             LeafRecord* change_out, uint32_t change_cap, Counters* ctr, uint32_t n)
+                                                             LeafRecord* change_out, uint32_t change_cap, Counters* ctr, uint32_t n,
+                                                             const uint32_t* n_dev)
 {
+  if (n_dev) n = *n_dev;
   const int lane         = threadIdx.x & 31;
   const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -798,11 +806,33 @@ __global__ void __launch_bounds__(256, 4) apply_update_kernel(UpdateGrid g, MapT
 // growth / import / export helpers
 // ====================================================================================================
 // after the entries were consumed (their masks are zero again): forget the bricks
-__global__ void reset_bricks_kernel(UpdateGrid g, uint32_t n_bricks)
+__global__ void reset_bricks_kernel(UpdateGrid g, uint32_t n_bricks, const uint32_t* n_dev)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev)
+  {
+    n_bricks = *n_dev; // deferred launch: 0 = the update was skipped, leave the grid alone
+    if (n_bricks == 0) return;
+  }
   if (i < n_bricks) g.bkeys[g.btouched[i]] = kEmptyKey;
   if (i == 0) { g.counters[0] = 0; g.counters[1] = 0; }
+}
+
+// Deferred updateMap (vdbm_insert_async): the host queued the update kernels without knowing how many leaves the raycast
+// touched. This one-thread kernel decides ON THE DEVICE whether they may run: no overflow / range flag, the brick hash not
+// crowded, and room for every touched leaf in `resolved`, the leaf pool and the map hash. It publishes the counts the
+// following kernels read; zero counts turn them into no-ops and the host redoes the scan synchronously.
+__global__ void update_guard_kernel(UpdateGrid g, MapTable mt, Counters* ctr, uint32_t resolved_cap)
+{
+  const uint32_t n_bricks = g.counters[0], n_entries = g.counters[1];
+  const uint64_t need = uint64_t(*mt.n_leaves) + n_entries;
+  const bool ok = (ctr->flags & (kFlagUpdateOverflow | kFlagCoordRange | kFlagMapOverflow)) == 0 &&
+                  uint64_t(n_bricks) * 10 <= (uint64_t(g.cap_mask) + 1) * 7 && n_entries <= resolved_cap && need <= mt.pool_cap &&
+                  need * 2 <= uint64_t(mt.hcap_mask) + 1;
+  ctr->deferred_entries = ok ? n_entries : 0u;
+  ctr->deferred_bricks  = ok ? n_bricks : 0u;
+  ctr->deferred_skip    = ok ? 0u : 1u;
+  ctr->deferred_seen_entries = n_entries;
 }
 
 __global__ void clear_entries_kernel(UpdateGrid g, uint32_t n_entries)
@@ -1805,25 +1835,41 @@ void launchCompactLeaves(UpdateGrid g, cudaStream_t s)
   VDBM_LAUNCH(compact_leaves_kernel, grid, 512, s, g);
 }
 
-void launchApplyUpdate(UpdateGrid g, MapTable mt, LogOdds lo, uint32_t* resolved, LeafRecord* change_out, uint32_t change_cap,
-                       Counters* ctr, uint32_t n_entries, cudaStream_t s)
+static int applyUpdateBlocksPerSM()
 {
-  if (n_entries == 0) return;
   static int per_sm = 0;
   if (per_sm == 0)
   {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apply_update_kernel, 256, 0);
     if (per_sm < 1) per_sm = 1;
   }
-  VDBM_LAUNCH(resolve_leaves_kernel, blocksFor(n_entries, 256), 256, s, g, mt, lo, resolved, ctr, n_entries);
+  return per_sm;
+}
+
+void launchApplyUpdate(UpdateGrid g, MapTable mt, LogOdds lo, uint32_t* resolved, LeafRecord* change_out, uint32_t change_cap,
+                       Counters* ctr, uint32_t n_entries, cudaStream_t s)
+{
+  if (n_entries == 0) return;
+  VDBM_LAUNCH(resolve_leaves_kernel, blocksFor(n_entries, 256), 256, s, g, mt, lo, resolved, ctr, n_entries, (const uint32_t*)nullptr);
   // one warp per leaf, grid-stride; exactly one resident wave (multiple of the SM count)
-  unsigned grid = std::min<unsigned>(blocksFor(n_entries, 8), unsigned(smCount() * per_sm));
-  VDBM_LAUNCH(apply_update_kernel, grid, 256, s, g, mt, lo, resolved, change_out, change_cap, ctr, n_entries);
+  unsigned grid = std::min<unsigned>(blocksFor(n_entries, 8), unsigned(smCount() * applyUpdateBlocksPerSM()));
+  VDBM_LAUNCH(apply_update_kernel, grid, 256, s, g, mt, lo, resolved, change_out, change_cap, ctr, n_entries, (const uint32_t*)nullptr);
+}
+
+void launchApplyUpdateDeferred(UpdateGrid g, MapTable mt, LogOdds lo, uint32_t* resolved, uint32_t resolved_cap, Counters* ctr,
+                               uint32_t expected_entries, cudaStream_t s)
+{
+  VDBM_LAUNCH(update_guard_kernel, 1, 1, s, g, mt, ctr, resolved_cap);
+  const unsigned rgrid = std::max(1u, std::min<unsigned>(blocksFor(std::max(expected_entries, 1u), 256), unsigned(smCount()) * 8u));
+  VDBM_LAUNCH(resolve_leaves_kernel, rgrid, 256, s, g, mt, lo, resolved, ctr, 0u, (const uint32_t*)&ctr->deferred_entries);
+  VDBM_LAUNCH(apply_update_kernel, unsigned(smCount() * applyUpdateBlocksPerSM()), 256, s, g, mt, lo, resolved, (LeafRecord*)nullptr, 0u, ctr, 0u,
+              (const uint32_t*)&ctr->deferred_entries);
+  VDBM_LAUNCH(reset_bricks_kernel, blocksFor(uint64_t(g.cap_mask) + 1, 256), 256, s, g, 0u, (const uint32_t*)&ctr->deferred_bricks);
 }
 
 void launchResetBricks(UpdateGrid g, uint32_t n_bricks, cudaStream_t s)
 {
-  VDBM_LAUNCH(reset_bricks_kernel, std::max(1u, blocksFor(n_bricks, 256)), 256, s, g, n_bricks);
+  VDBM_LAUNCH(reset_bricks_kernel, std::max(1u, blocksFor(n_bricks, 256)), 256, s, g, n_bricks, (const uint32_t*)nullptr);
 }
 void launchClearEntries(UpdateGrid g, uint32_t n_entries, cudaStream_t s)
 {

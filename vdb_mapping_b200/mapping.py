@@ -164,6 +164,22 @@ class OccupancyVDBMapping:
         o = np.ascontiguousarray(origin, dtype=np.float64)
         self._check(self._L.vdbm_insert(self._h, source_id.encode(), C.c_void_p(ptr), n, stride, _dp(o)))
 
+    def insertPointCloudAsync(self, points, origin, source_id: str) -> bool:
+        """insertPointCloud as a pipeline stage (vdbm_insert_async): returns once the scan is queued; any later call on the
+        map (or flush()) finishes it. Results are identical to insertPointCloud."""
+        p = _pts16(points)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        rc = self._L.vdbm_insert_async(self._h, source_id.encode(), p.ctypes.data, p.shape[0], 16, _dp(o), 0)
+        self._check(rc, allow=(L.VDBM_ERR_UNKNOWN_SOURCE, L.VDBM_ERR_NOT_CONFIGURED))
+        return True
+
+    def insertRawAsync(self, ptr: int, n: int, origin, source_id: str, on_device: bool = False, stride: int = 16):
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._check(self._L.vdbm_insert_async(self._h, source_id.encode(), C.c_void_p(ptr), n, stride, _dp(o), int(on_device)))
+
+    def flush(self):
+        self._check(self._L.vdbm_flush(self._h))
+
     def updateMap(self, source_id: str) -> LeafSet:
         """updateMap(source's accumulated update grid) -> change grid."""
         out = C.c_void_p()
