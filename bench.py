@@ -402,6 +402,9 @@ def run_ours(args, rank, world, local_rank):
                     eng.accumulate_raw(pinned[k].data_ptr(), n_pts_k[k], origin, on_device=False)
                 else:
                     eng.accumulate_raw(resident[k].data_ptr(), n_pts_k[k], origin, on_device=True)
+                if e2e and k + 1 < n_steps:
+                    # the next cloud crosses PCIe while this scan's exchange / update runs
+                    m.prefetchRaw(pinned[k + 1].data_ptr(), n_pts_k[k + 1])
                 if k >= args.warmup:
                     s = m.stats()
                     acc_ms.append(s["last_accumulate_ms"]); prep_ms.append(s["last_prep_ms"]); leaves.append(s["last_touched_leaves"])

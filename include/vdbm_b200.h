@@ -133,6 +133,11 @@ int vdbm_insert(vdbm_map* map, const char* source_id, const void* points, uint64
  * `points` is device memory and must stay valid until the scan is finished; a host buffer is free when the call returns. */
 int vdbm_insert_async(vdbm_map* map, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes,
                       const double origin[3], int points_on_device);
+/* Start uploading the NEXT cloud (pinned host memory) on the copy stream while earlier work is still running; a following
+ * vdbm_accumulate called with the same pointer, count and stride uses the uploaded copy instead of copying on the critical
+ * path. The host buffer must stay untouched until that vdbm_accumulate returns. Used by callers that cannot use
+ * vdbm_insert_async because something happens between raycast and update (the multi-GPU exchange, createUpdate). */
+int vdbm_prefetch(vdbm_map* map, const void* points, uint64_t n, uint64_t stride_bytes);
 /* finish the queued scan, if any (every other entry point does this implicitly) */
 int vdbm_flush(vdbm_map* map);
 /* updateMap(UpdateGridT::Ptr) V:731-792 on ONE source's accumulated update grid; the grid is emptied.
@@ -244,6 +249,9 @@ int vdbm_exchange_create(vdbm_map* map, int32_t rank, int32_t n_ranks, uint64_t 
 int vdbm_exchange_connect(vdbm_map* map, const void* all_handles);
 int vdbm_update_push(vdbm_map* map, const char* source_id);
 int vdbm_update_pull(vdbm_map* map, const char* source_id);
+/* vdbm_update_pull followed by vdbm_integrate(map, 0) with one host synchronisation instead of two: the update kernels are
+ * queued behind a device-side capacity guard (see vdbm_insert_async); when it refuses, the two calls run synchronously. */
+int vdbm_update_pull_integrate(vdbm_map* map, const char* source_id);
 /* device times (ms, CUDA events) of the last push / pull pair: out[0] bin+send kernels, out[1] wait for the peers'
  * epoch words (includes their raycast skew), out[2] import + leaf compaction */
 int vdbm_exchange_timings(vdbm_map* map, float* out3);

@@ -536,3 +536,24 @@ def test_async_pipeline_full_size_and_interleaved_calls():
             a.insertPointCloud(p2[:5000], o2, "t"); b.insertPointCloud(p2[:5000], o2, "t")
     assert_leafsets_equal(a.exportMap(), b.exportMap(), "async vs sync map")
     assert a.stats()["visits"] == b.stats()["visits"] and a.stats()["voxel_updates"] == b.stats()["voxel_updates"]
+
+
+def test_prefetched_cloud_is_used_and_stale_prefetch_is_ignored():
+    """vdbm_prefetch uploads the next cloud on the copy stream; vdbm_accumulate with the same pointer uses that copy, with
+    another pointer it copies normally. Results equal the oracle either way."""
+    import torch
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, CFG_ROS)
+    clouds = [scans.small_scan(700 + k, n=2500, scale=2.5) for k in range(4)]
+    pinned = [torch.from_numpy(np.ascontiguousarray(np.concatenate([p[:, :3], np.ones((len(p), 1), np.float32)], axis=1))).pin_memory()
+              for p, _ in clouds]
+    g.prefetchRaw(pinned[0].data_ptr(), pinned[0].shape[0])
+    for k, (pts, origin) in enumerate(clouds):
+        if k == 2:
+            g.prefetchRaw(pinned[3].data_ptr(), pinned[3].shape[0])  # stale: the next accumulate passes another pointer
+        g.accumulateRaw(pinned[k].data_ptr(), pinned[k].shape[0], origin, "s")
+        if k == 0:
+            g.prefetchRaw(pinned[1].data_ptr(), pinned[1].shape[0])
+        g.integrateUpdate(keep_change=False)
+        o.insertPointCloud(pts, origin, "s")
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")

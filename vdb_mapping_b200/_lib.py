@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
     sig("vdbm_insert", C.c_int, vp, cp, vp, u64, u64, dblp)
     sig("vdbm_insert_async", C.c_int, vp, cp, vp, u64, u64, dblp, C.c_int)
     sig("vdbm_flush", C.c_int, vp)
+    sig("vdbm_prefetch", C.c_int, vp, vp, u64, u64)
     sig("vdbm_update_map", C.c_int, vp, cp, pvp)
     sig("vdbm_update_export", C.c_int, vp, cp, pvp)
     sig("vdbm_update_import", C.c_int, vp, cp, u64, i32p, u64p, u64p)
@@ -91,6 +92,7 @@ def lib() -> C.CDLL:
     sig("vdbm_exchange_connect", C.c_int, vp, vp)
     sig("vdbm_update_push", C.c_int, vp, cp)
     sig("vdbm_update_pull", C.c_int, vp, cp)
+    sig("vdbm_update_pull_integrate", C.c_int, vp, cp)
     sig("vdbm_exchange_timings", C.c_int, vp, f32p)
     sig("vdbm_stats", C.c_int, vp, C.POINTER(VdbmStats))
     sig("vdbm_last_error", cp, vp)

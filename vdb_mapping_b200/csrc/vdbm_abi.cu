@@ -127,6 +127,7 @@ struct vdbm_map
   uint8_t* d_points_async[2] = {nullptr, nullptr};
   size_t points_async_cap[2] = {0, 0};
   int async_buf              = 0;
+  struct Prefetch { const void* host = nullptr; uint64_t n = 0, stride = 0; int buf = 0; bool valid = false; } prefetch;
   uint32_t async_expect      = 0; // touched leaves of the last finished scan: sizes the next deferred update
   uint64_t async_fast = 0, async_redone = 0, async_sync = 0; // scans that took the queued path / were redone / went synchronous
 
@@ -841,6 +842,18 @@ int finishPending(vdbm_map* m)
     }                                          \
   } while (0)
 
+int ensureAsyncStaging(vdbm_map* m, int buf, size_t bytes)
+{
+  if (bytes <= m->points_async_cap[buf]) return VDBM_OK;
+  cudaFree(m->d_points_async[buf]);
+  m->d_points_async[buf]   = nullptr;
+  m->points_async_cap[buf] = 0;
+  const size_t want = bytes + bytes / 4 + 65536;
+  CU_TRY(m, cudaMalloc(&m->d_points_async[buf], want));
+  m->points_async_cap[buf] = want;
+  return VDBM_OK;
+}
+
 // May this scan take the queued path? Everything the synchronous path decides on the host between kernels must be
 // unnecessary: one source holding data, no segmentation planned, no artificial areas, staging already large enough.
 bool asyncEligible(vdbm_map* m, Source& s, uint64_t n, const double origin[3])
@@ -1071,6 +1084,13 @@ int vdbm_accumulate(vdbm_map* m, const char* source_id, const void* points, uint
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : "")); // V:320-326
   if (!(s->max_range > 0)) return VDBM_OK;                                                                             // V:331
   if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
+  if (m->prefetch.valid && m->prefetch.host == points && m->prefetch.n == n && m->prefetch.stride == stride_bytes)
+  {
+    // the cloud was uploaded ahead of time by vdbm_prefetch (copy stream): no H2D on the critical path
+    m->prefetch.valid = false;
+    CU_TRY(m, cudaEventSynchronize(m->ev_copy));
+    return raycastDevice(m, *s, m->d_points_async[m->prefetch.buf], n, stride_bytes, origin, s->max_range);
+  }
   int rc = stagePoints(m, points, n, stride_bytes);
   if (rc) return rc;
   return raycastDevice(m, *s, m->d_points, n, stride_bytes, origin, s->max_range);
@@ -1127,6 +1147,24 @@ int vdbm_insert(vdbm_map* m, const char* source_id, const void* points, uint64_t
   return rc_int ? rc_int : rc_acc;
 }
 
+int vdbm_prefetch(vdbm_map* m, const void* points, uint64_t n, uint64_t stride_bytes)
+{
+  if (!m || (!points && n) || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  // no VDBM_ENTER: the point is to run while earlier work is still in flight. The staging buffer used is the one the
+  // queued / last scan does NOT read.
+  const int buf      = m->async_buf ^ 1;
+  const size_t bytes = size_t(n) * stride_bytes;
+  m->prefetch.valid  = false;
+  if (bytes == 0) return VDBM_OK;
+  int rc = ensureAsyncStaging(m, buf, bytes);
+  if (rc) return rc;
+  CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+  CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
+  m->prefetch.host = points; m->prefetch.n = n; m->prefetch.stride = stride_bytes; m->prefetch.buf = buf; m->prefetch.valid = true;
+  m->async_buf = buf;
+  return VDBM_OK;
+}
+
 int vdbm_flush(vdbm_map* m)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
@@ -1138,6 +1176,7 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
 {
   if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
   Source* sp = findSource(m, source_id);
+  m->prefetch.valid = false;
   // 1. start the upload of THIS cloud while the previous scan may still be computing (its buffer is the other one)
   const int buf      = m->async_buf ^ 1;
   const size_t bytes = size_t(n) * stride_bytes;
@@ -1158,15 +1197,8 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
   {
     if (!uploaded && bytes)
     {
-      if (bytes > m->points_async_cap[buf])
-      {
-        cudaFree(m->d_points_async[buf]);
-        m->d_points_async[buf]   = nullptr;
-        m->points_async_cap[buf] = 0;
-        const size_t want = bytes + bytes / 4 + 65536;
-        CU_TRY(m, cudaMalloc(&m->d_points_async[buf], want));
-        m->points_async_cap[buf] = want;
-      }
+      rc = ensureAsyncStaging(m, buf, bytes);
+      if (rc) return rc;
       CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
       CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
     }
@@ -1928,6 +1960,94 @@ int vdbm_update_pull(vdbm_map* m, const char* source_id)
   cudaEventElapsedTime(&ex.ms[0], ex.ev[0], ex.ev[1]);
   cudaEventElapsedTime(&ex.ms[1], ex.ev[1], ex.ev[2]);
   cudaEventElapsedTime(&ex.ms[2], ex.ev[2], ex.ev[3]);
+  return VDBM_OK;
+}
+
+// vdbm_update_pull + vdbm_integrate with ONE host synchronisation: wait for the peers, OR their records in, rebuild the
+// leaf list and run the update behind the device-side guard (see vdbm_insert_async). If the guard refuses (the import
+// overflowed or crowded the brick hash, or the map must grow) the host falls back to the two synchronous calls; the
+// inbox still holds this epoch's records and importing them again is idempotent.
+int vdbm_update_pull_integrate(vdbm_map* m, const char* source_id)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  auto& ex = m->ex;
+  if (!ex.connected || ex.epoch == 0) return fail(m, VDBM_ERR_INVALID_ARG, "vdbm_update_push first");
+  bool other_data = false;
+  for (auto& kv : m->sources)
+    if (kv.second.get() != s && (kv.second->n_entries || kv.second->n_bricks)) other_data = true;
+  const bool fused = !other_data && !(m->artificial && m->artificial->n_entries) && m->async_expect != 0;
+  if (!fused)
+  {
+    int rc = vdbm_update_pull(m, source_id);
+    if (rc) return rc;
+    rc = vdbm_integrate(m, 0);
+    m->async_expect = uint32_t(std::max<uint64_t>(1, m->stats.last_touched_leaves));
+    return rc;
+  }
+  const uint32_t expect = m->async_expect + m->async_expect / 2 + 65536;
+  int rc = ensureMapCapacity(m, expect);
+  if (rc) return rc;
+  if (m->resolved_cap < expect)
+  {
+    cudaFree(m->d_resolved);
+    m->d_resolved   = nullptr;
+    m->resolved_cap = 0;
+    const size_t cap = size_t(expect) + expect / 4 + 1024;
+    CU_TRY(m, cudaMalloc(&m->d_resolved, cap * 4));
+    m->resolved_cap = cap;
+  }
+  const uint64_t upd_before = m->stats.voxel_updates;
+  launchWaitPeers(ex.ctrl, ex.px.n_ranks, ex.epoch & 1u, ex.epoch, ex.d_counts, m->d_ctr, m->stream);
+  CU_TRY(m, cudaEventRecord(ex.ev[2], m->stream));
+  launchPullUpdate(s->g, ex.inbox, ex.ctrl, ex.px.cap, ex.px.n_ranks, ex.epoch & 1u, ex.epoch, ex.d_counts, m->d_ctr, m->stream);
+  launchCompactLeaves(s->g, m->stream);
+  CU_TRY(m, cudaEventRecord(ex.ev[3], m->stream));
+  CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+  launchApplyUpdateDeferred(s->g, m->mt, m->lo, m->d_resolved, uint32_t(std::min<size_t>(m->resolved_cap, 0xFFFFFFFFu)), m->d_ctr, expect, m->stream);
+  CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
+  CU_TRY(m, cudaGetLastError());
+  rc = syncCounters(m);
+  if (rc) return rc;
+  cudaEventElapsedTime(&ex.ms[0], ex.ev[0], ex.ev[1]);
+  cudaEventElapsedTime(&ex.ms[1], ex.ev[1], ex.ev[2]);
+  cudaEventElapsedTime(&ex.ms[2], ex.ev[2], ex.ev[3]);
+  const uint32_t flags = m->h_ctr->flags;
+  if (flags & (kFlagExchangeOverflow | kFlagExchangeTimeout))
+  {
+    CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+    return fail(m, VDBM_ERR_OUT_OF_MEMORY, (flags & kFlagExchangeTimeout) ? "exchange: a peer did not publish its epoch in time"
+                                                                          : "exchange: inbox capacity_records_per_sender too small");
+  }
+  if (m->h_ctr->deferred_skip)
+  {
+    // redo on the synchronous path: the records are still in the inbox, the OR is idempotent
+    if (flags & kFlagUpdateOverflow) CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+    CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s->g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    s->n_bricks  = m->h_small[8];
+    s->n_entries = m->h_small[9];
+    if (flags & kFlagUpdateOverflow)
+    {
+      rc = growUpdateGrid(m, *s);
+      if (rc) return rc;
+    }
+    rc = vdbm_update_pull(m, source_id);
+    if (rc) return rc;
+    rc = vdbm_integrate(m, 0);
+    m->async_expect = uint32_t(std::max<uint64_t>(1, m->stats.last_touched_leaves));
+    return rc;
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, m->ev0, m->ev1);
+  m->stats.last_integrate_ms   = ms;
+  m->stats.last_touched_leaves = m->h_ctr->deferred_entries;
+  m->stats.last_voxel_updates  = m->stats.voxel_updates - upd_before;
+  m->async_expect              = std::max(1u, m->h_ctr->deferred_entries);
+  s->n_bricks = s->n_entries = 0;
+  s->n_change = 0;
   return VDBM_OK;
 }
 

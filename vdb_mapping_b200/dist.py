@@ -156,9 +156,12 @@ def push_pull_and_integrate(engine):
     t = [time.perf_counter()] if PROFILE else None
     engine.m.updatePush(engine.src)
     if PROFILE: t.append(time.perf_counter())
-    engine.m.updatePull(engine.src)
-    if PROFILE: t.append(time.perf_counter())
-    engine.integrate()
+    if PROFILE:
+        engine.m.updatePull(engine.src)
+        t.append(time.perf_counter())
+        engine.integrate()
+    else:
+        engine.m.updatePullIntegrate(engine.src)  # wait + import + updateMap behind the device-side guard: one host sync
     if PROFILE:
         t.append(time.perf_counter())
         # host: push (async launch), pull (wait + import + sync), integrate; device: push kernels, wait, import

@@ -177,6 +177,10 @@ class OccupancyVDBMapping:
         o = np.ascontiguousarray(origin, dtype=np.float64)
         self._check(self._L.vdbm_insert_async(self._h, source_id.encode(), C.c_void_p(ptr), n, stride, _dp(o), int(on_device)))
 
+    def prefetchRaw(self, ptr: int, n: int, stride: int = 16):
+        """Upload the next (pinned) cloud on the copy stream now; accumulateRaw with the same pointer then skips the copy."""
+        self._check(self._L.vdbm_prefetch(self._h, C.c_void_p(ptr), n, stride))
+
     def flush(self):
         self._check(self._L.vdbm_flush(self._h))
 
@@ -335,6 +339,9 @@ class OccupancyVDBMapping:
 
     def updatePull(self, source_id: str):
         self._check(self._L.vdbm_update_pull(self._h, source_id.encode()))
+
+    def updatePullIntegrate(self, source_id: str):
+        self._check(self._L.vdbm_update_pull_integrate(self._h, source_id.encode()))
 
     def exchangeTimings(self):
         out = np.zeros(3, dtype=np.float32)
