@@ -423,6 +423,7 @@ def run_ours(args, rank, world, local_rank):
                         if k >= args.warmup:
                             d2h_extra[0] += sp.origins.nbytes + sp.active.nbytes + sp.valmask.nbytes + fu.origins.nbytes + fu.active.nbytes + fu.values.nbytes
                             d2h_extra[1] += 1
+                        del sp, fu  # the consumer is done with them: the library's staging buffer is free for the next export
                     continue
                 if p2p:
                     vdist.push_pull_and_integrate(eng)

@@ -214,8 +214,8 @@ int vdbm_probe(vdbm_map* map, const int32_t xyz[3], float* value, int32_t* activ
  * A leaf set is read through the accessors below and released with vdbm_leafset_free(). Small sets own their
  * (pageable) memory. A large set (>= 1 MB) borrows the handle's persistent pinned staging buffer when it is free
  * (page-locking per call would cost more than the copy itself): free it BEFORE the next large export on the same
- * handle if you want that export to be fast too (otherwise the next one simply uses pageable memory of its own), and
- * before vdbm_destroy(). */
+ * handle if you want that export to be fast too (otherwise the next one simply uses pageable memory of its own). A set
+ * that still borrows the buffer when the handle is destroyed takes ownership of it. */
 uint64_t vdbm_leafset_size(const vdbm_leafset* s);
 const int32_t* vdbm_leafset_origins(const vdbm_leafset* s); /* [n][3] */
 const uint64_t* vdbm_leafset_active(const vdbm_leafset* s); /* [n][8] */

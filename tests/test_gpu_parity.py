@@ -557,3 +557,31 @@ def test_prefetched_cloud_is_used_and_stale_prefetch_is_ignored():
         g.integrateUpdate(keep_change=False)
         o.insertPointCloud(pts, origin, "s")
     assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
+
+
+def test_large_exports_are_views_that_outlive_calls_and_the_map():
+    """Leaf sets >= 16 MB come back as zero-copy numpy views of the library's pinned staging memory. They must stay valid
+    across later exports (which then use other memory) and after the map is closed."""
+    from vdb_mapping_b200 import scans
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    c = scans.CONFIGS[1]
+    m = OccupancyVDBMapping(c.resolution)
+    m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+    m.addInputSource("s", c.max_range)
+    pts, origin = scans.make_scan(1, 0)
+    m.insertPointCloud(pts, origin, "s")
+    a = m.exportMap()
+    assert a.values.nbytes >= (16 << 20) and a.values.base is not None  # a view, not a copy
+    snap = a.values.copy(); snap_act = a.active.copy()
+    b = m.exportMap()            # second large export while the first still borrows the staging buffer
+    assert np.array_equal(b.values.view(np.uint32), snap.view(np.uint32))
+    pts2, origin2 = scans.make_scan(1, 1)
+    m.insertPointCloud(pts2, origin2, "s")
+    c2 = m.exportMap()
+    assert len(c2) >= len(a)
+    m.close()                    # the map goes away first
+    assert np.array_equal(a.values.view(np.uint32), snap.view(np.uint32)) and np.array_equal(a.active, snap_act)
+    keep = a.values[5]
+    del a, b, c2
+    import gc; gc.collect()
+    assert np.array_equal(keep.view(np.uint32), snap[5].view(np.uint32))

@@ -26,6 +26,7 @@ struct vdbm_leafset
   float* values     = nullptr;
   bool pinned       = false;
   vdbm_map* lender  = nullptr; // non-null: the arrays live in the handle's persistent pinned staging buffer
+  void* orphan_stage = nullptr; // the handle was destroyed while this set borrowed its staging buffer: the set owns it now
 };
 
 namespace {
@@ -135,6 +136,7 @@ struct vdbm_map
   void* h_stage      = nullptr;
   size_t h_stage_cap = 0;
   bool h_stage_lent  = false;
+  vdbm_leafset* h_stage_borrower = nullptr;
 
   vdbm_stats_t stats{};
   Counters base{}; // counters at the last reset, to keep cumulative numbers across device counter resets
@@ -579,6 +581,7 @@ vdbm_leafset* newLeafset(vdbm_map* m, uint64_t n, bool with_valmask, bool with_v
       ls->pinned      = true;
       ls->lender      = m;
       m->h_stage_lent = true;
+      m->h_stage_borrower = ls;
       return ls;
     }
   }
@@ -970,6 +973,13 @@ void vdbm_destroy(vdbm_map* m)
   cudaFree(m->ex.inbox); cudaFree(m->ex.ctrl); cudaFree(m->ex.d_cursors); cudaFree(m->ex.d_counts);
   for (auto& e : m->ex.ev) if (e) cudaEventDestroy(e);
   cudaFreeHost(m->h_ctr); cudaFreeHost(m->h_small);
+  if (m->h_stage_lent && m->h_stage_borrower)
+  {
+    // a leaf set still borrows the staging buffer (e.g. numpy views of a large export): hand the buffer over to it
+    m->h_stage_borrower->lender       = nullptr;
+    m->h_stage_borrower->orphan_stage = m->h_stage;
+    m->h_stage                        = nullptr;
+  }
   if (m->h_stage) cudaFreeHost(m->h_stage);
   cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1); cudaEventDestroy(m->ev2);
   if (m->own_stream) cudaStreamDestroy(m->stream);
@@ -1758,7 +1768,14 @@ void vdbm_leafset_free(vdbm_leafset* s)
   if (!s) return;
   if (s->lender)
   {
-    s->lender->h_stage_lent = false; // arrays belong to the handle's staging buffer
+    s->lender->h_stage_lent     = false; // arrays belong to the handle's staging buffer
+    s->lender->h_stage_borrower = nullptr;
+    delete s;
+    return;
+  }
+  if (s->orphan_stage)
+  {
+    cudaFreeHost(s->orphan_stage);
     delete s;
     return;
   }

@@ -32,6 +32,26 @@ class LeafSet:
         return int(self.origins.shape[0])
 
 
+class _LeafsetOwner:
+    """Frees a vdbm_leafset when the last numpy view of it is garbage-collected."""
+
+    def __init__(self, lib, ptr):
+        self._lib, self._ptr = lib, ptr
+
+    def __del__(self):
+        p, self._ptr = self._ptr, None
+        if p:
+            self._lib.vdbm_leafset_free(p)
+
+
+class _View:
+    """Array-interface wrapper: np.asarray(view) aliases library memory and keeps `owner` alive through .base."""
+
+    def __init__(self, owner, address, shape, typestr):
+        self.owner = owner
+        self.__array_interface__ = {"data": (address, False), "shape": shape, "typestr": typestr, "version": 3}
+
+
 class VdbmError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"vdbm status {code}: {msg}")
@@ -90,17 +110,31 @@ class OccupancyVDBMapping:
         return rc
 
     def _take(self, ls_ptr, is_float: bool) -> LeafSet:
+        """vdbm_leafset -> LeafSet. Small sets are copied and released at once. Sets of 16 MB and more are NOT copied: the
+        numpy arrays are views of the library's (pinned) memory and keep the vdbm_leafset alive through their base object;
+        it is released when the last array goes away."""
         n = int(self._L.vdbm_leafset_size(ls_ptr))
+        big = n * (2048 if is_float else 128) >= (16 << 20)
+        owner = _LeafsetOwner(self._L, ls_ptr) if big else None
+
+        def arr(ptr, cols, dtype):
+            if n == 0:
+                return np.zeros((0, cols), dtype)
+            if big:
+                return np.asarray(_View(owner, C.cast(ptr, C.c_void_p).value, (n, cols), np.dtype(dtype).str))
+            return np.ctypeslib.as_array(ptr, shape=(n, cols)).copy()
+
         try:
-            origins = np.ctypeslib.as_array(self._L.vdbm_leafset_origins(ls_ptr), shape=(n, 3)).copy() if n else np.zeros((0, 3), np.int32)
-            active = np.ctypeslib.as_array(self._L.vdbm_leafset_active(ls_ptr), shape=(n, 8)).copy() if n else np.zeros((0, 8), np.uint64)
+            origins = arr(self._L.vdbm_leafset_origins(ls_ptr), 3, np.int32)
+            active = arr(self._L.vdbm_leafset_active(ls_ptr), 8, np.uint64)
             valmask = values = None
             if is_float:
-                values = np.ctypeslib.as_array(self._L.vdbm_leafset_values(ls_ptr), shape=(n, 512)).copy() if n else np.zeros((0, 512), np.float32)
+                values = arr(self._L.vdbm_leafset_values(ls_ptr), 512, np.float32)
             else:
-                valmask = np.ctypeslib.as_array(self._L.vdbm_leafset_valmask(ls_ptr), shape=(n, 8)).copy() if n else np.zeros((0, 8), np.uint64)
+                valmask = arr(self._L.vdbm_leafset_valmask(ls_ptr), 8, np.uint64)
         finally:
-            self._L.vdbm_leafset_free(ls_ptr)
+            if not big:
+                self._L.vdbm_leafset_free(ls_ptr)
         return LeafSet(origins, active, valmask, values)
 
     # ---- reference surface ---------------------------------------------------------------------------
