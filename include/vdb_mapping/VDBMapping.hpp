@@ -602,9 +602,7 @@ protected:
     if (!m_device_map) return;
     vdbm_leafset* ls = nullptr;
     if (report(vdbm_map_export(m_device_map, 1, &ls)) != VDBM_OK) return;
-    const std::uint64_t n = vdbm_leafset_size(ls);
-    for (std::uint64_t i = 0; i < n; ++i)
-      BackendT::putMapLeaf(*m_vdb_grid, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_values(ls) + 512 * i, vdbm_leafset_active(ls) + 8 * i);
+    BackendT::putMapLeaves(*m_vdb_grid, vdbm_leafset_size(ls), vdbm_leafset_origins(ls), vdbm_leafset_values(ls), vdbm_leafset_active(ls));
     vdbm_leafset_free(ls);
   }
 

@@ -6,8 +6,34 @@
 #ifndef VDB_MAPPING_DETAIL_BACKEND_HPP_INCLUDED
 #define VDB_MAPPING_DETAIL_BACKEND_HPP_INCLUDED
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <thread>
+#include <vector>
+
+namespace vdb_mapping {
+namespace detail {
+// f(i) for i in [0, n) on a few threads (host-side payload copies of the grid mirror); serial for small n
+template <typename F>
+inline void parallelFor(std::uint64_t n, F&& f)
+{
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const unsigned T  = n < 4096 ? 1u : std::min(8u, hw);
+  if (T == 1)
+  {
+    for (std::uint64_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < T; ++t)
+    th.emplace_back([&, t] {
+      for (std::uint64_t i = n * t / T; i < n * (t + 1) / T; ++i) f(i);
+    });
+  for (auto& x : th) x.join();
+}
+} // namespace detail
+} // namespace vdb_mapping
 
 #if !defined(VDBM_FORCE_COMPAT) && defined(__has_include)
 #if __has_include(<openvdb/openvdb.h>) && __has_include(<pcl/point_types.h>) && __has_include(<Eigen/Core>)
@@ -59,6 +85,20 @@ struct Backend
     typename GridT::TreeType::LeafNodeType::NodeMaskType mask;
     for (int w = 0; w < 8; ++w) mask.template getWord<openvdb::Index64>(w) = active[w];
     leaf->setValueMask(mask);
+  }
+  // many exported map leaves at once: the tree is touched serially (node creation is not thread-safe), the 2 KB payloads
+  // are then copied by a few threads (distinct leaves)
+  static void putMapLeaves(GridT& grid, std::uint64_t n, const std::int32_t* origins, const float* values, const std::uint64_t* active)
+  {
+    using LeafT = typename GridT::TreeType::LeafNodeType;
+    std::vector<LeafT*> dst(n);
+    for (std::uint64_t i = 0; i < n; ++i) dst[i] = grid.tree().touchLeaf(openvdb::Coord(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]));
+    parallelFor(n, [&](std::uint64_t i) {
+      std::memcpy(dst[i]->buffer().data(), values + 512 * i, 512 * sizeof(float));
+      typename LeafT::NodeMaskType mask;
+      for (int w = 0; w < 8; ++w) mask.template getWord<openvdb::Index64>(w) = active[8 * i + w];
+      dst[i]->setValueMask(mask);
+    });
   }
   static void putUpdateLeaf(UpdateGridT& grid, const std::int32_t origin[3], const std::uint64_t* active, const std::uint64_t* value)
   {
@@ -160,6 +200,15 @@ struct Backend
     auto& leaf = grid.touchLeaf(openvdb::Coord(origin[0], origin[1], origin[2]));
     std::memcpy(leaf.values, values, 512 * sizeof(float));
     std::memcpy(leaf.active, active, 8 * sizeof(std::uint64_t));
+  }
+  static void putMapLeaves(GridT& grid, std::uint64_t n, const std::int32_t* origins, const float* values, const std::uint64_t* active)
+  {
+    std::vector<openvdb::HostLeaf<float>*> dst(n);
+    for (std::uint64_t i = 0; i < n; ++i) dst[i] = &grid.touchLeaf(openvdb::Coord(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]));
+    parallelFor(n, [&](std::uint64_t i) {
+      std::memcpy(dst[i]->values, values + 512 * i, 512 * sizeof(float));
+      std::memcpy(dst[i]->active, active + 8 * i, 8 * sizeof(std::uint64_t));
+    });
   }
   static void putUpdateLeaf(UpdateGridT& grid, const std::int32_t origin[3], const std::uint64_t* active, const std::uint64_t* value)
   {
