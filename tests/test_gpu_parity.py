@@ -585,3 +585,25 @@ def test_large_exports_are_views_that_outlive_calls_and_the_map():
     del a, b, c2
     import gc; gc.collect()
     assert np.array_equal(keep.view(np.uint32), snap[5].view(np.uint32))
+
+
+def test_prefetch_mixed_with_queued_scans_does_not_clobber_the_cloud_in_flight():
+    """A prefetch issued while a queued scan is still reading its staging buffer must go to the OTHER buffer, also when the
+    next call is another vdbm_insert_async rather than the accumulate the prefetch was meant for."""
+    import torch
+    from vdb_mapping_b200 import scans
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    c = scans.CONFIGS[1]
+    g = OccupancyVDBMapping(c.resolution); ref = OccupancyVDBMapping(c.resolution)
+    for m in (g, ref):
+        m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+        m.addInputSource("s", c.max_range)
+    clouds = [scans.make_scan(1, k) for k in range(6)]
+    pinned = [torch.from_numpy(np.ascontiguousarray(np.concatenate([p[:, :3], np.ones((len(p), 1), np.float32)], axis=1))).pin_memory()
+              for p, _ in clouds]
+    junk = torch.full_like(pinned[0], 7.0).pin_memory()
+    for k, (pts, origin) in enumerate(clouds):
+        g.insertRawAsync(pinned[k].data_ptr(), pinned[k].shape[0], origin, "s")
+        g.prefetchRaw(junk.data_ptr(), junk.shape[0])  # never consumed
+        ref.insertPointCloud(pts, origin, "s")
+    assert_leafsets_equal(g.exportMap(), ref.exportMap(), "map")

@@ -1098,6 +1098,7 @@ int vdbm_accumulate(vdbm_map* m, const char* source_id, const void* points, uint
   {
     // the cloud was uploaded ahead of time by vdbm_prefetch (copy stream): no H2D on the critical path
     m->prefetch.valid = false;
+    m->async_buf      = m->prefetch.buf;
     CU_TRY(m, cudaEventSynchronize(m->ev_copy));
     return raycastDevice(m, *s, m->d_points_async[m->prefetch.buf], n, stride_bytes, origin, s->max_range);
   }
@@ -1171,8 +1172,7 @@ int vdbm_prefetch(vdbm_map* m, const void* points, uint64_t n, uint64_t stride_b
   CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
   CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
   m->prefetch.host = points; m->prefetch.n = n; m->prefetch.stride = stride_bytes; m->prefetch.buf = buf; m->prefetch.valid = true;
-  m->async_buf = buf;
-  return VDBM_OK;
+  return VDBM_OK; // async_buf (the buffer the latest scan reads) only moves when a scan actually uses this copy
 }
 
 int vdbm_flush(vdbm_map* m)
