@@ -310,8 +310,9 @@ __global__ void __launch_bounds__(128) long_ray_segments_kernel(RaycastArgs a, u
 // ====================================================================================================
 constexpr int kBatch = 4;
 
-// MODE is a profiling hook (env VDBM_DDA_MODE, default 0): 0 = product path; 1 = no mask writes (pure traversal
-// cost); 2 = plain 64-bit stores instead of REDs (LSU path without the L2 atomic unit). Modes 1/2 give WRONG maps.
+// MODE is a profiling hook: 0 = product path; 1 = no mask writes (pure traversal cost); 2 = plain 64-bit stores instead of
+// REDs (LSU path without the L2 atomic unit). Modes 1/2 give WRONG maps and only exist in builds made with
+// -DVDBM_EXPERIMENTS (then selected with env VDBM_DDA_MODE); the product library always runs mode 0.
 template <int MODE>
 __device__ __forceinline__ void markWord(uint64_t* p, uint64_t v)
 {
@@ -1820,10 +1821,13 @@ void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Co
   if (a.n == 0) return;
   const uint64_t blocks = (((uint64_t(a.n_segs) + 31) / 32) + 7) / 8;
   if (uint64_t(grid) > blocks) grid = int(blocks);
+#ifdef VDBM_EXPERIMENTS
   static const int mode = [] { const char* e = getenv("VDBM_DDA_MODE"); return e ? atoi(e) : 0; }();
   if (mode == 1) VDBM_LAUNCH(raycast_dda_kernel<1>, grid, 256, s, a, g, near_act, ctr);
   else if (mode == 2) VDBM_LAUNCH(raycast_dda_kernel<2>, grid, 256, s, a, g, near_act, ctr);
-  else VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, near_act, ctr);
+  else
+#endif
+    VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, near_act, ctr);
   VDBM_LAUNCH(merge_near_kernel, (kNearBricks * kBrickLeaves * 8) / 256, 256, s, g, near_act, nearBrick0(a.origin_idx[0]),
               nearBrick0(a.origin_idx[1]), nearBrick0(a.origin_idx[2]), ctr);
 }
