@@ -895,7 +895,8 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
     std::fprintf(stderr, "vdbm_b200: no CUDA device available; this library has no CPU fallback\n");
     return VDBM_ERR_CUDA;
   }
-  auto m    = std::make_unique<vdbm_map>();
+  // a failure anywhere below releases whatever was allocated so far (vdbm_destroy copes with a half-built handle)
+  std::unique_ptr<vdbm_map, void (*)(vdbm_map*)> m(new vdbm_map(), &vdbm_destroy);
   m->params = *params;
   if (params->device >= 0)
   {
@@ -955,8 +956,9 @@ void vdbm_destroy(vdbm_map* m)
   cudaStreamSynchronize(m->stream);
   cudaStreamSynchronize(m->copy_stream);
   cudaFree(m->d_points_async[0]); cudaFree(m->d_points_async[1]);
-  cudaEventDestroy(m->ev3); cudaEventDestroy(m->ev_copy); cudaEventDestroy(m->ev_done);
-  cudaStreamDestroy(m->copy_stream);
+  for (cudaEvent_t e : {m->ev3, m->ev_copy, m->ev_done})
+    if (e) cudaEventDestroy(e);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   for (auto& kv : m->sources)
   {
     freeUpdateGrid(kv.second->g);
@@ -981,8 +983,9 @@ void vdbm_destroy(vdbm_map* m)
     m->h_stage                        = nullptr;
   }
   if (m->h_stage) cudaFreeHost(m->h_stage);
-  cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1); cudaEventDestroy(m->ev2);
-  if (m->own_stream) cudaStreamDestroy(m->stream);
+  for (cudaEvent_t e : {m->ev0, m->ev1, m->ev2})
+    if (e) cudaEventDestroy(e);
+  if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
 
