@@ -607,3 +607,32 @@ def test_prefetch_mixed_with_queued_scans_does_not_clobber_the_cloud_in_flight()
         g.prefetchRaw(junk.data_ptr(), junk.shape[0])  # never consumed
         ref.insertPointCloud(pts, origin, "s")
     assert_leafsets_equal(g.exportMap(), ref.exportMap(), "map")
+
+
+@pytest.mark.parametrize("tbs", ["1", "auto"])
+def test_test_before_set_marking_is_exact(tbs, monkeypatch):
+    """Scans whose rays overlap heavily (depth camera) load a mask word and skip the RED when its bits are already set
+    (raycast_dda_kernel<4>). Forced on for random LiDAR-like scans, and chosen automatically on BASELINE config 3 at full
+    size (47 visits per distinct voxel): update grid, change grid and map stay bit-identical to the oracle."""
+    from vdb_mapping_b200 import scans
+    if tbs != "auto":
+        monkeypatch.setenv("VDBM_DDA_TBS", tbs)
+        g, o = _pair(0.1, 4.0, CFG_GTEST)
+        for k in range(5):
+            pts, origin = scans.small_scan(900 + k, n=4000, scale=2.5)
+            g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+            assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), f"update grid {k}")
+            g.integrateUpdate(keep_change=True); o.integrateUpdate()
+            assert_leafsets_equal(g.exportLastChange("s"), o.exportLastChange("s"), f"change {k}")
+        assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
+        return
+    c = scans.CONFIGS[3]
+    g, o = _pair(c.resolution, c.max_range, (c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max))
+    for k in range(3):  # the first scan runs the plain kernel, the overlap ratio it reports switches the next ones over
+        pts, origin = scans.make_scan(3, k)
+        g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+        assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), f"cfg3 update grid {k}")
+        g.integrateUpdate(keep_change=False); o.integrateUpdate()
+        st = g.stats()
+        assert st["last_visits"] > 8 * st["last_voxel_updates"]
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "cfg3 map")

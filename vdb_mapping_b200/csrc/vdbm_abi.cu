@@ -39,6 +39,7 @@ struct Source
   uint32_t cap       = 0;         // brick slots
   uint64_t prev_visits     = 0;   // voxel marks and longest ray of this source's previous scan: the segment length of
   uint32_t prev_max_visits = 0;   // the next scan is planned from them (consecutive scans of a sensor look alike)
+  uint64_t prev_updates    = 0;   // distinct voxels of the previous scan: visits / updates = how heavily its rays overlap
   uint32_t n_bricks  = 0;         // host copies, valid after every synchronising call
   uint32_t n_entries = 0;         // touched leaves (compact list is always rebuilt after a grid write)
   LeafRecord* d_change = nullptr; // change records of the last update (device)
@@ -332,6 +333,14 @@ bool originIndex(double res, const double o[3], int32_t out[3])
   return true;
 }
 
+// Rays of a depth camera overlap heavily (dozens of visits per distinct voxel): then the DDA tests a mask word before it
+// issues the RED. Decided from the source's previous scan; VDBM_DDA_TBS=0/1 overrides (tests, experiments).
+bool testBeforeSet(const Source& s)
+{
+  if (const char* e = getenv("VDBM_DDA_TBS")) return atoi(e) != 0;
+  return s.prev_updates != 0 && s.prev_visits > 8 * s.prev_updates;
+}
+
 // ---- the raycast (K0 + K1) on device-resident points ---------------------------------------------------
 int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, uint64_t stride, const double origin[3], double range,
                   bool index_mode = false)
@@ -430,7 +439,7 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     sortRaysByLength(m->d_sort_tmp, m->sort_tmp_bytes, a.sort_keys, m->d_sort + m->seg_cap, a.sort_idx, m->d_sort + 3 * m->seg_cap,
                      a.n_segs, m->stream);
     CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
-    launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream);
+    launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream, testBeforeSet(s));
     launchCompactLeaves(s.g, m->stream);
     CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
     CU_TRY(m, cudaGetLastError());
@@ -827,6 +836,7 @@ int finishPending(vdbm_map* m)
   cudaEventElapsedTime(&ms, m->ev1, m->ev3); m->stats.last_integrate_ms = ms;
   s.prev_visits     = m->stats.last_visits;
   s.prev_max_visits = c.max_visits;
+  s.prev_updates    = m->stats.last_voxel_updates;
   s.n_bricks = s.n_entries = 0;
   s.n_change        = 0;
   m->async_expect   = c.deferred_entries;
@@ -1129,6 +1139,10 @@ int vdbm_integrate(vdbm_map* m, int keep_change)
   m->stats.last_touched_leaves = 0;
   const uint64_t upd_before    = m->stats.voxel_updates;
   CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+  Source* only   = nullptr; // the one source that holds data, if there is exactly one (its ray-overlap ratio is then known)
+  int with_data  = 0;
+  for (auto& kv : m->sources)
+    if (kv.second->n_entries) { only = kv.second.get(); ++with_data; }
   for (auto& kv : m->sources) // std::map key order, V:380
   {
     int rc = updateMapInternal(m, *kv.second, keep_change != 0);
@@ -1148,6 +1162,7 @@ int vdbm_integrate(vdbm_map* m, int keep_change)
   cudaEventElapsedTime(&ms, m->ev0, m->ev1);
   m->stats.last_integrate_ms  = ms;
   m->stats.last_voxel_updates = m->stats.voxel_updates - upd_before;
+  if (with_data == 1) only->prev_updates = m->stats.last_voxel_updates;
   if (m->h_ctr->flags & kFlagMapOverflow) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "map hash / leaf pool overflow");
   return VDBM_OK;
 }
@@ -1285,7 +1300,7 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
   sortRaysByLength(m->d_sort_tmp, m->sort_tmp_bytes, a.sort_keys, m->d_sort + m->seg_cap, a.sort_idx, m->d_sort + 3 * m->seg_cap, a.n_segs,
                    m->stream);
   CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
-  launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream);
+  launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream, testBeforeSet(s));
   launchCompactLeaves(s.g, m->stream);
   CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
   launchApplyUpdateDeferred(s.g, m->mt, m->lo, m->d_resolved, uint32_t(std::min<size_t>(m->resolved_cap, 0xFFFFFFFFu)), m->d_ctr, expect, m->stream);

@@ -224,7 +224,9 @@ __host__ __device__ __forceinline__ size_t inboxBytes(uint32_t n_regions, uint32
 void launchPrepRays(const RaycastArgs& a, Counters* ctr, cudaStream_t s);
 void launchLongRaySegments(const RaycastArgs& a, uint32_t n_long, cudaStream_t s);
 // near_act: zero-initialised scratch of nearCopiesBytes() bytes (privatised near-field bricks), left zeroed again
-void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s);
+// test_before_set: load the mask word and skip the RED when its bits are already there (scans with heavily overlapping rays)
+void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s,
+                      bool test_before_set = false);
 size_t nearCopiesBytes();
 int raycastDDAGrid(int device);
 // rebuild ug.entries / counters[1] from the occupied bricks (brick count read on the device)

@@ -313,9 +313,20 @@ constexpr int kBatch = 4;
 // MODE is a profiling hook: 0 = product path; 1 = no mask writes (pure traversal cost); 2 = plain 64-bit stores instead of
 // REDs (LSU path without the L2 atomic unit). Modes 1/2 give WRONG maps and only exist in builds made with
 // -DVDBM_EXPERIMENTS (then selected with env VDBM_DDA_MODE); the product library always runs mode 0.
+// MODE 4 (product; chosen per scan by the host for scans whose rays overlap heavily, e.g. a depth camera: 47 visits per
+// distinct voxel in BASELINE config 3): test before set. Bits are only ever SET while this kernel runs, so a (possibly
+// stale, L1-cached) load that already shows all bits of `v` proves the RED redundant; a stale zero merely costs the RED
+// it would have cost anyway. There ~98 % of the REDs - same-address atomics that serialise in L2 - become L1/L2 load hits.
+// For LiDAR scans (2-3 visits per voxel) the extra dependent load would only add latency, hence a separate instantiation.
 template <int MODE>
 __device__ __forceinline__ void markWord(uint64_t* p, uint64_t v)
 {
+  if (MODE == 4)
+  {
+    const uint64_t old = __ldca(reinterpret_cast<const unsigned long long*>(p));
+    if ((old & v) != v) redOr64(p, v);
+    return;
+  }
   if (MODE == 0) redOr64(p, v);
   else if (MODE == 2) asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -1816,7 +1827,7 @@ int raycastDDAGrid(int device)
 
 size_t nearCopiesBytes() { return size_t(kNearCopies) * kNearBricks * kBrickLeaves * 8 * sizeof(uint64_t); }
 
-void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s)
+void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s, bool test_before_set)
 {
   if (a.n == 0) return;
   const uint64_t blocks = (((uint64_t(a.n_segs) + 31) / 32) + 7) / 8;
@@ -1827,7 +1838,8 @@ void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Co
   else if (mode == 2) VDBM_LAUNCH(raycast_dda_kernel<2>, grid, 256, s, a, g, near_act, ctr);
   else
 #endif
-    VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, near_act, ctr);
+  if (test_before_set) VDBM_LAUNCH(raycast_dda_kernel<4>, grid, 256, s, a, g, near_act, ctr);
+  else VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, near_act, ctr);
   VDBM_LAUNCH(merge_near_kernel, (kNearBricks * kBrickLeaves * 8) / 256, 256, s, g, near_act, nearBrick0(a.origin_idx[0]),
               nearBrick0(a.origin_idx[1]), nearBrick0(a.origin_idx[2]), ctr);
 }
