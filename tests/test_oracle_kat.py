@@ -394,3 +394,33 @@ def test_flat_probe_counts_match_the_oracle():
         sf = f.stats()
         assert sf["visits"] == so["visits"] and sf["voxel_updates"] == so["voxel_updates"]
         assert sf["map_leaves"] == o.mapLeafCount() and sf["active_voxels"] == active
+
+
+def test_oracle_vs_pyref_fuzz():
+    """Property test over resolutions, ranges, far-away / negative origins and points that sit exactly on voxel
+    boundaries (the fmod branch of worldToIndex): the oracle's update grid equals the pure-Python restatement's."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(res=st.sampled_from([0.02, 0.05, 0.1, 0.25, 1.0]), rng_m=st.sampled_from([0.6, 1.5, 4.0]),
+           ox=st.floats(-50, 50), oy=st.floats(-50, 50), oz=st.floats(-5, 5), seed=st.integers(0, 2**31 - 1),
+           snap=st.booleans())
+    def run(res, rng_m, ox, oy, oz, seed, snap):
+        rng = np.random.default_rng(seed)
+        origin = np.array([ox, oy, oz])
+        if snap:
+            origin = np.round(origin / res) * res  # origin on a voxel corner
+        pts = (origin + rng.uniform(-1.5 * rng_m, 1.5 * rng_m, size=(12, 3)) * np.array([1, 1, 0.4])).astype(np.float32)
+        if snap:
+            pts[::2] = (np.round(pts[::2].astype(np.float64) / res) * res).astype(np.float32)
+        pts[3] = pts[5]  # duplicate ray
+        pts[7] = origin.astype(np.float32)  # (almost) zero-length ray
+        o = OracleOccupancyVDBMapping(res)
+        assert o.setConfig(rng_m, 0.7, 0.4, 0.12, 0.97) == 0
+        o.addInputSource("s", rng_m, 0)
+        assert o.accumulateUpdate(pts, origin, "s") == 0
+        upd_o = pyref.leafset_to_voxels(o.exportUpdateGrid("s"))
+        upd_p = pyref.raycast(pts, origin, res, rng_m)
+        assert {k: v[1] for k, v in upd_o.items()} == upd_p
+
+    run()

@@ -505,6 +505,19 @@ int stagePoints(vdbm_map* m, const void* points, uint64_t n, uint64_t stride)
   return VDBM_OK;
 }
 
+// room for n entries in the K2a output array (geometric growth: reallocation synchronises the device)
+int ensureResolved(vdbm_map* m, size_t n)
+{
+  if (m->resolved_cap >= n) return VDBM_OK;
+  cudaFree(m->d_resolved);
+  m->d_resolved   = nullptr;
+  m->resolved_cap = 0;
+  const size_t cap = n + n / 4 + 1024;
+  CU_TRY(m, cudaMalloc(&m->d_resolved, cap * 4));
+  m->resolved_cap = cap;
+  return VDBM_OK;
+}
+
 // updateMap for one source (K2). want_change: keep change records on the device.
 int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
 {
@@ -529,15 +542,8 @@ int updateMapInternal(vdbm_map* m, Source& s, bool want_change)
     CU_TRY(m, cudaMalloc(&s.d_change, size_t(want) * sizeof(LeafRecord)));
     s.change_cap = want;
   }
-  if (m->resolved_cap < n)
-  {
-    cudaFree(m->d_resolved);
-    m->d_resolved   = nullptr;
-    m->resolved_cap = 0;
-    const size_t cap = size_t(n) + n / 4 + 1024;
-    CU_TRY(m, cudaMalloc(&m->d_resolved, cap * 4));
-    m->resolved_cap = cap;
-  }
+  rc = ensureResolved(m, n);
+  if (rc) return rc;
   CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_change, 0, sizeof(unsigned), m->stream));
   launchApplyUpdate(s.g, m->mt, m->lo, m->d_resolved, want_change ? s.d_change : nullptr, want_change ? s.change_cap : 0, m->d_ctr, n,
                     m->stream);
@@ -1256,15 +1262,8 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
   const uint32_t expect = m->async_expect + m->async_expect / 2 + 65536; // leaves the update is sized for (guard checks the truth)
   rc = ensureMapCapacity(m, expect);
   if (rc) return rc;
-  if (m->resolved_cap < expect)
-  {
-    cudaFree(m->d_resolved);
-    m->d_resolved   = nullptr;
-    m->resolved_cap = 0;
-    const size_t cap = size_t(expect) + expect / 4 + 1024;
-    CU_TRY(m, cudaMalloc(&m->d_resolved, cap * 4));
-    m->resolved_cap = cap;
-  }
+  rc = ensureResolved(m, expect);
+  if (rc) return rc;
   RaycastArgs a{};
   a.points = d_pts;
   a.n      = n;
@@ -2025,15 +2024,8 @@ int vdbm_update_pull_integrate(vdbm_map* m, const char* source_id)
   const uint32_t expect = m->async_expect + m->async_expect / 2 + 65536;
   int rc = ensureMapCapacity(m, expect);
   if (rc) return rc;
-  if (m->resolved_cap < expect)
-  {
-    cudaFree(m->d_resolved);
-    m->d_resolved   = nullptr;
-    m->resolved_cap = 0;
-    const size_t cap = size_t(expect) + expect / 4 + 1024;
-    CU_TRY(m, cudaMalloc(&m->d_resolved, cap * 4));
-    m->resolved_cap = cap;
-  }
+  rc = ensureResolved(m, expect);
+  if (rc) return rc;
   const uint64_t upd_before = m->stats.voxel_updates;
   launchWaitPeers(ex.ctrl, ex.px.n_ranks, ex.epoch & 1u, ex.epoch, ex.d_counts, m->d_ctr, m->stream);
   CU_TRY(m, cudaEventRecord(ex.ev[2], m->stream));
