@@ -636,3 +636,21 @@ def test_test_before_set_marking_is_exact(tbs, monkeypatch):
         st = g.stats()
         assert st["last_visits"] > 8 * st["last_voxel_updates"]
     assert_leafsets_equal(g.exportMap(), o.exportMap(), "cfg3 map")
+
+
+def test_many_invalid_points_do_not_starve_very_short_rays():
+    """Regression: the longest-first sort only looks at key bits [4, 20), so rays with 1..15 marks used to tie with the
+    empty work items (NaN points). With more empty items than resident lanes (a depth frame with > 60 % invalid pixels),
+    every lane retired on a zero key before the short rays behind them were fetched, and those rays were lost."""
+    g, o = _pair(0.1, 4.0, CFG_ROS)
+    rng = np.random.default_rng(3)
+    n_nan, n_short, n_long = 260_000, 120_000, 20_000
+    origin = np.array([0.03, 0.02, 0.01])
+    short = (origin + rng.uniform(-0.45, 0.45, size=(n_short, 3))).astype(np.float32)   # <= ~13 marks each
+    long_ = (origin + rng.uniform(-3.0, 3.0, size=(n_long, 3))).astype(np.float32)
+    pts = np.concatenate([np.full((n_nan, 3), np.nan, np.float32), short, long_])
+    assert g.accumulateUpdate(pts, origin, "s") == 0 and o.accumulateUpdate(pts, origin, "s") == 0
+    assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "update grid")
+    g.integrateUpdate(keep_change=False); o.integrateUpdate()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
+    assert g.stats()["visits"] == o.stats()["visits"]

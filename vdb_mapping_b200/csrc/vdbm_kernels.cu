@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
       }
     }
     a.segs[i]      = sg;
-    a.sort_keys[i] = key;
+    // The sort only looks at key bits [4, 20): a work item with 1..15 marks would tie with the empty items (key 0) and
+    // could end up behind more zero keys than there are lanes to retire on them. Lift every real item above the zeros.
+    a.sort_keys[i] = (key != 0u && key < 16u) ? 16u : key;
     a.sort_idx[i]  = uint32_t(i);
   }
   // warp-aggregated statistics
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(128) long_ray_segments_kernel(RaycastArgs a, u
     sg->ray   = ray;
     sg->last  = (j + 1 == P) ? 1u : 0u;
     const uint32_t slot = (j == 0) ? ray : (xb + j - 1);
-    a.sort_keys[slot]   = cnt > 0xFFFFFu ? 0xFFFFFu : cnt;
+    a.sort_keys[slot]   = cnt > 0xFFFFFu ? 0xFFFFFu : ((cnt != 0u && cnt < 16u) ? 16u : cnt); // see prep_rays_kernel
     a.sort_idx[slot]    = slot;
     s_prev              = s_next;
   }
