@@ -654,3 +654,25 @@ def test_many_invalid_points_do_not_starve_very_short_rays():
     g.integrateUpdate(keep_change=False); o.integrateUpdate()
     assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
     assert g.stats()["visits"] == o.stats()["visits"]
+
+
+def test_prefetch_is_one_shot_and_async_insert_of_unknown_source_still_integrates():
+    import torch
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, CFG_ROS, sources=("s",))
+    for m in (g, o):
+        m.addInputSource("off", -1.0, 0)  # negative range: accumulateUpdate ignores the cloud (VDBMapping.hpp:331)
+    (pa, origin), (pb, _) = scans.small_scan(810, n=2000, scale=2.5), scans.small_scan(811, n=2000, scale=2.5)
+    buf = torch.ones((2000, 4), dtype=torch.float32).pin_memory()
+    buf[:, :3] = torch.from_numpy(pa[:, :3])
+    g.prefetchRaw(buf.data_ptr(), 2000)
+    g.accumulateRaw(buf.data_ptr(), 2000, origin, "off")       # ignored call: must consume the prefetched copy anyway
+    g.synchronize()
+    buf[:, :3] = torch.from_numpy(pb[:, :3])                   # same address, new cloud
+    g.accumulateRaw(buf.data_ptr(), 2000, origin, "s")
+    o.accumulateUpdate(pa, origin, "off"); o.accumulateUpdate(pb, origin, "s")
+    assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "update grid must come from the refilled buffer")
+    # insertPointCloud on an unknown source: accumulateUpdate complains, integrateUpdate still runs (V:399-406)
+    g.insertPointCloudAsync(pa, origin, "nope"); o.insertPointCloud(pa, origin, "nope")
+    assert len(g.exportUpdateGrid("s")) == 0
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map after the integrate triggered by the unknown-source insert")

@@ -1109,17 +1109,20 @@ int vdbm_accumulate(vdbm_map* m, const char* source_id, const void* points, uint
 {
   if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
   VDBM_ENTER(m);
+  // a prefetched copy is good for exactly ONE accumulate call, whatever that call ends up doing (an ignored call must
+  // not leave a stale copy behind that a later call with a refilled buffer at the same address would pick up)
+  const auto pf     = m->prefetch;
+  m->prefetch.valid = false;
   Source* s = findSource(m, source_id);
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : "")); // V:320-326
   if (!(s->max_range > 0)) return VDBM_OK;                                                                             // V:331
   if (!m->config_set) return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
-  if (m->prefetch.valid && m->prefetch.host == points && m->prefetch.n == n && m->prefetch.stride == stride_bytes)
+  if (pf.valid && pf.host == points && pf.n == n && pf.stride == stride_bytes)
   {
     // the cloud was uploaded ahead of time by vdbm_prefetch (copy stream): no H2D on the critical path
-    m->prefetch.valid = false;
-    m->async_buf      = m->prefetch.buf;
+    m->async_buf = pf.buf;
     CU_TRY(m, cudaEventSynchronize(m->ev_copy));
-    return raycastDevice(m, *s, m->d_points_async[m->prefetch.buf], n, stride_bytes, origin, s->max_range);
+    return raycastDevice(m, *s, m->d_points_async[pf.buf], n, stride_bytes, origin, s->max_range);
   }
   int rc = stagePoints(m, points, n, stride_bytes);
   if (rc) return rc;
@@ -1225,7 +1228,13 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
   // 2. finish the previous scan (the one synchronisation per scan)
   int rc = finishPending(m);
   if (rc) return rc;
-  if (!sp) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  if (!sp)
+  {
+    // like vdbm_insert: accumulateUpdate complains and returns (V:320-326), integrateUpdate still runs (V:404)
+    rc = vdbm_integrate(m, 0);
+    if (rc) return rc;
+    return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  }
   Source& s = *sp;
   if (!points_on_device)
   {

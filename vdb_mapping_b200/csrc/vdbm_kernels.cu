@@ -833,14 +833,14 @@ __global__ void reset_bricks_kernel(UpdateGrid g, uint32_t n_bricks, const uint3
 }
 
 // Deferred updateMap (vdbm_insert_async): the host queued the update kernels without knowing how many leaves the raycast
-// touched. This one-thread kernel decides ON THE DEVICE whether they may run: no overflow / range flag, the brick hash not
+// touched. This one-thread kernel decides ON THE DEVICE whether they may run: no status flag raised, the brick hash not
 // crowded, and room for every touched leaf in `resolved`, the leaf pool and the map hash. It publishes the counts the
 // following kernels read; zero counts turn them into no-ops and the host redoes the scan synchronously.
 __global__ void update_guard_kernel(UpdateGrid g, MapTable mt, Counters* ctr, uint32_t resolved_cap)
 {
   const uint32_t n_bricks = g.counters[0], n_entries = g.counters[1];
   const uint64_t need = uint64_t(*mt.n_leaves) + n_entries;
-  const bool ok = (ctr->flags & (kFlagUpdateOverflow | kFlagCoordRange | kFlagMapOverflow)) == 0 &&
+  const bool ok = ctr->flags == 0 && // any pending condition (overflow, out-of-range points, exchange trouble) goes to the host first
                   uint64_t(n_bricks) * 10 <= (uint64_t(g.cap_mask) + 1) * 7 && n_entries <= resolved_cap && need <= mt.pool_cap &&
                   need * 2 <= uint64_t(mt.hcap_mask) + 1;
   ctr->deferred_entries = ok ? n_entries : 0u;
