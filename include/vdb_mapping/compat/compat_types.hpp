@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <iterator>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -246,6 +247,21 @@ public:
     return it == m_leaves.end() ? nullptr : &it->second;
   }
   LeafT& touchLeaf(const Coord& xyz) { return m_leaves[Coord(xyz[0] & ~7, xyz[1] & ~7, xyz[2] & ~7)]; }
+  // touchLeaf for many leaf origins at once. Exports arrive sorted by origin (x, then y, then z), the map's own order, so
+  // one merge walk over the map replaces n logarithmic look-ups; unsorted input still works (falls back to lower_bound).
+  void touchLeaves(std::uint64_t n, const std::int32_t* origins, std::vector<LeafT*>& out)
+  {
+    out.resize(n);
+    auto it = m_leaves.begin();
+    for (std::uint64_t i = 0; i < n; ++i)
+    {
+      const Coord key(origins[3 * i] & ~7, origins[3 * i + 1] & ~7, origins[3 * i + 2] & ~7);
+      if (it != m_leaves.begin() && !(std::prev(it)->first < key)) it = m_leaves.lower_bound(key); // went backwards
+      while (it != m_leaves.end() && it->first < key) ++it;
+      if (it == m_leaves.end() || key < it->first) it = m_leaves.emplace_hint(it, key, LeafT());
+      out[i] = &it->second;
+    }
+  }
   const LeafMap& leaves() const { return m_leaves; }
   LeafMap& leaves() { return m_leaves; }
 

@@ -203,8 +203,8 @@ struct Backend
   }
   static void putMapLeaves(GridT& grid, std::uint64_t n, const std::int32_t* origins, const float* values, const std::uint64_t* active)
   {
-    std::vector<openvdb::HostLeaf<float>*> dst(n);
-    for (std::uint64_t i = 0; i < n; ++i) dst[i] = &grid.touchLeaf(openvdb::Coord(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]));
+    std::vector<openvdb::HostLeaf<float>*> dst;
+    grid.touchLeaves(n, origins, dst);
     parallelFor(n, [&](std::uint64_t i) {
       std::memcpy(dst[i]->values, values + 512 * i, 512 * sizeof(float));
       std::memcpy(dst[i]->active, active + 8 * i, 8 * sizeof(std::uint64_t));

@@ -37,6 +37,15 @@ def test_shim_public_surface_matches_the_reference_names():
         assert name in occ, name
 
 
+def test_standin_host_grid_bulk_update(tmp_path):
+    """CPU-only: the bulk leaf update behind the shim's eager mirror (merge walk + threaded payload copy) equals per-leaf updates."""
+    exe = str(tmp_path / "test_compat_grid")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"),
+                    os.path.join(ROOT, "tests", "cpp", "test_compat_grid.cpp"), "-pthread", "-o", exe], check=True)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and "0 failed" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
 @pytest.mark.gpu
 def test_reference_scenarios_through_the_cpp_shim():
     p = subprocess.run([_build()], capture_output=True, text=True, timeout=300)
