@@ -129,7 +129,9 @@ int vdbm_insert(vdbm_map* map, const char* source_id, const void* points, uint64
  * handle - any entry point except vdbm_stats / vdbm_last_error - finishes it. Scans the queued path cannot take (tables
  * that must grow, long rays that need segmentation, several sources holding data, artificial areas, the first scans of a
  * map) run synchronously inside the call or are redone by the finishing call; results are identical either way. A status
- * belonging to a queued scan (e.g. VDBM_ERR_COORD_RANGE) is returned by the call that finishes it. points_on_device != 0:
+ * belonging to a queued scan (e.g. VDBM_ERR_COORD_RANGE) is returned by the call that finishes it: another entry point
+ * then returns that status instead of doing its own work (call it again), while vdbm_insert_async still queues its scan
+ * and returns the earlier scan's VDBM_ERR_COORD_RANGE as a warning. points_on_device != 0:
  * `points` is device memory and must stay valid until the scan is finished; a host buffer is free when the call returns. */
 int vdbm_insert_async(vdbm_map* map, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes,
                       const double origin[3], int points_on_device);

@@ -1227,6 +1227,10 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
   }
   // 2. finish the previous scan (the one synchronisation per scan)
   int rc = finishPending(m);
+  // out-of-range points of the PREVIOUS scan are a warning, not a reason to drop this one: remember it, carry on, and
+  // return it at the end unless this scan has something of its own to report
+  int rc_prev = VDBM_OK;
+  if (rc == VDBM_ERR_COORD_RANGE) { rc_prev = rc; rc = VDBM_OK; }
   if (rc) return rc;
   if (!sp)
   {
@@ -1265,7 +1269,7 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
     if (rc_acc != VDBM_OK && rc_acc != VDBM_ERR_COORD_RANGE) return rc_acc;
     int rc_int = vdbm_integrate(m, 0);
     m->async_expect = uint32_t(std::max<uint64_t>(1, m->stats.last_touched_leaves));
-    return rc_int ? rc_int : rc_acc;
+    return rc_int ? rc_int : (rc_acc ? rc_acc : rc_prev);
   }
   // 4. queue the whole scan
   const uint32_t expect = m->async_expect + m->async_expect / 2 + 65536; // leaves the update is sized for (guard checks the truth)
@@ -1323,7 +1327,7 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
   m->pending.stride = stride_bytes;
   m->pending.d_pts  = d_pts;
   for (int k = 0; k < 3; ++k) m->pending.origin[k] = origin[k];
-  return VDBM_OK;
+  return rc_prev;
 }
 
 int vdbm_update_map(vdbm_map* m, const char* source_id, vdbm_leafset** change)
