@@ -50,7 +50,12 @@ def test_sass_is_sm100a_with_blackwell_256bit_accesses(so_path):
     assert "sm_100a" in out or "SM100a" in out.replace("_", "").upper() or "arch = sm_100" in out
     assert ".256" in out          # LDG/STG.E.ENL2.256 in the update / gather kernels
     assert "RED" in out           # red.global.or.b64 in the DDA kernel
-    assert "DFMA" not in out.split("raycast_dda_kernel")[1].split("Function :")[0]  # -fmad=false: no fused fp64 in the DDA
+    # -fmad=false: no fp64 contraction anywhere near the voxel paths. The ONLY DFMAs of the DDA kernel are its three
+    # "next[axis] += delta[axis]" selects per step: fma(delta, 1.0 or 0.0, next), exact by construction
+    dda = out.split("raycast_dda_kernelILi0E")[1].split("Function :")[0]
+    steps = dda.count("DSETP.GEU")  # one MinIndex evaluation per unrolled step
+    assert steps >= 2 and dda.count("DFMA") == 3 * steps and "DMUL" not in dda and "DADD" not in dda
+    # (prep_rays / wall_dda contain DFMA too: inside the correctly rounded software division / sqrt / fmod sequences)
 
 
 def test_create_fails_loudly_without_gpu(so_path):

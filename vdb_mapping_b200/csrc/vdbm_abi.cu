@@ -417,6 +417,7 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   // call that changes device counters ends with syncCounters(), so the pinned host copy is current.
   int rc = VDBM_OK;
   const Counters before = *m->h_ctr;
+  bool coord_range = false;
   for (int attempt = 0; attempt < 24; ++attempt)
   {
     CU_TRY(m, cudaMemsetAsync(&m->d_ctr->ray_cursor, 0, sizeof(unsigned), m->stream));
@@ -424,6 +425,9 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_extra, 0, 3 * sizeof(unsigned), m->stream)); // n_extra, n_long, max_visits
     // extra-segment slots that end up unused must carry a zero sort key (the DDA kernel stops at the first zero key)
     CU_TRY(m, cudaMemsetAsync(m->d_sort + n, 0, (m->seg_cap - n) * sizeof(uint32_t), m->stream));
+    // The DDA kernel marks z-slice mask words; leaves the grid already holds (an earlier accumulate of this period, or
+    // the failed attempt being replayed) are in the x-slice layout every other kernel works on: turn them back first.
+    launchUncookLeaves(s.g, s.n_entries, m->stream);
     launchPrepRays(a, m->d_ctr, m->stream);
     uint32_t n_long = 0, n_extra = 0;
     if (a.seg_len)
@@ -440,7 +444,7 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
                      a.n_segs, m->stream);
     CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
     launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream, testBeforeSet(s));
-    launchCompactLeaves(s.g, m->stream);
+    launchCompactLeaves(s.g, m->stream, /*cook=*/true);
     CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
     CU_TRY(m, cudaGetLastError());
     CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s.g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
@@ -454,14 +458,9 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     cudaEventElapsedTime(&ms, m->ev0, m->ev2);
     m->stats.last_prep_ms = ms;
     const uint32_t flags = m->h_ctr->flags;
-    if (flags & kFlagCoordRange)
-    {
-      CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
-      m->last_error = "some ray end points were outside the +-2^23 voxel range and were dropped";
-      m->stats.last_visits         = m->h_ctr->visits - before.visits;
-      m->stats.last_touched_leaves = s.n_entries;
-      return VDBM_ERR_COORD_RANGE;
-    }
+    // Out-of-range end points are only REPORTED (the rays are dropped, like +-inf); they must not hide an overflow of the
+    // brick hash raised by the same scan: complete the grid first (grow, replay), report afterwards.
+    if (flags & kFlagCoordRange) coord_range = true;
     const bool overflow = (flags & kFlagUpdateOverflow) != 0;
     const bool crowded  = uint64_t(s.n_bricks) * 10 > uint64_t(s.cap) * 7;
     if (!overflow && !crowded) break;
@@ -485,6 +484,15 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     m->ends_src = &s;
     m->ends_n   = n;
     for (int k = 0; k < 3; ++k) m->ends_origin[k] = origin[k];
+  }
+  if (coord_range)
+  {
+    // clear only this bit: whatever else was raised stays for its own handler
+    m->h_ctr->flags &= ~kFlagCoordRange;
+    CU_TRY(m, cudaMemcpyAsync(&m->d_ctr->flags, &m->h_ctr->flags, sizeof(unsigned), cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    m->last_error = "some ray end points were outside the +-2^23 voxel range and were dropped";
+    return VDBM_ERR_COORD_RANGE;
   }
   return VDBM_OK;
 }
@@ -1313,7 +1321,7 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
                    m->stream);
   CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
   launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream, testBeforeSet(s));
-  launchCompactLeaves(s.g, m->stream);
+  launchCompactLeaves(s.g, m->stream, /*cook=*/true); // the grid was empty (asyncEligible): nothing to uncook before
   CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
   launchApplyUpdateDeferred(s.g, m->mt, m->lo, m->d_resolved, uint32_t(std::min<size_t>(m->resolved_cap, 0xFFFFFFFFu)), m->d_ctr, expect, m->stream);
   CU_TRY(m, cudaEventRecord(m->ev3, m->stream));

@@ -229,8 +229,12 @@ void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, uint64_t* near_act, C
                       bool test_before_set = false);
 size_t nearCopiesBytes();
 int raycastDDAGrid(int device);
-// rebuild ug.entries / counters[1] from the occupied bricks (brick count read on the device)
-void launchCompactLeaves(UpdateGrid ug, cudaStream_t s);
+// rebuild ug.entries / counters[1] from the occupied bricks (brick count read on the device).
+// cook = true after launchRaycastDDA: the DDA kernel marks Z-SLICE mask words (word z&7 = the 8x8 x-y tile); the compaction
+// turns every touched leaf into OpenVDB's x-slice layout in place, so every other kernel sees x-slice words only.
+void launchCompactLeaves(UpdateGrid ug, cudaStream_t s, bool cook = false);
+// the inverse (same transform) for the listed leaves: needed before the DDA kernel marks into a grid that holds data
+void launchUncookLeaves(UpdateGrid ug, uint32_t n_entries, cudaStream_t s);
 // resolve (K2a) + apply (K2b); `resolved` is a device scratch array of >= n_entries u32
 void launchApplyUpdate(UpdateGrid ug, MapTable mt, LogOdds lo, uint32_t* resolved, LeafRecord* change_out, uint32_t change_cap,
                        Counters* ctr, uint32_t n_entries, cudaStream_t s);

@@ -303,14 +303,38 @@ __global__ void __launch_bounds__(128) long_ray_segments_kernel(RaycastArgs a, u
 //   next[a] = 0.5*|1/dir[a]| (exact), then repeated  next[axis] += delta[axis]  in fp64,
 //   axis = MinIndex(next) with its tie table {2,1,9,1,2,9,0,0}, continue while t <= 1.0.
 // The step is branch-free (selects), so the 32 lanes stay converged whatever axis each one takes.
-// Marking: bits of consecutive visits that fall in the same (leaf, x-slice) 64-bit mask word are merged in a
-// register and flushed with ONE fire-and-forget red.global.or.b64; x is monotonic along a ray, so every mask
-// word is flushed at most once per ray. Mask words are addressed arithmetically inside a 64^3-voxel brick;
-// the brick hash is consulted only when a ray enters a new brick, and those lookups (like the ray refills) are
-// batched at warp-uniform points every kBatch iterations so that their L2 round trip is paid once per batch
-// and not once per lane event.
+//
+// Marking (round 2: the instruction diet). While this kernel runs, the masks of the update grid are Z-SLICE words: word
+// (z & 7) of a leaf holds its 8x8 x-y tile, bit (y&7)<<3 | (x&7). LiDAR rays are close to horizontal, so a ray stays 4-5
+// steps inside one such word (tools/word_orientation_study.py: 2.2-2.8x fewer flushes than with OpenVDB's x-slice
+// words). Bits of consecutive visits that fall in the same word are merged in a register and flushed with ONE
+// fire-and-forget red.global.or.b64. compact_leaves_kernel<true>, which reads every touched leaf anyway, turns the
+// touched leaves into OpenVDB's x-slice layout in place (an 8x8 bit transpose per byte lane), so every consumer of the
+// grid keeps seeing the reference's layout.
+// The voxel position inside the current 64^3 brick is ONE integer, the "voxel code":
+//   bits 0-5 x&63 | bits 6-7 guard | bits 8-13 y&63 | bits 14-15 guard | bits 16-21 z&63 | bits 22-23 guard
+// A DDA step is one add of +-1 / +-2^8 / +-2^16. Guards rest at binary 10: leaving the brick upwards carries into them
+// (11), downwards borrows from them (01), never into the neighbouring field. "Did the mask word change" and "did the
+// ray leave the brick" are each one masked compare; word index and bit index are a few shifts of the code. The brick
+// hash is consulted only when a ray enters a new brick, and those lookups (like the ray refills) are batched at
+// warp-uniform points every kBatch steps so that their L2 round trip is paid once per batch and not once per lane event.
 // ====================================================================================================
-constexpr int kBatch = 4;
+#ifndef VDBM_KBATCH
+#define VDBM_KBATCH 8
+#endif
+constexpr int kBatch = VDBM_KBATCH;
+
+constexpr uint32_t kCodeGuardRest = 0x00808080u; // guards at rest (binary 10 per field)
+constexpr uint32_t kCodeGuardMask = 0x00C0C0C0u;
+constexpr uint32_t kCodeWordMask  = 0x00FFF8F8u; // x>>3, y>>3, z and the guards: any change = another mask word
+__host__ __device__ __forceinline__ uint32_t voxelCode(int x, int y, int z)
+{
+  return uint32_t(x & 63) | (uint32_t(y & 63) << 8) | (uint32_t(z & 63) << 16) | kCodeGuardRest;
+}
+// word offset inside the brick: leaf_in_brick * 8 + (z & 7) = (x>>3)<<9 | (y>>3)<<6 | z     (brick-local x, y, z)
+__host__ __device__ __forceinline__ uint32_t codeWord(uint32_t c) { return ((c & 0x38u) << 6) | ((c >> 5) & 0x1C0u) | ((c >> 16) & 0x3Fu); }
+// bit inside a z-slice word: (y&7)<<3 | (x&7)
+__host__ __device__ __forceinline__ uint32_t codeBit(uint32_t c) { return (c & 7u) | ((c >> 5) & 0x38u); }
 
 // MODE is a profiling hook: 0 = product path; 1 = no mask writes (pure traversal cost); 2 = plain 64-bit stores instead of
 // REDs (LSU path without the L2 atomic unit). Modes 1/2 give WRONG maps and only exist in builds made with
@@ -333,6 +357,15 @@ __device__ __forceinline__ void markWord(uint64_t* p, uint64_t v)
   else if (MODE == 2) asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// same under a predicate (one predicated RED, no branch)
+template <int MODE>
+__device__ __forceinline__ void markWordIf(uint64_t* p, uint64_t v, bool pred)
+{
+  if (MODE == 0)
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.global.or.b64 [%0], %1; }" ::"l"(p), "l"(v), "r"((unsigned)pred) : "memory");
+  else if (pred) markWord<MODE>(p, v);
+}
+
 // Near field: every ray starts at the sensor, so the mask words within a few leaves of it receive an update
 // from (almost) every ray: measured on B200 those same-address REDs serialise in a handful of L2 slices and cost
 // a third of the kernel. The 2x2x2 bricks around the sensor (a 128^3-voxel region with the sensor at least 32
@@ -342,58 +375,83 @@ __device__ __forceinline__ void markWord(uint64_t* p, uint64_t v)
 // (a brick is just a base pointer).
 constexpr int kNearCopies = 32;
 constexpr int kNearBricks = 8;
+constexpr uint64_t kNearKeyBits = (uint64_t(1) << 42) | (uint64_t(1) << 21) | uint64_t(1);
 
 // first brick (per axis) of the 2x2x2 near region: the brick below the sensor's if the sensor sits in the lower half
 __host__ __device__ __forceinline__ int nearBrick0(int o) { return (o >> 6) - (((o & 63) < 32) ? 1 : 0); }
 
-// in-place predicated adds (one instruction each; keeps the three DDA axes branch-free without select chains)
+// in-place predicated add (one instruction; keeps the three DDA axes branch-free without select chains)
 __device__ __forceinline__ void addIf(double& n, double d, bool p)
 {
   asm("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q add.rn.f64 %0, %0, %1; }" : "+d"(n) : "d"(d), "r"((unsigned)p));
 }
-__device__ __forceinline__ void addIf(int& n, int d, bool p)
+
+// Pipe budget (ncu, B200): this loop is bound by the 16-lane ALU pipe (LOP3 / SHF / SEL / ISETP: 2 cycles per warp
+// instruction; 70 % busy, 84 % on the busiest SM), not by issue slots, fp64 or memory. Hence the odd-looking choices
+// below, each of which moves work OFF that pipe:
+//  * "next[axis] += delta[axis]" is a DFMA with a multiplier that is exactly 1.0 or 0.0 (one SEL for the high word; the
+//    low word of both constants is zero): fma(d, 1, n) = rn(n + d) and fma(d, 0, n) = n exactly (d is finite), so the
+//    rounding sequence is the reference's; the compiler turns a predicated DADD into DADD + 2 FSEL instead.
+//  * the code is stepped with three predicated integer adds (FMA pipe) instead of two SELs and an add;
+//  * 1 << bit comes from a shared-memory table indexed with the masked code (one LOP3 + LDS instead of 5 ALU ops);
+//  * "lane is running" is one test of the code word itself: bit 31 = no ray, low guard bits = waiting for a brick lookup.
+constexpr uint32_t kCodeLowGuards = 0x00404040u; // set (whatever the direction) by a step that leaves the brick
+constexpr uint32_t kCodeIdle      = 0x80000000u; // lane has no ray
+constexpr uint32_t kBitTableSize  = 0x708u;      // indexed by code & 0x707 (x&7 | (y&7) << 8)
+
+__device__ __forceinline__ void addIfInt(uint32_t& n, int d, bool p)
 {
   asm("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q add.s32 %0, %0, %1; }" : "+r"(n) : "r"(d), "r"((unsigned)p));
+}
+// n + (p ? d : 0) with the reference's single rounding, see above
+__device__ __forceinline__ double addSel(double n, double d, bool p)
+{
+  return __fma_rn(d, __hiloint2double(p ? 0x3FF00000 : 0, 0), n);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, uint64_t* near_act, Counters* ctr)
 {
   __shared__ uint32_t s_near_slot[kNearBricks];
+  __shared__ uint64_t s_bit[kBitTableSize];
   const int lane = threadIdx.x & 31;
   const int ox = a.origin_idx[0], oy = a.origin_idx[1], oz = a.origin_idx[2];
   const int nbx = nearBrick0(ox), nby = nearBrick0(oy), nbz = nearBrick0(oz);
   // resolve the real slots of the 8 near bricks once per CTA (endpoint hits and the merge kernel use them)
   if (threadIdx.x < kNearBricks)
     s_near_slot[threadIdx.x] = brickFindOrInsertOrTrash(g, packLeafKey(nbx + (threadIdx.x >> 2), nby + ((threadIdx.x >> 1) & 1), nbz + (threadIdx.x & 1)), ctr);
+  for (uint32_t i = threadIdx.x; i < kBitTableSize; i += blockDim.x) s_bit[i] = uint64_t(1) << ((i & 7u) | ((i >> 5) & 0x38u));
   __syncthreads();
-  uint64_t* const my_near = near_act + size_t(blockIdx.x % kNearCopies) * (kNearBricks * kBrickLeaves * 8);
-  const int origin_ni     = (((ox >> 6) - nbx) << 2) | (((oy >> 6) - nby) << 1) | ((oz >> 6) - nbz);
-  const uint32_t origin_slot = s_near_slot[origin_ni];
+  uint64_t* const my_near  = near_act + size_t(blockIdx.x % kNearCopies) * (kBrickLeaves * 8 * kNearBricks);
+  const uint64_t near_key0 = packLeafKey(nbx, nby, nbz);
+  uint32_t bit_table; // shared-window address of s_bit, opaque to the compiler so that it stays in ONE register
+  asm("mov.b32 %0, %1;" : "=r"(bit_table) : "r"(uint32_t(__cvta_generic_to_shared(s_bit))));
 
-  bool busy = false, done = false, need = false;
+  bool done = false;
   double n0 = 0, n1 = 0, n2 = 0, d0 = 0, d1 = 0, d2 = 0;
-  int x = 0, y = 0, z = 0, sx = 0, sy = 0, sz = 0;
+  uint32_t c = kCodeIdle | kCodeGuardRest; // voxel code of the current voxel inside its brick (+ lane state, see above)
+  int ix = 0, iy = 0, iz = 0;    // code increments of one step along x / y / z
+  uint64_t bkey = 0;             // key of the current brick
   uint32_t remaining = 0; // voxels still to mark on the current ray (exact: 1 + |dx|+|dy|+|dz|, see prep_rays_kernel)
   uint32_t clipped   = 0;
   uint32_t slot      = kInvalid;  // real brick slot (value masks, validity)
   uint64_t* act_base = my_near;   // where this brick's active mask words go: a private near copy or the real brick
-  uint32_t cur_off   = kInvalid;
-  uint64_t acc       = 0;
+  uint64_t acc       = 0;         // bits collected for the current mask word
 
   for (;;)
   {
     // ================= batch point (warp-uniform): refills + brick lookups, every kBatch voxel steps =================
     {
       // ---- refill idle lanes (warp-aggregated fetch from the global ray cursor) ----
-      const unsigned want = __ballot_sync(kFull, !busy && !done);
+      const bool idle     = (c & kCodeIdle) != 0;
+      const unsigned want = __ballot_sync(kFull, idle && !done);
       if (want)
       {
         unsigned base    = 0;
         const int leader = __ffs(want) - 1;
         if (lane == leader) base = atomicAdd(&ctr->ray_cursor, (unsigned)__popc(want));
         base = __shfl_sync(kFull, base, leader);
-        if (!busy && !done)
+        if (idle && !done)
         {
           const uint64_t idx = uint64_t(base) + __popc(want & ((1u << lane) - 1u));
           // keys are sorted descending: the first zero key means only empty work items (NaN / zero-length rays without a
@@ -410,8 +468,10 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
                 // no DDA (VDBMapping.hpp:559); a non-clipped endpoint is still set on with value true (:533-536)
                 if (!(r.flags & kRayClipped))
                 {
-                  const size_t w     = size_t(origin_slot) * (kBrickLeaves * 8) + brickWordOffset(ox, oy, oz);
-                  const uint64_t bit = uint64_t(1) << (((oy & 7) << 3) | (oz & 7));
+                  const int origin_ni = (((ox >> 6) - nbx) << 2) | (((oy >> 6) - nby) << 1) | ((oz >> 6) - nbz);
+                  const uint32_t co   = voxelCode(ox, oy, oz);
+                  const size_t w      = size_t(s_near_slot[origin_ni]) * (kBrickLeaves * 8) + codeWord(co);
+                  const uint64_t bit  = uint64_t(1) << codeBit(co);
                   redOr64(g.act + w, bit);
                   redOr64(g.val + w, bit);
                 }
@@ -420,100 +480,94 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
               {
                 d0 = r.delta[0]; d1 = r.delta[1]; d2 = r.delta[2];
                 n0 = sg.next[0]; n1 = sg.next[1]; n2 = sg.next[2];
-                sx = rayStep(r.flags, 0); sy = rayStep(r.flags, 1); sz = rayStep(r.flags, 2);
-                x = ox + sx * int(sg.m[0]); y = oy + sy * int(sg.m[1]); z = oz + sz * int(sg.m[2]);
+                const int sx = rayStep(r.flags, 0), sy = rayStep(r.flags, 1), sz = rayStep(r.flags, 2);
+                const int x = ox + sx * int(sg.m[0]), y = oy + sy * int(sg.m[1]), z = oz + sz * int(sg.m[2]);
+                // low guards set = "look my brick up" (right below; a first segment starts in the near field); with all
+                // high guards clear the lookup recognises a fresh segment whose bkey is already right
+                c    = (voxelCode(x, y, z) & ~kCodeGuardMask) | kCodeLowGuards;
+                bkey = packLeafKey(x >> 6, y >> 6, z >> 6);
+                ix = sx; iy = sy * 256; iz = sz * 65536;
                 remaining = sg.count;
                 // only the segment that reaches the end voxel delivers the hit; a clipped ray never does
-                clipped   = (r.flags & kRayClipped) | (sg.last ? 0u : 1u);
-                cur_off = kInvalid; acc = 0;
-                if (sg.m[0] | sg.m[1] | sg.m[2])
-                {
-                  need = true; // a later segment starts somewhere along the ray: look its brick up below
-                }
-                else
-                {
-                  slot     = origin_slot;
-                  act_base = my_near + size_t(origin_ni) * (kBrickLeaves * 8);
-                  need     = false;
-                }
-                busy = true;
+                clipped = (r.flags & kRayClipped) | (sg.last ? 0u : 1u);
+                acc     = 0;
               }
             }
           }
         }
       }
       // ---- batched brick lookups for lanes that entered a new brick ----
-      if (__any_sync(kFull, busy && need))
+      const bool lookup = !(c & kCodeIdle) && (c & kCodeLowGuards) != 0;
+      if (__any_sync(kFull, lookup))
       {
-        if (busy && need)
+        if (lookup)
         {
-          const int bx = x >> 6, by = y >> 6, bz = z >> 6;
-          const unsigned rx = unsigned(bx - nbx), ry = unsigned(by - nby), rz = unsigned(bz - nbz);
-          if (rx < 2u && ry < 2u && rz < 2u)
+          // a step that left the brick shows in the guard bits of that axis: 11 = one brick up, 01 = one brick down, the
+          // other two axes stay at rest (10). All three at 01 can only be the refill's "fresh segment" mark.
+          const int gx = int((c >> 6) & 3u), gy = int((c >> 14) & 3u), gz = int((c >> 22) & 3u);
+          const bool fresh = (c & kCodeGuardMask) == kCodeLowGuards; // straight from the refill: bkey is already right
+          const long long dkey = fresh ? 0ll
+                                       : ((long long)((gx & 1) * (gx - 2)) << 42) + ((long long)((gy & 1) * (gy - 2)) << 21) +
+                                           (long long)((gz & 1) * (gz - 2));
+          bkey += (uint64_t)dkey;
+          c = (c & ~kCodeGuardMask) | kCodeGuardRest;
+          // near field? (per-axis brick offset 0 or 1 from the first near brick: no borrow can fake that)
+          const uint64_t diff = bkey - near_key0;
+          if ((diff & ~kNearKeyBits) == 0)
           {
-            const int ni = int((rx << 2) | (ry << 1) | rz);
+            const int ni = int(((diff >> 42) & 1) << 2) | int(((diff >> 21) & 1) << 1) | int(diff & 1);
             slot         = s_near_slot[ni];
             act_base     = my_near + size_t(ni) * (kBrickLeaves * 8);
           }
           else
           {
-            slot     = brickFindOrInsertOrTrash(g, packLeafKey(bx, by, bz), ctr);
+            slot     = brickFindOrInsertOrTrash(g, bkey, ctr);
             act_base = g.act + size_t(slot) * (kBrickLeaves * 8);
           }
-          need = false;
         }
       }
-      if (__all_sync(kFull, done && !busy)) break;
+      if (__all_sync(kFull, done && (c & kCodeIdle) != 0)) break;
     }
 
     // ================= kBatch voxel steps =================
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
     {
-      if (busy && !need)
+      if ((c & (kCodeIdle | kCodeLowGuards)) == 0)
       {
         // ---- mark current voxel (setActiveState(dda.voxel(), true), VDBMapping.hpp:563) ----
-        const uint32_t off = brickWordOffset(x, y, z);
-        const uint64_t bit = uint64_t(1) << (((y & 7) << 3) | (z & 7));
-        if (off != cur_off)
-        {
-          if (acc != 0) markWord<MODE>(act_base + cur_off, acc);
-          cur_off = off;
-          acc     = 0;
-        }
+        uint64_t bit;
+        asm("ld.shared.u64 %0, [%1];" : "=l"(bit) : "r"((c & 0x707u) * 8u + bit_table));
         acc |= bit;
-
         if (--remaining == 0)
         {
           // Last voxel of the ray (= the end voxel). OpenVDB's loop ends when the NEXT crossing time exceeds t1 = 1;
           // that happens exactly after 1 + |dx|+|dy|+|dz| marks (the crossing times of axis a are (m + 0.5)/|d_a| up to
           // fp64 rounding, m < |d_a| <=> t < 1 with a margin of 0.5/|d_a| >> accumulated rounding for |d_a| < 2^24).
           // Flush; the end voxel also receives the hit unless the ray was clipped (VDBMapping.hpp:533-536).
-          markWord<MODE>(act_base + cur_off, acc);
-          if (!clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + cur_off, bit);
-          busy = false;
+          const uint32_t w = codeWord(c);
+          markWord<MODE>(act_base + w, acc);
+          if (!clipped) markWord<MODE>(g.val + size_t(slot) * (kBrickLeaves * 8) + w, bit);
+          c |= kCodeIdle;
         }
         else
         {
           // ---- DDA::step(): axis = MinIndex(next); next[axis] += delta[axis]; voxel[axis] += step[axis] ----
           // MinIndex table {2,1,9,1,2,9,0,0} on key ((n0<n1)<<2)+((n0<n2)<<1)+(n1<n2):
           //   (n0<n1 && n0<n2) -> x ; else (n1<n2) -> y ; else z      (keys 2 and 5 are unreachable)
-          // Branch-free: three predicated in-place adds per lane, whatever axis it takes.
           const bool ax = (n0 < n1) && (n0 < n2);
           const bool ay = !ax && (n1 < n2);
           const bool az = !ax && !ay;
-          addIf(n0, d0, ax); addIf(n1, d1, ay); addIf(n2, d2, az);
-          addIf(x, sx, ax);  addIf(y, sy, ay);  addIf(z, sz, az);
-          // did the step leave the brick? (the stepped coordinate crossed a multiple of 64)
-          const int c  = ax ? x : (ay ? y : z);
-          const int st = ax ? sx : (ay ? sy : sz);
-          if (((c + (st < 0 ? 1 : 0)) & 63) == 0)
+          n0 = addSel(n0, d0, ax); n1 = addSel(n1, d1, ay); n2 = addSel(n2, d2, az);
+          uint32_t c2 = c;
+          addIfInt(c2, ix, ax); addIfInt(c2, iy, ay); addIfInt(c2, iz, az);
+          if ((c2 ^ c) & kCodeWordMask)
           {
-            markWord<MODE>(act_base + cur_off, acc);
-            acc     = 0;
-            cur_off = kInvalid;
-            need    = true;
+            // the step left the mask word (or the brick, which shows in the guards): flush what was collected
+            markWord<MODE>(act_base + codeWord(c), acc);
+            acc = 0;
           }
+          c = c2; // a step out of the brick has set a low guard bit: the lane now waits for the next batch point
         }
       }
     }
@@ -544,7 +598,47 @@ __global__ void __launch_bounds__(256) merge_near_kernel(UpdateGrid g, uint64_t*
 // ====================================================================================================
 // K1b: rebuild the compact list of touched leaves from the occupied bricks. One block per brick, one thread per
 // leaf (512); a leaf is touched iff its 64-byte active mask is non-zero.
+// COOK (after the DDA kernel, which marks z-slice words): the thread also turns its leaf's two masks into OpenVDB's
+// x-slice layout, in place: x-slice word[x] bit (y<<3|z)  <->  z-slice word[z] bit (y<<3|x), i.e. for every byte lane y
+// an 8x8 bit transpose between word index and bit-in-byte. The transform is an involution: uncook_leaves_kernel applies
+// it again to the listed leaves before another scan is marked into a grid that already holds (cooked) data.
 // ====================================================================================================
+__device__ __forceinline__ void transposeLeafWords(uint64_t (&w)[8])
+{
+  uint32_t lo[8], hi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { lo[i] = uint32_t(w[i]); hi[i] = uint32_t(w[i] >> 32); }
+#pragma unroll
+  for (int j = 4; j >= 1; j >>= 1)
+  {
+    const uint32_t m = (j == 4) ? 0x0F0F0F0Fu : (j == 2 ? 0x33333333u : 0x55555555u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (!(i & j))
+      {
+        // swap the bits of word i whose in-byte index has bit j set with the bits of word i|j that have it clear
+        uint32_t t = ((lo[i] >> j) ^ lo[i | j]) & m; lo[i | j] ^= t; lo[i] ^= t << j;
+        t          = ((hi[i] >> j) ^ hi[i | j]) & m; hi[i | j] ^= t; hi[i] ^= t << j;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = (uint64_t(hi[i]) << 32) | lo[i];
+}
+
+__device__ __forceinline__ void loadLeafWords(const uint64_t* p, uint64_t (&w)[8])
+{
+  const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const ulonglong2 v = q[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+}
+__device__ __forceinline__ void storeLeafWords(uint64_t* p, const uint64_t (&w)[8])
+{
+  ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = make_ulonglong2(w[2 * k], w[2 * k + 1]);
+}
+
+template <bool COOK>
 __global__ void __launch_bounds__(512) compact_leaves_kernel(UpdateGrid g)
 {
   const int lane          = threadIdx.x & 31;
@@ -553,10 +647,10 @@ __global__ void __launch_bounds__(512) compact_leaves_kernel(UpdateGrid g)
   {
     const uint32_t slot = g.btouched[b];
     const uint32_t e    = slot * kBrickLeaves + threadIdx.x;
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(g.act + size_t(e) * 8);
-    const ulonglong2 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
-    const bool nz       = (q0.x | q0.y | q1.x | q1.y | q2.x | q2.y | q3.x | q3.y) != 0;
-    const unsigned m    = __ballot_sync(kFull, nz);
+    uint64_t a[8];
+    loadLeafWords(g.act + size_t(e) * 8, a);
+    const bool nz    = (a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) != 0;
+    const unsigned m = __ballot_sync(kFull, nz);
     if (m)
     {
       uint32_t base = 0;
@@ -564,6 +658,36 @@ __global__ void __launch_bounds__(512) compact_leaves_kernel(UpdateGrid g)
       base = __shfl_sync(kFull, base, 0);
       if (nz) g.entries[base + __popc(m & ((1u << lane) - 1u))] = e;
     }
+    if (COOK && nz)
+    {
+      transposeLeafWords(a);
+      storeLeafWords(g.act + size_t(e) * 8, a);
+      uint64_t v[8];
+      loadLeafWords(g.val + size_t(e) * 8, v);
+      if ((v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) != 0)
+      {
+        transposeLeafWords(v);
+        storeLeafWords(g.val + size_t(e) * 8, v);
+      }
+    }
+  }
+}
+
+// the listed (cooked, x-slice) leaves back to z-slice words, before the DDA kernel marks into a non-empty grid
+__global__ void __launch_bounds__(256) uncook_leaves_kernel(UpdateGrid g, uint32_t n_entries)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  const uint32_t e = g.entries[i];
+  uint64_t w[8];
+  loadLeafWords(g.act + size_t(e) * 8, w);
+  transposeLeafWords(w);
+  storeLeafWords(g.act + size_t(e) * 8, w);
+  loadLeafWords(g.val + size_t(e) * 8, w);
+  if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) != 0)
+  {
+    transposeLeafWords(w);
+    storeLeafWords(g.val + size_t(e) * 8, w);
   }
 }
 
@@ -1846,11 +1970,17 @@ void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Co
               nearBrick0(a.origin_idx[1]), nearBrick0(a.origin_idx[2]), ctr);
 }
 
-void launchCompactLeaves(UpdateGrid g, cudaStream_t s)
+void launchCompactLeaves(UpdateGrid g, cudaStream_t s, bool cook)
 {
   cudaMemsetAsync(g.counters + 1, 0, 4, s);
   const unsigned grid = std::min<unsigned>(g.cap_mask + 1u, unsigned(smCount()) * 4u);
-  VDBM_LAUNCH(compact_leaves_kernel, grid, 512, s, g);
+  if (cook) VDBM_LAUNCH(compact_leaves_kernel<true>, grid, 512, s, g);
+  else VDBM_LAUNCH(compact_leaves_kernel<false>, grid, 512, s, g);
+}
+
+void launchUncookLeaves(UpdateGrid g, uint32_t n_entries, cudaStream_t s)
+{
+  if (n_entries) VDBM_LAUNCH(uncook_leaves_kernel, blocksFor(n_entries, 256), 256, s, g, n_entries);
 }
 
 static int applyUpdateBlocksPerSM()
