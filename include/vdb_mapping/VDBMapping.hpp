@@ -241,15 +241,14 @@ public:
     if (!m_device_map || !cloud) return false;
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     ensureScratchSource();
+    ScratchClear clear_on_exit{m_device_map}; // whatever happens below, nothing stays behind for the next integrateUpdate
     const double o[3] = {origin.x(), origin.y(), origin.z()};
-    if (report(vdbm_raycast(m_device_map, kScratchSource, cloud->points.data(), cloud->points.size(), sizeof(PointT), o, raycast_range)) != VDBM_OK)
-      return false;
+    const int rc = report(vdbm_raycast(m_device_map, kScratchSource, cloud->points.data(), cloud->points.size(), sizeof(PointT), o, raycast_range));
+    if (rc != VDBM_OK && rc != VDBM_ERR_COORD_RANGE) return false; // out-of-range points are dropped and reported, the rest counts
     vdbm_leafset* ls = nullptr;
     if (report(vdbm_update_export(m_device_map, kScratchSource, &ls)) != VDBM_OK) return false;
     mergeIntoAccessor(ls, update_grid_acc);
     vdbm_leafset_free(ls);
-    // empty the scratch grid without touching the map: re-adding a source clears its update grid (vdbm_source_add)
-    vdbm_source_add(m_device_map, kScratchSource, 1.0);
     return true;
   }
 
@@ -281,6 +280,7 @@ public:
       active.insert(active.end(), a, a + 8);
       value.insert(value.end(), v, v + 8);
     });
+    ScratchClear clear_on_exit{m_device_map};
     if (report(vdbm_update_import(m_device_map, kScratchSource, origins.size() / 3, origins.data(), active.data(), value.data())) != VDBM_OK)
       return change;
     vdbm_leafset* ls = nullptr;
@@ -508,18 +508,31 @@ public:
   /*! R:1352-1375. The source is registered BEFORE its worker thread starts (the reference starts the thread first). */
   void addInputSource(std::string source_id, double max_range, double max_rate)
   {
-    auto s       = std::make_shared<InputSource>();
-    s->source_id = source_id;
-    s->max_range = (max_range == 0) ? m_max_range : max_range;
-    s->max_input_period = (max_rate <= 0) ? std::chrono::milliseconds(0) : std::chrono::milliseconds((int)(1000.0 / max_rate));
+    const double range = (max_range == 0) ? m_max_range : max_range;
+    const auto period  = (max_rate <= 0) ? std::chrono::milliseconds(0) : std::chrono::milliseconds((int)(1000.0 / max_rate));
     if (m_device_map)
     {
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
-      report(vdbm_source_add(m_device_map, source_id.c_str(), max_range));
+      report(vdbm_source_add(m_device_map, source_id.c_str(), max_range)); // a re-added source starts with an empty update grid
     }
-    auto old = m_worker_threads.find(source_id);
+    auto existing = m_input_sources.find(source_id);
+    if (existing != m_input_sources.end())
+    {
+      // Re-adding a source (the reference overwrites the map entry, R:1374): its worker thread is blocked on THIS object's
+      // condition variable, so the object stays and only its parameters change; pending input is dropped like the
+      // reference's fresh InputSource would.
+      std::unique_lock lock(existing->second->input_data_mutex);
+      existing->second->max_range        = range;
+      existing->second->max_input_period = period;
+      existing->second->input_data.reset();
+      return;
+    }
+    auto s              = std::make_shared<InputSource>();
+    s->source_id        = source_id;
+    s->max_range        = range;
+    s->max_input_period = period;
     m_input_sources[source_id] = s;
-    if (old == m_worker_threads.end()) m_worker_threads[source_id] = std::thread(&VDBMapping::accumulationThread, this, source_id);
+    m_worker_threads[source_id] = std::thread(&VDBMapping::accumulationThread, this, source_id);
   }
 
   /*! R:1456-1469 */
@@ -542,6 +555,12 @@ public:
 
 protected:
   static constexpr const char* kScratchSource = "\x01vdbm_scratch";
+  /*! empties the scratch source's update grid on scope exit without touching the map (re-adding a source clears its grid) */
+  struct ScratchClear
+  {
+    vdbm_map* m;
+    ~ScratchClear() { if (m) vdbm_source_add(m, kScratchSource, 1.0); }
+  };
 
   int report(int rc) const
   {

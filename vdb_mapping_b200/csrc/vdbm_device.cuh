@@ -193,7 +193,7 @@ struct RaycastArgs
   uint32_t n_segs;   // segments to traverse (n + extra segments in use); set by the host before the DDA kernel
   uint32_t* long_rays; // [n] indices of rays that were split (count in Counters::n_long)
   uint32_t* seg_base;  // [n] first extra segment slot of a split ray
-  uint32_t* sort_keys; // [seg_cap] min(segment marks, 2^20-1); 0 = nothing to do
+  uint32_t* sort_keys; // [seg_cap] min(segment marks, 2047); 0 = nothing to do
   uint32_t* sort_idx;  // [seg_cap] identity
   const uint32_t* order; // [n_segs] segment indices, longest first (LPT schedule for the DDA kernel)
   const uint32_t* sorted_keys; // [n_segs] the keys in that order (descending)
@@ -293,7 +293,7 @@ void launchWallDDA(const int32_t* d_walls, uint32_t n_walls, int32_t neg_index, 
 void launchGridActivate(UpdateGrid g, uint32_t n_entries, MapTable mt, Counters* ctr, cudaStream_t s);
 void launchRestoreState(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, Counters* ctr, cudaStream_t s);
 uint32_t launchCount(); // kernels of this library launched by this process
-// CUB radix sort (descending) of (visit count, ray index) on key bits [4, 20); returns temp bytes when d_temp == nullptr
+// CUB radix sort (descending) of (visit count, ray index) on key bits [3, 11) (one radix pass); returns temp bytes when d_temp == nullptr
 size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,
                         uint32_t* idx_out, uint32_t n, cudaStream_t s);
 // CUB radix sort of (key, idx) pairs; returns bytes of temp storage needed when d_temp == nullptr

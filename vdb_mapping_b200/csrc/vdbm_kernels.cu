@@ -106,6 +106,10 @@ __device__ __forceinline__ uint32_t brickWordOffset(int x, int y, int z)
 // K0: per-point set-up. One thread per point; fully convergent, so the expensive fp64 div/sqrt/fmod run at
 // full SIMD efficiency here instead of inside the divergent DDA kernel.
 // ====================================================================================================
+// sort keys of the work items (rays / segments): min(marks, 2047), sorted on bits [3, 11) only
+constexpr int kSortLoBit = 3, kSortHiBit = 11;
+constexpr uint32_t kSortMinKey = 1u << kSortLoBit, kSortMaxKey = (1u << kSortHiBit) - 1u;
+
 __device__ __forceinline__ int32_t worldToIndex1(double c, double res, double half_res, double inv_res)
 {
   // VDBMapping.hpp:612-631: +res/2 iff fmod(c,res) != 0; Transform::worldToIndex = multiply by 1/res; Coord::floor
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
     sg.ray   = uint32_t(i);
     sg.last  = 1;
     // zero-length rays with a hit still need one visit by the DDA kernel (count 0, flagged in the ray record)
-    uint32_t key = uint32_t(visits > 0xFFFFFull ? 0xFFFFFull : visits);
+    uint32_t key = uint32_t(visits > kSortMaxKey ? kSortMaxKey : visits);
     if ((r.flags & kRayValid) && (r.flags & kRayZeroLen) && !(r.flags & kRayClipped)) key = 1;
     if (a.seg_len != 0 && r.visits > a.seg_len + a.seg_len / 2)
     {
@@ -219,9 +223,10 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
       }
     }
     a.segs[i]      = sg;
-    // The sort only looks at key bits [4, 20): a work item with 1..15 marks would tie with the empty items (key 0) and
-    // could end up behind more zero keys than there are lanes to retire on them. Lift every real item above the zeros.
-    a.sort_keys[i] = (key != 0u && key < 16u) ? 16u : key;
+    // The sort only looks at key bits [3, 11) (ONE radix pass: longest-first scheduling needs no finer order than 8 marks,
+    // and everything above 2047 marks simply goes first): a work item with 1..7 marks would tie with the empty items
+    // (key 0) and could end up behind more zero keys than there are lanes to retire on them. Lift every real item above the zeros.
+    a.sort_keys[i] = (key != 0u && key < kSortMinKey) ? kSortMinKey : key;
     a.sort_idx[i]  = uint32_t(i);
   }
   // warp-aggregated statistics
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(128) long_ray_segments_kernel(RaycastArgs a, u
     sg->ray   = ray;
     sg->last  = (j + 1 == P) ? 1u : 0u;
     const uint32_t slot = (j == 0) ? ray : (xb + j - 1);
-    a.sort_keys[slot]   = cnt > 0xFFFFFu ? 0xFFFFFu : ((cnt != 0u && cnt < 16u) ? 16u : cnt); // see prep_rays_kernel
+    a.sort_keys[slot]   = cnt > kSortMaxKey ? kSortMaxKey : ((cnt != 0u && cnt < kSortMinKey) ? kSortMinKey : cnt); // see prep_rays_kernel
     a.sort_idx[slot]    = slot;
     s_prev              = s_next;
   }
@@ -429,6 +434,7 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
 
   bool done = false;
   double n0 = 0, n1 = 0, n2 = 0, d0 = 0, d1 = 0, d2 = 0;
+  uint64_t bit = 0;              // mask bit of the current voxel, fetched one step ahead (shared-memory latency)
   uint32_t c = kCodeIdle | kCodeGuardRest; // voxel code of the current voxel inside its brick (+ lane state, see above)
   int ix = 0, iy = 0, iz = 0;    // code increments of one step along x / y / z
   uint64_t bkey = 0;             // key of the current brick
@@ -527,6 +533,7 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
         }
       }
       if (__all_sync(kFull, done && (c & kCodeIdle) != 0)) break;
+      asm("ld.shared.u64 %0, [%1];" : "=l"(bit) : "r"((c & 0x707u) * 8u + bit_table));
     }
 
     // ================= kBatch voxel steps =================
@@ -536,8 +543,6 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
       if ((c & (kCodeIdle | kCodeLowGuards)) == 0)
       {
         // ---- mark current voxel (setActiveState(dda.voxel(), true), VDBMapping.hpp:563) ----
-        uint64_t bit;
-        asm("ld.shared.u64 %0, [%1];" : "=l"(bit) : "r"((c & 0x707u) * 8u + bit_table));
         acc |= bit;
         if (--remaining == 0)
         {
@@ -568,31 +573,36 @@ __global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, Upda
             acc = 0;
           }
           c = c2; // a step out of the brick has set a low guard bit: the lane now waits for the next batch point
+          asm("ld.shared.u64 %0, [%1];" : "=l"(bit) : "r"((c & 0x707u) * 8u + bit_table));
         }
       }
     }
   }
 }
 
-// OR the privatised near-brick copies into the real bricks and leave the copies zeroed for the next scan
+// OR the privatised near-brick copies into the real bricks and leave the copies zeroed for the next scan. Eight
+// threads per mask word, four copies each (word index fastest: coalesced); most words are zero, the few that are not are
+// OR-ed into the real brick with a RED.
+constexpr int kMergeSplit = 8;
 __global__ void __launch_bounds__(256) merge_near_kernel(UpdateGrid g, uint64_t* near_act, int nbx, int nby, int nbz, Counters* ctr)
 {
   __shared__ uint32_t s_slot[kNearBricks];
   if (threadIdx.x < kNearBricks)
     s_slot[threadIdx.x] = brickFindOrInsert(g, packLeafKey(nbx + (threadIdx.x >> 2), nby + ((threadIdx.x >> 1) & 1), nbz + (threadIdx.x & 1)), ctr);
   __syncthreads();
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // word index in [0, 8 * 4096)
-  if (i >= kNearBricks * kBrickLeaves * 8) return;
+  constexpr uint32_t kWords = kNearBricks * kBrickLeaves * 8;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = t % kWords, part = t / kWords; // word index in [0, 8 * 4096), copy group
+  if (part >= kMergeSplit) return;
+  uint64_t w[kNearCopies / kMergeSplit];
+#pragma unroll
+  for (int k = 0; k < kNearCopies / kMergeSplit; ++k) w[k] = near_act[size_t(part * (kNearCopies / kMergeSplit) + k) * kWords + i];
   uint64_t v = 0;
-#pragma unroll 8
-  for (int c = 0; c < kNearCopies; ++c)
-  {
-    uint64_t* p = near_act + size_t(c) * (kNearBricks * kBrickLeaves * 8) + i;
-    const uint64_t w = *p;
-    if (w) { v |= w; *p = 0; }
-  }
+#pragma unroll
+  for (int k = 0; k < kNearCopies / kMergeSplit; ++k)
+    if (w[k]) { v |= w[k]; near_act[size_t(part * (kNearCopies / kMergeSplit) + k) * kWords + i] = 0; }
   const uint32_t slot = s_slot[i / (kBrickLeaves * 8)];
-  if (v && slot != kInvalid) g.act[size_t(slot) * (kBrickLeaves * 8) + (i % (kBrickLeaves * 8))] |= v;
+  if (v && slot != kInvalid) redOr64(g.act + size_t(slot) * (kBrickLeaves * 8) + (i % (kBrickLeaves * 8)), v);
 }
 
 // ====================================================================================================
@@ -1591,33 +1601,43 @@ __global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t
   }
 }
 
+// bit 31 of the published count: this sender could not fit all its records into the receiver's region. The records that
+// did not fit are gone (their masks were consumed), so EVERY receiver of this epoch must fail loudly, not only the sender.
+constexpr uint32_t kExchangeOverflowBit = 0x80000000u;
+
 __global__ void publish_counts_kernel(ExchangePeers px, uint32_t parity, uint32_t epoch, const uint32_t* cursors)
 {
   const int r = threadIdx.x;
   if (r >= px.n_ranks) return;
-  const unsigned long long word = ((unsigned long long)epoch << 32) | min(cursors[r], px.cap);
+  const uint32_t sent = cursors[r];
+  const unsigned long long word = ((unsigned long long)epoch << 32) | min(sent, px.cap) | (sent > px.cap ? kExchangeOverflowBit : 0u);
   __threadfence_system(); // the records written by push_update_kernel (previous launch on this stream) come first
   unsigned long long* p = px.ctrl[r] + size_t(parity) * px.n_ranks + px.rank;
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(word) : "memory");
 }
 
-// single warp: wait (bounded) until every sender has published this epoch, then leave the counts in device memory
+// single warp: wait (bounded by timeout_ns of the global timer) until every sender has published this epoch, then leave the
+// counts in device memory. A sender that ran out of inbox space raises kFlagExchangeOverflow HERE as well.
 __global__ void wait_peers_kernel(const unsigned long long* ctrl, int32_t n_ranks, uint32_t parity, uint32_t epoch, uint32_t* counts_out,
-                                  Counters* ctr)
+                                  Counters* ctr, unsigned long long timeout_ns)
 {
   const int s = threadIdx.x;
   if (s >= n_ranks) return;
   const unsigned long long* p = ctrl + size_t(parity) * n_ranks + s;
-  const long long t0 = clock64();
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   unsigned long long w = 0;
   for (;;)
   {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     if (uint32_t(w >> 32) == epoch) break;
-    if (clock64() - t0 > 4000000000ll) { atomicOr(&ctr->flags, kFlagExchangeTimeout); w = 0; break; } // ~2 s
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) { atomicOr(&ctr->flags, kFlagExchangeTimeout); w = 0; break; }
     __nanosleep(200);
   }
-  counts_out[s] = uint32_t(w);
+  if (uint32_t(w) & kExchangeOverflowBit) atomicOr(&ctr->flags, kFlagExchangeOverflow);
+  counts_out[s] = uint32_t(w) & ~kExchangeOverflowBit;
 }
 
 __global__ void __launch_bounds__(256) pull_update_kernel(UpdateGrid g, const uint64_t* inbox, uint32_t cap, int32_t n_ranks, uint32_t parity,
@@ -1966,7 +1986,7 @@ void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Co
 #endif
   if (test_before_set) VDBM_LAUNCH(raycast_dda_kernel<4>, grid, 256, s, a, g, near_act, ctr);
   else VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, near_act, ctr);
-  VDBM_LAUNCH(merge_near_kernel, (kNearBricks * kBrickLeaves * 8) / 256, 256, s, g, near_act, nearBrick0(a.origin_idx[0]),
+  VDBM_LAUNCH(merge_near_kernel, (kNearBricks * kBrickLeaves * 8 * kMergeSplit) / 256, 256, s, g, near_act, nearBrick0(a.origin_idx[0]),
               nearBrick0(a.origin_idx[1]), nearBrick0(a.origin_idx[2]), ctr);
 }
 
@@ -2129,7 +2149,13 @@ void launchPushUpdate(UpdateGrid g, uint32_t n_entries, ExchangePeers px, uint32
 void launchWaitPeers(const unsigned long long* ctrl, int32_t n_ranks, uint32_t parity, uint32_t epoch, uint32_t* counts_out, Counters* ctr,
                      cudaStream_t s)
 {
-  VDBM_LAUNCH(wait_peers_kernel, 1, 32, s, ctrl, n_ranks, parity, epoch, counts_out, ctr);
+  // a peer may legitimately be late by a reallocation or a table growth (hundreds of ms): default 20 s, VDBM_EXCHANGE_TIMEOUT_MS overrides
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("VDBM_EXCHANGE_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 20000.0;
+    return (unsigned long long)((ms > 0 ? ms : 20000.0) * 1e6);
+  }();
+  VDBM_LAUNCH(wait_peers_kernel, 1, 32, s, ctrl, n_ranks, parity, epoch, counts_out, ctr, timeout_ns);
 }
 void launchPullUpdate(UpdateGrid g, const uint64_t* inbox, const unsigned long long* ctrl, uint32_t cap, int32_t n_ranks, uint32_t parity,
                       uint32_t epoch, uint32_t* counts_out, Counters* ctr, cudaStream_t s)
@@ -2143,7 +2169,7 @@ size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in
 {
   size_t bytes = temp_bytes;
   if (d_temp == nullptr) bytes = 0;
-  cub::DeviceRadixSort::SortPairsDescending(d_temp, bytes, keys_in, keys_out, idx_in, idx_out, int(n), 4, 20, s);
+  cub::DeviceRadixSort::SortPairsDescending(d_temp, bytes, keys_in, keys_out, idx_in, idx_out, int(n), kSortLoBit, kSortHiBit, s);
   return bytes;
 }
 
