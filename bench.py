@@ -34,7 +34,9 @@ sys.path.insert(0, ROOT)
 
 from vdb_mapping_b200 import scans  # noqa: E402
 
-REF_SAMPLE_STRIDE = 8  # reference arm: one contiguous 1/8 azimuth sector of the scan per step
+REF_SAMPLE_STRIDE = 1  # reference arm: FULL scans of the same sequence per step (same config as our arm)
+REF_MAX_STEPS = 30     # ... and a cap on the number of timed steps instead (2.7 s per cfg2 scan on one core); printed when it bites
+STRONG_WARMUP, STRONG_STEPS = 2, 6  # the strong_cfg4 block of every line: one 1M-point scan per step split over all ranks
 
 
 def measured_peaks():
@@ -162,6 +164,10 @@ def run_reference(args, rank, world):
     m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
     m.addInputSource("s", c.max_range)
     stride = REF_SAMPLE_STRIDE
+    steps_asked = args.steps
+    if args.workload != "cfg3":
+        args.steps = min(args.steps, REF_MAX_STEPS)
+        args.warmup = min(args.warmup, 3)
     clouds = []
     for k in range(args.warmup + args.steps):
         pts, origin = scans.make_scan(cfg, k)
@@ -204,7 +210,10 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     s1 = m.stats()
     value = rays / dt
-    sample = f"a contiguous 1/{stride} azimuth sector of each scan ({clouds[0][0].shape[0]} of {c.n_points} rays per step, sector rotates with the step), full pipeline"
+    sample = (f"full scans ({c.n_points} rays per step), full pipeline" if stride == 1 else
+              f"a contiguous 1/{stride} azimuth sector of each scan ({clouds[0][0].shape[0]} of {c.n_points} rays per step, sector rotates with the step), full pipeline")
+    if args.steps != steps_asked:
+        sample += f"; timed steps capped at {args.steps} of the {steps_asked} asked for (a scan takes seconds on one core)"
     line = {
         "impl": "reference", "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -312,6 +321,134 @@ def cpu_baseline_leg(cfg: int, n_scans: int):
     return out
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+def _gather(world, dist, obj):
+    if world == 1:
+        return [obj]
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def reference_checksum(c, local_rank, stream, scans_per_step):
+    """Rank 0, outside every timed region: the same scans integrated on ONE GPU (one accumulate per cloud of a step, then
+    one integrate) -> (checksum, leaves). scans_per_step: list over steps of lists of (points, origin)."""
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    m = OccupancyVDBMapping(c.resolution, device=local_rank, stream=stream.cuda_stream)
+    m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+    m.addInputSource("s", c.max_range)
+    for clouds in scans_per_step:
+        for pts, origin in clouds:
+            m.accumulateUpdate(pts, origin, "s")
+        m.integrateUpdate(keep_change=False)
+    out = m.mapChecksum()
+    m.close()
+    return out
+
+
+def strong_cfg4_block(args, rank, world, local_rank, stream, dist):
+    """BASELINE configs[3] / north_star's multi-GPU target, on every line: ONE 1,048,576-point scan (0.02 m, 100 m, bounded
+    hall) per step, split over all ranks of the run (strong scaling; at N = 1 this is the single-GPU time the efficiency is
+    measured against). Rays are split by azimuth sector around the sensor, the map is owned by the same sectors (ShardPlan
+    mode 1, bounds planned on rank 0 from a dry run of scan 0: equal voxel visits + weighted owned leaves), so only the leaves
+    near the sensor and along sector borders cross NVLink. Outside the timed region the order-independent checksum of all
+    shards is compared with rank 0 integrating the same full scans on one GPU."""
+    import torch
+    from vdb_mapping_b200 import dist as vdist
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    cfg, c = 4, scans.CONFIGS[4]
+    dev = torch.device("cuda", local_rank)
+    n_steps = STRONG_WARMUP + STRONG_STEPS
+    full = [scans.make_scan(cfg, k) for k in range(n_steps)]
+    plan = None
+    with torch.cuda.stream(stream):
+        if world > 1:
+            holder = [None]
+            if rank == 0:
+                # dry run: which leaves does scan 0 touch? (their azimuth histogram weights the sector bounds)
+                tmp = OccupancyVDBMapping(c.resolution, device=local_rank, stream=stream.cuda_stream)
+                tmp.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+                tmp.addInputSource("s", c.max_range)
+                tmp.accumulateUpdate(full[0][0], full[0][1], "s")
+                leaf_origins = np.array(tmp.exportUpdateGrid("s").origins)
+                tmp.close()
+                holder[0] = vdist.plan_sectors(full[0][0], full[0][1], c.resolution, c.max_range, world, leaf_origins=leaf_origins)
+                del leaf_origins
+            dist.broadcast_object_list(holder, src=0)
+            plan = holder[0]
+            mine = [(np.ascontiguousarray(p[vdist.sector_rays(p, o, plan, rank)]), o) for p, o in full]
+        else:
+            mine = full
+        resident = [torch.from_numpy(p).to(dev) for p, _ in mine]
+        m = OccupancyVDBMapping(c.resolution, device=local_rank, stream=stream.cuda_stream)
+        m.setConfig(c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+        m.addInputSource("s", c.max_range)
+        eng = vdist.CudaEngine(m, "s")
+        if world > 1:
+            m.setShardPlan(plan)
+            vdist.connect_peers(m, dist, capacity_records_per_sender=1 << 21)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ph = {"raycast": [], "push": [], "wait": [], "import": [], "update": []}
+        touched, owned, st0 = [], [], None
+        for k in range(n_steps):
+            if k == STRONG_WARMUP:
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                st0 = m.stats()
+                ev0.record(stream)
+            eng.accumulate_raw(resident[k].data_ptr(), mine[k][0].shape[0], mine[k][1], on_device=True)
+            sa = m.stats()
+            if world > 1:
+                vdist.push_pull_and_integrate(eng)
+            else:
+                eng.integrate()
+            if k >= STRONG_WARMUP:
+                sb = m.stats()
+                ph["raycast"].append(sa["last_accumulate_ms"]); ph["update"].append(sb["last_integrate_ms"])
+                touched.append(sa["last_touched_leaves"]); owned.append(sb["last_touched_leaves"])
+                if world > 1:
+                    a, b, cc = m.exchangeTimings()
+                    ph["push"].append(a); ph["wait"].append(b); ph["import"].append(cc)
+        ev1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        st1 = m.stats()
+        ms = ev0.elapsed_time(ev1)
+        chk = m.mapChecksum()
+        m.close()
+        del resident
+    mean = lambda x: float(sum(x) / max(1, len(x)))
+    mine_stats = {"ms": ms, "rays": st1["rays"] - st0["rays"], "visits": st1["visits"] - st0["visits"],
+                  "updates": st1["voxel_updates"] - st0["voxel_updates"], "chk": chk,
+                  "phases": {k: mean(v) for k, v in ph.items()}, "touched": mean(touched), "owned": mean(owned)}
+    allr = _gather(world, dist, mine_stats)
+    identical = None
+    if world > 1 and rank == 0:
+        ref = reference_checksum(c, local_rank, stream, [[f] for f in full])
+        tot = (sum(r["chk"][0] for r in allr) & ((1 << 64) - 1), sum(r["chk"][1] for r in allr))
+        identical = bool(tot == ref)
+    if rank != 0:
+        return None
+    ms_max = max(r["ms"] for r in allr)
+    rays = sum(r["rays"] for r in allr)
+    phases = {k: {"max": max(r["phases"][k] for r in allr), "mean": mean([r["phases"][k] for r in allr])} for k in ph}
+    return {
+        "workload": c.name, "scaling": "strong", "points_per_step": int(rays / STRONG_STEPS), "steps": STRONG_STEPS, "warmup": STRONG_WARMUP,
+        "ms_per_step": ms_max / STRONG_STEPS, "rays_per_sec": rays / (ms_max * 1e-3),
+        "voxel_updates_per_sec": sum(r["updates"] for r in allr) / (ms_max * 1e-3),
+        "visits_per_sec": sum(r["visits"] for r in allr) / (ms_max * 1e-3),
+        "per_rank_ms": phases,
+        "leaves_touched_per_rank": [r["touched"] for r in allr], "leaves_owned_per_rank": [r["owned"] for r in allr],
+        "map_checksum": "%016x" % (sum(r["chk"][0] for r in allr) & ((1 << 64) - 1)), "map_leaves": sum(r["chk"][1] for r in allr),
+        "sharded_map_identical": identical,
+        "ownership": (None if plan is None else {"kind": "azimuth sectors (ShardPlan mode 1)", "center_leaf_xy": [plan.cx, plan.cy], "bounds": plan.bounds}),
+        "note": "device time (CUDA events) of the timed steps, max over ranks; efficiency at N GPUs = ms_per_step(N=1) / (N * ms_per_step(N)) "
+                "from the driver's own N = 1 line; sharded_map_identical: sum of the shard checksums == the same scans on one GPU (rank 0)",
+    }
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -368,7 +505,7 @@ def run_ours(args, rank, world, local_rank):
             if p2p:
                 vdist.connect_peers(m, dist, capacity_records_per_sender=(1 << 22) if cfg == 4 else (1 << 19))
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            acc_ms, prep_ms, int_ms, leaves = [], [], [], []
+            acc_ms, prep_ms, int_ms, leaves, upd_leaves = [], [], [], [], []
             d2h_extra = [0, 0, 0]  # cfg5: bytes read back (reduced updates + sections), sections extracted, reduced-update bytes
             sent = recv = 0
             st0 = None
@@ -432,7 +569,8 @@ def run_ours(args, rank, world, local_rank):
                     a, b = vdist.exchange_and_integrate(eng, world, dist if world > 1 else None)
                 if k >= args.warmup:
                     sent += a; recv += b
-                    int_ms.append(m.stats()["last_integrate_ms"])
+                    s = m.stats()
+                    int_ms.append(s["last_integrate_ms"]); upd_leaves.append(s["last_touched_leaves"])
             ev1.record(stream)
             barrier()
             t_wall = time.perf_counter() - t_wall0
@@ -443,7 +581,9 @@ def run_ours(args, rank, world, local_rank):
                    "rays": st1["rays"] - st0["rays"], "voxel_updates": st1["voxel_updates"] - st0["voxel_updates"],
                    "visits": st1["visits"] - st0["visits"], "launches": st1["gpu_launches"] - launches0,
                    "acc_ms": acc_ms, "prep_ms": prep_ms, "int_ms": int_ms, "leaves": leaves, "map_leaves": st1["map_leaves"],
-                   "sent": sent, "recv": recv, "d2h_extra": d2h_extra}
+                   "sent": sent, "recv": recv, "d2h_extra": d2h_extra, "upd_leaves": upd_leaves}
+            if world > 1 and not mixed and not e2e:
+                out["checksum"] = m.mapChecksum()  # parity witness of the sharded map, compared below (outside the timed region)
             if mixed:
                 # outside the timed region: the remote map must equal the sender's (level-2 updates are lossless)
                 a, b = m.exportMap(), remote.exportMap()
@@ -467,6 +607,25 @@ def run_ours(args, rank, world, local_rank):
         print(f"[rank {rank}] value leg: step {res_v['ms'] / args.steps:.3f} ms  acc {mean_(res_v['acc_ms']):.3f}  int {mean_(res_v['int_ms']):.3f} | "
               f"e2e leg: step {res_e['ms'] / args.steps:.3f} ms acc {mean_(res_e['acc_ms']):.3f} int {mean_(res_e['int_ms']):.3f} phases {log.mean(axis=0).round(3).tolist()} "
               f"leaves {mean_(res_v['leaves']):.0f} map_leaves {res_v['map_leaves']}", file=sys.stderr, flush=True)
+
+    # ---- parity witness of the sharded map of the value leg (outside every timed region) ----
+    weak_identical = None
+    if world > 1 and not mixed and "checksum" in res_v:
+        allc = _gather(world, dist, res_v["checksum"])
+        if rank == 0:
+            if strong:
+                per_step = [[scans.make_scan(cfg, k)] for k in range(n_steps)]
+            else:
+                per_step = [[(scans.make_scan(cfg, k, sensor=r) if cfg == 2 else scans.make_scan(cfg, k + 1000 * r)) for r in range(world)]
+                            for k in range(n_steps)]
+            ref = reference_checksum(c, local_rank, stream, per_step)
+            weak_identical = bool((sum(x[0] for x in allc) & ((1 << 64) - 1), sum(x[1] for x in allc)) == ref)
+            del per_step
+    # ---- north_star's multi-GPU target on every line of the default workload ----
+    strong_block = None
+    if args.workload == "cfg2" and not strong and not args.no_strong_block:
+        torch.cuda.empty_cache()
+        strong_block = strong_cfg4_block(args, rank, world, local_rank, stream, dist if world > 1 else None)
 
     # ---- max over ranks of the device time; totals over ranks ----
     def reduce(vals, op):
@@ -492,7 +651,10 @@ def run_ours(args, rank, world, local_rank):
     t_dda = t_acc - t_prep
     b_alg = alg_bytes(n_pts, int(L))  # cfg5: roofline figures describe the SENDER's scan-step kernels only
     t_kernels = t_acc + t_int
-    upd_bytes = 4352 * L  # K2 alone: update masks read (128 B) + map leaf values+mask read and written (4224 B)
+    # K2 alone: update masks read (128 B) + map leaf values+mask read and written (4224 B) per leaf THIS RANK integrates
+    # (with N > 1 that is the rank's owned share after the exchange, not the leaves its own rays touched)
+    L_upd = mean(res_v["upd_leaves"]) if res_v["upd_leaves"] else L
+    upd_bytes = 4352 * L_upd
     tr_dda, tr_src = measured_traffic("raycast_dda_kernel")
     tr_upd, _ = measured_traffic("apply_update_kernel")
     traffic = (tr_dda + tr_upd) if (tr_dda is not None and tr_upd is not None and cfg == 2) else None
@@ -508,8 +670,9 @@ def run_ours(args, rank, world, local_rank):
                                    "achieved_gbs": (48 * n_pts + 128 * L) / (t_dda * 1e-3) / 1e9 if t_dda else None,
                                    "visits_per_sec": (res_v["visits"] / K) / (t_dda * 1e-3) if t_dda else None,
                                    "note": "not HBM-bound: bounded by L2 atomic (RED) throughput and instruction issue"},
-            "apply_update_kernel": {"ms": t_int, "alg_bytes": upd_bytes, "achieved_gbs": upd_bytes / (t_int * 1e-3) / 1e9 if t_int else None,
-                                    "frac": upd_bytes / (t_int * 1e-3) / 1e9 / peak if t_int else None},
+            "apply_update_kernel": {"ms": t_int, "alg_bytes": upd_bytes, "leaves": L_upd, "achieved_gbs": upd_bytes / (t_int * 1e-3) / 1e9 if t_int else None,
+                                    "frac": upd_bytes / (t_int * 1e-3) / 1e9 / peak if t_int else None,
+                                    "note": "rank 0's numbers" if world > 1 else None},
         },
     }
     line = {
@@ -545,6 +708,9 @@ def run_ours(args, rank, world, local_rank):
         line["e2e"]["api"] = "accumulate(host pinned cloud) + createUpdate(2) + integrate + remote applyUpdate(2) + periodic getMapSection*"
         line["config"]["parallelism"] = "1 GPU (sender and remote map)" if world == 1 else f"{world} independent sender/remote pairs, one per GPU"
         line["exchange"] = None
+    line["strong_cfg4"] = strong_block
+    if world > 1 and not mixed:
+        line["sharded_map_identical"] = weak_identical
     if world > 1 and not mixed:
         line["exchange"] = {"kind": args.exchange, "records_sent_per_step": (sent / K) if args.exchange == "nccl" else None,
                             "bytes_sent_per_step": (136 * sent / K) if args.exchange == "nccl" else None,
@@ -592,6 +758,7 @@ def main():
                     help="multi-GPU update-leaf exchange: fused peer-memory stores over NVLink (default) or NCCL all-to-all")
     ap.add_argument("--cpu-scans", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong-block", action="store_true", help="skip the strong_cfg4 block (1M-point scans split over all ranks)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="1 GPU: use the synchronous accumulate + integrate calls instead of vdbm_insert_async")
     args = ap.parse_args()

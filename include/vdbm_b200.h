@@ -228,6 +228,20 @@ void vdbm_leafset_free(vdbm_leafset* s);
 /* ---- multi-GPU: map sharded by leaf key, rays split across ranks -------------------- */
 /* Owner rank of a leaf (origin must be a multiple of 8): mix64(morton-brick(leaf)) % n_ranks. Pure function. */
 int32_t vdbm_leaf_owner(const int32_t origin[3], int32_t n_ranks);
+/* Ownership plan of the sharded map (replaces nothing in the reference: V:375-387 integrates ONE map; here every rank
+ * integrates its shard). mode 0 (default): the hash of vdbm_leaf_owner. mode 1: azimuth sectors around the leaf column
+ * center_leaf_xy (leaf coordinates = voxel >> 3): rank r owns the leaves whose centre direction, measured as a diamond
+ * angle in [0, 4) (dy/(|dx|+|dy|) per quadrant), lies in [bounds[r], bounds[r+1]); the last sector wraps around. Split the
+ * rays of a scan by the same bounds around the sensor and nearly every touched leaf stays on the rank that touched it
+ * (vdb_mapping_b200/dist.py plans the bounds from the first scan). Every rank must set the same plan; it cannot change
+ * while the map holds leaves. */
+int vdbm_shard_plan_set(vdbm_map* map, int32_t mode, int32_t n_ranks, const int32_t center_leaf_xy[2], const double* bounds);
+/* owner under the handle's plan (mode 0: same as vdbm_leaf_owner) */
+int32_t vdbm_leaf_owner_planned(vdbm_map* map, const int32_t origin[3], int32_t n_ranks);
+/* Order-independent parity witness of a (sharded) map: out2[0] = sum over the leaves of this handle of a 64-bit hash of
+ * (leaf key, active mask, 512 value bit patterns), out2[1] = number of leaves. Summed over all ranks (mod 2^64) it equals
+ * the checksum of the same scans integrated on one GPU (getGrid() V:799 compared without moving the map). */
+int vdbm_map_checksum(vdbm_map* map, uint64_t out2[2]);
 /* Bin the source's accumulated update leaves by owner into a device buffer of 136-byte records
  * {uint64 key, uint64 active[8], uint64 value[8]} grouped by rank; counts[n_ranks] (host) receives the group
  * sizes; the update grid is emptied. *d_records stays valid until the next call on this handle. */
@@ -244,7 +258,8 @@ int vdbm_update_import_device(vdbm_map* map, const char* source_id, const void* 
  *   vdbm_exchange_create : allocate this rank's inbox (2 parities x n_ranks sender regions x capacity records) and
  *                          return its IPC handles (VDBM_IPC_HANDLE_BYTES bytes) for an all-gather by the caller
  *   vdbm_exchange_connect: map every peer's inbox from the gathered handles (n_ranks x VDBM_IPC_HANDLE_BYTES)
- *   vdbm_update_push     : bin + send the source's update leaves (its grid is emptied); asynchronous
+ *   vdbm_update_push     : bin the source's update leaves by owner and send the FOREIGN ones (zeroed locally); the leaves
+ *                          this rank owns stay in its grid; asynchronous
  *   vdbm_update_pull     : wait for all senders of this epoch, OR their records into the source's grid */
 #define VDBM_IPC_HANDLE_BYTES 128
 int vdbm_exchange_create(vdbm_map* map, int32_t rank, int32_t n_ranks, uint64_t capacity_records_per_sender, void* handles_out);

@@ -26,8 +26,8 @@ from oracle.oracle import OracleOccupancyVDBMapping  # noqa: E402
 class OracleEngine:
     """Test double with the CudaEngine interface, backed by the CPU oracle (CPU tests only)."""
 
-    def __init__(self, m, src):
-        self.m, self.src = m, src
+    def __init__(self, m, src, plan=None):
+        self.m, self.src, self.plan = m, src, plan
 
     def accumulate(self, points, origin):
         return self.m.accumulateUpdate(points, origin, self.src)
@@ -35,7 +35,8 @@ class OracleEngine:
     def partition(self, world):
         ls = self.m.exportUpdateGrid(self.src)
         self.m.clearUpdateGrid(self.src)
-        owners = np.array([vdist.leaf_owner_py(o, world) for o in ls.origins], dtype=np.int64)
+        plan = self.plan or vdist.ShardPlan(0, world)
+        owners = np.array([vdist.leaf_owner_planned_py(o, plan) for o in ls.origins], dtype=np.int64)
         order = np.argsort(owners, kind="stable")
         counts = np.bincount(owners, minlength=world).astype(np.int64)
         rec = np.zeros((len(ls), vdist.RECORD_WORDS), dtype=np.uint64)
@@ -75,6 +76,8 @@ def main():
     ap.add_argument("--scans", type=int, default=3)
     ap.add_argument("--points", type=int, default=3000)
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--plan", default="hash", choices=["hash", "sectors"],
+                    help="map ownership: the leaf hash, or azimuth sectors planned from the first scan (rays split by the same sectors)")
     args = ap.parse_args()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -93,7 +96,13 @@ def main():
             m = OracleOccupancyVDBMapping(res)
         m.setConfig(rng, *cfg)
         m.addInputSource("s", rng)
-        eng = vdist.CudaEngine(m, "s") if args.backend == "nccl" else OracleEngine(m, "s")
+        plan = vdist.ShardPlan(0, world)
+        if args.plan == "sectors":
+            first_pts, first_origin = scans.small_scan(700, n=args.points, scale=2.5)
+            plan = vdist.plan_sectors(first_pts, first_origin, res, rng, world)
+            if args.backend == "nccl":
+                m.setShardPlan(plan)
+        eng = vdist.CudaEngine(m, "s") if args.backend == "nccl" else OracleEngine(m, "s", plan)
         p2p = args.backend == "nccl" and args.exchange == "p2p"
         if p2p:
             vdist.connect_peers(m, dist, capacity_records_per_sender=1 << 16)
@@ -102,8 +111,11 @@ def main():
             if not p2p:
                 return vdist.sharded_insert(eng, points, origin, world, dist, mode=mode)
             if mode == "split":
-                lo, hi = vdist.split_points(points.shape[0], rank, world)
-                points = points[lo:hi]
+                if args.plan == "sectors":
+                    points = points[vdist.sector_rays(points, origin, plan, rank)]
+                else:
+                    lo, hi = vdist.split_points(points.shape[0], rank, world)
+                    points = points[lo:hi]
             eng.accumulate(points, origin)
             vdist.push_pull_and_integrate(eng)
         ref = OracleOccupancyVDBMapping(res) if rank == 0 else None
@@ -122,12 +134,23 @@ def main():
                     ref.integrateUpdate()
             else:
                 pts, origin = scans.small_scan(700 + k, n=args.points, scale=2.5)
-                insert(pts, origin, "split")
+                if args.plan == "sectors" and not p2p:
+                    # sector split of the rays on the generic (all-to-all) path: done here, the exchange then sees "own clouds"
+                    sel = vdist.sector_rays(pts, origin, plan, rank)
+                    eng.accumulate(pts[sel], origin)
+                    vdist.exchange_and_integrate(eng, world, dist)
+                else:
+                    insert(pts, origin, "split")
                 if ref:
                     ref.insertPointCloud(pts, origin, "s")
         # gather the shards on rank 0 and compare the union with the single-process oracle map
         shard = m.exportMap()
-        owners_ok = all(vdist.leaf_owner_py(o, world) == rank for o in shard.origins)
+        owners_ok = all(vdist.leaf_owner_planned_py(o, plan) == rank for o in shard.origins)
+        if args.backend == "nccl":
+            owners_ok = owners_ok and all(m.leafOwnerPlanned(o, world) == rank for o in shard.origins[:2000])
+            chk = m.mapChecksum()
+            sums = [None] * world
+            dist.all_gather_object(sums, chk)
         payload = [shard.origins, shard.active, shard.values, owners_ok]
         gathered = [None] * world
         dist.all_gather_object(gathered, payload)
@@ -144,6 +167,14 @@ def main():
             assert np.array_equal(active[order], want.active), "active masks differ"
             assert np.array_equal(values[order].view(np.uint32), want.values.view(np.uint32)), "values differ"
             sizes = [len(g[0]) for g in gathered]
+            if args.backend == "nccl":
+                # the checksum witness bench.py relies on: sum over the shards == one map holding the union (rebuilt here
+                # from the oracle's leaves through applyMapSectionGrid)
+                one = OccupancyVDBMapping(res, device=torch.cuda.current_device())
+                one.setConfig(rng, *cfg)
+                one.applyMapSectionGrid(want, tile_quirk=False)
+                assert (sum(x[0] for x in sums) & ((1 << 64) - 1), sum(x[1] for x in sums)) == one.mapChecksum(), "checksum witness differs"
+                one.close()
             status = f"OK shards={sizes} total={len(keys)}"
     except Exception:
         status = "FAIL\n" + traceback.format_exc()

@@ -55,6 +55,38 @@ def test_exchange_logic_world2_gloo(mode, tmp_path):
     assert len(sizes) == 2 and min(sizes) > 0
 
 
+def test_sector_ownership_world2_gloo(tmp_path):
+    """rays split by azimuth sector, map owned by the same sectors (ShardPlan mode 1): union of shards == oracle"""
+    res = _run(2, "gloo", "split", tmp_path, extra=("--plan", "sectors"))
+    sizes = eval(res.split("shards=")[1].split(" total")[0])
+    assert len(sizes) == 2 and min(sizes) > 0
+
+
+def test_sector_planner_properties():
+    from vdb_mapping_b200 import dist as vdist, scans
+    pts, origin = scans.make_scan(1, 0)
+    for world in (2, 3, 8, 16):
+        plan = vdist.plan_sectors(pts, origin, 0.1, 50.0, world)
+        b = plan.bounds
+        assert len(b) == world and b[0] == 0.0 and all(x < y for x, y in zip(b, b[1:])) and b[-1] < 4.0
+        parts = [vdist.sector_rays(pts, origin, plan, r) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(len(pts)))  # every ray on exactly one rank
+        v = vdist.ray_visits(pts, origin, 0.1, 50.0)
+        share = np.array([v[p].sum() for p in parts]) / v.sum()
+        assert share.max() < 1.25 / world, share  # balanced by voxel visits
+    # diamond angle is monotone in the true angle
+    rng = np.random.default_rng(3)
+    d = rng.normal(size=(4000, 2))
+    assert (np.argsort(vdist.diamond_angle(d[:, 0], d[:, 1])) == np.argsort(np.mod(np.arctan2(d[:, 1], d[:, 0]), 2 * np.pi))).all()
+    # a leaf with the planned owner r lies in sector r
+    plan = vdist.plan_sectors(pts, origin, 0.1, 50.0, 4)
+    for o in (rng.integers(-300, 300, (200, 3)) * 8):
+        r = vdist.leaf_owner_planned_py(o, plan)
+        a = float(vdist.diamond_angle((int(o[0]) >> 3) - plan.cx, (int(o[1]) >> 3) - plan.cy))
+        lo, hi = plan.bounds[r], (plan.bounds[r + 1] if r + 1 < 4 else 4.0)
+        assert lo <= a < hi or (r == 3 and a < plan.bounds[0])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("exchange", ["nccl", "p2p"])
 @pytest.mark.parametrize("mode", ["own_cloud", "split"])
@@ -65,3 +97,12 @@ def test_sharded_map_world2_gpu(mode, exchange, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(2, "nccl", mode, tmp_path, extra=("--points", "20000", "--exchange", exchange))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_sector_ownership_world2_gpu(exchange, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(2, "nccl", "split", tmp_path, extra=("--points", "20000", "--exchange", exchange, "--plan", "sectors"))

@@ -7,7 +7,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}.log 2
 tail -5 gpurun_out/pytest_${TAG}.log
 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 ab() {
-  python bench.py --steps 20 --warmup 3 --no-cpu-baseline $2 | python -c "
+  python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-strong-block $2 | python -c "
 import sys,json; d=json.loads(sys.stdin.read()); k=d['roofline']['by_kernel']; print('$1', 'dda_ms', round(k['raycast_dda_kernel']['ms'],3), 'upd_ms', round(k['apply_update_kernel']['ms'],3), 'ms/step', round(d['ms_per_step'],3), 'frac', round(d['roofline']['frac'],3))" | tee -a gpurun_out/ab_${TAG}.txt
 }
 ab product ""

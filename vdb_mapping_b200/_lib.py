@@ -86,6 +86,9 @@ def lib() -> C.CDLL:
     sig("vdbm_leafset_values", f32p, vp)
     sig("vdbm_leafset_free", None, vp)
     sig("vdbm_leaf_owner", i32, i32p, i32)
+    sig("vdbm_shard_plan_set", C.c_int, vp, i32, i32, i32p, dblp)
+    sig("vdbm_leaf_owner_planned", i32, vp, i32p, i32)
+    sig("vdbm_map_checksum", C.c_int, vp, u64p)
     sig("vdbm_update_partition", C.c_int, vp, cp, i32, u64p, pvp)
     sig("vdbm_update_import_device", C.c_int, vp, cp, vp, u64)
     sig("vdbm_exchange_create", C.c_int, vp, i32, i32, u64, vp)

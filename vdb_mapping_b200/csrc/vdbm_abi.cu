@@ -98,6 +98,8 @@ struct vdbm_map
   size_t part_cap    = 0;
   int dda_grid       = 0;
 
+  ShardPlan shard{}; // ownership of map leaves across ranks (mode 0 = hash; vdbm_shard_plan_set)
+
   // peer-memory exchange (multi-GPU)
   struct Exchange
   {
@@ -1832,6 +1834,54 @@ int32_t vdbm_leaf_owner(const int32_t origin[3], int32_t n_ranks)
   return leafOwner(packLeafKey(origin[0] >> 3, origin[1] >> 3, origin[2] >> 3), n_ranks);
 }
 
+int vdbm_shard_plan_set(vdbm_map* m, int32_t mode, int32_t n_ranks, const int32_t center_leaf_xy[2], const double* bounds)
+{
+  if (!m || (mode != 0 && mode != 1) || n_ranks < 1 || n_ranks > kMaxRanks) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  ShardPlan sp{};
+  sp.mode = mode; sp.n_ranks = n_ranks;
+  if (mode == 1)
+  {
+    if (!center_leaf_xy || !bounds) return VDBM_ERR_INVALID_ARG;
+    sp.cx = center_leaf_xy[0]; sp.cy = center_leaf_xy[1];
+    for (int r = 0; r < n_ranks; ++r)
+    {
+      if (!(bounds[r] >= 0.0 && bounds[r] < 4.0) || (r && !(bounds[r] > bounds[r - 1])))
+        return fail(m, VDBM_ERR_INVALID_ARG, "sector bounds must be ascending diamond angles in [0, 4)");
+      sp.bounds[r] = bounds[r];
+    }
+  }
+  if (m->n_leaves != 0 && std::memcmp(&sp, &m->shard, sizeof(sp)) != 0)
+    return fail(m, VDBM_ERR_INVALID_ARG, "the shard plan cannot change while the map holds leaves (reset the map first)");
+  m->shard = sp;
+  return VDBM_OK;
+}
+
+int32_t vdbm_leaf_owner_planned(vdbm_map* m, const int32_t origin[3], int32_t n_ranks)
+{
+  if (!m || !origin || n_ranks <= 0) return -1;
+  ShardPlan plan = m->shard;
+  if (plan.mode == 0) plan.n_ranks = n_ranks;
+  return leafOwnerPlanned(packLeafKey(origin[0] >> 3, origin[1] >> 3, origin[2] >> 3), plan);
+}
+
+int vdbm_map_checksum(vdbm_map* m, uint64_t out2[2])
+{
+  if (!m || !out2) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  TempBuf d(m->stream);
+  CU_TRY(m, d.alloc(16));
+  CU_TRY(m, cudaMemsetAsync(d.p, 0, 16, m->stream));
+  launchMapChecksum(m->mt, m->n_leaves, d.as<unsigned long long>(), m->stream);
+  CU_TRY(m, cudaGetLastError());
+  CU_TRY(m, cudaMemcpyAsync(m->h_small + 32, d.p, 16, cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  std::memcpy(out2, m->h_small + 32, 16);
+  return VDBM_OK;
+}
+
 int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, uint64_t* counts, const void** d_records)
 {
   if (!m || !counts || !d_records || n_ranks <= 0 || n_ranks > 32) return VDBM_ERR_INVALID_ARG;
@@ -1862,7 +1912,10 @@ int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, u
   uint32_t* d_counts = d.as<uint32_t>();
   uint32_t* d_cursor = d_counts + 32;
   CU_TRY(m, cudaMemsetAsync(d_counts, 0, 64 * 4, m->stream));
-  launchPartition(s->g, n, n_ranks, d_counts, d_cursor, m->d_part, 0, m->stream);
+  ShardPlan plan = m->shard;
+  if (plan.mode == 0) plan.n_ranks = n_ranks;
+  else if (plan.n_ranks != n_ranks) return fail(m, VDBM_ERR_INVALID_ARG, "n_ranks differs from the shard plan set with vdbm_shard_plan_set");
+  launchPartition(s->g, n, plan, d_counts, d_cursor, m->d_part, 0, m->stream);
   CU_TRY(m, cudaMemcpyAsync(m->h_small + 24, d_counts, 32 * 4, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   uint32_t off[32];
@@ -1877,7 +1930,7 @@ int vdbm_update_partition(vdbm_map* m, const char* source_id, int32_t n_ranks, u
     }
   }
   CU_TRY(m, cudaMemcpyAsync(d_cursor, off, 32 * 4, cudaMemcpyHostToDevice, m->stream));
-  launchPartition(s->g, n, n_ranks, d_counts, d_cursor, m->d_part, 1, m->stream);
+  launchPartition(s->g, n, plan, d_counts, d_cursor, m->d_part, 1, m->stream);
   launchResetBricks(s->g, s->n_bricks, m->stream);
   CU_TRY(m, cudaGetLastError());
   CU_TRY(m, cudaStreamSynchronize(m->stream));
@@ -1965,13 +2018,16 @@ int vdbm_update_push(vdbm_map* m, const char* source_id)
   if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
   auto& ex = m->ex;
   if (!ex.connected) return fail(m, VDBM_ERR_INVALID_ARG, "exchange not connected");
+  ShardPlan plan = m->shard;
+  if (plan.mode == 0) plan.n_ranks = ex.px.n_ranks;
+  else if (plan.n_ranks != ex.px.n_ranks) return fail(m, VDBM_ERR_INVALID_ARG, "shard plan and exchange disagree on the number of ranks");
   ex.epoch += 1;
   CU_TRY(m, cudaEventRecord(ex.ev[0], m->stream));
-  launchPushUpdate(s->g, s->n_entries, ex.px, ex.epoch & 1u, ex.epoch, ex.d_cursors, m->d_ctr, m->stream);
+  launchPushUpdate(s->g, s->n_entries, ex.px, plan, ex.epoch & 1u, ex.epoch, ex.d_cursors, m->d_ctr, m->stream);
   CU_TRY(m, cudaEventRecord(ex.ev[1], m->stream));
-  launchResetBricks(s->g, s->n_bricks, m->stream);
   CU_TRY(m, cudaGetLastError());
-  s->n_bricks = s->n_entries = 0;
+  // The leaves this rank owns stay in the grid (the foreign ones were sent and zeroed): the host counts are upper bounds
+  // until vdbm_update_pull* rebuilds the leaf list on top of the imported records.
   return VDBM_OK;
 }
 

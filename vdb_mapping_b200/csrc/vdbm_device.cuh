@@ -60,6 +60,37 @@ __host__ __device__ __forceinline__ int32_t leafOwner(uint64_t key, int32_t n_ra
   return int32_t(mix64(brick ^ 0x9E3779B97F4A7C15ULL) % uint64_t(n_ranks));
 }
 
+// Sharding plan of the map (multi-GPU). mode 0: the hash above (nothing is local on purpose: any sensor layout balances).
+// mode 1: AZIMUTH SECTORS around a fixed leaf column (cx, cy): rank r owns the leaves whose centre direction falls into
+// [bounds[r], bounds[r+1]) (the last sector wraps), measured as a "diamond angle" in [0, 4) - a monotone function of the
+// true angle that needs one IEEE division of small integers, so host, device and the Python twin agree bit for bit.
+// A ray cast from a sensor near the centre stays inside its azimuth sector: when the rays are split by the same bounds
+// nearly every touched leaf is owned by the rank that touched it, and only the leaves around the sensor and along the
+// sector borders cross NVLink.
+constexpr int kMaxRanks = 16;
+struct ShardPlan
+{
+  int32_t mode, n_ranks;
+  int32_t cx, cy;           // centre, in LEAF coordinates (voxel >> 3)
+  double bounds[kMaxRanks]; // ascending diamond angles, one per rank
+};
+__host__ __device__ __forceinline__ double diamondAngle(double dx, double dy)
+{
+  if (dx == 0.0 && dy == 0.0) return 0.0;
+  if (dy >= 0.0) return dx >= 0.0 ? dy / (dx + dy) : 1.0 - dx / (dy - dx);
+  return dx < 0.0 ? 2.0 - dy / (-dx - dy) : 3.0 + dx / (dx - dy);
+}
+__host__ __device__ __forceinline__ int32_t leafOwnerPlanned(uint64_t key, const ShardPlan& sp)
+{
+  if (sp.mode == 0) return leafOwner(key, sp.n_ranks);
+  const int32_t lx = int32_t(uint32_t(key >> 42) & 0x1FFFFFu) - kLeafBias, ly = int32_t(uint32_t(key >> 21) & 0x1FFFFFu) - kLeafBias;
+  const double a = diamondAngle(double(lx - sp.cx), double(ly - sp.cy));
+  int32_t owner = sp.n_ranks - 1; // below the first bound: the last sector wraps around
+  for (int32_t r = 0; r < sp.n_ranks; ++r)
+    if (a >= sp.bounds[r]) owner = r;
+  return owner;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Update grid of one input source: an open-addressing hash of BRICKS (8^3 leaves = 64^3 voxels), slot ==
 // storage. Inside a brick every leaf mask word has a fixed address, so the DDA kernel needs a hash lookup only
@@ -205,7 +236,6 @@ struct RaycastArgs
 // words form ONE aligned 128-byte line (full-line NVLink stores): for region R = parity * n_ranks + sender:
 //   masks: uint64 [R][cap][16]  (active[8] | value[8])      keys: uint64 [2 * n_ranks * cap + R * cap + i] after the masks
 // ctrl layout: [parity 2][sender n_ranks] uint64 = (epoch << 32) | record count, written by the sender.
-constexpr int kMaxRanks = 16;
 struct ExchangePeers
 {
   uint64_t* inbox[kMaxRanks];          // peer r's inbox base (mapped into this process), [rank] = own
@@ -263,7 +293,7 @@ void launchSection(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const
                    Counters* ctr, cudaStream_t s);
 void launchProbe(MapTable mt, int32_t x, int32_t y, int32_t z, float* out_val, int32_t* out_active, cudaStream_t s);
 // pass 0: count entries per owner rank; pass 1: scatter records grouped by rank and zero the entry masks
-void launchPartition(UpdateGrid ug, uint32_t n_entries, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_cursor,
+void launchPartition(UpdateGrid ug, uint32_t n_entries, ShardPlan plan, uint32_t* rank_counts, uint32_t* rank_cursor,
                      LeafRecord* out, int pass, cudaStream_t s);
 void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, uint64_t* out_keys, uint32_t* out_idx, cudaStream_t s);
 // perm: optional permutation (output row i = record perm[i])
@@ -277,8 +307,10 @@ void launchSectionActivate(MapTable mt, const uint64_t* keys, const uint64_t* ac
 void launchSectionApplyGrid(MapTable mt, const uint64_t* keys, const uint64_t* active, const float* values, uint32_t n, Counters* ctr, cudaStream_t s);
 void launchSectionTileQuirk(MapTable mt, const uint64_t* blocks, uint32_t n_blocks, int level, const uint64_t* present, uint32_t n_present, cudaStream_t s);
 // fused bin + send over peer memory; cursors = device scratch [kMaxRanks] (zeroed by the wrapper)
-void launchPushUpdate(UpdateGrid ug, uint32_t n_entries, ExchangePeers px, uint32_t parity, uint32_t epoch, uint32_t* cursors,
+void launchPushUpdate(UpdateGrid ug, uint32_t n_entries, ExchangePeers px, ShardPlan plan, uint32_t parity, uint32_t epoch, uint32_t* cursors,
                       Counters* ctr, cudaStream_t s);
+// order-independent 64-bit checksum of the map: sum over leaves of hash(key, active mask, value bits); out[0] += sum, out[1] += leaves
+void launchMapChecksum(MapTable mt, uint32_t n_leaves, unsigned long long* out2, cudaStream_t s);
 void launchWaitPeers(const unsigned long long* ctrl, int32_t n_ranks, uint32_t parity, uint32_t epoch, uint32_t* counts_out, Counters* ctr,
                      cudaStream_t s);
 // after launchWaitPeers: OR all inbox records of this parity into the grid

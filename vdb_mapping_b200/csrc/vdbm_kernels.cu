@@ -1332,14 +1332,14 @@ __global__ void probe_kernel(MapTable mt, int32_t x, int32_t y, int32_t z, float
 }
 
 // multi-GPU: bin touched update leaves by owner rank. pass 0 counts, pass 1 scatters (and zeroes the entry masks).
-__global__ void partition_kernel(UpdateGrid g, uint32_t n, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_cursor,
+__global__ void partition_kernel(UpdateGrid g, uint32_t n, ShardPlan plan, uint32_t* rank_counts, uint32_t* rank_cursor,
                                  LeafRecord* out, int pass)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t e   = g.entries[i];
   const uint64_t key = leafKeyOfEntry(g.bkeys[e >> 9], e & 511u);
-  const int32_t r    = leafOwner(key, n_ranks);
+  const int32_t r    = leafOwnerPlanned(key, plan);
   if (pass == 0) { atomicAdd(rank_counts + r, 1u); return; }
   const uint32_t dst = atomicAdd(rank_cursor + r, 1u);
   out[dst].key       = key;
@@ -1541,11 +1541,11 @@ __global__ void section_tile_quirk_kernel(MapTable mt, const uint64_t* blocks, u
 //      (a mapped peer pointer: the stores go over NVLink); the update masks are zeroed as they are read
 // publish_counts_kernel then releases (epoch << 32 | count) to every peer with system scope.
 // ====================================================================================================
-__global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t n, ExchangePeers px, uint32_t parity, uint32_t* cursors,
-                                                         Counters* ctr)
+__global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t n, ExchangePeers px, ShardPlan plan, uint32_t parity,
+                                                         uint32_t* cursors, Counters* ctr)
 {
   __shared__ uint32_t s_count[kMaxRanks], s_base[kMaxRanks];
-  __shared__ uint32_t s_entry[256], s_dst[256]; // entry id, (owner << 24 | local slot)
+  __shared__ uint32_t s_entry[256], s_dst[256]; // entry id, (owner << 24 | local slot); kInvalid = the leaf is this rank's own
   __shared__ uint64_t s_key[256];
   const uint32_t i0 = blockIdx.x * 256u;
   if (threadIdx.x < kMaxRanks) s_count[threadIdx.x] = 0;
@@ -1555,10 +1555,12 @@ __global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t
   {
     const uint32_t e   = g.entries[i];
     const uint64_t key = leafKeyOfEntry(g.bkeys[e >> 9], e & 511u);
-    const uint32_t r   = uint32_t(leafOwner(key, px.n_ranks));
+    const uint32_t r   = uint32_t(leafOwnerPlanned(key, plan));
     s_entry[threadIdx.x] = e;
     s_key[threadIdx.x]   = key;
-    s_dst[threadIdx.x]   = (r << 24) | atomicAdd(&s_count[r], 1u);
+    // a leaf this rank owns STAYS in its update grid (the pull ORs the peers' records on top): with sector ownership
+    // that is nearly every touched leaf, and nothing of it is copied
+    s_dst[threadIdx.x] = (r == uint32_t(px.rank)) ? kInvalid : ((r << 24) | atomicAdd(&s_count[r], 1u));
   }
   __syncthreads();
   if (threadIdx.x < px.n_ranks) s_base[threadIdx.x] = s_count[threadIdx.x] ? atomicAdd(cursors + threadIdx.x, s_count[threadIdx.x]) : 0u;
@@ -1574,7 +1576,7 @@ __global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t
   {
     const uint32_t k = k0 + 16u * it;
     w[it] = 0;
-    if (k < n_here)
+    if (k < n_here && s_dst[k] != kInvalid)
     {
       const uint32_t e = s_entry[k];
       w[it] = (j < 8) ? g.act[size_t(e) * 8 + j] : g.val[size_t(e) * 8 + (j - 8)];
@@ -1584,7 +1586,7 @@ __global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t
   for (int it = 0; it < 16; ++it)
   {
     const uint32_t k = k0 + 16u * it;
-    if (k >= n_here) continue;
+    if (k >= n_here || s_dst[k] == kInvalid) continue;
     const uint32_t e = s_entry[k], r = s_dst[k] >> 24, pos = s_base[r] + (s_dst[k] & 0xFFFFFFu);
     if (j < 8) g.act[size_t(e) * 8 + j] = 0;
     else g.val[size_t(e) * 8 + (j - 8)] = 0;
@@ -1593,7 +1595,7 @@ __global__ void __launch_bounds__(256) push_update_kernel(UpdateGrid g, uint32_t
     px.inbox[r][inboxMaskWord(region, px.cap, pos) + j] = w[it];
   }
   // keys: thread t writes the key of record t (records of one owner are contiguous per block -> coalesced runs)
-  if (threadIdx.x < n_here)
+  if (threadIdx.x < n_here && s_dst[threadIdx.x] != kInvalid)
   {
     const uint32_t r = s_dst[threadIdx.x] >> 24, pos = s_base[r] + (s_dst[threadIdx.x] & 0xFFFFFFu);
     if (pos < px.cap)
@@ -1924,6 +1926,39 @@ __global__ void __launch_bounds__(256) restore_state_kernel(UpdateGrid g, uint32
 }
 
 
+// Order-independent checksum of the map (multi-GPU parity witness: the sum over all shards must equal the single-GPU
+// map's). Warp per leaf; a leaf's hash mixes its key, its 8 mask words and its 512 value bit patterns position by position.
+__global__ void __launch_bounds__(256) map_checksum_kernel(MapTable mt, uint32_t n_leaves, unsigned long long* out2)
+{
+  const int lane         = threadIdx.x & 31;
+  const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long sum = 0, cnt = 0;
+  for (uint32_t l = warp; l < n_leaves; l += n_warps)
+  {
+    float a[8], b[8];
+    ld256(mt.leaf_vals + size_t(l) * 512 + lane * 16, a);
+    ld256(mt.leaf_vals + size_t(l) * 512 + lane * 16 + 8, b);
+    uint64_t h = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+    {
+      h = mix64(h ^ (uint64_t(__float_as_uint(a[q])) | (uint64_t(lane * 16 + q + 1) << 32)));
+      h = mix64(h ^ (uint64_t(__float_as_uint(b[q])) | (uint64_t(lane * 16 + q + 9) << 32)));
+    }
+    if (lane < 8) h ^= mix64(mt.leaf_mask[size_t(l) * 8 + lane] + 0x9E3779B97F4A7C15ULL * uint64_t(lane + 1));
+    // combine the lanes position-dependently (lane index is already mixed into every term), then bind to the key
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) h += shflXor64(h, d);
+    if (lane == 0) { sum += mix64(h ^ mix64(mt.leaf_keys[l])); ++cnt; }
+  }
+  if (lane == 0 && cnt)
+  {
+    atomicAdd(out2, sum);
+    atomicAdd(out2 + 1, cnt);
+  }
+}
+
 // ====================================================================================================
 // launch wrappers
 // ====================================================================================================
@@ -2091,10 +2126,10 @@ void launchProbe(MapTable mt, int32_t x, int32_t y, int32_t z, float* out_val, i
 {
   VDBM_LAUNCH(probe_kernel, 1, 1, s, mt, x, y, z, out_val, out_active);
 }
-void launchPartition(UpdateGrid g, uint32_t n, int32_t n_ranks, uint32_t* rank_counts, uint32_t* rank_cursor, LeafRecord* out, int pass,
+void launchPartition(UpdateGrid g, uint32_t n, ShardPlan plan, uint32_t* rank_counts, uint32_t* rank_cursor, LeafRecord* out, int pass,
                      cudaStream_t s)
 {
-  if (n) VDBM_LAUNCH(partition_kernel, blocksFor(n, 256), 256, s, g, n, n_ranks, rank_counts, rank_cursor, out, pass);
+  if (n) VDBM_LAUNCH(partition_kernel, blocksFor(n, 256), 256, s, g, n, plan, rank_counts, rank_cursor, out, pass);
 }
 void launchKeysFromIdx(const uint64_t* keys, const uint32_t* idx, uint32_t n, uint64_t* out_keys, uint32_t* out_idx, cudaStream_t s)
 {
@@ -2138,11 +2173,11 @@ void launchSectionTileQuirk(MapTable mt, const uint64_t* blocks, uint32_t n_bloc
   VDBM_LAUNCH(section_tile_quirk_kernel, blocksFor(threads, 256), 256, s, mt, blocks, n_blocks, level, present, n_present);
 }
 
-void launchPushUpdate(UpdateGrid g, uint32_t n_entries, ExchangePeers px, uint32_t parity, uint32_t epoch, uint32_t* cursors, Counters* ctr,
-                      cudaStream_t s)
+void launchPushUpdate(UpdateGrid g, uint32_t n_entries, ExchangePeers px, ShardPlan plan, uint32_t parity, uint32_t epoch, uint32_t* cursors,
+                      Counters* ctr, cudaStream_t s)
 {
   cudaMemsetAsync(cursors, 0, kMaxRanks * sizeof(uint32_t), s);
-  if (n_entries) VDBM_LAUNCH(push_update_kernel, blocksFor(n_entries, 256), 256, s, g, n_entries, px, parity, cursors, ctr);
+  if (n_entries) VDBM_LAUNCH(push_update_kernel, blocksFor(n_entries, 256), 256, s, g, n_entries, px, plan, parity, cursors, ctr);
   VDBM_LAUNCH(publish_counts_kernel, 1, 32, s, px, parity, epoch, cursors);
 }
 
@@ -2162,6 +2197,13 @@ void launchPullUpdate(UpdateGrid g, const uint64_t* inbox, const unsigned long l
 {
   (void)ctrl; (void)epoch;
   VDBM_LAUNCH(pull_update_kernel, unsigned(smCount()) * 4u, 256, s, g, inbox, cap, n_ranks, parity, counts_out, ctr);
+}
+
+void launchMapChecksum(MapTable mt, uint32_t n_leaves, unsigned long long* out2, cudaStream_t s)
+{
+  if (!n_leaves) return;
+  const unsigned grid = std::min<unsigned>(blocksFor(uint64_t(n_leaves) * 32, 256), unsigned(smCount()) * 8u);
+  VDBM_LAUNCH(map_checksum_kernel, grid, 256, s, mt, n_leaves, out2);
 }
 
 size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,

@@ -52,6 +52,94 @@ def leaf_owner_py(origin, n_ranks: int) -> int:
     return _mix64(brick ^ 0x9E3779B97F4A7C15) % n_ranks
 
 
+# ---- sector ownership (ShardPlan mode 1): see ShardPlan in csrc/vdbm_device.cuh -------------------------------------
+from dataclasses import dataclass, field
+
+
+@dataclass
+class ShardPlan:
+    mode: int = 0                 # 0: hash ownership, 1: azimuth sectors around the leaf column (cx, cy)
+    n_ranks: int = 1
+    cx: int = 0
+    cy: int = 0
+    bounds: list = field(default_factory=list)  # ascending diamond angles in [0, 4), one per rank
+
+
+def diamond_angle(dx, dy):
+    """Monotone stand-in for atan2 on [0, 4): one IEEE division per point, identical on host, device and here."""
+    dx = np.asarray(dx, dtype=np.float64)
+    dy = np.asarray(dy, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q1 = dy / (dx + dy)
+        q2 = 1.0 - dx / (dy - dx)
+        q3 = 2.0 - dy / (-dx - dy)
+        q4 = 3.0 + dx / (dx - dy)
+    a = np.where(dy >= 0.0, np.where(dx >= 0.0, q1, q2), np.where(dx < 0.0, q3, q4))
+    return np.where((dx == 0.0) & (dy == 0.0), 0.0, a)
+
+
+def sector_of(angles, bounds):
+    """Index of the sector [bounds[r], bounds[r+1]) an angle falls into; below bounds[0] wraps to the last one."""
+    b = np.asarray(bounds, dtype=np.float64)
+    r = np.searchsorted(b, np.asarray(angles, dtype=np.float64), side="right") - 1
+    return np.where(r < 0, len(b) - 1, r)
+
+
+def leaf_owner_planned_py(origin, plan: ShardPlan) -> int:
+    """Pure-Python twin of vdbm_leaf_owner_planned."""
+    if plan.mode == 0:
+        return leaf_owner_py(origin, plan.n_ranks)
+    lx, ly = int(origin[0]) >> 3, int(origin[1]) >> 3
+    return int(sector_of(diamond_angle(lx - plan.cx, ly - plan.cy), plan.bounds))
+
+
+def ray_visits(points, origin, resolution: float, max_range: float):
+    """voxel visits of every ray (1 + |d|_1 / res after range clipping; 0 for invalid points): the DDA's cost."""
+    p = np.asarray(points, dtype=np.float64)[:, :3]
+    d = p - np.asarray(origin, dtype=np.float64)[None, :]
+    ln = np.sqrt((d * d).sum(axis=1))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        scale = np.where((max_range > 0) & (ln > max_range), max_range / ln, 1.0)
+    v = 1.0 + np.abs(d * scale[:, None]).sum(axis=1) / resolution
+    return np.where(np.isfinite(v), v, 0.0)
+
+
+def plan_sectors(points, origin, resolution: float, max_range: float, world: int, leaf_origins=None,
+                 leaf_cost_in_visits: float = 230.0, n_bins: int = 8192) -> ShardPlan:
+    """Sector bounds for `world` ranks from one representative scan, such that every rank gets about the same COST:
+    voxel visits of its rays (ray casting) + leaf_cost_in_visits x the map leaves it will own (updateMap streams 4.3 KB per
+    touched leaf: about 230 voxel visits' worth of time on a B200). leaf_origins: the scan's touched leaf origins (e.g. the
+    update grid of a dry-run raycast) - without them only the visits are balanced. Deterministic."""
+    o = np.asarray(origin, dtype=np.float64)
+    cx, cy = int(np.floor(o[0] / resolution)) >> 3, int(np.floor(o[1] / resolution)) >> 3
+    p = np.asarray(points, dtype=np.float64)[:, :3]
+    ang = diamond_angle(p[:, 0] - o[0], p[:, 1] - o[1])
+    ang = np.where(np.isfinite(ang), ang, 0.0)
+    cost = np.bincount(np.minimum((ang * (n_bins / 4.0)).astype(np.int64), n_bins - 1),
+                       weights=ray_visits(points, origin, resolution, max_range), minlength=n_bins)
+    if leaf_origins is not None and len(leaf_origins):
+        lo = np.asarray(leaf_origins, dtype=np.int64)
+        la = diamond_angle((lo[:, 0] >> 3) - cx, (lo[:, 1] >> 3) - cy)
+        cost = cost + leaf_cost_in_visits * np.bincount(np.minimum((la * (n_bins / 4.0)).astype(np.int64), n_bins - 1), minlength=n_bins)
+    c = np.cumsum(cost)
+    total = float(c[-1])
+    bounds = [0.0]
+    for r in range(1, world):
+        b = int(np.searchsorted(c, total * r / world)) + 1
+        b = min(max(b, int(round(bounds[-1] * n_bins / 4.0)) + 1), n_bins - (world - r))  # strictly ascending, room for the rest
+        bounds.append(4.0 * b / n_bins)
+    return ShardPlan(1, world, cx, cy, bounds)
+
+
+def sector_rays(points, origin, plan: ShardPlan, rank: int):
+    """Indices of the rays of `rank`: those whose direction around the SENSOR falls into the rank's sector."""
+    p = np.asarray(points, dtype=np.float64)[:, :3]
+    o = np.asarray(origin, dtype=np.float64)
+    ang = diamond_angle(p[:, 0] - o[0], p[:, 1] - o[1])
+    ang = np.where(np.isfinite(ang), ang, 0.0)   # NaN points: any rank will do (they are skipped), keep them on sector 0's owner
+    return np.nonzero(sector_of(ang, plan.bounds) == rank)[0]
+
+
 def split_points(n: int, rank: int, world: int):
     """Contiguous 1/world slice of a cloud (strong-scaling mode: one scan split across ranks)."""
     per = (n + world - 1) // world

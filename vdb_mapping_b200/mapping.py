@@ -348,6 +348,22 @@ class OccupancyVDBMapping:
         self._check(self._L.vdbm_synchronize(self._h))
 
     # ---- multi-GPU plumbing (see dist.py) -------------------------------------------------------------
+    def setShardPlan(self, plan):
+        """plan: dist.ShardPlan (mode 0 = hash ownership, 1 = azimuth sectors). Same plan on every rank, before the first insert."""
+        c = np.ascontiguousarray([plan.cx, plan.cy], dtype=np.int32)
+        b = np.ascontiguousarray(plan.bounds if plan.mode else [0.0], dtype=np.float64)
+        self._check(self._L.vdbm_shard_plan_set(self._h, int(plan.mode), int(plan.n_ranks), c.ctypes.data_as(C.POINTER(C.c_int32)), _dp(b)))
+
+    def leafOwnerPlanned(self, origin, n_ranks: int) -> int:
+        o = np.ascontiguousarray(origin, dtype=np.int32)
+        return int(self._L.vdbm_leaf_owner_planned(self._h, o.ctypes.data_as(C.POINTER(C.c_int32)), n_ranks))
+
+    def mapChecksum(self):
+        """-> (order-independent 64-bit checksum of this handle's leaves, number of leaves); add over ranks mod 2^64."""
+        out = np.zeros(2, dtype=np.uint64)
+        self._check(self._L.vdbm_map_checksum(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return int(out[0]), int(out[1])
+
     def partitionUpdate(self, source_id: str, n_ranks: int):
         counts = np.zeros(n_ranks, dtype=np.uint64)
         ptr = C.c_void_p()
