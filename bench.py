@@ -351,7 +351,9 @@ def strong_cfg4_block(args, rank, world, local_rank, stream, dist):
     """BASELINE configs[3] / north_star's multi-GPU target, on every line: ONE 1,048,576-point scan (0.02 m, 100 m, bounded
     hall) per step, split over all ranks of the run (strong scaling; at N = 1 this is the single-GPU time the efficiency is
     measured against). Rays are split by azimuth sector around the sensor, the map is owned by the same sectors (ShardPlan
-    mode 1, bounds planned on rank 0 from a dry run of scan 0: equal voxel visits + weighted owned leaves), so only the leaves
+    mode 1). Two sets of bounds are planned from a dry run of scan 0, because the exchange separates the two phases: the ray
+    sectors equalise the raycast cost (voxel visits + weighted touched leaves), the ownership sectors equalise the owned
+    leaves (dist.plan_rays_and_ownership; weights fitted to measured per-rank kernel times). Only the leaves
     near the sensor and along sector borders cross NVLink. Outside the timed region the order-independent checksum of all
     shards is compared with rank 0 integrating the same full scans on one GPU."""
     import torch
@@ -361,7 +363,7 @@ def strong_cfg4_block(args, rank, world, local_rank, stream, dist):
     dev = torch.device("cuda", local_rank)
     n_steps = STRONG_WARMUP + STRONG_STEPS
     full = [scans.make_scan(cfg, k) for k in range(n_steps)]
-    plan = None
+    plan = ray_plan = None
     with torch.cuda.stream(stream):
         if world > 1:
             holder = [None]
@@ -373,11 +375,11 @@ def strong_cfg4_block(args, rank, world, local_rank, stream, dist):
                 tmp.accumulateUpdate(full[0][0], full[0][1], "s")
                 leaf_origins = np.array(tmp.exportUpdateGrid("s").origins)
                 tmp.close()
-                holder[0] = vdist.plan_sectors(full[0][0], full[0][1], c.resolution, c.max_range, world, leaf_origins=leaf_origins)
+                holder[0] = vdist.plan_rays_and_ownership(full[0][0], full[0][1], c.resolution, c.max_range, world, leaf_origins)
                 del leaf_origins
             dist.broadcast_object_list(holder, src=0)
-            plan = holder[0]
-            mine = [(np.ascontiguousarray(p[vdist.sector_rays(p, o, plan, rank)]), o) for p, o in full]
+            ray_plan, plan = holder[0]
+            mine = [(np.ascontiguousarray(p[vdist.sector_rays(p, o, ray_plan, rank)]), o) for p, o in full]
         else:
             mine = full
         resident = [torch.from_numpy(p).to(dev) for p, _ in mine]
@@ -422,6 +424,7 @@ def strong_cfg4_block(args, rank, world, local_rank, stream, dist):
         del resident
     mean = lambda x: float(sum(x) / max(1, len(x)))
     mine_stats = {"ms": ms, "rays": st1["rays"] - st0["rays"], "visits": st1["visits"] - st0["visits"],
+                  "raycast_ms": mean(ph["raycast"]), "update_ms": mean(ph["update"]),
                   "updates": st1["voxel_updates"] - st0["voxel_updates"], "chk": chk,
                   "phases": {k: mean(v) for k, v in ph.items()}, "touched": mean(touched), "owned": mean(owned)}
     allr = _gather(world, dist, mine_stats)
@@ -442,9 +445,12 @@ def strong_cfg4_block(args, rank, world, local_rank, stream, dist):
         "visits_per_sec": sum(r["visits"] for r in allr) / (ms_max * 1e-3),
         "per_rank_ms": phases,
         "leaves_touched_per_rank": [r["touched"] for r in allr], "leaves_owned_per_rank": [r["owned"] for r in allr],
+        "raycast_ms_per_rank": [r["raycast_ms"] for r in allr], "update_ms_per_rank": [r["update_ms"] for r in allr],
+        "visits_per_step_per_rank": [r["visits"] / STRONG_STEPS for r in allr],
         "map_checksum": "%016x" % (sum(r["chk"][0] for r in allr) & ((1 << 64) - 1)), "map_leaves": sum(r["chk"][1] for r in allr),
         "sharded_map_identical": identical,
-        "ownership": (None if plan is None else {"kind": "azimuth sectors (ShardPlan mode 1)", "center_leaf_xy": [plan.cx, plan.cy], "bounds": plan.bounds}),
+        "ownership": (None if plan is None else {"kind": "azimuth sectors (ShardPlan mode 1)", "center_leaf_xy": [plan.cx, plan.cy], "bounds": plan.bounds,
+                                                 "ray_sector_bounds": ray_plan.bounds}),
         "note": "device time (CUDA events) of the timed steps, max over ranks; efficiency at N GPUs = ms_per_step(N=1) / (N * ms_per_step(N)) "
                 "from the driver's own N = 1 line; sharded_map_identical: sum of the shard checksums == the same scans on one GPU (rank 0)",
     }

@@ -104,31 +104,86 @@ def ray_visits(points, origin, resolution: float, max_range: float):
     return np.where(np.isfinite(v), v, 0.0)
 
 
-def plan_sectors(points, origin, resolution: float, max_range: float, world: int, leaf_origins=None,
-                 leaf_cost_in_visits: float = 230.0, n_bins: int = 8192) -> ShardPlan:
-    """Sector bounds for `world` ranks from one representative scan, such that every rank gets about the same COST:
-    voxel visits of its rays (ray casting) + leaf_cost_in_visits x the map leaves it will own (updateMap streams 4.3 KB per
-    touched leaf: about 230 voxel visits' worth of time on a B200). leaf_origins: the scan's touched leaf origins (e.g. the
-    update grid of a dry-run raycast) - without them only the visits are balanced. Deterministic."""
+def sector_histograms(points, origin, resolution: float, max_range: float, leaf_origins=None, n_bins: int = 8192):
+    """Per azimuth bin (diamond angle, n_bins over [0, 4)) of one representative scan: the voxel visits of the rays that
+    point into the bin, and the touched leaves whose column lies in it (leaf_origins: the scan's touched leaf origins, e.g.
+    the update grid of a dry-run raycast; zeros without them). Returns (visits[n_bins], leaves[n_bins], (cx, cy) = leaf
+    column of the sensor)."""
     o = np.asarray(origin, dtype=np.float64)
     cx, cy = int(np.floor(o[0] / resolution)) >> 3, int(np.floor(o[1] / resolution)) >> 3
     p = np.asarray(points, dtype=np.float64)[:, :3]
     ang = diamond_angle(p[:, 0] - o[0], p[:, 1] - o[1])
     ang = np.where(np.isfinite(ang), ang, 0.0)
-    cost = np.bincount(np.minimum((ang * (n_bins / 4.0)).astype(np.int64), n_bins - 1),
-                       weights=ray_visits(points, origin, resolution, max_range), minlength=n_bins)
+    visits = np.bincount(np.minimum((ang * (n_bins / 4.0)).astype(np.int64), n_bins - 1),
+                         weights=ray_visits(points, origin, resolution, max_range), minlength=n_bins).astype(np.float64)
+    leaves = np.zeros(n_bins)
     if leaf_origins is not None and len(leaf_origins):
         lo = np.asarray(leaf_origins, dtype=np.int64)
         la = diamond_angle((lo[:, 0] >> 3) - cx, (lo[:, 1] >> 3) - cy)
-        cost = cost + leaf_cost_in_visits * np.bincount(np.minimum((la * (n_bins / 4.0)).astype(np.int64), n_bins - 1), minlength=n_bins)
-    c = np.cumsum(cost)
+        leaves = np.bincount(np.minimum((la * (n_bins / 4.0)).astype(np.int64), n_bins - 1), minlength=n_bins).astype(np.float64)
+    return visits, leaves, (cx, cy)
+
+
+# Cost weights fitted on B200 (8 ranks, 1M-point scans at 0.02 m, per-rank kernel times): raycast = 2.7 us per 1000 voxel
+# visits + 0.18 us per touched leaf; updateMap = 0.71 us per owned leaf.
+RAYCAST_LEAF_COST_IN_VISITS = 67.0
+TOTAL_LEAF_COST_IN_VISITS = 330.0
+
+
+def sector_costs(points, origin, resolution: float, max_range: float, leaf_origins=None,
+                 leaf_cost_in_visits: float = TOTAL_LEAF_COST_IN_VISITS, n_bins: int = 8192):
+    """visits + leaf_cost_in_visits x leaves per azimuth bin (see sector_histograms). Returns (cost[n_bins], (cx, cy))."""
+    visits, leaves, center = sector_histograms(points, origin, resolution, max_range, leaf_origins, n_bins)
+    return visits + leaf_cost_in_visits * leaves, center
+
+
+def cut_sectors(cost, center, world: int) -> ShardPlan:
+    """Sector bounds that give every rank the same share of `cost` (per azimuth bin). Deterministic."""
+    n_bins = len(cost)
+    c = np.cumsum(np.asarray(cost, dtype=np.float64) + 1e-9)
     total = float(c[-1])
-    bounds = [0.0]
+    cuts = [0]
     for r in range(1, world):
         b = int(np.searchsorted(c, total * r / world)) + 1
-        b = min(max(b, int(round(bounds[-1] * n_bins / 4.0)) + 1), n_bins - (world - r))  # strictly ascending, room for the rest
-        bounds.append(4.0 * b / n_bins)
-    return ShardPlan(1, world, cx, cy, bounds)
+        cuts.append(min(max(b, cuts[-1] + 1), n_bins - (world - r)))  # strictly ascending, room for the rest
+    return ShardPlan(1, world, int(center[0]), int(center[1]), [4.0 * b / n_bins for b in cuts])
+
+
+def refine_costs(cost, plan: ShardPlan, measured_ms):
+    """Measured feedback for the planner: rank r needed measured_ms[r] for the sector it was given. The cost of the bins of
+    every sector is rescaled so that the sector's total equals its measured time; cut_sectors() of the result moves the
+    bounds towards equal TIME (the estimate's weights are only a first guess: the DDA's speed depends on how many distinct
+    mask words it hits, the update's on the leaf count). One or two rounds converge."""
+    n_bins = len(cost)
+    cost = np.asarray(cost, dtype=np.float64)
+    edges = [int(round(b * n_bins / 4.0)) for b in plan.bounds] + [n_bins]
+    out = cost.copy()
+    for r in range(plan.n_ranks):
+        lo, hi = edges[r], edges[r + 1]
+        tot = float(cost[lo:hi].sum())
+        if tot > 0 and measured_ms[r] > 0:
+            out[lo:hi] = cost[lo:hi] * (float(measured_ms[r]) / tot)
+    return out
+
+
+def plan_sectors(points, origin, resolution: float, max_range: float, world: int, leaf_origins=None,
+                 leaf_cost_in_visits: float = TOTAL_LEAF_COST_IN_VISITS, n_bins: int = 8192) -> ShardPlan:
+    """sector_costs + cut_sectors: ONE set of bounds for `world` ranks (rays and ownership) from one representative scan."""
+    cost, center = sector_costs(points, origin, resolution, max_range, leaf_origins, leaf_cost_in_visits, n_bins)
+    return cut_sectors(cost, center, world)
+
+
+def plan_rays_and_ownership(points, origin, resolution: float, max_range: float, world: int, leaf_origins, n_bins: int = 8192):
+    """TWO sets of sector bounds from one representative scan. The exchange sits between the ray casting and updateMap, so a
+    step costs max over ranks (raycast) + max over ranks (update): both phases are balanced on their own -
+      ray bounds : equal raycast cost (voxel visits + RAYCAST_LEAF_COST_IN_VISITS x touched leaves),
+      ownership  : equal number of owned leaves (what updateMap streams).
+    Where the two disagree the leaves between the two borders cross NVLink; everything else stays local.
+    Returns (ray_plan, ownership_plan): split the rays with sector_rays(points, origin, ray_plan, rank), give the map
+    ownership_plan (setShardPlan)."""
+    visits, leaves, center = sector_histograms(points, origin, resolution, max_range, leaf_origins, n_bins)
+    return (cut_sectors(visits + RAYCAST_LEAF_COST_IN_VISITS * leaves, center, world),
+            cut_sectors(leaves + 1e-6 * visits, center, world))
 
 
 def sector_rays(points, origin, plan: ShardPlan, rank: int):
