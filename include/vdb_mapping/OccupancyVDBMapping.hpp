@@ -55,6 +55,71 @@ public:
   }
 
 protected:
+  // O:92-135: the node operations, host versions (the device runs the same arithmetic inside apply_update_kernel /
+  // overwrite_kernel / restore_state_kernel; these serve host-side callers such as createMapFromPointCloud)
+  inline bool updateFreeNode(float& voxel_value, bool& active) override
+  {
+    voxel_value += m_logodds_miss;
+    if (voxel_value < m_logodds_thres_min)
+    {
+      active = false;
+      if (voxel_value < m_min_logodds) voxel_value = m_min_logodds;
+    }
+    return true;
+  }
+  inline bool updateOccupiedNode(float& voxel_value, bool& active) override
+  {
+    voxel_value += m_logodds_hit;
+    if (voxel_value > m_logodds_thres_max)
+    {
+      active = true;
+      if (voxel_value > m_max_logodds) voxel_value = m_max_logodds;
+    }
+    return true;
+  }
+  inline bool setNodeToFree(float& voxel_value, bool& active) override
+  {
+    voxel_value = m_min_logodds;
+    active      = false;
+    return true;
+  }
+  inline bool setNodeToOccupied(float& voxel_value, bool& active) override
+  {
+    voxel_value = m_max_logodds;
+    active      = true;
+    return true;
+  }
+  inline bool setNodeState(float& voxel_value, bool& active) override
+  {
+    active = voxel_value > m_logodds_thres_max;
+    return true;
+  }
+
+  /*! O:136-174: occupied voxels from a cloud (plain transform, no +res/2 rule), optionally the inactive rest of their
+   *  bounding box set to the minimum. Runs on the host grid; the caller (loadMapFromPCD) then imports it into the device map. */
+  inline void createMapFromPointCloud(const PointCloudT::Ptr& cloud, const bool set_background, const bool clear_map) override
+  {
+    if (clear_map) m_vdb_grid->clear();
+    typename GridT::Accessor acc = m_vdb_grid->getAccessor();
+    for (const auto& point : cloud->points)
+    {
+      const openvdb::Vec3d index_coord = m_vdb_grid->worldToIndex(openvdb::Vec3d(point.x, point.y, point.z));
+      acc.setValueOn(openvdb::Coord::floor(index_coord), m_max_logodds);
+    }
+    openvdb::CoordBBox bbox;
+    if (set_background && detail::Backend<float>::activeBBox(*m_vdb_grid, bbox))
+    {
+      for (int x = bbox.min().x(); x <= bbox.max().x(); ++x)
+        for (int y = bbox.min().y(); y <= bbox.max().y(); ++y)
+          for (int z = bbox.min().z(); z <= bbox.max().z(); ++z)
+          {
+            const openvdb::Coord c(x, y, z);
+            if (!acc.isValueOn(c)) acc.setValueOff(c, m_min_logodds);
+          }
+    }
+    detail::Backend<float>::prune(*m_vdb_grid);
+  }
+
   // O:179-199 (kept for subclasses that read them; the device holds the authoritative copies)
   float m_logodds_hit = 0, m_logodds_miss = 0, m_logodds_thres_min = 0, m_logodds_thres_max = 0, m_max_logodds = 0, m_min_logodds = 0;
 };

@@ -19,8 +19,11 @@
 // raycastPointCloud, updateMap, getGrid, getMapSection*, applyMapSection*, createIndexBoundingBox, addInputSource,
 // setConfig, resetMap, getMapMutex, worldToIndex, addPointsToGrid, removePointsFromGrid, addArtificialAreas,
 // restoreMapIntegrity, plus createUpdate / applyUpdate (remote-mapping deltas; see vdbm_b200.h for the level semantics).
-// Persistence, morphology, raytrace and fast_mode are out of scope of this build and are not declared (a translation
-// unit that needs them keeps using the reference).
+// The remaining public members of the reference are host code on the mirror grid: saveMap /
+// saveMapToPCD / loadMap / loadMapFromPCD (a loaded map is imported into the device map with vdbm_map_import),
+// morphological*Map, the zstd codec and gridToByteArray / byteArrayToGrid, createWorldBoundingBox, getMapSection<T>,
+// addArtificialPolygon / addArtificialWall, castRayIntoGrid (vdbm_cast_index_rays), raytrace and fast_mode
+// (vdbm_raytrace / the fast raycast; OpenVDB's VolumeRayIntersector is restated).
 // The device arithmetic implements the OccupancyVDBMapping node operations (TData = float); the protected virtual
 // update*Node hooks of the reference cannot be honoured on the device and are therefore not part of this class.
 #ifndef VDB_MAPPING_VDB_MAPPING_H_INCLUDED
@@ -30,12 +33,15 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <ctime>
+#include <iomanip>
 #include <iostream>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <optional>
 #include <shared_mutex>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -96,6 +102,7 @@ public:
     : m_resolution(resolution)
     , m_config_set(false)
   {
+    openvdb::initialize(); // R:122 (the grid types of this path are OpenVDB's own FloatGrid / a bool Tree4<1,4,3>)
     m_map_mutex = std::make_shared<std::shared_mutex>();
     vdbm_params p{};
     p.resolution            = resolution;
@@ -226,7 +233,8 @@ public:
     return true;
   }
 
-  /*! R:466-539 (fast_mode / intersector argument not supported). The rays are cast on the device into a scratch
+  /*! R:466-539 (fast_mode follows Config::fast_mode on the device; the optional host intersector argument has no meaning
+   *  here and is not declared). The rays are cast on the device into a scratch
    *  source; the resulting update leaves are then merged into the grid behind `update_grid_acc`. */
   bool raycastPointCloud(const typename PointCloudT::ConstPtr& cloud,
                          const Eigen::Matrix<double, 3, 1>& origin,
@@ -311,23 +319,8 @@ public:
                                             const Eigen::Matrix<double, 3, 1>& max_boundary,
                                             const Eigen::Matrix<double, 4, 4>& map_to_reference_tf) const
   {
-    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-    bool first  = true;
-    for (int k = 0; k < 8; ++k)
-    {
-      const float p[3] = {static_cast<float>((k & 4) ? max_boundary.x() : min_boundary.x()),
-                          static_cast<float>((k & 2) ? max_boundary.y() : min_boundary.y()),
-                          static_cast<float>((k & 1) ? max_boundary.z() : min_boundary.z())};
-      // pcl::transformPointCloud with a double matrix: float(M(r,0)*x + M(r,1)*y + M(r,2)*z + M(r,3))
-      for (int r = 0; r < 3; ++r)
-      {
-        const float q = static_cast<float>(map_to_reference_tf(r, 0) * p[0] + map_to_reference_tf(r, 1) * p[1] +
-                                           map_to_reference_tf(r, 2) * p[2] + map_to_reference_tf(r, 3));
-        if (first || q < lo[r]) lo[r] = q;
-        if (first || q > hi[r]) hi[r] = q;
-      }
-      first = false;
-    }
+    float lo[3], hi[3];
+    transformedCorners(min_boundary, max_boundary, map_to_reference_tf, lo, hi);
     const double inv = 1.0 / m_resolution;
     openvdb::Vec3d mn(lo[0] * inv, lo[1] * inv, lo[2] * inv), mx(hi[0] * inv, hi[1] * inv, hi[2] * inv);
     return openvdb::CoordBBox(openvdb::Coord::floor(mn), openvdb::Coord::floor(mx));
@@ -502,6 +495,210 @@ public:
     return change;
   }
 
+
+  // ------------------------------------------------------------------------------------------------------------------
+  // Persistence (R:193-307). Host code on the mirror grid; the device map is the authority, so the mirror is brought up
+  // to date first and a loaded grid is imported into the device map.
+  // ------------------------------------------------------------------------------------------------------------------
+  /*! R:193-211 */
+  bool saveMap() const
+  {
+    const std::string map_name = m_map_directory_path + timestampString() + "_map.vdb";
+    std::cout << map_name << std::endl;
+    typename GridT::Ptr grid = getGrid();
+    std::shared_lock map_lock(*m_map_mutex);
+    return BackendT::writeGridFile(map_name, grid);
+  }
+
+  /*! R:218-256: the centres of all active voxels as a PCD file */
+  bool saveMapToPCD()
+  {
+    const std::string pcd_path = m_map_directory_path + timestampString() + "_active_values_map.pcd";
+    typename PointCloudT::Ptr cloud(new PointCloudT);
+    typename GridT::Ptr grid = getGrid();
+    {
+      std::shared_lock map_lock(*m_map_mutex);
+      cloud->points.reserve(grid->activeVoxelCount());
+      BackendT::forEachActiveVoxel(*grid, [&](const openvdb::Coord& c, const TData&) {
+        openvdb::Vec3d w = grid->indexToWorld(c);
+        cloud->points.emplace_back(static_cast<float>(w.x() + 0.5 * m_resolution), static_cast<float>(w.y() + 0.5 * m_resolution),
+                                   static_cast<float>(w.z() + 0.5 * m_resolution));
+      });
+    }
+    cloud->points.shrink_to_fit();
+    cloud->width  = static_cast<std::uint32_t>(cloud->points.size());
+    cloud->height = 1;
+    if (!BackendT::savePCD(pcd_path, *cloud))
+    {
+      std::cerr << "Could not write PCD file." << std::endl;
+      return false;
+    }
+    std::cout << "Wrote pcd to: " << pcd_path << std::endl;
+    return true;
+  }
+
+  /*! R:263-284: m_vdb_grid is replaced by the (last) grid of the file; here the device map is replaced with it too */
+  bool loadMap(const std::string& file_path)
+  {
+    typename GridT::Ptr loaded = BackendT::readGridFile(file_path);
+    if (!loaded) return false;
+    std::unique_lock map_lock(*m_map_mutex);
+    m_vdb_grid->clear();
+    m_vdb_grid = loaded;
+    uploadMirrorLocked();
+    return true;
+  }
+
+  /*! R:295-307 */
+  bool loadMapFromPCD(const std::string& file_path, const bool set_background, const bool clear_map)
+  {
+    typename PointCloudT::Ptr cloud(new PointCloudT);
+    if (!BackendT::loadPCD(file_path, *cloud))
+    {
+      std::cerr << "Could not open PCD file" << std::endl;
+      return false;
+    }
+    if (!clear_map) getGrid(); // the points are added to the CURRENT map: the mirror must hold it
+    std::unique_lock map_lock(*m_map_mutex);
+    createMapFromPointCloud(cloud, set_background, clear_map);
+    uploadMirrorLocked();
+    return true;
+  }
+
+  /*! R:550-566 for one ray given by voxel indices, marked into the grid behind `update_grid_acc` (device DDA, same fp64
+   *  stepping as the scan path; the host accessor receives the result). */
+  void castRayIntoGrid(const openvdb::Coord& ray_origin_index, const openvdb::Coord& ray_end_index,
+                       typename UpdateGridT::Accessor& update_grid_acc) const
+  {
+    if (!m_device_map) return;
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    const_cast<VDBMapping*>(this)->ensureScratchSource();
+    ScratchClear clear_on_exit{m_device_map};
+    const std::int32_t ray[6] = {ray_origin_index.x(), ray_origin_index.y(), ray_origin_index.z(), ray_end_index.x(), ray_end_index.y(), ray_end_index.z()};
+    if (report(vdbm_cast_index_rays(m_device_map, kScratchSource, 1, ray)) != VDBM_OK) return;
+    vdbm_leafset* ls = nullptr;
+    if (report(vdbm_update_export(m_device_map, kScratchSource, &ls)) != VDBM_OK) return;
+    mergeIntoAccessor(ls, update_grid_acc);
+    vdbm_leafset_free(ls);
+  }
+
+  /*! R:643-664 */
+  void raytrace(const openvdb::Vec3d& ray_origin_world, const openvdb::Vec3d& ray_direction, const double max_ray_lengths, bool& success,
+                openvdb::Vec3d& end_point)
+  {
+    std::vector<openvdb::Vec3d> origins = {ray_origin_world}, directions = {ray_direction}, end_points;
+    std::vector<double> lengths = {max_ray_lengths};
+    std::vector<bool> successes;
+    raytrace(origins, directions, lengths, successes, end_points);
+    success   = successes[0];
+    end_point = end_points[0];
+  }
+
+  /*! R:675-721: first active map voxel along every ray (batch, one kernel launch: vdbm_raytrace) */
+  void raytrace(const std::vector<openvdb::Vec3d>& ray_origins_world, const std::vector<openvdb::Vec3d>& ray_directions,
+                const std::vector<double>& max_ray_lengths, std::vector<bool>& successes, std::vector<openvdb::Vec3d>& end_points)
+  {
+    const std::size_t n = ray_origins_world.size();
+    successes.assign(n, false);
+    end_points.resize(n);
+    if (!m_device_map || n == 0) return;
+    std::vector<double> o(3 * n), d(3 * n), e(3 * n);
+    std::vector<std::int32_t> ok(n);
+    for (std::size_t i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) { o[3 * i + k] = ray_origins_world[i][k]; d[3 * i + k] = ray_directions[i][k]; }
+    std::shared_lock map_lock(*m_map_mutex);
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    if (report(vdbm_raytrace(m_device_map, n, o.data(), d.data(), max_ray_lengths.data(), ok.data(), e.data())) != VDBM_OK) return;
+    for (std::size_t i = 0; i < n; ++i)
+    {
+      successes[i]  = ok[i] != 0;
+      end_points[i] = openvdb::Vec3d(e[3 * i], e[3 * i + 1], e[3 * i + 2]);
+    }
+  }
+
+  /*! R:810-847: world bounding box of a box given in a reference frame (corners stored as float like pcl::PointXYZ,
+   *  transformed with the double matrix, min / max taken) */
+  openvdb::BBoxd createWorldBoundingBox(const Eigen::Matrix<double, 3, 1>& min_boundary, const Eigen::Matrix<double, 3, 1>& max_boundary,
+                                        const Eigen::Matrix<double, 4, 4>& map_to_reference_tf) const
+  {
+    float lo[3], hi[3];
+    transformedCorners(min_boundary, max_boundary, map_to_reference_tf, lo, hi);
+    return openvdb::BBoxd(openvdb::Vec3d(lo[0], lo[1], lo[2]), openvdb::Vec3d(hi[0], hi[1], hi[2]));
+  }
+
+  /*! R:921-960 */
+  template <typename TResultGrid>
+  typename TResultGrid::Ptr getMapSection(const Eigen::Matrix<double, 3, 1>& min_boundary, const Eigen::Matrix<double, 3, 1>& max_boundary,
+                                          const Eigen::Matrix<double, 4, 4>& map_to_reference_tf, const bool full_grid = false) const
+  {
+    if constexpr (std::is_same<TResultGrid, UpdateGridT>::value)
+      return getMapSectionUpdateGrid(min_boundary, max_boundary, map_to_reference_tf, full_grid);
+    else
+      return getMapSectionGrid(min_boundary, max_boundary, map_to_reference_tf, full_grid);
+  }
+
+  /*! R:1094-1147 on a host grid (OpenVDB's tools with OpenVDB installed, a 26-neighbourhood restatement otherwise) */
+  template <typename TGrid>
+  void morphologicalCloseMap(typename TGrid::Ptr grid, int iterations)
+  {
+    morphologicalDilateMap<TGrid>(grid, iterations);
+    morphologicalErodeMap<TGrid>(grid, iterations);
+  }
+  template <typename TGrid>
+  void morphologicalOpenMap(typename TGrid::Ptr grid, int iterations)
+  {
+    morphologicalErodeMap<TGrid>(grid, iterations);
+    morphologicalDilateMap<TGrid>(grid, iterations);
+  }
+  template <typename TGrid>
+  void morphologicalDilateMap(typename TGrid::Ptr grid, int iterations) { BackendT::dilateActive(*grid, iterations); }
+  template <typename TGrid>
+  void morphologicalErodeMap(typename TGrid::Ptr grid, int iterations) { BackendT::erodeActive(*grid, iterations); }
+
+  /*! R:1198-1207 */
+  void addArtificialPolygon(const std::vector<Eigen::Matrix<double, 4, 1> >& polygon, const double negative_height, const double positive_height)
+  {
+    if (!m_device_map || polygon.empty()) return;
+    const std::uint32_t count = static_cast<std::uint32_t>(polygon.size());
+    std::vector<double> xyz;
+    for (const auto& p : polygon) xyz.insert(xyz.end(), {p[0], p[1], p[2]});
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_artificial_walls_add(m_device_map, 1, &count, xyz.data(), negative_height, positive_height, /*closed=*/1));
+    m_artificial_areas_present = true;
+  }
+
+  /*! R:1217-1236 */
+  void addArtificialWall(const Eigen::Matrix<double, 4, 1>& start, const Eigen::Matrix<double, 4, 1>& end, const double negative_height,
+                         const double positive_height)
+  {
+    if (!m_device_map) return;
+    const std::uint32_t count = 2;
+    const double xyz[6]       = {start[0], start[1], start[2], end[0], end[1], end[2]};
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_artificial_walls_add(m_device_map, 1, &count, xyz, negative_height, positive_height, /*closed=*/0));
+    m_artificial_areas_present = true;
+  }
+
+  /*! R:1246-1268 */
+  std::vector<uint8_t> compressString(const std::string& string) const { return detail::zstdCompress(string, m_compression_level); }
+  /*! R:1277-1300 */
+  std::string decompressByteArray(const std::vector<uint8_t>& byte_array) const { return detail::zstdDecompress(byte_array); }
+  /*! R:1310-1317 (bytes are OpenVDB's stream format only when OpenVDB is installed, see detail/host_io.hpp) */
+  template <typename TGrid>
+  std::vector<uint8_t> gridToByteArray(typename TGrid::Ptr grid)
+  {
+    return compressString(BackendT::template gridToString<TGrid>(grid));
+  }
+  /*! R:1328-1338 */
+  template <typename TGrid>
+  typename TGrid::Ptr byteArrayToGrid(std::vector<uint8_t> byte_array)
+  {
+    return BackendT::template stringToGrid<TGrid>(decompressByteArray(byte_array));
+  }
+
+  /*! R:1436-1449. fast_mode keeps no host-side intersector: the fast raycast probes the device map directly. */
+  void updateVolumeRayIntersectors() {}
+
   /*! R:1343 */
   std::shared_ptr<std::shared_mutex> getMapMutex() { return m_map_mutex; }
 
@@ -548,6 +745,11 @@ public:
     m_fast_mode           = config.fast_mode;
     m_accumulation_period = (int)(config.accumulation_period * 1000);
     m_config_set          = true;
+    if (m_device_map)
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex);
+      report(vdbm_set_fast_mode(m_device_map, m_fast_mode ? 1 : 0)); // R:333 / R:520: castRayIntoGridFast from now on
+    }
   }
 
   /*! Counters of the device path (rays, visits, voxel updates, kernel times); not part of the reference API. */
@@ -568,6 +770,71 @@ protected:
     if (rc != VDBM_OK && rc != VDBM_ERR_UNKNOWN_SOURCE && m_device_map)
       std::cerr << "vdb_mapping (B200): " << vdbm_last_error(m_device_map) << std::endl;
     return rc;
+  }
+
+
+  static std::string timestampString()
+  {
+    auto timestamp     = std::chrono::system_clock::now();
+    std::time_t now_tt = std::chrono::system_clock::to_time_t(timestamp);
+    std::tm tm         = *std::localtime(&now_tt);
+    std::stringstream sstime;
+    sstime << std::put_time(&tm, "%Y-%m-%d_%H-%M-%S");
+    return sstime.str();
+  }
+
+  /*! R:815-843: the 8 corners as float points, transformed (pcl::transformPointCloud with a double matrix:
+   *  float(M(r,0)*x + M(r,1)*y + M(r,2)*z + M(r,3))), then min / max per axis */
+  static void transformedCorners(const Eigen::Matrix<double, 3, 1>& min_boundary, const Eigen::Matrix<double, 3, 1>& max_boundary,
+                                 const Eigen::Matrix<double, 4, 4>& tf, float lo[3], float hi[3])
+  {
+    bool first = true;
+    for (int k = 0; k < 8; ++k)
+    {
+      const float p[3] = {static_cast<float>((k & 4) ? max_boundary.x() : min_boundary.x()),
+                          static_cast<float>((k & 2) ? max_boundary.y() : min_boundary.y()),
+                          static_cast<float>((k & 1) ? max_boundary.z() : min_boundary.z())};
+      for (int r = 0; r < 3; ++r)
+      {
+        const float q = static_cast<float>(tf(r, 0) * p[0] + tf(r, 1) * p[1] + tf(r, 2) * p[2] + tf(r, 3));
+        if (first || q < lo[r]) lo[r] = q;
+        if (first || q > hi[r]) hi[r] = q;
+      }
+      first = false;
+    }
+  }
+
+  /*! the whole host grid becomes the device map (after loadMap / createMapFromPointCloud; caller holds the map lock) */
+  void uploadMirrorLocked()
+  {
+    if (!m_device_map) return;
+    std::vector<std::int32_t> origins;
+    std::vector<std::uint64_t> active;
+    std::vector<float> values;
+    BackendT::forEachMapLeaf(*m_vdb_grid, [&](const std::int32_t o[3], const float* v, const std::uint64_t* a) {
+      origins.insert(origins.end(), o, o + 3);
+      values.insert(values.end(), v, v + 512);
+      active.insert(active.end(), a, a + 8);
+    });
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    report(vdbm_map_import(m_device_map, origins.size() / 3, origins.data(), active.data(), values.data(), 1));
+    vdbm_leafset* ls = nullptr; // nothing is dirty now: the mirror already equals the device map
+    if (vdbm_map_export(m_device_map, 1, &ls) == VDBM_OK) vdbm_leafset_free(ls);
+    m_mirror_stale = false;
+  }
+
+  // R:1472-1476: the node operations of the reference. On the B200 path updateMap runs them inside apply_update_kernel
+  // for the occupancy semantics (TData = float); the virtuals stay for host-side users (createMapFromPointCloud,
+  // subclasses that call them directly). Overriding them does NOT change what the device computes.
+  virtual bool updateFreeNode(TData& /*voxel_value*/, bool& /*active*/) { return false; }
+  virtual bool updateOccupiedNode(TData& /*voxel_value*/, bool& /*active*/) { return false; }
+  virtual bool setNodeToFree(TData& /*voxel_value*/, bool& /*active*/) { return false; }
+  virtual bool setNodeToOccupied(TData& /*voxel_value*/, bool& /*active*/) { return false; }
+  virtual bool setNodeState(TData& /*voxel_value*/, bool& /*active*/) { return false; }
+  /*! R:1478-1480 */
+  virtual void createMapFromPointCloud(const typename PointCloudT::Ptr& /*cloud*/, const bool /*set_background*/, const bool /*clear_map*/)
+  {
+    std::cerr << "Not implemented for data type" << std::endl;
   }
 
   /*! after a device-side map write (caller holds m_device_mutex) */
@@ -595,7 +862,7 @@ protected:
     }
   }
 
-  void mergeIntoAccessor(vdbm_leafset* ls, typename UpdateGridT::Accessor& acc)
+  void mergeIntoAccessor(vdbm_leafset* ls, typename UpdateGridT::Accessor& acc) const
   {
     const std::uint64_t n = vdbm_leafset_size(ls);
     for (std::uint64_t i = 0; i < n; ++i)
@@ -682,6 +949,7 @@ protected:
   mutable bool m_mirror_stale = false;
   bool m_scratch_ready        = false;
   bool m_artificial_areas_present = false; // R:1529
+  int m_compression_level         = 1;     // R:1524
   mutable std::mutex m_device_mutex; // serialises calls into the (thread-compatible) C ABI handle
   mutable std::shared_ptr<std::shared_mutex> m_map_mutex;
   mutable std::atomic<bool> m_map_mutex_requested{false};

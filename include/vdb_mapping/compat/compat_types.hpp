@@ -59,6 +59,11 @@ struct Matrix
     static_assert(R * C == 3, "3-vector constructor");
     m = {a, b, c};
   }
+  Matrix(T a, T b, T c, T d)
+  {
+    static_assert(R * C == 4, "4-vector constructor");
+    m = {a, b, c, d};
+  }
   T& operator()(int r, int c) { return m[r * C + c]; }
   const T& operator()(int r, int c) const { return m[r * C + c]; }
   T& operator[](int i) { return m[i]; }
@@ -88,6 +93,9 @@ struct Vec3d
   double z() const { return v[2]; }
   double& operator[](int i) { return v[i]; }
   double operator[](int i) const { return v[i]; }
+  Vec3d operator+(const Vec3d& o) const { return Vec3d(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
+  Vec3d operator*(double s) const { return Vec3d(v[0] * s, v[1] * s, v[2] * s); }
+  double length() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 };
 struct Coord
 {
@@ -98,6 +106,8 @@ struct Coord
   Int32 y() const { return c[1]; }
   Int32 z() const { return c[2]; }
   Int32 operator[](int i) const { return c[i]; }
+  Coord operator+(const Coord& o) const { return Coord(c[0] + o.c[0], c[1] + o.c[1], c[2] + o.c[2]); }
+  Coord offsetBy(Int32 dx, Int32 dy, Int32 dz) const { return Coord(c[0] + dx, c[1] + dy, c[2] + dz); }
   bool operator==(const Coord& o) const { return c[0] == o.c[0] && c[1] == o.c[1] && c[2] == o.c[2]; }
   bool operator!=(const Coord& o) const { return !(*this == o); }
   bool operator<(const Coord& o) const
@@ -113,6 +123,12 @@ struct CoordBBox
   CoordBBox(const Coord& a, const Coord& b) : mn(a), mx(b) {}
   const Coord& min() const { return mn; }
   const Coord& max() const { return mx; }
+  bool hasOverlap(const CoordBBox& b) const
+  {
+    for (int i = 0; i < 3; ++i)
+      if (mx[i] < b.mn[i] || mn[i] > b.mx[i]) return false;
+    return true;
+  }
   bool isInside(const Coord& p) const
   {
     for (int i = 0; i < 3; ++i)
@@ -198,6 +214,14 @@ public:
       l.set(n, v);
       l.active[n >> 6] |= std::uint64_t(1) << (n & 63);
     }
+    void setValueOff(const Coord& xyz, const ValueT& v)
+    {
+      LeafT& l         = m_grid->touchLeaf(xyz);
+      const unsigned n = offset(xyz);
+      l.set(n, v);
+      l.active[n >> 6] &= ~(std::uint64_t(1) << (n & 63));
+    }
+    void setValueOnly(const Coord& xyz, const ValueT& v) { m_grid->touchLeaf(xyz).set(offset(xyz), v); }
     void setActiveState(const Coord& xyz, bool on)
     {
       LeafT& l         = m_grid->touchLeaf(xyz);

@@ -9,8 +9,12 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
+
+#include "vdb_mapping/detail/host_io.hpp"
 
 namespace vdb_mapping {
 namespace detail {
@@ -49,9 +53,13 @@ inline void parallelFor(std::uint64_t n, F&& f)
 // ------------------------------------------------------------------------------------------------------
 #include <Eigen/Core>
 #include <Eigen/Geometry>
+#include <openvdb/io/Stream.h>
 #include <openvdb/openvdb.h>
+#include <openvdb/tools/Morphology.h>
+#include <pcl/io/pcd_io.h>
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
+#include <sstream>
 
 namespace vdb_mapping {
 namespace detail {
@@ -157,6 +165,73 @@ struct Backend
     g.insertMeta("bb_min", openvdb::Vec3DMetadata(openvdb::Vec3d(mn[0], mn[1], mn[2])));
     g.insertMeta("bb_max", openvdb::Vec3DMetadata(openvdb::Vec3d(mx[0], mx[1], mx[2])));
   }
+
+  // ---- host-side grid services behind the persistence / morphology / codec members (not on the scan path) ----
+  static void setVoxel(GridT& grid, const openvdb::Coord& c, const TData& v, bool on)
+  {
+    auto acc = grid.getAccessor();
+    if (on) acc.setValueOn(c, v);
+    else acc.setValueOff(c, v);
+  }
+  template <typename F>
+  static void forEachActiveVoxel(const GridT& grid, F&& f)
+  {
+    for (auto it = grid.cbeginValueOn(); it; ++it) f(it.getCoord(), it.getValue());
+  }
+  static bool activeBBox(const GridT& grid, openvdb::CoordBBox& bb)
+  {
+    bb = grid.evalActiveVoxelBoundingBox();
+    return !bb.empty();
+  }
+  static void prune(GridT& grid) { grid.pruneGrid(); }
+  template <typename G>
+  static void dilateActive(G& grid, int iterations) // R:1122-1129
+  {
+    openvdb::tools::dilateActiveValues(grid.tree(), iterations, openvdb::tools::NN_FACE_EDGE_VERTEX, openvdb::tools::EXPAND_TILES, true);
+  }
+  template <typename G>
+  static void erodeActive(G& grid, int iterations) // R:1139-1146
+  {
+    openvdb::tools::erodeActiveValues(grid.tree(), iterations, openvdb::tools::NN_FACE_EDGE_VERTEX, openvdb::tools::EXPAND_TILES, true);
+  }
+  static bool writeGridFile(const std::string& path, const typename GridT::Ptr& grid) // R:201-208
+  {
+    openvdb::io::File file_handle(path);
+    openvdb::GridPtrVec grids;
+    grids.push_back(grid);
+    file_handle.write(grids);
+    file_handle.close();
+    return true;
+  }
+  static typename GridT::Ptr readGridFile(const std::string& path) // R:265-279: the LAST grid of the file
+  {
+    openvdb::io::File file_handle(path);
+    file_handle.open();
+    openvdb::GridBase::Ptr base_grid;
+    for (openvdb::io::File::NameIterator name_iter = file_handle.beginName(); name_iter != file_handle.endName(); ++name_iter)
+      base_grid = file_handle.readGrid(name_iter.gridName());
+    file_handle.close();
+    return openvdb::gridPtrCast<GridT>(base_grid);
+  }
+  template <typename G>
+  static std::string gridToString(const typename G::Ptr& grid) // R:1312-1316
+  {
+    openvdb::GridPtrVec grids;
+    grids.push_back(grid);
+    std::ostringstream oss(std::ios_base::binary);
+    openvdb::io::Stream(oss).write(grids);
+    return oss.str();
+  }
+  template <typename G>
+  static typename G::Ptr stringToGrid(const std::string& bytes) // R:1330-1337
+  {
+    std::istringstream iss(bytes);
+    openvdb::io::Stream strm(iss);
+    openvdb::GridPtrVecPtr grids = strm.getGrids();
+    return openvdb::gridPtrCast<G>(grids->front());
+  }
+  static bool savePCD(const std::string& path, const PointCloudT& cloud) { return pcl::io::savePCDFile(path, cloud) == 0; }
+  static bool loadPCD(const std::string& path, PointCloudT& cloud) { return pcl::io::loadPCDFile<PointT>(path, cloud) != -1; }
 };
 
 } // namespace detail
@@ -249,6 +324,130 @@ struct Backend
     g.insertMeta("bb_min", openvdb::Vec3d(mn[0], mn[1], mn[2]));
     g.insertMeta("bb_max", openvdb::Vec3d(mx[0], mx[1], mx[2]));
   }
+
+  // ---- host-side grid services behind the persistence / morphology / codec members (not on the scan path) ----
+  static void setVoxel(GridT& grid, const openvdb::Coord& c, const TData& v, bool on)
+  {
+    auto acc = grid.getAccessor();
+    if (on) acc.setValueOn(c, v);
+    else acc.setValueOff(c, v);
+  }
+  template <typename G, typename F>
+  static void forEachActiveVoxelOf(const G& grid, F&& f)
+  {
+    for (auto& kv : grid.leaves())
+      for (unsigned n = 0; n < 512; ++n)
+        if ((kv.second.active[n >> 6] >> (n & 63)) & 1u)
+          f(openvdb::Coord(kv.first[0] + int(n >> 6), kv.first[1] + int((n >> 3) & 7), kv.first[2] + int(n & 7)), kv.second.get(n));
+  }
+  template <typename F>
+  static void forEachActiveVoxel(const GridT& grid, F&& f) { forEachActiveVoxelOf(grid, f); }
+  static bool activeBBox(const GridT& grid, openvdb::CoordBBox& bb)
+  {
+    bool any = false;
+    forEachActiveVoxel(grid, [&](const openvdb::Coord& c, const TData&) {
+      if (!any) { bb = openvdb::CoordBBox(c, c); any = true; return; }
+      for (int k = 0; k < 3; ++k)
+      {
+        if (c[k] < bb.mn.c[k]) bb.mn.c[k] = c[k];
+        if (c[k] > bb.mx.c[k]) bb.mx.c[k] = c[k];
+      }
+    });
+    return any;
+  }
+  static void prune(GridT&) {} // the stand-in grid has no tiles to collapse into
+  // tools::dilateActiveValues(NN_FACE_EDGE_VERTEX): every voxel with an active 26-neighbour becomes active (value untouched)
+  template <typename G>
+  static void dilateActive(G& grid, int iterations)
+  {
+    for (int it = 0; it < iterations; ++it)
+    {
+      std::vector<openvdb::Coord> on;
+      forEachActiveVoxelOf(grid, [&](const openvdb::Coord& c, const typename G::ValueType&) { on.push_back(c); });
+      auto acc = grid.getAccessor();
+      for (const auto& c : on)
+        for (int dx = -1; dx <= 1; ++dx)
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int dz = -1; dz <= 1; ++dz)
+              if (dx || dy || dz) acc.setActiveState(c.offsetBy(dx, dy, dz), true);
+    }
+  }
+  // tools::erodeActiveValues(NN_FACE_EDGE_VERTEX): an active voxel with an inactive 26-neighbour becomes inactive
+  template <typename G>
+  static void erodeActive(G& grid, int iterations)
+  {
+    for (int it = 0; it < iterations; ++it)
+    {
+      std::vector<openvdb::Coord> off;
+      auto acc = grid.getAccessor();
+      forEachActiveVoxelOf(grid, [&](const openvdb::Coord& c, const typename G::ValueType&) {
+        for (int dx = -1; dx <= 1; ++dx)
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int dz = -1; dz <= 1; ++dz)
+              if ((dx || dy || dz) && !acc.isValueOn(c.offsetBy(dx, dy, dz))) { off.push_back(c); return; }
+      });
+      for (const auto& c : off) acc.setActiveState(c, false);
+    }
+  }
+  // flat leaf stream of host_io.hpp (NOT the .vdb format, see there)
+  static std::string gridToStringImpl(const GridT& grid)
+  {
+    return leafStreamWrite(grid, 0u, grid.leafCount(), [&](auto&& put) {
+      for (auto& kv : grid.leaves()) { put(kv.first.c, 12); put(kv.second.values, 2048); put(kv.second.active, 64); }
+    });
+  }
+  static std::string gridToStringImpl(const UpdateGridT& grid)
+  {
+    return leafStreamWrite(grid, 1u, grid.leafCount(), [&](auto&& put) {
+      for (auto& kv : grid.leaves()) { put(kv.first.c, 12); put(kv.second.active, 64); put(kv.second.valmask, 64); }
+    });
+  }
+  template <typename G>
+  static std::string gridToString(const typename G::Ptr& grid) { return gridToStringImpl(*grid); }
+  template <typename G>
+  static typename G::Ptr stringToGrid(const std::string& bytes)
+  {
+    constexpr std::uint32_t want = std::is_same<typename G::ValueType, bool>::value ? 1u : 0u;
+    typename G::Ptr g = G::create(typename G::ValueType());
+    if (bytes.size() < 76 || bytes.compare(0, 8, "VDBMLEAF") != 0) return g;
+    const char* p = bytes.data() + 8;
+    std::uint32_t kind; double vs; std::uint64_t n; double bb[6];
+    std::memcpy(&kind, p, 4); p += 4; std::memcpy(&vs, p, 8); p += 8; std::memcpy(&n, p, 8); p += 8; std::memcpy(bb, p, 48); p += 48;
+    if (kind != want) return g;
+    g->setVoxelSize(vs);
+    g->insertMeta("bb_min", openvdb::Vec3d(bb[0], bb[1], bb[2]));
+    g->insertMeta("bb_max", openvdb::Vec3d(bb[3], bb[4], bb[5]));
+    const std::size_t rec = 12 + (want ? 128 : 2112);
+    if (bytes.size() < 76 + n * rec) return g;
+    for (std::uint64_t i = 0; i < n; ++i, p += rec)
+    {
+      std::int32_t o[3];
+      std::memcpy(o, p, 12);
+      auto& leaf = g->touchLeaf(openvdb::Coord(o[0], o[1], o[2]));
+      readLeafPayload(leaf, p + 12);
+    }
+    return g;
+  }
+  static void readLeafPayload(openvdb::HostLeaf<float>& leaf, const char* p) { std::memcpy(leaf.values, p, 2048); std::memcpy(leaf.active, p + 2048, 64); }
+  static void readLeafPayload(openvdb::HostLeaf<bool>& leaf, const char* p) { std::memcpy(leaf.active, p, 64); std::memcpy(leaf.valmask, p + 64, 64); }
+  static bool writeGridFile(const std::string& path, const typename GridT::Ptr& grid)
+  {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return false;
+    const std::string bytes = gridToString<GridT>(grid);
+    f.write(bytes.data(), std::streamsize(bytes.size()));
+    return bool(f);
+  }
+  static typename GridT::Ptr readGridFile(const std::string& path)
+  {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return nullptr;
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return stringToGrid<GridT>(ss.str());
+  }
+  static bool savePCD(const std::string& path, const PointCloudT& cloud) { return writePCD(path, cloud); }
+  static bool loadPCD(const std::string& path, PointCloudT& cloud) { return readPCD(path, cloud); }
 };
 
 } // namespace detail

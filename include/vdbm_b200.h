@@ -204,11 +204,36 @@ int vdbm_points_set(vdbm_map* map, const void* points, uint64_t n, uint64_t stri
  * those voxels active (V:785-789). */
 int vdbm_artificial_areas_add(vdbm_map* map, uint64_t n_polygons, const uint32_t* counts, const double* xyz, double negative_height,
                               double positive_height);
+/* addArtificialPolygon V:1198-1207 (closed != 0: every polyline also gets its closing edge) / addArtificialWall V:1217-1236
+ * (closed == 0, counts[p] == 2): walls added to the artificial-area grid WITHOUT the restoreMapIntegrity that
+ * addArtificialAreas runs first. */
+int vdbm_artificial_walls_add(vdbm_map* map, uint64_t n_polylines, const uint32_t* counts, const double* xyz, double negative_height,
+                              double positive_height, int closed);
 /* restoreMapIntegrity V:1152-1166: active = (value > thres_max) for every artificial-area voxel, then the grid is cleared. */
 int vdbm_map_integrity_restore(vdbm_map* map);
 /* the artificial-area grid (m_artificial_area_grid V:1493) as a bool leaf set */
 int vdbm_artificial_export(vdbm_map* map, vdbm_leafset** out);
 
+/* loadMap V:263-284 / loadMapFromPCD V:295-307 (device part): the given leaves (OpenVDB layout) become map leaves, leaf for
+ * leaf (values and active mask replace what the map held there). replace != 0 first forgets every map leaf, like the
+ * reference replacing m_vdb_grid. */
+int vdbm_map_import(vdbm_map* map, uint64_t n_leaves, const int32_t* origins, const uint64_t* active, const float* values, int replace);
+/* castRayIntoGrid V:550-566 for n explicit rays given as voxel index pairs rays6[n][6] = {start xyz, end xyz}: every voxel
+ * of the DDA from start to end (both included; nothing when start == end) becomes active in the named source's update
+ * grid. Same fp64 stepping as the scan path. */
+int vdbm_cast_index_rays(vdbm_map* map, const char* source_id, uint64_t n_rays, const int32_t* rays6);
+/* Config::fast_mode V:1466: on != 0 makes accumulate / raycast / insert use castRayIntoGridFast V:577-602 instead of
+ * castRayIntoGrid: nothing is cast while the map is empty (V:522); otherwise the ray is intersected with the map's node
+ * topology (tools::VolumeRayIntersector<FloatGrid>::hits, restated: hierarchical DDA over the 4096^3 / 128^3 / 8^3 node levels),
+ * a voxel DDA runs over every hit span and only voxels that are ACTIVE in the map become active in the update grid; the end
+ * point rule V:533-536 is unchanged. The intersector the reference rebuilds after every integrateUpdate (V:386, 1436-1449) is
+ * the map itself here: identical whenever the map was last changed by integrateUpdate. */
+int vdbm_set_fast_mode(vdbm_map* map, int on);
+/* raytrace V:675-721 for n rays: origins / directions are world vectors [n][3], max_lengths [n]; success[n] receives 1 when
+ * the ray meets a node span of the map (VolumeRayIntersector::march), end_points [n][3] the world position of the voxel the
+ * fine DDA stopped at (first active voxel after the span start, V:707-712) or origin + direction * length on failure. */
+int vdbm_raytrace(vdbm_map* map, uint64_t n, const double* origins, const double* directions, const double* max_lengths, int32_t* success,
+                  double* end_points);
 /* GridT::Accessor::getValue / isValueOn for one voxel (tests/mapping.cpp:27-29). */
 int vdbm_probe(vdbm_map* map, const int32_t xyz[3], float* value, int32_t* active);
 

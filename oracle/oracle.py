@@ -110,6 +110,11 @@ def lib() -> C.CDLL:
         L.vdbo_points_set.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_int]
         L.vdbo_add_artificial_areas.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(dbl), dbl, dbl]
         L.vdbo_restore_map_integrity.argtypes = [vp]
+        L.vdbo_set_fast_mode.argtypes = [vp, C.c_int]
+        L.vdbo_raytrace.argtypes = [vp, C.c_uint64, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl), i32p, C.POINTER(dbl)]
+        L.vdbo_add_artificial_wall.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), dbl, dbl]
+        L.vdbo_cast_index_rays.restype = C.c_int
+        L.vdbo_cast_index_rays.argtypes = [vp, C.c_char_p, C.c_uint64, i32p]
         _lib = L
     return _lib
 
@@ -313,3 +318,31 @@ class OracleOccupancyVDBMapping:
 
     def exportArtificialAreaGrid(self) -> LeafSet:
         return self._export(5)
+
+    def addArtificialWall(self, start, end, negative_height: float, positive_height: float):
+        a = np.ascontiguousarray(np.asarray(start, dtype=np.float64)[:3])
+        b = np.ascontiguousarray(np.asarray(end, dtype=np.float64)[:3])
+        self._L.vdbo_add_artificial_wall(self._h, _dp(a), _dp(b), float(negative_height), float(positive_height))
+
+    def addArtificialPolygon(self, polygon, negative_height: float, positive_height: float):
+        """VDBMapping.hpp:1198-1207: one wall per edge, closing edge included."""
+        pts = np.asarray(polygon, dtype=np.float64)[:, :3]
+        for i in range(len(pts)):
+            self.addArtificialWall(pts[i], pts[(i + 1) % len(pts)], negative_height, positive_height)
+
+    # ---- fast_mode (VDBMapping.hpp:577-602) and raytrace (VDBMapping.hpp:675-721) ----
+    def setFastMode(self, on: bool):
+        self._L.vdbo_set_fast_mode(self._h, int(bool(on)))
+
+    def raytrace(self, origins, directions, max_lengths):
+        o = np.ascontiguousarray(np.asarray(origins, dtype=np.float64).reshape(-1, 3))
+        d = np.ascontiguousarray(np.asarray(directions, dtype=np.float64).reshape(-1, 3))
+        ln = np.ascontiguousarray(np.broadcast_to(np.asarray(max_lengths, dtype=np.float64), (o.shape[0],)))
+        ok = np.zeros(o.shape[0], dtype=np.int32)
+        e = np.zeros((o.shape[0], 3), dtype=np.float64)
+        self._L.vdbo_raytrace(self._h, o.shape[0], _dp(o), _dp(d), _dp(ln), ok.ctypes.data_as(C.POINTER(C.c_int32)), _dp(e))
+        return ok.astype(bool), e
+
+    def castRaysIntoGrid(self, source_id: str, starts, ends):
+        r = np.ascontiguousarray(np.concatenate([np.asarray(starts, dtype=np.int32).reshape(-1, 3), np.asarray(ends, dtype=np.int32).reshape(-1, 3)], axis=1))
+        return self._L.vdbo_cast_index_rays(self._h, source_id.encode(), r.shape[0], r.ctypes.data_as(C.POINTER(C.c_int32)))

@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -293,6 +294,42 @@ struct Accessor
     return l;
   }
 
+  // probeConstNode<NodeT> of ValueAccessor3 for the two internal levels, and isValueOn (voxel flag, or the flag of the tile
+  // the descent ends at; a root miss is the inactive background)
+  I2* probeI2(const Coord& c)
+  {
+    if (hashed2(c)) return n2;
+    auto it = tree->table.find(TreeT::rootKey(c));
+    if (it == tree->table.end()) return nullptr;
+    insert(c, it->second);
+    return it->second;
+  }
+  I1* probeI1(const Coord& c)
+  {
+    if (hashed1(c)) return n1;
+    I2* b = probeI2(c);
+    if (!b) return nullptr;
+    const uint32_t n = I2::coordToOffset(c);
+    if (!b->childMask.isOn(n)) return nullptr;
+    insert(c, b->nodes[n].child);
+    return b->nodes[n].child;
+  }
+  bool isValueOn(const Coord& c)
+  {
+    if (hashed0(c)) return n0->vmask.isOn(leafOffset(c));
+    I2* b = probeI2(c);
+    if (!b) return false;
+    const uint32_t n = I2::coordToOffset(c);
+    if (!b->childMask.isOn(n)) return b->valueMask.isOn(n);
+    I1* a = b->nodes[n].child;
+    insert(c, a);
+    const uint32_t k = I1::coordToOffset(c);
+    if (!a->childMask.isOn(k)) return a->valueMask.isOn(k);
+    Leaf* l = a->nodes[k].child;
+    insert(c, l);
+    return l->vmask.isOn(leafOffset(c));
+  }
+
   // ---- touch path used by setActiveState(true)/setValueOn on the bool tree: tiles are always
   //      (background, inactive) here, and the requested state is "on", so a child is always
   //      created (InternalNode::setActiveStateAndCache / setValueAndCache). ----
@@ -449,6 +486,266 @@ inline void modifyValueAndActiveState(Accessor<FloatTree>& acc, const Coord& c, 
 }
 
 // --------------------------------------------------------------------------------------------
+// fast_mode / raytrace support: math::Ray<double>, math::DDA<RayT, Log2Dim>, math::VolumeHDDA and
+// tools::VolumeRayIntersector<FloatGrid> restated from OpenVDB's published algorithm (math/Ray.h, math/DDA.h,
+// tools/RayIntersector.h; v9.0 is what the reference's README recommends). PARITY UNPINNED: the reference holds no
+// test or vector for either caller (V:577-602, V:675-721) and OpenVDB is absent from this image.
+//   Ray(eye, dir, t0, t1): direction stored as given (not normalised), invDir = 1/dir, ray(t) = eye + dir * t
+//   Ray::clip(bbox): slab test against the CoordBBox corners, shrinking [t0, t1]; the span is left alone on a miss
+//   DDA<Ray, Log2Dim>::init(ray, t0, t1): voxel = floor(ray(t0)) & ~(DIM-1), per axis next = t0 + (voxel [+ DIM] - pos) * inv,
+//     delta = +-DIM * inv, a zero direction component disables the axis (DBL_MAX); step(): axis = MinIndex(next),
+//     time = next[axis], next[axis] += delta[axis], voxel[axis] += +-DIM, "more" while time <= t1;
+//     next() = Min(t1, next[0], next[1], next[2])
+//   VolumeHDDA<Tree, Ray, Level>: DDA over the nodes of that level; a child node -> recurse with the ray restricted to
+//     [time(), next()]; an active tile opens a span; anything else closes the open span (kept if longer than Delta = 1e-9);
+//     at level 0 a LEAF (whatever its voxels hold) or an active tile opens the span
+//   VolumeRayIntersector(grid): topology copy of the tree, bbox = root.evalActiveBoundingBox(visit_voxels = false) with
+//     max += 1; setIndexRay: ray.clip(bbox) (return value unused by the reference's fast path); hits(): all spans;
+//     march(t0, t1): the first span, only attempted when the ray's own span is valid
+// --------------------------------------------------------------------------------------------
+constexpr double kDelta = 1e-9; // math::Delta<double>::value()
+
+struct TimeSpan
+{
+  double t0, t1;
+  bool valid(double eps = kDelta) const { return (t1 - t0) > eps; }
+  void set(double a, double b) { t0 = a; t1 = b; }
+};
+
+struct Ray
+{
+  double eye[3], dir[3], inv[3];
+  TimeSpan span;
+  Ray(const double e[3], const double d[3], double t0, double t1)
+  {
+    for (int a = 0; a < 3; ++a) { eye[a] = e[a]; dir[a] = d[a]; inv[a] = 1.0 / d[a]; }
+    span.set(t0, t1);
+  }
+  void at(double t, double out[3]) const
+  {
+    for (int a = 0; a < 3; ++a) out[a] = eye[a] + dir[a] * t; // mEye + mDir * time
+  }
+  bool valid() const { return span.valid(); }
+  void setTimes(double t0, double t1) { span.set(t0, t1); }
+  // Ray::intersects(bbox, t0, t1) + Ray::clip
+  bool clip(const int32_t bmin[3], const int32_t bmax[3])
+  {
+    double t0 = span.t0, t1 = span.t1;
+    for (int i = 0; i < 3; ++i)
+    {
+      double a = (double(bmin[i]) - eye[i]) * inv[i];
+      double b = (double(bmax[i]) - eye[i]) * inv[i];
+      if (a > b) std::swap(a, b);
+      if (a > t0) t0 = a;
+      if (b < t1) t1 = b;
+      if (t0 > t1) return false;
+    }
+    span.set(t0, t1);
+    return true;
+  }
+};
+
+inline int minIndex3(const double n[3])
+{
+  static const int table[8] = {2, 1, 9, 1, 2, 9, 0, 0}; // math::MinIndex
+  return table[(int(n[0] < n[1]) << 2) + (int(n[0] < n[2]) << 1) + int(n[1] < n[2])];
+}
+
+template <int LOG2DIM>
+struct DDA
+{
+  static constexpr int32_t DIM = int32_t(1) << LOG2DIM;
+  double mT0, mT1, mNext[3], mDelta[3];
+  Coord mVoxel;
+  int32_t mStep[3];
+  void init(const Ray& ray) { init(ray, ray.span.t0, ray.span.t1); }
+  void init(const Ray& ray, double startTime, double maxTime)
+  {
+    mT0 = startTime;
+    mT1 = maxTime;
+    double pos[3];
+    ray.at(mT0, pos);
+    for (int a = 0; a < 3; ++a) mVoxel[a] = int32_t(std::floor(pos[a])) & ~(DIM - 1);
+    for (int a = 0; a < 3; ++a)
+    {
+      if (ray.dir[a] == 0.0) // math::isZero
+      {
+        mStep[a]  = 0;
+        mNext[a]  = DBL_MAX;
+        mDelta[a] = DBL_MAX;
+      }
+      else if (ray.inv[a] > 0)
+      {
+        mStep[a]  = DIM;
+        mNext[a]  = mT0 + (double(mVoxel[a] + DIM) - pos[a]) * ray.inv[a];
+        mDelta[a] = double(mStep[a]) * ray.inv[a];
+      }
+      else
+      {
+        mStep[a]  = -DIM;
+        mNext[a]  = mT0 + (double(mVoxel[a]) - pos[a]) * ray.inv[a];
+        mDelta[a] = double(mStep[a]) * ray.inv[a];
+      }
+    }
+  }
+  bool step()
+  {
+    const int a = minIndex3(mNext);
+    mT0         = mNext[a];
+    mNext[a] += mDelta[a];
+    mVoxel[a] += mStep[a];
+    return mT0 <= mT1;
+  }
+  double time() const { return mT0; }
+  double maxTime() const { return mT1; }
+  double next() const { return std::min(std::min(mT1, mNext[0]), std::min(mNext[1], mNext[2])); } // math::Min(a, b, c, d)
+};
+
+// VolumeHDDA<FloatTree, Ray, 2 / 1 / 0>. SpanFn(const TimeSpan&) -> true = terminate (march), false = keep going (hits).
+struct VolumeHDDA
+{
+  template <typename SpanFn>
+  static bool level0(Ray& ray, Accessor<FloatTree>& acc, TimeSpan& t, SpanFn& fn)
+  {
+    DDA<3> dda;
+    dda.init(ray);
+    do
+    {
+      if (acc.probeLeaf(dda.mVoxel) || acc.isValueOn(dda.mVoxel))
+      {
+        if (t.t0 < 0) t.t0 = dda.time();
+      }
+      else if (t.t0 >= 0)
+      {
+        t.t1 = dda.time();
+        if (t.valid() && fn(t)) return true;
+        t.set(-1, -1);
+      }
+    } while (dda.step());
+    if (t.t0 >= 0) t.t1 = dda.maxTime();
+    return false;
+  }
+  template <typename SpanFn>
+  static bool level1(Ray& ray, Accessor<FloatTree>& acc, TimeSpan& t, SpanFn& fn)
+  {
+    DDA<7> dda;
+    dda.init(ray);
+    do
+    {
+      if (acc.probeI1(dda.mVoxel) != nullptr)
+      {
+        ray.setTimes(dda.time(), dda.next());
+        if (level0(ray, acc, t, fn)) return true;
+      }
+      else if (acc.isValueOn(dda.mVoxel))
+      {
+        if (t.t0 < 0) t.t0 = dda.time();
+      }
+      else if (t.t0 >= 0)
+      {
+        t.t1 = dda.time();
+        if (t.valid() && fn(t)) return true;
+        t.set(-1, -1);
+      }
+    } while (dda.step());
+    if (t.t0 >= 0) t.t1 = dda.maxTime();
+    return false;
+  }
+  template <typename SpanFn>
+  static bool level2(Ray& ray, Accessor<FloatTree>& acc, TimeSpan& t, SpanFn& fn)
+  {
+    DDA<12> dda;
+    dda.init(ray);
+    do
+    {
+      if (acc.probeI2(dda.mVoxel) != nullptr)
+      {
+        ray.setTimes(dda.time(), dda.next());
+        if (level1(ray, acc, t, fn)) return true;
+      }
+      else if (acc.isValueOn(dda.mVoxel))
+      {
+        if (t.t0 < 0) t.t0 = dda.time();
+      }
+      else if (t.t0 >= 0)
+      {
+        t.t1 = dda.time();
+        if (t.valid() && fn(t)) return true;
+        t.set(-1, -1);
+      }
+    } while (dda.step());
+    if (t.t0 >= 0) t.t1 = dda.maxTime();
+    return false;
+  }
+};
+
+struct VolumeRayIntersector
+{
+  // The reference's intersector owns a topology COPY of the map taken after the last integrateUpdate (V:1436-1449); the map
+  // cannot change while accumulateUpdate / raytrace hold the shared lock, so reading the live tree is the same thing whenever
+  // the map was last changed by integrateUpdate. Other writers (sections, point edits) leave the reference with a stale
+  // copy; that staleness is NOT restated (the B200 path and this oracle both read the current map).
+  Accessor<FloatTree> acc;
+  int32_t bmin[3], bmax[3];
+  double tmax = 0;
+  explicit VolumeRayIntersector(FloatTree& tree) : acc(tree)
+  {
+    // RootNode / InternalNode / LeafNode::evalActiveBoundingBox(bbox, visitVoxels = false): active tiles with their full
+    // extent, leaves that hold at least one active voxel with their node bounding box
+    for (int a = 0; a < 3; ++a) { bmin[a] = INT32_MAX; bmax[a] = INT32_MIN; }
+    auto expand = [&](const Coord& o, int32_t dim) {
+      for (int a = 0; a < 3; ++a)
+      {
+        bmin[a] = std::min(bmin[a], o[a]);
+        bmax[a] = std::max(bmax[a], o[a] + dim - 1);
+      }
+    };
+    for (auto& kv : tree.table)
+    {
+      const FloatI2* n2 = kv.second;
+      for (uint32_t i = n2->valueMask.findNextOn(0); i < FloatI2::NUM; i = n2->valueMask.findNextOn(i + 1))
+        expand(Coord(n2->origin[0] + int32_t(i >> 10) * 128, n2->origin[1] + int32_t((i >> 5) & 31) * 128, n2->origin[2] + int32_t(i & 31) * 128), 128);
+      for (uint32_t i = n2->childMask.findNextOn(0); i < FloatI2::NUM; i = n2->childMask.findNextOn(i + 1))
+      {
+        const FloatI1* n1 = n2->nodes[i].child;
+        for (uint32_t k = n1->valueMask.findNextOn(0); k < FloatI1::NUM; k = n1->valueMask.findNextOn(k + 1))
+          expand(Coord(n1->origin[0] + int32_t(k >> 8) * 8, n1->origin[1] + int32_t((k >> 4) & 15) * 8, n1->origin[2] + int32_t(k & 15) * 8), 8);
+        for (uint32_t k = n1->childMask.findNextOn(0); k < FloatI1::NUM; k = n1->childMask.findNextOn(k + 1))
+        {
+          const FloatLeaf* l = n1->nodes[k].child;
+          if (!l->vmask.isOff()) expand(l->origin, 8);
+        }
+      }
+    }
+    for (int a = 0; a < 3; ++a) bmax[a] = int32_t(uint32_t(bmax[a]) + 1u); // mBBox.max().offset(1)
+  }
+  // setIndexRay: the clipped ray is what hits() / march() traverse
+  bool setIndexRay(Ray& ray)
+  {
+    const bool hit = ray.clip(bmin, bmax);
+    if (hit) tmax = ray.span.t1;
+    return hit;
+  }
+  void hits(Ray& ray, std::vector<TimeSpan>& list)
+  {
+    TimeSpan t{-1, -1};
+    list.clear();
+    auto keep = [&](const TimeSpan& s) { list.push_back(s); return false; };
+    VolumeHDDA::level2(ray, acc, t, keep);
+    if (t.valid()) list.push_back(t);
+  }
+  bool march(Ray& ray, double& t0, double& t1)
+  {
+    TimeSpan t{-1, -1};
+    auto stop = [&](const TimeSpan&) { return true; };
+    if (ray.valid()) VolumeHDDA::level2(ray, acc, t, stop);
+    t0 = t.t0;
+    t1 = t.t1;
+    return t.valid();
+  }
+};
+
+// --------------------------------------------------------------------------------------------
 // The mapping classes (restated reference logic).
 // --------------------------------------------------------------------------------------------
 struct Stats
@@ -487,6 +784,7 @@ struct MappingBase
   std::map<std::string, std::unique_ptr<Source> > m_input_sources; // std::map order, V:1545
   Stats stats;
   bool replicate_probe_quirk = true; // SURVEY F9; false = report only real flag flips
+  bool m_fast_mode           = false; // Config::fast_mode V:1466
 
   explicit MappingBase(double resolution) : m_resolution(resolution), m_inv_resolution(1.0 / resolution)
   {
@@ -583,12 +881,109 @@ struct MappingBase
     } while (more);
   }
 
-  // V:466-539 (fast_mode is out of scope)
+  // V:577-602: the ray is intersected with the map's node topology; a voxel DDA runs over every hit span and only voxels
+  // that are active in the map are activated in the update grid. st.visits counts those setActiveState calls (V:598).
+  void castRayIntoGridFast(const Coord& o, const Coord& e, Accessor<FloatTree>& grid_acc, Accessor<BoolTree>& update_acc,
+                           VolumeRayIntersector& intersector, Stats& st)
+  {
+    double eye[3], dir[3];
+    for (int a = 0; a < 3; ++a)
+    {
+      dir[a] = double(e[a]) - double(o[a]); // V:586
+      eye[a] = double(o[a]) + 0.5;          // V:587
+    }
+    Ray ray(eye, dir, 0, 1);
+    intersector.setIndexRay(ray); // V:588, result unused
+    std::vector<TimeSpan> hits;
+    intersector.hits(ray, hits);  // V:589-590
+    for (const TimeSpan& hit : hits)
+    {
+      Ray fine_ray(eye, dir, hit.t0, hit.t1); // V:593
+      DDA<0> dda;
+      dda.init(fine_ray);
+      do
+      {
+        if (grid_acc.isValueOn(dda.mVoxel)) // V:597
+        {
+          setActiveStateOn(update_acc, dda.mVoxel);
+          ++st.visits;
+        }
+      } while (dda.step());
+    }
+  }
+
+  // V:675-721. Vec3::normalize(): *= 1/length; Transform::worldToIndex / indexToWorld of a uniform scale map: multiply by the
+  // stored inverse scale / by the scale. m_volume_ray_intersector is only ever set in fast_mode (V:1438): the reference
+  // dereferences a null pointer otherwise; here the intersector is always the current map. An EMPTY map (the reference
+  // never builds an intersector for one) reports no hit.
+  void raytrace(size_t n, const double* origins, const double* directions, const double* max_lengths, int32_t* successes, double* end_points)
+  {
+    if (m_vdb_grid->empty())
+    {
+      for (size_t i = 0; i < n; ++i)
+      {
+        const double* d = directions + 3 * i;
+        const double len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const double il  = 1.0 / len;
+        for (int a = 0; a < 3; ++a)
+        {
+          const double dn  = (d[a] * il) * max_lengths[i];
+          const double oi  = origins[3 * i + a] * m_inv_resolution;
+          const double di  = dn * m_inv_resolution;
+          end_points[3 * i + a] = (oi + di) * m_resolution;
+        }
+        successes[i] = 0;
+      }
+      return;
+    }
+    VolumeRayIntersector intersector(*m_vdb_grid);
+    Accessor<FloatTree> acc(*m_vdb_grid);
+    for (size_t i = 0; i < n; ++i)
+    {
+      const double* d  = directions + 3 * i;
+      const double len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); // V:691 normalize
+      const double il  = 1.0 / len;
+      double oi[3], di[3];
+      for (int a = 0; a < 3; ++a)
+      {
+        const double dn = (d[a] * il) * max_lengths[i];  // V:692
+        oi[a] = origins[3 * i + a] * m_inv_resolution;   // V:694
+        di[a] = dn * m_inv_resolution;                   // V:695
+      }
+      Ray ray(oi, di, 0, 1);           // V:698
+      intersector.setIndexRay(ray);    // V:700
+      double t0, t1;
+      if (intersector.march(ray, t0, t1)) // V:704
+      {
+        Ray fine_ray(oi, di, t0, t1);
+        DDA<0> dda;
+        dda.init(fine_ray);
+        while (dda.step() && !acc.isValueOn(dda.mVoxel)) {} // V:709-713
+        for (int a = 0; a < 3; ++a) end_points[3 * i + a] = double(dda.mVoxel[a]) * m_resolution; // V:714
+        successes[i] = 1;
+      }
+      else
+      {
+        for (int a = 0; a < 3; ++a) end_points[3 * i + a] = (oi[a] + di[a]) * m_resolution; // V:719
+        successes[i] = 0;
+      }
+    }
+  }
+
+  // V:466-539
   bool raycastPointCloud(const uint8_t* pts, size_t n, size_t stride, const double origin[3], double raycast_range,
                          Accessor<BoolTree>& update_acc, Stats& st, Accessor<BoolTree>* reduced_acc = nullptr)
   {
     if (!m_config_set) return false; // V:478-482
     const Coord ray_origin_index = worldToIndex(origin);
+    const bool grid_empty        = m_vdb_grid->empty(); // V:495
+    std::unique_ptr<VolumeRayIntersector> intersector;
+    std::unique_ptr<Accessor<FloatTree> > grid_acc;
+    if (m_fast_mode && !grid_empty)
+    {
+      intersector.reset(new VolumeRayIntersector(*m_vdb_grid)); // V:1440 (see VolumeRayIntersector about the snapshot)
+      grid_acc.reset(new Accessor<FloatTree>(*m_vdb_grid));     // V:496
+    }
     const bool origin_nan        = std::isnan(origin[0]) || std::isnan(origin[1]) || std::isnan(origin[2]);
     for (size_t i = 0; i < n; ++i)
     {
@@ -616,7 +1011,11 @@ struct MappingBase
         }
       }
       const Coord ray_end_index = worldToIndex(end); // V:519
-      castRayIntoGrid(ray_origin_index, ray_end_index, update_acc, st); // V:530
+      if (m_fast_mode) // V:520-527
+      {
+        if (!grid_empty) castRayIntoGridFast(ray_origin_index, ray_end_index, *grid_acc, update_acc, *intersector, st);
+      }
+      else castRayIntoGrid(ray_origin_index, ray_end_index, update_acc, st); // V:530
       if (!max_range_ray) setValueOnTrue(update_acc, ray_end_index); // V:533-536
       if (reduced_acc)
       {
@@ -1374,6 +1773,29 @@ void vdbo_points_set(void* hh, const void* pts, uint64_t n, uint64_t stride, int
 void vdbo_add_artificial_areas(void* hh, uint64_t n_poly, const uint32_t* counts, const double* xyz, double negative_height, double positive_height)
 {
   static_cast<vo::Handle*>(hh)->map.addArtificialAreas(n_poly, counts, xyz, negative_height, positive_height);
+}
+void vdbo_set_fast_mode(void* hh, int on) { static_cast<vo::Handle*>(hh)->map.m_fast_mode = (on != 0); }
+void vdbo_raytrace(void* hh, uint64_t n, const double* origins, const double* directions, const double* max_lengths, int32_t* successes,
+                   double* end_points)
+{
+  static_cast<vo::Handle*>(hh)->map.raytrace(n, origins, directions, max_lengths, successes, end_points);
+}
+// addArtificialWall V:1217-1236 on its own (no restoreMapIntegrity)
+void vdbo_add_artificial_wall(void* hh, const double* start, const double* end, double negative_height, double positive_height)
+{
+  static_cast<vo::Handle*>(hh)->map.addArtificialWall(start, end, negative_height, positive_height);
+}
+// castRayIntoGrid V:550-566 for explicit voxel pairs into a source's update grid
+int vdbo_cast_index_rays(void* hh, const char* source, uint64_t n, const int32_t* rays6)
+{
+  auto& m = static_cast<vo::Handle*>(hh)->map;
+  auto it = m.m_input_sources.find(source);
+  if (it == m.m_input_sources.end()) return 1;
+  vo::Accessor<vo::BoolTree> acc(*it->second->update_grid);
+  vo::Stats st;
+  for (uint64_t i = 0; i < n; ++i)
+    m.castRayIntoGrid(vo::Coord(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]), vo::Coord(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]), acc, st);
+  return 0;
 }
 void vdbo_restore_map_integrity(void* hh) { static_cast<vo::Handle*>(hh)->map.restoreMapIntegrity(); }
 

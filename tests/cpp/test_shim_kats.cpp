@@ -25,6 +25,17 @@ static Config gtestConfig(double max_range)
 }
 static float logOdds(double p) { return static_cast<float>(std::log(p) - std::log(1 - p)); }
 
+
+// centres of all active voxels, like saveMapToPCD R:218-256 writes them
+static void detail_forEachActive(OccupancyVDBMapping& map, OccupancyVDBMapping::PointCloudT& cloud)
+{
+  auto grid = map.getGrid();
+  vdb_mapping::detail::Backend<float>::forEachActiveVoxel(*grid, [&](const openvdb::Coord& c, const float&) {
+    const openvdb::Vec3d w = grid->indexToWorld(c);
+    cloud.points.emplace_back(static_cast<float>(w.x() + 0.05), static_cast<float>(w.y() + 0.05), static_cast<float>(w.z() + 0.05));
+  });
+}
+
 struct Expect { int z; int kind; bool check_flag; bool flag; }; // kind: 0 untouched, 1 miss, 2 hit
 
 static void runAxisCase(double resolution, double max_range, double z_in_resolutions, std::initializer_list<Expect> exp)
@@ -263,6 +274,142 @@ TEST(Shim, PointEditsAndArtificialAreas)
   EXPECT_EQ(acc.getValue(openvdb::Coord(10, 15, 0)), 0.0f);
   map.restoreMapIntegrity(); // value 0 is not above the occupancy threshold -> inactive again
   EXPECT_FALSE(acc.isValueOn(openvdb::Coord(10, 15, 0)));
+}
+
+
+// ---- the rest of the reference's public surface ------------------------------------------------
+static OccupancyVDBMapping::PointCloudT::Ptr wallCloud(float x, int n_side, float step)
+{
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  for (int i = -n_side; i <= n_side; ++i)
+    for (int j = -n_side; j <= n_side; ++j) cloud->points.emplace_back(x, i * step, j * step);
+  return cloud;
+}
+
+TEST(Shim, RaytraceFindsTheWallAndFastModeOnlyTouchesOccupiedVoxels)
+{
+  OccupancyVDBMapping map(0.1);
+  Config conf = gtestConfig(10);
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  // world 2.0 -> voxel 20 and world 0.0 -> voxel 0 under the reference's worldToIndex rule (R:612-631)
+  Eigen::Matrix<double, 3, 1> origin(0.0, 0.0, 0.0);
+  map.insertPointCloud(wallCloud(2.0f, 10, 0.1f), origin, "test"); // a wall in the voxel plane x = 20; one hit is enough with this config
+  bool success = false;
+  openvdb::Vec3d end;
+  map.raytrace(openvdb::Vec3d(0.05, 0.05, 0.05), openvdb::Vec3d(1, 0, 0), 5.0, success, end);
+  EXPECT_TRUE(success);
+  EXPECT_TRUE(std::fabs(end.x() - 2.0) < 1e-9); // indexToWorld of voxel 20 = its lower corner
+  // behind the sensor: the ray misses the active bounding box, but the reference ignores setIndexRay's result (R:700) and
+  // marches the unclipped ray through the free-space leaf it starts in -> "success" with an end point behind the sensor
+  map.raytrace(openvdb::Vec3d(0.05, 0.05, 0.05), openvdb::Vec3d(-1, 0, 0), 5.0, success, end);
+  EXPECT_TRUE(end.x() < 0.05);
+  // far away from everything mapped: a miss, end point = origin + direction * length
+  map.raytrace(openvdb::Vec3d(50.0, 50.0, 50.0), openvdb::Vec3d(0, 0, 1), 5.0, success, end);
+  EXPECT_FALSE(success);
+  EXPECT_TRUE(std::fabs(end.z() - 55.0) < 1e-9);
+  std::vector<openvdb::Vec3d> origins(3, openvdb::Vec3d(0.05, 0.05, 0.05)), dirs = {openvdb::Vec3d(1, 0, 0), openvdb::Vec3d(2, 0.1, 0), openvdb::Vec3d(0, 0, -1)}, ends;
+  std::vector<double> lens = {5.0, 5.0, 5.0};
+  std::vector<bool> oks;
+  map.raytrace(origins, dirs, lens, oks, ends);
+  EXPECT_EQ(oks.size(), std::size_t(3));
+  EXPECT_TRUE(oks[0] && oks[1]);
+
+  // fast mode: a ray THROUGH the wall frees the wall voxel it passes, but creates no free-space voxels behind it
+  conf.fast_mode = true;
+  map.setConfig(conf);
+  const std::size_t leaves_before = map.getGrid()->leafCount();
+  OccupancyVDBMapping::PointCloudT::Ptr through(new OccupancyVDBMapping::PointCloudT);
+  through->points.emplace_back(6.0f, 0.0f, 0.0f);
+  map.insertPointCloud(through, origin, "test");
+  OccupancyVDBMapping::GridT::Accessor acc = map.getGrid()->getAccessor();
+  EXPECT_EQ(acc.getValue(openvdb::Coord(20, 0, 0)), logOdds(0.9) + logOdds(0.1)); // hit, then the fast-mode miss
+  EXPECT_EQ(acc.getValue(openvdb::Coord(40, 0, 0)), 0.0f);                        // behind the wall: untouched
+  EXPECT_EQ(acc.getValue(openvdb::Coord(60, 0, 0)), logOdds(0.9));                // the new end point
+  EXPECT_TRUE(map.getGrid()->leafCount() <= leaves_before + 1);
+}
+
+TEST(Shim, SaveLoadRoundTripAndPcdImport)
+{
+  OccupancyVDBMapping map(0.1);
+  Config conf             = gtestConfig(10);
+  conf.map_directory_path = "/tmp/vdbm_shim_test_";
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  Eigen::Matrix<double, 3, 1> origin(0.0, 0.0, 0.0);
+  map.insertPointCloud(wallCloud(1.5f, 6, 0.1f), origin, "test"); // voxel plane x = 15
+  const auto before_active = map.getGrid()->activeVoxelCount();
+  EXPECT_TRUE(before_active > 100);
+  // save through gridToByteArray / byteArrayToGrid (wire codec R:1310-1338) and through a file
+  std::vector<uint8_t> bytes = map.gridToByteArray<OccupancyVDBMapping::GridT>(map.getGrid());
+  EXPECT_TRUE(bytes.size() > 16);
+  OccupancyVDBMapping::GridT::Ptr back = map.byteArrayToGrid<OccupancyVDBMapping::GridT>(bytes);
+  EXPECT_EQ(back->activeVoxelCount(), before_active);
+  EXPECT_EQ(back->leafCount(), map.getGrid()->leafCount());
+  const std::string raw = "a string that should survive the zstd codec  a string that should survive the zstd codec";
+  EXPECT_EQ(map.decompressByteArray(map.compressString(raw)), raw);
+  EXPECT_TRUE(map.saveMapToPCD());
+  // a PCD written by saveMapToPCD read back into a fresh map (loadMapFromPCD R:295 -> createMapFromPointCloud O:136)
+  OccupancyVDBMapping::PointCloudT::Ptr centres(new OccupancyVDBMapping::PointCloudT);
+  detail_forEachActive(map, *centres);
+  const std::string pcd = "/tmp/vdbm_shim_test_points.pcd";
+  EXPECT_TRUE(vdb_mapping::detail::writePCD(pcd, *centres));
+  OccupancyVDBMapping other(0.1);
+  other.setConfig(conf);
+  other.addInputSource("test", conf.max_range, 0);
+  EXPECT_TRUE(other.loadMapFromPCD(pcd, /*set_background=*/false, /*clear_map=*/true));
+  EXPECT_EQ(other.getGrid()->activeVoxelCount(), before_active);
+  OccupancyVDBMapping::GridT::Accessor oacc = other.getGrid()->getAccessor();
+  EXPECT_TRUE(oacc.isValueOn(openvdb::Coord(15, 0, 0)));
+  EXPECT_EQ(oacc.getValue(openvdb::Coord(15, 0, 0)), logOdds(0.99));
+  // the loaded map lives on the DEVICE too: a scan integrates into it
+  OccupancyVDBMapping::PointCloudT::Ptr one(new OccupancyVDBMapping::PointCloudT);
+  one->points.emplace_back(1.5f, 0.0f, 0.0f);
+  other.insertPointCloud(one, origin, "test");
+  EXPECT_EQ(oacc.getValue(openvdb::Coord(15, 0, 0)), logOdds(0.99)); // already at the clamp
+  EXPECT_EQ(oacc.getValue(openvdb::Coord(7, 0, 0)), logOdds(0.1));
+  EXPECT_FALSE(other.loadMapFromPCD("/tmp/definitely_not_there.pcd", false, true));
+}
+
+TEST(Shim, ExplicitRaysWallsAndTypedSections)
+{
+  OccupancyVDBMapping map(0.1);
+  const Config conf = gtestConfig(10);
+  map.setConfig(conf);
+  map.addInputSource("test", conf.max_range, 0);
+  OccupancyVDBMapping::UpdateGridT::Ptr grid = OccupancyVDBMapping::UpdateGridT::create(false);
+  OccupancyVDBMapping::UpdateGridT::Accessor uacc = grid->getAccessor();
+  map.castRayIntoGrid(openvdb::Coord(0, 0, 0), openvdb::Coord(5, 0, 0), uacc);
+  for (int x = 0; x <= 5; ++x) EXPECT_TRUE(uacc.isValueOn(openvdb::Coord(x, 0, 0)));
+  EXPECT_FALSE(uacc.isValueOn(openvdb::Coord(6, 0, 0)));
+  map.castRayIntoGrid(openvdb::Coord(3, 3, 3), openvdb::Coord(3, 3, 3), uacc); // start == end: nothing (R:559)
+  EXPECT_FALSE(uacc.isValueOn(openvdb::Coord(3, 3, 3)));
+
+  Eigen::Matrix<double, 4, 1> a(1.0, 1.0, 0.0, 1.0), b(1.0, 2.0, 0.0, 1.0);
+  map.addArtificialWall(a, b, -0.1, 0.2);
+  std::vector<Eigen::Matrix<double, 4, 1> > tri = {Eigen::Matrix<double, 4, 1>(-1.0, -1.0, 0.0, 1.0), Eigen::Matrix<double, 4, 1>(-2.0, -1.0, 0.0, 1.0),
+                                                   Eigen::Matrix<double, 4, 1>(-2.0, -2.0, 0.0, 1.0)};
+  map.addArtificialPolygon(tri, 0.0, 0.1);
+  OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+  cloud->points.emplace_back(0.0f, 0.0f, 0.5f);
+  Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  map.insertPointCloud(cloud, origin, "test");
+  OccupancyVDBMapping::GridT::Accessor acc = map.getGrid()->getAccessor();
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(10, 15, 0)));   // the first wall survived the second call (no restore in between)
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(-15, -10, 0))); // polygon edge 0
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(-20, -15, 0))); // polygon edge 1
+  EXPECT_TRUE(acc.isValueOn(openvdb::Coord(-15, -15, 0))); // the closing edge (diagonal)
+
+  Eigen::Matrix<double, 3, 1> lo(-3, -3, -1), hi(3, 3, 1);
+  Eigen::Matrix<double, 4, 4> tf = Eigen::Matrix<double, 4, 4>::Identity();
+  auto ug = map.getMapSection<OccupancyVDBMapping::UpdateGridT>(lo, hi, tf, false);
+  auto fg = map.getMapSection<OccupancyVDBMapping::GridT>(lo, hi, tf, true);
+  EXPECT_TRUE(ug->activeVoxelCount() > 0);
+  EXPECT_EQ(ug->activeVoxelCount(), fg->activeVoxelCount());
+  const openvdb::BBoxd wb = map.createWorldBoundingBox(lo, hi, tf);
+  EXPECT_EQ(wb.min().x(), -3.0);
+  EXPECT_EQ(wb.max().z(), 1.0);
+  map.morphologicalCloseMap<OccupancyVDBMapping::UpdateGridT>(ug, 1); // runs; result checked in test_compat_grid
 }
 
 int main() { return RUN_ALL_TESTS(); }

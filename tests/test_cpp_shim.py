@@ -47,6 +47,19 @@ def test_standin_host_grid_bulk_update(tmp_path):
 
 
 @pytest.mark.gpu
+def test_the_references_own_test_file_passes_unmodified():
+    """/root/reference/tests/mapping.cpp compiled UNMODIFIED against include/vdb_mapping (by __graft_entry__.build() in the
+    build container, where the reference lives) and run here on the GPU through the C ABI."""
+    _build()
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "reference_mapping_tests")
+    if not os.path.exists(exe):
+        pytest.skip("reference_mapping_tests was not built (no /root/reference at build time)")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert "5 test(s), 0 failed" in p.stdout, p.stdout[-2000:]
+
+
+@pytest.mark.gpu
 def test_reference_scenarios_through_the_cpp_shim():
     p = subprocess.run([_build()], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]

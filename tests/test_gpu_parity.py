@@ -676,3 +676,235 @@ def test_prefetch_is_one_shot_and_async_insert_of_unknown_source_still_integrate
     g.insertPointCloudAsync(pa, origin, "nope"); o.insertPointCloud(pa, origin, "nope")
     assert len(g.exportUpdateGrid("s")) == 0
     assert_leafsets_equal(g.exportMap(), o.exportMap(), "map after the integrate triggered by the unknown-source insert")
+
+
+def test_cfg4_sector_at_real_resolution_bit_exact():
+    """BASELINE configs[3] at its own resolution / range (0.02 m, 100 m): a 1/8 azimuth sector of the 1M-point hall scan
+    that CONTAINS a door (rays clipped at 100 m: ~5,000-voxel rays, split into segments by the planner on "auto"), two
+    scans from a moving origin. Update grid, map and counters bit-exact vs the oracle."""
+    from vdb_mapping_b200 import scans, dist as vdist
+    c = scans.CONFIGS[4]
+    g, o = _pair(c.resolution, c.max_range, (c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max))
+    for k in range(2):
+        pts, origin = scans.make_scan(4, k)
+        ang = vdist.diamond_angle(pts[:, 0].astype(np.float64) - origin[0], pts[:, 1].astype(np.float64) - origin[1])
+        sel = np.nonzero(~np.isfinite(ang) | ((ang >= 0.0) & (ang < 0.5)))[0]   # 1/8 of the circle around the door at az 0.3 rad
+        sector = np.ascontiguousarray(pts[sel])
+        assert 100_000 < len(sector) < 200_000
+        g.accumulateUpdate(sector, origin, "s"); o.accumulateUpdate(sector, origin, "s")
+        assert g.stats()["clipped"] > 0
+        assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), f"cfg4 sector update grid scan {k}")
+        g.integrateUpdate(); o.integrateUpdate()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "cfg4 sector map")
+    sg, so = g.stats(), o.stats()
+    for key in ("rays", "clipped", "visits", "voxel_updates"):
+        assert sg[key] == so[key], key
+    # the longest (door) rays really were long: the planner had something to split
+    assert sg["visits"] / max(1, sg["rays"]) > 500
+
+
+def test_cfg5_remote_mapping_full_scan_vs_oracle():
+    """BASELINE configs[4] at full size: one cfg2 scan (262,144 rays) through createUpdate(2) on the sender and
+    applyUpdate(2) on a second GPU map; the reduced update and the RECEIVER's map are bit-exact vs the oracle's receiver."""
+    from vdb_mapping_b200 import scans
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    from oracle.oracle import OracleOccupancyVDBMapping
+    c = scans.CONFIGS[2]
+    cfg = (c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max)
+    snd, o_snd = _pair(c.resolution, c.max_range, cfg)
+    rcv = OccupancyVDBMapping(c.resolution)
+    o_rcv = OracleOccupancyVDBMapping(c.resolution)
+    for m in (rcv, o_rcv):
+        m.setConfig(c.max_range, *cfg)
+        m.addInputSource("s", c.max_range)
+    pts, origin = scans.make_scan(2, 0)
+    snd.accumulateUpdate(pts, origin, "s"); o_snd.accumulateUpdate(pts, origin, "s")
+    red, og = snd.createUpdate("s", 2)
+    red_o, og_o = o_snd.createUpdate("s", 2)
+    assert_leafsets_equal(red, red_o, "reduced (level 2) update")
+    assert np.array_equal(og, og_o)
+    snd.integrateUpdate(keep_change=False); o_snd.integrateUpdate()
+    rcv.applyUpdate(2, red, origin=og)
+    o_rcv.applyUpdate("s", 2, red_o, og_o)
+    assert_leafsets_equal(rcv.exportMap(), o_rcv.exportMap(), "receiver map (GPU) vs receiver map (oracle)")
+    assert_leafsets_equal(rcv.exportMap(), snd.exportMap(), "receiver map vs sender map")
+
+
+# ---- SURVEY.md 8f N3 / N4: fast_mode, raytrace, loadMap import, explicit rays, single walls ----------------------------
+def _room_scan(seed, n, origin, radius=3.0, noise=0.01, dtype=np.float32):
+    """points on a sphere-ish room around `origin` (hits repeat from scan to scan -> occupied voxels build up)"""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = radius * (1.0 + 0.25 * np.sin(3 * d[:, 0]) * np.cos(2 * d[:, 1]))
+    return (np.asarray(origin) + d * r[:, None] + rng.normal(scale=noise, size=d.shape)).astype(dtype)
+
+
+@pytest.mark.parametrize("cfg", [CFG_GTEST, CFG_ROS], ids=["gtest_cfg", "ros_cfg"])
+def test_fast_mode_bit_exact(cfg):
+    """Config::fast_mode (V:1466): castRayIntoGridFast V:577-602 against the oracle's restatement of VolumeRayIntersector.
+    Phase 1 builds a map in normal mode (free-space leaves everywhere), phase 2 switches both to fast mode: rays that pass
+    through occupied voxels, rays that stop short, clipped rays, NaN, zero-length rays, moving origin, two accumulates per
+    integrate. Phase 3 is a map built in fast mode from the first scan (empty map: only end points, V:522)."""
+    g, o = _pair(0.1, 6.0, cfg)
+    origin = np.array([0.031, -0.012, 0.2])
+    for k in range(5):
+        pts = _room_scan(5, 6000, origin)
+        for m in (g, o):
+            m.insertPointCloud(pts, origin, "s")
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map before fast mode")
+    assert popcount64(o.exportMap().active) > 1000   # there are occupied voxels for the fast rays to find
+    for m in (g, o):
+        m.setFastMode(True)
+    for k in range(4):
+        og = origin + np.array([0.21 * k, -0.13 * k, 0.05 * k])
+        pts = _room_scan(40 + k, 5000, og, radius=[4.5, 2.0, 3.0, 7.5][k])   # through the wall / short / on it / clipped
+        pts[11] = np.nan
+        pts[12] = og.astype(np.float32)                                       # zero-length ray
+        assert g.accumulateUpdate(pts, og, "s") == 0 and o.accumulateUpdate(pts, og, "s") == 0
+        if k == 1:   # a second cloud in the same accumulation period
+            pts2 = _room_scan(77, 2000, og, radius=5.0)
+            g.accumulateUpdate(pts2, og, "s"); o.accumulateUpdate(pts2, og, "s")
+        ug, uo = g.exportUpdateGrid("s"), o.exportUpdateGrid("s")
+        assert len(uo) > 0
+        assert_leafsets_equal(ug, uo, f"fast-mode update grid {k}")
+        g.integrateUpdate(keep_change=True); o.integrateUpdate()
+        assert_leafsets_equal(g.exportLastChange("s"), o.exportLastChange("s"), f"fast-mode change grid {k}")
+        assert_leafsets_equal(g.exportMap(), o.exportMap(), f"fast-mode map {k}")
+    sg, so = g.stats(), o.stats()
+    for key in ("rays", "nan_skipped", "clipped", "visits", "voxel_updates", "state_changes"):
+        assert sg[key] == so[key], key
+    # phase 3: fast mode from an empty map
+    for m in (g, o):
+        m.resetMap()
+    for k in range(5):
+        pts = _room_scan(5 if k < 4 else 6, 6000, origin, radius=3.0 if k < 4 else 5.0)
+        g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+        assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), f"fast-only update grid {k}")
+        g.integrateUpdate(); o.integrateUpdate()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "fast-only map")
+    # a reduced (level 2) update is refused in fast mode (it describes castRayIntoGrid scans)
+    from vdb_mapping_b200.mapping import VdbmError
+    g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+    with pytest.raises(VdbmError):
+        g.createUpdate("s", 2)
+    # and back to normal mode, on top of the fast-mode accumulate that is still in the update grid
+    for m in (g, o):
+        m.setFastMode(False)
+    g.accumulateUpdate(pts, origin, "s"); o.accumulateUpdate(pts, origin, "s")
+    assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "normal-mode accumulate on top of a fast-mode one")
+
+
+def test_fast_mode_large_coordinates_and_many_nodes():
+    """Rays far from the world origin crossing many 128^3 and several 4096^3 blocks (0.02 m voxels, 90 m rays): the coarse node
+    sets grow, negative coordinates, long spans."""
+    g, o = _pair(0.02, 100.0, CFG_ROS)
+    origin = np.array([-351.237, 812.001, -3.3])
+    rng = np.random.default_rng(3)
+    d = rng.normal(size=(300, 3)); d[:, 2] *= 0.1
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = (origin + d * rng.uniform(20, 90, size=(300, 1))).astype(np.float32)
+    for k in range(2):
+        for m in (g, o):
+            m.insertPointCloud(pts, origin, "s")
+    for m in (g, o):
+        m.setFastMode(True)
+    pts2 = (origin + d * 95.0).astype(np.float32)   # through every end point of the first scans
+    g.accumulateUpdate(pts2, origin, "s"); o.accumulateUpdate(pts2, origin, "s")
+    assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "fast-mode update grid, long rays")
+    g.integrateUpdate(); o.integrateUpdate()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
+    assert g.stats()["visits"] == o.stats()["visits"]
+
+
+def test_raytrace_matches_the_oracle():
+    """Batch raytrace V:675-721: hits, misses, rays that start inside / outside the map's bounding box, axis-aligned and
+    zero-component directions, unnormalised directions, an empty map. End points compared as fp64 bit patterns."""
+    g, o = _pair(0.1, 6.0, CFG_GTEST)
+    rng = np.random.default_rng(9)
+    n = 4000
+    org = rng.uniform(-1.0, 1.0, size=(n, 3))
+    org[:200] = rng.uniform(-30, 30, size=(200, 3))           # outside the mapped room
+    dirs = rng.normal(size=(n, 3)) * rng.uniform(0.1, 5.0, size=(n, 1))
+    dirs[200:260, 1:] = 0.0                                    # axis-aligned
+    dirs[260:300, 2] = 0.0
+    lens = rng.uniform(0.5, 12.0, size=n)
+    ok_g, e_g = g.raytrace(org, dirs, lens)
+    ok_o, e_o = o.raytrace(org, dirs, lens)
+    assert not ok_g.any() and not ok_o.any()
+    assert np.array_equal(e_g.view(np.uint64), e_o.view(np.uint64)), "end points on an empty map"
+    origin = np.array([0.031, -0.012, 0.2])
+    for k in range(3):
+        pts = _room_scan(5, 8000, origin)
+        for m in (g, o):
+            m.insertPointCloud(pts, origin, "s")
+    ok_g, e_g = g.raytrace(org, dirs, lens)
+    ok_o, e_o = o.raytrace(org, dirs, lens)
+    assert ok_o.sum() > n // 2 and (~ok_o).sum() > 20
+    assert np.array_equal(ok_g, ok_o), "success flags"
+    assert np.array_equal(e_g.view(np.uint64), e_o.view(np.uint64)), "end points"
+    # single-ray form used by the reference's other overload (V:643-664)
+    ok1, e1 = g.raytrace(origin, [1.0, 0.2, 0.0], 10.0)
+    ok2, e2 = o.raytrace(origin, [1.0, 0.2, 0.0], 10.0)
+    assert ok1[0] and ok2[0] and np.array_equal(e1, e2)
+
+
+def test_map_import_replaces_and_merges():
+    """loadMap V:263-284 (device part, vdbm_map_import): a map exported from one handle and imported into another is the
+    same map and keeps integrating identically; replace=False overwrites leaf for leaf."""
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, CFG_ROS)
+    for k in range(3):
+        pts, origin = scans.small_scan(60 + k, n=3000, scale=2.5)
+        for m in (g, o):
+            m.insertPointCloud(pts, origin, "s")
+    saved = g.exportMap()
+    g2, _ = _pair(0.1, 4.0, CFG_ROS)
+    pts0, origin0 = scans.small_scan(1, n=500, scale=1.0)
+    g2.insertPointCloud(pts0, origin0 + 7.0, "s")        # content that must disappear
+    g2.importMap(saved, replace=True)
+    assert_leafsets_equal(g2.exportMap(), saved, "imported map")
+    assert g2.mapLeafCount() == len(saved)
+    pts, origin = scans.small_scan(70, n=3000, scale=2.5)
+    for m in (g, g2, o):
+        m.insertPointCloud(pts, origin, "s")
+    assert_leafsets_equal(g2.exportMap(), o.exportMap(), "scan on top of an imported map")
+    assert_leafsets_equal(g2.exportMap(), g.exportMap(), "imported handle == original handle")
+    # merge: leaves of `part` overwrite, the rest stays
+    part = saved
+    g3, _ = _pair(0.1, 4.0, CFG_ROS)
+    g3.insertPointCloud(pts0, origin0 + 7.0, "s")
+    far = g3.exportMap()
+    g3.importMap(part, replace=False)
+    merged = g3.exportMap()
+    assert len(merged) == len(far) + len(part)
+    # fast mode / raytrace see the imported topology (coarse node sets are rebuilt)
+    ok, _e = g2.raytrace(origin, [1.0, 0.0, 0.0], 3.0)
+    ok_o, _e2 = o.raytrace(origin, [1.0, 0.0, 0.0], 3.0)
+    assert ok[0] == ok_o[0]
+
+
+def test_cast_index_rays_and_single_walls():
+    """castRayIntoGrid V:550-566 on explicit voxel pairs, addArtificialWall V:1217 / addArtificialPolygon V:1198 without the
+    restoreMapIntegrity of addArtificialAreas."""
+    g, o = _pair(0.1, 4.0, CFG_ROS)
+    rng = np.random.default_rng(21)
+    starts = rng.integers(-40, 40, size=(500, 3)).astype(np.int32)
+    ends = starts + rng.integers(-60, 60, size=(500, 3)).astype(np.int32)
+    ends[:20] = starts[:20]                         # zero-length: nothing is marked
+    ends[20:40, 1:] = starts[20:40, 1:]             # axis-aligned
+    g.castRaysIntoGrid("s", starts, ends)
+    assert o.castRaysIntoGrid("s", starts, ends) == 0
+    assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "explicit rays")
+    g.integrateUpdate(); o.integrateUpdate()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map after explicit rays")
+    for m in (g, o):
+        m.addArtificialWall([0.52, 0.5, 0.0, 1], [2.31, 0.77, 0.0, 1], -0.35, 0.55)
+        m.addArtificialPolygon(np.array([[-1.0, -1.0, 0.2, 1], [-2.0, -1.5, 0.2, 1], [-1.2, -2.4, 0.2, 1]]), -0.2, 0.3)
+        m.addArtificialWall([0.52, 0.5, 0.0, 1], [0.52, 0.5, 0.0, 1], -0.35, 0.55)   # start == end: nothing
+    assert_leafsets_equal(g.exportArtificialAreaGrid(), o.exportArtificialAreaGrid(), "walls accumulate without a restore")
+    from vdb_mapping_b200 import scans
+    pts, origin = scans.small_scan(3, n=2000, scale=2.5)
+    for m in (g, o):
+        m.insertPointCloud(pts, origin, "s")
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "updateMap re-activates the walls")

@@ -73,10 +73,15 @@ def lib() -> C.CDLL:
     sig("vdbm_section_apply_update", C.c_int, vp, i32p, i32p, u64, i32p, u64p)
     sig("vdbm_section_apply_grid", C.c_int, vp, u64, i32p, u64p, f32p, C.c_int)
     sig("vdbm_probe", C.c_int, vp, i32p, f32p, i32p)
+    sig("vdbm_map_import", C.c_int, vp, u64, i32p, u64p, f32p, C.c_int)
+    sig("vdbm_cast_index_rays", C.c_int, vp, cp, u64, i32p)
     sig("vdbm_update_create", C.c_int, vp, cp, C.c_int, pvp, dblp)
     sig("vdbm_update_apply", C.c_int, vp, C.c_int, u64, i32p, u64p, u64p, dblp, pvp)
     sig("vdbm_points_set", C.c_int, vp, vp, u64, u64, C.c_int)
     sig("vdbm_artificial_areas_add", C.c_int, vp, u64, C.POINTER(C.c_uint32), dblp, dbl, dbl)
+    sig("vdbm_artificial_walls_add", C.c_int, vp, u64, C.POINTER(C.c_uint32), dblp, dbl, dbl, C.c_int)
+    sig("vdbm_set_fast_mode", C.c_int, vp, C.c_int)
+    sig("vdbm_raytrace", C.c_int, vp, u64, dblp, dblp, dblp, i32p, dblp)
     sig("vdbm_map_integrity_restore", C.c_int, vp)
     sig("vdbm_artificial_export", C.c_int, vp, pvp)
     sig("vdbm_leafset_size", u64, vp)

@@ -100,6 +100,13 @@ struct vdbm_map
 
   ShardPlan shard{}; // ownership of map leaves across ranks (mode 0 = hash; vdbm_shard_plan_set)
 
+  // fast_mode / raytrace (V:577-602, V:675-721): node levels above the leaves as coarse key sets, built lazily
+  bool fast_mode = false; // Config::fast_mode V:1466
+  CoarseSets coarse{};
+  uint32_t coarse_cap1 = 0, coarse_cap2 = 0;
+  uint32_t coarse_built = 0; // map leaves [0, coarse_built) are in the sets
+  int32_t* d_bbox = nullptr; // [6] active bounding box of the map (min xyz, max xyz inclusive)
+
   // peer-memory exchange (multi-GPU)
   struct Exchange
   {
@@ -343,6 +350,65 @@ bool testBeforeSet(const Source& s)
   return s.prev_updates != 0 && s.prev_visits > 8 * s.prev_updates;
 }
 
+// ---- fast_mode / raytrace support: coarse node sets + active bounding box of the CURRENT map ----------------------------
+// (the reference rebuilds its VolumeRayIntersector after every integrateUpdate V:386; here the structures follow the map
+// lazily: new leaves are appended to the sets, the bounding box is re-reduced - one 64 B/leaf pass - on every use)
+int allocCoarse(vdbm_map* m, uint32_t cap1, uint32_t cap2)
+{
+  cudaFree(m->coarse.k1); cudaFree(m->coarse.k2);
+  m->coarse.k1 = m->coarse.k2 = nullptr;
+  CU_TRY(m, cudaMalloc(&m->coarse.k1, size_t(cap1) * 8));
+  CU_TRY(m, cudaMalloc(&m->coarse.k2, size_t(cap2) * 8));
+  if (!m->coarse.counts) CU_TRY(m, cudaMalloc(&m->coarse.counts, 8));
+  if (!m->d_bbox) CU_TRY(m, cudaMalloc(&m->d_bbox, 6 * sizeof(int32_t)));
+  m->coarse_cap1  = cap1;
+  m->coarse_cap2  = cap2;
+  m->coarse.mask1 = cap1 - 1;
+  m->coarse.mask2 = cap2 - 1;
+  m->coarse_built = ~0u;
+  return VDBM_OK;
+}
+
+// m->n_leaves must be current (every entry point that changes the map ends with syncCounters)
+int ensureCoarse(vdbm_map* m)
+{
+  if (!m->coarse.k1)
+  {
+    int rc = allocCoarse(m, 1u << 14, 1u << 10);
+    if (rc) return rc;
+  }
+  for (int attempt = 0; attempt < 24; ++attempt)
+  {
+    if (m->coarse_built == ~0u || m->coarse_built > m->n_leaves)
+    {
+      CU_TRY(m, cudaMemsetAsync(m->coarse.k1, 0xFF, size_t(m->coarse_cap1) * 8, m->stream));
+      CU_TRY(m, cudaMemsetAsync(m->coarse.k2, 0xFF, size_t(m->coarse_cap2) * 8, m->stream));
+      CU_TRY(m, cudaMemsetAsync(m->coarse.counts, 0, 8, m->stream));
+      m->coarse_built = 0;
+    }
+    if (m->coarse_built < m->n_leaves) launchCoarseInsert(m->mt, m->coarse_built, m->n_leaves, m->coarse, m->d_ctr, m->stream);
+    CU_TRY(m, cudaMemcpyAsync(m->h_small + 16, m->coarse.counts, 8, cudaMemcpyDeviceToHost, m->stream));
+    int rc = syncCounters(m);
+    if (rc) return rc;
+    m->coarse_built = m->n_leaves;
+    const bool overflow = (m->h_ctr->flags & kFlagUpdateOverflow) != 0;
+    const bool crowded1 = uint64_t(m->h_small[16]) * 2 > m->coarse_cap1, crowded2 = uint64_t(m->h_small[17]) * 2 > m->coarse_cap2;
+    if (!overflow && !crowded1 && !crowded2) break;
+    if (overflow)
+    {
+      m->h_ctr->flags &= ~kFlagUpdateOverflow;
+      CU_TRY(m, cudaMemcpyAsync(&m->d_ctr->flags, &m->h_ctr->flags, sizeof(unsigned), cudaMemcpyHostToDevice, m->stream));
+    }
+    rc = allocCoarse(m, (overflow || crowded1) ? m->coarse_cap1 * 2 : m->coarse_cap1, (overflow || crowded2) ? m->coarse_cap2 * 2 : m->coarse_cap2);
+    if (rc) return rc;
+  }
+  // RootNode::evalActiveBoundingBox(bbox, false): leaves that hold an active voxel
+  const int32_t init[6] = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN};
+  CU_TRY(m, cudaMemcpyAsync(m->d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, m->stream));
+  launchActiveBBox(m->mt, m->n_leaves, m->d_bbox, m->stream);
+  return VDBM_OK;
+}
+
 // ---- the raycast (K0 + K1) on device-resident points ---------------------------------------------------
 int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, uint64_t stride, const double origin[3], double range,
                   bool index_mode = false)
@@ -391,6 +457,12 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     m->rays_cap = rc;
     m->seg_cap  = seg_cap;
   }
+  a.fast_mode = (m->fast_mode && !index_mode) ? 1u : 0u;
+  if (a.fast_mode && m->n_leaves != 0)
+  {
+    int rcc = ensureCoarse(m);
+    if (rcc) return rcc;
+  }
   a.rays      = m->d_rays;
   a.ends       = index_mode ? nullptr : m->d_ends;
   a.index_mode = index_mode ? 1u : 0u;
@@ -429,6 +501,16 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     CU_TRY(m, cudaMemsetAsync(m->d_sort + n, 0, (m->seg_cap - n) * sizeof(uint32_t), m->stream));
     // The DDA kernel marks z-slice mask words; leaves the grid already holds (an earlier accumulate of this period, or
     // the failed attempt being replayed) are in the x-slice layout every other kernel works on: turn them back first.
+    if (a.fast_mode)
+    {
+      // castRayIntoGridFast V:577-602: end-voxel records from prep_rays, then one thread per ray through the map's node levels
+      launchPrepRays(a, m->d_ctr, m->stream);
+      CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
+      launchRaycastFast(a, s.g, m->mt, m->coarse, m->d_bbox, m->n_leaves == 0 ? 1u : 0u, m->d_ctr, m->stream);
+      launchCompactLeaves(s.g, m->stream, /*cook=*/false);
+    }
+    else
+    {
     launchUncookLeaves(s.g, s.n_entries, m->stream);
     launchPrepRays(a, m->d_ctr, m->stream);
     uint32_t n_long = 0, n_extra = 0;
@@ -447,6 +529,7 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
     launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream, testBeforeSet(s));
     launchCompactLeaves(s.g, m->stream, /*cook=*/true);
+    }
     CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
     CU_TRY(m, cudaGetLastError());
     CU_TRY(m, cudaMemcpyAsync(m->h_small + 8, s.g.counters, 8, cudaMemcpyDeviceToHost, m->stream));
@@ -460,6 +543,10 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     cudaEventElapsedTime(&ms, m->ev0, m->ev2);
     m->stats.last_prep_ms = ms;
     const uint32_t flags = m->h_ctr->flags;
+    if (getenv("VDBM_DEBUG"))
+      std::fprintf(stderr, "[vdbm] raycast attempt %d n=%llu seg_len=%u flags=%u bricks=%u cap=%u entries=%u clipped=%llu (before %llu) visits=%llu (before %llu)\n", attempt,
+                   (unsigned long long)n, a.seg_len, flags, s.n_bricks, s.cap, s.n_entries, (unsigned long long)m->h_ctr->clipped,
+                   (unsigned long long)before.clipped, (unsigned long long)m->h_ctr->visits, (unsigned long long)before.visits);
     // Out-of-range end points are only REPORTED (the rays are dropped, like +-inf); they must not hide an overflow of the
     // brick hash raised by the same scan: complete the grid first (grow, replay), report afterwards.
     if (flags & kFlagCoordRange) coord_range = true;
@@ -479,8 +566,11 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   m->stats.last_visits         = m->h_ctr->visits - before.visits;
   m->stats.last_touched_leaves = s.n_entries;
   m->stats.update_capacity     = std::max(m->stats.update_capacity, s.cap * uint32_t(kBrickLeaves));
-  s.prev_visits     = m->stats.last_visits;
-  s.prev_max_visits = m->h_ctr->max_visits;
+  if (!a.fast_mode)
+  {
+    s.prev_visits     = m->stats.last_visits;
+    s.prev_max_visits = m->h_ctr->max_visits;
+  }
   if (!index_mode)
   {
     m->ends_src = &s;
@@ -887,7 +977,7 @@ int ensureAsyncStaging(vdbm_map* m, int buf, size_t bytes)
 // unnecessary: one source holding data, no segmentation planned, no artificial areas, staging already large enough.
 bool asyncEligible(vdbm_map* m, Source& s, uint64_t n, const double origin[3])
 {
-  if (n == 0 || n > 0xFFFFFFF0ull || !(s.max_range > 0) || !m->config_set) return false;
+  if (n == 0 || n > 0xFFFFFFF0ull || !(s.max_range > 0) || !m->config_set || m->fast_mode) return false;
   for (int k = 0; k < 3; ++k)
     if (!std::isfinite(origin[k])) return false;
   for (auto& kv : m->sources)
@@ -958,6 +1048,10 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
   CU_TRY(mm, cudaMemsetAsync(m->d_ctr, 0, sizeof(Counters), m->stream));
   CU_TRY(mm, cudaHostAlloc(&m->h_ctr, sizeof(Counters), cudaHostAllocDefault));
   CU_TRY(mm, cudaHostAlloc(&m->h_small, 64 * sizeof(uint32_t), cudaHostAllocDefault));
+  // pinned memory is recycled, not zeroed: a stale counter block of an earlier handle would become the "before" state a
+  // replayed first scan restores
+  std::memset(m->h_ctr, 0, sizeof(Counters));
+  std::memset(m->h_small, 0, 64 * sizeof(uint32_t));
   CU_TRY(mm, cudaMalloc(&m->d_map_counters, 8));
   CU_TRY(mm, cudaMemsetAsync(m->d_map_counters, 0, 8, m->stream));
   m->mt.n_leaves = m->d_map_counters;
@@ -993,6 +1087,7 @@ void vdbm_destroy(vdbm_map* m)
   for (Source* aux : {m->scratch.get(), m->artificial.get()})
     if (aux) { freeUpdateGrid(aux->g); cudaFree(aux->d_change); }
   cudaFree(m->d_ends);
+  cudaFree(m->coarse.k1); cudaFree(m->coarse.k2); cudaFree(m->coarse.counts); cudaFree(m->d_bbox);
   freeMapPool(m->mt);
   cudaFree(m->mt.hkeys); cudaFree(m->mt.hvals);
   cudaFree(m->d_ctr); cudaFree(m->d_map_counters); cudaFree(m->d_points); cudaFree(m->d_rays); cudaFree(m->d_part);
@@ -1024,6 +1119,7 @@ int vdbm_reset(vdbm_map* m)
   CU_TRY(m, cudaMemsetAsync(m->mt.leaf_dirty, 0, size_t(m->mt.pool_cap) * 4, m->stream));
   CU_TRY(m, cudaMemsetAsync(m->d_map_counters, 0, 8, m->stream));
   m->n_leaves = 0;
+  m->coarse_built = ~0u; // the coarse node sets describe the old map: rebuilt from scratch on next use
   for (auto& kv : m->sources)
   {
     Source& s = *kv.second;
@@ -1416,6 +1512,8 @@ int vdbm_update_create(vdbm_map* m, const char* source_id, int level, vdbm_leafs
   if (level == 0) return exportGrid(m, *s, out);
   if (level == 1) return recordsToLeafset(m, s->d_change, s->n_change, out);
   if (level != 2) return fail(m, VDBM_ERR_INVALID_ARG, "update level must be 0, 1 or 2");
+  if (m->fast_mode)
+    return fail(m, VDBM_ERR_INVALID_ARG, "level 2 (reduced) updates describe castRayIntoGrid scans; in fast_mode the update grid depends on the map: use level 0");
   if (m->ends_src != s)
     return fail(m, VDBM_ERR_INVALID_ARG, "no reduced update available: level 2 describes the source's LAST accumulate call on this handle");
   int rc = scratchGrid(m);
@@ -1533,22 +1631,20 @@ int vdbm_map_integrity_restore(vdbm_map* m)
   return syncCounters(m);
 }
 
-int vdbm_artificial_areas_add(vdbm_map* m, uint64_t n_polygons, const uint32_t* counts, const double* xyz, double negative_height,
-                              double positive_height)
+// addArtificialPolygon V:1198-1207 / addArtificialWall V:1217-1236 into the artificial-area grid: one wall per consecutive point
+// pair of every polyline (plus the closing edge when closed), end points through worldToIndex V:1224-1226
+static int addWalls(vdbm_map* m, uint64_t n_polygons, const uint32_t* counts, const double* xyz, double negative_height, double positive_height,
+                    bool closed)
 {
-  if (!m || (n_polygons && (!counts || !xyz))) return VDBM_ERR_INVALID_ARG;
-  VDBM_ENTER(m);
-  int rc = vdbm_map_integrity_restore(m); // V:1181
-  if (rc) return rc;
-  rc = auxGrid(m, m->artificial, "<artificial>", 64);
+  int rc = auxGrid(m, m->artificial, "<artificial>", 64);
   if (rc) return rc;
   Source& ar = *m->artificial;
-  // addArtificialPolygon V:1200-1207: one wall per polygon edge (closing edge included), end points through worldToIndex V:1224-1226
   std::vector<int32_t> walls;
   size_t base = 0;
   for (uint64_t p = 0; p < n_polygons; ++p)
   {
-    for (uint32_t i = 0; i < counts[p]; ++i)
+    const uint32_t n_edges = closed ? counts[p] : (counts[p] ? counts[p] - 1 : 0);
+    for (uint32_t i = 0; i < n_edges; ++i)
     {
       int32_t a[3], b[3];
       if (!originIndex(m->params.resolution, xyz + 3 * (base + i), a) || !originIndex(m->params.resolution, xyz + 3 * (base + (i + 1) % counts[p]), b))
@@ -1573,6 +1669,24 @@ int vdbm_artificial_areas_add(vdbm_map* m, uint64_t n_polygons, const uint32_t* 
     return fail(m, VDBM_ERR_COORD_RANGE, "an artificial wall left the +-2^23 voxel range");
   }
   return VDBM_OK;
+}
+
+int vdbm_artificial_areas_add(vdbm_map* m, uint64_t n_polygons, const uint32_t* counts, const double* xyz, double negative_height,
+                              double positive_height)
+{
+  if (!m || (n_polygons && (!counts || !xyz))) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  int rc = vdbm_map_integrity_restore(m); // V:1181
+  if (rc) return rc;
+  return addWalls(m, n_polygons, counts, xyz, negative_height, positive_height, true);
+}
+
+int vdbm_artificial_walls_add(vdbm_map* m, uint64_t n_polylines, const uint32_t* counts, const double* xyz, double negative_height,
+                              double positive_height, int closed)
+{
+  if (!m || (n_polylines && (!counts || !xyz))) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  return addWalls(m, n_polylines, counts, xyz, negative_height, positive_height, closed != 0);
 }
 
 int vdbm_artificial_export(vdbm_map* m, vdbm_leafset** out)
@@ -1782,6 +1896,100 @@ int vdbm_section_apply_grid(vdbm_map* m, uint64_t n, const int32_t* origins, con
   launchSectionApplyGrid(m->mt, dk.as<uint64_t>(), da.as<uint64_t>(), dv.as<float>(), uint32_t(n), m->d_ctr, m->stream);
   CU_TRY(m, cudaGetLastError());
   return syncCounters(m);
+}
+
+int vdbm_map_import(vdbm_map* m, uint64_t n, const int32_t* origins, const uint64_t* active, const float* values, int replace)
+{
+  if (!m || (n && (!origins || !active || !values))) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  if (replace)
+  {
+    // loadMap V:263-284 replaces m_vdb_grid: forget every map leaf (the update grids of the sources are left alone)
+    CU_TRY(m, cudaMemsetAsync(m->mt.hkeys, 0xFF, size_t(m->hcap) * 8, m->stream));
+    CU_TRY(m, cudaMemsetAsync(m->mt.leaf_dirty, 0, size_t(m->mt.pool_cap) * 4, m->stream));
+    CU_TRY(m, cudaMemsetAsync(m->d_map_counters, 0, 8, m->stream));
+    m->n_leaves = 0;
+    m->coarse_built = ~0u;
+    int rc = syncCounters(m);
+    if (rc) return rc;
+  }
+  // leaf for leaf: values and active mask of the given leaf replace the map's (a leaf without any content is not created)
+  return vdbm_section_apply_grid(m, n, origins, active, values, 0);
+}
+
+int vdbm_cast_index_rays(vdbm_map* m, const char* source_id, uint64_t n_rays, const int32_t* rays6)
+{
+  if (!m || (n_rays && !rays6) || n_rays > 0xFFFFFFF0ull) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  Source* s = findSource(m, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  if (n_rays == 0) return VDBM_OK;
+  TempBuf d(m->stream);
+  CU_TRY(m, d.alloc(n_rays * 24));
+  CU_TRY(m, cudaMemcpyAsync(d.p, rays6, n_rays * 24, cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  // castRayIntoGrid V:550-566 for explicit voxel pairs: the wall kernel with one height level is exactly that loop
+  int rc = markIntoGrid(m, *s, [&] { launchWallDDA(d.as<int32_t>(), uint32_t(n_rays), 0, 1, s->g, m->d_ctr, m->stream); });
+  if (rc) return rc;
+  if (m->h_ctr->flags & kFlagCoordRange)
+  {
+    CU_TRY(m, cudaMemsetAsync(&m->d_ctr->flags, 0, sizeof(unsigned), m->stream));
+    return fail(m, VDBM_ERR_COORD_RANGE, "a ray left the +-2^23 voxel range");
+  }
+  return VDBM_OK;
+}
+
+int vdbm_set_fast_mode(vdbm_map* m, int on)
+{
+  if (!m) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  m->fast_mode = on != 0;
+  return VDBM_OK;
+}
+
+int vdbm_raytrace(vdbm_map* m, uint64_t n, const double* origins, const double* directions, const double* max_lengths, int32_t* success,
+                  double* end_points)
+{
+  if (!m || (n && (!origins || !directions || !max_lengths || !success || !end_points)) || n > 0xFFFFFFF0ull) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  if (n == 0) return VDBM_OK;
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  if (m->n_leaves != 0)
+  {
+    rc = ensureCoarse(m);
+    if (rc) return rc;
+  }
+  else if (!m->d_bbox)
+  {
+    rc = allocCoarse(m, 1u << 14, 1u << 10);
+    if (rc) return rc;
+  }
+  TempBuf in(m->stream), out(m->stream);
+  CU_TRY(m, in.alloc(n * 7 * sizeof(double)));
+  CU_TRY(m, out.alloc(n * (3 * sizeof(double) + sizeof(int32_t))));
+  double* d_o = in.as<double>();
+  double* d_d = d_o + 3 * n;
+  double* d_l = d_d + 3 * n;
+  double* d_e = out.as<double>();
+  int32_t* d_ok = reinterpret_cast<int32_t*>(d_e + 3 * n);
+  CU_TRY(m, cudaMemcpyAsync(d_o, origins, n * 3 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(d_d, directions, n * 3 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(d_l, max_lengths, n * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  launchRaytrace(n, d_o, d_d, d_l, m->params.resolution, 1.0 / m->params.resolution, m->mt, m->coarse, m->d_bbox, m->n_leaves == 0 ? 1u : 0u, d_ok,
+                 d_e, m->d_ctr, m->stream);
+  CU_TRY(m, cudaMemcpyAsync(end_points, d_e, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CU_TRY(m, cudaMemcpyAsync(success, d_ok, n * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+  rc = syncCounters(m);
+  if (rc) return rc;
+  if (m->h_ctr->flags & kFlagCoordRange)
+  {
+    m->h_ctr->flags &= ~kFlagCoordRange;
+    CU_TRY(m, cudaMemcpyAsync(&m->d_ctr->flags, &m->h_ctr->flags, sizeof(unsigned), cudaMemcpyHostToDevice, m->stream));
+    CU_TRY(m, cudaStreamSynchronize(m->stream));
+    return fail(m, VDBM_ERR_COORD_RANGE, "some rays left the +-2^23 voxel range and were reported as misses");
+  }
+  return VDBM_OK;
 }
 
 int vdbm_probe(vdbm_map* m, const int32_t xyz[3], float* value, int32_t* active)

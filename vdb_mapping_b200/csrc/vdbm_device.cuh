@@ -140,6 +140,17 @@ struct MapTable
   uint32_t* n_leaves; // device counter
 };
 
+// Node levels of the reference's 5-4-3 tree above the leaves, for fast_mode / raytrace (VolumeRayIntersector): open-addressing
+// SETS of the 128^3-voxel (k1) and 4096^3-voxel (k2) blocks that hold at least one map leaf; key = packLeafKey(voxel >> 7)
+// resp. (voxel >> 12). Built lazily and incrementally from the (append-only) leaf pool.
+struct CoarseSets
+{
+  uint64_t* k1;
+  uint64_t* k2;
+  uint32_t mask1, mask2;
+  uint32_t* counts; // device: [0] keys in k1, [1] keys in k2
+};
+
 struct LogOdds
 {
   float hit, miss, thres_min, thres_max, max_lo, min_lo;
@@ -230,6 +241,7 @@ struct RaycastArgs
   const uint32_t* sorted_keys; // [n_segs] the keys in that order (descending)
   int4* ends;          // [n] or nullptr: end voxel of every ray + (bit0 valid | bit1 hit), the scan's "reduced" update
   uint32_t index_mode; // 1: `points` holds such int4 end-voxel records (16-byte stride) instead of world points
+  uint32_t fast_mode;  // 1: castRayIntoGridFast follows (prep_rays only produces the end-voxel records and the ray statistics)
 };
 
 // Peer-memory exchange state (device-visible part). inbox layout on every rank, SoA so that every record's 16 mask
@@ -324,6 +336,13 @@ void launchOverwrite(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, 
 void launchWallDDA(const int32_t* d_walls, uint32_t n_walls, int32_t neg_index, int32_t pos_index, UpdateGrid g, Counters* ctr, cudaStream_t s);
 void launchGridActivate(UpdateGrid g, uint32_t n_entries, MapTable mt, Counters* ctr, cudaStream_t s);
 void launchRestoreState(UpdateGrid g, uint32_t n_entries, MapTable mt, LogOdds lo, Counters* ctr, cudaStream_t s);
+// fast_mode / raytrace
+void launchCoarseInsert(MapTable mt, uint32_t from, uint32_t to, CoarseSets cs, Counters* ctr, cudaStream_t s);
+void launchActiveBBox(MapTable mt, uint32_t n_leaves, int32_t* out6, cudaStream_t s); // out6 pre-set to INT_MAX x3, INT_MIN x3
+void launchRaycastFast(const RaycastArgs& a, UpdateGrid g, MapTable mt, CoarseSets cs, const int32_t* bbox6, uint32_t map_empty, Counters* ctr,
+                       cudaStream_t s);
+void launchRaytrace(uint64_t n, const double* origins, const double* directions, const double* max_lengths, double res, double inv_res, MapTable mt,
+                    CoarseSets cs, const int32_t* bbox6, uint32_t map_empty, int32_t* success, double* end_points, Counters* ctr, cudaStream_t s);
 uint32_t launchCount(); // kernels of this library launched by this process
 // CUB radix sort (descending) of (visit count, ray index) on key bits [3, 11) (one radix pass); returns temp bytes when d_temp == nullptr
 size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,

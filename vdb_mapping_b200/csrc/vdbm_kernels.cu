@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
     a.sort_keys[i] = (key != 0u && key < kSortMinKey) ? kSortMinKey : key;
     a.sort_idx[i]  = uint32_t(i);
   }
+  if (a.fast_mode) visits = 0; // fast_mode counts the marks castRayIntoGridFast really makes (raycast_fast_kernel)
   // warp-aggregated statistics
   const unsigned vmax = __reduce_max_sync(kFull, unsigned(visits));
   visits      = __reduce_add_sync(kFull, unsigned(visits)); // per-lane visits <= 1 + 3*2^24, 32 lanes fit in 32 bits
@@ -1926,6 +1927,401 @@ __global__ void __launch_bounds__(256) restore_state_kernel(UpdateGrid g, uint32
 }
 
 
+// ====================================================================================================
+// fast_mode (castRayIntoGridFast, VDBMapping.hpp:577-602) and raytrace (VDBMapping.hpp:675-721): SURVEY.md 8f N3 / N4.
+// Both are built on openvdb::tools::VolumeRayIntersector<FloatGrid>, restated here on the flat map: the node levels of the
+// 5-4-3 tree are the 4096^3 / 128^3 / 8^3 blocks that hold at least one map leaf (nodes of this path are only ever created
+// together with a leaf and never pruned; the device map holds no tiles), kept as two small hash sets of coarse block keys
+// next to the leaf hash. Arithmetic follows math/Ray.h, math/DDA.h and tools/RayIntersector.h operation for operation
+// (explicit _rn intrinsics, -fmad=false). Parity is unpinned at the
+// OpenVDB boundary like everything else that has no vector in the reference.
+// ====================================================================================================
+namespace {
+
+struct HRay
+{
+  double eye[3], dir[3], inv[3];
+};
+struct DdaState
+{
+  double t0, t1, next[3], delta[3];
+  int32_t vox[3], step[3];
+};
+
+// DDA<Ray, LOG2>::init(ray, startTime, maxTime)
+template <int LOG2>
+__device__ __forceinline__ void ddaInit(DdaState& d, const HRay& r, double start, double maxt)
+{
+  constexpr int32_t DIM = int32_t(1) << LOG2;
+  d.t0 = start;
+  d.t1 = maxt;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    const double pos = __dadd_rn(r.eye[k], __dmul_rn(r.dir[k], start)); // ray(t) = eye + dir * t
+    const int32_t v  = int32_t(floor(pos)) & ~(DIM - 1);
+    d.vox[k]         = v;
+    if (r.dir[k] == 0.0)
+    {
+      d.step[k]  = 0;
+      d.next[k]  = DBL_MAX;
+      d.delta[k] = DBL_MAX;
+    }
+    else if (r.inv[k] > 0.0)
+    {
+      d.step[k]  = DIM;
+      d.next[k]  = __dadd_rn(start, __dmul_rn(__dsub_rn(double(v + DIM), pos), r.inv[k]));
+      d.delta[k] = __dmul_rn(double(DIM), r.inv[k]);
+    }
+    else
+    {
+      d.step[k]  = -DIM;
+      d.next[k]  = __dadd_rn(start, __dmul_rn(__dsub_rn(double(v), pos), r.inv[k]));
+      d.delta[k] = __dmul_rn(double(-DIM), r.inv[k]);
+    }
+  }
+}
+// DDA::step(): axis = math::MinIndex(next) (x iff n0 < n1 && n0 < n2; else y iff n1 < n2; else z)
+__device__ __forceinline__ bool ddaStep(DdaState& d)
+{
+  if (d.next[0] < d.next[1] && d.next[0] < d.next[2])
+  {
+    d.t0 = d.next[0];
+    d.next[0] = __dadd_rn(d.next[0], d.delta[0]);
+    d.vox[0] += d.step[0];
+  }
+  else if (d.next[1] < d.next[2])
+  {
+    d.t0 = d.next[1];
+    d.next[1] = __dadd_rn(d.next[1], d.delta[1]);
+    d.vox[1] += d.step[1];
+  }
+  else
+  {
+    d.t0 = d.next[2];
+    d.next[2] = __dadd_rn(d.next[2], d.delta[2]);
+    d.vox[2] += d.step[2];
+  }
+  return d.t0 <= d.t1;
+}
+// DDA::next() = math::Min(t1, next[0], next[1], next[2])
+__device__ __forceinline__ double ddaNext(const DdaState& d)
+{
+  const double a = d.next[0] < d.t1 ? d.next[0] : d.t1;
+  const double b = d.next[2] < d.next[1] ? d.next[2] : d.next[1];
+  return b < a ? b : a;
+}
+
+__device__ __forceinline__ bool coarseContains(const uint64_t* keys, uint32_t mask, uint64_t key)
+{
+  uint32_t h = uint32_t(mix64(key)) & mask;
+  for (uint32_t probe = 0; probe <= mask; ++probe)
+  {
+    const uint64_t k = keys[h];
+    if (k == key) return true;
+    if (k == kEmptyKey) return false;
+    h = (h + 1) & mask;
+  }
+  return false;
+}
+__device__ __forceinline__ uint32_t mapFindLeaf(const MapTable& mt, uint64_t key)
+{
+  uint32_t h = uint32_t(mix64(key)) & mt.hcap_mask;
+  for (uint32_t probe = 0; probe <= mt.hcap_mask; ++probe)
+  {
+    const uint64_t k = mt.hkeys[h];
+    if (k == key) return mt.hvals[h];
+    if (k == kEmptyKey) return kInvalid;
+    h = (h + 1) & mt.hcap_mask;
+  }
+  return kInvalid;
+}
+
+// Ray::clip(bbox) (Ray::intersects): slab test; the span is only replaced on a hit
+__device__ __forceinline__ bool rayClip(const HRay& r, const int32_t* bb /*min xyz, max xyz*/, double& t0, double& t1)
+{
+  double a0 = t0, a1 = t1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    double a = __dmul_rn(__dsub_rn(double(bb[k]), r.eye[k]), r.inv[k]);
+    double b = __dmul_rn(__dsub_rn(double(bb[3 + k]), r.eye[k]), r.inv[k]);
+    if (a > b) { const double t = a; a = b; b = t; }
+    if (a > a0) a0 = a;
+    if (b < a1) a1 = b;
+    if (a0 > a1) return false;
+  }
+  t0 = a0;
+  t1 = a1;
+  return true;
+}
+
+constexpr double kTimeDelta = 1e-9; // math::Delta<double>::value()
+
+// VolumeHDDA<Tree, Ray, 2> over the ray span [t0, t1]: fn(span_t0, span_t1) is called for every valid span of consecutive
+// leaf nodes; it returns true to terminate (march) or false to go on (hits). The last span (closed by the end of the ray)
+// is delivered like the others.
+template <typename Fn>
+__device__ __forceinline__ void volumeHdda(const HRay& r, double t0, double t1, const MapTable& mt, const CoarseSets& cs, Fn&& fn)
+{
+  double s0 = -1.0, s1 = -1.0;
+  DdaState d2;
+  ddaInit<12>(d2, r, t0, t1);
+  do
+  {
+    if (coarseContains(cs.k2, cs.mask2, packLeafKey(d2.vox[0] >> 12, d2.vox[1] >> 12, d2.vox[2] >> 12)))
+    {
+      DdaState d1;
+      ddaInit<7>(d1, r, d2.t0, ddaNext(d2));
+      do
+      {
+        if (coarseContains(cs.k1, cs.mask1, packLeafKey(d1.vox[0] >> 7, d1.vox[1] >> 7, d1.vox[2] >> 7)))
+        {
+          DdaState d0;
+          ddaInit<3>(d0, r, d1.t0, ddaNext(d1));
+          do
+          {
+            if (mapFindLeaf(mt, packLeafKey(d0.vox[0] >> 3, d0.vox[1] >> 3, d0.vox[2] >> 3)) != kInvalid)
+            {
+              if (s0 < 0.0) s0 = d0.t0;
+            }
+            else if (s0 >= 0.0)
+            {
+              s1 = d0.t0;
+              if (__dsub_rn(s1, s0) > kTimeDelta && fn(s0, s1)) return;
+              s0 = s1 = -1.0;
+            }
+          } while (ddaStep(d0));
+          if (s0 >= 0.0) s1 = d0.t1;
+        }
+        else if (s0 >= 0.0)
+        {
+          s1 = d1.t0;
+          if (__dsub_rn(s1, s0) > kTimeDelta && fn(s0, s1)) return;
+          s0 = s1 = -1.0;
+        }
+      } while (ddaStep(d1));
+      if (s0 >= 0.0) s1 = d1.t1;
+    }
+    else if (s0 >= 0.0)
+    {
+      s1 = d2.t0;
+      if (__dsub_rn(s1, s0) > kTimeDelta && fn(s0, s1)) return;
+      s0 = s1 = -1.0;
+    }
+  } while (ddaStep(d2));
+  if (s0 >= 0.0) s1 = d2.t1;
+  if (__dsub_rn(s1, s0) > kTimeDelta) fn(s0, s1);
+}
+
+// GridT::Accessor::isValueOn(voxel) on the flat map with a one-leaf cache
+struct LeafCache
+{
+  uint64_t key  = kEmptyKey;
+  uint32_t leaf = kInvalid;
+};
+__device__ __forceinline__ bool mapIsValueOn(const MapTable& mt, LeafCache& c, const int32_t v[3])
+{
+  const uint64_t key = packLeafKey(v[0] >> 3, v[1] >> 3, v[2] >> 3);
+  if (key != c.key)
+  {
+    c.key  = key;
+    c.leaf = mapFindLeaf(mt, key);
+  }
+  if (c.leaf == kInvalid) return false;
+  return (mt.leaf_mask[size_t(c.leaf) * 8 + (v[0] & 7)] >> (((v[1] & 7) << 3) | (v[2] & 7))) & 1ull;
+}
+
+} // namespace
+
+// the 128^3 and 4096^3 block keys of map leaves [from, to) -> the coarse sets (leaves are only ever appended to the pool)
+__global__ void __launch_bounds__(256) coarse_insert_kernel(MapTable mt, uint32_t from, uint32_t to, CoarseSets cs, Counters* ctr)
+{
+  const uint32_t i = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= to) return;
+  const uint64_t key = mt.leaf_keys[i];
+  const int32_t lx = int32_t(uint32_t(key >> 42) & 0x1FFFFFu) - kLeafBias, ly = int32_t(uint32_t(key >> 21) & 0x1FFFFFu) - kLeafBias,
+                lz = int32_t(uint32_t(key) & 0x1FFFFFu) - kLeafBias;
+#pragma unroll
+  for (int level = 0; level < 2; ++level)
+  {
+    const int sh         = level ? 9 : 4; // leaf coordinate -> 128^3 block (>> 4), 4096^3 block (>> 9)
+    uint64_t* keys       = level ? cs.k2 : cs.k1;
+    const uint32_t mask  = level ? cs.mask2 : cs.mask1;
+    const uint64_t ckey  = packLeafKey(lx >> sh, ly >> sh, lz >> sh);
+    uint32_t h           = uint32_t(mix64(ckey)) & mask;
+    bool done            = false;
+    for (uint32_t probe = 0; probe <= mask && !done; ++probe)
+    {
+      const uint64_t k = keys[h];
+      if (k == ckey) done = true;
+      else if (k == kEmptyKey)
+      {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + h), kEmptyKey, ckey);
+        if (old == kEmptyKey)
+        {
+          atomicAdd(level ? &cs.counts[1] : &cs.counts[0], 1u);
+          done = true;
+        }
+        else if (old == ckey) done = true;
+      }
+      h = (h + 1) & mask;
+    }
+    if (!done) atomicOr(&ctr->flags, kFlagUpdateOverflow);
+  }
+}
+
+// RootNode::evalActiveBoundingBox(bbox, visit_voxels = false): union of the node boxes of all leaves that hold an active voxel.
+// out6 = min xyz, max xyz (voxel coordinates, max inclusive), initialised to INT_MAX / INT_MIN by the host.
+__global__ void __launch_bounds__(256) active_bbox_kernel(MapTable mt, uint32_t n_leaves, int32_t* out6)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+  if (i < n_leaves)
+  {
+    const uint64_t* w = mt.leaf_mask + size_t(i) * 8;
+    if (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7])
+    {
+      int32_t o[3];
+      unpackLeafOrigin(mt.leaf_keys[i], o[0], o[1], o[2]);
+      for (int k = 0; k < 3; ++k) { mn[k] = o[k]; mx[k] = o[k] + 7; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    mn[k] = __reduce_min_sync(kFull, mn[k]);
+    mx[k] = __reduce_max_sync(kFull, mx[k]);
+  }
+  if ((threadIdx.x & 31) == 0 && mn[0] != INT32_MAX)
+  {
+    for (int k = 0; k < 3; ++k)
+    {
+      atomicMin(out6 + k, mn[k]);
+      atomicMax(out6 + 3 + k, mx[k]);
+    }
+  }
+}
+
+// castRayIntoGridFast for every prepared ray (thread per ray; the rays of a fast-mode scan are cheap: ~len/8 node probes plus
+// voxel probes inside the spans). bb = intersector bbox (max already offset by 1). Marks x-slice words like every
+// non-DDA marker. Followed by the end point rule V:533-536.
+__global__ void __launch_bounds__(128) raycast_fast_kernel(RaycastArgs a, UpdateGrid g, MapTable mt, CoarseSets cs, const int32_t* bbox6,
+                                                          uint32_t map_empty, Counters* ctr)
+{
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  unsigned marks = 0;
+  if (i < a.n)
+  {
+    const int4 q = a.ends[i];
+    if (q.w & 1)
+    {
+      uint64_t cur_bkey = kEmptyKey;
+      uint32_t slot     = kInvalid;
+      auto mark = [&](const int32_t v[3], bool value) {
+        const uint64_t bkey = packLeafKey(v[0] >> 6, v[1] >> 6, v[2] >> 6);
+        if (bkey != cur_bkey) { cur_bkey = bkey; slot = brickFindOrInsert(g, bkey, ctr); }
+        if (slot == kInvalid) return;
+        const size_t w     = size_t(slot) * (kBrickLeaves * 8) + brickWordOffset(v[0], v[1], v[2]);
+        const uint64_t bit = uint64_t(1) << (((v[1] & 7) << 3) | (v[2] & 7));
+        redOr64(g.act + w, bit);
+        if (value) redOr64(g.val + w, bit);
+      };
+      const int32_t e[3] = {q.x, q.y, q.z};
+      if (!map_empty) // V:522
+      {
+        HRay r;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+          r.dir[k] = __dsub_rn(double(e[k]), double(a.origin_idx[k])); // V:586
+          r.eye[k] = __dadd_rn(double(a.origin_idx[k]), 0.5);          // V:587
+          r.inv[k] = __ddiv_rn(1.0, r.dir[k]);
+        }
+        int32_t bb[6];
+        for (int k = 0; k < 3; ++k) { bb[k] = bbox6[k]; bb[3 + k] = int32_t(uint32_t(bbox6[3 + k]) + 1u); }
+        double t0 = 0.0, t1 = 1.0;
+        rayClip(r, bb, t0, t1); // setIndexRay V:588; a miss leaves [0, 1]
+        LeafCache cache;
+        volumeHdda(r, t0, t1, mt, cs, [&](double h0, double h1) {
+          DdaState d;
+          ddaInit<0>(d, r, h0, h1); // fine_ray V:593-594
+          do
+          {
+            if (mapIsValueOn(mt, cache, d.vox)) // V:597
+            {
+              mark(d.vox, false);
+              ++marks;
+            }
+          } while (ddaStep(d));
+          return false;
+        });
+      }
+      if (q.w & 2) mark(e, true); // V:533-536
+    }
+  }
+  marks = __reduce_add_sync(kFull, marks);
+  if ((threadIdx.x & 31) == 0 && marks) atomicAdd(&ctr->visits, (unsigned long long)marks);
+}
+
+// raytrace V:675-721, thread per ray. success: 1 hit, 0 miss; a ray whose index-space end points leave the +-2^23 voxel range
+// is reported as a miss and raises kFlagCoordRange.
+__global__ void __launch_bounds__(128) raytrace_kernel(uint64_t n, const double* origins, const double* directions, const double* max_lengths,
+                                                      double res, double inv_res, MapTable mt, CoarseSets cs, const int32_t* bbox6,
+                                                      uint32_t map_empty, int32_t* success, double* end_points, Counters* ctr)
+{
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  HRay r;
+  const double dx = directions[3 * i], dy = directions[3 * i + 1], dz = directions[3 * i + 2];
+  const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+  const double il  = __ddiv_rn(1.0, len); // Vec3::normalize: *= 1 / length
+  const double d3[3] = {dx, dy, dz};
+  bool in_range = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    const double dn = __dmul_rn(__dmul_rn(d3[k], il), max_lengths[i]);  // V:691-692
+    r.eye[k]        = __dmul_rn(origins[3 * i + k], inv_res);           // V:694
+    r.dir[k]        = __dmul_rn(dn, inv_res);                           // V:695
+    r.inv[k]        = __ddiv_rn(1.0, r.dir[k]);
+    if (!(fabs(r.eye[k]) < double(kVoxelLimit)) || !(fabs(__dadd_rn(r.eye[k], r.dir[k])) < double(kVoxelLimit))) in_range = false;
+  }
+  bool hit = false;
+  double h0 = -1.0, h1 = -1.0;
+  if (!in_range) atomicOr(&ctr->flags, kFlagCoordRange);
+  else if (!map_empty)
+  {
+    int32_t bb[6];
+    for (int k = 0; k < 3; ++k) { bb[k] = bbox6[k]; bb[3 + k] = int32_t(uint32_t(bbox6[3 + k]) + 1u); }
+    double t0 = 0.0, t1 = 1.0;
+    rayClip(r, bb, t0, t1);
+    if (__dsub_rn(t1, t0) > kTimeDelta) // VolumeHDDA::march: only a valid ray is marched
+      volumeHdda(r, t0, t1, mt, cs, [&](double a0, double a1) {
+        if (hit) return true;
+        h0  = a0;
+        h1  = a1;
+        hit = true;
+        return true;
+      });
+  }
+  if (hit)
+  {
+    DdaState d;
+    ddaInit<0>(d, r, h0, h1);
+    LeafCache cache;
+    while (ddaStep(d) && !mapIsValueOn(mt, cache, d.vox)) {} // V:709-713
+    for (int k = 0; k < 3; ++k) end_points[3 * i + k] = __dmul_rn(double(d.vox[k]), res); // V:714
+    success[i] = 1;
+  }
+  else
+  {
+    for (int k = 0; k < 3; ++k) end_points[3 * i + k] = __dmul_rn(__dadd_rn(r.eye[k], r.dir[k]), res); // V:719
+    success[i] = 0;
+  }
+}
+
+
 // Order-independent checksum of the map (multi-GPU parity witness: the sum over all shards must equal the single-GPU
 // map's). Warp per leaf; a leaf's hash mixes its key, its 8 mask words and its 512 value bit patterns position by position.
 __global__ void __launch_bounds__(256) map_checksum_kernel(MapTable mt, uint32_t n_leaves, unsigned long long* out2)
@@ -2199,6 +2595,29 @@ void launchPullUpdate(UpdateGrid g, const uint64_t* inbox, const unsigned long l
   VDBM_LAUNCH(pull_update_kernel, unsigned(smCount()) * 4u, 256, s, g, inbox, cap, n_ranks, parity, counts_out, ctr);
 }
 
+void launchCoarseInsert(MapTable mt, uint32_t from, uint32_t to, CoarseSets cs, Counters* ctr, cudaStream_t s)
+{
+  if (to <= from) return;
+  VDBM_LAUNCH(coarse_insert_kernel, blocksFor(to - from, 256), 256, s, mt, from, to, cs, ctr);
+}
+void launchActiveBBox(MapTable mt, uint32_t n_leaves, int32_t* out6, cudaStream_t s)
+{
+  if (!n_leaves) return;
+  VDBM_LAUNCH(active_bbox_kernel, blocksFor(n_leaves, 256), 256, s, mt, n_leaves, out6);
+}
+void launchRaycastFast(const RaycastArgs& a, UpdateGrid g, MapTable mt, CoarseSets cs, const int32_t* bbox6, uint32_t map_empty, Counters* ctr,
+                       cudaStream_t s)
+{
+  if (!a.n) return;
+  VDBM_LAUNCH(raycast_fast_kernel, blocksFor(a.n, 128), 128, s, a, g, mt, cs, bbox6, map_empty, ctr);
+}
+void launchRaytrace(uint64_t n, const double* origins, const double* directions, const double* max_lengths, double res, double inv_res, MapTable mt,
+                    CoarseSets cs, const int32_t* bbox6, uint32_t map_empty, int32_t* success, double* end_points, Counters* ctr, cudaStream_t s)
+{
+  if (!n) return;
+  VDBM_LAUNCH(raytrace_kernel, blocksFor(n, 128), 128, s, n, origins, directions, max_lengths, res, inv_res, mt, cs, bbox6, map_empty, success,
+         end_points, ctr);
+}
 void launchMapChecksum(MapTable mt, uint32_t n_leaves, unsigned long long* out2, cudaStream_t s)
 {
   if (!n_leaves) return;

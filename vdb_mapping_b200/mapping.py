@@ -330,6 +330,48 @@ class OccupancyVDBMapping:
         self._check(self._L.vdbm_artificial_export(self._h, C.byref(out)))
         return self._take(out, False)
 
+    def addArtificialWall(self, start, end, negative_height: float, positive_height: float):
+        """VDBMapping.hpp:1217-1236 (no restoreMapIntegrity, unlike addArtificialAreas)."""
+        xyz = np.ascontiguousarray(np.stack([np.asarray(start, dtype=np.float64)[:3], np.asarray(end, dtype=np.float64)[:3]]))
+        counts = np.asarray([2], dtype=np.uint32)
+        self._check(self._L.vdbm_artificial_walls_add(self._h, 1, counts.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(xyz), float(negative_height),
+                                                       float(positive_height), 0))
+
+    def addArtificialPolygon(self, polygon, negative_height: float, positive_height: float):
+        """VDBMapping.hpp:1198-1207: one wall per edge, closing edge included."""
+        xyz = np.ascontiguousarray(np.asarray(polygon, dtype=np.float64)[:, :3])
+        counts = np.asarray([xyz.shape[0]], dtype=np.uint32)
+        self._check(self._L.vdbm_artificial_walls_add(self._h, 1, counts.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(xyz), float(negative_height),
+                                                       float(positive_height), 1))
+
+    # ---- fast_mode (VDBMapping.hpp:577-602) and raytrace (VDBMapping.hpp:675-721) ----
+    def setFastMode(self, on: bool):
+        """Config::fast_mode (VDBMapping.hpp:1466): accumulate / insert use castRayIntoGridFast."""
+        self._check(self._L.vdbm_set_fast_mode(self._h, int(bool(on))))
+
+    def raytrace(self, origins, directions, max_lengths):
+        """Batch raytrace (VDBMapping.hpp:675-721): returns (success bool[n], end_points float64[n, 3])."""
+        o = np.ascontiguousarray(np.asarray(origins, dtype=np.float64).reshape(-1, 3))
+        d = np.ascontiguousarray(np.asarray(directions, dtype=np.float64).reshape(-1, 3))
+        ln = np.ascontiguousarray(np.broadcast_to(np.asarray(max_lengths, dtype=np.float64), (o.shape[0],)))
+        ok = np.zeros(o.shape[0], dtype=np.int32)
+        e = np.zeros((o.shape[0], 3), dtype=np.float64)
+        self._check(self._L.vdbm_raytrace(self._h, o.shape[0], _dp(o), _dp(d), _dp(ln), ok.ctypes.data_as(C.POINTER(C.c_int32)), _dp(e)))
+        return ok.astype(bool), e
+
+    def importMap(self, leaves: LeafSet, replace: bool = True):
+        """loadMap (VDBMapping.hpp:263-284), device part: the leaf set becomes the map (replace) or overwrites it leaf for leaf."""
+        i32p, u64p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_float)
+        o = np.ascontiguousarray(leaves.origins, dtype=np.int32)
+        a = np.ascontiguousarray(leaves.active, dtype=np.uint64)
+        v = np.ascontiguousarray(leaves.values, dtype=np.float32)
+        self._check(self._L.vdbm_map_import(self._h, o.shape[0], o.ctypes.data_as(i32p), a.ctypes.data_as(u64p), v.ctypes.data_as(f32p), int(replace)))
+
+    def castRaysIntoGrid(self, source_id: str, starts, ends):
+        """castRayIntoGrid (VDBMapping.hpp:550-566) for explicit voxel index pairs, into the source's update grid."""
+        r = np.ascontiguousarray(np.concatenate([np.asarray(starts, dtype=np.int32).reshape(-1, 3), np.asarray(ends, dtype=np.int32).reshape(-1, 3)], axis=1))
+        self._check(self._L.vdbm_cast_index_rays(self._h, source_id.encode(), r.shape[0], r.ctypes.data_as(C.POINTER(C.c_int32))))
+
     def probe(self, coord):
         c = np.ascontiguousarray(coord, dtype=np.int32)
         v, a = C.c_float(0), C.c_int32(0)
