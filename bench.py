@@ -661,6 +661,9 @@ def run_ours(args, rank, world, local_rank):
     # (with N > 1 that is the rank's owned share after the exchange, not the leaves its own rays touched)
     L_upd = mean(res_v["upd_leaves"]) if res_v["upd_leaves"] else L
     upd_bytes = 4352 * L_upd
+    if world > 1:
+        # rank 0's own kernels: it raycasts its rays (16 B/point in, 128 B per touched leaf out) and integrates the leaves it OWNS
+        b_alg = 16 * n_pts + 128 * L + upd_bytes
     tr_dda, tr_src = measured_traffic("raycast_dda_kernel")
     tr_upd, _ = measured_traffic("apply_update_kernel")
     traffic = (tr_dda + tr_upd) if (tr_dda is not None and tr_upd is not None and cfg == 2) else None

@@ -261,6 +261,11 @@ int32_t vdbm_leaf_owner(const int32_t origin[3], int32_t n_ranks);
  * (vdb_mapping_b200/dist.py plans the bounds from the first scan). Every rank must set the same plan; it cannot change
  * while the map holds leaves. */
 int vdbm_shard_plan_set(vdbm_map* map, int32_t mode, int32_t n_ranks, const int32_t center_leaf_xy[2], const double* bounds);
+/* Ray split on the device: with n_ranks > 1 every accumulate / raycast / insert of this handle casts only the points whose
+ * direction around the SCAN ORIGIN (diamond angle of (x - origin.x, y - origin.y)) lies in sector `rank` of `bounds` (same
+ * convention as the shard plan; invalid points belong to the sector that holds angle 0). Give every rank of a box the whole
+ * cloud and the same bounds and each ray is cast exactly once. n_ranks <= 1 switches the filter off. */
+int vdbm_ray_sector_set(vdbm_map* map, int32_t n_ranks, int32_t rank, const double* bounds);
 /* owner under the handle's plan (mode 0: same as vdbm_leaf_owner) */
 int32_t vdbm_leaf_owner_planned(vdbm_map* map, const int32_t origin[3], int32_t n_ranks);
 /* Order-independent parity witness of a (sharded) map: out2[0] = sum over the leaves of this handle of a 64-bit hash of
@@ -289,6 +294,9 @@ int vdbm_update_import_device(vdbm_map* map, const char* source_id, const void* 
 #define VDBM_IPC_HANDLE_BYTES 128
 int vdbm_exchange_create(vdbm_map* map, int32_t rank, int32_t n_ranks, uint64_t capacity_records_per_sender, void* handles_out);
 int vdbm_exchange_connect(vdbm_map* map, const void* all_handles);
+/* vdbm_exchange_connect for handles that live in THIS process (one per GPU): peers[r] is the handle created with rank r
+ * (peers[own rank] is ignored); peer access is enabled and the inboxes are addressed directly, no CUDA IPC involved. */
+int vdbm_exchange_connect_peers(vdbm_map* map, vdbm_map* const* peers);
 int vdbm_update_push(vdbm_map* map, const char* source_id);
 int vdbm_update_pull(vdbm_map* map, const char* source_id);
 /* vdbm_update_pull followed by vdbm_integrate(map, 0) with one host synchronisation instead of two: the update kernels are
@@ -297,6 +305,38 @@ int vdbm_update_pull_integrate(vdbm_map* map, const char* source_id);
 /* device times (ms, CUDA events) of the last push / pull pair: out[0] bin+send kernels, out[1] wait for the peers'
  * epoch words (includes their raycast skew), out[2] import + leaf compaction */
 int vdbm_exchange_timings(vdbm_map* map, float* out3);
+
+/* ---- one process, several GPUs (SURVEY.md 8e from the C ABI: a ROS node is ONE process) ------------------------------
+ * A vdbm_group is a sharded map on n_devices GPUs of one NVLink / NVSwitch box, driven from one process: one vdbm_map per
+ * device (each with its own worker thread), inboxes wired with direct peer pointers, the same fused bin-and-send exchange as
+ * the multi-process path. integrateUpdate V:375-387 integrates ONE map; here every shard integrates the leaves it owns and
+ * the union of the shards is that map (vdbm_group_checksum == vdbm_map_checksum of the same scans on one GPU).
+ *   vdbm_group_insert : insertPointCloud V:399-406 across the shards: every shard receives the whole cloud (host buffer, pinned
+ *                       for speed) and casts the rays of its azimuth sector (vdbm_ray_sector_set), foreign update leaves are
+ *                       pushed to their owners over NVLink, every shard runs updateMap on its own leaves. The sector plan
+ *                       (ray sectors of equal raycast cost, ownership sectors of equal owned leaves) is cut from the FIRST scan
+ *                       of an empty map (dry-run raycast on shard 0) unless vdbm_group_plan_set supplied one.
+ *   vdbm_group_shard  : the per-device handle, for everything that is read shard by shard (vdbm_map_export, vdbm_section,
+ *                       vdbm_probe, vdbm_stats ...): the shards hold disjoint leaf sets.
+ * params->stream must be NULL (every shard owns its stream); params->device is ignored. inbox_capacity_records: update
+ * leaves one shard may send to one other shard per scan (0 = 1 << 19). Calls on a group must come from one thread at a time. */
+typedef struct vdbm_group vdbm_group;
+int vdbm_group_create(const vdbm_params* params, int32_t n_devices, const int32_t* devices, uint64_t inbox_capacity_records, vdbm_group** out);
+void vdbm_group_destroy(vdbm_group* group);
+int32_t vdbm_group_size(const vdbm_group* group);
+vdbm_map* vdbm_group_shard(vdbm_group* group, int32_t i);
+int vdbm_group_set_config(vdbm_group* group, double max_range, double prob_hit, double prob_miss, double prob_thres_min, double prob_thres_max);
+int vdbm_group_source_add(vdbm_group* group, const char* source_id, double max_range);
+int vdbm_group_reset(vdbm_group* group);
+int vdbm_group_insert(vdbm_group* group, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3]);
+/* explicit sector plan (diamond angles, see vdbm_shard_plan_set / vdbm_ray_sector_set); only while the map is empty */
+int vdbm_group_plan_set(vdbm_group* group, const int32_t center_leaf_xy[2], const double* ray_bounds, const double* ownership_bounds);
+int vdbm_group_plan_get(vdbm_group* group, int32_t center_leaf_xy[2], double* ray_bounds, double* ownership_bounds);
+/* sum of the shard checksums / leaf counts (mod 2^64) */
+int vdbm_group_checksum(vdbm_group* group, uint64_t out2[2]);
+/* counters summed over the shards (times: max over the shards) */
+int vdbm_group_stats(vdbm_group* group, vdbm_stats_t* out);
+const char* vdbm_group_last_error(vdbm_group* group);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 int vdbm_stats(vdbm_map* map, vdbm_stats_t* out);

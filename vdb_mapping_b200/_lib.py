@@ -92,6 +92,21 @@ def lib() -> C.CDLL:
     sig("vdbm_leafset_free", None, vp)
     sig("vdbm_leaf_owner", i32, i32p, i32)
     sig("vdbm_shard_plan_set", C.c_int, vp, i32, i32, i32p, dblp)
+    sig("vdbm_ray_sector_set", C.c_int, vp, i32, i32, dblp)
+    sig("vdbm_exchange_connect_peers", C.c_int, vp, pvp)
+    sig("vdbm_group_create", C.c_int, C.POINTER(VdbmParams), i32, i32p, u64, pvp)
+    sig("vdbm_group_destroy", None, vp)
+    sig("vdbm_group_size", i32, vp)
+    sig("vdbm_group_shard", vp, vp, i32)
+    sig("vdbm_group_set_config", C.c_int, vp, dbl, dbl, dbl, dbl, dbl)
+    sig("vdbm_group_source_add", C.c_int, vp, cp, dbl)
+    sig("vdbm_group_reset", C.c_int, vp)
+    sig("vdbm_group_insert", C.c_int, vp, cp, vp, u64, u64, dblp)
+    sig("vdbm_group_plan_set", C.c_int, vp, i32p, dblp, dblp)
+    sig("vdbm_group_plan_get", C.c_int, vp, i32p, dblp, dblp)
+    sig("vdbm_group_checksum", C.c_int, vp, u64p)
+    sig("vdbm_group_stats", C.c_int, vp, C.POINTER(VdbmStats))
+    sig("vdbm_group_last_error", cp, vp)
     sig("vdbm_leaf_owner_planned", i32, vp, i32p, i32)
     sig("vdbm_map_checksum", C.c_int, vp, u64p)
     sig("vdbm_update_partition", C.c_int, vp, cp, i32, u64p, pvp)

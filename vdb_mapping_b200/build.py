@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libvdbm_b200.so")
-SOURCES = ["vdbm_kernels.cu", "vdbm_abi.cu"]
+SOURCES = ["vdbm_kernels.cu", "vdbm_abi.cu", "vdbm_group.cu"]
 HEADERS = [os.path.join(CSRC, "vdbm_device.cuh"), os.path.join(ROOT, "include", "vdbm_b200.h")]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",

@@ -99,6 +99,8 @@ struct vdbm_map
   int dda_grid       = 0;
 
   ShardPlan shard{}; // ownership of map leaves across ranks (mode 0 = hash; vdbm_shard_plan_set)
+  int32_t sector_n = 0, sector_rank = 0; // ray split on the device (vdbm_ray_sector_set); sector_n <= 1: off
+  double sector_bounds[kMaxRanks] = {};
 
   // fast_mode / raytrace (V:577-602, V:675-721): node levels above the leaves as coarse key sets, built lazily
   bool fast_mode = false; // Config::fast_mode V:1466
@@ -456,6 +458,12 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
     CU_TRY(m, cudaMalloc(&m->d_sort_tmp, m->sort_tmp_bytes ? m->sort_tmp_bytes : 8));
     m->rays_cap = rc;
     m->seg_cap  = seg_cap;
+  }
+  if (!index_mode && m->sector_n > 1)
+  {
+    a.sector_n    = m->sector_n;
+    a.sector_rank = m->sector_rank;
+    for (int r = 0; r < m->sector_n; ++r) a.sector_bounds[r] = m->sector_bounds[r];
   }
   a.fast_mode = (m->fast_mode && !index_mode) ? 1u : 0u;
   if (a.fast_mode && m->n_leaves != 0)
@@ -951,9 +959,18 @@ int finishPending(vdbm_map* m)
   return VDBM_OK;
 }
 
+// every entry point runs on the handle's device whatever the calling thread's current device is (one process may drive
+// several handles on several GPUs: vdbm_group_*)
+inline void enterDevice(vdbm_map* m)
+{
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != m->device) cudaSetDevice(m->device);
+}
+
 #define VDBM_ENTER(m)                          \
   do                                           \
   {                                            \
+    enterDevice(m);                            \
     if ((m)->pending.active)                   \
     {                                          \
       int rc_enter__ = finishPending(m);       \
@@ -977,7 +994,7 @@ int ensureAsyncStaging(vdbm_map* m, int buf, size_t bytes)
 // unnecessary: one source holding data, no segmentation planned, no artificial areas, staging already large enough.
 bool asyncEligible(vdbm_map* m, Source& s, uint64_t n, const double origin[3])
 {
-  if (n == 0 || n > 0xFFFFFFF0ull || !(s.max_range > 0) || !m->config_set || m->fast_mode) return false;
+  if (n == 0 || n > 0xFFFFFFF0ull || !(s.max_range > 0) || !m->config_set || m->fast_mode || m->sector_n > 1) return false;
   for (int k = 0; k < 3; ++k)
     if (!std::isfinite(origin[k])) return false;
   for (auto& kv : m->sources)
@@ -2065,6 +2082,20 @@ int vdbm_shard_plan_set(vdbm_map* m, int32_t mode, int32_t n_ranks, const int32_
   return VDBM_OK;
 }
 
+int vdbm_ray_sector_set(vdbm_map* m, int32_t n_ranks, int32_t rank, const double* bounds)
+{
+  if (!m || n_ranks < 0 || n_ranks > kMaxRanks || (n_ranks > 1 && (!bounds || rank < 0 || rank >= n_ranks))) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  if (n_ranks > 1)
+    for (int r = 0; r < n_ranks; ++r)
+      if (!(bounds[r] >= 0.0 && bounds[r] < 4.0) || (r && !(bounds[r] > bounds[r - 1])))
+        return fail(m, VDBM_ERR_INVALID_ARG, "sector bounds must be ascending diamond angles in [0, 4)");
+  m->sector_n    = n_ranks > 1 ? n_ranks : 0;
+  m->sector_rank = rank;
+  for (int r = 0; r < m->sector_n; ++r) m->sector_bounds[r] = bounds[r];
+  return VDBM_OK;
+}
+
 int32_t vdbm_leaf_owner_planned(vdbm_map* m, const int32_t origin[3], int32_t n_ranks)
 {
   if (!m || !origin || n_ranks <= 0) return -1;
@@ -2213,6 +2244,37 @@ int vdbm_exchange_connect(vdbm_map* m, const void* all_handles)
     ex.opened.push_back(pc);
     ex.px.inbox[r] = static_cast<uint64_t*>(pi);
     ex.px.ctrl[r]  = static_cast<unsigned long long*>(pc);
+  }
+  ex.connected = true;
+  return VDBM_OK;
+}
+
+int vdbm_exchange_connect_peers(vdbm_map* m, vdbm_map* const* peers)
+{
+  if (!m || !peers) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  auto& ex = m->ex;
+  if (!ex.created) return fail(m, VDBM_ERR_INVALID_ARG, "vdbm_exchange_create first");
+  for (int r = 0; r < ex.px.n_ranks; ++r)
+  {
+    vdbm_map* p = (r == ex.px.rank) ? m : peers[r];
+    if (!p || !p->ex.created || p->ex.px.n_ranks != ex.px.n_ranks || p->ex.px.cap != ex.px.cap || p->ex.px.rank != r)
+      return fail(m, VDBM_ERR_INVALID_ARG, "peer handle missing or its exchange was created with another rank / size / capacity");
+    if (p->device != m->device)
+    {
+      int can = 0;
+      CU_TRY(m, cudaDeviceCanAccessPeer(&can, m->device, p->device));
+      if (!can) return fail(m, VDBM_ERR_CUDA, "no peer access between the devices of this group");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      {
+        m->last_error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+        return VDBM_ERR_CUDA;
+      }
+      cudaGetLastError(); // clear "already enabled"
+    }
+    ex.px.inbox[r] = p->ex.inbox;
+    ex.px.ctrl[r]  = p->ex.ctrl;
   }
   ex.connected = true;
   return VDBM_OK;

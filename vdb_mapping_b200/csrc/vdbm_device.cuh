@@ -241,6 +241,10 @@ struct RaycastArgs
   const uint32_t* sorted_keys; // [n_segs] the keys in that order (descending)
   int4* ends;          // [n] or nullptr: end voxel of every ray + (bit0 valid | bit1 hit), the scan's "reduced" update
   uint32_t index_mode; // 1: `points` holds such int4 end-voxel records (16-byte stride) instead of world points
+  // multi-GPU ray split on the device: only the points whose direction around the scan origin (diamond angle of
+  // (x - origin.x, y - origin.y)) falls into sector `sector_rank` of `sector_bounds` are cast; the others are not this rank's
+  int32_t sector_n, sector_rank; // sector_n <= 1: no filter
+  double sector_bounds[kMaxRanks];
   uint32_t fast_mode;  // 1: castRayIntoGridFast follows (prep_rays only produces the end-voxel records and the ray statistics)
 };
 

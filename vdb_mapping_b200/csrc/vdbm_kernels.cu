@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
     uint32_t sign_bits = 0;
     int4 end_rec = make_int4(0, 0, 0, 0); // end voxel + (bit0 valid, bit1 hit): the "reduced" update of this scan
     double e[3] = {0.0, 0.0, 0.0};
-    bool finite, index_ray = false, max_range_ray = false;
+    bool finite, index_ray = false, max_range_ray = false, mine = true;
     int32_t ei_given[3] = {0, 0, 0};
     if (a.index_mode)
     {
@@ -148,8 +148,20 @@ __global__ void __launch_bounds__(256) prep_rays_kernel(RaycastArgs a, Counters*
       e[0] = double(p[0]); e[1] = double(p[1]); e[2] = double(p[2]); // VDBMapping.hpp:501
       // VDBMapping.hpp:505-510 skips NaN; +-inf is undefined behaviour in the reference and is dropped here too
       finite = isfinite(e[0]) && isfinite(e[1]) && isfinite(e[2]);
+      if (a.sector_n > 1)
+      {
+        // one scan split across the GPUs of a box: every rank sees the whole cloud and keeps the rays of its azimuth sector
+        // (invalid points count as angle 0, so exactly one rank reports them)
+        double ang = finite ? diamondAngle(__dsub_rn(e[0], a.origin[0]), __dsub_rn(e[1], a.origin[1])) : 0.0;
+        if (!(ang >= 0.0 && ang < 4.0)) ang = 0.0;
+        int32_t sector = a.sector_n - 1;
+        for (int32_t r = 0; r < a.sector_n; ++r)
+          if (ang >= a.sector_bounds[r]) sector = r;
+        mine = sector == a.sector_rank;
+      }
     }
-    if (!finite) nan_skipped = index_ray ? 0 : 1;
+    if (!mine) {}
+    else if (!finite) nan_skipped = index_ray ? 0 : 1;
     else
     {
       if (!index_ray && a.range > 0.0)

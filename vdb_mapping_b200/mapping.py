@@ -444,3 +444,110 @@ class OccupancyVDBMapping:
 def leaf_owner(origin, n_ranks: int) -> int:
     o = np.ascontiguousarray(origin, dtype=np.int32)
     return int(L.lib().vdbm_leaf_owner(o.ctypes.data_as(C.POINTER(C.c_int32)), n_ranks))
+
+
+class _ShardView(OccupancyVDBMapping):
+    """A shard of a group seen through the single-map interface (exports, sections, probes, stats). Not owned: the group
+    destroys it."""
+
+    def __init__(self, lib, handle, resolution):  # noqa: D401 - no vdbm_create here
+        self._L = lib
+        self._h = handle
+        self.resolution = resolution
+        self.stream_handle = 0
+
+    def close(self):
+        self._h = None
+
+
+class OccupancyVDBMappingGroup:
+    """One process, several GPUs: vdbm_group_* of include/vdbm_b200.h (a sharded map whose union is the reference's one map).
+    insertPointCloud gives every shard the whole cloud; each casts the rays of its azimuth sector, foreign update leaves go to
+    their owners over NVLink peer memory, every shard integrates its own leaves."""
+
+    def __init__(self, resolution: float, devices, replicate_probe_quirk: bool = True, update_capacity_leaves: int = 0,
+                 map_capacity_leaves: int = 0, inbox_capacity_records: int = 0):
+        self._L = L.lib()
+        self.resolution = float(resolution)
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        p = L.VdbmParams(float(resolution), -1, int(replicate_probe_quirk), int(update_capacity_leaves), int(map_capacity_leaves), None)
+        h = C.c_void_p()
+        rc = self._L.vdbm_group_create(C.byref(p), len(devs), devs.ctypes.data_as(C.POINTER(C.c_int32)), int(inbox_capacity_records), C.byref(h))
+        if rc != L.VDBM_OK:
+            raise VdbmError(rc, "vdbm_group_create failed (needs that many CUDA devices with peer access)")
+        self._h = h
+        self.n = len(devs)
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.vdbm_group_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=()):
+        if rc != L.VDBM_OK and rc not in allow:
+            raise VdbmError(rc, (self._L.vdbm_group_last_error(self._h) or b"").decode())
+        return rc
+
+    def setConfig(self, max_range, prob_hit, prob_miss, prob_thres_min, prob_thres_max) -> int:
+        rc = self._L.vdbm_group_set_config(self._h, max_range, prob_hit, prob_miss, prob_thres_min, prob_thres_max)
+        if rc == L.VDBM_ERR_BAD_CONFIG:
+            return 1 if max_range < 0 else 2
+        self._check(rc)
+        return 0
+
+    def addInputSource(self, source_id: str, max_range: float, max_rate: float = 0.0):
+        self._check(self._L.vdbm_group_source_add(self._h, source_id.encode(), float(max_range)))
+
+    def resetMap(self):
+        self._check(self._L.vdbm_group_reset(self._h))
+
+    def insertPointCloud(self, points, origin, source_id: str) -> bool:
+        p = _pts16(points)
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        rc = self._L.vdbm_group_insert(self._h, source_id.encode(), p.ctypes.data, p.shape[0], 16, _dp(o))
+        self._check(rc, allow=(L.VDBM_ERR_UNKNOWN_SOURCE, L.VDBM_ERR_NOT_CONFIGURED))
+        return True
+
+    def insertRaw(self, ptr: int, n: int, origin, source_id: str, stride: int = 16):
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        self._check(self._L.vdbm_group_insert(self._h, source_id.encode(), C.c_void_p(ptr), n, stride, _dp(o)))
+
+    def setPlan(self, center_leaf_xy, ray_bounds, ownership_bounds):
+        c = np.ascontiguousarray(center_leaf_xy, dtype=np.int32)
+        rb = np.ascontiguousarray(ray_bounds, dtype=np.float64)
+        ob = np.ascontiguousarray(ownership_bounds, dtype=np.float64)
+        self._check(self._L.vdbm_group_plan_set(self._h, c.ctypes.data_as(C.POINTER(C.c_int32)), _dp(rb), _dp(ob)))
+
+    def plan(self):
+        c = np.zeros(2, dtype=np.int32)
+        rb, ob = np.zeros(self.n), np.zeros(self.n)
+        self._check(self._L.vdbm_group_plan_get(self._h, c.ctypes.data_as(C.POINTER(C.c_int32)), _dp(rb), _dp(ob)))
+        return c, rb, ob
+
+    def shard(self, i: int) -> OccupancyVDBMapping:
+        return _ShardView(self._L, C.c_void_p(self._L.vdbm_group_shard(self._h, i)), self.resolution)
+
+    def checksum(self):
+        out = np.zeros(2, dtype=np.uint64)
+        self._check(self._L.vdbm_group_checksum(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return int(out[0]), int(out[1])
+
+    def stats(self) -> dict:
+        s = L.VdbmStats()
+        self._check(self._L.vdbm_group_stats(self._h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in L.VdbmStats._fields_ if n != "reserved"}
+
+    def exportMap(self) -> LeafSet:
+        """Union of the shards' (disjoint) leaf sets, sorted by origin like every export."""
+        parts = [self.shard(i).exportMap() for i in range(self.n)]
+        origins = np.concatenate([p.origins for p in parts])
+        active = np.concatenate([p.active for p in parts])
+        values = np.concatenate([p.values for p in parts])
+        order = np.lexsort((origins[:, 2], origins[:, 1], origins[:, 0]))
+        return LeafSet(origins[order], active[order], None, values[order])
