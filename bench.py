@@ -588,6 +588,18 @@ def run_ours(args, rank, world, local_rank):
                    "visits": st1["visits"] - st0["visits"], "launches": st1["gpu_launches"] - launches0,
                    "acc_ms": acc_ms, "prep_ms": prep_ms, "int_ms": int_ms, "leaves": leaves, "map_leaves": st1["map_leaves"],
                    "sent": sent, "recv": recv, "d2h_extra": d2h_extra, "upd_leaves": upd_leaves}
+            if pipelined and not e2e:
+                # Per-kernel times for the roofline, OUTSIDE the timed region: in the pipeline the raycast of scan k+1 runs next
+                # to updateMap of scan k, so CUDA events around one kernel also see the other. A few more scans through the
+                # synchronous calls (same kernels, nothing overlapped) give clean launch durations.
+                acc_ms, prep_ms, int_ms, leaves = [], [], [], []
+                for k in range(max(args.warmup, n_steps - 8), n_steps):
+                    eng.accumulate_raw(resident[k].data_ptr(), n_pts_k[k], clouds[k][1], on_device=True)
+                    s = m.stats()
+                    acc_ms.append(s["last_accumulate_ms"]); prep_ms.append(s["last_prep_ms"]); leaves.append(s["last_touched_leaves"])
+                    eng.integrate()
+                    int_ms.append(m.stats()["last_integrate_ms"])
+                out.update({"acc_ms": acc_ms, "prep_ms": prep_ms, "int_ms": int_ms, "leaves": leaves, "kernel_probe": len(acc_ms)})
             if world > 1 and not mixed and not e2e:
                 out["checksum"] = m.mapChecksum()  # parity witness of the sharded map, compared below (outside the timed region)
             if mixed:
@@ -673,6 +685,10 @@ def run_ours(args, rank, world, local_rank):
         "frac": b_alg / (t_kernels * 1e-3) / 1e9 / peak, "traffic": traffic,
         "traffic_source": (f"profiles/{tr_src}: dram bytes of raycast_dda_kernel + apply_update_kernel per scan (ncu --set full, cfg2)" if traffic else None),
         "algorithmic_bytes_per_step": b_alg, "touched_leaves_per_step": L, "kernel_ms_per_step": t_kernels,
+        "frac_of_step_time": b_alg / (ms_v / K * 1e-3) / 1e9 / peak,
+        "kernel_times_from": ("%d extra scans through the synchronous calls after the timed region (the pipeline overlaps the raycast of "
+                              "scan k+1 with updateMap of scan k, so events inside it would see both kernels)" % res_v["kernel_probe"]) if res_v.get("kernel_probe")
+                             else "CUDA events of the timed steps",
         "by_kernel": {
             "prep_rays_kernel": {"ms": t_prep, "alg_bytes": 64 * n_pts, "achieved_gbs": 64 * n_pts / (t_prep * 1e-3) / 1e9 if t_prep else None},
             "raycast_dda_kernel": {"ms": t_dda, "alg_bytes": 48 * n_pts + 128 * L,

@@ -42,6 +42,10 @@ struct Source
   uint64_t prev_updates    = 0;   // distinct voxels of the previous scan: visits / updates = how heavily its rays overlap
   uint32_t n_bricks  = 0;         // host copies, valid after every synchronising call
   uint32_t n_entries = 0;         // touched leaves (compact list is always rebuilt after a grid write)
+  // second update grid of the scan pipeline (vdbm_insert_async with overlap): the raycast of scan k+1 marks into one grid
+  // while updateMap of scan k consumes the other; swapped with (g, cap, n_bricks, n_entries) by swapParity(). Lazy.
+  UpdateGrid g_alt{};
+  uint32_t cap_alt = 0, n_bricks_alt = 0, n_entries_alt = 0;
   LeafRecord* d_change = nullptr; // change records of the last update (device)
   uint32_t change_cap  = 0;
   uint32_t n_change    = 0;
@@ -137,6 +141,19 @@ struct vdbm_map
   } pending;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr, ev_done = nullptr, ev3 = nullptr;
+  // overlap of scan k+1's raycast with scan k's updateMap: a second counter block, a second set of
+  // timing events and a second stream for the update half of a queued scan. (d_ctr, h_ctr, ev0..ev3) always name the
+  // CURRENT set; swapParity() exchanges them with the *_alt set together with the source's two update grids.
+  Counters* d_ctr_alt = nullptr;
+  Counters* h_ctr_alt = nullptr; // pinned
+  cudaEvent_t ev_alt[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t update_stream = nullptr;
+  cudaEvent_t ev_ray = nullptr; // raycast half of the queued scan finished (and everything queued on `stream` before its update half)
+  bool overlap = true;          // VDBM_OVERLAP=0 switches it off (experiments)
+  bool ends_clobbered = false;
+  bool ray_in_flight = false;   // the next scan's raycast half is already queued while finishPending() works on the previous scan
+  int dda_grid_overlap = 0;     // DDA CTAs when the raycast half runs next to an update (fewer per SM: leaves room for the update CTAs)
+  uint64_t async_overlapped = 0;
   uint8_t* d_points_async[2] = {nullptr, nullptr};
   size_t points_async_cap[2] = {0, 0};
   int async_buf              = 0;
@@ -303,22 +320,30 @@ int ensureMapCapacity(vdbm_map* m, uint64_t extra)
 }
 
 // D2H of the counter block + map counters, synchronising the stream
+// cumulative statistics = counters at the last reset + BOTH device counter blocks (host copies; the block that is not
+// current only changes through queued scans, whose finishing call refreshes its host copy)
+void publishCumulative(vdbm_map* m)
+{
+  const Counters& c = *m->h_ctr;
+  const Counters& o = *m->h_ctr_alt;
+  m->stats.nan_skipped   = m->base.nan_skipped + c.nan_skipped + o.nan_skipped;
+  m->stats.clipped       = m->base.clipped + c.clipped + o.clipped;
+  m->stats.visits        = m->base.visits + c.visits + o.visits;
+  m->stats.voxel_updates = m->base.voxel_updates + c.voxel_updates + o.voxel_updates;
+  m->stats.state_changes = m->base.state_changes + c.state_changes + o.state_changes;
+  m->stats.new_leaves    = m->base.new_leaves + c.new_leaves + o.new_leaves;
+  m->stats.map_leaves    = m->n_leaves;
+  m->stats.map_capacity  = m->mt.pool_cap;
+  m->stats.gpu_launches  = launchCount();
+}
+
 int syncCounters(vdbm_map* m)
 {
   CU_TRY(m, cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaMemcpyAsync(m->h_small, m->d_map_counters, 4, cudaMemcpyDeviceToHost, m->stream));
   CU_TRY(m, cudaStreamSynchronize(m->stream));
   m->n_leaves = m->h_small[0];
-  const Counters& c      = *m->h_ctr;
-  m->stats.nan_skipped   = m->base.nan_skipped + c.nan_skipped;
-  m->stats.clipped       = m->base.clipped + c.clipped;
-  m->stats.visits        = m->base.visits + c.visits;
-  m->stats.voxel_updates = m->base.voxel_updates + c.voxel_updates;
-  m->stats.state_changes = m->base.state_changes + c.state_changes;
-  m->stats.new_leaves    = m->base.new_leaves + c.new_leaves;
-  m->stats.map_leaves    = m->n_leaves;
-  m->stats.map_capacity  = m->mt.pool_cap;
-  m->stats.gpu_launches  = launchCount();
+  publishCumulative(m);
   return VDBM_OK;
 }
 
@@ -924,6 +949,7 @@ int finishPending(vdbm_map* m)
     s.n_bricks  = m->h_small[8];
     s.n_entries = m->h_small[9];
     int rc = raycastDevice(m, s, pd.d_pts, pd.n, pd.stride, pd.origin, s.max_range);
+    if (m->ray_in_flight) { m->ends_clobbered = true; m->ends_src = nullptr; } // the staging buffers held the NEXT scan's rays
     if (rc != VDBM_OK && rc != VDBM_ERR_COORD_RANGE) return rc;
     int rc2 = vdbm_integrate(m, 0);
     m->async_expect = uint32_t(m->stats.last_touched_leaves);
@@ -932,15 +958,7 @@ int finishPending(vdbm_map* m)
   ++m->async_fast;
   // the queued path ran to completion: publish what accumulate + integrate would have published
   const uint64_t upd_before = m->stats.voxel_updates;
-  m->stats.nan_skipped   = m->base.nan_skipped + c.nan_skipped;
-  m->stats.clipped       = m->base.clipped + c.clipped;
-  m->stats.visits        = m->base.visits + c.visits;
-  m->stats.voxel_updates = m->base.voxel_updates + c.voxel_updates;
-  m->stats.state_changes = m->base.state_changes + c.state_changes;
-  m->stats.new_leaves    = m->base.new_leaves + c.new_leaves;
-  m->stats.map_leaves    = m->n_leaves;
-  m->stats.map_capacity  = m->mt.pool_cap;
-  m->stats.gpu_launches  = launchCount();
+  publishCumulative(m);
   m->stats.last_visits         = c.visits - pd.before.visits;
   m->stats.last_touched_leaves = c.deferred_entries;
   m->stats.last_voxel_updates  = m->stats.voxel_updates - upd_before;
@@ -954,8 +972,15 @@ int finishPending(vdbm_map* m)
   s.n_bricks = s.n_entries = 0;
   s.n_change        = 0;
   m->async_expect   = c.deferred_entries;
-  m->ends_src = &s; m->ends_n = pd.n;
-  for (int k = 0; k < 3; ++k) m->ends_origin[k] = pd.origin[k];
+  // the end-voxel records of this scan (its reduced update) are still in the staging buffer unless the NEXT scan's raycast
+  // half has already been queued behind it, or a redo re-used the buffer in between
+  if (m->ray_in_flight || m->ends_clobbered) m->ends_src = nullptr;
+  else
+  {
+    m->ends_src = &s; m->ends_n = pd.n;
+    for (int k = 0; k < 3; ++k) m->ends_origin[k] = pd.origin[k];
+  }
+  m->ends_clobbered = false;
   return VDBM_OK;
 }
 
@@ -1065,6 +1090,20 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
   CU_TRY(mm, cudaMemsetAsync(m->d_ctr, 0, sizeof(Counters), m->stream));
   CU_TRY(mm, cudaHostAlloc(&m->h_ctr, sizeof(Counters), cudaHostAllocDefault));
   CU_TRY(mm, cudaHostAlloc(&m->h_small, 64 * sizeof(uint32_t), cudaHostAllocDefault));
+  CU_TRY(mm, cudaMalloc(&m->d_ctr_alt, sizeof(Counters)));
+  CU_TRY(mm, cudaMemsetAsync(m->d_ctr_alt, 0, sizeof(Counters), m->stream));
+  CU_TRY(mm, cudaHostAlloc(&m->h_ctr_alt, sizeof(Counters), cudaHostAllocDefault));
+  std::memset(m->h_ctr_alt, 0, sizeof(Counters));
+  for (auto& e : m->ev_alt) CU_TRY(mm, cudaEventCreate(&e));
+  CU_TRY(mm, cudaEventCreateWithFlags(&m->ev_ray, cudaEventDisableTiming));
+  {
+    int lo = 0, hi = 0; // the update half of a queued scan fills the SM resources the persistent DDA CTAs leave free
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    int prio = hi;
+    if (const char* e = getenv("VDBM_UPDATE_PRIORITY")) prio = atoi(e) ? hi : lo; // experiments
+    CU_TRY(mm, cudaStreamCreateWithPriority(&m->update_stream, cudaStreamNonBlocking, prio));
+  }
+  if (const char* e = getenv("VDBM_OVERLAP")) m->overlap = atoi(e) != 0;
   // pinned memory is recycled, not zeroed: a stale counter block of an earlier handle would become the "before" state a
   // replayed first scan restores
   std::memset(m->h_ctr, 0, sizeof(Counters));
@@ -1081,6 +1120,13 @@ int vdbm_create(const vdbm_params* params, vdbm_map** out)
   CU_TRY(mm, cudaMemsetAsync(m->d_near, 0, nearCopiesBytes(), m->stream));
   m->lo.replicate_quirk = params->replicate_probe_quirk ? 1u : 0u;
   m->dda_grid           = raycastDDAGrid(m->device);
+  m->dda_grid_overlap   = m->dda_grid;
+  if (const char* e = getenv("VDBM_OVERLAP_DDA_CTAS_PER_SM"))
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    m->dda_grid_overlap = std::min(m->dda_grid, std::max(1, atoi(e)) * sms);
+  }
   CU_TRY(mm, cudaStreamSynchronize(m->stream));
   *out = m.release();
   return VDBM_OK;
@@ -1092,6 +1138,11 @@ void vdbm_destroy(vdbm_map* m)
   if (m->pending.active) finishPending(m);
   cudaStreamSynchronize(m->stream);
   cudaStreamSynchronize(m->copy_stream);
+  if (m->update_stream) { cudaStreamSynchronize(m->update_stream); cudaStreamDestroy(m->update_stream); }
+  cudaFree(m->d_ctr_alt);
+  cudaFreeHost(m->h_ctr_alt);
+  for (cudaEvent_t e : m->ev_alt) if (e) cudaEventDestroy(e);
+  if (m->ev_ray) cudaEventDestroy(m->ev_ray);
   cudaFree(m->d_points_async[0]); cudaFree(m->d_points_async[1]);
   for (cudaEvent_t e : {m->ev3, m->ev_copy, m->ev_done})
     if (e) cudaEventDestroy(e);
@@ -1099,6 +1150,7 @@ void vdbm_destroy(vdbm_map* m)
   for (auto& kv : m->sources)
   {
     freeUpdateGrid(kv.second->g);
+    freeUpdateGrid(kv.second->g_alt);
     cudaFree(kv.second->d_change);
   }
   for (Source* aux : {m->scratch.get(), m->artificial.get()})
@@ -1331,75 +1383,19 @@ int vdbm_flush(vdbm_map* m)
   return finishPending(m);
 }
 
-int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3],
-                      int points_on_device)
+// (d_ctr, h_ctr, ev0..ev3) of the handle and (g, cap, n_bricks, n_entries) of the source <-> their alternates
+static void swapParity(vdbm_map* m, Source& s)
 {
-  if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
-  Source* sp = findSource(m, source_id);
-  m->prefetch.valid = false;
-  // 1. start the upload of THIS cloud while the previous scan may still be computing (its buffer is the other one)
-  const int buf      = m->async_buf ^ 1;
-  const size_t bytes = size_t(n) * stride_bytes;
-  const uint8_t* d_pts = static_cast<const uint8_t*>(points);
-  bool uploaded = false;
-  if (sp && !points_on_device && bytes && bytes <= m->points_async_cap[buf])
-  {
-    CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
-    CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
-    uploaded = true;
-  }
-  // 2. finish the previous scan (the one synchronisation per scan)
-  int rc = finishPending(m);
-  // out-of-range points of the PREVIOUS scan are a warning, not a reason to drop this one: remember it, carry on, and
-  // return it at the end unless this scan has something of its own to report
-  int rc_prev = VDBM_OK;
-  if (rc == VDBM_ERR_COORD_RANGE) { rc_prev = rc; rc = VDBM_OK; }
-  if (rc) return rc;
-  if (!sp)
-  {
-    // like vdbm_insert: accumulateUpdate complains and returns (V:320-326), integrateUpdate still runs (V:404)
-    rc = vdbm_integrate(m, 0);
-    if (rc) return rc;
-    return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
-  }
-  Source& s = *sp;
-  if (!points_on_device)
-  {
-    if (!uploaded && bytes)
-    {
-      rc = ensureAsyncStaging(m, buf, bytes);
-      if (rc) return rc;
-      CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
-      CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
-    }
-    d_pts = m->d_points_async[buf];
-    // the caller's buffer is free again when this call returns; by now the copy has normally long finished (it ran
-    // while finishPending waited for the previous scan)
-    if (bytes) CU_TRY(m, cudaEventSynchronize(m->ev_copy));
-    m->async_buf = buf;
-  }
-  // 3. not eligible for the queued path: the ordinary synchronous insert on the uploaded cloud
-  if (!asyncEligible(m, s, n, origin))
-  {
-    ++m->async_sync;
-    if (!(s.max_range > 0)) return vdbm_integrate(m, 0); // V:331 then integrateUpdate
-    if (!m->config_set)
-    {
-      vdbm_integrate(m, 0);
-      return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
-    }
-    int rc_acc = raycastDevice(m, s, d_pts, n, stride_bytes, origin, s.max_range);
-    if (rc_acc != VDBM_OK && rc_acc != VDBM_ERR_COORD_RANGE) return rc_acc;
-    int rc_int = vdbm_integrate(m, 0);
-    m->async_expect = uint32_t(std::max<uint64_t>(1, m->stats.last_touched_leaves));
-    return rc_int ? rc_int : (rc_acc ? rc_acc : rc_prev);
-  }
-  // 4. queue the whole scan
-  const uint32_t expect = m->async_expect + m->async_expect / 2 + 65536; // leaves the update is sized for (guard checks the truth)
-  rc = ensureMapCapacity(m, expect);
-  if (rc) return rc;
-  rc = ensureResolved(m, expect);
-  if (rc) return rc;
+  std::swap(m->d_ctr, m->d_ctr_alt);
+  std::swap(m->h_ctr, m->h_ctr_alt);
+  std::swap(m->ev0, m->ev_alt[0]); std::swap(m->ev1, m->ev_alt[1]); std::swap(m->ev2, m->ev_alt[2]); std::swap(m->ev3, m->ev_alt[3]);
+  std::swap(s.g, s.g_alt);
+  std::swap(s.cap, s.cap_alt); std::swap(s.n_bricks, s.n_bricks_alt); std::swap(s.n_entries, s.n_entries_alt);
+}
+
+// Raycast half of a queued scan on m->stream, into the CURRENT set: prep -> sort -> DDA -> merge -> compaction (+ cook)
+static int queueRaycastHalf(vdbm_map* m, Source& s, const uint8_t* d_pts, uint64_t n, uint64_t stride_bytes, const double origin[3], int dda_grid)
+{
   RaycastArgs a{};
   a.points = d_pts;
   a.n      = n;
@@ -1423,10 +1419,6 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
   a.sorted_keys = m->d_sort + m->seg_cap;
   a.seg_len    = 0;
   a.n_segs     = uint32_t(n);
-  m->pending.before      = *m->h_ctr;
-  m->pending.rays_before = m->stats.rays;
-  m->stats.rays += n;
-  m->ends_src = nullptr;
   CU_TRY(m, cudaMemsetAsync(&m->d_ctr->ray_cursor, 0, sizeof(unsigned), m->stream));
   CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
   CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_extra, 0, 3 * sizeof(unsigned), m->stream));
@@ -1435,15 +1427,167 @@ int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, ui
   sortRaysByLength(m->d_sort_tmp, m->sort_tmp_bytes, a.sort_keys, m->d_sort + m->seg_cap, a.sort_idx, m->d_sort + 3 * m->seg_cap, a.n_segs,
                    m->stream);
   CU_TRY(m, cudaEventRecord(m->ev2, m->stream));
-  launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, m->dda_grid, m->stream, testBeforeSet(s));
+  launchRaycastDDA(a, s.g, m->d_near, m->d_ctr, dda_grid, m->stream, testBeforeSet(s));
   launchCompactLeaves(s.g, m->stream, /*cook=*/true); // the grid was empty (asyncEligible): nothing to uncook before
   CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
-  launchApplyUpdateDeferred(s.g, m->mt, m->lo, m->d_resolved, uint32_t(std::min<size_t>(m->resolved_cap, 0xFFFFFFFFu)), m->d_ctr, expect, m->stream);
-  CU_TRY(m, cudaEventRecord(m->ev3, m->stream));
   CU_TRY(m, cudaGetLastError());
-  CU_TRY(m, cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
-  CU_TRY(m, cudaMemcpyAsync(m->h_small, m->d_map_counters, 4, cudaMemcpyDeviceToHost, m->stream));
-  CU_TRY(m, cudaEventRecord(m->ev_done, m->stream));
+  return VDBM_OK;
+}
+
+// A raycast half was queued into the current set but its scan cannot be completed (an error in between): wait for it,
+// forget what it marked and what it counted.
+static int abandonQueuedRaycast(vdbm_map* m, Source& s, const Counters& before)
+{
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  int rc = readGridCounters(m, s);
+  if (rc) return rc;
+  rc = clearUpdateGrid(m, s);
+  if (rc) return rc;
+  Counters restored   = before;
+  restored.flags      = 0;
+  restored.ray_cursor = 0;
+  CU_TRY(m, cudaMemcpyAsync(m->d_ctr, &restored, sizeof(Counters), cudaMemcpyHostToDevice, m->stream));
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  *m->h_ctr = restored;
+  return VDBM_OK;
+}
+
+int vdbm_insert_async(vdbm_map* m, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3],
+                      int points_on_device)
+{
+  if (!m || (!points && n) || !origin || stride_bytes < 12) return VDBM_ERR_INVALID_ARG;
+  enterDevice(m);
+  Source* sp = findSource(m, source_id);
+  m->prefetch.valid = false;
+  // 1. start the upload of THIS cloud while the previous scan may still be computing (its buffer is the other one)
+  const int buf      = m->async_buf ^ 1;
+  const size_t bytes = size_t(n) * stride_bytes;
+  const uint8_t* d_pts = static_cast<const uint8_t*>(points);
+  bool uploaded = false;
+  if (sp && !points_on_device && bytes && bytes <= m->points_async_cap[buf])
+  {
+    CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+    CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
+    uploaded = true;
+  }
+  // 2a. OVERLAP: the raycast half of this scan does not read the map, so it is queued - into the source's OTHER update grid,
+  // counting into the other counter block - BEFORE the previous scan is waited for: its DDA (instruction-bound) then runs
+  // next to the previous scan's updateMap (HBM-bound), which sits on the update stream.
+  bool ray_queued = false;
+  Counters before{};
+  uint64_t rays_before = 0;
+  cudaStream_t upd_stream = m->overlap ? m->update_stream : m->stream;
+  if (m->overlap && m->pending.active && sp && m->pending.src == sp && (points_on_device || uploaded) && asyncEligible(m, *sp, n, origin))
+  {
+    Source& s = *sp;
+    if (!s.g_alt.bkeys)
+    {
+      s.cap_alt = s.cap;
+      int rca   = allocUpdateGrid(m, s.g_alt, s.cap_alt);
+      if (rca) return rca;
+    }
+    swapParity(m, s);
+    before      = *m->h_ctr;
+    rays_before = m->stats.rays;
+    if (!points_on_device)
+    {
+      d_pts = m->d_points_async[buf];
+      CU_TRY(m, cudaStreamWaitEvent(m->stream, m->ev_copy, 0));
+    }
+    const int rcq = queueRaycastHalf(m, s, d_pts, n, stride_bytes, origin, m->dda_grid_overlap);
+    swapParity(m, s); // the previous scan's set is the current one again: finishPending() works on it
+    if (rcq) return rcq; // (only the origin check can fail, before anything is queued)
+    ray_queued          = true;
+    m->ray_in_flight    = true;
+  }
+  // 2b. finish the previous scan (the one synchronisation per scan)
+  int rc = finishPending(m);
+  m->ray_in_flight = false;
+  // out-of-range points of the PREVIOUS scan are a warning, not a reason to drop this one: remember it, carry on, and
+  // return it at the end unless this scan has something of its own to report
+  int rc_prev = VDBM_OK;
+  if (rc == VDBM_ERR_COORD_RANGE) { rc_prev = rc; rc = VDBM_OK; }
+  if (rc)
+  {
+    if (ray_queued) { swapParity(m, *sp); abandonQueuedRaycast(m, *sp, before); swapParity(m, *sp); }
+    return rc;
+  }
+  if (!sp)
+  {
+    // like vdbm_insert: accumulateUpdate complains and returns (V:320-326), integrateUpdate still runs (V:404)
+    rc = vdbm_integrate(m, 0);
+    if (rc) return rc;
+    return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  }
+  Source& s = *sp;
+  if (!points_on_device)
+  {
+    if (!uploaded && bytes)
+    {
+      rc = ensureAsyncStaging(m, buf, bytes);
+      if (rc) return rc;
+      CU_TRY(m, cudaMemcpyAsync(m->d_points_async[buf], points, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+      CU_TRY(m, cudaEventRecord(m->ev_copy, m->copy_stream));
+    }
+    d_pts = m->d_points_async[buf];
+    // the caller's buffer is free again when this call returns; by now the copy has normally long finished (it ran
+    // while finishPending waited for the previous scan)
+    if (bytes) CU_TRY(m, cudaEventSynchronize(m->ev_copy));
+    m->async_buf = buf;
+  }
+  if (ray_queued)
+  {
+    swapParity(m, s); // this scan's set (grid + counter block + events) becomes the current one
+    ++m->async_overlapped;
+  }
+  else
+  {
+    // 3. not eligible for the queued path: the ordinary synchronous insert on the uploaded cloud
+    if (!asyncEligible(m, s, n, origin))
+    {
+      ++m->async_sync;
+      if (!(s.max_range > 0)) return vdbm_integrate(m, 0); // V:331 then integrateUpdate
+      if (!m->config_set)
+      {
+        vdbm_integrate(m, 0);
+        return fail(m, VDBM_ERR_NOT_CONFIGURED, "Map not properly configured. Did you call setConfig method?");
+      }
+      int rc_acc = raycastDevice(m, s, d_pts, n, stride_bytes, origin, s.max_range);
+      if (rc_acc != VDBM_OK && rc_acc != VDBM_ERR_COORD_RANGE) return rc_acc;
+      int rc_int = vdbm_integrate(m, 0);
+      m->async_expect = uint32_t(std::max<uint64_t>(1, m->stats.last_touched_leaves));
+      return rc_int ? rc_int : (rc_acc ? rc_acc : rc_prev);
+    }
+    before      = *m->h_ctr;
+    rays_before = m->stats.rays;
+  }
+  // 4. queue the scan (its raycast half may already be running)
+  const uint32_t expect = m->async_expect + m->async_expect / 2 + 65536; // leaves the update is sized for (guard checks the truth)
+  rc = ensureMapCapacity(m, expect);
+  if (!rc) rc = ensureResolved(m, expect);
+  if (!rc && !ray_queued) rc = queueRaycastHalf(m, s, d_pts, n, stride_bytes, origin, m->dda_grid);
+  if (rc)
+  {
+    if (ray_queued) abandonQueuedRaycast(m, s, before);
+    return rc;
+  }
+  m->pending.before      = before;
+  m->pending.rays_before = rays_before;
+  m->stats.rays += n;
+  m->ends_src = nullptr;
+  // update half: guard -> resolve -> apply -> reset, behind everything queued on the main stream so far (the raycast half and,
+  // possibly, a reallocation of the map tables)
+  if (upd_stream != m->stream)
+  {
+    CU_TRY(m, cudaEventRecord(m->ev_ray, m->stream));
+    CU_TRY(m, cudaStreamWaitEvent(upd_stream, m->ev_ray, 0));
+  }
+  launchApplyUpdateDeferred(s.g, m->mt, m->lo, m->d_resolved, uint32_t(std::min<size_t>(m->resolved_cap, 0xFFFFFFFFu)), m->d_ctr, expect, upd_stream);
+  CU_TRY(m, cudaEventRecord(m->ev3, upd_stream));
+  CU_TRY(m, cudaGetLastError());
+  CU_TRY(m, cudaMemcpyAsync(m->h_ctr, m->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, upd_stream));
+  CU_TRY(m, cudaMemcpyAsync(m->h_small, m->d_map_counters, 4, cudaMemcpyDeviceToHost, upd_stream));
+  CU_TRY(m, cudaEventRecord(m->ev_done, upd_stream));
   m->pending.active = true;
   m->pending.src    = &s;
   m->pending.n      = n;

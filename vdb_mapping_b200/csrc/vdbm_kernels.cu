@@ -337,6 +337,9 @@ __global__ void __launch_bounds__(128) long_ray_segments_kernel(RaycastArgs a, u
 // hash is consulted only when a ray enters a new brick, and those lookups (like the ray refills) are batched at
 // warp-uniform points every kBatch steps so that their L2 round trip is paid once per batch and not once per lane event.
 // ====================================================================================================
+#ifndef VDBM_DDA_CTAS
+#define VDBM_DDA_CTAS 4 // resident CTAs per SM the DDA kernel is compiled for: 52 registers at 4 (measured on B200: 0.42 ms per cfg2 scan; 5 CTAs x 48 registers 0.47 ms, 6 x 40 with spills 0.52 ms)
+#endif
 #ifndef VDBM_KBATCH
 #define VDBM_KBATCH 8
 #endif
@@ -428,7 +431,7 @@ __device__ __forceinline__ double addSel(double n, double d, bool p)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 5) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, uint64_t* near_act, Counters* ctr)
+__global__ void __launch_bounds__(256, VDBM_DDA_CTAS) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, uint64_t* near_act, Counters* ctr)
 {
   __shared__ uint32_t s_near_slot[kNearBricks];
   __shared__ uint64_t s_bit[kBitTableSize];
@@ -2411,6 +2414,7 @@ int raycastDDAGrid(int device)
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_dda_kernel<0>, 256, 0);
   if (per_sm < 1) per_sm = 1;
+  if (const char* e = getenv("VDBM_DDA_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e))); // experiments
   return sms * per_sm; // persistent: exactly one resident wave
 }
 
