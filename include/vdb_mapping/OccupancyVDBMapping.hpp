@@ -34,6 +34,15 @@ public:
   inline void setConfig(const Config& config) override
   {
     VDBMapping::setConfig(config);
+    // The device takes the same decisions in the same order (vdbm_set_config: a negative range changes nothing; otherwise
+    // range and the "configured" flag are accepted BEFORE the probability checks, O:61 then O:65-76), so host and device
+    // never disagree on whether the map is configured.
+    int device_rc = VDBM_OK;
+    if (m_device_map)
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex);
+      device_rc = vdbm_set_config(m_device_map, config.max_range, config.prob_hit, config.prob_miss, config.prob_thres_min, config.prob_thres_max);
+    }
     if (config.prob_miss > 0.5)
     {
       std::cerr << "Probability for a miss should be below 0.5 but is " << config.prob_miss << std::endl;
@@ -44,9 +53,8 @@ public:
       std::cerr << "Probability for a hit should be above 0.5 but is " << config.prob_hit << std::endl;
       return;
     }
-    if (config.max_range < 0.0 || !m_device_map) return; // base already complained / no device
+    if (config.max_range < 0.0 || !m_device_map || device_rc != VDBM_OK) return; // base already complained / no device
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
-    vdbm_set_config(m_device_map, config.max_range, config.prob_hit, config.prob_miss, config.prob_thres_min, config.prob_thres_max);
     float lo[6];
     vdbm_get_logodds(m_device_map, lo);
     m_logodds_hit = lo[0]; m_logodds_miss = lo[1]; m_logodds_thres_min = lo[2]; m_logodds_thres_max = lo[3];

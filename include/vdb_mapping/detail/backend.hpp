@@ -39,10 +39,17 @@ inline void parallelFor(std::uint64_t n, F&& f)
 } // namespace detail
 } // namespace vdb_mapping
 
-#if !defined(VDBM_FORCE_COMPAT) && defined(__has_include)
+// Which types the shim hands out. The CMake package decides and exports the decision on the vdb_mapping::vdb_mapping
+// target: VDBM_HAVE_OPENVDB=1 when OpenVDB, PCL and Eigen were all FOUND AND LINKED, VDBM_FORCE_COMPAT=1 otherwise - so a
+// box that has the headers but no linkable package never compiles against OpenVDB and then fails to link. Only a consumer
+// that uses the headers without the package (plain -I) falls back to header detection.
+#if !defined(VDBM_HAVE_OPENVDB) && !defined(VDBM_FORCE_COMPAT) && defined(__has_include)
 #if __has_include(<openvdb/openvdb.h>) && __has_include(<pcl/point_types.h>) && __has_include(<Eigen/Core>)
 #define VDBM_HAVE_OPENVDB 1
 #endif
+#endif
+#if defined(VDBM_FORCE_COMPAT)
+#undef VDBM_HAVE_OPENVDB
 #endif
 
 #ifdef VDBM_HAVE_OPENVDB

@@ -1997,14 +1997,18 @@ int vdbm_section_apply_update(vdbm_map* m, const int32_t bbmin[3], const int32_t
   VDBM_ENTER(m);
   int rc = syncCounters(m);
   if (rc) return rc;
-  launchSectionDeactivate(m->mt, m->n_leaves, bbmin, bbmax, m->stream);
+  // validate the section and make room BEFORE the box is deactivated: a rejected call must leave the map untouched
+  std::vector<uint64_t> keys;
   if (n)
   {
-    std::vector<uint64_t> keys;
     rc = originsToKeys(m, n, origins, keys);
     if (rc) return rc;
     rc = ensureMapCapacity(m, n);
     if (rc) return rc;
+  }
+  launchSectionDeactivate(m->mt, m->n_leaves, bbmin, bbmax, m->stream);
+  if (n)
+  {
     TempBuf dk(m->stream), da(m->stream);
     CU_TRY(m, dk.alloc(n * 8));
     CU_TRY(m, da.alloc(n * 64));
