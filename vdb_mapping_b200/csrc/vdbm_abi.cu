@@ -2108,6 +2108,8 @@ int vdbm_set_fast_mode(vdbm_map* m, int on)
 {
   if (!m) return VDBM_ERR_INVALID_ARG;
   VDBM_ENTER(m);
+  if (on && (m->ex.connected || m->sector_n > 1))
+    return fail(m, VDBM_ERR_INVALID_ARG, "fast_mode probes the map along every ray: it needs the whole map on one device (this handle is a shard)");
   m->fast_mode = on != 0;
   return VDBM_OK;
 }
@@ -2234,6 +2236,7 @@ int vdbm_ray_sector_set(vdbm_map* m, int32_t n_ranks, int32_t rank, const double
 {
   if (!m || n_ranks < 0 || n_ranks > kMaxRanks || (n_ranks > 1 && (!bounds || rank < 0 || rank >= n_ranks))) return VDBM_ERR_INVALID_ARG;
   VDBM_ENTER(m);
+  if (n_ranks > 1 && m->fast_mode) return fail(m, VDBM_ERR_INVALID_ARG, "fast_mode needs the whole map on one device: switch it off before sharding");
   if (n_ranks > 1)
     for (int r = 0; r < n_ranks; ++r)
       if (!(bounds[r] >= 0.0 && bounds[r] < 4.0) || (r && !(bounds[r] > bounds[r - 1])))
