@@ -340,6 +340,10 @@ const char* vdbm_group_last_error(vdbm_group* group);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 int vdbm_stats(vdbm_map* map, vdbm_stats_t* out);
+/* How the scans given to vdbm_insert_async travelled so far: out4 = { finished on the queued path, redone synchronously after
+ * the device-side guard refused, run synchronously because they were not eligible, queued with their raycast half
+ * overlapping the previous scan's updateMap }. Like vdbm_stats it does not finish a queued scan. */
+int vdbm_pipeline_counts(vdbm_map* map, uint64_t out4[4]);
 const char* vdbm_last_error(vdbm_map* map);
 int vdbm_abi_version(void);
 /* wait for all work queued on the handle's stream */

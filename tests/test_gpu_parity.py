@@ -493,13 +493,29 @@ def test_async_pipeline_matches_the_oracle(small_tables):
     redos - the map must equal the oracle's after every flush, and the counters must agree."""
     from vdb_mapping_b200 import scans
     kw = dict(update_capacity_leaves=1024, map_capacity_leaves=256) if small_tables else {}
-    g, o = _pair(0.1, 4.0, CFG_ROS, **kw)
+    res = 0.05 if small_tables else 0.1
+    g, o = _pair(res, 4.0, CFG_ROS, **kw)
+    # 300 k short rays per scan (clipped at 4 m): many more rays than resident DDA lanes and no ray longer than twice a
+    # lane's share, i.e. scans the planner sends down the QUEUED path (3,000-ray clouds never are). Tiny tables: a few
+    # scans of small extent keep the 16-brick update hash small, then a scan of the full 4 m extent overflows it while it is
+    # already queued behind the device-side guard -> refused -> redone by the finishing call (with the next raycast in flight).
+    def cloud(k):
+        n = 300000 + 2000 * (k % 3)
+        if small_tables and k in (0, 1, 2, 3, 5, 6):
+            # small extent, no long rays at all (ray length 0.2 .. 1.0 m): the planner keeps the NEXT scan on the queued path
+            rng = np.random.default_rng(900 + k)
+            d = rng.normal(size=(n, 3))
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            origin = rng.normal(size=3) * 0.3
+            return (origin + d * rng.uniform(0.2, 1.0, size=(n, 1))).astype(np.float32), origin
+        return scans.small_scan(500 + k, n=n, scale=2.5 + 0.3 * (k % 4))
+
     for k in range(12):
-        pts, origin = scans.small_scan(500 + k, n=3000 + 200 * (k % 3), scale=2.5 + 0.3 * (k % 4))
+        pts, origin = cloud(k)
         origin = origin + np.array([0.137 * k, 0.061 * k, 0.013 * k])
         g.insertPointCloudAsync(pts, origin, "s")
         pts[:] = np.nan  # the host buffer is free again as soon as the call returns
-        pts2, _ = scans.small_scan(500 + k, n=3000 + 200 * (k % 3), scale=2.5 + 0.3 * (k % 4))
+        pts2, _ = cloud(k)
         o.insertPointCloud(pts2, origin, "s")
         if k % 4 == 3:
             assert_leafsets_equal(g.exportMap(), o.exportMap(), f"map after scan {k}")  # exportMap finishes the queued scan
@@ -509,14 +525,21 @@ def test_async_pipeline_matches_the_oracle(small_tables):
     for key in ("rays", "clipped", "visits", "voxel_updates"):
         assert sg[key] == so[key], key
     assert sg["map_leaves"] == o.mapLeafCount()
+    # the paths this test is about were really taken: scans queued with their raycast half overlapping the previous scan's
+    # update, and (tiny tables) scans the device-side guard refused and the finishing call redid - with a raycast in flight
+    pc = g.pipelineCounts()
+    assert pc["queued"] + pc["redone"] + pc["synchronous"] == 12
+    assert pc["overlapped"] >= 4, pc
+    if small_tables:
+        assert pc["redone"] >= 1, pc
 
 
 def test_async_pipeline_full_size_and_interleaved_calls():
-    """cfg1 at full size: async inserts interleaved with sections, a reduced update and a synchronous insert of a second
-    source equal the all-synchronous run."""
+    """cfg2 at full size (the scans the queued path is made for): async inserts interleaved with sections and a synchronous
+    insert of a second source equal the all-synchronous run."""
     from vdb_mapping_b200 import scans
     from vdb_mapping_b200.mapping import OccupancyVDBMapping
-    c = scans.CONFIGS[1]
+    c = scans.CONFIGS[2]
     maps = []
     for _ in range(2):
         m = OccupancyVDBMapping(c.resolution)
@@ -524,18 +547,20 @@ def test_async_pipeline_full_size_and_interleaved_calls():
         m.addInputSource("s", c.max_range); m.addInputSource("t", c.max_range)
         maps.append(m)
     a, b = maps
-    for k in range(8):
-        pts, origin = scans.make_scan(1, k)
+    for k in range(10):
+        pts, origin = scans.make_scan(2, k)
         a.insertPointCloudAsync(pts, origin, "s")
         b.insertPointCloud(pts, origin, "s")
-        if k == 3:
-            lo, hi = np.array([-40, -40, -10], np.int32), np.array([40, 40, 10], np.int32)
+        if k == 4:
+            lo, hi = np.array([-80, -80, -20], np.int32), np.array([80, 80, 20], np.int32)
             assert_leafsets_equal(a.getMapSectionUpdateGrid(lo, hi), b.getMapSectionUpdateGrid(lo, hi), "section mid-pipeline")
-        if k == 5:
-            p2, o2 = scans.make_scan(1, 100)
+        if k == 6:
+            p2, o2 = scans.make_scan(2, 100)
             a.insertPointCloud(p2[:5000], o2, "t"); b.insertPointCloud(p2[:5000], o2, "t")
     assert_leafsets_equal(a.exportMap(), b.exportMap(), "async vs sync map")
     assert a.stats()["visits"] == b.stats()["visits"] and a.stats()["voxel_updates"] == b.stats()["voxel_updates"]
+    pc = a.pipelineCounts()
+    assert pc["queued"] >= 4 and pc["overlapped"] >= 3, pc
 
 
 def test_prefetched_cloud_is_used_and_stale_prefetch_is_ignored():

@@ -117,6 +117,7 @@ def lib() -> C.CDLL:
     sig("vdbm_update_pull", C.c_int, vp, cp)
     sig("vdbm_update_pull_integrate", C.c_int, vp, cp)
     sig("vdbm_exchange_timings", C.c_int, vp, f32p)
+    sig("vdbm_pipeline_counts", C.c_int, vp, u64p)
     sig("vdbm_stats", C.c_int, vp, C.POINTER(VdbmStats))
     sig("vdbm_last_error", cp, vp)
     sig("vdbm_synchronize", C.c_int, vp)

@@ -2576,6 +2576,16 @@ int vdbm_update_pull_integrate(vdbm_map* m, const char* source_id)
   return VDBM_OK;
 }
 
+int vdbm_pipeline_counts(vdbm_map* m, uint64_t out4[4])
+{
+  if (!m || !out4) return VDBM_ERR_INVALID_ARG;
+  out4[0] = m->async_fast;
+  out4[1] = m->async_redone;
+  out4[2] = m->async_sync;
+  out4[3] = m->async_overlapped;
+  return VDBM_OK;
+}
+
 int vdbm_stats(vdbm_map* m, vdbm_stats_t* out)
 {
   if (!m || !out) return VDBM_ERR_INVALID_ARG;

@@ -383,6 +383,12 @@ class OccupancyVDBMapping:
         self._check(self._L.vdbm_stats(self._h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in L.VdbmStats._fields_ if n != "reserved"}
 
+    def pipelineCounts(self) -> dict:
+        """Scans of insertPointCloudAsync by path: queued / redone after a guard refusal / synchronous / overlapped."""
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self._L.vdbm_pipeline_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return dict(zip(("queued", "redone", "synchronous", "overlapped"), (int(x) for x in out)))
+
     def mapLeafCount(self) -> int:
         return int(self.stats()["map_leaves"])
 
