@@ -592,14 +592,14 @@ def run_ours(args, rank, world, local_rank):
                 # Per-kernel times for the roofline, OUTSIDE the timed region: in the pipeline the raycast of scan k+1 runs next
                 # to updateMap of scan k, so CUDA events around one kernel also see the other. A few more scans through the
                 # synchronous calls (same kernels, nothing overlapped) give clean launch durations.
-                acc_ms, prep_ms, int_ms, leaves = [], [], [], []
+                p_acc, p_prep, p_int, p_leaves = [], [], [], []
                 for k in range(max(args.warmup, n_steps - 8), n_steps):
                     eng.accumulate_raw(resident[k].data_ptr(), n_pts_k[k], clouds[k][1], on_device=True)
                     s = m.stats()
-                    acc_ms.append(s["last_accumulate_ms"]); prep_ms.append(s["last_prep_ms"]); leaves.append(s["last_touched_leaves"])
+                    p_acc.append(s["last_accumulate_ms"]); p_prep.append(s["last_prep_ms"]); p_leaves.append(s["last_touched_leaves"])
                     eng.integrate()
-                    int_ms.append(m.stats()["last_integrate_ms"])
-                out.update({"acc_ms": acc_ms, "prep_ms": prep_ms, "int_ms": int_ms, "leaves": leaves, "kernel_probe": len(acc_ms)})
+                    p_int.append(m.stats()["last_integrate_ms"])
+                out["probe"] = {"acc_ms": p_acc, "prep_ms": p_prep, "int_ms": p_int, "leaves": p_leaves}
             if world > 1 and not mixed and not e2e:
                 out["checksum"] = m.mapChecksum()  # parity witness of the sharded map, compared below (outside the timed region)
             if mixed:
@@ -664,10 +664,18 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = rays_e / (ms_e * 1e-3)
     peak, peak_src = measured_peaks()
     mean = lambda x: float(sum(x) / max(1, len(x)))
-    L = mean(res_v["leaves"])
-    t_prep, t_acc, t_int = mean(res_v["prep_ms"]), mean(res_v["acc_ms"]), mean(res_v["int_ms"])
+    L_step = mean(res_v["leaves"])  # touched leaves per scan of the TIMED steps
+    probe = res_v.get("probe")
+    if probe:
+        # kernel durations (and the leaves those launches processed) come from the synchronous probe scans, see run_leg
+        L = mean(probe["leaves"])
+        t_prep, t_acc, t_int = mean(probe["prep_ms"]), mean(probe["acc_ms"]), mean(probe["int_ms"])
+    else:
+        L = L_step
+        t_prep, t_acc, t_int = mean(res_v["prep_ms"]), mean(res_v["acc_ms"]), mean(res_v["int_ms"])
     t_dda = t_acc - t_prep
     b_alg = alg_bytes(n_pts, int(L))  # cfg5: roofline figures describe the SENDER's scan-step kernels only
+    b_alg_step = alg_bytes(n_pts, int(L_step))
     t_kernels = t_acc + t_int
     # K2 alone: update masks read (128 B) + map leaf values+mask read and written (4224 B) per leaf THIS RANK integrates
     # (with N > 1 that is the rank's owned share after the exchange, not the leaves its own rays touched)
@@ -685,10 +693,12 @@ def run_ours(args, rank, world, local_rank):
         "frac": b_alg / (t_kernels * 1e-3) / 1e9 / peak, "traffic": traffic,
         "traffic_source": (f"profiles/{tr_src}: dram bytes of raycast_dda_kernel + apply_update_kernel per scan (ncu --set full, cfg2)" if traffic else None),
         "algorithmic_bytes_per_step": b_alg, "touched_leaves_per_step": L, "kernel_ms_per_step": t_kernels,
-        "frac_of_step_time": b_alg / (ms_v / K * 1e-3) / 1e9 / peak,
-        "kernel_times_from": ("%d extra scans through the synchronous calls after the timed region (the pipeline overlaps the raycast of "
-                              "scan k+1 with updateMap of scan k, so events inside it would see both kernels)" % res_v["kernel_probe"]) if res_v.get("kernel_probe")
-                             else "CUDA events of the timed steps",
+        "frac_of_step_time": b_alg_step / (ms_v / K * 1e-3) / 1e9 / peak,
+        "algorithmic_bytes_per_timed_step": b_alg_step, "touched_leaves_per_timed_step": L_step,
+        "kernel_times_from": ("%d extra scans through the synchronous calls after the timed region (the pipeline overlaps the raycast of scan k+1 "
+                              "with updateMap of scan k, so events inside it would see both kernels); achieved / frac / algorithmic_bytes_per_step / "
+                              "by_kernel describe those launches, frac_of_step_time = algorithmic bytes of the timed steps / ms_per_step"
+                              % len(probe["acc_ms"])) if probe else "CUDA events of the timed steps",
         "by_kernel": {
             "prep_rays_kernel": {"ms": t_prep, "alg_bytes": 64 * n_pts, "achieved_gbs": 64 * n_pts / (t_prep * 1e-3) / 1e9 if t_prep else None},
             "raycast_dda_kernel": {"ms": t_dda, "alg_bytes": 48 * n_pts + 128 * L,

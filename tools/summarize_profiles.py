@@ -35,10 +35,19 @@ for rep in sorted(glob.glob(os.path.join(go, f"prof_{tag}_*.ncu-rep"))):
         continue
     if hdr is None:
         hdr, units = rows[0], rows[1]
-    # different kernels expose the same metric set with --set full; align by name
+    # different kernels expose the same metric set with --set full; align by name. ncu picks the UNIT of a metric per report
+    # (the DDA's DRAM writes come in Kbyte, the update kernel's in Mbyte): rescale every value to the first report's unit.
     idxmap = {h: i for i, h in enumerate(rows[0])}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+    def conv(val, u_from, u_to):
+        if u_from == u_to or u_from not in scale or u_to not in scale:
+            return val
+        try:
+            return "%.6f" % (float(val.replace(",", "")) * scale[u_from] / scale[u_to])
+        except ValueError:
+            return val
     for r in rows[2:]:
-        data.append([r[idxmap[h]] if h in idxmap else "" for h in hdr])
+        data.append([conv(r[idxmap[h]], rows[1][idxmap[h]], units[j]) if h in idxmap else "" for j, h in enumerate(hdr)])
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
