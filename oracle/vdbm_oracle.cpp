@@ -997,6 +997,13 @@ struct MappingBase
         ++st.nan_skipped;
         continue;
       }
+      // +-inf is UNDEFINED in the reference (it ends in Coord::floor(NaN) / an int cast of inf). The documented behaviour of
+      // the B200 path - and therefore of its checker - is to drop such a point like a NaN.
+      if (std::isinf(end[0]) || std::isinf(end[1]) || std::isinf(end[2]) || std::isinf(origin[0]) || std::isinf(origin[1]) || std::isinf(origin[2]))
+      {
+        ++st.nan_skipped;
+        continue;
+      }
       if (raycast_range > 0.0)
       {
         // Vec3::length(): sqrt(x*x + y*y + z*z), left-associated

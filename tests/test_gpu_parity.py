@@ -129,8 +129,9 @@ def test_edge_inputs():
     for pts in (empty, allnan, same, one):
         assert g.accumulateUpdate(pts, [0, 0, 0], "s") == 0 and o.accumulateUpdate(pts, [0, 0, 0], "s") == 0
         assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "update")
-    g.accumulateUpdate(inf, [0, 0, 0], "s")                   # dropped (undefined in the reference)
+    g.accumulateUpdate(inf, [0, 0, 0], "s"); o.accumulateUpdate(inf, [0, 0, 0], "s")   # dropped (undefined in the reference)
     assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "update after inf")
+    assert g.stats()["nan_skipped"] == o.stats()["nan_skipped"] == 64 + 2
     # NaN origin: every point skipped (VDBMapping.hpp:505-510)
     g.accumulateUpdate(one, [np.nan, 0, 0], "s"); o.accumulateUpdate(one, [np.nan, 0, 0], "s")
     assert_leafsets_equal(g.exportUpdateGrid("s"), o.exportUpdateGrid("s"), "nan origin")

@@ -111,3 +111,17 @@ def test_raytrace_known_answers():
     empty = _map()
     ok, e = empty.raytrace([[0.0, 0.0, 0.0]], [[1.0, 0.0, 0.0]], 2.0)
     assert not ok[0] and np.allclose(e[0], [2.0, 0.0, 0.0])
+
+
+def test_infinite_points_are_dropped_like_nan():
+    """+-inf coordinates are undefined behaviour in the reference; the documented rule of this build is
+    'dropped and counted like NaN' - on the device (tests/test_gpu_parity.py::test_edge_inputs) and in the checker."""
+    o = _map()
+    pts = np.array([[np.inf, 0, 0], [0, -np.inf, 0], [1.0, 0, 0], [np.nan, 0, 0], [0, 0, np.inf]], dtype=np.float32)
+    o.accumulateUpdate(pts, np.zeros(3), "s")
+    st = o.stats()
+    assert st["rays"] == 5 and st["nan_skipped"] == 4
+    u = o.exportUpdateGrid("s")
+    assert _voxels(u, value=True) == {(10, 0, 0)}
+    o.accumulateUpdate(pts[2:3], np.array([np.inf, 0.0, 0.0]), "s")     # an infinite ORIGIN drops every point
+    assert o.stats()["nan_skipped"] == 5
