@@ -2477,7 +2477,9 @@ void launchApplyUpdateDeferred(UpdateGrid g, MapTable mt, LogOdds lo, uint32_t* 
   VDBM_LAUNCH(update_guard_kernel, 1, 1, s, g, mt, ctr, resolved_cap);
   const unsigned rgrid = std::max(1u, std::min<unsigned>(blocksFor(std::max(expected_entries, 1u), 256), unsigned(smCount()) * 8u));
   VDBM_LAUNCH(resolve_leaves_kernel, rgrid, 256, s, g, mt, lo, resolved, ctr, 0u, (const uint32_t*)&ctr->deferred_entries);
-  VDBM_LAUNCH(apply_update_kernel, unsigned(smCount() * applyUpdateBlocksPerSM()), 256, s, g, mt, lo, resolved, (LeafRecord*)nullptr, 0u, ctr, 0u,
+  int per_sm = applyUpdateBlocksPerSM();
+  if (const char* e = getenv("VDBM_APPLY_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e))); // experiments (co-residency with the DDA)
+  VDBM_LAUNCH(apply_update_kernel, unsigned(smCount() * per_sm), 256, s, g, mt, lo, resolved, (LeafRecord*)nullptr, 0u, ctr, 0u,
               (const uint32_t*)&ctr->deferred_entries);
   VDBM_LAUNCH(reset_bricks_kernel, blocksFor(uint64_t(g.cap_mask) + 1, 256), 256, s, g, 0u, (const uint32_t*)&ctr->deferred_bricks);
 }
