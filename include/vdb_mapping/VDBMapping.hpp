@@ -886,11 +886,40 @@ protected:
   {
     m_mirror_stale = false;
     if (!m_device_map) return;
-    vdbm_leafset* ls = nullptr;
-    if (report(vdbm_map_export(m_device_map, 1, &ls)) != VDBM_OK) return;
-    BackendT::putMapLeaves(*m_vdb_grid, vdbm_leafset_size(ls), vdbm_leafset_origins(ls), vdbm_leafset_values(ls), vdbm_leafset_active(ls));
-    vdbm_leafset_free(ls);
+    // the table "device pool index -> host leaf" is only good for one grid object, one generation of the device pool and
+    // as long as no leaf was removed from the host grid
+    const std::uint64_t generation = vdbm_map_generation(m_device_map), epoch = BackendT::gridEpoch(*m_vdb_grid);
+    if (m_mirror_table_grid != m_vdb_grid.get() || m_mirror_table_generation != generation || m_mirror_table_epoch != epoch)
+    {
+      m_mirror_table.clear();
+      m_mirror_table_grid       = m_vdb_grid.get();
+      m_mirror_table_generation = generation;
+      m_mirror_table_epoch      = epoch;
+    }
+    report(vdbm_map_mirror(m_device_map, m_mirror_chunk_leaves, &VDBMapping::mirrorSink, this, nullptr));
   }
+
+  /*! vdbm_mirror_sink: one chunk of modified leaves lands in the host grid while the next chunk is still on its way */
+  static int mirrorSink(void* user, std::uint64_t n, const std::uint32_t* leaf_index, const std::int32_t* origins, const float* values,
+                        const std::uint64_t* active)
+  {
+    VDBMapping* self = static_cast<VDBMapping*>(user);
+    BackendT::putMapLeavesIndexed(*self->m_vdb_grid, self->m_mirror_table, n, leaf_index, origins, values, active);
+    return 0;
+  }
+
+public:
+  /*! Not part of the reference API: forget the leaf table of the host mirror. Needed only by a consumer that removes or
+   *  merges leaf nodes of the grid returned by getGrid() (prune, clear ...) while the map keeps running. */
+  void invalidateMirrorTable()
+  {
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    m_mirror_table.clear();
+  }
+  /*! Not part of the reference API: leaves per chunk of the mirror transfer (0 = library default). */
+  void setMirrorChunkLeaves(std::uint64_t n) { m_mirror_chunk_leaves = n; }
+
+protected:
 
   /*! R:1383-1411 */
   void accumulationThread(std::string source_id)
@@ -947,6 +976,10 @@ protected:
   std::atomic<bool> m_config_set;
   MirrorMode m_mirror_mode = MirrorMode::Eager;
   mutable bool m_mirror_stale = false;
+  std::vector<typename BackendT::MapLeafT*> m_mirror_table; // device pool index -> leaf of m_vdb_grid
+  const void* m_mirror_table_grid         = nullptr;
+  std::uint64_t m_mirror_table_generation = 0, m_mirror_table_epoch = 0;
+  std::uint64_t m_mirror_chunk_leaves     = 0;
   bool m_scratch_ready        = false;
   bool m_artificial_areas_present = false; // R:1529
   int m_compression_level         = 1;     // R:1524

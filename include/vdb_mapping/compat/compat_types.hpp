@@ -241,7 +241,13 @@ public:
   Accessor getAccessor() { return Accessor(this); }
   const ValueT& background() const { return m_background; }
   bool empty() const { return m_leaves.empty(); }
-  void clear() { m_leaves.clear(); }
+  void clear()
+  {
+    m_leaves.clear();
+    ++m_epoch;
+  }
+  // changes whenever leaves were REMOVED (pointers to leaves handed out earlier are void)
+  std::uint64_t structureEpoch() const { return m_epoch; }
   std::size_t leafCount() const { return m_leaves.size(); }
   std::uint64_t activeVoxelCount() const
   {
@@ -293,6 +299,7 @@ private:
   ValueT m_background;
   double m_voxel_size = 1.0;
   LeafMap m_leaves;
+  std::uint64_t m_epoch = 0;
   std::map<std::string, Vec3d> m_meta;
 };
 

@@ -7,8 +7,11 @@
 #define VDB_MAPPING_DETAIL_BACKEND_HPP_INCLUDED
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -36,6 +39,88 @@ inline void parallelFor(std::uint64_t n, F&& f)
     });
   for (auto& x : th) x.join();
 }
+
+// The same on a persistent pool: the mirror of the device map (VDBMapping::syncMirrorLocked) merges a chunk of leaves every
+// few hundred microseconds while the next chunk crosses PCIe; starting threads per chunk would cost more than the copies.
+// Static ranges, the caller works too; one job at a time (callers are serialised by the shim's device mutex anyway).
+class WorkerPool
+{
+public:
+  static WorkerPool& instance()
+  {
+    static WorkerPool pool;
+    return pool;
+  }
+  template <typename F>
+  void run(std::uint64_t n, F&& f)
+  {
+    const unsigned T = unsigned(m_threads.size()) + 1;
+    if (n < 1024 || T == 1)
+    {
+      for (std::uint64_t i = 0; i < n; ++i) f(i);
+      return;
+    }
+    std::lock_guard<std::mutex> one_job(m_job_mutex);
+    std::function<void(unsigned)> body = [&](unsigned t) {
+      for (std::uint64_t i = n * t / T; i < n * (t + 1) / T; ++i) f(i);
+    };
+    {
+      std::lock_guard<std::mutex> lk(m_mutex);
+      m_body    = &body;
+      m_pending = T - 1;
+      ++m_ticket;
+    }
+    m_wake.notify_all();
+    body(0);
+    std::unique_lock<std::mutex> lk(m_mutex);
+    m_done.wait(lk, [&] { return m_pending == 0; });
+    m_body = nullptr;
+  }
+
+private:
+  WorkerPool()
+  {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned T  = std::min(16u, hw);
+    for (unsigned t = 1; t < T; ++t) m_threads.emplace_back([this, t] { loop(t); });
+  }
+  ~WorkerPool()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m_mutex);
+      m_stop = true;
+    }
+    m_wake.notify_all();
+    for (auto& th : m_threads) th.join();
+  }
+  void loop(unsigned t)
+  {
+    std::uint64_t seen = 0;
+    for (;;)
+    {
+      std::function<void(unsigned)>* body = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(m_mutex);
+        m_wake.wait(lk, [&] { return m_stop || m_ticket != seen; });
+        if (m_stop) return;
+        seen = m_ticket;
+        body = m_body;
+      }
+      (*body)(t);
+      {
+        std::lock_guard<std::mutex> lk(m_mutex);
+        if (--m_pending == 0) m_done.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> m_threads;
+  std::mutex m_mutex, m_job_mutex;
+  std::condition_variable m_wake, m_done;
+  std::function<void(unsigned)>* m_body = nullptr;
+  std::uint64_t m_ticket = 0;
+  unsigned m_pending     = 0;
+  bool m_stop            = false;
+};
 } // namespace detail
 } // namespace vdb_mapping
 
@@ -111,6 +196,31 @@ struct Backend
     parallelFor(n, [&](std::uint64_t i) {
       std::memcpy(dst[i]->buffer().data(), values + 512 * i, 512 * sizeof(float));
       typename LeafT::NodeMaskType mask;
+      for (int w = 0; w < 8; ++w) mask.template getWord<openvdb::Index64>(w) = active[8 * i + w];
+      dst[i]->setValueMask(mask);
+    });
+  }
+  // One chunk of vdbm_map_mirror: `table` maps the device pool index of a leaf to its host leaf, so a leaf is looked up in
+  // the tree only the first time it is seen (leaf nodes stay where they are while the tree is only grown; a consumer that
+  // restructures the mirror grid - prune, clear, merge - must call VDBMapping::invalidateMirrorTable()). The origin check
+  // catches a table that no longer matches the tree.
+  using MapLeafT = typename GridT::TreeType::LeafNodeType;
+  static std::uint64_t gridEpoch(const GridT&) { return 0; }
+  static void putMapLeavesIndexed(GridT& grid, std::vector<MapLeafT*>& table, std::uint64_t n, const std::uint32_t* index,
+                                  const std::int32_t* origins, const float* values, const std::uint64_t* active)
+  {
+    std::vector<MapLeafT*> dst(n);
+    for (std::uint64_t i = 0; i < n; ++i)
+    {
+      const openvdb::Coord o(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+      if (index[i] >= table.size()) table.resize(std::max<std::size_t>(index[i] + 1, table.size() * 2), nullptr);
+      MapLeafT*& slot = table[index[i]];
+      if (!slot || slot->origin() != o) slot = grid.tree().touchLeaf(o);
+      dst[i] = slot;
+    }
+    WorkerPool::instance().run(n, [&](std::uint64_t i) {
+      std::memcpy(dst[i]->buffer().data(), values + 512 * i, 512 * sizeof(float));
+      typename MapLeafT::NodeMaskType mask;
       for (int w = 0; w < 8; ++w) mask.template getWord<openvdb::Index64>(w) = active[8 * i + w];
       dst[i]->setValueMask(mask);
     });
@@ -288,6 +398,26 @@ struct Backend
     std::vector<openvdb::HostLeaf<float>*> dst;
     grid.touchLeaves(n, origins, dst);
     parallelFor(n, [&](std::uint64_t i) {
+      std::memcpy(dst[i]->values, values + 512 * i, 512 * sizeof(float));
+      std::memcpy(dst[i]->active, active + 8 * i, 8 * sizeof(std::uint64_t));
+    });
+  }
+  // One chunk of vdbm_map_mirror (see the OpenVDB branch): device pool index -> host leaf table; std::map nodes never move,
+  // and HostGrid::structureEpoch() tells the shim when leaves were removed.
+  using MapLeafT = openvdb::HostLeaf<TData>;
+  static std::uint64_t gridEpoch(const GridT& grid) { return grid.structureEpoch(); }
+  static void putMapLeavesIndexed(GridT& grid, std::vector<MapLeafT*>& table, std::uint64_t n, const std::uint32_t* index,
+                                  const std::int32_t* origins, const float* values, const std::uint64_t* active)
+  {
+    std::vector<MapLeafT*> dst(n);
+    for (std::uint64_t i = 0; i < n; ++i)
+    {
+      if (index[i] >= table.size()) table.resize(std::max<std::size_t>(index[i] + 1, table.size() * 2), nullptr);
+      MapLeafT*& slot = table[index[i]];
+      if (!slot) slot = &grid.touchLeaf(openvdb::Coord(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]));
+      dst[i] = slot;
+    }
+    WorkerPool::instance().run(n, [&](std::uint64_t i) {
       std::memcpy(dst[i]->values, values + 512 * i, 512 * sizeof(float));
       std::memcpy(dst[i]->active, active + 8 * i, 8 * sizeof(std::uint64_t));
     });

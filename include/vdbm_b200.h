@@ -158,6 +158,19 @@ int vdbm_change_export(vdbm_map* map, const char* source_id, vdbm_leafset** out)
 /* getGrid V:799: map leaves (origin, 512 x f32, active mask). dirty_only != 0: only leaves modified since the
  * previous vdbm_map_export call (what an eager/lazy host mirror needs); 0: all leaves. */
 int vdbm_map_export(vdbm_map* map, int dirty_only, vdbm_leafset** out);
+/* getGrid V:799 for a host grid that FOLLOWS the device map (the shim's mirror, tests/mapping.cpp:13-29 read through an
+ * accessor taken before the insert): every leaf modified since the previous vdbm_map_mirror / vdbm_map_export(dirty) call is
+ * handed to `sink` in chunks of at most chunk_leaves (0 = 16384); the device gather and the D2H copy of the following
+ * chunks run while sink works on the current one, so the host-side merge hides behind PCIe. Chunks arrive in ascending
+ * leaf_index = the leaf's slot in the device pool: fixed for the lifetime of the leaf and dense (a new leaf takes the
+ * next index) until the pool restarts (vdbm_reset, vdbm_map_import with replace: vdbm_map_generation changes), so a
+ * consumer can keep a table leaf_index -> host leaf instead of looking leaves up by origin. The arrays are valid only
+ * during the call. sink returns non-zero to abort: the chunk of that call and every later one stay dirty. n_leaves (may be
+ * NULL) receives the number of leaves delivered. */
+typedef int (*vdbm_mirror_sink)(void* user, uint64_t n, const uint32_t* leaf_index /*[n]*/, const int32_t* origins /*[n][3]*/,
+                                const float* values /*[n][512]*/, const uint64_t* active /*[n][8]*/);
+int vdbm_map_mirror(vdbm_map* map, uint64_t chunk_leaves, vdbm_mirror_sink sink, void* user, uint64_t* n_leaves);
+uint64_t vdbm_map_generation(const vdbm_map* map);
 /* getMapSection<T> V:921-960 with extractSparseLeaf V:999-1011 / extractFullLeaf V:970-989 on an INCLUSIVE
  * index bounding box (createIndexBoundingBox V:857-871 is host maths and stays in the shim).
  * result_float = 0 -> UpdateGridT result (active + value masks), 1 -> GridT result (active + 512 f32). */

@@ -191,6 +191,71 @@ def test_sections_and_dirty_export():
     assert len(g.exportMap(dirty_only=True)) == 0
 
 
+def test_mirror_stream_follows_the_map():
+    """vdbm_map_mirror (the shim's host mirror): a host copy kept up to date ONLY from the chunked stream, addressed through the
+    pool-index table, equals the oracle's map after every scan; chunks are index-ordered, an aborted transfer loses nothing, a
+    reset starts a new generation."""
+    from vdb_mapping_b200 import scans
+    g, o = _pair(0.1, 4.0, CFG_ROS)
+    host = {}      # pool index -> [origin, values, active]
+    seen_chunks = []
+
+    def sink(idx, origins, values, active):
+        assert np.all(np.diff(idx.astype(np.int64)) > 0)
+        seen_chunks.append(len(idx))
+        for i, l in enumerate(idx):
+            if int(l) in host:
+                assert tuple(host[int(l)][0]) == tuple(origins[i])     # an index never changes its leaf
+            host[int(l)] = [origins[i].copy(), values[i].copy(), active[i].copy()]
+        return 0
+
+    def host_leafset():
+        items = sorted(host.values(), key=lambda t: tuple(t[0]))
+        return (np.array([t[0] for t in items]), np.array([t[1] for t in items]), np.array([t[2] for t in items]))
+
+    gen0 = g.mapGeneration()
+    last = 0
+    for k in range(5):
+        pts, origin = scans.small_scan(400 + k, n=6000, scale=2.5)
+        origin = origin + np.array([0.21 * k, -0.13 * k, 0.02 * k])
+        g.insertPointCloud(pts, origin, "s"); o.insertPointCloud(pts, origin, "s")
+        seen_chunks.clear()
+        n = g.mirrorMap(sink, chunk_leaves=(64, 100, 1 << 15, 7, 0)[k])       # many small chunks, one big chunk, default
+        assert n == sum(seen_chunks) and n > 0
+        if k == 0:
+            assert max(seen_chunks) <= 64 and len(seen_chunks) >= 3            # the rotation of the three buffers was exercised
+        ref = o.exportMap()
+        ho, hv, ha = host_leafset()
+        assert np.array_equal(ho, ref.origins) and np.array_equal(ha, ref.active)
+        assert np.array_equal(hv.view(np.uint32), ref.values.view(np.uint32))
+        assert sorted(host) == list(range(len(host))) and len(host) >= last    # dense pool indices, append-only
+        last = len(host)
+        assert g.mirrorMap(sink) == 0                                          # nothing is dirty any more
+    # abort after the first chunk: the rest stays dirty and arrives with the next call
+    pts, origin = scans.small_scan(999, n=6000, scale=2.5)
+    g.insertPointCloud(pts, origin, "s"); o.insertPointCloud(pts, origin, "s")
+    from vdb_mapping_b200.mapping import VdbmError
+    calls = []
+
+    def quitter(idx, origins, values, active):
+        calls.append(len(idx))
+        return 1
+
+    with pytest.raises(VdbmError):
+        g.mirrorMap(quitter, chunk_leaves=32)
+    assert len(calls) == 1
+    n = g.mirrorMap(sink, chunk_leaves=50)
+    assert n >= calls[0]
+    ref = o.exportMap()
+    ho, hv, ha = host_leafset()
+    assert np.array_equal(ho, ref.origins) and np.array_equal(ha, ref.active) and np.array_equal(hv.view(np.uint32), ref.values.view(np.uint32))
+    # the dirty export and the mirror share the flags
+    g.insertPointCloud(pts, origin, "s")
+    assert len(g.exportMap(dirty_only=True)) > 0 and g.mirrorMap(sink) == 0
+    g.resetMap()
+    assert g.mapGeneration() == gen0 + 1 and g.mirrorMap(sink) == 0
+
+
 def test_update_grid_import_roundtrip_and_reset():
     """updateMap(grid produced elsewhere): export on one map, import on another, maps end identical."""
     from vdb_mapping_b200 import scans

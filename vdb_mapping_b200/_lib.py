@@ -28,6 +28,10 @@ class VdbmStats(C.Structure):
                 ("update_capacity", C.c_uint32), ("map_capacity", C.c_uint32), ("gpu_launches", C.c_uint32)]
 
 
+# vdbm_mirror_sink: (user, n, leaf_index[n], origins[n][3], values[n][512], active[n][8]) -> 0 to go on
+MIRROR_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                          C.POINTER(C.c_uint64))
+
 _lib = None
 
 
@@ -69,6 +73,8 @@ def lib() -> C.CDLL:
     sig("vdbm_update_import", C.c_int, vp, cp, u64, i32p, u64p, u64p)
     sig("vdbm_change_export", C.c_int, vp, cp, pvp)
     sig("vdbm_map_export", C.c_int, vp, C.c_int, pvp)
+    sig("vdbm_map_mirror", C.c_int, vp, u64, MIRROR_SINK, vp, C.POINTER(C.c_uint64))
+    sig("vdbm_map_generation", C.c_uint64, vp)
     sig("vdbm_section", C.c_int, vp, i32p, i32p, C.c_int, C.c_int, pvp)
     sig("vdbm_section_apply_update", C.c_int, vp, i32p, i32p, u64, i32p, u64p)
     sig("vdbm_section_apply_grid", C.c_int, vp, u64, i32p, u64p, f32p, C.c_int)

@@ -167,6 +167,17 @@ struct vdbm_map
   bool h_stage_lent  = false;
   vdbm_leafset* h_stage_borrower = nullptr;
 
+  // vdbm_map_mirror: rotating chunk buffers (device gather target + pinned host landing zone) and their "copied" events
+  struct Mirror
+  {
+    static constexpr int kBufs = 3;
+    uint8_t* d_buf[kBufs] = {nullptr, nullptr, nullptr};
+    uint8_t* h_buf[kBufs] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[kBufs] = {nullptr, nullptr, nullptr};
+    uint32_t cap_leaves   = 0;
+  } mirror;
+  uint64_t generation = 0; // bumped whenever the leaf pool restarts (vdbm_reset, vdbm_map_import with replace): leaf indices are void
+
   vdbm_stats_t stats{};
   Counters base{}; // counters at the last reset, to keep cumulative numbers across device counter resets
 };
@@ -1172,6 +1183,12 @@ void vdbm_destroy(vdbm_map* m)
     m->h_stage_borrower->orphan_stage = m->h_stage;
     m->h_stage                        = nullptr;
   }
+  for (int b = 0; b < vdbm_map::Mirror::kBufs; ++b)
+  {
+    cudaFree(m->mirror.d_buf[b]);
+    if (m->mirror.h_buf[b]) cudaFreeHost(m->mirror.h_buf[b]);
+    if (m->mirror.ev[b]) cudaEventDestroy(m->mirror.ev[b]);
+  }
   if (m->h_stage) cudaFreeHost(m->h_stage);
   for (cudaEvent_t e : {m->ev0, m->ev1, m->ev2})
     if (e) cudaEventDestroy(e);
@@ -1189,6 +1206,7 @@ int vdbm_reset(vdbm_map* m)
   CU_TRY(m, cudaMemsetAsync(m->d_map_counters, 0, 8, m->stream));
   m->n_leaves = 0;
   m->coarse_built = ~0u; // the coarse node sets describe the old map: rebuilt from scratch on next use
+  ++m->generation;
   for (auto& kv : m->sources)
   {
     Source& s = *kv.second;
@@ -1906,6 +1924,99 @@ int vdbm_map_export(vdbm_map* m, int dirty_only, vdbm_leafset** out)
   return VDBM_OK;
 }
 
+uint64_t vdbm_map_generation(const vdbm_map* m) { return m ? m->generation : 0; }
+
+// Streams the dirty leaves to the consumer chunk by chunk: gather (HBM -> device chunk buffer) and the D2H copy of the
+// next chunks are queued while the consumer works on the current one; three buffers rotate. Bytes per leaf over PCIe:
+// 2048 values + 64 active mask + 12 origin + 4 pool index.
+int vdbm_map_mirror(vdbm_map* m, uint64_t chunk_leaves, vdbm_mirror_sink sink, void* user, uint64_t* n_leaves_out)
+{
+  if (!m || !sink) return VDBM_ERR_INVALID_ARG;
+  VDBM_ENTER(m);
+  if (n_leaves_out) *n_leaves_out = 0;
+  int rc = syncCounters(m);
+  if (rc) return rc;
+  const uint32_t n_all = m->n_leaves;
+  if (n_all == 0) return VDBM_OK;
+  TempBuf dl(m->stream), ds(m->stream), tmp(m->stream);
+  CU_TRY(m, dl.alloc(size_t(n_all) * 4));
+  CU_TRY(m, cudaMemsetAsync(&m->d_ctr->n_out, 0, sizeof(unsigned), m->stream));
+  launchCollectDirty(m->mt, n_all, dl.as<uint32_t>(), m->d_ctr, m->stream);
+  CU_TRY(m, cudaGetLastError());
+  rc = syncCounters(m);
+  if (rc) return rc;
+  const uint32_t n = std::min(m->h_ctr->n_out, n_all);
+  if (n == 0) return VDBM_OK;
+  // pool-index order: deterministic, new leaves arrive in creation order, the gather walks the pool front to back
+  CU_TRY(m, ds.alloc(size_t(n) * 4));
+  const size_t sort_bytes = sortKeys32(nullptr, 0, dl.as<uint32_t>(), ds.as<uint32_t>(), n, m->stream);
+  CU_TRY(m, tmp.alloc(sort_bytes));
+  sortKeys32(tmp.p, sort_bytes, dl.as<uint32_t>(), ds.as<uint32_t>(), n, m->stream);
+  CU_TRY(m, cudaGetLastError());
+  const uint32_t* d_idx = ds.as<uint32_t>();
+
+  vdbm_map::Mirror& mr = m->mirror;
+  const uint32_t want  = uint32_t(std::min<uint64_t>(chunk_leaves ? chunk_leaves : 16384, 1u << 20));
+  constexpr size_t kLeafBytes = 2048 + 64 + 12 + 4;
+  if (mr.cap_leaves < want)
+  {
+    for (int b = 0; b < vdbm_map::Mirror::kBufs; ++b)
+    {
+      cudaFree(mr.d_buf[b]);
+      if (mr.h_buf[b]) cudaFreeHost(mr.h_buf[b]);
+      mr.d_buf[b] = mr.h_buf[b] = nullptr;
+    }
+    mr.cap_leaves = 0;
+    for (int b = 0; b < vdbm_map::Mirror::kBufs; ++b)
+    {
+      CU_TRY(m, cudaMalloc(&mr.d_buf[b], size_t(want) * kLeafBytes));
+      CU_TRY(m, cudaHostAlloc(reinterpret_cast<void**>(&mr.h_buf[b]), size_t(want) * kLeafBytes, cudaHostAllocDefault));
+      if (!mr.ev[b]) CU_TRY(m, cudaEventCreateWithFlags(&mr.ev[b], cudaEventDisableTiming));
+    }
+    mr.cap_leaves = want;
+  }
+  const uint32_t C = want; // chunk size of THIS call (buffers may be larger)
+  // chunk buffer layout (same on both sides): values [C][512] | active [C][8] | origins [C][3] | index [C]
+  auto valuesOf  = [&](uint8_t* p) { return reinterpret_cast<float*>(p); };
+  auto activeOf  = [&](uint8_t* p) { return reinterpret_cast<uint64_t*>(p + size_t(C) * 2048); };
+  auto originsOf = [&](uint8_t* p) { return reinterpret_cast<int32_t*>(p + size_t(C) * (2048 + 64)); };
+  auto indexOf   = [&](uint8_t* p) { return reinterpret_cast<uint32_t*>(p + size_t(C) * (2048 + 64 + 12)); };
+  const uint32_t n_chunks = (n + C - 1) / C;
+  auto enqueue = [&](uint32_t k) -> cudaError_t {
+    const int b        = int(k % vdbm_map::Mirror::kBufs);
+    const uint32_t off = k * C, cnt = std::min(C, n - off);
+    uint8_t *d = mr.d_buf[b], *h = mr.h_buf[b];
+    launchGatherMap(m->mt, cnt, d_idx + off, originsOf(d), activeOf(d), valuesOf(d), m->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(valuesOf(h), valuesOf(d), size_t(cnt) * 2048, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(activeOf(h), activeOf(d), size_t(cnt) * 64, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(originsOf(h), originsOf(d), size_t(cnt) * 12, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(indexOf(h), d_idx + off, size_t(cnt) * 4, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(mr.ev[b], m->stream);
+    return e;
+  };
+  for (uint32_t k = 0; k < std::min<uint32_t>(n_chunks, vdbm_map::Mirror::kBufs); ++k) CU_TRY(m, enqueue(k));
+  for (uint32_t k = 0; k < n_chunks; ++k)
+  {
+    const int b        = int(k % vdbm_map::Mirror::kBufs);
+    const uint32_t off = k * C, cnt = std::min(C, n - off);
+    CU_TRY(m, cudaEventSynchronize(mr.ev[b]));
+    uint8_t* h = mr.h_buf[b];
+    if (sink(user, cnt, indexOf(h), originsOf(h), valuesOf(h), activeOf(h)) != 0)
+    {
+      // the consumer gave up: what it has not seen stays dirty for the next call
+      cudaStreamSynchronize(m->stream);
+      launchMarkDirty(m->mt, d_idx + off, n - off, m->stream);
+      CU_TRY(m, cudaStreamSynchronize(m->stream));
+      return fail(m, VDBM_ERR_INVALID_ARG, "vdbm_map_mirror: the sink aborted the transfer");
+    }
+    if (n_leaves_out) *n_leaves_out += cnt;
+    if (k + vdbm_map::Mirror::kBufs < n_chunks) CU_TRY(m, enqueue(k + vdbm_map::Mirror::kBufs));
+  }
+  CU_TRY(m, cudaStreamSynchronize(m->stream));
+  return VDBM_OK;
+}
+
 int vdbm_section(vdbm_map* m, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float, vdbm_leafset** out)
 {
   if (!m || !out || !bbmin || !bbmax) return VDBM_ERR_INVALID_ARG;
@@ -2075,6 +2186,7 @@ int vdbm_map_import(vdbm_map* m, uint64_t n, const int32_t* origins, const uint6
     CU_TRY(m, cudaMemsetAsync(m->d_map_counters, 0, 8, m->stream));
     m->n_leaves = 0;
     m->coarse_built = ~0u;
+    ++m->generation;
     int rc = syncCounters(m);
     if (rc) return rc;
   }

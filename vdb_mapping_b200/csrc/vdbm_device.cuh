@@ -304,6 +304,7 @@ void launchImportUpdateSoA(UpdateGrid ug, const int32_t* origins, const uint64_t
                            cudaStream_t s);
 void launchGatherMap(MapTable mt, uint32_t n, const uint32_t* leaf_idx, int32_t* origins, uint64_t* mask, float* vals, cudaStream_t s);
 void launchCollectDirty(MapTable mt, uint32_t n_leaves, uint32_t* out_idx, Counters* ctr, cudaStream_t s); // appends via ctr->n_out, clears flags
+void launchMarkDirty(MapTable mt, const uint32_t* idx, uint32_t n, cudaStream_t s); // sets the flags of the listed leaves again
 void launchSection(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float,
                    uint64_t* out_keys, uint64_t* out_active, uint64_t* out_valmask, float* out_vals, uint32_t out_cap,
                    Counters* ctr, cudaStream_t s);
@@ -351,6 +352,8 @@ uint32_t launchCount(); // kernels of this library launched by this process
 // CUB radix sort (descending) of (visit count, ray index) on key bits [3, 11) (one radix pass); returns temp bytes when d_temp == nullptr
 size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* idx_in,
                         uint32_t* idx_out, uint32_t n, cudaStream_t s);
+// CUB radix sort of 32-bit keys (ascending); returns bytes of temp storage needed when d_temp == nullptr
+size_t sortKeys32(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, uint32_t n, cudaStream_t s);
 // CUB radix sort of (key, idx) pairs; returns bytes of temp storage needed when d_temp == nullptr
 size_t sortPairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* idx_in,
                  uint32_t* idx_out, uint32_t n, cudaStream_t s);

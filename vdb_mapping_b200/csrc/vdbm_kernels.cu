@@ -1242,6 +1242,13 @@ __global__ void collect_dirty_kernel(MapTable mt, uint32_t n_leaves, uint32_t* o
   if (d) out_idx[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
+// vdbm_map_mirror aborted by its consumer: the leaves that were not delivered become dirty again
+__global__ void mark_dirty_kernel(MapTable mt, const uint32_t* idx, uint32_t n)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mt.leaf_dirty[idx[i]] = 1u;
+}
+
 // K3: getMapSection. One warp per map leaf; overlapping leaves with content inside the box are appended
 // (unsorted; the host sorts the small result by key).
 __global__ void __launch_bounds__(256) section_kernel(MapTable mt, uint32_t n_leaves, int bx0, int by0, int bz0, int bx1, int by1, int bz1,
@@ -2527,6 +2534,10 @@ void launchCollectDirty(MapTable mt, uint32_t n_leaves, uint32_t* out_idx, Count
 {
   if (n_leaves) VDBM_LAUNCH(collect_dirty_kernel, blocksFor(n_leaves, 256), 256, s, mt, n_leaves, out_idx, ctr);
 }
+void launchMarkDirty(MapTable mt, const uint32_t* idx, uint32_t n, cudaStream_t s)
+{
+  if (n) VDBM_LAUNCH(mark_dirty_kernel, blocksFor(n, 256), 256, s, mt, idx, n);
+}
 void launchSection(MapTable mt, uint32_t n_leaves, const int32_t bbmin[3], const int32_t bbmax[3], int full, int result_float,
                    uint64_t* out_keys, uint64_t* out_active, uint64_t* out_valmask, float* out_vals, uint32_t out_cap,
                    Counters* ctr, cudaStream_t s)
@@ -2649,6 +2660,14 @@ size_t sortRaysByLength(void* d_temp, size_t temp_bytes, const uint32_t* keys_in
   size_t bytes = temp_bytes;
   if (d_temp == nullptr) bytes = 0;
   cub::DeviceRadixSort::SortPairsDescending(d_temp, bytes, keys_in, keys_out, idx_in, idx_out, int(n), kSortLoBit, kSortHiBit, s);
+  return bytes;
+}
+
+size_t sortKeys32(void* d_temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, uint32_t n, cudaStream_t s)
+{
+  size_t bytes = temp_bytes;
+  if (d_temp == nullptr) bytes = 0;
+  cub::DeviceRadixSort::SortKeys(d_temp, bytes, keys_in, keys_out, int(n), 0, 32, s);
   return bytes;
 }
 

@@ -249,6 +249,25 @@ class OccupancyVDBMapping:
         self._check(self._L.vdbm_map_export(self._h, int(dirty_only), C.byref(out)))
         return self._take(out, True)
 
+    def mirrorMap(self, sink, chunk_leaves: int = 0) -> int:
+        """vdbm_map_mirror: streams the leaves modified since the previous mirror / dirty export to
+        sink(leaf_index[n], origins[n,3], values[n,512], active[n,8]) chunk by chunk (the arrays are views that die with the
+        call; a truthy return value aborts). Returns the number of leaves delivered."""
+        def _sink(_user, n, idx, origins, values, active):
+            n = int(n)
+            r = sink(np.ctypeslib.as_array(idx, (n,)), np.ctypeslib.as_array(origins, (n, 3)),
+                     np.ctypeslib.as_array(values, (n, 512)), np.ctypeslib.as_array(active, (n, 8)))
+            return 1 if r else 0
+        cb = L.MIRROR_SINK(_sink)
+        done = C.c_uint64(0)
+        rc = self._L.vdbm_map_mirror(self._h, int(chunk_leaves), cb, None, C.byref(done))
+        self._mirror_delivered = int(done.value)
+        self._check(rc)
+        return int(done.value)
+
+    def mapGeneration(self) -> int:
+        return int(self._L.vdbm_map_generation(self._h))
+
     def _section(self, bbmin, bbmax, full, result_float) -> LeafSet:
         mn = np.ascontiguousarray(bbmin, dtype=np.int32)
         mx = np.ascontiguousarray(bbmax, dtype=np.int32)
