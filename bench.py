@@ -456,6 +456,51 @@ def strong_cfg4_block(args, rank, world, local_rank, stream, dist):
     }
 
 # ------------------------------------------------------------------------------------------------------------------
+def shim_block(cfg: int, clouds, n_lazy: int = 30, n_eager: int = 14, warmup: int = 4):
+    """The same scans through the reference-compatible C++ CLASS (include/vdb_mapping/OccupancyVDBMapping.hpp ->
+    insertPointCloud), i.e. what an unmodified consumer of vdb_mapping sees: tools/bench_shim.cpp, a separate process with
+    no Python in it, clouds in ordinary (pageable) std::vector memory, wall clock. Two mirror policies of getGrid():
+    Lazy (the scan is queued; the host grid is brought up to date when getGrid() is called) and Eager (default of the
+    shim: every insert ends with the modified leaves copied into the host grid, so an accessor taken earlier stays live,
+    tests/mapping.cpp:13-29). Runs after the timed legs; never inside a timed region."""
+    import struct
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "tools", "build", "bench_shim")
+    so = os.path.join(ROOT, "vdb_mapping_b200", "libvdbm_b200.so")
+    try:
+        if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(so):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "bench_shim.cpp"),
+                            "-o", exe, so, "-Wl,-rpath," + os.path.join("$ORIGIN", "..", "..", "vdb_mapping_b200"), "-lpthread"], check=True, capture_output=True)
+        c = scans.CONFIGS[cfg]
+        n = min(len(clouds), max(n_lazy, n_eager))
+        out = {"api": "vdb_mapping::OccupancyVDBMapping::insertPointCloud (C++ shim over the C ABI, separate process, pageable clouds, wall clock)",
+               "modes": "lazy / eager = MirrorMode of getGrid(); sources4 = each scan split into 4 azimuth sectors fed as 4 input sources from 4 threads "
+                        "(accumulateUpdate x 4, then integrateUpdate; compare cpu_baseline.multi_source), every source on its own raycast handle; "
+                        "sources4_shared = the same with all sources taking turns on the map's handle"}
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "scans.bin")
+            with open(path, "wb") as f:
+                f.write(struct.pack("7d", c.resolution, c.max_range, c.prob_hit, c.prob_miss, c.prob_thres_min, c.prob_thres_max, n))
+                for pts, origin in clouds[:n]:
+                    p16 = np.ones((pts.shape[0], 4), dtype=np.float32)
+                    p16[:, :3] = pts[:, :3]
+                    f.write(struct.pack("3d", *origin)); f.write(struct.pack("I", p16.shape[0])); f.write(p16.tobytes())
+            for mode, count in (("lazy", n_lazy), ("eager", n_eager), ("sources4", n_lazy), ("sources4_shared", n_lazy)):
+                p = subprocess.run([exe, path, mode, str(warmup), str(min(n, count))], capture_output=True, text=True, timeout=600)
+                rows = [l for l in p.stdout.splitlines() if l.startswith("{")]
+                if p.returncode != 0 or not rows:
+                    out[mode] = {"error": (p.stderr or p.stdout)[-300:]}
+                    continue
+                d = json.loads(rows[-1])
+                out[mode] = {k: d[k] for k in ("scans", "ms_per_scan", "rays_per_sec", "map_leaves", "host_grid_active_voxels", "mirror_leaves_per_scan") if k in d}
+        return out
+    except Exception as e:  # the block is informative; it must never cost the bench line
+        return {"error": repr(e)[:300]}
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -750,6 +795,8 @@ def run_ours(args, rank, world, local_rank):
         line["exchange"] = {"kind": args.exchange, "records_sent_per_step": (sent / K) if args.exchange == "nccl" else None,
                             "bytes_sent_per_step": (136 * sent / K) if args.exchange == "nccl" else None,
                             "note": "p2p = one kernel bins the update leaves by owner and stores the 136-byte records into the owners' inboxes over NVLink (CUDA IPC), device-side epoch wait; nccl = count + record all-to-all"}
+    if world == 1 and not mixed and not args.no_shim_block:
+        line["shim"] = shim_block(cfg, clouds)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(cfg, args.cpu_scans)
     else:
@@ -794,6 +841,7 @@ def main():
     ap.add_argument("--cpu-scans", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong-block", action="store_true", help="skip the strong_cfg4 block (1M-point scans split over all ranks)")
+    ap.add_argument("--no-shim-block", action="store_true", help="skip the shim block (the same scans through the C++ class API)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="1 GPU: use the synchronous accumulate + integrate calls instead of vdbm_insert_async")
     args = ap.parse_args()

@@ -69,6 +69,22 @@ enum class MirrorMode
   Lazy
 };
 
+/*! Where the rays of an input source are cast (not part of the reference API). The reference's one parallel axis is a
+ *  thread per input source, each raycasting into its own update grid under a shared lock (R:316-346, 1383-1411). A C ABI
+ *  handle is thread-compatible, not thread-safe, so sources that share the map's handle take turns on the device. With
+ *  PerSource every source owns a second, raycast-only handle (own stream, staging buffers and counters, a one-leaf map):
+ *  accumulateUpdate() of different sources then runs concurrently - host side and on the GPU, where the DDA launches of small
+ *  clouds co-reside - and integrateUpdate() moves the accumulated update leaves device-to-device into the map's handle
+ *  (vdbm_update_partition -> vdbm_update_import_device) before updateMap. Auto = PerSource as soon as more than one source
+ *  is registered (costs one update grid, 0.5 GB at the default capacity, per source). fast_mode always uses the map's
+ *  handle: castRayIntoGridFast reads the map. */
+enum class SourceConcurrency
+{
+  Auto,
+  Shared,
+  PerSource
+};
+
 template <typename TData, typename TConfig = BaseConfig>
 class VDBMapping
 {
@@ -91,6 +107,11 @@ public:
     std::optional<std::pair<typename PointCloudT::ConstPtr, Eigen::Matrix<double, 3, 1> > > input_data;
     std::chrono::milliseconds max_input_period;
     std::condition_variable data_available_cv;
+    // SourceConcurrency::PerSource (all three guarded by update_grid_mutex or the exclusive map lock)
+    double max_range_as_given = 0.0;     // addInputSource argument (0 = follow the config range), what the device is told
+    vdbm_map* raycaster       = nullptr; // raycast-only device handle of this source
+    double raycaster_range    = -1.0;    // config range it was last configured with
+    bool raycaster_holds_data = false;   // update leaves accumulated there and not yet moved to the map's handle
   };
 
   VDBMapping()                  = delete;
@@ -130,6 +151,8 @@ public:
       if (worker_thread.joinable()) worker_thread.join();
     }
     if (m_integration_thread.joinable()) m_integration_thread.join();
+    for (auto& kv : m_input_sources)
+      if (kv.second->raycaster) vdbm_destroy(kv.second->raycaster);
     if (m_device_map) vdbm_destroy(m_device_map);
   }
 
@@ -144,6 +167,12 @@ public:
     {
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
       vdbm_reset(m_device_map);
+      for (auto& kv : m_input_sources) // "new empty update grids" R:181-185, wherever they live
+        if (kv.second->raycaster)
+        {
+          vdbm_reset(kv.second->raycaster);
+          kv.second->raycaster_holds_data = false;
+        }
     }
     m_vdb_grid->clear();
     m_vdb_grid = createVDBMap(m_resolution);
@@ -152,6 +181,8 @@ public:
 
   /*! Mirror policy of getGrid(); see the header comment. Not part of the reference API. */
   void setMirrorMode(MirrorMode mode) { m_mirror_mode = mode; }
+  /*! See SourceConcurrency. Not part of the reference API. */
+  void setSourceConcurrency(SourceConcurrency mode) { m_source_concurrency = mode; }
 
   /*! R:316-346. Unknown source: message + return; source range <= 0: nothing is raycast. */
   void accumulateUpdate(const typename PointCloudT::ConstPtr& cloud,
@@ -168,8 +199,16 @@ public:
     std::unique_lock update_grid_lock(source->second->update_grid_mutex);
     if (!m_device_map || !cloud) return;
     const double o[3] = {origin.x(), origin.y(), origin.z()};
-    // The C ABI handle is thread-compatible, not thread-safe: sources share its stream and staging buffers, so the
-    // accumulation threads of different sources take turns on the device (they still overlap their host work).
+    if (vdbm_map* raycaster = sourceRaycaster(source_id, *source->second))
+    {
+      // this source's own handle: no other thread touches it (update_grid_mutex), nothing is shared with the map's handle
+      const int rc = vdbm_accumulate(raycaster, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o);
+      source->second->raycaster_holds_data = true;
+      reportOn(raycaster, rc);
+      return;
+    }
+    // The C ABI handle is thread-compatible, not thread-safe: sources that share the map's handle take turns on the device
+    // (they still overlap their host work).
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     // the ABI wants the pcl::PointXYZ records as they lie in the cloud (16-byte stride)
     const int rc = vdbm_accumulate(m_device_map, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o);
@@ -200,6 +239,7 @@ public:
     m_map_mutex_requested = false;
     if (!m_device_map) return;
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    for (auto& kv : m_input_sources) collectRaycasterLocked(kv.first, *kv.second); // exclusive map lock: no accumulation is running
     report(vdbm_integrate(m_device_map, 0));
     if (m_mirror_mode == MirrorMode::Eager) syncMirrorLocked();
     else m_mirror_stale = true;
@@ -215,7 +255,7 @@ public:
       // throughput mode: the scan is queued as one pipeline stage (vdbm_insert_async: upload overlapped with the previous
       // scan, no host round trip between raycast and updateMap); getGrid() / any other member finishes it
       auto source = m_input_sources.find(source_id);
-      if (source != m_input_sources.end())
+      if (source != m_input_sources.end() && !source->second->raycaster_holds_data && !wantsRaycaster())
       {
         m_map_mutex_requested = true;
         std::unique_lock map_lock(*m_map_mutex);
@@ -456,10 +496,21 @@ public:
   {
     typename UpdateGridT::Ptr out = BackendT::createUpdateGrid(m_resolution);
     if (!m_device_map) return out;
+    auto source = m_input_sources.find(source_id);
+    std::unique_lock<std::mutex> update_grid_lock;
+    if (source != m_input_sources.end()) update_grid_lock = std::unique_lock<std::mutex>(source->second->update_grid_mutex);
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     vdbm_leafset* ls = nullptr;
     double o[3]      = {0, 0, 0};
-    if (report(vdbm_update_create(m_device_map, source_id.c_str(), level, &ls, o)) != VDBM_OK) return out;
+    vdbm_map* from   = m_device_map;
+    if (source != m_input_sources.end() && source->second->raycaster_holds_data)
+    {
+      // the ray end voxels of the last accumulate (level 2) stay with the handle that cast them; a raw grid (level 0) may be
+      // spread over both handles and is gathered in the map's first
+      if (level == 2) from = source->second->raycaster;
+      else if (level == 0) collectRaycasterLocked(source_id, *source->second);
+    }
+    if (reportOn(from, vdbm_update_create(from, source_id.c_str(), level, &ls, o)) != VDBM_OK) return out;
     if (origin) *origin = Eigen::Matrix<double, 3, 1>(o[0], o[1], o[2]);
     const std::uint64_t n = vdbm_leafset_size(ls);
     for (std::uint64_t i = 0; i < n; ++i)
@@ -718,15 +769,25 @@ public:
       // Re-adding a source (the reference overwrites the map entry, R:1374): its worker thread is blocked on THIS object's
       // condition variable, so the object stays and only its parameters change; pending input is dropped like the
       // reference's fresh InputSource would.
-      std::unique_lock lock(existing->second->input_data_mutex);
-      existing->second->max_range        = range;
-      existing->second->max_input_period = period;
-      existing->second->input_data.reset();
+      {
+        std::unique_lock lock(existing->second->input_data_mutex);
+        existing->second->max_range          = range;
+        existing->second->max_range_as_given = max_range;
+        existing->second->max_input_period   = period;
+        existing->second->input_data.reset();
+      }
+      std::unique_lock grid_lock(existing->second->update_grid_mutex);
+      if (existing->second->raycaster)
+      {
+        vdbm_source_add(existing->second->raycaster, source_id.c_str(), max_range); // empty grid, new range
+        existing->second->raycaster_holds_data = false;
+      }
       return;
     }
     auto s              = std::make_shared<InputSource>();
     s->source_id        = source_id;
     s->max_range        = range;
+    s->max_range_as_given = max_range;
     s->max_input_period = period;
     m_input_sources[source_id] = s;
     m_worker_threads[source_id] = std::thread(&VDBMapping::accumulationThread, this, source_id);
@@ -772,6 +833,60 @@ protected:
     return rc;
   }
 
+
+  int reportOn(vdbm_map* handle, int rc) const
+  {
+    if (rc != VDBM_OK && rc != VDBM_ERR_UNKNOWN_SOURCE && handle) std::cerr << "vdb_mapping (B200): " << vdbm_last_error(handle) << std::endl;
+    return rc;
+  }
+
+  /*! does accumulateUpdate() cast this map's rays on per-source handles right now? (see SourceConcurrency) */
+  bool wantsRaycaster() const
+  {
+    if (!m_device_map || !m_config_set || m_fast_mode || m_source_concurrency == SourceConcurrency::Shared) return false;
+    return m_source_concurrency == SourceConcurrency::PerSource || m_input_sources.size() > 1;
+  }
+
+  /*! the source's raycast-only handle, created and (re)configured on demand; nullptr = use the map's handle.
+   *  Caller holds src.update_grid_mutex. */
+  vdbm_map* sourceRaycaster(const std::string& source_id, InputSource& src)
+  {
+    if (!wantsRaycaster()) return nullptr;
+    if (!src.raycaster)
+    {
+      vdbm_params p{};
+      p.resolution            = m_resolution;
+      p.device                = -1;
+      p.replicate_probe_quirk = 1;
+      p.map_capacity_leaves   = 1; // it never integrates
+      if (vdbm_create(&p, &src.raycaster) != VDBM_OK)
+      {
+        src.raycaster = nullptr;
+        return nullptr;
+      }
+      src.raycaster_range = -1.0;
+      vdbm_source_add(src.raycaster, source_id.c_str(), src.max_range_as_given);
+    }
+    if (src.raycaster_range != m_max_range)
+    {
+      // only the range matters to a raycast (R:1456-1469); the probabilities just have to be valid
+      if (vdbm_set_config(src.raycaster, m_max_range, 0.7, 0.4, 0.12, 0.97) != VDBM_OK) return nullptr;
+      src.raycaster_range = m_max_range;
+    }
+    return src.raycaster;
+  }
+
+  /*! moves what the source accumulated on its own handle into its update grid on the map's handle, device to device.
+   *  Caller holds m_device_mutex and either the exclusive map lock or src.update_grid_mutex. */
+  void collectRaycasterLocked(const std::string& source_id, InputSource& src)
+  {
+    if (!src.raycaster || !src.raycaster_holds_data) return;
+    src.raycaster_holds_data = false;
+    std::uint64_t count   = 0;
+    const void* d_records = nullptr;
+    if (reportOn(src.raycaster, vdbm_update_partition(src.raycaster, source_id.c_str(), 1, &count, &d_records)) != VDBM_OK) return;
+    if (count) report(vdbm_update_import_device(m_device_map, source_id.c_str(), d_records, count));
+  }
 
   static std::string timestampString()
   {
@@ -975,6 +1090,7 @@ protected:
   std::string m_map_directory_path;
   std::atomic<bool> m_config_set;
   MirrorMode m_mirror_mode = MirrorMode::Eager;
+  SourceConcurrency m_source_concurrency = SourceConcurrency::Auto;
   mutable bool m_mirror_stale = false;
   std::vector<typename BackendT::MapLeafT*> m_mirror_table; // device pool index -> leaf of m_vdb_grid
   const void* m_mirror_table_grid         = nullptr;

@@ -3,7 +3,12 @@
 // reference's tests use (OccupancyVDBMapping, PointCloudT, Config, getGrid()->getAccessor(), openvdb::Coord).
 // Table-driven instead of one TEST per scenario; plus API cases the reference does not test (updateMap with a
 // caller grid, raycastPointCloud into an accessor, sections, lazy mirror).
+#include <algorithm>
+#include <array>
 #include <cmath>
+#include <map>
+#include <thread>
+#include <vector>
 #include <vdb_mapping/OccupancyVDBMapping.hpp>
 
 #include "mini_gtest.h"
@@ -410,6 +415,134 @@ TEST(Shim, ExplicitRaysWallsAndTypedSections)
   EXPECT_EQ(wb.min().x(), -3.0);
   EXPECT_EQ(wb.max().z(), 1.0);
   map.morphologicalCloseMap<OccupancyVDBMapping::UpdateGridT>(ug, 1); // runs; result checked in test_compat_grid
+}
+
+// a quarter of a synthetic room scan per source (deterministic, no <random>: the two maps must see identical clouds)
+static OccupancyVDBMapping::PointCloudT::Ptr sectorCloud(int sector, int n, unsigned seed)
+{
+  OccupancyVDBMapping::PointCloudT::Ptr c(new OccupancyVDBMapping::PointCloudT);
+  unsigned state = seed * 2654435761u + 12345u;
+  auto rnd = [&] { state = state * 1664525u + 1013904223u; return float((state >> 8) & 0xFFFF) / 65536.0f; };
+  for (int i = 0; i < n; ++i)
+  {
+    const float az = (float(sector) + rnd()) * 1.5707963f, el = (rnd() - 0.5f) * 0.8f, r = 2.0f + 9.0f * rnd();
+    c->points.emplace_back(r * std::cos(el) * std::cos(az), r * std::cos(el) * std::sin(az), r * std::sin(el));
+  }
+  return c;
+}
+
+static bool gridsIdentical(OccupancyVDBMapping& a, OccupancyVDBMapping& b)
+{
+  // every leaf, every voxel value (free space is inactive but carries log-odds) and every active flag
+  using B = vdb_mapping::detail::Backend<float>;
+  struct Leaf { std::array<float, 512> v; std::array<std::uint64_t, 8> m; };
+  std::map<std::array<std::int32_t, 3>, Leaf> la;
+  B::forEachMapLeaf(*a.getGrid(), [&](const std::int32_t o[3], const float* v, const std::uint64_t* m) {
+    Leaf& l = la[{o[0], o[1], o[2]}];
+    std::copy(v, v + 512, l.v.begin());
+    std::copy(m, m + 8, l.m.begin());
+  });
+  bool same = true;
+  std::size_t n = 0;
+  B::forEachMapLeaf(*b.getGrid(), [&](const std::int32_t o[3], const float* v, const std::uint64_t* m) {
+    ++n;
+    auto it = la.find({o[0], o[1], o[2]});
+    if (it == la.end() || !std::equal(v, v + 512, it->second.v.begin()) || !std::equal(m, m + 8, it->second.m.begin())) same = false;
+  });
+  return same && n == la.size() && n > 50;
+}
+
+TEST(Shim, SourcesOnTheirOwnHandlesAccumulateConcurrentlyAndGiveTheSameMap)
+{
+  // SourceConcurrency: four sources fed from four threads. PerSource (what Auto picks for > 1 source): every source raycasts on
+  // its own device handle, integrateUpdate gathers the update leaves device-to-device. Shared: the threads take turns on the
+  // map's handle. Same clouds -> the maps must be identical voxel for voxel (updateMap runs per source in key order in both).
+  const Config conf = gtestConfig(8);
+  OccupancyVDBMapping per_source(0.1), shared(0.1);
+  shared.setSourceConcurrency(vdb_mapping::SourceConcurrency::Shared);
+  const char* ids[4] = {"lidar_a", "lidar_b", "lidar_c", "lidar_d"};
+  for (OccupancyVDBMapping* m : {&per_source, &shared})
+  {
+    m->setConfig(conf);
+    m->setMirrorMode(vdb_mapping::MirrorMode::Lazy);
+    for (const char* id : ids) m->addInputSource(id, id == ids[3] ? 5.0 : 0.0, 0); // one source with its own (shorter) range
+  }
+  for (int scan = 0; scan < 3; ++scan)
+  {
+    const Eigen::Matrix<double, 3, 1> origin(0.03 * scan, -0.02 * scan, 0.01);
+    std::vector<OccupancyVDBMapping::PointCloudT::Ptr> clouds;
+    for (int s = 0; s < 4; ++s) clouds.push_back(sectorCloud(s, 6000, 17u * unsigned(scan) + unsigned(s)));
+    for (OccupancyVDBMapping* m : {&per_source, &shared})
+    {
+      std::vector<std::thread> th;
+      for (int s = 0; s < 4; ++s) th.emplace_back([&, s] { m->accumulateUpdate(clouds[s], origin, ids[s]); });
+      for (auto& t : th) t.join();
+      if (scan == 1)
+      {
+        // deltas while the data still sits on the sources' own handles: raw grid and reduced update of one source
+        Eigen::Matrix<double, 3, 1> o(9, 9, 9);
+        auto reduced = m->createUpdate(ids[2], 2, &o);
+        auto raw     = m->createUpdate(ids[2], 0);
+        EXPECT_EQ(o.x(), origin.x());
+        EXPECT_TRUE(reduced->activeVoxelCount() > 3000 && reduced->activeVoxelCount() <= 6000);
+        EXPECT_TRUE(raw->activeVoxelCount() > reduced->activeVoxelCount());
+      }
+      m->integrateUpdate();
+    }
+    EXPECT_TRUE(gridsIdentical(per_source, shared));
+  }
+  // insertPointCloud (accumulate + integrate) of one source while the others are idle, then a reset
+  auto extra = sectorCloud(1, 3000, 99u);
+  for (OccupancyVDBMapping* m : {&per_source, &shared}) EXPECT_TRUE(m->insertPointCloud(extra, Eigen::Matrix<double, 3, 1>(0, 0, 0), ids[1]));
+  EXPECT_TRUE(gridsIdentical(per_source, shared));
+  vdbm_stats_t sp, ss;
+  EXPECT_TRUE(per_source.deviceStats(sp) && shared.deviceStats(ss));
+  EXPECT_EQ(sp.voxel_updates, ss.voxel_updates); // the map's handle integrated the same update voxels
+  EXPECT_TRUE(sp.rays < ss.rays);                // ... but did not cast the rays itself
+  per_source.resetMap();
+  EXPECT_EQ(per_source.getGrid()->activeVoxelCount(), std::uint64_t(0));
+  per_source.insertPointCloud(extra, Eigen::Matrix<double, 3, 1>(0, 0, 0), ids[1]);
+  shared.resetMap();
+  shared.insertPointCloud(extra, Eigen::Matrix<double, 3, 1>(0, 0, 0), ids[1]);
+  EXPECT_TRUE(gridsIdentical(per_source, shared));
+}
+
+TEST(Shim, EagerMirrorFollowsLargeScansThroughTheChunkedStream)
+{
+  // the default (Eager) mirror on scans that touch thousands of leaves, with a chunk size small enough for many chunks per
+  // insert: an accessor taken BEFORE the inserts reads the same values as a lazily mirrored twin afterwards.
+  const Config conf = gtestConfig(12);
+  OccupancyVDBMapping eager(0.05), lazy(0.05);
+  lazy.setMirrorMode(vdb_mapping::MirrorMode::Lazy);
+  eager.setMirrorChunkLeaves(512);
+  for (OccupancyVDBMapping* m : {&eager, &lazy})
+  {
+    m->setConfig(conf);
+    m->addInputSource("lidar", 0.0, 0);
+  }
+  OccupancyVDBMapping::GridT::Accessor early = eager.getGrid()->getAccessor();
+  for (int scan = 0; scan < 4; ++scan)
+  {
+    OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+    for (int s = 0; s < 4; ++s)
+      for (const auto& p : sectorCloud(s, 5000, 5u * unsigned(scan) + unsigned(s))->points) cloud->points.push_back(p);
+    const Eigen::Matrix<double, 3, 1> origin(0.1 * scan, 0.05 * scan, 0.0);
+    eager.insertPointCloud(cloud, origin, "lidar");
+    lazy.insertPointCloud(cloud, origin, "lidar");
+  }
+  EXPECT_TRUE(gridsIdentical(eager, lazy));
+  std::uint64_t n = 0, bad = 0;
+  vdb_mapping::detail::Backend<float>::forEachActiveVoxel(*lazy.getGrid(), [&](const openvdb::Coord& c, const float& v) {
+    ++n;
+    if (!early.isValueOn(c) || early.getValue(c) != v) ++bad;
+  });
+  EXPECT_TRUE(n > 1000);
+  EXPECT_EQ(bad, std::uint64_t(0));
+  eager.resetMap(); // new generation of the device pool, new host grid: the leaf table must not survive
+  eager.insertPointCloud(sectorCloud(0, 2000, 1u), Eigen::Matrix<double, 3, 1>(0, 0, 0), "lidar");
+  lazy.resetMap();
+  lazy.insertPointCloud(sectorCloud(0, 2000, 1u), Eigen::Matrix<double, 3, 1>(0, 0, 0), "lidar");
+  EXPECT_TRUE(gridsIdentical(eager, lazy));
 }
 
 int main() { return RUN_ALL_TESTS(); }

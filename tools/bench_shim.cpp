@@ -3,10 +3,13 @@
 // vdb_mapping sees after switching headers. Reads scans written by tools/bench_shim.py (one file: header, then per scan
 // origin[3] f64 + n u32 + n x pcl::PointXYZ), runs them in MirrorMode::Lazy (default: the pipelined insert) or Eager, and
 // prints one JSON line.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <vdb_mapping/OccupancyVDBMapping.hpp>
@@ -16,14 +19,20 @@ using vdb_mapping::OccupancyVDBMapping;
 
 int main(int argc, char** argv)
 {
-  if (argc < 2) { std::fprintf(stderr, "usage: bench_shim scans.bin [eager|lazy] [warmup]\n"); return 2; }
-  const bool eager = argc > 2 && std::string(argv[2]) == "eager";
+  if (argc < 2) { std::fprintf(stderr, "usage: bench_shim scans.bin [eager|lazy] [warmup] [max_scans]\n"); return 2; }
+  const std::string mode = argc > 2 ? argv[2] : "lazy";
+  const bool eager = mode == "eager";
+  // "sources4" / "sources4_shared": every scan split into 4 azimuth sectors fed as 4 input sources from 4 threads (the
+  // reference's one parallel axis, R:1373), then integrateUpdate; per-source raycast handles (SourceConcurrency::Auto) or
+  // all sources on the map's handle
+  const bool multi = mode.rfind("sources4", 0) == 0;
   const int warmup = argc > 3 ? std::atoi(argv[3]) : 5;
   FILE* f = std::fopen(argv[1], "rb");
   if (!f) { std::perror("open"); return 2; }
   double hdr[7]; // resolution, max_range, prob_hit, prob_miss, thres_min, thres_max, n_scans
   if (std::fread(hdr, sizeof(double), 7, f) != 7) return 2;
-  const int n_scans = int(hdr[6]);
+  int n_scans = int(hdr[6]);
+  if (argc > 4) n_scans = std::min(n_scans, std::atoi(argv[4]));
   std::vector<OccupancyVDBMapping::PointCloudT::Ptr> clouds;
   std::vector<Eigen::Matrix<double, 3, 1> > origins;
   for (int k = 0; k < n_scans; ++k)
@@ -47,13 +56,39 @@ int main(int argc, char** argv)
   map.setConfig(conf);
   map.addInputSource("lidar", conf.max_range, 0);
   map.setMirrorMode(eager ? vdb_mapping::MirrorMode::Eager : vdb_mapping::MirrorMode::Lazy);
+  if (const char* e = std::getenv("VDBM_MIRROR_CHUNK")) map.setMirrorChunkLeaves(std::strtoull(e, nullptr, 10)); // experiments
+  const char* ids[4] = {"lidar_0", "lidar_1", "lidar_2", "lidar_3"};
+  std::vector<std::vector<OccupancyVDBMapping::PointCloudT::Ptr> > parts;
+  if (multi)
+  {
+    for (const char* id : ids) map.addInputSource(id, conf.max_range, 0);
+    if (mode == "sources4_shared") map.setSourceConcurrency(vdb_mapping::SourceConcurrency::Shared);
+    for (auto& c : clouds)
+    {
+      parts.emplace_back();
+      const std::size_t n = c->points.size();
+      for (int s = 0; s < 4; ++s)
+      {
+        OccupancyVDBMapping::PointCloudT::Ptr p(new OccupancyVDBMapping::PointCloudT);
+        p->points.assign(c->points.begin() + n * s / 4, c->points.begin() + n * (s + 1) / 4);
+        parts.back().push_back(p);
+      }
+    }
+  }
 
   unsigned long long rays = 0;
   std::chrono::steady_clock::time_point t0;
   for (int k = 0; k < n_scans; ++k)
   {
     if (k == warmup) { map.getGrid(); t0 = std::chrono::steady_clock::now(); }
-    map.insertPointCloud(clouds[k], origins[k], "lidar");
+    if (multi)
+    {
+      std::thread th[4];
+      for (int s = 0; s < 4; ++s) th[s] = std::thread([&, s] { map.accumulateUpdate(parts[k][s], origins[k], ids[s]); });
+      for (auto& t : th) t.join();
+      map.integrateUpdate();
+    }
+    else map.insertPointCloud(clouds[k], origins[k], "lidar");
     if (k >= warmup) rays += clouds[k]->points.size();
   }
   vdbm_stats_t st;
@@ -63,9 +98,9 @@ int main(int argc, char** argv)
   const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   const auto grid = map.getGrid(); // lazy mode: the one full mirror copy, outside the timed region
   map.deviceStats(st);
-  std::printf("{\"api\": \"vdb_mapping::OccupancyVDBMapping::insertPointCloud (C++ shim, %s mirror)\", \"scans\": %d, \"rays_per_sec\": %.1f, "
+  std::printf("{\"api\": \"vdb_mapping::OccupancyVDBMapping::insertPointCloud (C++ shim, %s)\", \"scans\": %d, \"rays_per_sec\": %.1f, "
               "\"ms_per_scan\": %.4f, \"map_leaves\": %llu, \"host_grid_active_voxels\": %llu}\n",
-              eager ? "eager" : "lazy", n_scans - warmup, double(rays) / dt, 1e3 * dt / (n_scans - warmup), (unsigned long long)st.map_leaves,
+              mode.c_str(), n_scans - warmup, double(rays) / dt, 1e3 * dt / (n_scans - warmup), (unsigned long long)st.map_leaves,
               (unsigned long long)grid->activeVoxelCount());
   return 0;
 }
