@@ -108,10 +108,11 @@ public:
     std::chrono::milliseconds max_input_period;
     std::condition_variable data_available_cv;
     // SourceConcurrency::PerSource (all three guarded by update_grid_mutex or the exclusive map lock)
-    double max_range_as_given = 0.0;     // addInputSource argument (0 = follow the config range), what the device is told
+    bool shared_holds_data    = false;   // update leaves accumulated on the MAP's handle and not yet integrated
     vdbm_map* raycaster       = nullptr; // raycast-only device handle of this source
     double raycaster_range    = -1.0;    // config range it was last configured with
     bool raycaster_holds_data = false;   // update leaves accumulated there and not yet moved to the map's handle
+    bool last_cast_on_raycaster = false; // where the source's most recent accumulate ran (its ray end voxels stay there)
   };
 
   VDBMapping()                  = delete;
@@ -168,11 +169,14 @@ public:
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
       vdbm_reset(m_device_map);
       for (auto& kv : m_input_sources) // "new empty update grids" R:181-185, wherever they live
+      {
+        kv.second->shared_holds_data = false;
         if (kv.second->raycaster)
         {
           vdbm_reset(kv.second->raycaster);
           kv.second->raycaster_holds_data = false;
         }
+      }
     }
     m_vdb_grid->clear();
     m_vdb_grid = createVDBMap(m_resolution);
@@ -203,7 +207,8 @@ public:
     {
       // this source's own handle: no other thread touches it (update_grid_mutex), nothing is shared with the map's handle
       const int rc = vdbm_accumulate(raycaster, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o);
-      source->second->raycaster_holds_data = true;
+      source->second->raycaster_holds_data   = true;
+      source->second->last_cast_on_raycaster = true;
       reportOn(raycaster, rc);
       return;
     }
@@ -212,6 +217,8 @@ public:
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     // the ABI wants the pcl::PointXYZ records as they lie in the cloud (16-byte stride)
     const int rc = vdbm_accumulate(m_device_map, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o);
+    source->second->shared_holds_data      = true;
+    source->second->last_cast_on_raycaster = false;
     report(rc);
   }
 
@@ -239,8 +246,26 @@ public:
     m_map_mutex_requested = false;
     if (!m_device_map) return;
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
-    for (auto& kv : m_input_sources) collectRaycasterLocked(kv.first, *kv.second); // exclusive map lock: no accumulation is running
-    report(vdbm_integrate(m_device_map, 0));
+    bool on_raycasters = false; // exclusive map lock: no accumulation is running, the sources' flags are stable
+    for (auto& kv : m_input_sources) on_raycasters = on_raycasters || kv.second->raycaster_holds_data;
+    if (!on_raycasters) report(vdbm_integrate(m_device_map, 0));
+    else
+    {
+      // updateMap per source in key order (R:380), each grid read where it lies; a source with leaves on BOTH handles (the
+      // mode changed between two accumulates) is one update grid in the reference: gathered on the map's handle first
+      for (auto& kv : m_input_sources)
+      {
+        InputSource& src = *kv.second;
+        if (src.raycaster_holds_data && src.shared_holds_data) collectRaycasterLocked(kv.first, src);
+        if (src.raycaster_holds_data)
+        {
+          src.raycaster_holds_data = false;
+          report(vdbm_integrate_from(m_device_map, src.raycaster, kv.first.c_str(), 0));
+        }
+        else if (src.shared_holds_data) report(vdbm_integrate_from(m_device_map, m_device_map, kv.first.c_str(), 0));
+      }
+    }
+    for (auto& kv : m_input_sources) kv.second->shared_holds_data = false;
     if (m_mirror_mode == MirrorMode::Eager) syncMirrorLocked();
     else m_mirror_stale = true;
   }
@@ -264,6 +289,7 @@ public:
         std::lock_guard<std::mutex> device_lock(m_device_mutex);
         const double o[3] = {origin.x(), origin.y(), origin.z()};
         report(vdbm_insert_async(m_device_map, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o, 0));
+        source->second->last_cast_on_raycaster = false;
         m_mirror_stale = true;
         return true;
       }
@@ -503,11 +529,11 @@ public:
     vdbm_leafset* ls = nullptr;
     double o[3]      = {0, 0, 0};
     vdbm_map* from   = m_device_map;
-    if (source != m_input_sources.end() && source->second->raycaster_holds_data)
+    if (source != m_input_sources.end() && source->second->raycaster)
     {
       // the ray end voxels of the last accumulate (level 2) stay with the handle that cast them; a raw grid (level 0) may be
       // spread over both handles and is gathered in the map's first
-      if (level == 2) from = source->second->raycaster;
+      if (level == 2 && source->second->last_cast_on_raycaster) from = source->second->raycaster;
       else if (level == 0) collectRaycasterLocked(source_id, *source->second);
     }
     if (reportOn(from, vdbm_update_create(from, source_id.c_str(), level, &ls, o)) != VDBM_OK) return out;
@@ -771,23 +797,22 @@ public:
       // reference's fresh InputSource would.
       {
         std::unique_lock lock(existing->second->input_data_mutex);
-        existing->second->max_range          = range;
-        existing->second->max_range_as_given = max_range;
-        existing->second->max_input_period   = period;
+        existing->second->max_range        = range;
+        existing->second->max_input_period = period;
         existing->second->input_data.reset();
       }
       std::unique_lock grid_lock(existing->second->update_grid_mutex);
       if (existing->second->raycaster)
       {
-        vdbm_source_add(existing->second->raycaster, source_id.c_str(), max_range); // empty grid, new range
+        vdbm_source_add(existing->second->raycaster, source_id.c_str(), range); // empty grid, new (resolved, R:1356-1363) range
         existing->second->raycaster_holds_data = false;
       }
+      existing->second->shared_holds_data = false;
       return;
     }
     auto s              = std::make_shared<InputSource>();
     s->source_id        = source_id;
     s->max_range        = range;
-    s->max_range_as_given = max_range;
     s->max_input_period = period;
     m_input_sources[source_id] = s;
     m_worker_threads[source_id] = std::thread(&VDBMapping::accumulationThread, this, source_id);
@@ -864,12 +889,19 @@ protected:
         src.raycaster = nullptr;
         return nullptr;
       }
-      src.raycaster_range = -1.0;
-      vdbm_source_add(src.raycaster, source_id.c_str(), src.max_range_as_given);
+      // only the range matters to a raycast (R:1456-1469); the probabilities just have to be valid. The source gets the range
+      // addInputSource resolved for it (R:1356-1363: 0 = the config range at THAT time), like its twin on the map's handle.
+      if (vdbm_set_config(src.raycaster, m_max_range, 0.7, 0.4, 0.12, 0.97) != VDBM_OK ||
+          vdbm_source_add(src.raycaster, source_id.c_str(), src.max_range) != VDBM_OK)
+      {
+        vdbm_destroy(src.raycaster);
+        src.raycaster = nullptr;
+        return nullptr;
+      }
+      src.raycaster_range = m_max_range;
     }
     if (src.raycaster_range != m_max_range)
     {
-      // only the range matters to a raycast (R:1456-1469); the probabilities just have to be valid
       if (vdbm_set_config(src.raycaster, m_max_range, 0.7, 0.4, 0.12, 0.97) != VDBM_OK) return nullptr;
       src.raycaster_range = m_max_range;
     }
@@ -886,6 +918,7 @@ protected:
     const void* d_records = nullptr;
     if (reportOn(src.raycaster, vdbm_update_partition(src.raycaster, source_id.c_str(), 1, &count, &d_records)) != VDBM_OK) return;
     if (count) report(vdbm_update_import_device(m_device_map, source_id.c_str(), d_records, count));
+    if (count) src.shared_holds_data = true;
   }
 
   static std::string timestampString()

@@ -152,7 +152,7 @@ struct HostLeaf;
 template <>
 struct HostLeaf<float>
 {
-  float values[512];
+  alignas(64) float values[512]; // cache-line aligned like an OpenVDB leaf buffer: the mirror update streams into it
   std::uint64_t active[8];
   HostLeaf()
   {

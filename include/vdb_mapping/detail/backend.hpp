@@ -17,6 +17,10 @@
 #include <type_traits>
 #include <vector>
 
+#if defined(__SSE2__) && !defined(VDBM_NO_STREAMING_COPY)
+#include <emmintrin.h>
+#endif
+
 #include "vdb_mapping/detail/host_io.hpp"
 
 namespace vdb_mapping {
@@ -40,6 +44,37 @@ inline void parallelFor(std::uint64_t n, F&& f)
   for (auto& x : th) x.join();
 }
 
+// 2 KB leaf payload, pinned staging buffer -> leaf of the host grid. The destination is written once and not read again
+// soon, so on x86-64 the copy uses non-temporal stores when the leaf buffer is 16-byte aligned: no read-for-ownership of
+// the destination lines (a third of the memory traffic of the mirror update, which is bound by host memory bandwidth,
+// not by PCIe: profiles/README.md). Callers fence once per batch (streamingCopyFence).
+inline void copyLeafPayload(void* dst, const void* src, std::size_t bytes)
+{
+#if defined(__SSE2__) && !defined(VDBM_NO_STREAMING_COPY)
+  if (((reinterpret_cast<std::uintptr_t>(dst) | reinterpret_cast<std::uintptr_t>(src) | bytes) & 15u) == 0)
+  {
+    __m128i* d       = static_cast<__m128i*>(dst);
+    const __m128i* s = static_cast<const __m128i*>(src);
+    for (std::size_t i = 0; i < bytes / 16; i += 4)
+    {
+      const __m128i a = _mm_load_si128(s + i), b = _mm_load_si128(s + i + 1), c = _mm_load_si128(s + i + 2), e = _mm_load_si128(s + i + 3);
+      _mm_stream_si128(d + i, a);
+      _mm_stream_si128(d + i + 1, b);
+      _mm_stream_si128(d + i + 2, c);
+      _mm_stream_si128(d + i + 3, e);
+    }
+    return;
+  }
+#endif
+  std::memcpy(dst, src, bytes);
+}
+inline void streamingCopyFence()
+{
+#if defined(__SSE2__) && !defined(VDBM_NO_STREAMING_COPY)
+  _mm_sfence();
+#endif
+}
+
 // The same on a persistent pool: the mirror of the device map (VDBMapping::syncMirrorLocked) merges a chunk of leaves every
 // few hundred microseconds while the next chunk crosses PCIe; starting threads per chunk would cost more than the copies.
 // Static ranges, the caller works too; one job at a time (callers are serialised by the shim's device mutex anyway).
@@ -58,11 +93,13 @@ public:
     if (n < 1024 || T == 1)
     {
       for (std::uint64_t i = 0; i < n; ++i) f(i);
+      streamingCopyFence();
       return;
     }
     std::lock_guard<std::mutex> one_job(m_job_mutex);
     std::function<void(unsigned)> body = [&](unsigned t) {
       for (std::uint64_t i = n * t / T; i < n * (t + 1) / T; ++i) f(i);
+      streamingCopyFence(); // copyLeafPayload's non-temporal stores are visible before the job counts as done
     };
     {
       std::lock_guard<std::mutex> lk(m_mutex);
@@ -219,7 +256,7 @@ struct Backend
       dst[i] = slot;
     }
     WorkerPool::instance().run(n, [&](std::uint64_t i) {
-      std::memcpy(dst[i]->buffer().data(), values + 512 * i, 512 * sizeof(float));
+      copyLeafPayload(dst[i]->buffer().data(), values + 512 * i, 512 * sizeof(float));
       typename MapLeafT::NodeMaskType mask;
       for (int w = 0; w < 8; ++w) mask.template getWord<openvdb::Index64>(w) = active[8 * i + w];
       dst[i]->setValueMask(mask);
@@ -418,7 +455,7 @@ struct Backend
       dst[i] = slot;
     }
     WorkerPool::instance().run(n, [&](std::uint64_t i) {
-      std::memcpy(dst[i]->values, values + 512 * i, 512 * sizeof(float));
+      copyLeafPayload(dst[i]->values, values + 512 * i, 512 * sizeof(float));
       std::memcpy(dst[i]->active, active + 8 * i, 8 * sizeof(std::uint64_t));
     });
   }

@@ -119,6 +119,14 @@ int vdbm_raycast(vdbm_map* map, const char* source_id, const void* points, uint6
 /* integrateUpdate V:375-387: updateMap V:731-792 for every source in std::map key order, then fresh update
  * grids. The change grids are discarded like V:382 unless keep_change != 0 (then vdbm_change_export works). */
 int vdbm_integrate(vdbm_map* map, int keep_change);
+/* updateMap V:731-792 for ONE source whose update grid lives in another handle of the same device and resolution (holder
+ * may also be `map` itself), then a fresh update grid there (V:384). The reference's one parallel axis is a thread per input
+ * source, each raycasting into its own grid (V:316-346, 1383-1411); a handle is thread-compatible, so a host that wants the
+ * sources to raycast concurrently gives every source a raycast-only handle (own stream, staging and counters,
+ * map_capacity_leaves = 1) and integrates them into the map's handle in std::map key order with this call: the map's kernels
+ * read the holder's grid in place, nothing is copied. Neither handle may be used by another thread during the call. With
+ * keep_change the change records stay with the holder (vdbm_change_export(holder, source_id)). */
+int vdbm_integrate_from(vdbm_map* map, vdbm_map* holder, const char* source_id, int keep_change);
 /* insertPointCloud V:399-406 = accumulate + integrate. */
 int vdbm_insert(vdbm_map* map, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes,
                 const double origin[3]);

@@ -1,6 +1,9 @@
 // mini_gtest.h — the handful of gtest macros the reference's test style needs (gtest is not installed here).
 #pragma once
+#include <csignal>
 #include <cstdio>
+#include <execinfo.h>
+#include <unistd.h>
 #include <functional>
 #include <string>
 #include <vector>
@@ -9,8 +12,19 @@ struct Case { std::string name; std::function<void()> fn; };
 inline std::vector<Case>& cases() { static std::vector<Case> c; return c; }
 inline int& failures() { static int f = 0; return f; }
 struct Reg { Reg(const char* s, const char* n, std::function<void()> f) { cases().push_back({std::string(s) + "." + n, f}); } };
+inline void on_fatal_signal(int sig)
+{
+  const char msg[] = "\n*** fatal signal, backtrace (resolve with addr2line -e <binary>):\n";
+  if (write(2, msg, sizeof(msg) - 1) < 0) {}
+  void* frames[64];
+  backtrace_symbols_fd(frames, backtrace(frames, 64), 2);
+  _exit(128 + sig);
+}
 inline int run_all()
 {
+  std::setvbuf(stdout, nullptr, _IONBF, 0); // a crash must not swallow the lines before it
+  std::signal(SIGSEGV, on_fatal_signal);
+  std::signal(SIGABRT, on_fatal_signal);
   int bad = 0;
   for (auto& c : cases())
   {

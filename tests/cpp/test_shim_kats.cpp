@@ -480,12 +480,17 @@ TEST(Shim, SourcesOnTheirOwnHandlesAccumulateConcurrentlyAndGiveTheSameMap)
       if (scan == 1)
       {
         // deltas while the data still sits on the sources' own handles: raw grid and reduced update of one source
-        Eigen::Matrix<double, 3, 1> o(9, 9, 9);
-        auto reduced = m->createUpdate(ids[2], 2, &o);
-        auto raw     = m->createUpdate(ids[2], 0);
-        EXPECT_EQ(o.x(), origin.x());
-        EXPECT_TRUE(reduced->activeVoxelCount() > 3000 && reduced->activeVoxelCount() <= 6000);
-        EXPECT_TRUE(raw->activeVoxelCount() > reduced->activeVoxelCount());
+        auto raw = m->createUpdate(ids[2], 0);
+        EXPECT_TRUE(raw->activeVoxelCount() > 6000);
+        if (m == &per_source)
+        {
+          // (on a shared handle level 2 describes the LAST accumulate of the handle, whichever source's thread came last)
+          Eigen::Matrix<double, 3, 1> o(9, 9, 9);
+          auto reduced = m->createUpdate(ids[2], 2, &o);
+          EXPECT_EQ(o.x(), origin.x());
+          EXPECT_TRUE(reduced->activeVoxelCount() > 3000 && reduced->activeVoxelCount() <= 6000);
+          EXPECT_TRUE(raw->activeVoxelCount() > reduced->activeVoxelCount());
+        }
       }
       m->integrateUpdate();
     }
@@ -525,7 +530,10 @@ TEST(Shim, EagerMirrorFollowsLargeScansThroughTheChunkedStream)
   {
     OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
     for (int s = 0; s < 4; ++s)
-      for (const auto& p : sectorCloud(s, 5000, 5u * unsigned(scan) + unsigned(s))->points) cloud->points.push_back(p);
+    {
+      const auto part = sectorCloud(s, 5000, 5u * unsigned(scan) + unsigned(s));
+      cloud->points.insert(cloud->points.end(), part->points.begin(), part->points.end());
+    }
     const Eigen::Matrix<double, 3, 1> origin(0.1 * scan, 0.05 * scan, 0.0);
     eager.insertPointCloud(cloud, origin, "lidar");
     lazy.insertPointCloud(cloud, origin, "lidar");

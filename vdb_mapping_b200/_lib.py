@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
     sig("vdbm_get_logodds", C.c_int, vp, f32p)
     sig("vdbm_source_add", C.c_int, vp, cp, dbl)
     sig("vdbm_accumulate", C.c_int, vp, cp, vp, u64, u64, dblp)
+    sig("vdbm_integrate_from", C.c_int, vp, vp, cp, C.c_int)
     sig("vdbm_accumulate_device", C.c_int, vp, cp, vp, u64, u64, dblp)
     sig("vdbm_raycast", C.c_int, vp, cp, vp, u64, u64, dblp, dbl)
     sig("vdbm_integrate", C.c_int, vp, C.c_int)

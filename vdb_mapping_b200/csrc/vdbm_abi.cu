@@ -6,6 +6,7 @@
 #include "vdbm_device.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1369,6 +1370,38 @@ int vdbm_integrate(vdbm_map* m, int keep_change)
   return VDBM_OK;
 }
 
+int vdbm_integrate_from(vdbm_map* m, vdbm_map* holder, const char* source_id, int keep_change)
+{
+  if (!m || !holder) return VDBM_ERR_INVALID_ARG;
+  if (holder != m)
+  {
+    if (holder->device != m->device || holder->params.resolution != m->params.resolution)
+      return fail(m, VDBM_ERR_INVALID_ARG, "vdbm_integrate_from: the holder must live on the same device and have the same resolution");
+    VDBM_ENTER(holder); // a scan still queued there is finished first
+    // accumulate calls are synchronous, so this returns at once; it orders anything else the caller queued there before us
+    CU_TRY(holder, cudaStreamSynchronize(holder->stream));
+  }
+  VDBM_ENTER(m);
+  Source* s = findSource(holder, source_id);
+  if (!s) return fail(m, VDBM_ERR_UNKNOWN_SOURCE, std::string("Source not available: ") + (source_id ? source_id : ""));
+  m->stats.last_touched_leaves = 0;
+  const uint64_t upd_before    = m->stats.voxel_updates;
+  CU_TRY(m, cudaEventRecord(m->ev0, m->stream));
+  int rc = updateMapInternal(m, *s, keep_change != 0); // this map's stream, counters and leaf pool; the holder's grid
+  if (rc) return rc;
+  CU_TRY(m, cudaEventRecord(m->ev1, m->stream));
+  rc = syncCounters(m); // the grid is consumed and reset when this returns: the holder may accumulate again
+  if (rc) return rc;
+  if (keep_change) s->n_change = std::min(m->h_ctr->n_change, s->change_cap);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, m->ev0, m->ev1);
+  m->stats.last_integrate_ms  = ms;
+  m->stats.last_voxel_updates = m->stats.voxel_updates - upd_before;
+  s->prev_updates             = m->stats.last_voxel_updates;
+  if (m->h_ctr->flags & kFlagMapOverflow) return fail(m, VDBM_ERR_OUT_OF_MEMORY, "map hash / leaf pool overflow");
+  return VDBM_OK;
+}
+
 int vdbm_insert(vdbm_map* m, const char* source_id, const void* points, uint64_t n, uint64_t stride_bytes, const double origin[3])
 {
   // insertPointCloud V:399-406: accumulateUpdate (whatever it does) then integrateUpdate
@@ -1934,6 +1967,11 @@ int vdbm_map_mirror(vdbm_map* m, uint64_t chunk_leaves, vdbm_mirror_sink sink, v
   if (!m || !sink) return VDBM_ERR_INVALID_ARG;
   VDBM_ENTER(m);
   if (n_leaves_out) *n_leaves_out = 0;
+  static const bool profile = getenv("VDBM_MIRROR_PROFILE") != nullptr; // experiments: where a mirror call spends its time
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+  const clk::time_point t_begin = clk::now();
+  double ms_wait = 0, ms_sink = 0;
   int rc = syncCounters(m);
   if (rc) return rc;
   const uint32_t n_all = m->n_leaves;
@@ -1995,14 +2033,20 @@ int vdbm_map_mirror(vdbm_map* m, uint64_t chunk_leaves, vdbm_mirror_sink sink, v
     if (e == cudaSuccess) e = cudaEventRecord(mr.ev[b], m->stream);
     return e;
   };
+  const double ms_prepare = ms_since(t_begin);
   for (uint32_t k = 0; k < std::min<uint32_t>(n_chunks, vdbm_map::Mirror::kBufs); ++k) CU_TRY(m, enqueue(k));
   for (uint32_t k = 0; k < n_chunks; ++k)
   {
     const int b        = int(k % vdbm_map::Mirror::kBufs);
     const uint32_t off = k * C, cnt = std::min(C, n - off);
+    clk::time_point t0 = clk::now();
     CU_TRY(m, cudaEventSynchronize(mr.ev[b]));
+    ms_wait += ms_since(t0);
     uint8_t* h = mr.h_buf[b];
-    if (sink(user, cnt, indexOf(h), originsOf(h), valuesOf(h), activeOf(h)) != 0)
+    t0 = clk::now();
+    const int sink_rc = sink(user, cnt, indexOf(h), originsOf(h), valuesOf(h), activeOf(h));
+    ms_sink += ms_since(t0);
+    if (sink_rc != 0)
     {
       // the consumer gave up: what it has not seen stays dirty for the next call
       cudaStreamSynchronize(m->stream);
@@ -2014,6 +2058,9 @@ int vdbm_map_mirror(vdbm_map* m, uint64_t chunk_leaves, vdbm_mirror_sink sink, v
     if (k + vdbm_map::Mirror::kBufs < n_chunks) CU_TRY(m, enqueue(k + vdbm_map::Mirror::kBufs));
   }
   CU_TRY(m, cudaStreamSynchronize(m->stream));
+  if (profile)
+    std::fprintf(stderr, "vdbm_map_mirror: %u leaves (%.1f MB) in %u chunks: total %.2f ms = prepare %.2f + waiting for copies %.2f + sink %.2f\n", n,
+                 double(n) * kLeafBytes / 1e6, n_chunks, ms_since(t_begin), ms_prepare, ms_wait, ms_sink);
   return VDBM_OK;
 }
 

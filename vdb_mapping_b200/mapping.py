@@ -253,15 +253,22 @@ class OccupancyVDBMapping:
         """vdbm_map_mirror: streams the leaves modified since the previous mirror / dirty export to
         sink(leaf_index[n], origins[n,3], values[n,512], active[n,8]) chunk by chunk (the arrays are views that die with the
         call; a truthy return value aborts). Returns the number of leaves delivered."""
+        raised = []
+
         def _sink(_user, n, idx, origins, values, active):
             n = int(n)
-            r = sink(np.ctypeslib.as_array(idx, (n,)), np.ctypeslib.as_array(origins, (n, 3)),
-                     np.ctypeslib.as_array(values, (n, 512)), np.ctypeslib.as_array(active, (n, 8)))
+            try:
+                r = sink(np.ctypeslib.as_array(idx, (n,)), np.ctypeslib.as_array(origins, (n, 3)),
+                         np.ctypeslib.as_array(values, (n, 512)), np.ctypeslib.as_array(active, (n, 8)))
+            except BaseException as e:  # an exception cannot cross the C frames: abort the transfer, re-raise afterwards
+                raised.append(e)
+                return 1
             return 1 if r else 0
         cb = L.MIRROR_SINK(_sink)
         done = C.c_uint64(0)
         rc = self._L.vdbm_map_mirror(self._h, int(chunk_leaves), cb, None, C.byref(done))
-        self._mirror_delivered = int(done.value)
+        if raised:
+            raise raised[0]
         self._check(rc)
         return int(done.value)
 
