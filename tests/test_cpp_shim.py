@@ -64,3 +64,31 @@ def test_reference_scenarios_through_the_cpp_shim():
     p = subprocess.run([_build()], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert "0 failed" in p.stdout
+
+
+def test_openvdb_branch_of_the_shim_type_checks_against_the_api_stubs():
+    """CPU-only: the VDBM_HAVE_OPENVDB branch of detail/backend.hpp (what a consumer with OpenVDB / PCL / Eigen installed
+    compiles) against tests/cpp/stubs, headers with the public API shape of the three libraries: no errors, no warnings."""
+    p = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-DVDBM_HAVE_OPENVDB=1", "-I", os.path.join(ROOT, "tests", "cpp", "stubs"),
+                        "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"),
+                        os.path.join(ROOT, "tests", "cpp", "test_shim_kats.cpp")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "warning" not in p.stderr, p.stderr[-3000:]
+    backend = open(os.path.join(ROOT, "include", "vdb_mapping", "detail", "backend.hpp")).read()
+    real = backend.split("#ifdef VDBM_HAVE_OPENVDB")[1].split("#else")[0]
+    for api in ("tree().touchLeaf", "buffer().data()", "setValueMask", "getValueMask()", "cbeginLeaf()", "cbeginValueOn()", "io::File", "io::Stream",
+                "dilateActiveValues", "erodeActiveValues", "pcl::io::savePCDFile", "createLinearTransform"):
+        assert api in real, api
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe", ["test_shim_kats_vdbapi", "reference_mapping_tests_vdbapi"])
+def test_programs_run_through_the_openvdb_branch(exe):
+    """The shim's own scenarios and the reference's unmodified test file, compiled through the OpenVDB branch of the shim
+    (against tests/cpp/stubs) and run on the GPU."""
+    _build()
+    path = os.path.join(ROOT, "tests", "cpp", "build", exe)
+    if not os.path.exists(path):
+        pytest.skip(exe + " was not built (no /root/reference at build time)")
+    p = subprocess.run([path], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert "0 failed" in p.stdout, p.stdout[-2000:]

@@ -22,5 +22,5 @@ with open(path, "wb") as f:
         pts, origin = scans.make_scan(2, k)
         p16 = np.ones((pts.shape[0], 4), dtype=np.float32); p16[:, :3] = pts[:, :3]
         f.write(struct.pack("3d", *origin)); f.write(struct.pack("I", p16.shape[0])); f.write(p16.tobytes())
-for mode, n in (("lazy", n_scans), ("eager", min(n_scans, 12))):
-    print(subprocess.run([exe, path, mode, "5"], capture_output=True, text=True).stdout.strip())
+for mode, n in (("lazy", n_scans), ("eager", min(n_scans, 14)), ("sources4", n_scans), ("sources4_shared", n_scans)):
+    print(subprocess.run([exe, path, mode, "5", str(n)], capture_output=True, text=True).stdout.strip())
