@@ -80,6 +80,17 @@ def test_openvdb_branch_of_the_shim_type_checks_against_the_api_stubs():
         assert api in real, api
 
 
+def test_openvdb_branch_host_services_run_against_the_api_stubs(tmp_path):
+    """CPU-only: leaf transfer, iteration, section metadata, wire bytes, files, morphology and PCD io of the shim's OpenVDB
+    branch, executed against tests/cpp/stubs (tests/cpp/test_openvdb_branch_host.cpp)."""
+    exe = str(tmp_path / "test_openvdb_branch_host")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "tests", "cpp", "stubs"), "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ROOT, "tests", "cpp"), os.path.join(ROOT, "tests", "cpp", "test_openvdb_branch_host.cpp"), "-pthread", "-o", exe],
+                   check=True)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and "3 test(s), 0 failed" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("exe", ["test_shim_kats_vdbapi", "reference_mapping_tests_vdbapi"])
 def test_programs_run_through_the_openvdb_branch(exe):
