@@ -89,6 +89,51 @@ def test_accumulation_over_several_scans_and_sources():
         assert_leafsets_equal(g.exportMap(), o.exportMap(), "map")
 
 
+def test_sources_on_their_own_handles_integrate_in_place():
+    """vdbm_integrate_from: every source raycasts on a raycast-only handle of its own (one-leaf map), the map's handle runs
+    updateMap per source in key order on the holders' grids where they lie. Map, change grids and counters equal the oracle's
+    two-source run; the holders are left with fresh update grids."""
+    from vdb_mapping_b200 import scans
+    from vdb_mapping_b200.mapping import OccupancyVDBMapping
+    g, o = _pair(0.05, 3.0, CFG_GTEST, sources=("b_src", "a_src"))
+    holders = {}
+    for s in ("a_src", "b_src"):
+        h = OccupancyVDBMapping(0.05, map_capacity_leaves=1)
+        assert h.setConfig(3.0, 0.7, 0.4, 0.12, 0.97) == 0          # only the range matters to a raycast
+        h.addInputSource(s, 3.0, 0)
+        holders[s] = h
+    for rep in range(3):
+        for i, s in enumerate(("b_src", "a_src", "b_src")):
+            pts, origin = scans.small_scan(70 * rep + i, n=2500, scale=1.5)
+            holders[s].accumulateUpdate(pts, origin, s)
+            o.accumulateUpdate(pts, origin, s)
+        for s in ("a_src", "b_src"):
+            assert_leafsets_equal(holders[s].exportUpdateGrid(s), o.exportUpdateGrid(s), f"update {s}")
+        for s in ("a_src", "b_src"):                                # std::map key order, VDBMapping.hpp:380
+            g.integrateFrom(holders[s], s, keep_change=True)
+        o.integrateUpdate()
+        for s in ("a_src", "b_src"):
+            assert_leafsets_equal(holders[s].exportLastChange(s), o.exportLastChange(s), f"change {s}")   # stays with the holder
+            assert len(holders[s].exportUpdateGrid(s)) == 0
+        assert_leafsets_equal(g.exportMap(), o.exportMap(), f"map {rep}")
+    st, so = g.stats(), o.stats()
+    assert st["voxel_updates"] == so["voxel_updates"] and st["rays"] == 0
+    assert sum(h.stats()["visits"] for h in holders.values()) == so["visits"]
+    # the map's own grid of a source integrates through the same call (holder == map); unknown source / foreign resolution refused
+    pts, origin = scans.small_scan(999, n=1500, scale=1.5)
+    g.accumulateUpdate(pts, origin, "a_src"); o.accumulateUpdate(pts, origin, "a_src")
+    g.integrateFrom(g, "a_src"); o.integrateUpdate()
+    assert_leafsets_equal(g.exportMap(), o.exportMap(), "map after holder == map")
+    from vdb_mapping_b200.mapping import VdbmError
+    with pytest.raises(VdbmError):
+        g.integrateFrom(holders["a_src"], "nobody")
+    other = OccupancyVDBMapping(0.1, map_capacity_leaves=1)
+    with pytest.raises(VdbmError):
+        g.integrateFrom(other, "a_src")
+    for h in list(holders.values()) + [other]:
+        h.close()
+
+
 def test_clamping_and_state_flips_after_repeated_hits():
     """Same scan 12 times: values run into +-clamp, flags flip once; bit-exact all the way."""
     from vdb_mapping_b200 import scans

@@ -187,6 +187,11 @@ class OccupancyVDBMapping:
     def integrateUpdate(self, keep_change: bool = True):
         self._check(self._L.vdbm_integrate(self._h, int(keep_change)))
 
+    def integrateFrom(self, holder: "OccupancyVDBMapping", source_id: str, keep_change: bool = False):
+        """vdbm_integrate_from: updateMap of ONE source whose update grid lives in `holder` (another handle of the same device
+        and resolution, e.g. a raycast-only handle of that source), read in place; then a fresh update grid there."""
+        self._check(self._L.vdbm_integrate_from(self._h, holder._h, source_id.encode(), int(keep_change)))
+
     def insertPointCloud(self, points, origin, source_id: str) -> bool:
         p = _pts16(points)
         o = np.ascontiguousarray(origin, dtype=np.float64)
