@@ -1,4 +1,5 @@
-"""Small end-to-end run for compute-sanitizer: scan path (sync + queued), fast_mode, raytrace, sections, a 2-shard group on one GPU.
+"""Small end-to-end run for compute-sanitizer: scan path (sync + queued), fast_mode, raytrace, sections, the host
+mirror stream, a source on its own handle (vdbm_integrate_from), a 2-shard group on one GPU.
     compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
 import os, sys
 import numpy as np
@@ -29,6 +30,23 @@ m2 = OccupancyVDBMapping(0.1)
 m2.setConfig(4.0, 0.7, 0.4, 0.12, 0.97); m2.addInputSource("s", 4.0)
 m2.importMap(full)
 assert m2.mapChecksum() == m.mapChecksum()
+# host mirror stream (several chunks, an aborted transfer, the rest on the next call) and a source on its own raycast handle
+got = []
+m.mirrorMap(lambda idx, o, v, a: got.append(len(idx)) or 0, chunk_leaves=64)
+pts, origin = scans.small_scan(31, n=20000, scale=2.5)
+m.insertPointCloud(pts, origin, "s")
+try:
+    m.mirrorMap(lambda idx, o, v, a: 1, chunk_leaves=32)
+except Exception:
+    pass
+n_rest = m.mirrorMap(lambda idx, o, v, a: 0, chunk_leaves=50)
+h = OccupancyVDBMapping(0.1, map_capacity_leaves=1)
+h.setConfig(4.0, 0.7, 0.4, 0.12, 0.97); h.addInputSource("s", 4.0)
+pts, origin = scans.small_scan(32, n=20000, scale=2.5)
+h.accumulateUpdate(pts, origin, "s")
+m.integrateFrom(h, "s", keep_change=True)
+print("mirror chunks", len(got), "rest", n_rest, "change leaves on the holder", len(h.exportLastChange("s")))
+h.close()
 g = OccupancyVDBMappingGroup(0.1, [0, 0])
 g.setConfig(4.0, 0.7, 0.4, 0.12, 0.97); g.addInputSource("s", 4.0)
 for k in range(3):
