@@ -527,7 +527,7 @@ int raycastDevice(vdbm_map* m, Source& s, const uint8_t* d_points, uint64_t n, u
   if (const char* e = getenv("VDBM_SEG_LEN")) a.seg_len = uint32_t(atoi(e)); // experiment override
   else if (s.prev_visits)
   {
-    const uint64_t lanes    = uint64_t(m->dda_grid) * 256;
+    const uint64_t lanes    = uint64_t(m->dda_grid) * uint64_t(raycastDDABlock());
     const uint64_t per_lane = std::max<uint64_t>(1, s.prev_visits / lanes);
     if (uint64_t(s.prev_max_visits) > per_lane * 2) a.seg_len = uint32_t(std::min<uint64_t>(4096, std::max<uint64_t>(256, per_lane / 2)));
   }
@@ -1041,7 +1041,7 @@ bool asyncEligible(vdbm_map* m, Source& s, uint64_t n, const double origin[3])
   if (getenv("VDBM_SEG_LEN")) return false;
   if (s.prev_visits)
   {
-    const uint64_t lanes    = uint64_t(m->dda_grid) * 256;
+    const uint64_t lanes    = uint64_t(m->dda_grid) * uint64_t(raycastDDABlock());
     const uint64_t per_lane = std::max<uint64_t>(1, s.prev_visits / lanes);
     if (uint64_t(s.prev_max_visits) > per_lane * 2) return false; // long rays: the segment planner needs a read-back
   }

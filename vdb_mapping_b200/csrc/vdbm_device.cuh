@@ -275,6 +275,7 @@ void launchRaycastDDA(const RaycastArgs& a, UpdateGrid ug, uint64_t* near_act, C
                       bool test_before_set = false);
 size_t nearCopiesBytes();
 int raycastDDAGrid(int device);
+int raycastDDABlock(); // threads per DDA CTA
 // rebuild ug.entries / counters[1] from the occupied bricks (brick count read on the device).
 // cook = true after launchRaycastDDA: the DDA kernel marks Z-SLICE mask words (word z&7 = the 8x8 x-y tile); the compaction
 // turns every touched leaf into OpenVDB's x-slice layout in place, so every other kernel sees x-slice words only.

@@ -340,6 +340,9 @@ __global__ void __launch_bounds__(128) long_ray_segments_kernel(RaycastArgs a, u
 #ifndef VDBM_DDA_CTAS
 #define VDBM_DDA_CTAS 4 // resident CTAs per SM the DDA kernel is compiled for: 52 registers at 4 (measured on B200: 0.42 ms per cfg2 scan; 5 CTAs x 48 registers 0.47 ms, 6 x 40 with spills 0.52 ms)
 #endif
+#ifndef VDBM_DDA_BLOCK
+#define VDBM_DDA_BLOCK 256 // threads per DDA CTA (a multiple of 32)
+#endif
 #ifndef VDBM_KBATCH
 #define VDBM_KBATCH 8
 #endif
@@ -431,7 +434,7 @@ __device__ __forceinline__ double addSel(double n, double d, bool p)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, VDBM_DDA_CTAS) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, uint64_t* near_act, Counters* ctr)
+__global__ void __launch_bounds__(VDBM_DDA_BLOCK, VDBM_DDA_CTAS) raycast_dda_kernel(RaycastArgs a, UpdateGrid g, uint64_t* near_act, Counters* ctr)
 {
   __shared__ uint32_t s_near_slot[kNearBricks];
   __shared__ uint64_t s_bit[kBitTableSize];
@@ -2422,27 +2425,29 @@ int raycastDDAGrid(int device)
 {
   int sms = 148, per_sm = 4;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_dda_kernel<0>, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_dda_kernel<0>, VDBM_DDA_BLOCK, 0);
   if (per_sm < 1) per_sm = 1;
   if (const char* e = getenv("VDBM_DDA_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e))); // experiments
   return sms * per_sm; // persistent: exactly one resident wave
 }
+int raycastDDABlock() { return VDBM_DDA_BLOCK; }
 
 size_t nearCopiesBytes() { return size_t(kNearCopies) * kNearBricks * kBrickLeaves * 8 * sizeof(uint64_t); }
 
 void launchRaycastDDA(const RaycastArgs& a, UpdateGrid g, uint64_t* near_act, Counters* ctr, int grid, cudaStream_t s, bool test_before_set)
 {
   if (a.n == 0) return;
-  const uint64_t blocks = (((uint64_t(a.n_segs) + 31) / 32) + 7) / 8;
+  constexpr uint64_t kWarps = VDBM_DDA_BLOCK / 32;
+  const uint64_t blocks     = (((uint64_t(a.n_segs) + 31) / 32) + kWarps - 1) / kWarps;
   if (uint64_t(grid) > blocks) grid = int(blocks);
 #ifdef VDBM_EXPERIMENTS
   static const int mode = [] { const char* e = getenv("VDBM_DDA_MODE"); return e ? atoi(e) : 0; }();
-  if (mode == 1) VDBM_LAUNCH(raycast_dda_kernel<1>, grid, 256, s, a, g, near_act, ctr);
-  else if (mode == 2) VDBM_LAUNCH(raycast_dda_kernel<2>, grid, 256, s, a, g, near_act, ctr);
+  if (mode == 1) VDBM_LAUNCH(raycast_dda_kernel<1>, grid, VDBM_DDA_BLOCK, s, a, g, near_act, ctr);
+  else if (mode == 2) VDBM_LAUNCH(raycast_dda_kernel<2>, grid, VDBM_DDA_BLOCK, s, a, g, near_act, ctr);
   else
 #endif
-  if (test_before_set) VDBM_LAUNCH(raycast_dda_kernel<4>, grid, 256, s, a, g, near_act, ctr);
-  else VDBM_LAUNCH(raycast_dda_kernel<0>, grid, 256, s, a, g, near_act, ctr);
+  if (test_before_set) VDBM_LAUNCH(raycast_dda_kernel<4>, grid, VDBM_DDA_BLOCK, s, a, g, near_act, ctr);
+  else VDBM_LAUNCH(raycast_dda_kernel<0>, grid, VDBM_DDA_BLOCK, s, a, g, near_act, ctr);
   VDBM_LAUNCH(merge_near_kernel, (kNearBricks * kBrickLeaves * 8 * kMergeSplit) / 256, 256, s, g, near_act, nearBrick0(a.origin_idx[0]),
               nearBrick0(a.origin_idx[1]), nearBrick0(a.origin_idx[2]), ctr);
 }
