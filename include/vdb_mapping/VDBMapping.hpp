@@ -839,7 +839,23 @@ public:
   }
 
   /*! Counters of the device path (rays, visits, voxel updates, kernel times); not part of the reference API. */
-  bool deviceStats(vdbm_stats_t& out) const { return m_device_map && vdbm_stats(m_device_map, &out) == VDBM_OK; }
+  bool deviceStats(vdbm_stats_t& out) const
+  {
+    if (!m_device_map || vdbm_stats(m_device_map, &out) != VDBM_OK) return false;
+    // rays cast on the sources' own handles (SourceConcurrency) belong to this map's raycast counters
+    for (auto& kv : m_input_sources)
+    {
+      std::unique_lock<std::mutex> grid_lock(kv.second->update_grid_mutex);
+      vdbm_stats_t s;
+      if (!kv.second->raycaster || vdbm_stats(kv.second->raycaster, &s) != VDBM_OK) continue;
+      out.rays += s.rays;
+      out.nan_skipped += s.nan_skipped;
+      out.clipped += s.clipped;
+      out.visits += s.visits;
+      out.gpu_launches = std::max(out.gpu_launches, s.gpu_launches); // one process-wide launch counter
+    }
+    return true;
+  }
 
 protected:
   static constexpr const char* kScratchSource = "\x01vdbm_scratch";

@@ -512,7 +512,9 @@ TEST(Shim, SourcesOnTheirOwnHandlesAccumulateConcurrentlyAndGiveTheSameMap)
   vdbm_stats_t sp, ss;
   EXPECT_TRUE(per_source.deviceStats(sp) && shared.deviceStats(ss));
   EXPECT_EQ(sp.voxel_updates, ss.voxel_updates); // the map's handle integrated the same update voxels
-  EXPECT_TRUE(sp.rays < ss.rays);                // ... but did not cast the rays itself
+  EXPECT_EQ(sp.rays, ss.rays);                   // the raycast counters include the sources' own handles
+  EXPECT_EQ(sp.visits, ss.visits);
+  EXPECT_EQ(sp.clipped, ss.clipped);
   per_source.resetMap();
   EXPECT_EQ(per_source.getGrid()->activeVoxelCount(), std::uint64_t(0));
   per_source.insertPointCloud(extra, Eigen::Matrix<double, 3, 1>(0, 0, 0), ids[1]);
