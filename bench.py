@@ -638,7 +638,8 @@ def run_ours(args, rank, world, local_rank):
                 # to updateMap of scan k, so CUDA events around one kernel also see the other. A few more scans through the
                 # synchronous calls (same kernels, nothing overlapped) give clean launch durations.
                 p_acc, p_prep, p_int, p_leaves = [], [], [], []
-                for k in range(max(args.warmup, n_steps - 8), n_steps):
+                # (8 scans spread evenly over the timed range, so that their touched-leaf count is the sequence's, not its tail's)
+                for k in sorted(set(int(round(x)) for x in np.linspace(args.warmup, n_steps - 1, 8))):
                     eng.accumulate_raw(resident[k].data_ptr(), n_pts_k[k], clouds[k][1], on_device=True)
                     s = m.stats()
                     p_acc.append(s["last_accumulate_ms"]); p_prep.append(s["last_prep_ms"]); p_leaves.append(s["last_touched_leaves"])
