@@ -51,7 +51,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region, sampled in-process through NVML every 10 ms
+    """SM clock + throttle reasons DURING the timed region, sampled in-process through NVML every ~2 ms
     (spawning `nvidia-smi -lms` from every rank measurably perturbs multi-GPU runs)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -84,7 +84,7 @@ class ClockSampler:
                 self.rows.append((sm, rs, pw))
             except Exception:
                 pass
-            self.stop_flag.wait(0.01)
+            self.stop_flag.wait(0.002)
 
     def start(self):
         if self.h is None:
