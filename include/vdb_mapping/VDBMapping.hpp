@@ -1148,7 +1148,7 @@ protected:
   bool m_scratch_ready        = false;
   bool m_artificial_areas_present = false; // R:1529
   int m_compression_level         = 1;     // R:1524
-  mutable std::mutex m_device_mutex; // serialises calls into the (thread-compatible) C ABI handle
+  mutable std::mutex m_device_mutex; // serialises calls into the MAP's (thread-compatible) C ABI handle; sources may own handles of their own
   mutable std::shared_ptr<std::shared_mutex> m_map_mutex;
   mutable std::atomic<bool> m_map_mutex_requested{false};
   std::map<std::string, std::shared_ptr<InputSource> > m_input_sources;

@@ -176,9 +176,10 @@ private:
 
 #ifdef VDBM_HAVE_OPENVDB
 // ------------------------------------------------------------------------------------------------------
-// Real OpenVDB / PCL / Eigen. NOTE: this branch cannot be compiled in the build image (the libraries are
-// absent there); it is kept small and uses only long-stable OpenVDB API
-// (Tree::touchLeaf, LeafNode::buffer().data(), LeafNode::setValueMask / getValueMask, NodeMask::getWord).
+// Real OpenVDB / PCL / Eigen. NOTE: the libraries are absent from the build image, so this branch is
+// compiled and run there against headers with their public API shape (tests/cpp/stubs); it is kept small and uses only
+// long-stable OpenVDB API (Tree::touchLeaf, LeafNode::buffer().data(), LeafNode::setValueMask / getValueMask,
+// NodeMask::getWord).
 // ------------------------------------------------------------------------------------------------------
 #include <Eigen/Core>
 #include <Eigen/Geometry>
