@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -118,7 +119,8 @@ private:
   WorkerPool()
   {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned T  = std::min(16u, hw);
+    unsigned T        = std::min(16u, hw);
+    if (const char* e = std::getenv("VDBM_MIRROR_THREADS")) T = std::max(1, std::atoi(e)); // experiments
     for (unsigned t = 1; t < T; ++t) m_threads.emplace_back([this, t] { loop(t); });
   }
   ~WorkerPool()
