@@ -38,6 +38,11 @@ public:
     // range and the "configured" flag are accepted BEFORE the probability checks, O:61 then O:65-76), so host and device
     // never disagree on whether the map is configured.
     int device_rc = VDBM_OK;
+    if (m_device_group)
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex);
+      device_rc = vdbm_group_set_config(m_device_group, config.max_range, config.prob_hit, config.prob_miss, config.prob_thres_min, config.prob_thres_max);
+    }
     if (m_device_map)
     {
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
@@ -53,10 +58,11 @@ public:
       std::cerr << "Probability for a hit should be above 0.5 but is " << config.prob_hit << std::endl;
       return;
     }
-    if (config.max_range < 0.0 || !m_device_map || device_rc != VDBM_OK) return; // base already complained / no device
+    vdbm_map* any_handle = m_device_group ? vdbm_group_shard(m_device_group, 0) : m_device_map; // the shards share one configuration
+    if (config.max_range < 0.0 || !any_handle || device_rc != VDBM_OK) return; // base already complained / no device
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     float lo[6];
-    vdbm_get_logodds(m_device_map, lo);
+    vdbm_get_logodds(any_handle, lo);
     m_logodds_hit = lo[0]; m_logodds_miss = lo[1]; m_logodds_thres_min = lo[2]; m_logodds_thres_max = lo[3];
     m_max_logodds = lo[4]; m_min_logodds = lo[5];
     m_config_set  = true;

@@ -155,6 +155,7 @@ public:
     for (auto& kv : m_input_sources)
       if (kv.second->raycaster) vdbm_destroy(kv.second->raycaster);
     if (m_device_map) vdbm_destroy(m_device_map);
+    if (m_device_group) vdbm_group_destroy(m_device_group);
   }
 
   /*! R:163-169 */
@@ -164,6 +165,11 @@ public:
   void resetMap()
   {
     std::unique_lock map_lock(*m_map_mutex);
+    if (m_device_group)
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex);
+      reportGroup(vdbm_group_reset(m_device_group));
+    }
     if (m_device_map)
     {
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
@@ -188,6 +194,45 @@ public:
   /*! See SourceConcurrency. Not part of the reference API. */
   void setSourceConcurrency(SourceConcurrency mode) { m_source_concurrency = mode; }
 
+  /*! Not part of the reference API: shard the map over several GPUs of one NVLink box, driven from this one process
+   *  (vdbm_group_*): every device raycasts the rays of its azimuth sector and owns the map leaves of a sector,
+   *  update leaves travel between the devices over NVLink, the union of the shards is bit for bit the map one GPU would hold.
+   *  Call it right after construction (before setConfig / addInputSource). What a sharded map offers: setConfig,
+   *  addInputSource, insertPointCloud (accumulateUpdate integrates its cloud at once: the group works scan by scan),
+   *  getGrid, getMapSection*, resetMap, saveMap*, deviceStats. Everything that needs the whole map on one device
+   *  (raycastPointCloud / updateMap with caller grids, createUpdate / applyUpdate, applyMapSection*, point edits, artificial
+   *  areas, loadMap*, raytrace, fast_mode) reports that it is unavailable and does nothing.
+   *  A device may be listed more than once (several shards on one GPU: how the test tier runs it on a single GPU). */
+  bool setDevices(const std::vector<int>& devices)
+  {
+    std::unique_lock map_lock(*m_map_mutex);
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    if (m_config_set || !m_input_sources.empty() || m_device_group)
+    {
+      std::cerr << "vdb_mapping (B200): setDevices must be called once, before setConfig and addInputSource" << std::endl;
+      return false;
+    }
+    if (devices.empty()) return false;
+    vdbm_params p{};
+    p.resolution            = m_resolution;
+    p.device                = -1;
+    p.replicate_probe_quirk = 1;
+    std::vector<std::int32_t> ids(devices.begin(), devices.end());
+    vdbm_group* group = nullptr;
+    const int rc      = vdbm_group_create(&p, static_cast<std::int32_t>(ids.size()), ids.data(), 0, &group);
+    if (rc != VDBM_OK || !group)
+    {
+      std::cerr << "vdb_mapping (B200): could not create the device group (status " << rc << "); the map stays on one device" << std::endl;
+      return false;
+    }
+    if (m_device_map) vdbm_destroy(m_device_map);
+    m_device_map   = nullptr; // every single-handle member is a no-op from here on; the sharded ones use the group
+    m_device_group = group;
+    m_shard_tables.assign(ids.size(), {});
+    m_shard_generations.assign(ids.size(), ~std::uint64_t(0));
+    return true;
+  }
+
   /*! R:316-346. Unknown source: message + return; source range <= 0: nothing is raycast. */
   void accumulateUpdate(const typename PointCloudT::ConstPtr& cloud,
                         const Eigen::Matrix<double, 3, 1>& origin,
@@ -197,6 +242,12 @@ public:
     if (source == m_input_sources.end())
     {
       std::cout << "Tried to accumulate update for " << source_id << ". Source not available" << std::endl;
+      return;
+    }
+    if (m_device_group)
+    {
+      // the group works scan by scan (raycast, exchange and updateMap are one call): this cloud is integrated by itself
+      insertSharded(cloud, origin, source_id);
       return;
     }
     std::shared_lock map_lock(*m_map_mutex);
@@ -275,6 +326,16 @@ public:
                         const Eigen::Matrix<double, 3, 1>& origin,
                         const std::string source_id)
   {
+    if (m_device_group)
+    {
+      if (m_input_sources.find(source_id) == m_input_sources.end())
+      {
+        std::cout << "Tried to accumulate update for " << source_id << ". Source not available" << std::endl;
+        return true;
+      }
+      insertSharded(cloud, origin, source_id);
+      return true;
+    }
     if (m_mirror_mode == MirrorMode::Lazy && m_device_map && cloud)
     {
       // throughput mode: the scan is queued as one pipeline stage (vdbm_insert_async: upload overlapped with the previous
@@ -307,6 +368,7 @@ public:
                          const double raycast_range,
                          typename UpdateGridT::Accessor& update_grid_acc)
   {
+    if (shardedUnavailable("raycastPointCloud")) return false;
     if (!m_config_set)
     {
       std::cerr << "Map not properly configured. Did you call setConfig method?" << std::endl;
@@ -344,6 +406,7 @@ public:
   typename UpdateGridT::Ptr updateMap(const typename UpdateGridT::Ptr& temp_grid)
   {
     typename UpdateGridT::Ptr change = BackendT::createUpdateGrid(m_resolution);
+    if (shardedUnavailable("updateMap")) return change;
     if (!m_device_map || !temp_grid || temp_grid->empty()) return change;
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     ensureScratchSource();
@@ -403,14 +466,14 @@ public:
     const std::int32_t mn[3] = {bb.min().x(), bb.min().y(), bb.min().z()}, mx[3] = {bb.max().x(), bb.max().y(), bb.max().z()};
     std::shared_lock map_lock(*m_map_mutex);
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
-    vdbm_leafset* ls = nullptr;
-    if (m_device_map && vdbm_section(m_device_map, mn, mx, full_grid ? 1 : 0, 0, &ls) == VDBM_OK)
-    {
+    forEachMapHandle([&](vdbm_map* handle, std::size_t) { // the shards of a sharded map hold disjoint leaf sets
+      vdbm_leafset* ls = nullptr;
+      if (vdbm_section(handle, mn, mx, full_grid ? 1 : 0, 0, &ls) != VDBM_OK) return;
       const std::uint64_t n = vdbm_leafset_size(ls);
       for (std::uint64_t i = 0; i < n; ++i)
         BackendT::putUpdateLeaf(*out, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_active(ls) + 8 * i, vdbm_leafset_valmask(ls) + 8 * i);
       vdbm_leafset_free(ls);
-    }
+    });
     BackendT::setSectionMeta(*out, mn, mx); // R:955-958
     return out;
   }
@@ -426,14 +489,14 @@ public:
     const std::int32_t mn[3] = {bb.min().x(), bb.min().y(), bb.min().z()}, mx[3] = {bb.max().x(), bb.max().y(), bb.max().z()};
     std::shared_lock map_lock(*m_map_mutex);
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
-    vdbm_leafset* ls = nullptr;
-    if (m_device_map && vdbm_section(m_device_map, mn, mx, full_grid ? 1 : 0, 1, &ls) == VDBM_OK)
-    {
+    forEachMapHandle([&](vdbm_map* handle, std::size_t) {
+      vdbm_leafset* ls = nullptr;
+      if (vdbm_section(handle, mn, mx, full_grid ? 1 : 0, 1, &ls) != VDBM_OK) return;
       const std::uint64_t n = vdbm_leafset_size(ls);
       for (std::uint64_t i = 0; i < n; ++i)
         BackendT::putMapLeaf(*out, vdbm_leafset_origins(ls) + 3 * i, vdbm_leafset_values(ls) + 512 * i, vdbm_leafset_active(ls) + 8 * i);
       vdbm_leafset_free(ls);
-    }
+    });
     BackendT::setSectionMeta(*out, mn, mx);
     return out;
   }
@@ -442,6 +505,7 @@ public:
    *  part of this build: smooth_map = true is reported and ignored. */
   void applyMapSectionGrid(const typename GridT::Ptr section, bool smooth_map = false, int smoothing_iterations = 2)
   {
+    if (shardedUnavailable("applyMapSectionGrid")) return;
     (void)smoothing_iterations;
     if (smooth_map) std::cerr << "vdb_mapping (B200): morphological smoothing is not supported; section applied unsmoothed" << std::endl;
     if (!m_device_map || !section) return;
@@ -463,6 +527,7 @@ public:
   /*! R:1058-1085 (same remark on smoothing). The box comes from the section's bb_min / bb_max metadata. */
   void applyMapSectionUpdateGrid(const typename UpdateGridT::Ptr section, bool smooth_map = false, int smoothing_iterations = 2)
   {
+    if (shardedUnavailable("applyMapSectionUpdateGrid")) return;
     (void)smoothing_iterations;
     if (smooth_map) std::cerr << "vdb_mapping (B200): morphological smoothing is not supported; section applied unsmoothed" << std::endl;
     if (!m_device_map || !section) return;
@@ -489,6 +554,7 @@ public:
   /*! R:1152-1166 */
   void restoreMapIntegrity()
   {
+    if (shardedUnavailable("restoreMapIntegrity")) return;
     if (!m_device_map) return;
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     report(vdbm_map_integrity_restore(m_device_map));
@@ -503,6 +569,7 @@ public:
   {
     if (!m_device_map) return;
     std::vector<std::uint32_t> counts;
+    if (shardedUnavailable("addArtificialAreas")) return;
     std::vector<double> xyz;
     for (const auto& area : artificial_areas)
     {
@@ -521,6 +588,7 @@ public:
   typename UpdateGridT::Ptr createUpdate(const std::string& source_id, int level, Eigen::Matrix<double, 3, 1>* origin = nullptr)
   {
     typename UpdateGridT::Ptr out = BackendT::createUpdateGrid(m_resolution);
+    if (shardedUnavailable("createUpdate")) return out;
     if (!m_device_map) return out;
     auto source = m_input_sources.find(source_id);
     std::unique_lock<std::mutex> update_grid_lock;
@@ -550,6 +618,7 @@ public:
                                         const Eigen::Matrix<double, 3, 1>& origin = Eigen::Matrix<double, 3, 1>(0, 0, 0))
   {
     typename UpdateGridT::Ptr change = BackendT::createUpdateGrid(m_resolution);
+    if (shardedUnavailable("applyUpdate")) return change;
     if (!m_device_map || !update) return change;
     std::vector<std::int32_t> origins;
     std::vector<std::uint64_t> active, value;
@@ -617,6 +686,7 @@ public:
   /*! R:263-284: m_vdb_grid is replaced by the (last) grid of the file; here the device map is replaced with it too */
   bool loadMap(const std::string& file_path)
   {
+    if (shardedUnavailable("loadMap")) return false;
     typename GridT::Ptr loaded = BackendT::readGridFile(file_path);
     if (!loaded) return false;
     std::unique_lock map_lock(*m_map_mutex);
@@ -629,6 +699,7 @@ public:
   /*! R:295-307 */
   bool loadMapFromPCD(const std::string& file_path, const bool set_background, const bool clear_map)
   {
+    if (shardedUnavailable("loadMapFromPCD")) return false;
     typename PointCloudT::Ptr cloud(new PointCloudT);
     if (!BackendT::loadPCD(file_path, *cloud))
     {
@@ -647,6 +718,7 @@ public:
   void castRayIntoGrid(const openvdb::Coord& ray_origin_index, const openvdb::Coord& ray_end_index,
                        typename UpdateGridT::Accessor& update_grid_acc) const
   {
+    if (shardedUnavailable("castRayIntoGrid")) return;
     if (!m_device_map) return;
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     const_cast<VDBMapping*>(this)->ensureScratchSource();
@@ -678,6 +750,7 @@ public:
     const std::size_t n = ray_origins_world.size();
     successes.assign(n, false);
     end_points.resize(n);
+    if (shardedUnavailable("raytrace")) return;
     if (!m_device_map || n == 0) return;
     std::vector<double> o(3 * n), d(3 * n), e(3 * n);
     std::vector<std::int32_t> ok(n);
@@ -735,6 +808,7 @@ public:
   /*! R:1198-1207 */
   void addArtificialPolygon(const std::vector<Eigen::Matrix<double, 4, 1> >& polygon, const double negative_height, const double positive_height)
   {
+    if (shardedUnavailable("addArtificialPolygon")) return;
     if (!m_device_map || polygon.empty()) return;
     const std::uint32_t count = static_cast<std::uint32_t>(polygon.size());
     std::vector<double> xyz;
@@ -748,6 +822,7 @@ public:
   void addArtificialWall(const Eigen::Matrix<double, 4, 1>& start, const Eigen::Matrix<double, 4, 1>& end, const double negative_height,
                          const double positive_height)
   {
+    if (shardedUnavailable("addArtificialWall")) return;
     if (!m_device_map) return;
     const std::uint32_t count = 2;
     const double xyz[6]       = {start[0], start[1], start[2], end[0], end[1], end[2]};
@@ -784,6 +859,11 @@ public:
   {
     const double range = (max_range == 0) ? m_max_range : max_range;
     const auto period  = (max_rate <= 0) ? std::chrono::milliseconds(0) : std::chrono::milliseconds((int)(1000.0 / max_rate));
+    if (m_device_group)
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex);
+      reportGroup(vdbm_group_source_add(m_device_group, source_id.c_str(), max_range));
+    }
     if (m_device_map)
     {
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
@@ -831,6 +911,12 @@ public:
     m_fast_mode           = config.fast_mode;
     m_accumulation_period = (int)(config.accumulation_period * 1000);
     m_config_set          = true;
+    if (m_device_group && m_fast_mode)
+    {
+      std::cerr << "vdb_mapping (B200): fast_mode is not available while the map is sharded over several devices; normal raycasting is used"
+                << std::endl;
+      m_fast_mode = false;
+    }
     if (m_device_map)
     {
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
@@ -841,6 +927,7 @@ public:
   /*! Counters of the device path (rays, visits, voxel updates, kernel times); not part of the reference API. */
   bool deviceStats(vdbm_stats_t& out) const
   {
+    if (m_device_group) return vdbm_group_stats(m_device_group, &out) == VDBM_OK; // summed over the shards
     if (!m_device_map || vdbm_stats(m_device_map, &out) != VDBM_OK) return false;
     // rays cast on the sources' own handles (SourceConcurrency) belong to this map's raycast counters
     for (auto& kv : m_input_sources)
@@ -879,6 +966,43 @@ protected:
   {
     if (rc != VDBM_OK && rc != VDBM_ERR_UNKNOWN_SOURCE && handle) std::cerr << "vdb_mapping (B200): " << vdbm_last_error(handle) << std::endl;
     return rc;
+  }
+
+  int reportGroup(int rc) const
+  {
+    if (rc != VDBM_OK && rc != VDBM_ERR_UNKNOWN_SOURCE && m_device_group)
+      std::cerr << "vdb_mapping (B200): " << vdbm_group_last_error(m_device_group) << std::endl;
+    return rc;
+  }
+
+  /*! members that need the whole map on one device say so when the map is sharded (setDevices) and do nothing */
+  bool shardedUnavailable(const char* member) const
+  {
+    if (!m_device_group) return false;
+    std::cerr << "vdb_mapping (B200): " << member << " is not available while the map is sharded over several devices" << std::endl;
+    return true;
+  }
+
+  /*! f(handle, shard index) for the map's handle, or for every shard of a sharded map */
+  template <typename F>
+  void forEachMapHandle(F&& f) const
+  {
+    if (m_device_group)
+      for (std::int32_t i = 0; i < vdbm_group_size(m_device_group); ++i) f(vdbm_group_shard(m_device_group, i), std::size_t(i));
+    else if (m_device_map) f(m_device_map, std::size_t(0));
+  }
+
+  /*! insertPointCloud R:399-406 on a sharded map: raycast on every device, exchange over NVLink, updateMap on every shard */
+  void insertSharded(const typename PointCloudT::ConstPtr& cloud, const Eigen::Matrix<double, 3, 1>& origin, const std::string& source_id)
+  {
+    if (!cloud) return;
+    m_map_mutex_requested = true;
+    std::unique_lock map_lock(*m_map_mutex);
+    m_map_mutex_requested = false;
+    std::lock_guard<std::mutex> device_lock(m_device_mutex);
+    const double o[3] = {origin.x(), origin.y(), origin.z()};
+    reportGroup(vdbm_group_insert(m_device_group, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o));
+    afterMapWriteLocked();
   }
 
   /*! does accumulateUpdate() cast this map's rays on per-source handles right now? (see SourceConcurrency) */
@@ -1010,6 +1134,7 @@ protected:
 
   bool setPoints(const typename PointCloudT::ConstPtr& cloud, int occupied)
   {
+    if (shardedUnavailable("addPointsToGrid / removePointsFromGrid")) return true;
     if (!m_device_map || !cloud) return true; // the reference returns true unconditionally (R:428,446)
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     report(vdbm_points_set(m_device_map, cloud->points.data(), cloud->points.size(), sizeof(PointT), occupied));
@@ -1049,18 +1174,25 @@ protected:
   void syncMirrorLocked()
   {
     m_mirror_stale = false;
-    if (!m_device_map) return;
-    // the table "device pool index -> host leaf" is only good for one grid object, one generation of the device pool and
-    // as long as no leaf was removed from the host grid
-    const std::uint64_t generation = vdbm_map_generation(m_device_map), epoch = BackendT::gridEpoch(*m_vdb_grid);
-    if (m_mirror_table_grid != m_vdb_grid.get() || m_mirror_table_generation != generation || m_mirror_table_epoch != epoch)
+    if (!m_device_map && !m_device_group) return;
+    if (m_shard_tables.empty())
     {
-      m_mirror_table.clear();
-      m_mirror_table_grid       = m_vdb_grid.get();
-      m_mirror_table_generation = generation;
-      m_mirror_table_epoch      = epoch;
+      m_shard_tables.assign(1, {});
+      m_shard_generations.assign(1, ~std::uint64_t(0));
     }
-    report(vdbm_map_mirror(m_device_map, m_mirror_chunk_leaves, &VDBMapping::mirrorSink, this, nullptr));
+    // the tables "device pool index -> host leaf" (one per shard: every shard has its own pool) are only good for one grid
+    // object, one generation of that pool and as long as no leaf was removed from the host grid
+    const std::uint64_t epoch = BackendT::gridEpoch(*m_vdb_grid);
+    const bool grid_changed   = m_mirror_table_grid != m_vdb_grid.get() || m_mirror_table_epoch != epoch;
+    m_mirror_table_grid       = m_vdb_grid.get();
+    m_mirror_table_epoch      = epoch;
+    forEachMapHandle([&](vdbm_map* handle, std::size_t shard) {
+      const std::uint64_t generation = vdbm_map_generation(handle);
+      if (grid_changed || m_shard_generations[shard] != generation) m_shard_tables[shard].clear();
+      m_shard_generations[shard] = generation;
+      m_mirror_sink_shard        = shard;
+      reportOn(handle, vdbm_map_mirror(handle, m_mirror_chunk_leaves, &VDBMapping::mirrorSink, this, nullptr));
+    });
   }
 
   /*! vdbm_mirror_sink: one chunk of modified leaves lands in the host grid while the next chunk is still on its way */
@@ -1068,7 +1200,7 @@ protected:
                         const std::uint64_t* active)
   {
     VDBMapping* self = static_cast<VDBMapping*>(user);
-    BackendT::putMapLeavesIndexed(*self->m_vdb_grid, self->m_mirror_table, n, leaf_index, origins, values, active);
+    BackendT::putMapLeavesIndexed(*self->m_vdb_grid, self->m_shard_tables[self->m_mirror_sink_shard], n, leaf_index, origins, values, active);
     return 0;
   }
 
@@ -1078,7 +1210,7 @@ public:
   void invalidateMirrorTable()
   {
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
-    m_mirror_table.clear();
+    for (auto& table : m_shard_tables) table.clear();
   }
   /*! Not part of the reference API: leaves per chunk of the mirror transfer (0 = library default). */
   void setMirrorChunkLeaves(std::uint64_t n) { m_mirror_chunk_leaves = n; }
@@ -1131,6 +1263,7 @@ protected:
   }
 
   vdbm_map* m_device_map = nullptr;
+  vdbm_group* m_device_group = nullptr; // setDevices(): the map is sharded over several GPUs (then m_device_map is null)
   typename GridT::Ptr m_vdb_grid;
   double m_max_range = 0.0;
   double m_resolution;
@@ -1141,10 +1274,12 @@ protected:
   MirrorMode m_mirror_mode = MirrorMode::Eager;
   SourceConcurrency m_source_concurrency = SourceConcurrency::Auto;
   mutable bool m_mirror_stale = false;
-  std::vector<typename BackendT::MapLeafT*> m_mirror_table; // device pool index -> leaf of m_vdb_grid
-  const void* m_mirror_table_grid         = nullptr;
-  std::uint64_t m_mirror_table_generation = 0, m_mirror_table_epoch = 0;
-  std::uint64_t m_mirror_chunk_leaves     = 0;
+  std::vector<std::vector<typename BackendT::MapLeafT*> > m_shard_tables; // per map handle: device pool index -> leaf of m_vdb_grid
+  std::vector<std::uint64_t> m_shard_generations;
+  std::size_t m_mirror_sink_shard     = 0;
+  const void* m_mirror_table_grid     = nullptr;
+  std::uint64_t m_mirror_table_epoch  = 0;
+  std::uint64_t m_mirror_chunk_leaves = 0;
   bool m_scratch_ready        = false;
   bool m_artificial_areas_present = false; // R:1529
   int m_compression_level         = 1;     // R:1524

@@ -564,4 +564,82 @@ TEST(Shim, EagerMirrorFollowsLargeScansThroughTheChunkedStream)
   EXPECT_TRUE(gridsIdentical(eager, lazy));
 }
 
+TEST(Shim, MapShardedOverSeveralDevicesEqualsTheSingleDeviceMap)
+{
+  // setDevices(): one process, the map sharded by azimuth sector over several device handles (vdbm_group_*). The shards may
+  // share a GPU, which is how this runs on a one-GPU box; tests/test_group.py and the 2 / 8-GPU logs under profiles/ cover
+  // real device sets. Host grid, sections and counters must equal the single-device map's.
+  const Config conf = gtestConfig(12);
+  OccupancyVDBMapping sharded(0.05), single(0.05);
+  EXPECT_TRUE(sharded.setDevices({0, 0, 0}));
+  EXPECT_FALSE(sharded.setDevices({0}));                       // once only
+  for (OccupancyVDBMapping* m : {&sharded, &single})
+  {
+    m->setConfig(conf);
+    m->addInputSource("lidar", 0.0, 0);
+  }
+  OccupancyVDBMapping late(0.05);
+  late.setConfig(conf);
+  EXPECT_FALSE(late.setDevices({0, 0}));                       // after setConfig: refused, the map stays on one device
+  OccupancyVDBMapping::GridT::Accessor early = sharded.getGrid()->getAccessor(); // Eager mirror fed by all shards
+  for (int scan = 0; scan < 4; ++scan)
+  {
+    OccupancyVDBMapping::PointCloudT::Ptr cloud(new OccupancyVDBMapping::PointCloudT);
+    for (int s = 0; s < 4; ++s)
+    {
+      const auto part = sectorCloud(s, 5000, 31u * unsigned(scan) + unsigned(s));
+      cloud->points.insert(cloud->points.end(), part->points.begin(), part->points.end());
+    }
+    const Eigen::Matrix<double, 3, 1> origin(0.07 * scan, -0.04 * scan, 0.02);
+    EXPECT_TRUE(sharded.insertPointCloud(cloud, origin, "lidar"));
+    EXPECT_TRUE(single.insertPointCloud(cloud, origin, "lidar"));
+    EXPECT_TRUE(gridsIdentical(sharded, single));
+  }
+  std::uint64_t n = 0, bad = 0;
+  vdb_mapping::detail::Backend<float>::forEachActiveVoxel(*single.getGrid(), [&](const openvdb::Coord& c, const float& v) {
+    ++n;
+    if (!early.isValueOn(c) || early.getValue(c) != v) ++bad;
+  });
+  EXPECT_TRUE(n > 1000);
+  EXPECT_EQ(bad, std::uint64_t(0));
+  // sections are gathered from all shards
+  const Eigen::Matrix<double, 3, 1> lo(-3.0, -2.0, -1.0), hi(2.5, 3.0, 1.5);
+  const auto tf = Eigen::Matrix<double, 4, 4>::Identity();
+  for (bool full : {false, true})
+  {
+    auto a = sharded.getMapSectionGrid(lo, hi, tf, full);
+    auto b = single.getMapSectionGrid(lo, hi, tf, full);
+    EXPECT_EQ(a->activeVoxelCount(), b->activeVoxelCount());
+    EXPECT_EQ(leafCountOf(*a), leafCountOf(*b));
+    auto ua = sharded.getMapSectionUpdateGrid(lo, hi, tf, full);
+    auto ub = single.getMapSectionUpdateGrid(lo, hi, tf, full);
+    EXPECT_EQ(ua->activeVoxelCount(), ub->activeVoxelCount());
+    EXPECT_TRUE(b->activeVoxelCount() > 0);
+  }
+  vdbm_stats_t a, b;
+  EXPECT_TRUE(sharded.deviceStats(a) && single.deviceStats(b));
+  EXPECT_EQ(a.rays, b.rays);
+  EXPECT_EQ(a.voxel_updates, b.voxel_updates);
+  EXPECT_EQ(a.map_leaves, b.map_leaves);
+  // what needs the whole map on one device says so and leaves the map alone
+  bool ok = true;
+  openvdb::Vec3d end;
+  sharded.raytrace(openvdb::Vec3d(0, 0, 0), openvdb::Vec3d(1, 0, 0), 5.0, ok, end);
+  EXPECT_FALSE(ok);
+  EXPECT_EQ(sharded.createUpdate("lidar", 0)->activeVoxelCount(), std::uint64_t(0));
+  EXPECT_TRUE(gridsIdentical(sharded, single));
+  // accumulateUpdate integrates its cloud at once on a sharded map; reset gives an empty map on every shard
+  const auto extra = sectorCloud(2, 3000, 77u);
+  sharded.accumulateUpdate(extra, Eigen::Matrix<double, 3, 1>(0, 0, 0), "lidar");
+  sharded.integrateUpdate();
+  single.insertPointCloud(extra, Eigen::Matrix<double, 3, 1>(0, 0, 0), "lidar");
+  EXPECT_TRUE(gridsIdentical(sharded, single));
+  sharded.resetMap();
+  EXPECT_EQ(sharded.getGrid()->activeVoxelCount(), std::uint64_t(0));
+  single.resetMap();
+  sharded.insertPointCloud(extra, Eigen::Matrix<double, 3, 1>(0.1, 0, 0), "lidar");
+  single.insertPointCloud(extra, Eigen::Matrix<double, 3, 1>(0.1, 0, 0), "lidar");
+  EXPECT_TRUE(gridsIdentical(sharded, single));
+}
+
 int main() { return RUN_ALL_TESTS(); }

@@ -26,6 +26,8 @@ int main(int argc, char** argv)
   // reference's one parallel axis, R:1373), then integrateUpdate; per-source raycast handles (SourceConcurrency::Auto) or
   // all sources on the map's handle
   const bool multi = mode.rfind("sources4", 0) == 0;
+  // "groupN": the map sharded over devices 0 .. N-1 (setDevices; one process, no Python), lazy mirror
+  const int group_n = mode.rfind("group", 0) == 0 ? std::atoi(mode.c_str() + 5) : 0;
   const int warmup = argc > 3 ? std::atoi(argv[3]) : 5;
   FILE* f = std::fopen(argv[1], "rb");
   if (!f) { std::perror("open"); return 2; }
@@ -50,6 +52,12 @@ int main(int argc, char** argv)
   std::fclose(f);
 
   OccupancyVDBMapping map(hdr[0]);
+  if (group_n > 0)
+  {
+    std::vector<int> devices;
+    for (int d = 0; d < group_n; ++d) devices.push_back(d);
+    if (!map.setDevices(devices)) return 3;
+  }
   Config conf;
   conf.max_range = hdr[1]; conf.prob_hit = hdr[2]; conf.prob_miss = hdr[3]; conf.prob_thres_min = hdr[4]; conf.prob_thres_max = hdr[5];
   conf.fast_mode = false; conf.accumulation_period = 0.0;
