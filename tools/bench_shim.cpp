@@ -55,7 +55,8 @@ int main(int argc, char** argv)
   if (group_n > 0)
   {
     std::vector<int> devices;
-    for (int d = 0; d < group_n; ++d) devices.push_back(d);
+    const bool same_device = std::getenv("VDBM_GROUP_ONE_DEVICE") != nullptr; // experiments: all shards on device 0
+    for (int d = 0; d < group_n; ++d) devices.push_back(same_device ? 0 : d);
     if (!map.setDevices(devices)) return 3;
   }
   Config conf;
@@ -96,7 +97,13 @@ int main(int argc, char** argv)
       for (auto& t : th) t.join();
       map.integrateUpdate();
     }
-    else map.insertPointCloud(clouds[k], origins[k], "lidar");
+    else
+    {
+      const auto t_scan = std::chrono::steady_clock::now();
+      map.insertPointCloud(clouds[k], origins[k], "lidar");
+      if (std::getenv("VDBM_BENCH_TRACE"))
+        std::fprintf(stderr, "scan %d: %.3f ms\n", k, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_scan).count());
+    }
     if (k >= warmup) rays += clouds[k]->points.size();
   }
   vdbm_stats_t st;
