@@ -839,7 +839,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU update-leaf exchange: fused peer-memory stores over NVLink (default) or NCCL all-to-all")
-    ap.add_argument("--cpu-scans", type=int, default=3)
+    ap.add_argument("--cpu-scans", type=int, default=4)  # ~11 s of single-thread CPU work for cfg2 (+ the multi-source and flat-hash legs)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong-block", action="store_true", help="skip the strong_cfg4 block (1M-point scans split over all ranks)")
     ap.add_argument("--no-shim-block", action="store_true", help="skip the shim block (the same scans through the C++ class API)")

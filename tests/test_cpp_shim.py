@@ -32,6 +32,9 @@ def test_shim_public_surface_matches_the_reference_names():
                  "applyMapSectionUpdateGrid", "createUpdate", "applyUpdate",
                  "using PointCloudT", "using GridT", "using UpdateGridT"]:
         assert name in hdr, name
+    # B200-only knobs next to the reference surface (none of them changes what the reference members compute)
+    for name in ["setMirrorMode", "setSourceConcurrency", "setDevices", "invalidateMirrorTable", "deviceStats"]:
+        assert name in hdr, name
     occ = open(os.path.join(ROOT, "include", "vdb_mapping", "OccupancyVDBMapping.hpp")).read()
     for name in ["struct Config : BaseConfig", "class OccupancyVDBMapping : public VDBMapping<float, Config>", "prob_thres_min"]:
         assert name in occ, name
