@@ -1251,12 +1251,13 @@ protected:
     while (!m_config_set && !m_thread_stop_signal) std::this_thread::sleep_for(std::chrono::milliseconds(10));
     while (!m_thread_stop_signal)
     {
-      if (m_accumulation_period <= 0 || m_accumulation_period > 3600000)
+      const int period_ms = m_accumulation_period; // one read: setConfig may change it while this thread runs
+      if (period_ms <= 0 || period_ms > 3600000)
       {
         std::this_thread::sleep_for(std::chrono::milliseconds(20));
         continue;
       }
-      auto wake_time = std::chrono::high_resolution_clock::now() + std::chrono::milliseconds(m_accumulation_period);
+      auto wake_time = std::chrono::high_resolution_clock::now() + std::chrono::milliseconds(period_ms);
       integrateUpdate();
       std::this_thread::sleep_until(wake_time);
     }
@@ -1268,7 +1269,7 @@ protected:
   double m_max_range = 0.0;
   double m_resolution;
   bool m_fast_mode          = false;
-  int m_accumulation_period = 0;
+  std::atomic<int> m_accumulation_period{0}; // written by setConfig, read by the integration thread (a plain int in the reference, R:1416 / 1466: a data race there)
   std::string m_map_directory_path;
   std::atomic<bool> m_config_set;
   MirrorMode m_mirror_mode = MirrorMode::Eager;

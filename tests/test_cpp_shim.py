@@ -106,3 +106,35 @@ def test_programs_run_through_the_openvdb_branch(exe):
     p = subprocess.run([path], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert "0 failed" in p.stdout, p.stdout[-2000:]
+
+
+MOCK_PROGRAMS = ["test_shim_kats_mock", "test_shim_kats_vdbapi_mock", "reference_mapping_tests_mock", "reference_mapping_tests_vdbapi_mock"]
+
+
+@pytest.mark.parametrize("exe", MOCK_PROGRAMS)
+def test_shim_host_logic_on_the_cpu_mock_of_the_abi(exe):
+    """CPU-only: the C++ scenarios (and the reference's unmodified test file) linked against tests/cpp/mock_abi - the C ABI
+    restated on the CPU oracle, test infrastructure - instead of libvdbm_b200.so, through both backends of the shim. What this
+    covers is the shim's HOST logic (locks and threads, per-source raycast handles, the sharded mode, mirror tables, sections,
+    persistence); the CUDA path is only ever judged by the -m gpu tier, which runs the same programs on the real library."""
+    path = os.path.join(ROOT, "tests", "cpp", "build", exe)
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build_mock_programs()
+    if not os.path.exists(path):
+        pytest.skip(exe + " was not built (no /root/reference at build time)")
+    p = subprocess.run([path], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert "0 failed" in p.stdout, p.stdout[-2000:]
+    syms = subprocess.run(["nm", "-D", "--undefined-only", path], capture_output=True, text=True, check=True).stdout
+    assert "cuda" not in syms.lower()          # nothing of the CUDA runtime in these executables
+
+
+def test_the_mock_abi_is_test_infrastructure_only():
+    """Neither the product package nor the public headers refer to the mock; the bench never touches it."""
+    for rel in ("vdb_mapping_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, rel)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    assert "mock_abi" not in open(os.path.join(dirpath, f), errors="ignore").read(), os.path.join(dirpath, f)
+    assert "mock" not in open(os.path.join(ROOT, "bench.py")).read()
