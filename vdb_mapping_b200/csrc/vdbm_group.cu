@@ -394,6 +394,14 @@ int vdbm_group_insert(vdbm_group* g, const char* source_id, const void* points, 
     if (g->shared_device) g->barrier();
     if (r0 == VDBM_ERR_UNKNOWN_SOURCE) return r0; // the same on every shard: nobody pushes
     const int r1 = vdbm_update_push(m, source_id);
+    if (g->shared_device)
+    {
+      // Shards on ONE device (the test tier): a peer that still allocates (cudaMalloc waits for the device to drain) could never
+      // publish its epoch while this shard's wait kernel spins on that same device, and the wait would run into its time-out.
+      // Let every push finish before anybody waits. With one device per shard the device-side wait is the point of the design.
+      vdbm_synchronize(m);
+      g->barrier();
+    }
     const int r2 = r1 ? r1 : vdbm_update_pull_integrate(m, source_id);
     if (r2) return r2;
     return (r0 == VDBM_ERR_COORD_RANGE || r0 == VDBM_ERR_NOT_CONFIGURED) ? r0 : (r0 ? r0 : VDBM_OK);
