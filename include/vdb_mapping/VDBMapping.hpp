@@ -148,11 +148,11 @@ public:
     m_thread_stop_signal = true;
     for (auto& [source_id, worker_thread] : m_worker_threads)
     {
-      m_input_sources[source_id]->data_available_cv.notify_all();
+      if (auto src = findSource(source_id)) src->data_available_cv.notify_all();
       if (worker_thread.joinable()) worker_thread.join();
     }
     if (m_integration_thread.joinable()) m_integration_thread.join();
-    for (auto& kv : m_input_sources)
+    for (auto& kv : sourcesSnapshot())
       if (kv.second->raycaster) vdbm_destroy(kv.second->raycaster);
     if (m_device_map) vdbm_destroy(m_device_map);
     if (m_device_group) vdbm_group_destroy(m_device_group);
@@ -174,7 +174,7 @@ public:
     {
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
       vdbm_reset(m_device_map);
-      for (auto& kv : m_input_sources) // "new empty update grids" R:181-185, wherever they live
+      for (auto& kv : sourcesSnapshot()) // "new empty update grids" R:181-185, wherever they live
       {
         kv.second->shared_holds_data = false;
         if (kv.second->raycaster)
@@ -207,7 +207,7 @@ public:
   {
     std::unique_lock map_lock(*m_map_mutex);
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
-    if (m_config_set || !m_input_sources.empty() || m_device_group)
+    if (m_config_set || sourceCount() != 0 || m_device_group)
     {
       std::cerr << "vdb_mapping (B200): setDevices must be called once, before setConfig and addInputSource" << std::endl;
       return false;
@@ -238,8 +238,8 @@ public:
                         const Eigen::Matrix<double, 3, 1>& origin,
                         const std::string source_id)
   {
-    auto source = m_input_sources.find(source_id);
-    if (source == m_input_sources.end())
+    const std::shared_ptr<InputSource> source = findSource(source_id);
+    if (!source)
     {
       std::cout << "Tried to accumulate update for " << source_id << ". Source not available" << std::endl;
       return;
@@ -251,15 +251,15 @@ public:
       return;
     }
     std::shared_lock map_lock(*m_map_mutex);
-    std::unique_lock update_grid_lock(source->second->update_grid_mutex);
+    std::unique_lock update_grid_lock(source->update_grid_mutex);
     if (!m_device_map || !cloud) return;
     const double o[3] = {origin.x(), origin.y(), origin.z()};
-    if (vdbm_map* raycaster = sourceRaycaster(source_id, *source->second))
+    if (vdbm_map* raycaster = sourceRaycaster(source_id, *source))
     {
       // this source's own handle: no other thread touches it (update_grid_mutex), nothing is shared with the map's handle
       const int rc = vdbm_accumulate(raycaster, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o);
-      source->second->raycaster_holds_data   = true;
-      source->second->last_cast_on_raycaster = true;
+      source->raycaster_holds_data   = true;
+      source->last_cast_on_raycaster = true;
       reportOn(raycaster, rc);
       return;
     }
@@ -268,8 +268,8 @@ public:
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     // the ABI wants the pcl::PointXYZ records as they lie in the cloud (16-byte stride)
     const int rc = vdbm_accumulate(m_device_map, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o);
-    source->second->shared_holds_data      = true;
-    source->second->last_cast_on_raycaster = false;
+    source->shared_holds_data      = true;
+    source->last_cast_on_raycaster = false;
     report(rc);
   }
 
@@ -278,15 +278,15 @@ public:
                            const Eigen::Matrix<double, 3, 1>& origin,
                            const std::string source_id)
   {
-    auto source = m_input_sources.find(source_id);
-    if (source == m_input_sources.end())
+    const std::shared_ptr<InputSource> source = findSource(source_id);
+    if (!source)
     {
       std::cout << "Tried to add data for accumulation of " << source_id << ". Source not available" << std::endl;
       return;
     }
-    std::unique_lock lock(source->second->input_data_mutex);
-    source->second->input_data = std::make_pair(cloud, origin);
-    source->second->data_available_cv.notify_all();
+    std::unique_lock lock(source->input_data_mutex);
+    source->input_data = std::make_pair(cloud, origin);
+    source->data_available_cv.notify_all();
   }
 
   /*! R:375-387: exclusive map lock (writer priority flag), updateMap for every source in key order. */
@@ -298,13 +298,14 @@ public:
     if (!m_device_map) return;
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     bool on_raycasters = false; // exclusive map lock: no accumulation is running, the sources' flags are stable
-    for (auto& kv : m_input_sources) on_raycasters = on_raycasters || kv.second->raycaster_holds_data;
+    const auto sources = sourcesSnapshot(); // key order, R:380
+    for (auto& kv : sources) on_raycasters = on_raycasters || kv.second->raycaster_holds_data;
     if (!on_raycasters) report(vdbm_integrate(m_device_map, 0));
     else
     {
       // updateMap per source in key order (R:380), each grid read where it lies; a source with leaves on BOTH handles (the
       // mode changed between two accumulates) is one update grid in the reference: gathered on the map's handle first
-      for (auto& kv : m_input_sources)
+      for (auto& kv : sources)
       {
         InputSource& src = *kv.second;
         if (src.raycaster_holds_data && src.shared_holds_data) collectRaycasterLocked(kv.first, src);
@@ -316,7 +317,7 @@ public:
         else if (src.shared_holds_data) report(vdbm_integrate_from(m_device_map, m_device_map, kv.first.c_str(), 0));
       }
     }
-    for (auto& kv : m_input_sources) kv.second->shared_holds_data = false;
+    for (auto& kv : sources) kv.second->shared_holds_data = false;
     if (m_mirror_mode == MirrorMode::Eager) syncMirrorLocked();
     else m_mirror_stale = true;
   }
@@ -328,7 +329,7 @@ public:
   {
     if (m_device_group)
     {
-      if (m_input_sources.find(source_id) == m_input_sources.end())
+      if (!findSource(source_id))
       {
         std::cout << "Tried to accumulate update for " << source_id << ". Source not available" << std::endl;
         return true;
@@ -340,17 +341,17 @@ public:
     {
       // throughput mode: the scan is queued as one pipeline stage (vdbm_insert_async: upload overlapped with the previous
       // scan, no host round trip between raycast and updateMap); getGrid() / any other member finishes it
-      auto source = m_input_sources.find(source_id);
-      if (source != m_input_sources.end() && !source->second->raycaster_holds_data && !wantsRaycaster())
+      const std::shared_ptr<InputSource> source = findSource(source_id);
+      if (source && !source->raycaster_holds_data && !wantsRaycaster())
       {
         m_map_mutex_requested = true;
         std::unique_lock map_lock(*m_map_mutex);
         m_map_mutex_requested = false;
-        std::unique_lock update_grid_lock(source->second->update_grid_mutex);
+        std::unique_lock update_grid_lock(source->update_grid_mutex);
         std::lock_guard<std::mutex> device_lock(m_device_mutex);
         const double o[3] = {origin.x(), origin.y(), origin.z()};
         report(vdbm_insert_async(m_device_map, source_id.c_str(), cloud->points.data(), cloud->points.size(), sizeof(PointT), o, 0));
-        source->second->last_cast_on_raycaster = false;
+        source->last_cast_on_raycaster = false;
         m_mirror_stale = true;
         return true;
       }
@@ -590,19 +591,19 @@ public:
     typename UpdateGridT::Ptr out = BackendT::createUpdateGrid(m_resolution);
     if (shardedUnavailable("createUpdate")) return out;
     if (!m_device_map) return out;
-    auto source = m_input_sources.find(source_id);
+    const std::shared_ptr<InputSource> source = findSource(source_id);
     std::unique_lock<std::mutex> update_grid_lock;
-    if (source != m_input_sources.end()) update_grid_lock = std::unique_lock<std::mutex>(source->second->update_grid_mutex);
+    if (source) update_grid_lock = std::unique_lock<std::mutex>(source->update_grid_mutex);
     std::lock_guard<std::mutex> device_lock(m_device_mutex);
     vdbm_leafset* ls = nullptr;
     double o[3]      = {0, 0, 0};
     vdbm_map* from   = m_device_map;
-    if (source != m_input_sources.end() && source->second->raycaster)
+    if (source && source->raycaster)
     {
       // the ray end voxels of the last accumulate (level 2) stay with the handle that cast them; a raw grid (level 0) may be
       // spread over both handles and is gathered in the map's first
-      if (level == 2 && source->second->last_cast_on_raycaster) from = source->second->raycaster;
-      else if (level == 0) collectRaycasterLocked(source_id, *source->second);
+      if (level == 2 && source->last_cast_on_raycaster) from = source->raycaster;
+      else if (level == 0) collectRaycasterLocked(source_id, *source);
     }
     if (reportOn(from, vdbm_update_create(from, source_id.c_str(), level, &ls, o)) != VDBM_OK) return out;
     if (origin) *origin = Eigen::Matrix<double, 3, 1>(o[0], o[1], o[2]);
@@ -869,32 +870,37 @@ public:
       std::lock_guard<std::mutex> device_lock(m_device_mutex);
       report(vdbm_source_add(m_device_map, source_id.c_str(), max_range)); // a re-added source starts with an empty update grid
     }
-    auto existing = m_input_sources.find(source_id);
-    if (existing != m_input_sources.end())
+    const std::shared_ptr<InputSource> existing = findSource(source_id);
+    if (existing)
     {
       // Re-adding a source (the reference overwrites the map entry, R:1374): its worker thread is blocked on THIS object's
       // condition variable, so the object stays and only its parameters change; pending input is dropped like the
       // reference's fresh InputSource would.
       {
-        std::unique_lock lock(existing->second->input_data_mutex);
-        existing->second->max_range        = range;
-        existing->second->max_input_period = period;
-        existing->second->input_data.reset();
+        std::unique_lock lock(existing->input_data_mutex);
+        existing->max_range        = range;
+        existing->max_input_period = period;
+        existing->input_data.reset();
       }
-      std::unique_lock grid_lock(existing->second->update_grid_mutex);
-      if (existing->second->raycaster)
+      std::unique_lock grid_lock(existing->update_grid_mutex);
+      if (existing->raycaster)
       {
-        vdbm_source_add(existing->second->raycaster, source_id.c_str(), range); // empty grid, new (resolved, R:1356-1363) range
-        existing->second->raycaster_holds_data = false;
+        vdbm_source_add(existing->raycaster, source_id.c_str(), range); // empty grid, new (resolved, R:1356-1363) range
+        existing->raycaster_holds_data = false;
       }
-      existing->second->shared_holds_data = false;
+      existing->shared_holds_data = false;
       return;
     }
     auto s              = std::make_shared<InputSource>();
     s->source_id        = source_id;
     s->max_range        = range;
     s->max_input_period = period;
-    m_input_sources[source_id] = s;
+    {
+      // published under the sources lock: the integration and accumulation threads look sources up while a node is still
+      // registering its sensors (the reference mutates the std::map unguarded, R:1374 against R:380 / R:1388)
+      std::unique_lock<std::shared_mutex> sources_lock(m_sources_mutex);
+      m_input_sources[source_id] = s;
+    }
     m_worker_threads[source_id] = std::thread(&VDBMapping::accumulationThread, this, source_id);
   }
 
@@ -927,10 +933,13 @@ public:
   /*! Counters of the device path (rays, visits, voxel updates, kernel times); not part of the reference API. */
   bool deviceStats(vdbm_stats_t& out) const
   {
-    if (m_device_group) return vdbm_group_stats(m_device_group, &out) == VDBM_OK; // summed over the shards
-    if (!m_device_map || vdbm_stats(m_device_map, &out) != VDBM_OK) return false;
+    {
+      std::lock_guard<std::mutex> device_lock(m_device_mutex); // not while another thread is inside a call on the handle
+      if (m_device_group) return vdbm_group_stats(m_device_group, &out) == VDBM_OK; // summed over the shards
+      if (!m_device_map || vdbm_stats(m_device_map, &out) != VDBM_OK) return false;
+    }
     // rays cast on the sources' own handles (SourceConcurrency) belong to this map's raycast counters
-    for (auto& kv : m_input_sources)
+    for (auto& kv : sourcesSnapshot())
     {
       std::unique_lock<std::mutex> grid_lock(kv.second->update_grid_mutex);
       vdbm_stats_t s;
@@ -966,6 +975,25 @@ protected:
   {
     if (rc != VDBM_OK && rc != VDBM_ERR_UNKNOWN_SOURCE && handle) std::cerr << "vdb_mapping (B200): " << vdbm_last_error(handle) << std::endl;
     return rc;
+  }
+
+  /*! the registered sources are looked up by the accumulation threads, the integration thread and every caller while
+   *  addInputSource may still be adding one: lookups copy the shared_ptr under a reader lock */
+  std::shared_ptr<InputSource> findSource(const std::string& source_id) const
+  {
+    std::shared_lock<std::shared_mutex> sources_lock(m_sources_mutex);
+    auto it = m_input_sources.find(source_id);
+    return it == m_input_sources.end() ? std::shared_ptr<InputSource>() : it->second;
+  }
+  std::vector<std::pair<std::string, std::shared_ptr<InputSource> > > sourcesSnapshot() const
+  {
+    std::shared_lock<std::shared_mutex> sources_lock(m_sources_mutex);
+    return std::vector<std::pair<std::string, std::shared_ptr<InputSource> > >(m_input_sources.begin(), m_input_sources.end());
+  }
+  std::size_t sourceCount() const
+  {
+    std::shared_lock<std::shared_mutex> sources_lock(m_sources_mutex);
+    return m_input_sources.size();
   }
 
   int reportGroup(int rc) const
@@ -1009,7 +1037,7 @@ protected:
   bool wantsRaycaster() const
   {
     if (!m_device_map || !m_config_set || m_fast_mode || m_source_concurrency == SourceConcurrency::Shared) return false;
-    return m_source_concurrency == SourceConcurrency::PerSource || m_input_sources.size() > 1;
+    return m_source_concurrency == SourceConcurrency::PerSource || sourceCount() > 1;
   }
 
   /*! the source's raycast-only handle, created and (re)configured on demand; nullptr = use the map's handle.
@@ -1223,7 +1251,12 @@ protected:
     while (!m_config_set && !m_thread_stop_signal) std::this_thread::sleep_for(std::chrono::milliseconds(10));
     while (!m_thread_stop_signal)
     {
-      std::shared_ptr<InputSource> src = m_input_sources[source_id];
+      std::shared_ptr<InputSource> src = findSource(source_id);
+      if (!src) // started before its source was published: try again
+      {
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        continue;
+      }
       auto wake_time = std::chrono::high_resolution_clock::now() + src->max_input_period;
       std::unique_lock lock(src->input_data_mutex);
       src->data_available_cv.wait(lock, [&] { return src->input_data || m_thread_stop_signal; });
@@ -1274,7 +1307,7 @@ protected:
   std::atomic<bool> m_config_set;
   MirrorMode m_mirror_mode = MirrorMode::Eager;
   SourceConcurrency m_source_concurrency = SourceConcurrency::Auto;
-  mutable bool m_mirror_stale = false;
+  mutable std::atomic<bool> m_mirror_stale{false}; // set under the device mutex, peeked at by getGrid() without it
   std::vector<std::vector<typename BackendT::MapLeafT*> > m_shard_tables; // per map handle: device pool index -> leaf of m_vdb_grid
   std::vector<std::uint64_t> m_shard_generations;
   std::size_t m_mirror_sink_shard     = 0;
@@ -1288,6 +1321,7 @@ protected:
   mutable std::shared_ptr<std::shared_mutex> m_map_mutex;
   mutable std::atomic<bool> m_map_mutex_requested{false};
   std::map<std::string, std::shared_ptr<InputSource> > m_input_sources;
+  mutable std::shared_mutex m_sources_mutex; // guards the STRUCTURE of m_input_sources (see findSource)
   std::atomic<bool> m_thread_stop_signal{false};
   std::map<std::string, std::thread> m_worker_threads;
   std::thread m_integration_thread;

@@ -5,6 +5,7 @@
 // caller grid, raycastPointCloud into an accessor, sections, lazy mirror).
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <map>
 #include <thread>
@@ -641,5 +642,84 @@ TEST(Shim, MapShardedOverSeveralDevicesEqualsTheSingleDeviceMap)
   single.insertPointCloud(extra, Eigen::Matrix<double, 3, 1>(0.1, 0, 0), "lidar");
   EXPECT_TRUE(gridsIdentical(sharded, single));
 }
+
+#ifdef VDBM_TEST_ON_MOCK
+// Scenarios that only run in the CPU tier (programs linked against tests/cpp/mock_abi): host logic of the shim whose timing
+// has not been exercised on the real library in this round, kept out of the GPU tier on purpose.
+
+TEST(ShimHostLogic, ThreadedAccumulationAndPeriodicIntegrationLikeTheReferenceNodes)
+{
+  // addDataToAccumulate R:355-370 -> the source's accumulation thread R:1383-1411 -> the integration thread R:1416-1430
+  // (accumulation_period > 0): what the ROS wrappers use. One cloud per source at a time, each waited for, so that the
+  // result is comparable with direct inserts.
+  Config conf              = gtestConfig(8);
+  conf.accumulation_period = 0.03; // seconds
+  OccupancyVDBMapping threaded(0.1), direct(0.1);
+  const char* ids[2] = {"front", "rear"};
+  for (OccupancyVDBMapping* m : {&threaded, &direct})
+  {
+    m->setMirrorMode(vdb_mapping::MirrorMode::Lazy);
+    m->setConfig(conf);
+    for (const char* id : ids) m->addInputSource(id, 0.0, 0);
+  }
+  std::uint64_t expected_updates = 0;
+  for (int round = 0; round < 3; ++round)
+    for (int s = 0; s < 2; ++s)
+    {
+      const auto cloud = sectorCloud(s, 3000, 11u * unsigned(round) + unsigned(s));
+      const Eigen::Matrix<double, 3, 1> origin(0.02 * round, 0.01 * s, 0.0);
+      direct.insertPointCloud(cloud, origin, ids[s]);
+      vdbm_stats_t want;
+      direct.deviceStats(want);
+      expected_updates = want.voxel_updates;
+      threaded.addDataToAccumulate(cloud, origin, ids[s]);
+      bool done = false;
+      for (int spin = 0; spin < 400 && !done; ++spin) // <= 8 s
+      {
+        std::this_thread::sleep_for(std::chrono::milliseconds(20));
+        vdbm_stats_t got;
+        done = threaded.deviceStats(got) && got.voxel_updates == expected_updates;
+      }
+      EXPECT_TRUE(done);
+    }
+  EXPECT_TRUE(gridsIdentical(threaded, direct));
+}
+
+TEST(ShimHostLogic, SourceConcurrencyCanChangeBetweenAccumulates)
+{
+  // a source with update leaves on BOTH handles (accumulated on the map's handle, then on its own) is ONE update grid in
+  // the reference: integrateUpdate gathers it on the map's handle first, so a voxel seen by both clouds is updated once
+  const Config conf = gtestConfig(8);
+  OccupancyVDBMapping switching(0.1), plain(0.1);
+  plain.setSourceConcurrency(vdb_mapping::SourceConcurrency::Shared);
+  switching.setSourceConcurrency(vdb_mapping::SourceConcurrency::Shared);
+  for (OccupancyVDBMapping* m : {&switching, &plain})
+  {
+    m->setMirrorMode(vdb_mapping::MirrorMode::Lazy);
+    m->setConfig(conf);
+    m->addInputSource("a", 0.0, 0);
+    m->addInputSource("b", 0.0, 0);
+  }
+  const Eigen::Matrix<double, 3, 1> origin(0, 0, 0);
+  for (int round = 0; round < 3; ++round)
+  {
+    const auto c1 = sectorCloud(0, 3000, 5u + unsigned(round)), c2 = sectorCloud(0, 3000, 50u + unsigned(round)), c3 = sectorCloud(1, 3000, 500u + unsigned(round));
+    for (OccupancyVDBMapping* m : {&switching, &plain})
+    {
+      m->accumulateUpdate(c1, origin, "a");                                                       // on the map's handle
+      if (m == &switching) m->setSourceConcurrency(vdb_mapping::SourceConcurrency::PerSource);
+      m->accumulateUpdate(c2, origin, "a");                                                       // same source, own handle
+      m->accumulateUpdate(c3, origin, "b");
+      m->integrateUpdate();
+      if (m == &switching) m->setSourceConcurrency(vdb_mapping::SourceConcurrency::Shared);
+    }
+    EXPECT_TRUE(gridsIdentical(switching, plain));
+  }
+  vdbm_stats_t a, b;
+  EXPECT_TRUE(switching.deviceStats(a) && plain.deviceStats(b));
+  EXPECT_EQ(a.voxel_updates, b.voxel_updates);
+  EXPECT_EQ(a.rays, b.rays);
+}
+#endif // VDBM_TEST_ON_MOCK
 
 int main() { return RUN_ALL_TESTS(); }
