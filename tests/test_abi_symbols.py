@@ -39,6 +39,16 @@ def test_library_exports_every_declared_symbol(so_path):
     assert lib.vdbm_abi_version() == 1
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/vdbm_b200.h compiles as C99 (-pedantic, warnings as errors) and a C program links it."""
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "vdbm_b200.h"\n'
+                   'static int sink(void* u, uint64_t n, const uint32_t* i, const int32_t* o, const float* v, const uint64_t* a)\n'
+                   '{ (void)u; (void)n; (void)i; (void)o; (void)v; (void)a; return 0; }\n'
+                   'int main(void) { vdbm_mirror_sink s = sink; vdbm_params p; p.resolution = 0.1; return (s != 0 && p.resolution > 0 && vdbm_abi_version() == VDBM_ABI_VERSION) ? 0 : 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], check=True)
+
+
 def test_only_the_abi_is_exported(so_path):
     out = subprocess.run(["nm", "-D", "--defined-only", so_path], capture_output=True, text=True, check=True).stdout
     syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
